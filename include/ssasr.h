@@ -1,0 +1,94 @@
+/* ssasr.h -- C ABI of libssasr.so: the B200 (sm_100a) kernels behind the Listen-Attend-Spell hot path of
+ * cadia-lvl/ss_asr.  The reference has no native/FFI layer (it is pure Python on torch); each
+ * entry point below names the reference Python interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless marked HOST; buffers are
+ * caller-owned (no hidden allocation except the cached fbank tables); `stream` is a cudaStream_t passed as
+ * void*; every function returns 0 on success, <0 on error (ssasr_last_error() gives a thread-local message);
+ * nothing throws across the boundary.  Distinct streams may run concurrently; one stream is serial.
+ *
+ * Gate layout used by all LSTM buffers ("interleaved"): column = dir*4S + unit*4 + gate, gate order i,f,g,o.
+ */
+#ifndef SSASR_H_
+#define SSASR_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ssasr_last_error(void);
+
+/* ---- log-mel filterbank: preprocess.py:187-208 log_fbank(y, sample_rate) (librosa 0.6.3 melspectrogram) ---- */
+long long ssasr_fbank_num_frames(long long n_samples, int sample_rate);
+int ssasr_fbank(const float* audio, const long long* offsets /*[n_utt+1]*/, int n_utt, int sample_rate, int n_mels,
+                float* out /*[sum frames, n_mels]*/, const long long* out_offsets /*[n_utt+1] rows*/, int max_frames,
+                void* stream);
+
+/* ---- fp32 GEMM (the nn.Linear / LSTM gate products of asr.py on the exact path) ---- */
+int ssasr_gemm_f32(int M, int N, int K, const float* A, int lda, int a_kmajor, const float* B, int ldb, int b_kmajor,
+                   float* C, int ldc, const float* bias, int accumulate, int act_tanh, void* stream);
+
+/* ---- parameter packing: nn.LSTM / nn.LSTMCell tensors of asr.py:234-238,277-283,403-404 -> kernel layout ---- */
+int ssasr_pack_blstm(const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+                     const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r, int S, int K,
+                     float* wih_p /*[8S,K]*/, float* bias_p /*[8S]*/, float* whh_p /*[2,4S,S]*/,
+                     float* whhT_p /*[2,S,4S] or NULL*/, void* stream);
+int ssasr_unpack_blstm_grads(const float* dwih_p, const float* dbias_p, const float* dwhh_p, int S, int K,
+                             float* g_w_ih_f, float* g_w_hh_f, float* g_b_ih_f, float* g_b_hh_f, float* g_w_ih_r,
+                             float* g_w_hh_r, float* g_b_ih_r, float* g_b_hh_r, void* stream);
+int ssasr_pack_lstmcell(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int S, int Kin,
+                        float* wcat /*[4S,Kin+S]*/, float* bcat /*[4S]*/, void* stream);
+int ssasr_unpack_lstmcell_grads(const float* dwcat, const float* dbcat, int S, int Kin, float* g_w_ih, float* g_w_hh,
+                                float* g_b_ih, float* g_b_hh, void* stream);
+
+/* ---- one bidirectional LSTM layer: pBLSTM.forward asr.py:406-427 (packed-sequence semantics through `lens`)
+ *      and encoder.blstm_4 asr.py:237-238,262 (seq-first quirk: n_seq = batch size, n_batch = frames, lens NULL).
+ *      Row index of x/xp/hout/cbuf = seq*rs_seq + batch*rs_batch.  The pair-concat down-sampling
+ *      (asr.py:429-450) is a view of hout and costs nothing. ---- */
+int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* bias_p, const float* whh_p,
+                        int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, const int* lens,
+                        float* xp /*[n_rows,8S] out: gate activations*/, float* hout /*[n_rows,2S], pre-zeroed*/,
+                        float* cbuf /*[n_rows,2S]*/, unsigned* bar /*2 words scratch*/, void* stream);
+int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* whhT_p, int S, int n_seq,
+                        int n_batch, long long rs_seq, long long rs_batch, const int* lens,
+                        float* act /*in: activations, out: gate grads*/, const float* hout, const float* cbuf,
+                        const float* dhout, float* dx /*[n_rows,K] or NULL*/, float* dwih_p, float* dbias_p,
+                        float* dwhh_p, float* dcstate /*[n_batch,2S] scratch*/, unsigned* bar, int zero_period,
+                        void* stream);
+
+/* ---- attend-and-spell loop: Attention.forward asr.py:343-392 + Speller.forward asr.py:314-326 + the decode loop
+ *      of ASR.forward asr.py:65-110 (teacher forcing / greedy / sampled), all U steps on the device ---- */
+typedef struct {
+  int B, Tp, E, Sd, M, C, U;
+  const float *phi_w, *psi_w, *psi_b, *w1cat, *b1, *w2cat, *b2, *emb_w, *wc, *bc;
+  const float* enc;         /* [B,Tp,E] listener output */
+  const int* enc_lens;      /* [B] */
+  int* tok_in;              /* [B,U] input token per step (col 0 = <sos>=0; teacher columns pre-filled) */
+  const int* step_mode;     /* HOST [U] or NULL: token after step t: 0 teacher, 1 argmax, 2 sample */
+  unsigned long long seed;
+  float *psi, *xin1, *xin2, *act1, *act2, *c1, *c2, *h2all, *q, *alpha, *logits; /* outputs + saved state */
+} ssasr_speller_fwd_args;
+int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
+
+typedef struct {
+  int B, Tp, E, Sd, M, C, U;
+  const float *phi_w, *psi_w, *w1cat, *w2cat, *wc;
+  const float* enc;
+  const int* enc_lens;
+  const int* tok_in;
+  const float *psi, *xin1, *xin2, *c1, *c2, *h2all, *q, *alpha;
+  float *act1, *act2;
+  const float* dlogits;     /* [B,U,C] */
+  float *d_phi_w, *d_psi_w, *d_psi_b, *d_w1cat, *d_b1, *d_w2cat, *d_b2, *d_emb_w, *d_wc, *d_bc, *denc;
+  float *dh2all, *dxin1, *dxin2, *dc1s, *dc2s, *dh1att, *dpsi, *dqpre;   /* scratch */
+} ssasr_speller_bwd_args;
+int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream);
+
+/* ---- ASR loss: trainer.py:394-395,426-434 (CrossEntropyLoss(ignore_index=0,'none'), per-utterance length
+ *      normalisation, batch mean), fused with its gradient ---- */
+int ssasr_ce_loss_f32(const float* logits, const long long* y, int B, int U, int C, int L, float* loss_b /*[B]*/,
+                      float* loss_out /*[1]*/, float* dlogits /*[B,U,C] or NULL*/, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSASR_H_ */

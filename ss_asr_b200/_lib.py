@@ -1,0 +1,98 @@
+"""ctypes binding of libssasr.so (include/ssasr.h).  There is NO fallback: if the CUDA library is missing
+or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+_LIB = None
+
+
+class SpellerFwdArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ('B', 'Tp', 'E', 'Sd', 'M', 'C', 'U')] +
+                [(n, C.c_void_p) for n in ('phi_w', 'psi_w', 'psi_b', 'w1cat', 'b1', 'w2cat', 'b2', 'emb_w', 'wc', 'bc',
+                                           'enc', 'enc_lens', 'tok_in', 'step_mode')] +
+                [('seed', C.c_ulonglong)] +
+                [(n, C.c_void_p) for n in ('psi', 'xin1', 'xin2', 'act1', 'act2', 'c1', 'c2', 'h2all', 'q', 'alpha',
+                                           'logits')])
+
+
+class SpellerBwdArgs(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ('B', 'Tp', 'E', 'Sd', 'M', 'C', 'U')] +
+                [(n, C.c_void_p) for n in ('phi_w', 'psi_w', 'w1cat', 'w2cat', 'wc', 'enc', 'enc_lens', 'tok_in',
+                                           'psi', 'xin1', 'xin2', 'c1', 'c2', 'h2all', 'q', 'alpha', 'act1', 'act2',
+                                           'dlogits',
+                                           'd_phi_w', 'd_psi_w', 'd_psi_b', 'd_w1cat', 'd_b1', 'd_w2cat', 'd_b2',
+                                           'd_emb_w', 'd_wc', 'd_bc', 'denc',
+                                           'dh2all', 'dxin1', 'dxin2', 'dc1s', 'dc2s', 'dh1att', 'dpsi', 'dqpre')])
+
+
+_P, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+SIGNATURES = {
+    'ssasr_last_error': (C.c_char_p, []),
+    'ssasr_fbank_num_frames': (_LL, [_LL, _I]),
+    'ssasr_fbank': (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _P]),
+    'ssasr_gemm_f32': (_I, [_I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P]),
+    'ssasr_pack_blstm': (_I, [_P] * 8 + [_I, _I] + [_P] * 5),
+    'ssasr_unpack_blstm_grads': (_I, [_P] * 3 + [_I, _I] + [_P] * 9),
+    'ssasr_pack_lstmcell': (_I, [_P] * 4 + [_I, _I] + [_P] * 3),
+    'ssasr_unpack_lstmcell_grads': (_I, [_P, _P, _I, _I] + [_P] * 5),
+    'ssasr_blstm_fwd_f32': (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P]),
+    'ssasr_blstm_bwd_f32': (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                 _I, _P]),
+    'ssasr_speller_fwd_f32': (_I, [C.POINTER(SpellerFwdArgs), _P]),
+    'ssasr_speller_bwd_f32': (_I, [C.POINTER(SpellerBwdArgs), _P]),
+    'ssasr_ce_loss_f32': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P]),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_needed=True):
+    """Loads (building first if the sources are newer) libssasr.so and types every entry point."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if build_if_needed and os.environ.get('SSASR_NO_BUILD') != '1':
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.isfile(_build.LIB):
+                raise
+    if not os.path.isfile(_build.LIB):
+        raise RuntimeError('libssasr.so is missing (%s): build it with `python -m ss_asr_b200.build`; there is no '
+                           'CPU/PyTorch fallback for the hot path' % _build.LIB)
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().ssasr_last_error()
+        raise RuntimeError('%s failed (rc=%d): %s' % (what, rc, msg.decode() if msg else '?'))
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'kernel arguments must be contiguous CUDA tensors'
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError('%s: the ss_asr_b200 hot path runs on a CUDA device only (got a %s tensor); there is '
+                           'no CPU fallback' % (what, t.device))

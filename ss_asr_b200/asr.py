@@ -1,0 +1,258 @@
+"""Drop-in Listen-Attend-Spell modules for the ss_asr trainers, backed by libssasr.so (sm_100a CUDA).
+
+Mirrors the public surface of /root/reference/src/asr.py -- same class names, constructor signatures,
+attribute names, `state_dict` keys/shapes and return tuples -- so `trainer.py`'s
+ASRTrainer / ASRTester call sites (trainer.py:397-398, 422, 478, 591) work unchanged after
+`from ss_asr_b200.asr import ASR`.  The torch.nn containers below (nn.LSTM, nn.LSTMCell, nn.Linear,
+nn.Embedding) are used ONLY as parameter holders, which gives identical initialisation order, strict
+`load_state_dict` compatibility and `.to(device)` behaviour; their own forward() is never called.
+"""
+import math
+import random
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fk
+
+EOS_TKN = '>'          # preprocess.py:25
+
+
+def _lens_list(state_len):
+    if torch.is_tensor(state_len):
+        state_len = state_len.tolist()
+    return [int(s) for s in state_len]
+
+
+def _blstm_params(lstm):
+    return (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
+            lstm.weight_ih_l0_reverse, lstm.weight_hh_l0_reverse, lstm.bias_ih_l0_reverse, lstm.bias_hh_l0_reverse)
+
+
+def _fit_time(x, t_h):
+    """Slices / zero-pads the time axis of x [B,T,K] to exactly t_h frames."""
+    T = x.shape[1]
+    if T == t_h:
+        return x
+    if T > t_h:
+        return x[:, :t_h]
+    return torch.nn.functional.pad(x, (0, 0, 0, t_h - T))
+
+
+class pBLSTM(nn.Module):
+    """asr.py:394-450: BLSTM over a (packed) batch followed by frame-pair concatenation."""
+
+    def __init__(self, in_dim, out_dim):
+        super(pBLSTM, self).__init__()
+        self.layer = nn.LSTM(in_dim, out_dim, bidirectional=True, batch_first=True)   # parameter holder
+
+    def forward(self, input_x, state=None, state_len=None, pack_input=False):
+        if state is not None:
+            raise NotImplementedError('pBLSTM: a non-zero initial state is never passed on the ASR path '
+                                      '(asr.py:256-261) and is not supported by the CUDA kernels')
+        B, T, _ = input_x.shape
+        if pack_input:
+            assert state_len is not None, "Please specify seq len for pack_padded_sequence."
+            lens = _lens_list(state_len)
+            if any(lens[i] < lens[i + 1] for i in range(len(lens) - 1)) or lens[-1] <= 0:
+                raise RuntimeError('pBLSTM: `state_len` must be sorted in decreasing order and positive '
+                                   '(pack_padded_sequence contract, asr.py:413)')
+            run_lens = lens
+            t_max = lens[0]
+        else:
+            run_lens = [T] * B
+            t_max = T
+        if t_max > T:
+            raise RuntimeError('pBLSTM: length %d exceeds the padded time dimension %d' % (t_max, T))
+        t_h = t_max + (t_max & 1)
+        x = _fit_time(input_x, t_h)
+        lens_dev = torch.tensor(run_lens, dtype=torch.int32, device=input_x.device)
+        hout = Fk.blstm(x, lens_dev, True, _blstm_params(self.layer))               # [B, t_h, 2S]
+        out = hout.view(B, t_h // 2, 2 * hout.shape[2])[:, :t_max // 2]              # downsample = a view
+        hidden = None   # (h_n, c_n) is discarded by every caller on the ASR path (asr.py:256-262)
+        if state_len is not None:
+            if pack_input:
+                new_len = [int(s / 2) for s in run_lens]
+            else:
+                new_len = [int(s / 2) for s in _lens_list(state_len)]
+            return out, hidden, new_len
+        return out, hidden
+
+    def downsample(self, x):
+        t_dim, f_dim = x.shape[1], x.shape[2]
+        t2 = t_dim // 2
+        return x[:, :2 * t2, :].contiguous().view(-1, t2, f_dim * 2)
+
+
+class Listener(nn.Module):
+    """asr.py:214-264."""
+
+    def __init__(self, state_size, feature_dim):
+        super(Listener, self).__init__()
+        self.state_size = state_size
+        self.out_dim = 2 * self.state_size
+        self.blstm_1 = pBLSTM(feature_dim, self.state_size)
+        self.blstm_2 = pBLSTM(self.state_size * 2 * 2, self.state_size)
+        self.blstm_3 = pBLSTM(self.state_size * 2 * 2, self.state_size)
+        self.blstm_4 = nn.LSTM(self.state_size * 2 * 2, self.state_size, bidirectional=True)   # parameter holder
+        self.utterance_independent = False   # True: run blstm_4 as bs=1 would (ASR.decode batching)
+
+    def get_outdim(self):
+        return self.out_dim
+
+    def forward(self, x, state_len, pack_input=True):
+        x, _, state_len = self.blstm_1(x, state_len=state_len, pack_input=pack_input)
+        x, _, state_len = self.blstm_2(x, state_len=state_len, pack_input=pack_input)
+        x, _, state_len = self.blstm_3(x, state_len=state_len, pack_input=pack_input)
+        x = x.contiguous()
+        if self.utterance_independent:
+            # bs=1 semantics for every utterance at once: one cell step from zero state per frame
+            B, Tp, K = x.shape
+            x = Fk.blstm(x.view(1, B * Tp, K), None, False, _blstm_params(self.blstm_4)).view(B, Tp, -1)
+        else:
+            # seq-first quirk (asr.py:237-238,262): dim 0 (utterances) is the time axis of blstm_4
+            x = Fk.blstm(x, None, False, _blstm_params(self.blstm_4))
+        return x, state_len
+
+
+class Speller(nn.Module):
+    """asr.py:267-326 (parameter holder + per-utterance state attributes)."""
+
+    def __init__(self, state_size, encoder_out_size):
+        super(Speller, self).__init__()
+        self.layer_1 = nn.LSTMCell(input_size=encoder_out_size + state_size, hidden_size=state_size)
+        self.layer_2 = nn.LSTMCell(input_size=state_size, hidden_size=state_size)
+        self.state_list = []
+        self.cell_list = []
+        self.state_size = state_size
+        self.num_layers = 2
+
+    def init_rnn(self, batch_size, device):
+        self.state_list = [torch.zeros(batch_size, self.state_size).to(device)] * self.num_layers
+        self.cell_list = [torch.zeros(batch_size, self.state_size).to(device)] * self.num_layers
+
+    @property
+    def hidden_state(self):
+        return [s.clone().detach().cpu() for s in self.state_list], \
+            [c.clone().detach().cpu() for c in self.cell_list]
+
+    @hidden_state.setter
+    def hidden_state(self, state):
+        device = self.state_list[0].device
+        self.state_list = [s.to(device) for s in state[0]]
+        self.cell_list = [c.to(device) for c in state[1]]
+
+    def params(self):
+        l1, l2 = self.layer_1, self.layer_2
+        return (l1.weight_ih, l1.weight_hh, l1.bias_ih, l1.bias_hh, l2.weight_ih, l2.weight_hh, l2.bias_ih, l2.bias_hh)
+
+
+class Attention(nn.Module):
+    """asr.py:328-392 (parameter holder + cached-memory attributes)."""
+
+    def __init__(self, mlp_out_size, encoder_out_size, decoder_state_size):
+        super(Attention, self).__init__()
+        self.softmax = nn.Softmax(dim=-1)
+        self.phi = nn.Linear(decoder_state_size, mlp_out_size, bias=False)
+        self.psi = nn.Linear(encoder_out_size, mlp_out_size)
+        self.comp_listener_feature = None
+        self.state_mask = None
+
+    def reset_enc_mem(self):
+        self.comp_listener_feature = None
+        self.state_mask = None
+
+    def params(self):
+        return (self.phi.weight, self.psi.weight, self.psi.bias)
+
+
+class ASR(nn.Module):
+    """asr.py:15-212."""
+
+    def __init__(self, output_dim, encoder_state_size, decoder_state_size, mlp_out_size, feature_dim, tf_rate):
+        super(ASR, self).__init__()
+        enc_out_dim = encoder_state_size * 2
+        self.encoder = Listener(encoder_state_size, feature_dim)
+        self.attention = Attention(mlp_out_size, enc_out_dim, decoder_state_size)
+        self.decoder = Speller(decoder_state_size, enc_out_dim)
+        self.embed = nn.Embedding(output_dim, decoder_state_size)
+        self.char_trans = nn.Linear(decoder_state_size, output_dim)
+        self.tf_rate = tf_rate
+        self.att_on_device = False       # True: keep attention maps on the GPU (skips the reference's D2H copy)
+        self.sample_seed = 0
+        self.last_tokens = None          # [B,U] int32: the input token of every step of the last forward
+        self.init_parameters()
+
+    # ------------------------------------------------------------------------------------------
+    def _spell(self, enc, enc_len, tok_in, modes):
+        lens_dev = torch.tensor(enc_len, dtype=torch.int32, device=enc.device)
+        params = self.attention.params() + self.decoder.params() + (self.embed.weight, self.char_trans.weight,
+                                                                    self.char_trans.bias)
+        self.sample_seed += 1
+        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params)
+
+    def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
+        """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
+        encode_feature, encode_len = self.encoder(audio_feature, state_len)
+        B = audio_feature.shape[0]
+        U = int(decode_step)
+        tok_in = torch.zeros(B, U, dtype=torch.int32, device=encode_feature.device)
+        if teacher is not None:
+            n = min(U, teacher.shape[1])
+            tok_in[:, 1:n] = teacher[:, 1:n].to(torch.int32)
+            # one host draw per step, same stream of draws as asr.py:94
+            modes = [0 if random.random() <= self.tf_rate else 2 for _ in range(U)]
+        else:
+            modes = [1] * U
+        logits, att, toks = self._spell(encode_feature, encode_len, tok_in, modes)
+        self.last_tokens = toks
+        att = att.detach()
+        return encode_len, logits, (att if self.att_on_device else att.cpu())
+
+    @torch.no_grad()
+    def decode_batch(self, xs, x_lens, max_steps=200):
+        """Greedy decoding of many utterances at once with the per-utterance (bs=1) semantics of ASR.decode:
+        xs [N,T,F] zero-padded, x_lens sorted in decreasing order.  Returns a list of token-id lists."""
+        prev = self.encoder.utterance_independent
+        self.encoder.utterance_independent = True
+        try:
+            enc, enc_len = self.encoder(xs, x_lens)
+        finally:
+            self.encoder.utterance_independent = prev
+        N = xs.shape[0]
+        tok_in = torch.zeros(N, max_steps + 1, dtype=torch.int32, device=enc.device)
+        _, _, toks = self._spell(enc, enc_len, tok_in, [1] * (max_steps + 1))
+        toks = toks[:, 1:].cpu().tolist()
+        out = []
+        for row in toks:
+            ids = []
+            for v in row[:max_steps]:
+                if v == 1:
+                    break
+                ids.append(v)
+            out.append(ids)
+        return out
+
+    def decode(self, x, x_len, rnn_lm, mapper, lm_weight):
+        """asr.py:112-173 (bs=1).  lm_weight == 0 runs entirely in the fused kernels."""
+        assert len(x.shape) == 3 and x.shape[0] == 1
+        if lm_weight != 0:
+            raise NotImplementedError('decode with a language model (lm_weight != 0) is not wired yet')
+        ids = self.decode_batch(x, x_len)[0]
+        return ''.join(mapper.ind_to_char(i) for i in ids)
+
+    # ------------------------------------------------------------------------------------------
+    def init_parameters(self):
+        """asr.py:175-212."""
+        for p in self.parameters():
+            data = p.data
+            if data.dim() == 1:
+                data.zero_()
+            elif data.dim() == 2:
+                data.normal_(0, 1. / math.sqrt(data.size(1)))
+            else:
+                raise NotImplementedError
+        self.embed.weight.data.normal_(0, 1)
+        for bias in (self.decoder.layer_1.bias_ih, self.decoder.layer_2.bias_ih):
+            n = bias.size(0)
+            bias.data[n // 4:n // 2].fill_(1.)

@@ -1,0 +1,78 @@
+// Shared helpers for the ss_asr_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace ssasr {
+
+void set_error(const char* fmt, ...);
+
+#define SSASR_CHECK_CUDA(expr)                                                        \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      ssasr::set_error("%s:%d CUDA error %d (%s) in %s", __FILE__, __LINE__, (int)_e, \
+                       cudaGetErrorString(_e), #expr);                                \
+      return -2;                                                                      \
+    }                                                                                 \
+  } while (0)
+
+#define SSASR_REQUIRE(cond, ...)        \
+  do {                                  \
+    if (!(cond)) {                      \
+      ssasr::set_error(__VA_ARGS__);    \
+      return -1;                        \
+    }                                   \
+  } while (0)
+
+#define SSASR_LAUNCH_CHECK() SSASR_CHECK_CUDA(cudaGetLastError())
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reductions through a 32-float shared scratch (blockDim.x multiple of 32, <= 1024).
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : 0.0f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+
+int sm_count();
+
+// internal fp32 GEMM launcher (gemm_f32.cu): C[M,N] = (accumulate ? C : 0) + op(A) * op(B) (+ bias[N]) (+tanh)
+//   a_kmajor: element A(m,k) at A[m*lda + k] (1) or A[k*lda + m] (0)
+//   b_kmajor: element B(k,n) at B[n*ldb + k] (1, the "weights [N,K]" form) or B[k*ldb + n] (0)
+int gemm_f32(cudaStream_t st, int M, int N, int K, const float* A, int lda, int a_kmajor, const float* B, int ldb,
+             int b_kmajor, float* C, int ldc, const float* bias, int accumulate, int act_tanh, int zero_period = 0,
+             int zero_pos = 0);
+//   zero_period > 0: reduction index k with (k % zero_period) == zero_pos contributes nothing (used to drop
+//   the first/last frame of every utterance from the recurrent-weight gradient).
+
+}  // namespace ssasr

@@ -1,0 +1,305 @@
+// Batched log-mel filterbank frontend: framing (reflect-padded, centred), periodic Hann window, real FFT,
+// power spectrum, Slaney mel projection and log, in ONE kernel, output already [frames, n_mels].
+//
+// Reference semantics: log_fbank, /root/reference/src/preprocess.py:187-208, i.e.
+// librosa(0.6.3).feature.melspectrogram(y, sr, n_mels=N_DIMS, n_fft=ws, hop_length=st) -> log(. + eps) -> T.
+//
+// One CTA handles FPB consecutive frames of one utterance: the audio span they share is read once
+// (hop < window, every sample is used by 2.5 frames), frames are built in shared memory, the
+// 25 ms window at 16 kHz (400 samples) is transformed as a 200-point complex FFT (radix 5*5*4*2
+// Stockham, one butterfly per thread) plus the real-input split; other window sizes (the reference's
+// default 22.05 kHz gives 551 = 19*29) take a direct-DFT path in the same kernel.  The mel matrix is
+// applied in its sparse (two triangles per bin) form.
+#include "common.cuh"
+#include <math.h>
+#include <mutex>
+#include <vector>
+
+namespace ssasr {
+
+constexpr int FPB = 16;            // frames per CTA
+constexpr int NT = 256;
+
+struct FbankTables {
+  int sr = 0, n_mels = 0, ws = 0, st = 0, nbins = 0;
+  float* window = nullptr;     // [ws]
+  float2* tw = nullptr;        // fast path: [200] W_200^m then [201] W_400^k ; generic: [ws] W_ws^m
+  int* mel_start = nullptr;    // [n_mels]
+  int* mel_cnt = nullptr;      // [n_mels]
+  int* mel_off = nullptr;      // [n_mels]
+  float* mel_w = nullptr;      // packed non-zero weights
+  int max_cnt = 0;
+};
+
+static double hz_to_mel(double f) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+  const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+  return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+static std::mutex g_tab_mu;
+static std::vector<FbankTables> g_tabs;
+
+static int get_tables(int sr, int n_mels, FbankTables* out) {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  for (auto& t : g_tabs)
+    if (t.sr == sr && t.n_mels == n_mels) { *out = t; return 0; }
+  FbankTables t;
+  t.sr = sr; t.n_mels = n_mels;
+  t.ws = (int)(sr * 0.001 * 25);
+  t.st = (int)(sr * 0.001 * 10);
+  t.nbins = 1 + t.ws / 2;
+  const int ws = t.ws;
+  std::vector<float> win(ws);
+  for (int n = 0; n < ws; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * n / ws));
+  std::vector<float2> tw;
+  if (ws == 400) {
+    for (int m = 0; m < 200; ++m) tw.push_back(make_float2((float)cos(2.0 * M_PI * m / 200), (float)-sin(2.0 * M_PI * m / 200)));
+    for (int k = 0; k <= 200; ++k) tw.push_back(make_float2((float)cos(2.0 * M_PI * k / 400), (float)-sin(2.0 * M_PI * k / 400)));
+  } else {
+    for (int m = 0; m < ws; ++m) tw.push_back(make_float2((float)cos(2.0 * M_PI * m / ws), (float)-sin(2.0 * M_PI * m / ws)));
+  }
+  // Slaney mel basis (librosa.filters.mel, htk=False, norm=1), fp64 then rounded to fp32
+  std::vector<double> mel_f(n_mels + 2);
+  const double m_lo = hz_to_mel(0.0), m_hi = hz_to_mel(sr / 2.0);
+  for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (n_mels + 1));
+  std::vector<int> start(n_mels), cnt(n_mels), off(n_mels);
+  std::vector<float> wts;
+  for (int i = 0; i < n_mels; ++i) {
+    int first = -1, last = -1;
+    std::vector<double> row(t.nbins);
+    for (int b = 0; b < t.nbins; ++b) {
+      const double f = (sr / 2.0) * b / (t.nbins - 1);
+      const double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
+      const double upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
+      double w = lower < upper ? lower : upper;
+      if (w < 0) w = 0;
+      w *= 2.0 / (mel_f[i + 2] - mel_f[i]);
+      row[b] = w;
+      if (w > 0) { if (first < 0) first = b; last = b; }
+    }
+    start[i] = first < 0 ? 0 : first;
+    cnt[i] = first < 0 ? 0 : last - first + 1;
+    off[i] = (int)wts.size();
+    for (int b = 0; b < cnt[i]; ++b) wts.push_back((float)row[start[i] + b]);
+    if (cnt[i] > t.max_cnt) t.max_cnt = cnt[i];
+  }
+  if (wts.empty()) wts.push_back(0.f);
+  SSASR_CHECK_CUDA(cudaMalloc(&t.window, sizeof(float) * ws));
+  SSASR_CHECK_CUDA(cudaMalloc(&t.tw, sizeof(float2) * tw.size()));
+  SSASR_CHECK_CUDA(cudaMalloc(&t.mel_start, sizeof(int) * n_mels));
+  SSASR_CHECK_CUDA(cudaMalloc(&t.mel_cnt, sizeof(int) * n_mels));
+  SSASR_CHECK_CUDA(cudaMalloc(&t.mel_off, sizeof(int) * n_mels));
+  SSASR_CHECK_CUDA(cudaMalloc(&t.mel_w, sizeof(float) * wts.size()));
+  SSASR_CHECK_CUDA(cudaMemcpy(t.window, win.data(), sizeof(float) * ws, cudaMemcpyHostToDevice));
+  SSASR_CHECK_CUDA(cudaMemcpy(t.tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+  SSASR_CHECK_CUDA(cudaMemcpy(t.mel_start, start.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+  SSASR_CHECK_CUDA(cudaMemcpy(t.mel_cnt, cnt.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+  SSASR_CHECK_CUDA(cudaMemcpy(t.mel_off, off.data(), sizeof(int) * n_mels, cudaMemcpyHostToDevice));
+  SSASR_CHECK_CUDA(cudaMemcpy(t.mel_w, wts.data(), sizeof(float) * wts.size(), cudaMemcpyHostToDevice));
+  g_tabs.push_back(t);
+  *out = t;
+  return 0;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// one Stockham stage of radix R over `nfr` frames of N=200 complex points (src -> dst), twiddles tw200
+template <int R>
+__device__ __forceinline__ void stockham_stage(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw200,
+                                               int Ns, int nfr) {
+  constexpr int N = 200;
+  constexpr int NB = N / R;
+  for (int w = threadIdx.x; w < nfr * NB; w += NT) {
+    const int f = w / NB, j = w % NB;
+    const float2* x = src + f * N;
+    float2* y = dst + f * N;
+    const int k = j % Ns;
+    const int tstep = k * (N / (Ns * R));       // twiddle index step: W_{Ns*R}^{k} = W_200^{k*200/(Ns*R)}
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      v[r] = x[j + r * NB];
+      if (r > 0 && Ns > 1) v[r] = cmul(v[r], tw200[(tstep * r) % N]);
+    }
+    float2 o[R];
+    if constexpr (R == 2) {
+      o[0] = cadd(v[0], v[1]);
+      o[1] = csub(v[0], v[1]);
+    } else if constexpr (R == 4) {
+      const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
+      o[0] = cadd(t0, t2);
+      o[2] = csub(t0, t2);
+      o[1] = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i*t3
+      o[3] = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i*t3
+    } else {  // R == 5
+      const float c1 = 0.30901699437494745f, c2 = -0.8090169943749475f, s1 = 0.9510565162951535f, s2 = 0.5877852522924731f;
+      const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+      o[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
+      const float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+      const float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+      const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+      const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+      o[1] = make_float2(a1.x + b1.y, a1.y - b1.x);   // a1 - i*b1
+      o[4] = make_float2(a1.x - b1.y, a1.y + b1.x);
+      o[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
+      o[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
+    }
+    const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) y[j0 + r * Ns] = o[r];
+  }
+}
+
+struct FbankParams {
+  const float* audio; const long long* offsets; int n_utt;
+  float* out; const long long* out_offsets;
+  int ws, st, nbins, n_mels;
+  const float* window; const float2* tw;
+  const int *mel_start, *mel_cnt, *mel_off; const float* mel_w;
+};
+
+__global__ void __launch_bounds__(NT) fbank_kernel(FbankParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int u = blockIdx.y;
+  const long long a0 = p.offsets[u];
+  const int n = (int)(p.offsets[u + 1] - a0);
+  const int ws = p.ws, st = p.st, half = ws / 2;
+  const int nframes = 1 + (n + 2 * half - ws) / st;
+  const int f0 = blockIdx.x * FPB;
+  if (f0 >= nframes) return;
+  const int nfr = min(FPB, nframes - f0);
+  const bool fast = (ws == 400);
+  // shared layout: span | bufA | bufB | P | tw
+  const int span_len = (FPB - 1) * st + ws;
+  float* span = smem;                                            // [span_len]
+  float* bufA = span + ((span_len + 3) & ~3);                    // fast: FPB*200 float2 ; generic: FPB*ws floats
+  const int bufA_floats = fast ? FPB * 400 : FPB * ws;
+  float* bufB = bufA + ((bufA_floats + 3) & ~3);                 // fast only: FPB*200 float2
+  float* P = bufB + (fast ? FPB * 400 : 0);                      // [FPB][nbins+1]
+  float2* tws = reinterpret_cast<float2*>(P + ((FPB * (p.nbins + 1) + 3) & ~3));   // twiddles
+  const int ntw = fast ? 401 : ws;
+  for (int i = threadIdx.x; i < ntw; i += NT) tws[i] = p.tw[i];
+  // 1. audio span with numpy 'reflect' padding at the utterance edges
+  const float* au = p.audio + a0;
+  const int s0 = f0 * st - half;
+  const int need = (nfr - 1) * st + ws;
+  for (int i = threadIdx.x; i < need; i += NT) {
+    int idx = s0 + i;
+    if (idx < 0) idx = -idx;
+    if (idx >= n) idx = 2 * (n - 1) - idx;
+    span[i] = au[idx];
+  }
+  __syncthreads();
+  const int PB = p.nbins + 1;
+  if (fast) {
+    float2* A = reinterpret_cast<float2*>(bufA);
+    float2* Bf = reinterpret_cast<float2*>(bufB);
+    // 2. window and pack z[m] = xw[2m] + i*xw[2m+1]
+    for (int w = threadIdx.x; w < nfr * 200; w += NT) {
+      const int f = w / 200, m = w % 200;
+      const float* s = span + f * st + 2 * m;
+      A[f * 200 + m] = make_float2(s[0] * p.window[2 * m], s[1] * p.window[2 * m + 1]);
+    }
+    __syncthreads();
+    stockham_stage<5>(A, Bf, tws, 1, nfr);
+    __syncthreads();
+    stockham_stage<5>(Bf, A, tws, 5, nfr);
+    __syncthreads();
+    stockham_stage<4>(A, Bf, tws, 25, nfr);
+    __syncthreads();
+    stockham_stage<2>(Bf, A, tws, 100, nfr);
+    __syncthreads();
+    // 3. real-input split: X[k] = E[k] + W_400^k * O[k],  k = 0..200
+    const float2* w400 = tws + 200;
+    for (int w = threadIdx.x; w < nfr * 201; w += NT) {
+      const int f = w / 201, k = w % 201;
+      const float2 zk = A[f * 200 + (k % 200)];
+      const float2 zn = A[f * 200 + ((200 - k) % 200)];
+      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // (zk - conj(zn)) / (2i)
+      const float2 x = cadd(e, cmul(w400[k], o));
+      P[f * PB + k] = x.x * x.x + x.y * x.y;
+    }
+  } else {
+    // generic window length: direct DFT, one (frame, bin) per thread
+    for (int w = threadIdx.x; w < nfr * ws; w += NT) {
+      const int f = w / ws, i = w % ws;
+      bufA[f * ws + i] = span[f * st + i] * p.window[i];
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < nfr * p.nbins; w += NT) {
+      const int f = w / p.nbins, k = w % p.nbins;
+      const float* x = bufA + f * ws;
+      float re = 0.f, im = 0.f;
+      int idx = 0;
+      for (int i = 0; i < ws; ++i) {
+        const float2 t = tws[idx];
+        re = fmaf(x[i], t.x, re);
+        im = fmaf(x[i], t.y, im);
+        idx += k;
+        if (idx >= ws) idx -= ws;
+      }
+      P[f * PB + k] = re * re + im * im;
+    }
+  }
+  __syncthreads();
+  // 4. sparse mel projection + log, coalesced [frame, mel] store
+  float* outp = p.out + (size_t)(p.out_offsets[u] + f0) * p.n_mels;
+  for (int w = threadIdx.x; w < nfr * p.n_mels; w += NT) {
+    const int f = w / p.n_mels, i = w % p.n_mels;
+    const int b0 = p.mel_start[i], c = p.mel_cnt[i];
+    const float* wt = p.mel_w + p.mel_off[i];
+    const float* pr = P + f * PB + b0;
+    float s = 0.f;
+    for (int b = 0; b < c; ++b) s = fmaf(wt[b], pr[b], s);
+    outp[w] = logf(s + 2.220446049250313e-16f);
+  }
+}
+
+}  // namespace ssasr
+
+using namespace ssasr;
+
+extern "C" {
+
+// frames produced for an utterance of n_samples (preprocess.py:194-198 + librosa centred STFT)
+long long ssasr_fbank_num_frames(long long n_samples, int sample_rate) {
+  const int ws = (int)(sample_rate * 0.001 * 25), st = (int)(sample_rate * 0.001 * 10);
+  return 1 + (n_samples + 2 * (ws / 2) - ws) / st;
+}
+
+// audio: concatenated fp32 samples; offsets int64 [n_utt+1] (device): utterance u = audio[offsets[u]:offsets[u+1]]
+// out: fp32 [total_frames, n_mels]; out_offsets int64 [n_utt+1] (device): first output row of every utterance
+// max_frames: largest per-utterance frame count (host value, sizes the grid)
+int ssasr_fbank(const float* audio, const long long* offsets, int n_utt, int sample_rate, int n_mels, float* out,
+                const long long* out_offsets, int max_frames, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSASR_REQUIRE(n_utt > 0 && n_utt <= 65535, "fbank: n_utt=%d out of range (1..65535 per call)", n_utt);
+  SSASR_REQUIRE(n_mels > 0 && sample_rate >= 1000, "fbank: bad n_mels=%d / sample_rate=%d", n_mels, sample_rate);
+  FbankTables t;
+  int rc = get_tables(sample_rate, n_mels, &t);
+  if (rc) return rc;
+  FbankParams p;
+  p.audio = audio; p.offsets = offsets; p.n_utt = n_utt; p.out = out; p.out_offsets = out_offsets;
+  p.ws = t.ws; p.st = t.st; p.nbins = t.nbins; p.n_mels = n_mels;
+  p.window = t.window; p.tw = t.tw; p.mel_start = t.mel_start; p.mel_cnt = t.mel_cnt; p.mel_off = t.mel_off; p.mel_w = t.mel_w;
+  const bool fast = t.ws == 400;
+  const int span_len = (FPB - 1) * t.st + t.ws;
+  size_t floats = ((span_len + 3) & ~3) + (((fast ? FPB * 400 : FPB * t.ws) + 3) & ~3) + (fast ? FPB * 400 : 0) +
+                  ((FPB * (t.nbins + 1) + 3) & ~3) + 2 * (fast ? 401 : t.ws);
+  const size_t smem = floats * sizeof(float);
+  SSASR_REQUIRE(smem <= 227 * 1024, "fbank: window of %d samples needs %zu B shared memory", t.ws, smem);
+  SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((max_frames + FPB - 1) / FPB, n_utt);
+  fbank_kernel<<<grid, NT, smem, st>>>(p);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,482 @@
+// Attend-and-spell decoder loop (fp32 path): attention energy / masked softmax / context, two stacked
+// LSTM cells, character projection, next-token selection, and the full backward pass.
+//
+// Reference semantics: Attention.forward asr.py:343-392, Speller.forward asr.py:314-326, the decode loop
+// of ASR.forward asr.py:65-110 (query = layer-1 state BEFORE this step's update), loss trainer.py:426-434.
+// Everything stays on the device for all U steps (the reference syncs to the host every step,
+// asr.py:103); attention maps are written straight into the stacked [B,U,T'] layout.
+#include "common.cuh"
+#include <curand_kernel.h>
+
+namespace ssasr {
+
+int colsum(cudaStream_t st, const float* src, float* out, int R, int C, int ld, int accumulate);
+
+// ------------------------------------------------------------------------------------------------
+// attention step, forward.  One CTA (256 threads) per utterance.
+// ------------------------------------------------------------------------------------------------
+struct AttnFwd {
+  int Tp, E, Sd, M;
+  const float* h1prev; long long h1_ld;      // [B,Sd] rows (null at t == 0)
+  const float* phi_w;                        // [M,Sd]
+  const float* psi;                          // [B,Tp,M]  tanh(psi(enc))
+  const float* enc;                          // [B,Tp,E]
+  const int* enc_lens;                       // [B]
+  const float* emb_w; const int* tok; long long tok_ld;   // embedding gather for the step input
+  float* xin1; long long xin1_ld;            // row b: [emb(Sd) ; ctx(E) ; h1prev(Sd)]
+  float* q; long long q_ld;                  // [B,M]
+  float* alpha; long long alpha_ld;          // [B,Tp]
+};
+
+__global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
+  extern __shared__ float sm[];
+  float* hs = sm;                 // [Sd]
+  float* qs = hs + a.Sd;          // [M]
+  float* es = qs + a.M;           // [Tp]
+  float* scratch = es + a.Tp;     // [32]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  float* xrow = a.xin1 + (size_t)b * a.xin1_ld;
+  const int tk = a.tok[(size_t)b * a.tok_ld];
+  for (int k = tid; k < a.Sd; k += blockDim.x) {
+    const float h = a.h1prev ? a.h1prev[(size_t)b * a.h1_ld + k] : 0.f;
+    hs[k] = h;
+    xrow[a.Sd + a.E + k] = h;
+    xrow[k] = a.emb_w[(size_t)tk * a.Sd + k];
+  }
+  __syncthreads();
+  for (int m = warp; m < a.M; m += nwarp) {
+    float s = 0.f;
+    for (int k = lane; k < a.Sd; k += 32) s = fmaf(a.phi_w[(size_t)m * a.Sd + k], hs[k], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float qv = tanhf(s);
+      qs[m] = qv;
+      a.q[(size_t)b * a.q_ld + m] = qv;
+    }
+  }
+  __syncthreads();
+  const int len = a.enc_lens[b];
+  const float* psib = a.psi + (size_t)b * a.Tp * a.M;
+  for (int j = warp; j < a.Tp; j += nwarp) {
+    float s = 0.f;
+    if (j < len) {
+      for (int m = lane; m < a.M; m += 32) s = fmaf(psib[(size_t)j * a.M + m], qs[m], s);
+      s = warp_sum(s);
+    } else {
+      s = -INFINITY;
+    }
+    if (lane == 0) es[j] = s;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < a.Tp; j += blockDim.x) mx = fmaxf(mx, es[j]);
+  mx = block_max(mx, scratch);
+  float sum = 0.f;
+  for (int j = tid; j < a.Tp; j += blockDim.x) {
+    const float e = (es[j] == -INFINITY) ? 0.f : expf(es[j] - mx);
+    es[j] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, scratch);
+  const float inv = 1.0f / sum;
+  __syncthreads();
+  for (int j = tid; j < a.Tp; j += blockDim.x) {
+    const float al = es[j] * inv;
+    es[j] = al;
+    a.alpha[(size_t)b * a.alpha_ld + j] = al;
+  }
+  __syncthreads();
+  const float* encb = a.enc + (size_t)b * a.Tp * a.E;
+  for (int c = tid; c < a.E; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < len; ++j) s = fmaf(es[j], encb[(size_t)j * a.E + c], s);
+    xrow[a.Sd + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention step, backward.  One CTA per utterance.
+// ------------------------------------------------------------------------------------------------
+struct AttnBwd {
+  int Tp, E, Sd, M;
+  const float* dctx; long long dctx_ld;      // [B,E]
+  const float* alpha; long long alpha_ld;    // [B,Tp]
+  const float* q; long long q_ld;            // [B,M]
+  const float* phi_w;                        // [M,Sd]
+  const float* psi;                          // [B,Tp,M]
+  const float* enc;                          // [B,Tp,E]
+  const int* enc_lens;
+  float* denc;                               // [B,Tp,E]  +=
+  float* dpsi;                               // [B,Tp,M]  +=
+  float* dqpre; long long dqpre_ld;          // [B,M] out
+  float* dh1att;                             // [B,Sd] out
+};
+
+__global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
+  extern __shared__ float sm[];
+  float* dcs = sm;                 // [E]
+  float* als = dcs + a.E;          // [Tp]  alpha, then de
+  float* das = als + a.Tp;         // [Tp]  dalpha
+  float* dqs = das + a.Tp;         // [M]
+  float* scratch = dqs + a.M;      // [32]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int len = a.enc_lens[b];
+  for (int c = tid; c < a.E; c += blockDim.x) dcs[c] = a.dctx[(size_t)b * a.dctx_ld + c];
+  for (int j = tid; j < a.Tp; j += blockDim.x) als[j] = a.alpha[(size_t)b * a.alpha_ld + j];
+  __syncthreads();
+  const float* encb = a.enc + (size_t)b * a.Tp * a.E;
+  float* dencb = a.denc + (size_t)b * a.Tp * a.E;
+  for (int j = warp; j < a.Tp; j += nwarp) {
+    float s = 0.f;
+    if (j < len) {
+      const float al = als[j];
+      for (int c = lane; c < a.E; c += 32) {
+        const float d = dcs[c];
+        s = fmaf(d, encb[(size_t)j * a.E + c], s);
+        dencb[(size_t)j * a.E + c] += al * d;
+      }
+      s = warp_sum(s);
+    }
+    if (lane == 0) das[j] = s;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int j = tid; j < len; j += blockDim.x) dot = fmaf(als[j], das[j], dot);
+  dot = block_sum(dot, scratch);
+  __syncthreads();
+  for (int j = tid; j < a.Tp; j += blockDim.x) als[j] = (j < len) ? als[j] * (das[j] - dot) : 0.f;   // de_j
+  __syncthreads();
+  const float* psib = a.psi + (size_t)b * a.Tp * a.M;
+  float* dpsib = a.dpsi + (size_t)b * a.Tp * a.M;
+  for (int m = tid; m < a.M; m += blockDim.x) {
+    const float qv = a.q[(size_t)b * a.q_ld + m];
+    float s = 0.f;
+    for (int j = 0; j < len; ++j) {
+      const float de = als[j];
+      s = fmaf(de, psib[(size_t)j * a.M + m], s);
+      dpsib[(size_t)j * a.M + m] += de * qv;
+    }
+    const float dq = s * (1.f - qv * qv);
+    dqs[m] = dq;
+    a.dqpre[(size_t)b * a.dqpre_ld + m] = dq;
+  }
+  __syncthreads();
+  for (int k = tid; k < a.Sd; k += blockDim.x) {
+    float s = 0.f;
+    for (int m = 0; m < a.M; ++m) s = fmaf(dqs[m], a.phi_w[(size_t)m * a.Sd + k], s);
+    a.dh1att[(size_t)b * a.Sd + k] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM cell pointwise (gates interleaved: col = unit*4 + gate)
+// ------------------------------------------------------------------------------------------------
+__global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long long g_ld, const float* __restrict__ cprev,
+                                long long cp_ld, float* __restrict__ cout, long long c_ld, float* __restrict__ hout,
+                                long long h_ld, const float* __restrict__ cp_src, long long cps_ld, float* __restrict__ cp_dst,
+                                long long cpd_ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S) return;
+  const int b = i / S, u = i % S;
+  float4* gp = reinterpret_cast<float4*>(gates + (size_t)b * g_ld) + u;
+  const float4 g = *gp;
+  float4 a;
+  a.x = sigmoidf_acc(g.x); a.y = sigmoidf_acc(g.y); a.z = tanhf(g.z); a.w = sigmoidf_acc(g.w);
+  const float cp = cprev ? cprev[(size_t)b * cp_ld + u] : 0.f;
+  const float c = a.y * cp + a.x * a.z;
+  *gp = a;
+  cout[(size_t)b * c_ld + u] = c;
+  hout[(size_t)b * h_ld + u] = a.w * tanhf(c);
+  if (cp_dst) cp_dst[(size_t)b * cpd_ld + u] = cp_src ? cp_src[(size_t)b * cps_ld + u] : 0.f;
+}
+
+__global__ void cell_bwd_kernel(int B, int S, float* __restrict__ act, long long a_ld, const float* __restrict__ c, long long c_ld,
+                                const float* __restrict__ cprev, long long cp_ld, const float* __restrict__ dh_a, long long da_ld,
+                                const float* __restrict__ dh_b, long long db_ld, const float* __restrict__ dh_c, long long dc_ld,
+                                float* __restrict__ dcstate, int first) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S) return;
+  const int b = i / S, u = i % S;
+  float dh = dh_a[(size_t)b * da_ld + u];
+  if (dh_b) dh += dh_b[(size_t)b * db_ld + u];
+  if (dh_c) dh += dh_c[(size_t)b * dc_ld + u];
+  float4* ap = reinterpret_cast<float4*>(act + (size_t)b * a_ld) + u;
+  const float4 a = *ap;
+  const float cv = c[(size_t)b * c_ld + u];
+  const float cp = cprev ? cprev[(size_t)b * cp_ld + u] : 0.f;
+  const float dcr = first ? 0.f : dcstate[i];
+  const float tc = tanhf(cv);
+  const float dc = dh * a.w * (1.f - tc * tc) + dcr;
+  float4 dg;
+  dg.w = dh * tc * a.w * (1.f - a.w);
+  dg.x = dc * a.z * a.x * (1.f - a.x);
+  dg.z = dc * a.x * (1.f - a.z * a.z);
+  dg.y = dc * cp * a.y * (1.f - a.y);
+  *ap = dg;
+  dcstate[i] = dc * a.y;
+}
+
+__global__ void emb_grad_add_kernel(int B, int Sd, const float* __restrict__ demb, long long ld, const int* __restrict__ tok,
+                                    long long tok_ld, float* __restrict__ gemb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Sd) return;
+  const int b = i / Sd, k = i % Sd;
+  atomicAdd(gemb + (size_t)tok[(size_t)b * tok_ld] * Sd + k, demb[(size_t)b * ld + k]);
+}
+
+__global__ void dtanh_inplace_kernel(float* __restrict__ d, const float* __restrict__ y, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    d[i] *= (1.f - v * v);
+  }
+}
+
+// next-token selection from logits row (C <= 1024): mode 1 = argmax (first max index, torch.argmax),
+// mode 2 = sample from softmax (Philox; the one intentionally non-bit-reproducible branch, asr.py:97)
+__global__ void pick_token_kernel(int B, int C, const float* __restrict__ logits, long long ld, int mode, unsigned long long seed,
+                                  unsigned long long step, int* __restrict__ tok_out, long long tok_ld) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* l = logits + (size_t)b * ld;
+  int best = 0;
+  float mx = l[0];
+  for (int c = 1; c < C; ++c)
+    if (l[c] > mx) { mx = l[c]; best = c; }
+  if (mode == 2) {
+    curandStatePhilox4_32_10_t rs;
+    curand_init(seed, (unsigned long long)b, step, &rs);
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) sum += expf(l[c] - mx);
+    const float r = curand_uniform(&rs) * sum;
+    float acc = 0.f;
+    best = C - 1;
+    for (int c = 0; c < C; ++c) {
+      acc += expf(l[c] - mx);
+      if (r <= acc) { best = c; break; }
+    }
+  }
+  tok_out[(size_t)b * tok_ld] = best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused cross-entropy (trainer.py:426-434): loss and dL/dlogits in one pass.  One CTA per utterance.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ce_kernel(int B, int U, int C, int L, const float* __restrict__ logits,
+                                                 const long long* __restrict__ y, float* __restrict__ loss_b,
+                                                 float* __restrict__ dlogits, float grad_scale) {
+  __shared__ float scratch[32];
+  __shared__ float part[4];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float cnt = 0.f;
+  for (int i = tid; i < L; i += blockDim.x) cnt += (y[(size_t)b * L + i] != 0) ? 1.f : 0.f;
+  cnt = block_sum(cnt, scratch);
+  const float w = grad_scale / (cnt * (float)B);
+  float acc = 0.f;
+  for (int t = warp; t < U; t += 4) {
+    const float* l = logits + ((size_t)b * U + t) * C;
+    const int label = (int)y[(size_t)b * L + t + 1];
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, l[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(l[c] - mx);
+    s = warp_sum(s);
+    const float lse = mx + logf(s);
+    if (label != 0 && lane == 0) acc += lse - l[label];
+    if (dlogits) {
+      float* d = dlogits + ((size_t)b * U + t) * C;
+      for (int c = lane; c < C; c += 32) {
+        float g = 0.f;
+        if (label != 0) g = (expf(l[c] - lse) - (c == label ? 1.f : 0.f)) * w;
+        d[c] = g;
+      }
+    }
+  }
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (tid == 0) loss_b[b] = (part[0] + part[1] + part[2] + part[3]) / cnt;
+}
+__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += v[i];
+    *out = s / (float)n;
+  }
+}
+
+}  // namespace ssasr
+
+using namespace ssasr;
+
+extern "C" {
+
+// Plain-C argument block for the decoder loop (all device pointers unless noted).
+typedef struct {
+  int B, Tp, E, Sd, M, C, U;
+  // parameters (kernel layout, see ssasr_pack_lstmcell)
+  const float *phi_w, *psi_w, *psi_b, *w1cat, *b1, *w2cat, *b2, *emb_w, *wc, *bc;
+  // inputs
+  const float* enc;          // [B,Tp,E]
+  const int* enc_lens;       // [B]
+  int* tok_in;               // [B,U] input token of every step (col 0 = SOS; teacher columns pre-filled)
+  const int* step_mode;      // HOST [U]: how the token AFTER step t is chosen: 0 teacher, 1 argmax, 2 sample
+  unsigned long long seed;
+  // outputs / saved state
+  float *psi, *xin1, *xin2, *act1, *act2, *c1, *c2, *h2all, *q, *alpha, *logits;
+} ssasr_speller_fwd_args;
+
+int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = a->B, Tp = a->Tp, E = a->E, Sd = a->Sd, M = a->M, C = a->C, U = a->U;
+  const int K1 = Sd + E, X1 = K1 + Sd, X2 = 2 * Sd;
+  SSASR_REQUIRE(Sd % 4 == 0, "speller: decoder state size %d must be a multiple of 4", Sd);
+  int rc = gemm_f32(st, B * Tp, M, E, a->enc, E, 1, a->psi_w, E, 1, a->psi, M, a->psi_b, 0, 1);
+  if (rc) return rc;
+  const size_t attn_smem = (size_t)(Sd + M + Tp + 32) * sizeof(float);
+  SSASR_REQUIRE(attn_smem <= 200 * 1024, "speller: attention working set too large (Tp=%d)", Tp);
+  if (attn_smem > 48 * 1024)
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+  const int cell_blocks = (B * Sd + 255) / 256;
+  for (int t = 0; t < U; ++t) {
+    AttnFwd f;
+    f.Tp = Tp; f.E = E; f.Sd = Sd; f.M = M;
+    f.h1prev = t ? a->xin2 + (size_t)(t - 1) * X2 : nullptr; f.h1_ld = (long long)U * X2;
+    f.phi_w = a->phi_w; f.psi = a->psi; f.enc = a->enc; f.enc_lens = a->enc_lens;
+    f.emb_w = a->emb_w; f.tok = a->tok_in + t; f.tok_ld = U;
+    f.xin1 = a->xin1 + (size_t)t * X1; f.xin1_ld = (long long)U * X1;
+    f.q = a->q + (size_t)t * M; f.q_ld = (long long)U * M;
+    f.alpha = a->alpha + (size_t)t * Tp; f.alpha_ld = (long long)U * Tp;
+    attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f);
+    // layer 1
+    rc = gemm_f32(st, B, 4 * Sd, X1, a->xin1 + (size_t)t * X1, U * X1, 1, a->w1cat, X1, 1, a->act1 + (size_t)t * 4 * Sd,
+                  U * 4 * Sd, a->b1, 0, 0);
+    if (rc) return rc;
+    cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+                                                 t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
+                                                 a->c1 + (size_t)t * Sd, (long long)U * Sd, a->xin2 + (size_t)t * X2,
+                                                 (long long)U * X2, t ? a->h2all + (size_t)(t - 1) * Sd : nullptr,
+                                                 (long long)U * Sd, a->xin2 + (size_t)t * X2 + Sd, (long long)U * X2);
+    // layer 2
+    rc = gemm_f32(st, B, 4 * Sd, X2, a->xin2 + (size_t)t * X2, U * X2, 1, a->w2cat, X2, 1, a->act2 + (size_t)t * 4 * Sd,
+                  U * 4 * Sd, a->b2, 0, 0);
+    if (rc) return rc;
+    cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+                                                 t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
+                                                 a->c2 + (size_t)t * Sd, (long long)U * Sd, a->h2all + (size_t)t * Sd,
+                                                 (long long)U * Sd, nullptr, 0, nullptr, 0);
+    const int mode = a->step_mode ? a->step_mode[t] : 0;
+    if (mode != 0 && t + 1 < U) {
+      rc = gemm_f32(st, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
+                    0, 0);
+      if (rc) return rc;
+      pick_token_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
+                                                         (unsigned long long)t, a->tok_in + t + 1, U);
+    }
+  }
+  rc = gemm_f32(st, B * U, C, Sd, a->h2all, Sd, 1, a->wc, Sd, 1, a->logits, C, a->bc, 0, 0);
+  if (rc) return rc;
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+typedef struct {
+  int B, Tp, E, Sd, M, C, U;
+  const float *phi_w, *psi_w, *w1cat, *w2cat, *wc;
+  const float* enc;
+  const int* enc_lens;
+  const int* tok_in;
+  // saved by forward (act1/act2 are overwritten with gate gradients)
+  const float *psi, *xin1, *xin2, *c1, *c2, *h2all, *q, *alpha;
+  float *act1, *act2;
+  const float* dlogits;      // [B,U,C]
+  // gradient outputs (overwritten), kernel layout
+  float *d_phi_w, *d_psi_w, *d_psi_b, *d_w1cat, *d_b1, *d_w2cat, *d_b2, *d_emb_w, *d_wc, *d_bc, *denc;
+  // scratch
+  float *dh2all /*[B,U,Sd]*/, *dxin1 /*[B,X1]*/, *dxin2 /*[B,X2]*/, *dc1s, *dc2s, *dh1att /*[B,Sd] each*/,
+      *dpsi /*[B,Tp,M]*/, *dqpre /*[B,U,M]*/;
+} ssasr_speller_bwd_args;
+
+int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = a->B, Tp = a->Tp, E = a->E, Sd = a->Sd, M = a->M, C = a->C, U = a->U;
+  const int K1 = Sd + E, X1 = K1 + Sd, X2 = 2 * Sd;
+  int rc;
+  // through the character projection, all steps at once
+  rc = gemm_f32(st, B * U, Sd, C, a->dlogits, C, 1, a->wc, Sd, 0, a->dh2all, Sd, nullptr, 0, 0);
+  if (rc) return rc;
+  rc = gemm_f32(st, C, Sd, B * U, a->dlogits, C, 0, a->h2all, Sd, 0, a->d_wc, Sd, nullptr, 0, 0);
+  if (rc) return rc;
+  rc = colsum(st, a->dlogits, a->d_bc, B * U, C, C, 0);
+  if (rc) return rc;
+  SSASR_CHECK_CUDA(cudaMemsetAsync(a->denc, 0, sizeof(float) * (size_t)B * Tp * E, st));
+  SSASR_CHECK_CUDA(cudaMemsetAsync(a->dpsi, 0, sizeof(float) * (size_t)B * Tp * M, st));
+  SSASR_CHECK_CUDA(cudaMemsetAsync(a->d_emb_w, 0, sizeof(float) * (size_t)C * Sd, st));
+  const size_t attn_smem = (size_t)(E + 2 * Tp + M + 32) * sizeof(float);
+  SSASR_REQUIRE(attn_smem <= 200 * 1024, "speller bwd: attention working set too large (Tp=%d)", Tp);
+  if (attn_smem > 48 * 1024)
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+  const int cell_blocks = (B * Sd + 255) / 256;
+  for (int t = U - 1; t >= 0; --t) {
+    const int last = (t == U - 1);
+    cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+                                                 a->c2 + (size_t)t * Sd, (long long)U * Sd,
+                                                 t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
+                                                 a->dh2all + (size_t)t * Sd, (long long)U * Sd, last ? nullptr : a->dxin2 + Sd,
+                                                 (long long)X2, nullptr, 0, a->dc2s, last);
+    rc = gemm_f32(st, B, X2, 4 * Sd, a->act2 + (size_t)t * 4 * Sd, U * 4 * Sd, 1, a->w2cat, X2, 0, a->dxin2, X2, nullptr, 0, 0);
+    if (rc) return rc;
+    cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+                                                 a->c1 + (size_t)t * Sd, (long long)U * Sd,
+                                                 t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, a->dxin2,
+                                                 (long long)X2, last ? nullptr : a->dxin1 + K1, (long long)X1,
+                                                 last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last);
+    rc = gemm_f32(st, B, X1, 4 * Sd, a->act1 + (size_t)t * 4 * Sd, U * 4 * Sd, 1, a->w1cat, X1, 0, a->dxin1, X1, nullptr, 0, 0);
+    if (rc) return rc;
+    AttnBwd g;
+    g.Tp = Tp; g.E = E; g.Sd = Sd; g.M = M;
+    g.dctx = a->dxin1 + Sd; g.dctx_ld = X1;
+    g.alpha = a->alpha + (size_t)t * Tp; g.alpha_ld = (long long)U * Tp;
+    g.q = a->q + (size_t)t * M; g.q_ld = (long long)U * M;
+    g.phi_w = a->phi_w; g.psi = a->psi; g.enc = a->enc; g.enc_lens = a->enc_lens;
+    g.denc = a->denc; g.dpsi = a->dpsi;
+    g.dqpre = a->dqpre + (size_t)t * M; g.dqpre_ld = (long long)U * M;
+    g.dh1att = a->dh1att;
+    attn_bwd_kernel<<<B, 256, attn_smem, st>>>(g);
+    emb_grad_add_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->dxin1, X1, a->tok_in + t, U, a->d_emb_w);
+  }
+  // weight gradients, batched over all steps
+  rc = gemm_f32(st, 4 * Sd, X1, B * U, a->act1, 4 * Sd, 0, a->xin1, X1, 0, a->d_w1cat, X1, nullptr, 0, 0);
+  if (rc) return rc;
+  rc = colsum(st, a->act1, a->d_b1, B * U, 4 * Sd, 4 * Sd, 0);
+  if (rc) return rc;
+  rc = gemm_f32(st, 4 * Sd, X2, B * U, a->act2, 4 * Sd, 0, a->xin2, X2, 0, a->d_w2cat, X2, nullptr, 0, 0);
+  if (rc) return rc;
+  rc = colsum(st, a->act2, a->d_b2, B * U, 4 * Sd, 4 * Sd, 0);
+  if (rc) return rc;
+  rc = gemm_f32(st, M, Sd, B * U, a->dqpre, M, 0, a->xin1 + K1, X1, 0, a->d_phi_w, Sd, nullptr, 0, 0);
+  if (rc) return rc;
+  dtanh_inplace_kernel<<<256, 256, 0, st>>>(a->dpsi, a->psi, (size_t)B * Tp * M);
+  rc = gemm_f32(st, M, E, B * Tp, a->dpsi, M, 0, a->enc, E, 0, a->d_psi_w, E, nullptr, 0, 0);
+  if (rc) return rc;
+  rc = colsum(st, a->dpsi, a->d_psi_b, B * Tp, M, M, 0);
+  if (rc) return rc;
+  rc = gemm_f32(st, B * Tp, E, M, a->dpsi, M, 1, a->psi_w, E, 0, a->denc, E, nullptr, 1, 0);
+  if (rc) return rc;
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+// Fused loss of trainer.py:426-434: per-utterance sum of CE(ignore_index=0) / count(y != 0), batch mean.
+//   logits [B,U,C], y int64 [B,L] (label of step t is y[:, t+1]); loss_b [B] scratch; loss_out scalar;
+//   dlogits [B,U,C] or null: d(loss * grad_scale)/dlogits.
+int ssasr_ce_loss_f32(const float* logits, const long long* y, int B, int U, int C, int L, float* loss_b, float* loss_out,
+                      float* dlogits, float grad_scale, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSASR_REQUIRE(L >= U + 1, "ce_loss: targets have %d columns, need at least U+1=%d", L, U + 1);
+  ce_kernel<<<B, 128, 0, st>>>(B, U, C, L, logits, y, loss_b, dlogits, grad_scale);
+  mean_kernel<<<1, 32, 0, st>>>(loss_b, B, loss_out);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,200 @@
+"""torch.autograd glue over the C ABI (include/ssasr.h).  PyTorch is used here for device memory, streams
+and the autograd graph only; every FLOP of the hot path is in libssasr.so."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# bidirectional LSTM layer
+# --------------------------------------------------------------------------------------------------
+class _BLSTM(torch.autograd.Function):
+    """One bidirectional LSTM layer over rows indexed (seq, batch) -- see ssasr_blstm_fwd_f32.
+
+    time_major=True : x [B, T_h, K], seq axis = dim 1 with per-utterance `lens` (packed-sequence semantics,
+                      asr.py:410-418).  T_h must be even and >= max(lens).
+    time_major=False: x [L, N, K], seq axis = dim 0, no lengths (encoder.blstm_4 quirk, asr.py:262)."""
+
+    @staticmethod
+    def forward(ctx, x, lens_dev, time_major, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        lib = _lib.load()
+        _lib.require_cuda(x, 'BLSTM')
+        x = _f32c(x)
+        d0, d1, K = x.shape
+        S = w_hh_f.shape[1]
+        dev = x.device
+        n_rows = d0 * d1
+        st = stream()
+        wih_p = torch.empty(8 * S, K, device=dev)
+        bias_p = torch.empty(8 * S, device=dev)
+        whh_p = torch.empty(2, 4 * S, S, device=dev)
+        whhT_p = torch.empty(2, S, 4 * S, device=dev)
+        ws = [_f32c(w) for w in (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
+        check(lib.ssasr_pack_blstm(*[ptr(w) for w in ws], S, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), ptr(whhT_p), st),
+              'ssasr_pack_blstm')
+        xp = torch.empty(n_rows, 8 * S, device=dev)
+        hout = torch.empty(d0, d1, 2 * S, device=dev)
+        cbuf = torch.empty(d0, d1, 2 * S, device=dev)
+        bar = torch.zeros(2, dtype=torch.int32, device=dev)
+        if time_major:
+            n_seq, n_batch, rs_seq, rs_batch = d1, d0, 1, d1
+        else:
+            n_seq, n_batch, rs_seq, rs_batch = d0, d1, d1, 1
+        check(lib.ssasr_blstm_fwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch, rs_seq,
+                                      rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
+                                      ptr(bar), st), 'ssasr_blstm_fwd_f32')
+        ctx.save_for_backward(x, wih_p, whhT_p, xp, hout, cbuf, lens_dev if time_major else torch.empty(0))
+        ctx.geom = (n_rows, K, S, n_seq, n_batch, rs_seq, rs_batch, time_major, d1)
+        ctx.need_dx = ctx.needs_input_grad[0]
+        return hout
+
+    @staticmethod
+    def backward(ctx, dhout):
+        lib = _lib.load()
+        x, wih_p, whhT_p, act, hout, cbuf, lens_dev = ctx.saved_tensors
+        n_rows, K, S, n_seq, n_batch, rs_seq, rs_batch, time_major, d1 = ctx.geom
+        dev = x.device
+        st = stream()
+        dhout = _f32c(dhout)
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        dwih_p = torch.empty(8 * S, K, device=dev)
+        dbias_p = torch.empty(8 * S, device=dev)
+        dwhh_p = torch.empty(2, 4 * S, S, device=dev)
+        dcs = torch.empty(n_batch, 2 * S, device=dev)
+        bar = torch.zeros(2, dtype=torch.int32, device=dev)
+        check(lib.ssasr_blstm_bwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
+                                      ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf), ptr(dhout),
+                                      ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
+                                      d1 if time_major else 0, st), 'ssasr_blstm_bwd_f32')
+        g = [torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev), torch.zeros(4 * S, device=dev),
+             torch.zeros(4 * S, device=dev), torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev),
+             torch.zeros(4 * S, device=dev), torch.zeros(4 * S, device=dev)]
+        check(lib.ssasr_unpack_blstm_grads(ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), S, K, *[ptr(t) for t in g], st),
+              'ssasr_unpack_blstm_grads')
+        return (dx, None, None) + tuple(g)
+
+
+def blstm(x, lens_dev, time_major, params):
+    return _BLSTM.apply(x, lens_dev, time_major, *params)
+
+
+# --------------------------------------------------------------------------------------------------
+# attend-and-spell loop
+# --------------------------------------------------------------------------------------------------
+class _Spell(torch.autograd.Function):
+    """U steps of attention + 2 LSTM cells + character projection (asr.py:65-110)."""
+
+    @staticmethod
+    def forward(ctx, enc, enc_lens_dev, tok_in, step_mode, seed, phi_w, psi_w, psi_b, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2,
+                w_hh2, b_ih2, b_hh2, emb_w, wc, bc):
+        lib = _lib.load()
+        _lib.require_cuda(enc, 'Speller')
+        enc = _f32c(enc)
+        B, Tp, E = enc.shape
+        Sd = w_hh1.shape[1]
+        M = phi_w.shape[0]
+        Cc = wc.shape[0]
+        U = tok_in.shape[1]
+        K1, X1, X2 = Sd + E, 2 * Sd + E, 2 * Sd
+        dev = enc.device
+        st = stream()
+        f = lambda *s: torch.empty(*s, device=dev)
+        w1cat, b1, w2cat, b2 = f(4 * Sd, X1), f(4 * Sd), f(4 * Sd, X2), f(4 * Sd)
+        check(lib.ssasr_pack_lstmcell(ptr(_f32c(w_ih1)), ptr(_f32c(w_hh1)), ptr(_f32c(b_ih1)), ptr(_f32c(b_hh1)), Sd, K1,
+                                      ptr(w1cat), ptr(b1), st), 'ssasr_pack_lstmcell')
+        check(lib.ssasr_pack_lstmcell(ptr(_f32c(w_ih2)), ptr(_f32c(w_hh2)), ptr(_f32c(b_ih2)), ptr(_f32c(b_hh2)), Sd, Sd,
+                                      ptr(w2cat), ptr(b2), st), 'ssasr_pack_lstmcell')
+        phi_w, psi_w, psi_b, emb_w, wc, bc = [_f32c(t) for t in (phi_w, psi_w, psi_b, emb_w, wc, bc)]
+        tok_in = tok_in.to(torch.int32).contiguous().clone()
+        psi, xin1, xin2 = f(B, Tp, M), f(B, U, X1), f(B, U, X2)
+        act1, act2, c1, c2, h2all = f(B, U, 4 * Sd), f(B, U, 4 * Sd), f(B, U, Sd), f(B, U, Sd), f(B, U, Sd)
+        q, alpha, logits = f(B, U, M), f(B, U, Tp), f(B, U, Cc)
+        modes = (C.c_int * U)(*[int(m) for m in step_mode])
+        a = _lib.SpellerFwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
+                                psi_b=ptr(psi_b), w1cat=ptr(w1cat), b1=ptr(b1), w2cat=ptr(w2cat), b2=ptr(b2),
+                                emb_w=ptr(emb_w), wc=ptr(wc), bc=ptr(bc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
+                                tok_in=ptr(tok_in), step_mode=C.cast(modes, C.c_void_p), seed=int(seed), psi=ptr(psi),
+                                xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
+                                h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits))
+        check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
+        ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
+                              c2, h2all, q, alpha)
+        ctx.dims = (B, Tp, E, Sd, M, Cc, U)
+        ctx.mark_non_differentiable(alpha, tok_in)
+        return logits, alpha, tok_in
+
+    @staticmethod
+    def backward(ctx, dlogits, _dalpha, _dtok):
+        lib = _lib.load()
+        (enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1, c2, h2all, q,
+         alpha) = ctx.saved_tensors
+        B, Tp, E, Sd, M, Cc, U = ctx.dims
+        K1, X1, X2 = Sd + E, 2 * Sd + E, 2 * Sd
+        dev = enc.device
+        st = stream()
+        f = lambda *s: torch.empty(*s, device=dev)
+        dlogits = _f32c(dlogits)
+        d_phi_w, d_psi_w, d_psi_b = f(M, Sd), f(M, E), f(M)
+        d_w1cat, d_b1, d_w2cat, d_b2 = f(4 * Sd, X1), f(4 * Sd), f(4 * Sd, X2), f(4 * Sd)
+        d_emb_w, d_wc, d_bc, denc = f(Cc, Sd), f(Cc, Sd), f(Cc), f(B, Tp, E)
+        scr = [f(B, U, Sd), f(B, X1), f(B, X2), f(B, Sd), f(B, Sd), f(B, Sd), f(B, Tp, M), f(B, U, M)]   # kept alive
+        a = _lib.SpellerBwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
+                                w1cat=ptr(w1cat), w2cat=ptr(w2cat), wc=ptr(wc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
+                                tok_in=ptr(tok_in), psi=ptr(psi), xin1=ptr(xin1), xin2=ptr(xin2), c1=ptr(c1), c2=ptr(c2),
+                                h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), act1=ptr(act1), act2=ptr(act2),
+                                dlogits=ptr(dlogits), d_phi_w=ptr(d_phi_w), d_psi_w=ptr(d_psi_w), d_psi_b=ptr(d_psi_b),
+                                d_w1cat=ptr(d_w1cat), d_b1=ptr(d_b1), d_w2cat=ptr(d_w2cat), d_b2=ptr(d_b2),
+                                d_emb_w=ptr(d_emb_w), d_wc=ptr(d_wc), d_bc=ptr(d_bc), denc=ptr(denc),
+                                dh2all=ptr(scr[0]), dxin1=ptr(scr[1]), dxin2=ptr(scr[2]), dc1s=ptr(scr[3]),
+                                dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]))
+        check(lib.ssasr_speller_bwd_f32(C.byref(a), st), 'ssasr_speller_bwd_f32')
+        z = lambda *s: torch.zeros(*s, device=dev)
+        g1 = [z(4 * Sd, K1), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
+        g2 = [z(4 * Sd, Sd), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
+        check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w1cat), ptr(d_b1), Sd, K1, *[ptr(t) for t in g1], st), 'unpack1')
+        check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w2cat), ptr(d_b2), Sd, Sd, *[ptr(t) for t in g2], st), 'unpack2')
+        return (denc, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
+
+
+def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params):
+    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, *params)
+
+
+# --------------------------------------------------------------------------------------------------
+# loss
+# --------------------------------------------------------------------------------------------------
+class _ASRLoss(torch.autograd.Function):
+    """trainer.py:426-434 in one kernel, gradient included."""
+
+    @staticmethod
+    def forward(ctx, logits, y):
+        lib = _lib.load()
+        _lib.require_cuda(logits, 'asr_loss')
+        logits = _f32c(logits)
+        y = y.to(torch.int64).contiguous()
+        B, U, Cc = logits.shape
+        L = y.shape[1]
+        loss_b = torch.empty(B, device=logits.device)
+        loss = torch.empty((), device=logits.device)
+        dlogits = torch.empty_like(logits)
+        check(lib.ssasr_ce_loss_f32(ptr(logits), ptr(y), B, U, Cc, L, ptr(loss_b), ptr(loss), ptr(dlogits), 1.0, stream()),
+              'ssasr_ce_loss_f32')
+        ctx.save_for_backward(dlogits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g, None
+
+
+def asr_loss(logits, y):
+    """loss of ASRTrainer.exec (trainer.py:426-434): logits [B,U,C], y [B,L] (label of step t = y[:, t+1])."""
+    return _ASRLoss.apply(logits, y)
