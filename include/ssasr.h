@@ -88,6 +88,14 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream);
 int ssasr_ce_loss_f32(const float* logits, const long long* y, int B, int U, int C, int L, float* loss_b /*[B]*/,
                       float* loss_out /*[1]*/, float* dlogits /*[B,U,C] or NULL*/, float grad_scale, void* stream);
 
+/* ---- launch accounting and per-family CUDA-event timing (used by bench.py; no reference counterpart) ---- */
+int ssasr_num_families(void);
+const char* ssasr_family_name(int i);
+long long ssasr_launch_count(void);
+void ssasr_launch_count_reset(void);
+void ssasr_profile_enable(int enable);
+int ssasr_profile_read(double* ms /*[num_families]*/, long long* launches /*[num_families]*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,12 @@ SIGNATURES = {
     'ssasr_speller_fwd_f32': (_I, [C.POINTER(SpellerFwdArgs), _P]),
     'ssasr_speller_bwd_f32': (_I, [C.POINTER(SpellerBwdArgs), _P]),
     'ssasr_ce_loss_f32': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P]),
+    'ssasr_num_families': (_I, []),
+    'ssasr_family_name': (C.c_char_p, [_I]),
+    'ssasr_launch_count': (_LL, []),
+    'ssasr_launch_count_reset': (None, []),
+    'ssasr_profile_enable': (None, [_I]),
+    'ssasr_profile_read': (_I, [_P, _P]),
 }
 
 
@@ -96,3 +102,13 @@ def require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError('%s: the ss_asr_b200 hot path runs on a CUDA device only (got a %s tensor); there is '
                            'no CPU fallback' % (what, t.device))
+
+
+def profile_read():
+    """-> {family: (total_ms, launches)} since the last read (synchronises the device)."""
+    lib = load()
+    n = lib.ssasr_num_families()
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(lib.ssasr_profile_read(C.cast(ms, C.c_void_p), C.cast(cnt, C.c_void_p)), 'ssasr_profile_read')
+    return {lib.ssasr_family_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}

@@ -66,6 +66,15 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 
 int sm_count();
 
+// Launch accounting / optional per-family CUDA-event timing (bench.py reads it through ssasr_profile_*).
+enum Family { F_GEMM_F32 = 0, F_REC_FWD, F_REC_BWD, F_ATTN_FWD, F_ATTN_BWD, F_POINTWISE, F_CE, F_FBANK, F_PACK,
+              F_GEMM_TC, F_REC_TC_FWD, F_REC_TC_BWD, F_OPTIM, F_COUNT };
+struct ProfScope {
+  int fam; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(int family, cudaStream_t stream);
+  ~ProfScope();
+};
+
 // internal fp32 GEMM launcher (gemm_f32.cu): C[M,N] = (accumulate ? C : 0) + op(A) * op(B) (+ bias[N]) (+tanh)
 //   a_kmajor: element A(m,k) at A[m*lda + k] (1) or A[k*lda + m] (0)
 //   b_kmajor: element B(k,n) at B[n*ldb + k] (1, the "weights [N,K]" form) or B[k*ldb + n] (0)

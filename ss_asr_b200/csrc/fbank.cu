@@ -297,6 +297,7 @@ int ssasr_fbank(const float* audio, const long long* offsets, int n_utt, int sam
   SSASR_REQUIRE(smem <= 227 * 1024, "fbank: window of %d samples needs %zu B shared memory", t.ws, smem);
   SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((max_frames + FPB - 1) / FPB, n_utt);
+  ProfScope ps(F_FBANK, st);
   fbank_kernel<<<grid, NT, smem, st>>>(p);
   SSASR_LAUNCH_CHECK();
   return 0;

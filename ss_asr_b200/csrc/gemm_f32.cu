@@ -104,6 +104,7 @@ int gemm_f32(cudaStream_t st, int M, int N, int K, const float* A, int lda, int 
   if (M <= 0 || N <= 0) return 0;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   SSASR_REQUIRE(grid.y <= 65535, "gemm_f32: N=%d too large for grid.y", N);
+  ProfScope ps(F_GEMM_F32, st);
   gemm_f32_kernel<<<grid, 256, 0, st>>>(M, N, K, A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, bias, accumulate, act_tanh,
                                         zero_period, zero_pos);
   SSASR_LAUNCH_CHECK();

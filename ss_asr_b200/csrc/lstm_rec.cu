@@ -318,6 +318,7 @@ __global__ void colsum_kernel(const float* __restrict__ src, float* __restrict__
 }
 
 int colsum(cudaStream_t st, const float* src, float* out, int R, int C, int ld, int accumulate) {
+  ProfScope ps(F_POINTWISE, st);
   colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(src, out, R, C, ld, accumulate);
   SSASR_LAUNCH_CHECK();
   return 0;
@@ -338,6 +339,7 @@ static int launch_fwd(RecFwdParams& p, cudaStream_t st) {
   dim3 grid(p.S / UPC, 2);
   SSASR_REQUIRE((int)(grid.x * 2) <= per_sm * sm_count(), "rec_fwd: %d CTAs cannot be co-resident (S=%d)", grid.x * 2, p.S);
   void* args[] = {&p};
+  ProfScope ps(F_REC_FWD, st);
   SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_fwd_kernel<UPC>, grid, dim3(256), args, smem, st));
   return 0;
 }
@@ -350,6 +352,7 @@ static int launch_bwd(RecBwdParams& p, cudaStream_t st) {
   dim3 grid(p.S / UPC, 2);
   SSASR_REQUIRE((int)(grid.x * 2) <= per_sm * sm_count(), "rec_bwd: %d CTAs cannot be co-resident (S=%d)", grid.x * 2, p.S);
   void* args[] = {&p};
+  ProfScope ps(F_REC_BWD, st);
   SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_bwd_kernel<UPC>, grid, dim3(256), args, smem, st));
   return 0;
 }
@@ -371,6 +374,7 @@ int ssasr_pack_blstm(const float* w_ih_f, const float* w_hh_f, const float* b_ih
   const float* whh[2] = {w_hh_f, w_hh_r};
   const float* bih[2] = {b_ih_f, b_ih_r};
   const float* bhh[2] = {b_hh_f, b_hh_r};
+  ProfScope ps(F_PACK, st);
   for (int d = 0; d < 2; ++d) {
     pack_rows_kernel<<<256, 256, 0, st>>>(wih[d], wih_p + (size_t)d * 4 * S * K, S, K, K, 0);
     pack_rows_kernel<<<256, 256, 0, st>>>(whh[d], whh_p + (size_t)d * 4 * S * S, S, S, S, 0);
@@ -392,6 +396,7 @@ int ssasr_unpack_blstm_grads(const float* dwih_p, const float* dbias_p, const fl
   float* gwhh[2] = {g_w_hh_f, g_w_hh_r};
   float* gbih[2] = {g_b_ih_f, g_b_ih_r};
   float* gbhh[2] = {g_b_hh_f, g_b_hh_r};
+  ProfScope ps(F_PACK, st);
   for (int d = 0; d < 2; ++d) {
     unpack_rows_add_kernel<<<256, 256, 0, st>>>(dwih_p + (size_t)d * 4 * S * K, gwih[d], S, K, K, 0);
     unpack_rows_add_kernel<<<256, 256, 0, st>>>(dwhh_p + (size_t)d * 4 * S * S, gwhh[d], S, S, S, 0);
@@ -406,6 +411,7 @@ int ssasr_unpack_blstm_grads(const float* dwih_p, const float* dbias_p, const fl
 int ssasr_pack_lstmcell(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int S, int Kin,
                         float* wcat, float* bcat, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(F_PACK, st);
   pack_rows_kernel<<<256, 256, 0, st>>>(w_ih, wcat, S, Kin, Kin + S, 0);
   pack_rows_kernel<<<256, 256, 0, st>>>(w_hh, wcat, S, S, Kin + S, Kin);
   pack_bias_kernel<<<(4 * S + 255) / 256, 256, 0, st>>>(b_ih, b_hh, bcat, S);
@@ -415,6 +421,7 @@ int ssasr_pack_lstmcell(const float* w_ih, const float* w_hh, const float* b_ih,
 int ssasr_unpack_lstmcell_grads(const float* dwcat, const float* dbcat, int S, int Kin, float* g_w_ih, float* g_w_hh,
                                 float* g_b_ih, float* g_b_hh, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(F_PACK, st);
   unpack_rows_add_kernel<<<256, 256, 0, st>>>(dwcat, g_w_ih, S, Kin, Kin + S, 0);
   unpack_rows_add_kernel<<<256, 256, 0, st>>>(dwcat, g_w_hh, S, S, Kin + S, Kin);
   unpack_bias_add_kernel<<<(4 * S + 255) / 256, 256, 0, st>>>(dbcat, g_b_ih, g_b_hh, S);

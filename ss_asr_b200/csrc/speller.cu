@@ -346,11 +346,12 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     f.xin1 = a->xin1 + (size_t)t * X1; f.xin1_ld = (long long)U * X1;
     f.q = a->q + (size_t)t * M; f.q_ld = (long long)U * M;
     f.alpha = a->alpha + (size_t)t * Tp; f.alpha_ld = (long long)U * Tp;
-    attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f);
+    { ProfScope ps(F_ATTN_FWD, st); attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f); }
     // layer 1
     rc = gemm_f32(st, B, 4 * Sd, X1, a->xin1 + (size_t)t * X1, U * X1, 1, a->w1cat, X1, 1, a->act1 + (size_t)t * 4 * Sd,
                   U * 4 * Sd, a->b1, 0, 0);
     if (rc) return rc;
+    { ProfScope ps(F_POINTWISE, st); }
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd, a->xin2 + (size_t)t * X2,
@@ -360,6 +361,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     rc = gemm_f32(st, B, 4 * Sd, X2, a->xin2 + (size_t)t * X2, U * X2, 1, a->w2cat, X2, 1, a->act2 + (size_t)t * 4 * Sd,
                   U * 4 * Sd, a->b2, 0, 0);
     if (rc) return rc;
+    { ProfScope ps(F_POINTWISE, st); }
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c2 + (size_t)t * Sd, (long long)U * Sd, a->h2all + (size_t)t * Sd,
@@ -369,6 +371,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
       rc = gemm_f32(st, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
                     0, 0);
       if (rc) return rc;
+      { ProfScope ps(F_POINTWISE, st); }
       pick_token_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
                                                          (unsigned long long)t, a->tok_in + t + 1, U);
     }
@@ -418,6 +421,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   const int cell_blocks = (B * Sd + 255) / 256;
   for (int t = U - 1; t >= 0; --t) {
     const int last = (t == U - 1);
+    { ProfScope ps(F_POINTWISE, st); }
     cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  a->c2 + (size_t)t * Sd, (long long)U * Sd,
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
@@ -425,6 +429,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                                                  (long long)X2, nullptr, 0, a->dc2s, last);
     rc = gemm_f32(st, B, X2, 4 * Sd, a->act2 + (size_t)t * 4 * Sd, U * 4 * Sd, 1, a->w2cat, X2, 0, a->dxin2, X2, nullptr, 0, 0);
     if (rc) return rc;
+    { ProfScope ps(F_POINTWISE, st); }
     cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, a->dxin2,
@@ -441,7 +446,8 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     g.denc = a->denc; g.dpsi = a->dpsi;
     g.dqpre = a->dqpre + (size_t)t * M; g.dqpre_ld = (long long)U * M;
     g.dh1att = a->dh1att;
-    attn_bwd_kernel<<<B, 256, attn_smem, st>>>(g);
+    { ProfScope ps(F_ATTN_BWD, st); attn_bwd_kernel<<<B, 256, attn_smem, st>>>(g); }
+    { ProfScope ps(F_POINTWISE, st); }
     emb_grad_add_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->dxin1, X1, a->tok_in + t, U, a->d_emb_w);
   }
   // weight gradients, batched over all steps
@@ -455,6 +461,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   if (rc) return rc;
   rc = gemm_f32(st, M, Sd, B * U, a->dqpre, M, 0, a->xin1 + K1, X1, 0, a->d_phi_w, Sd, nullptr, 0, 0);
   if (rc) return rc;
+  { ProfScope ps(F_POINTWISE, st); }
   dtanh_inplace_kernel<<<256, 256, 0, st>>>(a->dpsi, a->psi, (size_t)B * Tp * M);
   rc = gemm_f32(st, M, E, B * Tp, a->dpsi, M, 0, a->enc, E, 0, a->d_psi_w, E, nullptr, 0, 0);
   if (rc) return rc;
@@ -473,6 +480,7 @@ int ssasr_ce_loss_f32(const float* logits, const long long* y, int B, int U, int
                       float* dlogits, float grad_scale, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(L >= U + 1, "ce_loss: targets have %d columns, need at least U+1=%d", L, U + 1);
+  ProfScope ps(F_CE, st);
   ce_kernel<<<B, 128, 0, st>>>(B, U, C, L, logits, y, loss_b, dlogits, grad_scale);
   mean_kernel<<<1, 32, 0, st>>>(loss_b, B, loss_out);
   SSASR_LAUNCH_CHECK();

@@ -1,0 +1,276 @@
+"""Parity of the CUDA path (through the C ABI, libssasr.so) against the CPU oracle and the committed golden
+vectors of the unmodified reference.  Needs a B200: `pytest -m gpu`.
+
+Tolerances (fp32 path): logits/attention atol 1e-5, loss rel 1e-6 (+1e-6 abs), gradients
+rel-L2 1e-4 with an absolute floor of 1e-6 * global grad norm, fbank atol 1e-4 in the log domain, greedy
+token sequences identical."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fbank_oracle as FB
+from oracle import las_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _model(dims, sd, tf=1.0):
+    from ss_asr_b200.asr import ASR
+    m = ASR(*dims, tf).to(DEV)
+    m.load_state_dict(sd)
+    return m
+
+
+def _check_grads(model, ref_grads, rel=1e-4):
+    gtot = float(torch.sqrt(sum(torch.as_tensor(v).double().pow(2).sum() for v in ref_grads.values())))
+    for k, p in model.named_parameters():
+        want = torch.as_tensor(ref_grads[k]).double()
+        d = float((p.grad.cpu().double() - want).norm())
+        assert d <= rel * float(want.norm()) + 1e-6 * gtot, (k, d, float(want.norm()))
+
+
+# ------------------------------------------------------------------------------------------------ library
+def test_library_loaded_is_in_tree():
+    from ss_asr_b200 import _lib
+    _lib.load()
+    assert os.path.samefile(_lib.lib_path(), os.path.join(os.path.dirname(os.path.dirname(__file__)), 'ss_asr_b200',
+                                                          'libssasr.so'))
+    with open('/proc/self/maps') as f:
+        assert 'libssasr.so' in f.read()
+
+
+def test_cpu_tensors_fail_loudly():
+    sd = O.make_state_dict(50, 16, 16, 8, 12, seed=1)
+    from ss_asr_b200.asr import ASR
+    m = ASR(50, 16, 16, 8, 12, 1.0)
+    m.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.randn(2, 16, 12), 3, state_len=[16, 16])
+
+
+@pytest.mark.parametrize('M,N,K,akm,bkm', [(70, 50, 33, 1, 1), (128, 64, 80, 1, 0), (65, 130, 257, 0, 0), (1, 7, 5, 1, 1),
+                                           (40, 24, 500, 0, 1)])
+def test_gemm_f32(M, N, K, akm, bkm):
+    from ss_asr_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A, B, bias = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g), torch.randn(N, generator=g)
+    ref = (A.double() @ B.double() + bias.double())
+    Ad = (A if akm else A.t().contiguous()).to(DEV)
+    Bd = (B.t().contiguous() if bkm else B).to(DEV)
+    Cd = torch.empty(M, N, device=DEV)
+    _lib.check(lib.ssasr_gemm_f32(M, N, K, Ad.data_ptr(), K if akm else M, akm, Bd.data_ptr(), K if bkm else N, bkm,
+                                  Cd.data_ptr(), N, bias.to(DEV).data_ptr(), 0, 0, _lib.stream()), 'gemm')
+    assert float((Cd.cpu().double() - ref).abs().max()) < 1e-5 * K ** 0.5 * 4
+
+
+# ------------------------------------------------------------------------------------------------ fbank
+def test_fbank_golden(golden_dir):
+    from ss_asr_b200 import preprocess as PP
+    z = np.load(os.path.join(golden_dir, 'fbank_1s.npz'))
+    assert np.abs(PP.log_fbank_batch([z['y16']], 16000, 80)[0] - z['fb16_80']).max() < 1e-4
+    assert np.abs(PP.log_fbank_batch([z['y16']], 16000, 40)[0] - z['fb16_40']).max() < 1e-4
+    assert np.abs(PP.log_fbank(z['y16'][:11025], 22050) - z['fb22_40']).max() < 1e-4     # reference defaults
+
+
+def test_fbank_ragged_batch_and_edges():
+    from ss_asr_b200 import preprocess as PP
+    rng = np.random.RandomState(3)
+    ns = [16000, 8000, 12345, 401, 201, 3200, 160000, 1599, 1600, 1601]
+    ys = [(0.1 * rng.randn(n)).astype(np.float32) for n in ns]
+    ys[3][:] = 0.0                                                   # digital silence -> log(eps)
+    outs = PP.log_fbank_batch(ys, 16000, 80)
+    for y, o in zip(ys, outs):
+        w = FB.log_fbank(y, 16000, 80)
+        assert o.shape == w.shape and o.dtype == np.float32
+        assert np.abs(o - w).max() < 1e-4
+    assert np.allclose(outs[3], np.log(np.finfo(float).eps))
+    with pytest.raises(ValueError):
+        PP.log_fbank_batch([np.zeros(200, np.float32)], 16000, 80)  # numpy reflect pad needs > ws//2 samples
+
+
+def test_fbank_full_size_properties():
+    """C2 shape (160 000-sample utterances): linearity in the power domain and agreement with the oracle on
+    sampled utterances."""
+    from ss_asr_b200 import preprocess as PP
+    g = torch.Generator().manual_seed(1234)
+    n_utt, n = 64, 160000
+    audio = (0.1 * torch.randn(n_utt * n, generator=g)).to(DEV)
+    off = [i * n for i in range(n_utt + 1)]
+    out, foff = PP.log_fbank_device(audio, off, 16000, 80)
+    assert out.shape == (n_utt * 1001, 80) and foff[1] == 1001
+    out2, _ = PP.log_fbank_device(audio * 2.0, off, 16000, 80)
+    assert float((out2 - out - np.log(4.0)).abs().max()) < 1e-4      # power scales by 4 -> log shifts by ln 4
+    for u in (0, 17, 63):
+        w = FB.log_fbank(audio[u * n:(u + 1) * n].cpu().numpy(), 16000, 80)
+        assert np.abs(out[u * 1001:(u + 1) * 1001].cpu().numpy() - w).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ LAS
+def test_tiny_golden_forward_loss_grads(golden_dir):
+    from ss_asr_b200.functional import asr_loss
+    z = np.load(os.path.join(golden_dir, 'las_tiny.npz'))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}
+    dims = tuple(int(v) for v in z['dims'])
+    x, lens, y = torch.from_numpy(z['x']), [int(v) for v in z['lens']], torch.from_numpy(z['y'])
+    m = _model(dims, sd)
+    enc, el = m.encoder(x.to(DEV), lens)
+    assert el == [int(v) for v in z['enc_len']] and tuple(enc.shape) == z['enc'].shape
+    assert np.abs(enc.detach().cpu().numpy() - z['enc']).max() < 1e-5
+    U = z['logits'].shape[1]
+    el, logits, att = m(x.to(DEV), U, teacher=y.to(DEV), state_len=lens)
+    assert not att.is_cuda and logits.is_cuda                        # reference return convention (asr.py:103,110)
+    assert np.abs(logits.detach().cpu().numpy() - z['logits']).max() < 1e-5
+    assert np.abs(att.numpy() - z['att']).max() < 1e-5
+    loss = asr_loss(logits, y.to(DEV))
+    assert abs(float(loss) - float(z['loss'])) < 1e-6 * float(z['loss']) + 1e-6
+    loss.backward()
+    _check_grads(m, {k: z['grad.' + k] for k in sd})
+
+
+def test_tiny_golden_loss_through_torch_cross_entropy(golden_dir):
+    """The unchanged trainer.py:426-434 loss code (torch CrossEntropyLoss) on our logits gives the same grads."""
+    z = np.load(os.path.join(golden_dir, 'las_tiny.npz'))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}
+    x, lens, y = torch.from_numpy(z['x']), [int(v) for v in z['lens']], torch.from_numpy(z['y']).to(DEV)
+    m = _model(tuple(int(v) for v in z['dims']), sd)
+    ans_len = z['logits'].shape[1]
+    _, pred, _ = m(x.to(DEV), ans_len, teacher=y, state_len=lens)
+    label = y[:, 1:ans_len + 1].contiguous()
+    b, t, c = pred.shape
+    loss = torch.nn.CrossEntropyLoss(ignore_index=0, reduction='none')(pred.view(b * t, c), label.view(-1))
+    loss = torch.mean(torch.sum(loss.view(b, t), dim=-1) / torch.sum(y != 0, dim=-1).to(dtype=torch.float32))
+    loss.backward()
+    assert abs(float(loss) - float(z['loss'])) < 1e-5
+    _check_grads(m, {k: z['grad.' + k] for k in sd})
+
+
+def test_tiny_golden_greedy_and_decode(golden_dir):
+    z = np.load(os.path.join(golden_dir, 'las_tiny.npz'))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd.')}
+    x, lens = torch.from_numpy(z['x']), [int(v) for v in z['lens']]
+    m = _model(tuple(int(v) for v in z['dims']), sd)
+    U = z['greedy_logits'].shape[1]
+    with torch.no_grad():
+        _, gl, ga = m(x.to(DEV), U, state_len=lens)
+    assert np.array_equal(gl.argmax(-1).cpu().numpy(), z['greedy_logits'].argmax(-1))
+    assert np.abs(gl.cpu().numpy() - z['greedy_logits']).max() < 1e-4
+    assert np.abs(ga.numpy() - z['greedy_att']).max() < 1e-5
+
+    class Mapper:
+        def ind_to_char(self, i):
+            return O.TOKENS[i]
+    for i in range(len(z['decode_lm0'])):
+        xi = x[i:i + 1, :lens[i]].to(DEV)
+        assert m.decode(xi, [lens[i]], None, Mapper(), 0.0) == str(z['decode_lm0'][i])
+
+
+def test_default_dims_golden(golden_dir):
+    from ss_asr_b200.functional import asr_loss
+    z = np.load(os.path.join(golden_dir, 'las_default.npz'))
+    dims = (50, 256, 256, 128, 80)
+    torch.manual_seed(1)
+    from ss_asr_b200.asr import ASR
+    m = ASR(*dims, 1.0).to(DEV)                                       # same init stream as the reference
+    x, lens, y = O.synth_batch(int(z['B']), int(z['T']), int(z['F']), int(z['U']), seed=1234)
+    U = z['logits'].shape[1]
+    el, logits, att = m(x.to(DEV), U, teacher=y.to(DEV), state_len=lens)
+    assert el == [int(v) for v in z['enc_len']]
+    assert np.abs(logits.detach().cpu().numpy() - z['logits']).max() < 1e-5
+    assert np.abs(att.numpy() - z['att']).max() < 1e-5
+    loss = asr_loss(logits, y.to(DEV))
+    assert abs(float(loss) - float(z['loss'])) < 1e-6 * float(z['loss']) + 1e-6
+    loss.backward()
+    gtot = float(z['gnorm_total'])
+    for k, p in m.named_parameters():
+        g = p.grad.cpu()
+        assert abs(float(g.double().norm()) - float(z['gnorm.' + k])) <= 1e-4 * float(z['gnorm.' + k]) + 1e-6 * gtot, k
+        assert np.abs(g.flatten()[:256].numpy() - z['ghead.' + k]).max() <= 1e-4 * np.abs(z['ghead.' + k]).max() + 1e-6 * gtot, k
+
+
+@pytest.mark.parametrize('dims,B,T,U,lens', [
+    ((50, 32, 48, 16, 20), 7, 64, 9, None),
+    ((50, 16, 32, 8, 10), 6, 91, 7, [91, 90, 75, 50, 23, 8]),        # odd T at every layer, length-1 encoder rows
+    ((50, 48, 16, 24, 40), 1, 40, 5, [40]),                           # batch of one
+    ((50, 16, 16, 8, 12), 70, 24, 4, None),                           # more utterances than one 64-row tile
+])
+def test_oracle_parity_shapes(dims, B, T, U, lens):
+    from ss_asr_b200.functional import asr_loss
+    sd = O.make_state_dict(*dims, seed=3)
+    if lens is None:
+        x, lens, y = O.synth_batch(B, T, dims[4], U, seed=77)
+    else:
+        x, _, y = O.synth_batch(B, T, dims[4], U, seed=77)
+        for i, l in enumerate(lens):
+            x[i, l:] = 0
+            x[i, :l] += 0.01
+    loss_o, logits_o, att_o, enc_o, grads_o = O.train_step_grads(sd, x, lens, y)
+    m = _model(dims, sd)
+    ans_len = logits_o.shape[1]
+    el, logits, att = m(x.to(DEV), ans_len, teacher=y.to(DEV), state_len=lens)
+    assert float((logits.detach().cpu() - logits_o).abs().max()) < 1e-5
+    assert float((att - att_o).abs().max()) < 1e-5
+    loss = asr_loss(logits, y.to(DEV))
+    assert abs(float(loss) - float(loss_o)) < 1e-6 * float(loss_o) + 1e-6
+    loss.backward()
+    _check_grads(m, grads_o)
+
+
+def test_blstm4_batch_coupling_quirk():
+    """layer 4 recurs across utterances; perturbing the last utterance changes the first."""
+    dims = (50, 16, 16, 8, 12)
+    sd = O.make_state_dict(*dims, seed=1)
+    m = _model(dims, sd)
+    x, lens, _ = O.synth_batch(4, 32, 12, 4, seed=5)
+    with torch.no_grad():
+        e1, _ = m.encoder(x.to(DEV), lens)
+        x2 = x.clone()
+        x2[3, :lens[3]] += 0.5
+        e2, _ = m.encoder(x2.to(DEV), lens)
+        o2, _ = O.listener(sd, x2, lens)
+    assert float((e1[0] - e2[0]).abs().max()) > 1e-4
+    assert float((e2.cpu() - o2).abs().max()) < 1e-5
+
+
+def test_decode_default_margin_strings(golden_dir):
+    """Greedy transcripts identical to the unmodified reference's ASR.decode (bs=1 semantics, batched here)."""
+    z = np.load(os.path.join(golden_dir, 'decode_default.npz'))
+    sd = O.make_state_dict(50, 256, 256, 128, 80, seed=1)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 20.0
+    m = _model((50, 256, 256, 128, 80), sd)
+    Ts = [int(v) for v in z['Ts']]
+    xs = [torch.randn(1, Ti, 80, generator=torch.Generator().manual_seed(7000 + i)) for i, Ti in enumerate(Ts)]
+    order = sorted(range(len(Ts)), key=lambda i: -Ts[i])
+    xb = torch.zeros(len(Ts), max(Ts), 80)
+    for j, i in enumerate(order):
+        xb[j, :Ts[i]] = xs[i][0]
+    ids = m.decode_batch(xb.to(DEV), [Ts[i] for i in order])
+    for j, i in enumerate(order):
+        assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
+
+
+def test_teacher_forcing_draws_follow_python_rng():
+    """tf_rate < 1: one random.random() per step, like asr.py:94; sampled steps replayed through the oracle."""
+    import random
+    dims = (50, 16, 16, 8, 12)
+    sd = O.make_state_dict(*dims, seed=1)
+    m = _model(dims, sd, tf=0.5)
+    x, lens, y = O.synth_batch(4, 32, 12, 8, seed=5)
+    random.seed(11)
+    _, logits, att = m(x.to(DEV), 9, teacher=y.to(DEV), state_len=lens)
+    after = random.random()
+    random.seed(11)
+    mask = [random.random() <= 0.5 for _ in range(9)]
+    assert random.random() == after and not all(mask) and any(mask)
+    toks = m.last_tokens.cpu().long()                               # input token of every step
+    sampled = torch.zeros(4, 9, dtype=torch.long)
+    sampled[:, :8] = toks[:, 1:]
+    with torch.no_grad():
+        _, lo, ao, _ = O.asr_forward(sd, x, lens, 9, teacher=y, tf_mask=mask, sampled=sampled)
+    assert float((logits.detach().cpu() - lo).abs().max()) < 1e-5
+    for t in range(8):
+        if mask[t]:
+            assert torch.equal(toks[:, t + 1], y[:, t + 1])
