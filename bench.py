@@ -206,6 +206,8 @@ def run_ours(args):
     torch.manual_seed(1)
     random.seed(1)
     model = ASR(tf_rate=0.9, **DIMS).to(dev)
+    model.train_precision = args.precision
+    model.train()
     optim = torch.optim.Adadelta(model.parameters(), lr=1.0, eps=1e-8)
     sync = GradSync(model, world)
     x, lens, y = synth_batch(B, T, F, U, seed=1234 + rank)
@@ -313,7 +315,8 @@ def run_ours(args):
     if rank == 0:
         line = {'metric': 'asr_train_utt_per_s', 'value': value, 'unit': 'utt/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
                 'config': workload_config(world) if not args.small else dict(workload_config(world), small=cfg),
                 'clocks': clocks,
                 'e2e': {'value': e2e_value, 'unit': 'utt/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -389,6 +392,8 @@ def main():
     ap.add_argument('--small', action='store_true', help='debug-sized shapes (not a bench number)')
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help='bf16: tcgen05 gate GEMMs (fp32 accumulate, fp32 recurrence); fp32: exact SIMT path')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -55,6 +55,27 @@ int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
                         float* dwhh_p, float* dcstate /*[n_batch,2S] scratch*/, unsigned* bar, int zero_period,
                         void* stream);
 
+/* ---- bf16 tensor-core path (tcgen05 + TMA) for the batched-over-time gate GEMMs of training:
+ *      C[M,N] fp32 (+)= A[M,K] x B[N,K]^T (+bias); A, B bf16 with K contiguous, 16-byte aligned base and row pitch;
+ *      a_koff / b_koff shift the reduction window inside the operands' rows.  Replaces the GEMMs cuDNN/ATen run
+ *      inside nn.LSTM forward/backward (asr.py:414,262; trainer.py:437). ---- */
+int ssasr_gemm_bf16_tc(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
+                       int b_koff, float* C, int ldc, const float* bias, int accumulate, void* stream);
+int ssasr_cvt_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream);
+int ssasr_cvt_bf16_t(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
+                     int mask_period, int mask_pos_lo, int mask_pos_hi, int mask_split, void* stream);
+/* same contracts as ssasr_blstm_fwd_f32 / _bwd_f32 plus caller-provided bf16 operands and workspaces */
+int ssasr_blstm_fwd_bf16(const float* x, int n_rows, int K, int Kp, const void* wih_bf /*[8S,Kp]*/, const float* bias_p,
+                         const float* whh_p, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch,
+                         const int* lens, void* xb_ws /*[n_rows,Kp]*/, float* xp, float* hout, float* cbuf, unsigned* bar,
+                         void* stream);
+int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf /*[K,8S]*/, const float* whhT_p, int S,
+                         int n_seq, int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* act,
+                         const float* hout, const float* cbuf, const float* dhout, float* dx, float* dwih_p,
+                         float* dbias_p, float* dwhh_p, float* dcstate, unsigned* bar, int zero_period, long long Rp,
+                         void* dgb_ws /*[n_rows,8S]*/, void* dgT_ws /*[8S,Rp]*/, void* xT_ws /*[K,Rp]*/,
+                         void* hT_ws /*[2S,Rp]*/, void* stream);
+
 /* ---- attend-and-spell loop: Attention.forward asr.py:343-392 + Speller.forward asr.py:314-326 + the decode loop
  *      of ASR.forward asr.py:65-110 (teacher forcing / greedy / sampled), all U steps on the device ---- */
 typedef struct {

@@ -34,6 +34,65 @@ def gemm_check():
         print('gemm', (M, N, K, akm, bkm), 'max err', float((Cd.cpu().double() - ref).abs().max()))
 
 
+def tc_check():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K, ak, bk) in [(128, 128, 64, 0, 0), (256, 256, 256, 0, 0), (300, 200, 80, 0, 0), (1024, 2048, 1024, 0, 0),
+                              (128, 128, 512, 16, 0), (256, 128, 1000, 0, 8), (2048, 80, 4096, 0, 0)]:
+        Kt = K + max(ak, bk)
+        Kp = (Kt + 7) // 8 * 8
+        A = torch.randn(M, Kp, generator=g).to(dev)
+        B = torch.randn(N, Kp, generator=g).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        Ab, Bb = A.to(torch.bfloat16), B.to(torch.bfloat16)
+        ref = Ab[:, ak:ak + K].double() @ Bb[:, bk:bk + K].double().t() + bias.double()
+        C = torch.zeros(M, N, device=dev)
+        _lib.check(lib.ssasr_gemm_bf16_tc(M, N, K, Ab.data_ptr(), Kp, ak, Bb.data_ptr(), Kp, bk, C.data_ptr(), N,
+                                          bias.data_ptr(), 0, _lib.stream()), 'gemm_tc')
+        torch.cuda.synchronize()
+        print('gemm_tc', (M, N, K, ak, bk), 'max err', float((C.double() - ref).abs().max()), 'ref max', float(ref.abs().max()))
+    # throughput
+    M, N, K = 131072, 2048, 1024
+    Ab = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    Bb = torch.randn(N, K, device=dev).to(torch.bfloat16)
+    C = torch.empty(M, N, device=dev)
+    for _ in range(2):
+        lib.ssasr_gemm_bf16_tc(M, N, K, Ab.data_ptr(), K, 0, Bb.data_ptr(), K, 0, C.data_ptr(), N, None, 0, _lib.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        lib.ssasr_gemm_bf16_tc(M, N, K, Ab.data_ptr(), K, 0, Bb.data_ptr(), K, 0, C.data_ptr(), N, None, 0, _lib.stream())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print('gemm_tc %dx%dx%d: %.3f ms, %.1f TFLOP/s' % (M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
+
+
+def bf16_check(dims=(50, 256, 256, 128, 80), B=8, T=128, U=20):
+    sd = O.make_state_dict(*dims, seed=1)
+    x, lens, y = O.synth_batch(B, T, dims[4], U, seed=1234)
+    loss_o, logits_o, att_o, enc_o, grads_o = O.train_step_grads(sd, x, lens, y)
+    m = ASR(*dims, 1.0).to(dev)
+    m.load_state_dict(sd)
+    m.train_precision = 'bf16'
+    m.train()
+    ans_len = logits_o.shape[1]
+    el, logits, att = m(x.to(dev), ans_len, teacher=y.to(dev), state_len=lens)
+    print('bf16 logits max err', float((logits.detach().cpu() - logits_o).abs().max()), 'att', float((att - att_o).abs().max()))
+    loss = Fk.asr_loss(logits, y.to(dev))
+    print('bf16 loss', float(loss), float(loss_o))
+    loss.backward()
+    worst = 0
+    for k, p in m.named_parameters():
+        a, b = p.grad.cpu().double(), grads_o[k].double()
+        rel = float((a - b).norm() / (b.norm() + 1e-12))
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+        worst = max(worst, rel)
+        if rel > 1e-2:
+            print('  grad', k, 'rel', rel, 'cos', cos)
+    print('bf16 worst grad rel-L2', worst)
+
+
 def fbank_check():
     z = np.load(os.path.join(ROOT, 'tests/golden/fbank_1s.npz'))
     for n_mels, key in ((80, 'fb16_80'), (40, 'fb16_40')):
@@ -113,6 +172,11 @@ if __name__ == '__main__':
     which = sys.argv[1:] or ['gemm', 'fbank', 'tiny', 'default', 'decode']
     if 'gemm' in which:
         gemm_check()
+    if 'tc' in which:
+        tc_check()
+    if 'bf16' in which:
+        bf16_check()
+        bf16_check((50, 32, 48, 16, 20), 7, 64, 9)
     if 'fbank' in which:
         fbank_check()
     if 'tiny' in which:

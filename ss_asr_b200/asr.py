@@ -45,6 +45,7 @@ class pBLSTM(nn.Module):
     def __init__(self, in_dim, out_dim):
         super(pBLSTM, self).__init__()
         self.layer = nn.LSTM(in_dim, out_dim, bidirectional=True, batch_first=True)   # parameter holder
+        self.precision = 'fp32'
 
     def forward(self, input_x, state=None, state_len=None, pack_input=False):
         if state is not None:
@@ -67,7 +68,7 @@ class pBLSTM(nn.Module):
         t_h = t_max + (t_max & 1)
         x = _fit_time(input_x, t_h)
         lens_dev = torch.tensor(run_lens, dtype=torch.int32, device=input_x.device)
-        hout = Fk.blstm(x, lens_dev, True, _blstm_params(self.layer))               # [B, t_h, 2S]
+        hout = Fk.blstm(x, lens_dev, True, _blstm_params(self.layer), self.precision)   # [B, t_h, 2S]
         out = hout.view(B, t_h // 2, 2 * hout.shape[2])[:, :t_max // 2]              # downsample = a view
         hidden = None   # (h_n, c_n) is discarded by every caller on the ASR path (asr.py:256-262)
         if state_len is not None:
@@ -96,6 +97,14 @@ class Listener(nn.Module):
         self.blstm_3 = pBLSTM(self.state_size * 2 * 2, self.state_size)
         self.blstm_4 = nn.LSTM(self.state_size * 2 * 2, self.state_size, bidirectional=True)   # parameter holder
         self.utterance_independent = False   # True: run blstm_4 as bs=1 would (ASR.decode batching)
+        self.precision = 'fp32'
+
+    def set_precision(self, precision):
+        """'fp32': exact SIMT path (decode / validation / tight parity); 'bf16': tcgen05 gate GEMMs (training)."""
+        assert precision in ('fp32', 'bf16')
+        self.precision = precision
+        for m in (self.blstm_1, self.blstm_2, self.blstm_3):
+            m.precision = precision
 
     def get_outdim(self):
         return self.out_dim
@@ -108,10 +117,10 @@ class Listener(nn.Module):
         if self.utterance_independent:
             # bs=1 semantics for every utterance at once: one cell step from zero state per frame
             B, Tp, K = x.shape
-            x = Fk.blstm(x.view(1, B * Tp, K), None, False, _blstm_params(self.blstm_4)).view(B, Tp, -1)
+            x = Fk.blstm(x.view(1, B * Tp, K), None, False, _blstm_params(self.blstm_4), self.precision).view(B, Tp, -1)
         else:
             # seq-first quirk (asr.py:237-238,262): dim 0 (utterances) is the time axis of blstm_4
-            x = Fk.blstm(x, None, False, _blstm_params(self.blstm_4))
+            x = Fk.blstm(x, None, False, _blstm_params(self.blstm_4), self.precision)
         return x, state_len
 
 
@@ -179,6 +188,7 @@ class ASR(nn.Module):
         self.char_trans = nn.Linear(decoder_state_size, output_dim)
         self.tf_rate = tf_rate
         self.att_on_device = False       # True: keep attention maps on the GPU (skips the reference's D2H copy)
+        self.train_precision = 'fp32'    # 'bf16': tensor-core gate GEMMs when training with grad enabled
         self.sample_seed = 0
         self.last_tokens = None          # [B,U] int32: the input token of every step of the last forward
         self.init_parameters()
@@ -193,7 +203,12 @@ class ASR(nn.Module):
 
     def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
         """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
-        encode_feature, encode_len = self.encoder(audio_feature, state_len)
+        use_bf16 = self.train_precision == 'bf16' and self.training and torch.is_grad_enabled() and teacher is not None
+        self.encoder.set_precision('bf16' if use_bf16 else 'fp32')
+        try:
+            encode_feature, encode_len = self.encoder(audio_feature, state_len)
+        finally:
+            self.encoder.set_precision('fp32')
         B = audio_feature.shape[0]
         U = int(decode_step)
         tok_in = torch.zeros(B, U, dtype=torch.int32, device=encode_feature.device)

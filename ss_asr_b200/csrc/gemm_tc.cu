@@ -1,0 +1,283 @@
+// bf16 tensor-core GEMM for the batched-over-time LSTM gate products of the training path:
+//   C[M,N] (fp32) (+)= A[M,K] (bf16, K contiguous) x B[N,K]^T (bf16, K contiguous) (+ bias[N])
+// tcgen05.mma (cta_group::1, 128 x BN x 16 atoms, fp32 accumulators in TMEM) fed by TMA through a multi-stage
+// mbarrier ring; warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (tcgen05.ld -> bias -> global).  Out-of-range rows/columns/reduction indices are
+// zero-filled by TMA, so M, N, K need no padding (only 16-byte row pitches).
+//
+// Reference call sites replaced: the cuDNN/ATen input-projection GEMMs inside nn.LSTM (asr.py:234-238,414,262)
+// and their dgrad/wgrad in loss.backward() (trainer.py:437) -- SURVEY.md §2.2 K2a/K4/K17.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ssasr {
+
+using namespace tc;
+
+constexpr int GT_BM = 128;
+constexpr int GT_BK = 64;             // 64 bf16 = 128 B = one swizzle row
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GT_BM * GT_BK * 2;
+  static constexpr int B_BYTES = BN * GT_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+               int ldc, const float* __restrict__ bias, int M, int N, int K, int a_koff, int b_koff, int accumulate) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * BN;
+  const int num_k = (K + GT_BK - 1) / GT_BK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
+        uint8_t* st = smem + s * L::STAGE_BYTES;
+        tma_load_2d(&tmA, full_bar + s, st, a_koff + kb * GT_BK, m0);
+        tma_load_2d(&tmB, full_bar + s, st + L::A_BYTES, b_koff + kb * GT_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GT_BM, BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t da = umma_desc_k128(a_addr);
+        const uint64_t db = umma_desc_k128(a_addr + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GT_BK / 16; ++k)   // +32 B per K=16 step inside the 128-B swizzle row
+          mma_bf16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        mma_commit(empty_bar + s);
+      }
+      mma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;                 // TMEM lanes [32*ew, 32*ew+32)
+    const int row = m0 + ew * 32 + (threadIdx.x & 31);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (row < M) {
+        if (n0 + c0 + 32 <= N && (ldc & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
+            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+            if (bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
+            if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            *dst = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < N) {
+              float o = __uint_as_float(v[j]) + (bias ? bias[n] : 0.f);
+              if (accumulate) o += crow[c0 + j];
+              crow[c0 + j] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<BN>(tmem_base);
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = {64 cols, box_rows}; 128-B swizzle
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  SSASR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  SSASR_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand needs a 16-byte aligned base and row pitch (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GT_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSASR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+  return 0;
+}
+
+int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
+                 int b_koff, float* C, int ldc, const float* bias, int accumulate) {
+  if (M <= 0 || N <= 0) return 0;
+  SSASR_REQUIRE(K > 0, "gemm_bf16_tc: K must be positive");
+  SSASR_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0, "gemm_bf16_tc: reduction offsets must be multiples of 8 elements (TMA 16-byte "
+                "box alignment), got %d / %d", a_koff, b_koff);
+  constexpr int BN = 128, STAGES = 6;
+  using L = GemmSmem<BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, M, (long long)a_koff + K, lda, GT_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, N, (long long)b_koff + K, ldb, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024));
+    attr_set = true;
+  }
+  dim3 grid((M + GT_BM - 1) / GT_BM, (N + BN - 1) / BN);
+  SSASR_REQUIRE(grid.y <= 65535, "gemm_bf16_tc: N=%d too large", N);
+  ProfScope ps(F_GEMM_TC, st);
+  gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, bias, M, N, K, a_koff, b_koff, accumulate);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- fp32 -> bf16 conversion (optionally transposed, optionally masking a periodic column) ----------
+__global__ void cvt_bf16_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst, long long ld_dst,
+                                long long rows, int cols) {
+  const long long total = rows * (long long)((cols + 1) / 2);
+  const int half = (cols + 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / half;
+    const int c = (int)(i % half) * 2;
+    const float a = src[r * ld_src + c];
+    const float b = (c + 1 < cols) ? src[r * ld_src + c + 1] : 0.f;
+    if (c + 1 < cols || (ld_dst & 1) == 0) {
+      *reinterpret_cast<__nv_bfloat162*>(dst + r * ld_dst + c) = __floats2bfloat162_rn(a, b);
+    } else {
+      dst[r * ld_dst + c] = __float2bfloat16(a);
+    }
+  }
+}
+
+// dst[c, r + shift(c)] = bf16(src[r, c]) for r < rows, c < cols; dst row pitch ld_dst; shift(c) = shift_lo for
+// c < mask_split, shift_hi otherwise (destinations outside [0, rows) are dropped; the caller pre-zeroes dst).
+// mask_period > 0: source rows with (r % mask_period) == mask_pos_lo are written as 0 for c < mask_split, and rows
+// with (r % mask_period) == mask_pos_hi are written as 0 for c >= mask_split (drops the frame that has no
+// forward-order predecessor from the recurrent-weight gradient; see ssasr_blstm_bwd_bf16).
+__global__ void cvt_bf16_t_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                  long long ld_dst, long long rows, int cols, int mask_period, int mask_pos_lo, int mask_pos_hi,
+                                  int mask_split, int shift_lo, int shift_hi) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      v = src[r * ld_src + c];
+      if (mask_period > 0) {
+        const int ph = (int)(r % mask_period);
+        if ((c < mask_split && ph == mask_pos_lo) || (c >= mask_split && ph == mask_pos_hi)) v = 0.f;
+      }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long r = r0 + threadIdx.x;
+    const long long rd = r + (c < mask_split ? shift_lo : shift_hi);
+    if (c < cols && r < rows && rd >= 0 && rd < rows) dst[(long long)c * ld_dst + rd] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+int cvt_bf16(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  ProfScope ps(F_PACK, st);
+  cvt_bf16_kernel<<<1184, 256, 0, st>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+int cvt_bf16_t(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
+               int mask_period, int mask_pos_lo, int mask_pos_hi, int mask_split, int shift_lo, int shift_hi) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((unsigned)((rows + 31) / 32), (cols + 31) / 32);
+  SSASR_REQUIRE(grid.y <= 65535, "cvt_bf16_t: too many columns (%d)", cols);
+  ProfScope ps(F_PACK, st);
+  cvt_bf16_t_kernel<<<grid, dim3(32, 8), 0, st>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols, mask_period, mask_pos_lo,
+                                                  mask_pos_hi, mask_split, shift_lo, shift_hi);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace ssasr
+
+using namespace ssasr;
+
+extern "C" {
+
+int ssasr_gemm_bf16_tc(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb, int b_koff,
+                       float* C, int ldc, const float* bias, int accumulate, void* stream) {
+  return gemm_bf16_tc((cudaStream_t)stream, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate);
+}
+int ssasr_cvt_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream) {
+  return cvt_bf16((cudaStream_t)stream, src, ld_src, dst, ld_dst, rows, cols);
+}
+int ssasr_cvt_bf16_t(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, int mask_period,
+                     int mask_pos_lo, int mask_pos_hi, int mask_split, void* stream) {
+  return cvt_bf16_t((cudaStream_t)stream, src, ld_src, dst, ld_dst, rows, cols, mask_period, mask_pos_lo, mask_pos_hi, mask_split,
+                    0, 0);
+}
+
+}  // extern "C"

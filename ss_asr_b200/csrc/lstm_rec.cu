@@ -502,4 +502,78 @@ int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
   return 0;
 }
 
+
+// ---- bf16 tensor-core variants: the batched-over-time gate GEMMs run on tcgen05 (gemm_tc.cu); the recurrence
+// itself still uses the fp32 persistent kernel above.  Extra arguments are caller-provided bf16 workspaces.
+//   wih_bf [8S, Kp] bf16 (Kp = K rounded up to 8), xb_ws [n_rows, Kp] bf16
+int ssasr_blstm_fwd_bf16(const float* x, int n_rows, int K, int Kp, const void* wih_bf, const float* bias_p,
+                         const float* whh_p, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch,
+                         const int* lens, void* xb_ws, float* xp, float* hout, float* cbuf, unsigned* bar, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSASR_REQUIRE(S % 16 == 0 && Kp % 8 == 0 && Kp >= K, "blstm_fwd_bf16: bad S=%d / Kp=%d (K=%d)", S, Kp, K);
+  int rc = cvt_bf16(st, x, K, xb_ws, Kp, n_rows, K);
+  if (rc) return rc;
+  rc = gemm_bf16_tc(st, n_rows, 8 * S, K, xb_ws, Kp, 0, wih_bf, Kp, 0, xp, 8 * S, bias_p, 0);
+  if (rc) return rc;
+  SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
+  RecFwdParams p;
+  p.xp = xp; p.whh = whh_p; p.hout = hout; p.cbuf = cbuf; p.lens = lens;
+  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch;
+  p.xs_seq = rs_seq; p.xs_batch = rs_batch; p.hs_seq = rs_seq; p.hs_batch = rs_batch;
+  p.bar = bar;
+  p.UPC = pick_upc(S);
+  return p.UPC == 4 ? launch_fwd<4>(p, st) : launch_fwd<8>(p, st);
+}
+
+//   wihT_bf [K, 8S] bf16 (transposed packed input weights); Rp = n_rows rounded up to 8
+//   workspaces: dgb_ws [n_rows, 8S] bf16, dgT_ws [8S, Rp] bf16, xT_ws [K, Rp] bf16, hT_ws [2S, Rp] bf16
+int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf, const float* whhT_p, int S, int n_seq,
+                         int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* act, const float* hout,
+                         const float* cbuf, const float* dhout, float* dx, float* dwih_p, float* dbias_p, float* dwhh_p,
+                         float* dcstate, unsigned* bar, int zero_period, long long Rp, void* dgb_ws, void* dgT_ws, void* xT_ws,
+                         void* hT_ws, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSASR_REQUIRE(Rp % 8 == 0 && Rp >= n_rows, "blstm_bwd_bf16: bad Rp=%lld (n_rows=%d)", Rp, n_rows);
+  SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
+  RecBwdParams p;
+  p.act = act; p.whhT = whhT_p; p.cbuf = cbuf; p.dhout = dhout; p.dcstate = dcstate; p.lens = lens;
+  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch;
+  p.xs_seq = rs_seq; p.xs_batch = rs_batch; p.hs_seq = rs_seq; p.hs_batch = rs_batch;
+  p.bar = bar;
+  p.UPC = pick_upc(S);
+  int rc = p.UPC == 4 ? launch_bwd<4>(p, st) : launch_bwd<8>(p, st);
+  if (rc) return rc;
+  const float* dg = act;
+  rc = colsum(st, dg, dbias_p, n_rows, 8 * S, 8 * S, 0);
+  if (rc) return rc;
+  if (dx) {
+    rc = cvt_bf16(st, dg, 8 * S, dgb_ws, 8 * S, n_rows, 8 * S);
+    if (rc) return rc;
+    rc = gemm_bf16_tc(st, n_rows, K, 8 * S, dgb_ws, 8 * S, 0, wihT_bf, 8 * S, 0, dx, K, nullptr, 0);
+    if (rc) return rc;
+  }
+  rc = cvt_bf16_t(st, dg, 8 * S, dgT_ws, Rp, n_rows, 8 * S, 0, 0, 0, 0);
+  if (rc) return rc;
+  rc = cvt_bf16_t(st, x, K, xT_ws, Rp, n_rows, K, 0, 0, 0, 0);
+  if (rc) return rc;
+  rc = gemm_bf16_tc(st, 8 * S, K, n_rows, dgT_ws, Rp, 0, xT_ws, Rp, 0, dwih_p, K, nullptr, 0);
+  if (rc) return rc;
+  // h transposed AND shifted to its consumer row (fwd: h[r-sh] -> column r, rev: h[r+sh] -> column r), with the frame
+  // that has no forward-order predecessor zeroed per direction; then dW_hh[d] = dG_d^T . hshift_d over all rows.
+  const int sh = (int)rs_seq;
+  SSASR_CHECK_CUDA(cudaMemsetAsync(hT_ws, 0, (size_t)2 * S * Rp * 2, st));
+  rc = cvt_bf16_t(st, hout, 2 * S, hT_ws, Rp, n_rows, 2 * S, zero_period, zero_period > 0 ? zero_period - 1 : 0, 0, S, sh, -sh);
+  if (rc) return rc;
+  {
+    const char* dgT = (const char*)dgT_ws;
+    const char* hT = (const char*)hT_ws;
+    rc = gemm_bf16_tc(st, 4 * S, S, n_rows, dgT, Rp, 0, hT, Rp, 0, dwhh_p, S, nullptr, 0);
+    if (rc) return rc;
+    rc = gemm_bf16_tc(st, 4 * S, S, n_rows, dgT + (size_t)4 * S * Rp * 2, Rp, 0, hT + (size_t)S * Rp * 2, Rp, 0,
+                      dwhh_p + (size_t)4 * S * S, S, nullptr, 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -23,7 +23,7 @@ class _BLSTM(torch.autograd.Function):
     time_major=False: x [L, N, K], seq axis = dim 0, no lengths (encoder.blstm_4 quirk, asr.py:262)."""
 
     @staticmethod
-    def forward(ctx, x, lens_dev, time_major, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+    def forward(ctx, x, lens_dev, time_major, precision, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         lib = _lib.load()
         _lib.require_cuda(x, 'BLSTM')
         x = _f32c(x)
@@ -47,9 +47,21 @@ class _BLSTM(torch.autograd.Function):
             n_seq, n_batch, rs_seq, rs_batch = d1, d0, 1, d1
         else:
             n_seq, n_batch, rs_seq, rs_batch = d0, d1, d1, 1
-        check(lib.ssasr_blstm_fwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch, rs_seq,
-                                      rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
-                                      ptr(bar), st), 'ssasr_blstm_fwd_f32')
+        bf16 = precision == 'bf16'
+        if bf16:
+            Kp = (K + 7) // 8 * 8
+            wih_bf = torch.zeros(8 * S, Kp, device=dev, dtype=torch.bfloat16)
+            check(lib.ssasr_cvt_bf16(ptr(wih_p), K, ptr(wih_bf), Kp, 8 * S, K, st), 'ssasr_cvt_bf16')
+            xb = torch.zeros(n_rows, Kp, device=dev, dtype=torch.bfloat16) if Kp != K else \
+                torch.empty(n_rows, Kp, device=dev, dtype=torch.bfloat16)
+            check(lib.ssasr_blstm_fwd_bf16(ptr(x), n_rows, K, Kp, ptr(wih_bf), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch,
+                                           rs_seq, rs_batch, ptr(lens_dev) if time_major else None, ptr(xb), ptr(xp),
+                                           ptr(hout), ptr(cbuf), ptr(bar), st), 'ssasr_blstm_fwd_bf16')
+        else:
+            check(lib.ssasr_blstm_fwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch, rs_seq,
+                                          rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
+                                          ptr(bar), st), 'ssasr_blstm_fwd_f32')
+        ctx.bf16 = bf16
         ctx.save_for_backward(x, wih_p, whhT_p, xp, hout, cbuf, lens_dev if time_major else torch.empty(0))
         ctx.geom = (n_rows, K, S, n_seq, n_batch, rs_seq, rs_batch, time_major, d1)
         ctx.need_dx = ctx.needs_input_grad[0]
@@ -69,20 +81,32 @@ class _BLSTM(torch.autograd.Function):
         dwhh_p = torch.empty(2, 4 * S, S, device=dev)
         dcs = torch.empty(n_batch, 2 * S, device=dev)
         bar = torch.zeros(2, dtype=torch.int32, device=dev)
-        check(lib.ssasr_blstm_bwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
-                                      ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf), ptr(dhout),
-                                      ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
-                                      d1 if time_major else 0, st), 'ssasr_blstm_bwd_f32')
+        if ctx.bf16:
+            Rp = (n_rows + 7) // 8 * 8
+            bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+            wihT_bf = bf(K, 8 * S)
+            check(lib.ssasr_cvt_bf16_t(ptr(wih_p), K, ptr(wihT_bf), 8 * S, 8 * S, K, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
+            ws = [bf(n_rows, 8 * S) if ctx.need_dx else None, bf(8 * S, Rp), bf(K, Rp), bf(2 * S, Rp)]
+            check(lib.ssasr_blstm_bwd_bf16(ptr(x), n_rows, K, ptr(wihT_bf), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
+                                           ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf),
+                                           ptr(dhout), ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
+                                           d1 if time_major else 0, Rp, ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), st),
+                  'ssasr_blstm_bwd_bf16')
+        else:
+            check(lib.ssasr_blstm_bwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
+                                          ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf), ptr(dhout),
+                                          ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
+                                          d1 if time_major else 0, st), 'ssasr_blstm_bwd_f32')
         g = [torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev), torch.zeros(4 * S, device=dev),
              torch.zeros(4 * S, device=dev), torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev),
              torch.zeros(4 * S, device=dev), torch.zeros(4 * S, device=dev)]
         check(lib.ssasr_unpack_blstm_grads(ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), S, K, *[ptr(t) for t in g], st),
               'ssasr_unpack_blstm_grads')
-        return (dx, None, None) + tuple(g)
+        return (dx, None, None, None) + tuple(g)
 
 
-def blstm(x, lens_dev, time_major, params):
-    return _BLSTM.apply(x, lens_dev, time_major, *params)
+def blstm(x, lens_dev, time_major, params, precision='fp32'):
+    return _BLSTM.apply(x, lens_dev, time_major, precision, *params)
 
 
 # --------------------------------------------------------------------------------------------------
