@@ -67,14 +67,16 @@ int ssasr_cvt_bf16_t(const float* src, long long ld_src, void* dst, long long ld
 /* same contracts as ssasr_blstm_fwd_f32 / _bwd_f32 plus caller-provided bf16 operands and workspaces */
 int ssasr_blstm_fwd_bf16(const float* x, int n_rows, int K, int Kp, const void* wih_bf /*[8S,Kp]*/, const float* bias_p,
                          const float* whh_p, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch,
-                         const int* lens, void* xb_ws /*[n_rows,Kp]*/, float* xp, float* hout, float* cbuf, unsigned* bar,
-                         void* stream);
+                         const int* lens, void* xb_ws /*[n_rows,Kp]*/, float* xp, float* hout, float* cbuf,
+                         unsigned* bar /*512 words*/, const void* whh_bf /*[8S,S] bf16 or NULL*/,
+                         void* hb_ws /*[n_rows,2S] bf16 or NULL; both set => tensor-core recurrence*/, void* stream);
 int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf /*[K,8S]*/, const float* whhT_p, int S,
                          int n_seq, int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* act,
                          const float* hout, const float* cbuf, const float* dhout, float* dx, float* dwih_p,
                          float* dbias_p, float* dwhh_p, float* dcstate, unsigned* bar, int zero_period, long long Rp,
                          void* dgb_ws /*[n_rows,8S]*/, void* dgT_ws /*[8S,Rp]*/, void* xT_ws /*[K,Rp]*/,
-                         void* hT_ws /*[2S,Rp]*/, void* stream);
+                         void* hT_ws /*[2S,Rp]*/, const void* whhT_bf /*[2S,4S] bf16 or NULL => fp32 recurrence*/,
+                         void* stream);
 
 /* ---- attend-and-spell loop: Attention.forward asr.py:343-392 + Speller.forward asr.py:314-326 + the decode loop
  *      of ASR.forward asr.py:65-110 (teacher forcing / greedy / sampled), all U steps on the device ---- */

@@ -92,4 +92,11 @@ int cvt_bf16(cudaStream_t st, const float* src, long long ld_src, void* dst, lon
 int cvt_bf16_t(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
                int mask_period, int mask_pos_lo, int mask_pos_hi, int mask_split, int shift_lo = 0, int shift_hi = 0);
 
+// tensor-core recurrent kernels (rec_tc.cu)
+int rec_tc_supported(int S);
+int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
+               int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
+int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,
+               const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
+
 }  // namespace ssasr

@@ -165,6 +165,26 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long co
   return 0;
 }
 
+// 3-D bf16 tensor: dim0 = cols (contiguous), dim1 = nA entries strideA elements apart, dim2 = nB entries strideB
+// elements apart (strideA <= strideB expected); box = {64, boxA, boxB}; 128-B swizzle.
+int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long cols, long long nA, long long strideA, long long nB,
+                      long long strideB, int boxA, int boxB) {
+  EncodeTiledFn enc = get_encode();
+  SSASR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  SSASR_REQUIRE(((uintptr_t)ptr & 15) == 0 && (strideA * 2) % 16 == 0 && (strideB * 2) % 16 == 0,
+                "TMA operand needs 16-byte aligned base and strides");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)nA, (cuuint64_t)nB};
+  cuuint64_t strides[2] = {(cuuint64_t)strideA * 2, (cuuint64_t)strideB * 2};
+  cuuint32_t box[3] = {(cuuint32_t)GT_BK, (cuuint32_t)boxA, (cuuint32_t)boxB};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSASR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed (%d) cols=%lld nA=%lld sA=%lld nB=%lld sB=%lld", (int)r, cols,
+                nA, strideA, nB, strideB);
+  return 0;
+}
+
 int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                  int b_koff, float* C, int ldc, const float* bias, int accumulate) {
   if (M <= 0 || N <= 0) return 0;

@@ -508,13 +508,16 @@ int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
 //   wih_bf [8S, Kp] bf16 (Kp = K rounded up to 8), xb_ws [n_rows, Kp] bf16
 int ssasr_blstm_fwd_bf16(const float* x, int n_rows, int K, int Kp, const void* wih_bf, const float* bias_p,
                          const float* whh_p, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch,
-                         const int* lens, void* xb_ws, float* xp, float* hout, float* cbuf, unsigned* bar, void* stream) {
+                         const int* lens, void* xb_ws, float* xp, float* hout, float* cbuf, unsigned* bar,
+                         const void* whh_bf, void* hb_ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(S % 16 == 0 && Kp % 8 == 0 && Kp >= K, "blstm_fwd_bf16: bad S=%d / Kp=%d (K=%d)", S, Kp, K);
   int rc = cvt_bf16(st, x, K, xb_ws, Kp, n_rows, K);
   if (rc) return rc;
   rc = gemm_bf16_tc(st, n_rows, 8 * S, K, xb_ws, Kp, 0, wih_bf, Kp, 0, xp, 8 * S, bias_p, 0);
   if (rc) return rc;
+  if (whh_bf && hb_ws && rec_tc_supported(S))   // recurrence on tensor cores
+    return rec_tc_fwd(st, xp, whh_bf, hout, cbuf, hb_ws, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar);
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
   RecFwdParams p;
   p.xp = xp; p.whh = whh_p; p.hout = hout; p.cbuf = cbuf; p.lens = lens;
@@ -531,24 +534,34 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
                          int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* act, const float* hout,
                          const float* cbuf, const float* dhout, float* dx, float* dwih_p, float* dbias_p, float* dwhh_p,
                          float* dcstate, unsigned* bar, int zero_period, long long Rp, void* dgb_ws, void* dgT_ws, void* xT_ws,
-                         void* hT_ws, void* stream) {
+                         void* hT_ws, const void* whhT_bf, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(Rp % 8 == 0 && Rp >= n_rows, "blstm_bwd_bf16: bad Rp=%lld (n_rows=%d)", Rp, n_rows);
-  SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
-  RecBwdParams p;
-  p.act = act; p.whhT = whhT_p; p.cbuf = cbuf; p.dhout = dhout; p.dcstate = dcstate; p.lens = lens;
-  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch;
-  p.xs_seq = rs_seq; p.xs_batch = rs_batch; p.hs_seq = rs_seq; p.hs_batch = rs_batch;
-  p.bar = bar;
-  p.UPC = pick_upc(S);
-  int rc = p.UPC == 4 ? launch_bwd<4>(p, st) : launch_bwd<8>(p, st);
-  if (rc) return rc;
+  int rc;
+  const bool tc_rec = whhT_bf && dgb_ws && rec_tc_supported(S);
+  if (tc_rec) {
+    rc = rec_tc_bwd(st, act, whhT_bf, cbuf, dhout, dgb_ws, dcstate, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar);
+    if (rc) return rc;
+  } else {
+    SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
+    RecBwdParams p;
+    p.act = act; p.whhT = whhT_p; p.cbuf = cbuf; p.dhout = dhout; p.dcstate = dcstate; p.lens = lens;
+    p.S = S; p.n_seq = n_seq; p.n_batch = n_batch;
+    p.xs_seq = rs_seq; p.xs_batch = rs_batch; p.hs_seq = rs_seq; p.hs_batch = rs_batch;
+    p.bar = bar;
+    p.UPC = pick_upc(S);
+    rc = p.UPC == 4 ? launch_bwd<4>(p, st) : launch_bwd<8>(p, st);
+    if (rc) return rc;
+  }
   const float* dg = act;
   rc = colsum(st, dg, dbias_p, n_rows, 8 * S, 8 * S, 0);
   if (rc) return rc;
   if (dx) {
-    rc = cvt_bf16(st, dg, 8 * S, dgb_ws, 8 * S, n_rows, 8 * S);
-    if (rc) return rc;
+    if (!tc_rec) {
+      SSASR_REQUIRE(dgb_ws != nullptr, "blstm_bwd_bf16: dgb_ws required when dx is requested");
+      rc = cvt_bf16(st, dg, 8 * S, dgb_ws, 8 * S, n_rows, 8 * S);
+      if (rc) return rc;
+    }
     rc = gemm_bf16_tc(st, n_rows, K, 8 * S, dgb_ws, 8 * S, 0, wihT_bf, 8 * S, 0, dx, K, nullptr, 0);
     if (rc) return rc;
   }

@@ -1,11 +1,15 @@
 """torch.autograd glue over the C ABI (include/ssasr.h).  PyTorch is used here for device memory, streams
 and the autograd graph only; every FLOP of the hot path is in libssasr.so."""
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib
 from ._lib import check, ptr, stream
+
+
+_TC_RECURRENCE = os.environ.get('SSASR_TC_RECURRENCE', '1') != '0'   # bf16 path: recurrence on tcgen05
 
 
 def _f32c(t):
@@ -42,7 +46,7 @@ class _BLSTM(torch.autograd.Function):
         xp = torch.empty(n_rows, 8 * S, device=dev)
         hout = torch.empty(d0, d1, 2 * S, device=dev)
         cbuf = torch.empty(d0, d1, 2 * S, device=dev)
-        bar = torch.zeros(2, dtype=torch.int32, device=dev)
+        bar = torch.zeros(512, dtype=torch.int32, device=dev)
         if time_major:
             n_seq, n_batch, rs_seq, rs_batch = d1, d0, 1, d1
         else:
@@ -54,9 +58,16 @@ class _BLSTM(torch.autograd.Function):
             check(lib.ssasr_cvt_bf16(ptr(wih_p), K, ptr(wih_bf), Kp, 8 * S, K, st), 'ssasr_cvt_bf16')
             xb = torch.zeros(n_rows, Kp, device=dev, dtype=torch.bfloat16) if Kp != K else \
                 torch.empty(n_rows, Kp, device=dev, dtype=torch.bfloat16)
+            tc_rec = S % 64 == 0 and S <= 512 and _TC_RECURRENCE
+            whh_bf = hb = None
+            if tc_rec:
+                whh_bf = torch.empty(8 * S, S, device=dev, dtype=torch.bfloat16)
+                check(lib.ssasr_cvt_bf16(ptr(whh_p), S, ptr(whh_bf), S, 8 * S, S, st), 'ssasr_cvt_bf16')
+                hb = torch.empty(n_rows, 2 * S, device=dev, dtype=torch.bfloat16)
             check(lib.ssasr_blstm_fwd_bf16(ptr(x), n_rows, K, Kp, ptr(wih_bf), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch,
                                            rs_seq, rs_batch, ptr(lens_dev) if time_major else None, ptr(xb), ptr(xp),
-                                           ptr(hout), ptr(cbuf), ptr(bar), st), 'ssasr_blstm_fwd_bf16')
+                                           ptr(hout), ptr(cbuf), ptr(bar), ptr(whh_bf), ptr(hb), st),
+                  'ssasr_blstm_fwd_bf16')
         else:
             check(lib.ssasr_blstm_fwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch, rs_seq,
                                           rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
@@ -80,18 +91,23 @@ class _BLSTM(torch.autograd.Function):
         dbias_p = torch.empty(8 * S, device=dev)
         dwhh_p = torch.empty(2, 4 * S, S, device=dev)
         dcs = torch.empty(n_batch, 2 * S, device=dev)
-        bar = torch.zeros(2, dtype=torch.int32, device=dev)
+        bar = torch.zeros(512, dtype=torch.int32, device=dev)
         if ctx.bf16:
             Rp = (n_rows + 7) // 8 * 8
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
             wihT_bf = bf(K, 8 * S)
             check(lib.ssasr_cvt_bf16_t(ptr(wih_p), K, ptr(wihT_bf), 8 * S, 8 * S, K, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
-            ws = [bf(n_rows, 8 * S) if ctx.need_dx else None, bf(8 * S, Rp), bf(K, Rp), bf(2 * S, Rp)]
+            tc_rec = S % 64 == 0 and S <= 512 and _TC_RECURRENCE
+            whhT_bf = None
+            if tc_rec:
+                whhT_bf = bf(2 * S, 4 * S)
+                check(lib.ssasr_cvt_bf16(ptr(whhT_p), 4 * S, ptr(whhT_bf), 4 * S, 2 * S, 4 * S, st), 'ssasr_cvt_bf16')
+            ws = [bf(n_rows, 8 * S) if (ctx.need_dx or tc_rec) else None, bf(8 * S, Rp), bf(K, Rp), bf(2 * S, Rp)]
             check(lib.ssasr_blstm_bwd_bf16(ptr(x), n_rows, K, ptr(wihT_bf), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
                                            ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf),
                                            ptr(dhout), ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
-                                           d1 if time_major else 0, Rp, ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), st),
-                  'ssasr_blstm_bwd_bf16')
+                                           d1 if time_major else 0, Rp, ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]),
+                                           ptr(whhT_bf), st), 'ssasr_blstm_bwd_bf16')
         else:
             check(lib.ssasr_blstm_bwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
                                           ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf), ptr(dhout),
