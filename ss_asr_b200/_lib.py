@@ -57,6 +57,7 @@ SIGNATURES = {
     'ssasr_launch_count_reset': (None, []),
     'ssasr_profile_enable': (None, [_I]),
     'ssasr_profile_read': (_I, [_P, _P]),
+    'ssasr_rec_tc_set_debug': (None, [_P]),
 }
 
 

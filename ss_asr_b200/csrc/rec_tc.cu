@@ -34,10 +34,11 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 2.f * sigmoid_fast(2.f * x) - 1.f; }
 
-__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target) {
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target, long long* stamp = nullptr) {
   fence_proxy_async_all();          // generic-proxy global stores -> visible to other CTAs' TMA (async proxy) reads
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (stamp) stamp[6] = clock64();
     __threadfence();
     atomicAdd(counter, 1u);
     unsigned v, spins = 0;
@@ -46,9 +47,23 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target
       if (++spins > (1u << 26)) __trap();
     } while (v < target);
     fence_proxy_async_all();
+    if (stamp) stamp[7] = clock64();
   }
   __syncthreads();
 }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ float tanh_apx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_apx(float x) { return fmaf(tanh_apx(0.5f * x), 0.5f, 0.5f); }
 
 constexpr int RT_UNITS = 16;           // hidden units per CTA slice
 constexpr int RT_THREADS = 192;        // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
@@ -65,11 +80,26 @@ struct RecTcParams {
   long long rs_seq, rs_batch;
   int seq_inner;             // 1: tensor-map dim1 = seq, dim2 = batch (time-major layers); 0: dim1 = batch, dim2 = seq
   unsigned* bar;             // [2 * gridDim.z]
+  long long* dbg;            // optional [n_seq][8] clock64 stamps of CTA (0,0,0); null = off
 };
+
+constexpr int XS_P = 68;    // fp32 row pitch of the 128 x 64 gate tile in smem (conflict-free float4 row access)
+constexpr int HS_P = 20;    // fp32 row pitch of the 128 x 16 state tiles
+constexpr int HB_P = 24;    // bf16 row pitch of the 128 x 16 h exchange tile
+constexpr int GB_P = 72;    // bf16 row pitch of the 128 x 64 dG exchange tile
+
+static long long* g_dbg = nullptr;
+#define DBG_STAMP(idx)                                                                   \
+  do {                                                                                   \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 8 + (idx)] = clock64(); \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// Epilogue data movement is staged through shared memory so that every global access is a contiguous 64-256 B
+// row segment: the xp tile of the NEXT step is prefetched with cp.async while the step barrier / TMA / MMA of
+// that step are in flight, the thread-per-batch-row cell math works on smem, results leave as coalesced stores.
 template <int KB>   // KB = S / 64 resident k-blocks
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW, RecTcParams p) {
@@ -79,7 +109,11 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Wsm = smem;
   uint8_t* Asm = smem + KB * W_BLK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Asm + KB * A_BLK);
+  float* xs = reinterpret_cast<float*>(Asm + KB * A_BLK);                 // [128][XS_P]
+  float* hst = xs + 128 * XS_P;                                           // [128][HS_P]
+  float* cst = hst + 128 * HS_P;                                          // [128][HS_P]
+  __nv_bfloat16* hbst = reinterpret_cast<__nv_bfloat16*>(cst + 128 * HS_P);   // [128][HB_P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hbst + 128 * HB_P);
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
   uint64_t* mma_done = bars + 2;
@@ -110,7 +144,28 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   uint32_t it = 0;                         // completed (tile, s>0) iterations: phase of a_full / mma_done
   bool w_ready = false;
   const int eg = warp & 3;                 // TMEM lane group of an epilogue warp
+  const int te = threadIdx.x - 64;         // epilogue thread id 0..127 (warps 2-5)
+  const bool single = p.n_tiles <= Z;      // one batch tile per CTA: cell state lives in registers
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+  float creg[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) creg[j] = 0.f;
+
+  // coalesced prefetch of the xp tile of (time t_, tile bt_) into xs
+  auto prefetch_x = [&](int t_, int bt_) {
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int idx = i * 128 + te, r = idx >> 4, c4 = idx & 15;
+      const int n = bt_ * 128 + r;
+      float* dst = xs + r * XS_P + c4 * 4;
+      if (n < p.n_batch)
+        cp_async16(dst, p.xp + ((size_t)t_ * p.rs_seq + (size_t)n * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4);
+      else
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+  if (warp >= 2) prefetch_x(dir == 0 ? 0 : p.n_seq - 1, z);
 
   for (int s = 0; s < p.n_seq; ++s) {
     const int t = dir == 0 ? s : p.n_seq - 1 - s;
@@ -119,6 +174,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       if (s > 0) {
         if (warp == 0) {
           if (elect_one()) {
+            DBG_STAMP(0);
             mbar_expect_tx(a_full, KB * A_BLK);
             for (int kb = 0; kb < KB; ++kb)
               tma_load_3d(&tmH, a_full, Asm + kb * A_BLK, dir * S + kb * 64, p.seq_inner ? tp : bt * 128, p.seq_inner ? bt * 128 : tp);
@@ -127,6 +183,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           if (elect_one()) {
             if (!w_ready) { mbar_wait(w_full, 0); w_ready = true; }
             mbar_wait(a_full, it & 1);
+            DBG_STAMP(1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(Asm), w0 = smem_u32(Wsm);
 #pragma unroll
@@ -136,67 +193,122 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
               for (int k = 0; k < 4; ++k) mma_bf16_ss(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
             }
             mma_commit(mma_done);
+            DBG_STAMP(2);
           }
         }
       }
       if (warp >= 2) {
-        const int n = bt * 128 + eg * 32 + lane;
-        if (s > 0) {
-          mbar_wait(mma_done, it & 1);
-          tc_fence_after();
-        }
+        const int r = eg * 32 + lane;            // tile row == TMEM lane
+        const int n = bt * 128 + r;
         const bool in_range = n < p.n_batch;
         const bool valid = in_range && (p.lens ? (t < p.lens[in_range ? n : 0]) : true);
-        const size_t row = (size_t)t * p.rs_seq + (size_t)(in_range ? n : 0) * p.rs_batch;
-        const size_t rowp = (size_t)(s > 0 ? tp : t) * p.rs_seq + (size_t)(in_range ? n : 0) * p.rs_batch;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {     // 4 units (16 gate columns) per chunk
-          uint32_t v[16];
-          if (s > 0) {
-            tmem_ld16(tmem + ((uint32_t)(eg * 32) << 16) + (uint32_t)(ch * 16), v);
-            tmem_ld_wait();
-          } else {
+        const size_t hoff = (size_t)dir * S + slice * RT_UNITS;
+        cp_async_wait_all();
+        epi_bar();                                // xs holds the xp tile of (t, bt)
+        float cpv[16];
+        if (single) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0u;
-          }
-          if (in_range) {
-            float* xptr = p.xp + row * 8 * S + (size_t)dir * 4 * S + slice * 64 + ch * 16;
-            const size_t hoff = (size_t)dir * S + slice * RT_UNITS + ch * 4;
-            float4 cp4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s > 0 && valid) cp4 = *reinterpret_cast<const float4*>(p.cbuf + rowp * 2 * S + hoff);
-            const float cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
-            float hv[4], cv[4];
+          for (int j = 0; j < 16; ++j) cpv[j] = creg[j];
+        } else {
+          const size_t rowp = (size_t)(s > 0 ? tp : t) * p.rs_seq + (size_t)(in_range ? n : 0) * p.rs_batch;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float4 g = *reinterpret_cast<const float4*>(xptr + u * 4);
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              hv[u] = 0.f; cv[u] = 0.f;
-              if (valid) {
-                g.x += __uint_as_float(v[u * 4 + 0]); g.y += __uint_as_float(v[u * 4 + 1]);
-                g.z += __uint_as_float(v[u * 4 + 2]); g.w += __uint_as_float(v[u * 4 + 3]);
-                a.x = sigmoid_fast(g.x); a.y = sigmoid_fast(g.y); a.z = tanh_fast(g.z); a.w = sigmoid_fast(g.w);
-                cv[u] = a.y * cpv[u] + a.x * a.z;
-                hv[u] = a.w * tanh_fast(cv[u]);
-              }
-              *reinterpret_cast<float4*>(xptr + u * 4) = a;
-            }
-            *reinterpret_cast<float4*>(p.hout + row * 2 * S + hoff) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-            *reinterpret_cast<float4*>(p.cbuf + row * 2 * S + hoff) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-            __nv_bfloat162 b01 = __floats2bfloat162_rn(hv[0], hv[1]), b23 = __floats2bfloat162_rn(hv[2], hv[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&b01);
-            pk.y = *reinterpret_cast<uint32_t*>(&b23);
-            *reinterpret_cast<uint2*>(p.xb + row * 2 * S + hoff) = pk;
+          for (int q = 0; q < 4; ++q) {
+            const float4 c4 = (s > 0 && valid) ? *(reinterpret_cast<const float4*>(p.cbuf + rowp * 2 * S + hoff) + q)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            cpv[q * 4 + 0] = c4.x; cpv[q * 4 + 1] = c4.y; cpv[q * 4 + 2] = c4.z; cpv[q * 4 + 3] = c4.w;
           }
         }
+        uint32_t v[64];
+        if (s > 0) {
+          mbar_wait(mma_done, it & 1);
+          if (warp == 2 && lane == 0) DBG_STAMP(3);
+          tc_fence_after();
+          const uint32_t ta = tmem + ((uint32_t)(eg * 32) << 16);
+          tmem_ld16(ta, v);
+          tmem_ld16(ta + 16, v + 16);
+          tmem_ld16(ta + 32, v + 32);
+          tmem_ld16(ta + 48, v + 48);
+          tmem_ld_wait();
+          if (warp == 2 && lane == 0) DBG_STAMP(4);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = 0u;
+        }
         tc_fence_before();
+        float* xrow = xs + r * XS_P;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float hv[4], cv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = q * 4 + u;
+            float4 g = *reinterpret_cast<const float4*>(xrow + j * 4);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            hv[u] = 0.f; cv[u] = 0.f;
+            if (valid) {
+              g.x += __uint_as_float(v[j * 4 + 0]); g.y += __uint_as_float(v[j * 4 + 1]);
+              g.z += __uint_as_float(v[j * 4 + 2]); g.w += __uint_as_float(v[j * 4 + 3]);
+              a.x = sigmoid_apx(g.x); a.y = sigmoid_apx(g.y); a.z = tanh_apx(g.z); a.w = sigmoid_apx(g.w);
+              cv[u] = fmaf(a.y, cpv[j], a.x * a.z);
+              hv[u] = a.w * tanh_apx(cv[u]);
+            }
+            creg[j] = cv[u];
+            *reinterpret_cast<float4*>(xrow + j * 4) = a;
+          }
+          *reinterpret_cast<float4*>(hst + r * HS_P + q * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(cst + r * HS_P + q * 4) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+          __nv_bfloat162 b01 = __floats2bfloat162_rn(hv[0], hv[1]), b23 = __floats2bfloat162_rn(hv[2], hv[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&b01);
+          pk.y = *reinterpret_cast<uint32_t*>(&b23);
+          *reinterpret_cast<uint2*>(hbst + r * HB_P + q * 4) = pk;
+        }
+        epi_bar();
+        // coalesced write-out: exchange buffer first, then the saved tensors
+        {
+          const size_t rbase = (size_t)t * p.rs_seq;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 1, hh = idx & 1, nn = bt * 128 + rr;
+            if (nn < p.n_batch)
+              *reinterpret_cast<uint4*>(p.xb + (rbase + (size_t)nn * p.rs_batch) * 2 * S + hoff + hh * 8) =
+                  *reinterpret_cast<const uint4*>(hbst + rr * HB_P + hh * 8);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 2, c4 = idx & 3, nn = bt * 128 + rr;
+            if (nn < p.n_batch) {
+              const size_t o = (rbase + (size_t)nn * p.rs_batch) * 2 * S + hoff + c4 * 4;
+              *reinterpret_cast<float4*>(p.hout + o) = *reinterpret_cast<const float4*>(hst + rr * HS_P + c4 * 4);
+              *reinterpret_cast<float4*>(p.cbuf + o) = *reinterpret_cast<const float4*>(cst + rr * HS_P + c4 * 4);
+            }
+          }
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nn = bt * 128 + rr;
+            if (nn < p.n_batch)
+              __stcs(reinterpret_cast<float4*>(p.xp + (rbase + (size_t)nn * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4),
+                     *reinterpret_cast<const float4*>(xs + rr * XS_P + c4 * 4));
+          }
+        }
+        if (warp == 2 && lane == 0) DBG_STAMP(5);
+        epi_bar();                                // staging buffers drained
+        // prefetch the xp tile of the next (step, tile) iteration
+        {
+          int bn = bt + Z, sn = s;
+          if (bn >= p.n_tiles) { bn = z; sn = s + 1; }
+          if (sn < p.n_seq) prefetch_x(dir == 0 ? sn : p.n_seq - 1 - sn, bn);
+        }
       }
       if (s > 0) ++it;
       __syncthreads();                      // A tile and TMEM accumulator are free again
       tc_fence_after();
     }
-    if (s + 1 < p.n_seq) group_barrier(gbar, (unsigned)(s + 1) * G);
+    if (s + 1 < p.n_seq)
+      group_barrier(gbar, (unsigned)(s + 1) * G,
+                    (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg + (size_t)s * 8 : nullptr);
   }
+  cp_async_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<64>(tmem);
@@ -215,8 +327,13 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int S = p.S;
   const int KB = 4 * S / 64;              // k-blocks of the 4S-long reduction
   uint8_t* Asm = smem;                    // NST stages
-  uint8_t* Wsm = smem + NST * A_BLK;      // KB blocks of 2 KB, padded to 1024-B alignment each -> use 2 KB pitch
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Wsm + KB * W_BLK);
+  uint8_t* Wsm = smem + NST * A_BLK;      // KB blocks of 2 KB
+  float* as = reinterpret_cast<float*>(Wsm + KB * W_BLK);                 // [128][XS_P] activations -> dG
+  float* dhs = as + 128 * XS_P;                                           // [128][HS_P]
+  float* cs = dhs + 128 * HS_P;                                           // [128][HS_P] c(t)
+  float* cps = cs + 128 * HS_P;                                           // [128][HS_P] c(t_prev)
+  __nv_bfloat16* gbs = reinterpret_cast<__nv_bfloat16*>(cps + 128 * HS_P);    // [128][GB_P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbs + 128 * GB_P);
   uint64_t* w_full = bars;
   uint64_t* mma_done = bars + 1;
   uint64_t* full = bars + 2;
@@ -248,7 +365,46 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   uint32_t kcount = 0;                     // k-blocks streamed so far (ring position / phase), same in producer and MMA
   bool w_ready = false;
   const int eg = warp & 3;
+  const int te = threadIdx.x - 64;
+  const bool single = p.n_tiles <= Z;
   constexpr uint32_t idesc = umma_idesc_bf16(128, 16);
+  const size_t hoff = (size_t)dir * S + slice * RT_UNITS;
+  float dcreg[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) dcreg[j] = 0.f;
+
+  // coalesced prefetch of everything step (s_) of tile bt_ needs that does not depend on the recurrence
+  auto prefetch_in = [&](int s_, int bt_) {
+    const int t_ = dir == 0 ? p.n_seq - 1 - s_ : s_;
+    const int tp_ = dir == 0 ? t_ - 1 : t_ + 1;
+    const bool hp = dir == 0 ? (t_ > 0) : (t_ < p.n_seq - 1);
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int idx = i * 128 + te, r = idx >> 4, c4 = idx & 15, n = bt_ * 128 + r;
+      float* dst = as + r * XS_P + c4 * 4;
+      if (n < p.n_batch)
+        cp_async16(dst, p.xp + ((size_t)t_ * p.rs_seq + (size_t)n * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4);
+      else
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 128 + te, r = idx >> 2, c4 = idx & 3, n = bt_ * 128 + r;
+      if (n < p.n_batch) {
+        const size_t o = ((size_t)t_ * p.rs_seq + (size_t)n * p.rs_batch) * 2 * S + hoff + c4 * 4;
+        cp_async16(dhs + r * HS_P + c4 * 4, p.dhout + o);
+        cp_async16(cs + r * HS_P + c4 * 4, p.cbuf + o);
+        if (hp) cp_async16(cps + r * HS_P + c4 * 4, p.cbuf + ((size_t)tp_ * p.rs_seq + (size_t)n * p.rs_batch) * 2 * S + hoff + c4 * 4);
+        else *reinterpret_cast<float4*>(cps + r * HS_P + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        *reinterpret_cast<float4*>(dhs + r * HS_P + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(cs + r * HS_P + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(cps + r * HS_P + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cp_async_commit();
+  };
+  if (warp >= 2) prefetch_in(0, z);
 
   for (int s = 0; s < p.n_seq; ++s) {
     const int t = dir == 0 ? p.n_seq - 1 - s : s;
@@ -259,6 +415,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       if (s > 0) {
         if (warp == 0) {
           if (elect_one()) {
+            DBG_STAMP(0);
             uint32_t kc = kcount;
             for (int kb = 0; kb < KB; ++kb, ++kc) {
               const int st = kc % NST;
@@ -276,6 +433,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             for (int kb = 0; kb < KB; ++kb, ++kc) {
               const int st = kc % NST;
               mbar_wait(full + st, (kc / NST) & 1);
+              if (kb == 0) DBG_STAMP(1);
               tc_fence_after();
               const uint64_t da = umma_desc_k128(a0 + st * A_BLK), db = umma_desc_k128(w0 + kb * W_BLK);
 #pragma unroll
@@ -283,76 +441,118 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
               mma_commit(empty + st);
             }
             mma_commit(mma_done);
+            DBG_STAMP(2);
           }
         }
         kcount += KB;
       }
       if (warp >= 2) {
-        const int n = bt * 128 + eg * 32 + lane;
+        const int r = eg * 32 + lane;
+        const int n = bt * 128 + r;
+        const bool in_range = n < p.n_batch;
+        const int nn = in_range ? n : 0;
+        const bool valid = in_range && (p.lens ? (t < p.lens[nn]) : true);
+        const bool pv = valid && has_prev && (p.lens ? (tp < p.lens[nn]) : true);
+        float* dcs = p.dcstate + (size_t)nn * 2 * S + hoff;
+        cp_async_wait_all();
+        epi_bar();                                // as / dhs / cs / cps hold the tiles of (t, bt)
+        float dcr[16];
+        if (single) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dcr[j] = dcreg[j];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 d4 = (valid && s > 0) ? *(reinterpret_cast<const float4*>(dcs) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dcr[q * 4 + 0] = d4.x; dcr[q * 4 + 1] = d4.y; dcr[q * 4 + 2] = d4.z; dcr[q * 4 + 3] = d4.w;
+          }
+        }
         uint32_t v[16];
         if (s > 0) {
           mbar_wait(mma_done, it & 1);
+          if (warp == 2 && lane == 0) DBG_STAMP(3);
           tc_fence_after();
           tmem_ld16(tmem + ((uint32_t)(eg * 32) << 16), v);
           tmem_ld_wait();
+          if (warp == 2 && lane == 0) DBG_STAMP(4);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
         tc_fence_before();
-        if (n < p.n_batch) {
-          const bool valid = p.lens ? (t < p.lens[n]) : true;
-          const size_t row = (size_t)t * p.rs_seq + (size_t)n * p.rs_batch;
-          const size_t rowp = (size_t)(has_prev ? tp : t) * p.rs_seq + (size_t)n * p.rs_batch;
-          const bool pv = has_prev && (p.lens ? (tp < p.lens[n]) : true);
-          const size_t hoff = (size_t)dir * S + slice * RT_UNITS;
-          float* aptr = p.xp + row * 8 * S + (size_t)dir * 4 * S + slice * 64;
-          __nv_bfloat16* gb = p.xb + row * 8 * S + (size_t)dir * 4 * S + slice * 64;
-          float* dcs = p.dcstate + (size_t)n * 2 * S + hoff;
+        float* arow = as + r * XS_P;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {      // 4 units per group
-            float4 dh4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = dh4, cp4 = dh4, dcr4 = dh4;
+        for (int q = 0; q < 4; ++q) {
+          const float4 dh4 = *reinterpret_cast<const float4*>(dhs + r * HS_P + q * 4);
+          const float4 c4 = *reinterpret_cast<const float4*>(cs + r * HS_P + q * 4);
+          const float4 cp4 = *reinterpret_cast<const float4*>(cps + r * HS_P + q * 4);
+          const float dhv[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+          const float cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = q * 4 + u;
+            float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+            float dco = 0.f;
             if (valid) {
-              dh4 = *reinterpret_cast<const float4*>(p.dhout + row * 2 * S + hoff + q * 4);
-              c4 = *reinterpret_cast<const float4*>(p.cbuf + row * 2 * S + hoff + q * 4);
-              if (pv) cp4 = *reinterpret_cast<const float4*>(p.cbuf + rowp * 2 * S + hoff + q * 4);
-              if (s > 0) dcr4 = *reinterpret_cast<const float4*>(dcs + q * 4);
+              const float4 a = *reinterpret_cast<const float4*>(arow + j * 4);
+              const float dh = dhv[u] + __uint_as_float(v[j]);
+              const float tc_ = tanh_apx(cv[u]);
+              const float dc = fmaf(dh * a.w, 1.f - tc_ * tc_, dcr[j]);
+              dg.w = dh * tc_ * a.w * (1.f - a.w);
+              dg.x = dc * a.z * a.x * (1.f - a.x);
+              dg.z = dc * a.x * (1.f - a.z * a.z);
+              dg.y = pv ? dc * cpv[u] * a.y * (1.f - a.y) : 0.f;
+              dco = dc * a.y;
             }
-            const float dhv[4] = {dh4.x, dh4.y, dh4.z, dh4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
-            const float cpv[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, dcrv[4] = {dcr4.x, dcr4.y, dcr4.z, dcr4.w};
-            float dco[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-              dco[u] = 0.f;
-              if (valid) {
-                const float4 a = *reinterpret_cast<const float4*>(aptr + (q * 4 + u) * 4);
-                const float dh = dhv[u] + __uint_as_float(v[q * 4 + u]);
-                const float tc_ = tanh_fast(cv[u]);
-                const float dc = dh * a.w * (1.f - tc_ * tc_) + dcrv[u];
-                dg.w = dh * tc_ * a.w * (1.f - a.w);
-                dg.x = dc * a.z * a.x * (1.f - a.x);
-                dg.z = dc * a.x * (1.f - a.z * a.z);
-                dg.y = dc * cpv[u] * a.y * (1.f - a.y);
-                dco[u] = dc * a.y;
-              }
-              *reinterpret_cast<float4*>(aptr + (q * 4 + u) * 4) = dg;
-              __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&b01);
-              pk.y = *reinterpret_cast<uint32_t*>(&b23);
-              *reinterpret_cast<uint2*>(gb + (q * 4 + u) * 4) = pk;
-            }
-            *reinterpret_cast<float4*>(dcs + q * 4) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+            dcreg[j] = dco;
+            *reinterpret_cast<float4*>(arow + j * 4) = dg;
+            __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&b01);
+            pk.y = *reinterpret_cast<uint32_t*>(&b23);
+            *reinterpret_cast<uint2*>(gbs + r * GB_P + j * 4) = pk;
           }
+        }
+        if (!single && in_range) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *(reinterpret_cast<float4*>(dcs) + q) = make_float4(dcreg[q * 4], dcreg[q * 4 + 1], dcreg[q * 4 + 2], dcreg[q * 4 + 3]);
+        }
+        epi_bar();
+        {
+          const size_t rbase = (size_t)t * p.rs_seq;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {          // bf16 exchange tile first: 128 rows x 128 B
+            const int idx = i * 128 + te, rr = idx >> 3, c8 = idx & 7, nb = bt * 128 + rr;
+            if (nb < p.n_batch)
+              *reinterpret_cast<uint4*>(p.xb + (rbase + (size_t)nb * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c8 * 8) =
+                  *reinterpret_cast<const uint4*>(gbs + rr * GB_P + c8 * 8);
+          }
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nb = bt * 128 + rr;
+            if (nb < p.n_batch)
+              __stcs(reinterpret_cast<float4*>(p.xp + (rbase + (size_t)nb * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4),
+                     *reinterpret_cast<const float4*>(as + rr * XS_P + c4 * 4));
+          }
+        }
+        if (warp == 2 && lane == 0) DBG_STAMP(5);
+        epi_bar();
+        {
+          int bn = bt + Z, sn = s;
+          if (bn >= p.n_tiles) { bn = z; sn = s + 1; }
+          if (sn < p.n_seq) prefetch_in(sn, bn);
         }
       }
       if (s > 0) ++it;
       __syncthreads();
       tc_fence_after();
     }
-    if (s + 1 < p.n_seq) group_barrier(gbar, (unsigned)(s + 1) * G);
+    if (s + 1 < p.n_seq)
+      group_barrier(gbar, (unsigned)(s + 1) * G,
+                    (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg + (size_t)s * 8 : nullptr);
   }
+  cp_async_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<32>(tmem);
@@ -372,11 +572,11 @@ static int pick_z(int S, int n_tiles) {
 // scratch words needed for the step barriers of one launch
 int rec_tc_bar_words(int S, int n_batch) { return 2 * pick_z(S, (n_batch + 127) / 128); }
 
-int rec_tc_supported(int S) { return (S % 64 == 0 && S >= 64 && S <= 512) ? 1 : 0; }
+int rec_tc_supported(int S) { return (S % 64 == 0 && S >= 64 && S <= 256) ? 1 : 0; }
 
 template <int KB>
 static int launch_fwd_tc(const CUtensorMap& tmH, const CUtensorMap& tmW, RecTcParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)KB * (64 * 128 + 128 * 128) + 64 + 1024;
+  const size_t smem = (size_t)KB * (64 * 128 + 128 * 128) + (size_t)128 * (XS_P + 2 * HS_P) * 4 + (size_t)128 * HB_P * 2 + 64 + 1024;
   SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_fwd_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&tmH, (void*)&tmW, (void*)&p};
   ProfScope ps(F_REC_TC_FWD, st);
@@ -391,7 +591,7 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
   RecTcParams p;
   p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.dhout = nullptr; p.dcstate = nullptr; p.lens = lens;
   p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + 127) / 128;
-  p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar;
+  p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;
   const int Z = pick_z(S, p.n_tiles);
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned) * 2 * Z, st));
   CUtensorMap tmH, tmW;
@@ -419,11 +619,11 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,
                const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar) {
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_bwd: unsupported state size %d", S);
-  constexpr int NST = 6;
+  constexpr int NST = 5;
   RecTcParams p;
   p.xp = act; p.hout = nullptr; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dcstate = dcstate;
   p.lens = lens; p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + 127) / 128;
-  p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar;
+  p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;
   const int Z = pick_z(S, p.n_tiles);
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned) * 2 * Z, st));
   CUtensorMap tmG, tmW;
@@ -433,7 +633,9 @@ int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW, whhT_bf, 2 * S, 4 * S, 4 * S, 16);
   if (rc) return rc;
-  const size_t smem = (size_t)NST * 128 * 128 + (size_t)(4 * S / 64) * 16 * 128 + (2 + 2 * NST) * 8 + 16 + 1024;
+  const size_t smem = (size_t)NST * 128 * 128 + (size_t)(4 * S / 64) * 16 * 128 + (size_t)128 * (XS_P + 3 * HS_P) * 4 +
+                      (size_t)128 * GB_P * 2 + (2 + 2 * NST) * 8 + 16 + 1024;
+  SSASR_REQUIRE(smem <= 227 * 1024, "rec_tc_bwd: %zu B shared memory needed (S=%d)", smem, S);
   SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_bwd_kernel<NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(S / RT_UNITS, 2, Z);
   void* args[] = {(void*)&tmG, (void*)&tmW, (void*)&p};
@@ -443,3 +645,8 @@ int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
 }
 
 }  // namespace ssasr
+
+extern "C" {
+// debug: device buffer [n_seq][8] of clock64 stamps written by CTA (0,0,0) of the next tensor-core recurrent launches
+void ssasr_rec_tc_set_debug(long long* dev_buf) { ssasr::g_dbg = dev_buf; }
+}
