@@ -194,12 +194,12 @@ class ASR(nn.Module):
         self.init_parameters()
 
     # ------------------------------------------------------------------------------------------
-    def _spell(self, enc, enc_len, tok_in, modes):
+    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32'):
         lens_dev = torch.tensor(enc_len, dtype=torch.int32, device=enc.device)
         params = self.attention.params() + self.decoder.params() + (self.embed.weight, self.char_trans.weight,
                                                                     self.char_trans.bias)
         self.sample_seed += 1
-        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params)
+        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision)
 
     def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
         """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
@@ -219,7 +219,7 @@ class ASR(nn.Module):
             modes = [0 if random.random() <= self.tf_rate else 2 for _ in range(U)]
         else:
             modes = [1] * U
-        logits, att, toks = self._spell(encode_feature, encode_len, tok_in, modes)
+        logits, att, toks = self._spell(encode_feature, encode_len, tok_in, modes, 'bf16' if use_bf16 else 'fp32')
         self.last_tokens = toks
         att = att.detach()
         return encode_len, logits, (att if self.att_on_device else att.cpu())

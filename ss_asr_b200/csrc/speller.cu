@@ -323,6 +323,9 @@ typedef struct {
   unsigned long long seed;
   // outputs / saved state
   float *psi, *xin1, *xin2, *act1, *act2, *c1, *c2, *h2all, *q, *alpha, *logits;
+  // bf16 tensor-core mode (all three non-null): bf16 copies of w1cat / w2cat and a [B, max(X1,X2)] bf16 scratch
+  const void *w1cat_bf, *w2cat_bf;
+  void* ws_bf;
 } ssasr_speller_fwd_args;
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
@@ -337,6 +340,16 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   if (attn_smem > 48 * 1024)
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   const int cell_blocks = (B * Sd + 255) / 256;
+  const bool tc = a->w1cat_bf && a->w2cat_bf && a->ws_bf && X1 % 8 == 0 && X2 % 8 == 0;
+  // gates = x_t @ Wcat^T + b, fp32 SIMT or (bf16 mode) tcgen05 after a bf16 copy of the step's input rows
+  auto gate_gemm = [&](const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out) -> int {
+    if (tc) {
+      int r = cvt_bf16(st, x, ldx, a->ws_bf, K, B, K);
+      if (r) return r;
+      return gemm_bf16_tc(st, B, 4 * Sd, K, a->ws_bf, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0);
+    }
+    return gemm_f32(st, B, 4 * Sd, K, x, ldx, 1, w, K, 1, out, U * 4 * Sd, bias, 0, 0);
+  };
   for (int t = 0; t < U; ++t) {
     AttnFwd f;
     f.Tp = Tp; f.E = E; f.Sd = Sd; f.M = M;
@@ -348,8 +361,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     f.alpha = a->alpha + (size_t)t * Tp; f.alpha_ld = (long long)U * Tp;
     { ProfScope ps(F_ATTN_FWD, st); attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f); }
     // layer 1
-    rc = gemm_f32(st, B, 4 * Sd, X1, a->xin1 + (size_t)t * X1, U * X1, 1, a->w1cat, X1, 1, a->act1 + (size_t)t * 4 * Sd,
-                  U * 4 * Sd, a->b1, 0, 0);
+    rc = gate_gemm(a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
@@ -358,8 +370,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
                                                  (long long)U * X2, t ? a->h2all + (size_t)(t - 1) * Sd : nullptr,
                                                  (long long)U * Sd, a->xin2 + (size_t)t * X2 + Sd, (long long)U * X2);
     // layer 2
-    rc = gemm_f32(st, B, 4 * Sd, X2, a->xin2 + (size_t)t * X2, U * X2, 1, a->w2cat, X2, 1, a->act2 + (size_t)t * 4 * Sd,
-                  U * 4 * Sd, a->b2, 0, 0);
+    rc = gate_gemm(a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
@@ -397,6 +408,11 @@ typedef struct {
   // scratch
   float *dh2all /*[B,U,Sd]*/, *dxin1 /*[B,X1]*/, *dxin2 /*[B,X2]*/, *dc1s, *dc2s, *dh1att /*[B,Sd] each*/,
       *dpsi /*[B,Tp,M]*/, *dqpre /*[B,U,M]*/;
+  // bf16 tensor-core mode (all non-null): transposed bf16 weights [X1,4Sd] / [X2,4Sd], scratch wsA [4Sd,BUp],
+  // wsB [X1,BUp] (BUp = B*U rounded up to 8)
+  const void *w1catT_bf, *w2catT_bf;
+  void *wsA, *wsB;
+  long long BUp;
 } ssasr_speller_bwd_args;
 
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
@@ -419,6 +435,28 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   if (attn_smem > 48 * 1024)
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   const int cell_blocks = (B * Sd + 255) / 256;
+  const bool tc = a->w1catT_bf && a->w2catT_bf && a->wsA && a->wsB && X1 % 8 == 0 && X2 % 8 == 0 && a->BUp >= (long long)B * U &&
+                  a->BUp % 8 == 0;
+  // dx = dG_t @ Wcat (through the cells' input weights), fp32 SIMT or tcgen05
+  auto dgrad_gemm = [&](const float* dg, int N, const float* w, const void* wT_bf, float* out) -> int {
+    if (tc) {
+      int r = cvt_bf16(st, dg, U * 4 * Sd, a->wsA, 4 * Sd, B, 4 * Sd);
+      if (r) return r;
+      return gemm_bf16_tc(st, B, N, 4 * Sd, a->wsA, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, N, nullptr, 0);
+    }
+    return gemm_f32(st, B, N, 4 * Sd, dg, U * 4 * Sd, 1, w, N, 0, out, N, nullptr, 0, 0);
+  };
+  // dW = dG_all^T @ X_all over all B*U rows
+  auto wgrad_gemm = [&](const float* dg, const float* x, int N, float* out) -> int {
+    if (tc) {
+      int r = cvt_bf16_t(st, dg, 4 * Sd, a->wsA, a->BUp, (long long)B * U, 4 * Sd, 0, 0, 0, 0);
+      if (r) return r;
+      r = cvt_bf16_t(st, x, N, a->wsB, a->BUp, (long long)B * U, N, 0, 0, 0, 0);
+      if (r) return r;
+      return gemm_bf16_tc(st, 4 * Sd, N, B * U, a->wsA, a->BUp, 0, a->wsB, a->BUp, 0, out, N, nullptr, 0);
+    }
+    return gemm_f32(st, 4 * Sd, N, B * U, dg, 4 * Sd, 0, x, N, 0, out, N, nullptr, 0, 0);
+  };
   for (int t = U - 1; t >= 0; --t) {
     const int last = (t == U - 1);
     { ProfScope ps(F_POINTWISE, st); }
@@ -427,7 +465,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->dh2all + (size_t)t * Sd, (long long)U * Sd, last ? nullptr : a->dxin2 + Sd,
                                                  (long long)X2, nullptr, 0, a->dc2s, last);
-    rc = gemm_f32(st, B, X2, 4 * Sd, a->act2 + (size_t)t * 4 * Sd, U * 4 * Sd, 1, a->w2cat, X2, 0, a->dxin2, X2, nullptr, 0, 0);
+    rc = dgrad_gemm(a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, a->dxin2);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
     cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
@@ -435,7 +473,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, a->dxin2,
                                                  (long long)X2, last ? nullptr : a->dxin1 + K1, (long long)X1,
                                                  last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last);
-    rc = gemm_f32(st, B, X1, 4 * Sd, a->act1 + (size_t)t * 4 * Sd, U * 4 * Sd, 1, a->w1cat, X1, 0, a->dxin1, X1, nullptr, 0, 0);
+    rc = dgrad_gemm(a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1);
     if (rc) return rc;
     AttnBwd g;
     g.Tp = Tp; g.E = E; g.Sd = Sd; g.M = M;
@@ -451,11 +489,11 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     emb_grad_add_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->dxin1, X1, a->tok_in + t, U, a->d_emb_w);
   }
   // weight gradients, batched over all steps
-  rc = gemm_f32(st, 4 * Sd, X1, B * U, a->act1, 4 * Sd, 0, a->xin1, X1, 0, a->d_w1cat, X1, nullptr, 0, 0);
+  rc = wgrad_gemm(a->act1, a->xin1, X1, a->d_w1cat);
   if (rc) return rc;
   rc = colsum(st, a->act1, a->d_b1, B * U, 4 * Sd, 4 * Sd, 0);
   if (rc) return rc;
-  rc = gemm_f32(st, 4 * Sd, X2, B * U, a->act2, 4 * Sd, 0, a->xin2, X2, 0, a->d_w2cat, X2, nullptr, 0, 0);
+  rc = wgrad_gemm(a->act2, a->xin2, X2, a->d_w2cat);
   if (rc) return rc;
   rc = colsum(st, a->act2, a->d_b2, B * U, 4 * Sd, 4 * Sd, 0);
   if (rc) return rc;

@@ -132,7 +132,7 @@ class _Spell(torch.autograd.Function):
     """U steps of attention + 2 LSTM cells + character projection (asr.py:65-110)."""
 
     @staticmethod
-    def forward(ctx, enc, enc_lens_dev, tok_in, step_mode, seed, phi_w, psi_w, psi_b, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2,
+    def forward(ctx, enc, enc_lens_dev, tok_in, step_mode, seed, precision, phi_w, psi_w, psi_b, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2,
                 w_hh2, b_ih2, b_hh2, emb_w, wc, bc):
         lib = _lib.load()
         _lib.require_cuda(enc, 'Speller')
@@ -157,12 +157,21 @@ class _Spell(torch.autograd.Function):
         act1, act2, c1, c2, h2all = f(B, U, 4 * Sd), f(B, U, 4 * Sd), f(B, U, Sd), f(B, U, Sd), f(B, U, Sd)
         q, alpha, logits = f(B, U, M), f(B, U, Tp), f(B, U, Cc)
         modes = (C.c_int * U)(*[int(m) for m in step_mode])
+        bf16 = precision == 'bf16' and X1 % 8 == 0 and X2 % 8 == 0
+        w1b = w2b = wsb = None
+        if bf16:
+            bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+            w1b, w2b, wsb = bf(4 * Sd, X1), bf(4 * Sd, X2), bf(B, max(X1, X2))
+            check(lib.ssasr_cvt_bf16(ptr(w1cat), X1, ptr(w1b), X1, 4 * Sd, X1, st), 'ssasr_cvt_bf16')
+            check(lib.ssasr_cvt_bf16(ptr(w2cat), X2, ptr(w2b), X2, 4 * Sd, X2, st), 'ssasr_cvt_bf16')
+        ctx.bf16 = bf16
         a = _lib.SpellerFwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
                                 psi_b=ptr(psi_b), w1cat=ptr(w1cat), b1=ptr(b1), w2cat=ptr(w2cat), b2=ptr(b2),
                                 emb_w=ptr(emb_w), wc=ptr(wc), bc=ptr(bc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
                                 tok_in=ptr(tok_in), step_mode=C.cast(modes, C.c_void_p), seed=int(seed), psi=ptr(psi),
                                 xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
-                                h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits))
+                                h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits), w1cat_bf=ptr(w1b),
+                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb))
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
@@ -185,6 +194,13 @@ class _Spell(torch.autograd.Function):
         d_w1cat, d_b1, d_w2cat, d_b2 = f(4 * Sd, X1), f(4 * Sd), f(4 * Sd, X2), f(4 * Sd)
         d_emb_w, d_wc, d_bc, denc = f(Cc, Sd), f(Cc, Sd), f(Cc), f(B, Tp, E)
         scr = [f(B, U, Sd), f(B, X1), f(B, X2), f(B, Sd), f(B, Sd), f(B, Sd), f(B, Tp, M), f(B, U, M)]   # kept alive
+        w1T = w2T = wsA = wsB = None
+        BUp = (B * U + 7) // 8 * 8
+        if ctx.bf16:
+            bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+            w1T, w2T, wsA, wsB = bf(X1, 4 * Sd), bf(X2, 4 * Sd), bf(4 * Sd, max(BUp, B)), bf(X1, BUp)
+            check(lib.ssasr_cvt_bf16_t(ptr(w1cat), X1, ptr(w1T), 4 * Sd, 4 * Sd, X1, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
+            check(lib.ssasr_cvt_bf16_t(ptr(w2cat), X2, ptr(w2T), 4 * Sd, 4 * Sd, X2, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
         a = _lib.SpellerBwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
                                 w1cat=ptr(w1cat), w2cat=ptr(w2cat), wc=ptr(wc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
                                 tok_in=ptr(tok_in), psi=ptr(psi), xin1=ptr(xin1), xin2=ptr(xin2), c1=ptr(c1), c2=ptr(c2),
@@ -193,18 +209,19 @@ class _Spell(torch.autograd.Function):
                                 d_w1cat=ptr(d_w1cat), d_b1=ptr(d_b1), d_w2cat=ptr(d_w2cat), d_b2=ptr(d_b2),
                                 d_emb_w=ptr(d_emb_w), d_wc=ptr(d_wc), d_bc=ptr(d_bc), denc=ptr(denc),
                                 dh2all=ptr(scr[0]), dxin1=ptr(scr[1]), dxin2=ptr(scr[2]), dc1s=ptr(scr[3]),
-                                dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]))
+                                dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]),
+                                w1catT_bf=ptr(w1T), w2catT_bf=ptr(w2T), wsA=ptr(wsA), wsB=ptr(wsB), BUp=BUp)
         check(lib.ssasr_speller_bwd_f32(C.byref(a), st), 'ssasr_speller_bwd_f32')
         z = lambda *s: torch.zeros(*s, device=dev)
         g1 = [z(4 * Sd, K1), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
         g2 = [z(4 * Sd, Sd), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
         check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w1cat), ptr(d_b1), Sd, K1, *[ptr(t) for t in g1], st), 'unpack1')
         check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w2cat), ptr(d_b2), Sd, Sd, *[ptr(t) for t in g2], st), 'unpack2')
-        return (denc, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
+        return (denc, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
 
 
-def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params):
-    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, *params)
+def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32'):
+    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, *params)
 
 
 # --------------------------------------------------------------------------------------------------
