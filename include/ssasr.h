@@ -91,6 +91,7 @@ typedef struct {
   float *psi, *xin1, *xin2, *act1, *act2, *c1, *c2, *h2all, *q, *alpha, *logits; /* outputs + saved state */
   const void *w1cat_bf, *w2cat_bf; /* bf16 copies of w1cat/w2cat, or NULL (fp32 path) */
   void* ws_bf;                     /* bf16 scratch [B, max(X1,X2)], or NULL */
+  void* enc_bf;                    /* bf16 scratch [(B*Tp + M) * E], or NULL */
 } ssasr_speller_fwd_args;
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
 
@@ -104,10 +105,10 @@ typedef struct {
   float *act1, *act2;
   const float* dlogits;     /* [B,U,C] */
   float *d_phi_w, *d_psi_w, *d_psi_b, *d_w1cat, *d_b1, *d_w2cat, *d_b2, *d_emb_w, *d_wc, *d_bc, *denc;
-  float *dh2all, *dxin1, *dxin2, *dc1s, *dc2s, *dh1att, *dpsi, *dqpre;   /* scratch */
+  float *dh2all, *dxin1 /*[B,U,X1]*/, *dxin2, *dc1s, *dc2s, *dh1att, *dpsi, *dqpre, *de_all /*[B,U,Tp]*/;   /* scratch */
   const void *w1catT_bf, *w2catT_bf; /* bf16 [X1,4Sd] / [X2,4Sd] transposed weights, or NULL (fp32 path) */
-  void *wsA, *wsB;                   /* bf16 scratch [4Sd,BUp] / [X1,BUp] */
-  long long BUp;                     /* B*U rounded up to a multiple of 8 */
+  void *wsA, *wsB;                   /* bf16 scratch: >= max(4Sd*BUp, M*BTp) and >= max(X1*BUp, E*BTp + E*M) elements */
+  long long BUp, BTp;                /* B*U and B*Tp rounded up to multiples of 8 */
 } ssasr_speller_bwd_args;
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream);
 

@@ -16,7 +16,7 @@ class SpellerFwdArgs(C.Structure):
                                            'enc', 'enc_lens', 'tok_in', 'step_mode')] +
                 [('seed', C.c_ulonglong)] +
                 [(n, C.c_void_p) for n in ('psi', 'xin1', 'xin2', 'act1', 'act2', 'c1', 'c2', 'h2all', 'q', 'alpha',
-                                           'logits', 'w1cat_bf', 'w2cat_bf', 'ws_bf')])
+                                           'logits', 'w1cat_bf', 'w2cat_bf', 'ws_bf', 'enc_bf')])
 
 
 class SpellerBwdArgs(C.Structure):
@@ -26,9 +26,9 @@ class SpellerBwdArgs(C.Structure):
                                            'dlogits',
                                            'd_phi_w', 'd_psi_w', 'd_psi_b', 'd_w1cat', 'd_b1', 'd_w2cat', 'd_b2',
                                            'd_emb_w', 'd_wc', 'd_bc', 'denc',
-                                           'dh2all', 'dxin1', 'dxin2', 'dc1s', 'dc2s', 'dh1att', 'dpsi', 'dqpre',
+                                           'dh2all', 'dxin1', 'dxin2', 'dc1s', 'dc2s', 'dh1att', 'dpsi', 'dqpre', 'de_all',
                                            'w1catT_bf', 'w2catT_bf', 'wsA', 'wsB')] +
-                [('BUp', C.c_longlong)])
+                [('BUp', C.c_longlong), ('BTp', C.c_longlong)])
 
 
 _P, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float

@@ -29,7 +29,7 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-               int ldc, const float* __restrict__ bias, int M, int N, int K, int a_koff, int b_koff, int accumulate) {
+               int ldc, const float* __restrict__ bias, int M, int N, int K, int a_koff, int b_koff, int accumulate, int act_tanh) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -112,6 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
             if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            if (act_tanh) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
             *dst = o;
           }
         } else {
@@ -121,6 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n < N) {
               float o = __uint_as_float(v[j]) + (bias ? bias[n] : 0.f);
               if (accumulate) o += crow[c0 + j];
+              if (act_tanh) o = tanhf(o);
               crow[c0 + j] = o;
             }
           }
@@ -186,7 +188,7 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long cols, long long
 }
 
 int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
-                 int b_koff, float* C, int ldc, const float* bias, int accumulate) {
+                 int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
   if (M <= 0 || N <= 0) return 0;
   SSASR_REQUIRE(K > 0, "gemm_bf16_tc: K must be positive");
   SSASR_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0, "gemm_bf16_tc: reduction offsets must be multiples of 8 elements (TMA 16-byte "
@@ -206,7 +208,7 @@ int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long 
   dim3 grid((M + GT_BM - 1) / GT_BM, (N + BN - 1) / BN);
   SSASR_REQUIRE(grid.y <= 65535, "gemm_bf16_tc: N=%d too large", N);
   ProfScope ps(F_GEMM_TC, st);
-  gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, bias, M, N, K, a_koff, b_koff, accumulate);
+  gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, bias, M, N, K, a_koff, b_koff, accumulate, act_tanh);
   SSASR_LAUNCH_CHECK();
   return 0;
 }
@@ -289,7 +291,7 @@ extern "C" {
 
 int ssasr_gemm_bf16_tc(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb, int b_koff,
                        float* C, int ldc, const float* bias, int accumulate, void* stream) {
-  return gemm_bf16_tc((cudaStream_t)stream, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate);
+  return gemm_bf16_tc((cudaStream_t)stream, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, 0);
 }
 int ssasr_cvt_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream) {
   return cvt_bf16((cudaStream_t)stream, src, ld_src, dst, ld_dst, rows, cols);

@@ -300,26 +300,32 @@ __global__ void unpack_bias_add_kernel(const float* __restrict__ src, float* __r
     if (g2) g2[i] += v;
   }
 }
-// out[c] (+)= sum_r src[r*ld + c]
-__global__ void colsum_kernel(const float* __restrict__ src, float* __restrict__ out, int R, int C, int ld, int accumulate) {
+// out[c] (+)= sum_r src[r*ld + c].  grid (C/32, row chunks): each block reduces a 32-column x CS_ROWS-row panel
+// (coalesced 128-B row segments) and adds its 32 partial sums with atomics.
+constexpr int CS_ROWS = 512;
+__global__ void colsum_kernel(const float* __restrict__ src, float* __restrict__ out, int R, int C, int ld) {
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * CS_ROWS;
+  const int r1 = min(R, r0 + CS_ROWS);
   float s = 0.f;
   if (c < C)
-    for (int r = threadIdx.y; r < R; r += 8) s += src[(size_t)r * ld + c];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += src[(size_t)r * ld + c];
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
     float v = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) v += part[i][threadIdx.x];
-    out[c] = accumulate ? out[c] + v : v;
+    atomicAdd(out + c, v);
   }
 }
 
 int colsum(cudaStream_t st, const float* src, float* out, int R, int C, int ld, int accumulate) {
+  if (!accumulate) SSASR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+  if (R <= 0 || C <= 0) return 0;
   ProfScope ps(F_POINTWISE, st);
-  colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(src, out, R, C, ld, accumulate);
+  colsum_kernel<<<dim3((C + 31) / 32, (R + CS_ROWS - 1) / CS_ROWS), dim3(32, 8), 0, st>>>(src, out, R, C, ld);
   SSASR_LAUNCH_CHECK();
   return 0;
 }

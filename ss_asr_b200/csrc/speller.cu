@@ -6,6 +6,7 @@
 // Everything stays on the device for all U steps (the reference syncs to the host every step,
 // asr.py:103); attention maps are written straight into the stacked [B,U,T'] layout.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <curand_kernel.h>
 
 namespace ssasr {
@@ -106,8 +107,7 @@ struct AttnBwd {
   const float* psi;                          // [B,Tp,M]
   const float* enc;                          // [B,Tp,E]
   const int* enc_lens;
-  float* denc;                               // [B,Tp,E]  +=
-  float* dpsi;                               // [B,Tp,M]  +=
+  float* de; long long de_ld;                // [B,Tp] out: dL/d(energy) of this step (accumulated into denc/dpsi later)
   float* dqpre; long long dqpre_ld;          // [B,M] out
   float* dh1att;                             // [B,Sd] out
 };
@@ -125,16 +125,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
   for (int j = tid; j < a.Tp; j += blockDim.x) als[j] = a.alpha[(size_t)b * a.alpha_ld + j];
   __syncthreads();
   const float* encb = a.enc + (size_t)b * a.Tp * a.E;
-  float* dencb = a.denc + (size_t)b * a.Tp * a.E;
   for (int j = warp; j < a.Tp; j += nwarp) {
     float s = 0.f;
     if (j < len) {
-      const float al = als[j];
-      for (int c = lane; c < a.E; c += 32) {
-        const float d = dcs[c];
-        s = fmaf(d, encb[(size_t)j * a.E + c], s);
-        dencb[(size_t)j * a.E + c] += al * d;
-      }
+      for (int c = lane; c < a.E; c += 32) s = fmaf(dcs[c], encb[(size_t)j * a.E + c], s);
       s = warp_sum(s);
     }
     if (lane == 0) das[j] = s;
@@ -144,18 +138,17 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
   for (int j = tid; j < len; j += blockDim.x) dot = fmaf(als[j], das[j], dot);
   dot = block_sum(dot, scratch);
   __syncthreads();
-  for (int j = tid; j < a.Tp; j += blockDim.x) als[j] = (j < len) ? als[j] * (das[j] - dot) : 0.f;   // de_j
+  for (int j = tid; j < a.Tp; j += blockDim.x) {
+    const float de = (j < len) ? als[j] * (das[j] - dot) : 0.f;
+    als[j] = de;
+    a.de[(size_t)b * a.de_ld + j] = de;
+  }
   __syncthreads();
   const float* psib = a.psi + (size_t)b * a.Tp * a.M;
-  float* dpsib = a.dpsi + (size_t)b * a.Tp * a.M;
   for (int m = tid; m < a.M; m += blockDim.x) {
     const float qv = a.q[(size_t)b * a.q_ld + m];
     float s = 0.f;
-    for (int j = 0; j < len; ++j) {
-      const float de = als[j];
-      s = fmaf(de, psib[(size_t)j * a.M + m], s);
-      dpsib[(size_t)j * a.M + m] += de * qv;
-    }
+    for (int j = 0; j < len; ++j) s = fmaf(als[j], psib[(size_t)j * a.M + m], s);
     const float dq = s * (1.f - qv * qv);
     dqs[m] = dq;
     a.dqpre[(size_t)b * a.dqpre_ld + m] = dq;
@@ -165,6 +158,41 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
     float s = 0.f;
     for (int m = 0; m < a.M; ++m) s = fmaf(dqs[m], a.phi_w[(size_t)m * a.Sd + k], s);
     a.dh1att[(size_t)b * a.Sd + k] = s;
+  }
+}
+
+// After the loop: out[b,j,:] = sum_t w[b,t,j] * v[b,t,:]   (denc from alpha x dctx, dpsi from de x q).
+// One CTA per (utterance, 8-frame block); w tile in smem, v streamed with coalesced loads.
+__global__ void __launch_bounds__(256) attn_outer_accum_kernel(int U, int Tp, int D, const float* __restrict__ w /*[B,U,Tp]*/,
+                                                               const float* __restrict__ v, long long v_ld_t, long long v_ld_b,
+                                                               float* __restrict__ out /*[B,Tp,D]*/, const int* __restrict__ lens) {
+  extern __shared__ float ws[];     // [U][8]
+  const int b = blockIdx.y, j0 = blockIdx.x * 8;
+  const int len = lens[b];
+  float* ob = out + ((size_t)b * Tp + j0) * D;
+  if (j0 >= len) {                  // fully padded frame block: gradient is exactly zero
+    for (int i = threadIdx.x; i < 8 * D && j0 + i / D < Tp; i += blockDim.x) ob[i] = 0.f;
+    return;
+  }
+  for (int i = threadIdx.x; i < U * 8; i += blockDim.x) {
+    const int t = i >> 3, jj = i & 7;
+    ws[i] = (j0 + jj < Tp) ? w[((size_t)b * U + t) * Tp + j0 + jj] : 0.f;
+  }
+  __syncthreads();
+  const float* vb = v + (size_t)b * v_ld_b;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.f;
+    for (int t = 0; t < U; ++t) {
+      const float d = vb[(size_t)t * v_ld_t + c];
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + t * 8), w1 = *reinterpret_cast<const float4*>(ws + t * 8 + 4);
+      acc[0] = fmaf(w0.x, d, acc[0]); acc[1] = fmaf(w0.y, d, acc[1]); acc[2] = fmaf(w0.z, d, acc[2]); acc[3] = fmaf(w0.w, d, acc[3]);
+      acc[4] = fmaf(w1.x, d, acc[4]); acc[5] = fmaf(w1.y, d, acc[5]); acc[6] = fmaf(w1.z, d, acc[6]); acc[7] = fmaf(w1.w, d, acc[7]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj)
+      if (j0 + jj < Tp) ob[(size_t)jj * D + c] = acc[jj];
   }
 }
 
@@ -326,6 +354,7 @@ typedef struct {
   // bf16 tensor-core mode (all three non-null): bf16 copies of w1cat / w2cat and a [B, max(X1,X2)] bf16 scratch
   const void *w1cat_bf, *w2cat_bf;
   void* ws_bf;
+  void* enc_bf;   // bf16 scratch [(B*Tp + M) * E], or NULL
 } ssasr_speller_fwd_args;
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
@@ -333,7 +362,19 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   const int B = a->B, Tp = a->Tp, E = a->E, Sd = a->Sd, M = a->M, C = a->C, U = a->U;
   const int K1 = Sd + E, X1 = K1 + Sd, X2 = 2 * Sd;
   SSASR_REQUIRE(Sd % 4 == 0, "speller: decoder state size %d must be a multiple of 4", Sd);
-  int rc = gemm_f32(st, B * Tp, M, E, a->enc, E, 1, a->psi_w, E, 1, a->psi, M, a->psi_b, 0, 1);
+  int rc;
+  if (a->w1cat_bf && a->w2cat_bf && a->ws_bf && a->enc_bf && E % 8 == 0) {
+    // psi~ = tanh(enc @ Wpsi^T + b) on tensor cores: enc_bf [B*Tp,E] and (after it) Wpsi bf16 [M,E] live in enc_bf
+    __nv_bfloat16* eb = (__nv_bfloat16*)a->enc_bf;
+    __nv_bfloat16* wb = eb + (size_t)B * Tp * E;
+    rc = cvt_bf16(st, a->enc, E, eb, E, (long long)B * Tp, E);
+    if (rc) return rc;
+    rc = cvt_bf16(st, a->psi_w, E, wb, E, M, E);
+    if (rc) return rc;
+    rc = gemm_bf16_tc(st, B * Tp, M, E, eb, E, 0, wb, E, 0, a->psi, M, a->psi_b, 0, 1);
+  } else {
+    rc = gemm_f32(st, B * Tp, M, E, a->enc, E, 1, a->psi_w, E, 1, a->psi, M, a->psi_b, 0, 1);
+  }
   if (rc) return rc;
   const size_t attn_smem = (size_t)(Sd + M + Tp + 32) * sizeof(float);
   SSASR_REQUIRE(attn_smem <= 200 * 1024, "speller: attention working set too large (Tp=%d)", Tp);
@@ -406,13 +447,13 @@ typedef struct {
   // gradient outputs (overwritten), kernel layout
   float *d_phi_w, *d_psi_w, *d_psi_b, *d_w1cat, *d_b1, *d_w2cat, *d_b2, *d_emb_w, *d_wc, *d_bc, *denc;
   // scratch
-  float *dh2all /*[B,U,Sd]*/, *dxin1 /*[B,X1]*/, *dxin2 /*[B,X2]*/, *dc1s, *dc2s, *dh1att /*[B,Sd] each*/,
-      *dpsi /*[B,Tp,M]*/, *dqpre /*[B,U,M]*/;
+  float *dh2all /*[B,U,Sd]*/, *dxin1 /*[B,U,X1]*/, *dxin2 /*[B,X2]*/, *dc1s, *dc2s, *dh1att /*[B,Sd] each*/,
+      *dpsi /*[B,Tp,M]*/, *dqpre /*[B,U,M]*/, *de_all /*[B,U,Tp]*/;
   // bf16 tensor-core mode (all non-null): transposed bf16 weights [X1,4Sd] / [X2,4Sd], scratch wsA [4Sd,BUp],
   // wsB [X1,BUp] (BUp = B*U rounded up to 8)
   const void *w1catT_bf, *w2catT_bf;
-  void *wsA, *wsB;
-  long long BUp;
+  void *wsA, *wsB;   // element counts: wsA >= max(4Sd*BUp, M*BTp), wsB >= max(X1*BUp, E*BTp + E*M)
+  long long BUp, BTp;
 } ssasr_speller_bwd_args;
 
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
@@ -423,28 +464,39 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   // through the character projection, all steps at once
   rc = gemm_f32(st, B * U, Sd, C, a->dlogits, C, 1, a->wc, Sd, 0, a->dh2all, Sd, nullptr, 0, 0);
   if (rc) return rc;
-  rc = gemm_f32(st, C, Sd, B * U, a->dlogits, C, 0, a->h2all, Sd, 0, a->d_wc, Sd, nullptr, 0, 0);
+  const bool tc0 = a->w1catT_bf && a->w2catT_bf && a->wsA && a->wsB && a->BUp >= (long long)B * U && a->BUp % 8 == 0 &&
+                   a->BTp >= (long long)B * Tp && a->BTp % 8 == 0 && Sd % 8 == 0 && E % 8 == 0 && M % 8 == 0;
+  // out[Mo,No] = X^T Y over R rows (X [R,Mo] ldx, Y [R,No] ldy): tensor cores through transposed bf16 copies, or fp32
+  auto xty = [&](const float* X, int ldx, int Mo, const float* Y, int ldy, int No, long long R, long long Rp, float* out) -> int {
+    if (tc0) {
+      int r = cvt_bf16_t(st, X, ldx, a->wsA, Rp, R, Mo, 0, 0, 0, 0);
+      if (r) return r;
+      r = cvt_bf16_t(st, Y, ldy, a->wsB, Rp, R, No, 0, 0, 0, 0);
+      if (r) return r;
+      return gemm_bf16_tc(st, Mo, No, (int)R, a->wsA, Rp, 0, a->wsB, Rp, 0, out, No, nullptr, 0);
+    }
+    return gemm_f32(st, Mo, No, (int)R, X, ldx, 0, Y, ldy, 0, out, No, nullptr, 0, 0);
+  };
+  rc = xty(a->dlogits, C, C, a->h2all, Sd, Sd, (long long)B * U, a->BUp, a->d_wc);
   if (rc) return rc;
   rc = colsum(st, a->dlogits, a->d_bc, B * U, C, C, 0);
   if (rc) return rc;
-  SSASR_CHECK_CUDA(cudaMemsetAsync(a->denc, 0, sizeof(float) * (size_t)B * Tp * E, st));
-  SSASR_CHECK_CUDA(cudaMemsetAsync(a->dpsi, 0, sizeof(float) * (size_t)B * Tp * M, st));
   SSASR_CHECK_CUDA(cudaMemsetAsync(a->d_emb_w, 0, sizeof(float) * (size_t)C * Sd, st));
   const size_t attn_smem = (size_t)(E + 2 * Tp + M + 32) * sizeof(float);
-  SSASR_REQUIRE(attn_smem <= 200 * 1024, "speller bwd: attention working set too large (Tp=%d)", Tp);
+  SSASR_REQUIRE(attn_smem <= 200 * 1024 && (size_t)U * 8 * sizeof(float) <= 48 * 1024, "speller bwd: attention working set too large (Tp=%d, U=%d)", Tp, U);
   if (attn_smem > 48 * 1024)
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   const int cell_blocks = (B * Sd + 255) / 256;
   const bool tc = a->w1catT_bf && a->w2catT_bf && a->wsA && a->wsB && X1 % 8 == 0 && X2 % 8 == 0 && a->BUp >= (long long)B * U &&
                   a->BUp % 8 == 0;
   // dx = dG_t @ Wcat (through the cells' input weights), fp32 SIMT or tcgen05
-  auto dgrad_gemm = [&](const float* dg, int N, const float* w, const void* wT_bf, float* out) -> int {
+  auto dgrad_gemm = [&](const float* dg, int N, const float* w, const void* wT_bf, float* out, int ldo) -> int {
     if (tc) {
       int r = cvt_bf16(st, dg, U * 4 * Sd, a->wsA, 4 * Sd, B, 4 * Sd);
       if (r) return r;
-      return gemm_bf16_tc(st, B, N, 4 * Sd, a->wsA, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, N, nullptr, 0);
+      return gemm_bf16_tc(st, B, N, 4 * Sd, a->wsA, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, ldo, nullptr, 0);
     }
-    return gemm_f32(st, B, N, 4 * Sd, dg, U * 4 * Sd, 1, w, N, 0, out, N, nullptr, 0, 0);
+    return gemm_f32(st, B, N, 4 * Sd, dg, U * 4 * Sd, 1, w, N, 0, out, ldo, nullptr, 0, 0);
   };
   // dW = dG_all^T @ X_all over all B*U rows
   auto wgrad_gemm = [&](const float* dg, const float* x, int N, float* out) -> int {
@@ -465,28 +517,35 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->dh2all + (size_t)t * Sd, (long long)U * Sd, last ? nullptr : a->dxin2 + Sd,
                                                  (long long)X2, nullptr, 0, a->dc2s, last);
-    rc = dgrad_gemm(a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, a->dxin2);
+    rc = dgrad_gemm(a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, a->dxin2, X2);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
     cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, a->dxin2,
-                                                 (long long)X2, last ? nullptr : a->dxin1 + K1, (long long)X1,
-                                                 last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last);
-    rc = dgrad_gemm(a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1);
+                                                 (long long)X2, last ? nullptr : a->dxin1 + (size_t)(t + 1) * X1 + K1,
+                                                 (long long)U * X1, last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last);
+    rc = dgrad_gemm(a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
     if (rc) return rc;
     AttnBwd g;
     g.Tp = Tp; g.E = E; g.Sd = Sd; g.M = M;
-    g.dctx = a->dxin1 + Sd; g.dctx_ld = X1;
+    g.dctx = a->dxin1 + (size_t)t * X1 + Sd; g.dctx_ld = (long long)U * X1;
     g.alpha = a->alpha + (size_t)t * Tp; g.alpha_ld = (long long)U * Tp;
     g.q = a->q + (size_t)t * M; g.q_ld = (long long)U * M;
     g.phi_w = a->phi_w; g.psi = a->psi; g.enc = a->enc; g.enc_lens = a->enc_lens;
-    g.denc = a->denc; g.dpsi = a->dpsi;
+    g.de = a->de_all + (size_t)t * Tp; g.de_ld = (long long)U * Tp;
     g.dqpre = a->dqpre + (size_t)t * M; g.dqpre_ld = (long long)U * M;
     g.dh1att = a->dh1att;
     { ProfScope ps(F_ATTN_BWD, st); attn_bwd_kernel<<<B, 256, attn_smem, st>>>(g); }
-    { ProfScope ps(F_POINTWISE, st); }
-    emb_grad_add_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->dxin1, X1, a->tok_in + t, U, a->d_emb_w);
+  }
+  // attention memory gradients, accumulated over all steps at once
+  {
+    ProfScope ps(F_ATTN_BWD, st);
+    attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, (size_t)U * 8 * sizeof(float), st>>>(
+        U, Tp, E, a->alpha, a->dxin1 + Sd, X1, (long long)U * X1, a->denc, a->enc_lens);
+    attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, (size_t)U * 8 * sizeof(float), st>>>(
+        U, Tp, M, a->de_all, a->q, M, (long long)U * M, a->dpsi, a->enc_lens);
+    emb_grad_add_kernel<<<(B * U * Sd + 255) / 256, 256, 0, st>>>(B * U, Sd, a->dxin1, X1, a->tok_in, 1, a->d_emb_w);
   }
   // weight gradients, batched over all steps
   rc = wgrad_gemm(a->act1, a->xin1, X1, a->d_w1cat);
@@ -497,15 +556,24 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   if (rc) return rc;
   rc = colsum(st, a->act2, a->d_b2, B * U, 4 * Sd, 4 * Sd, 0);
   if (rc) return rc;
-  rc = gemm_f32(st, M, Sd, B * U, a->dqpre, M, 0, a->xin1 + K1, X1, 0, a->d_phi_w, Sd, nullptr, 0, 0);
+  rc = xty(a->dqpre, M, M, a->xin1 + K1, X1, Sd, (long long)B * U, a->BUp, a->d_phi_w);
   if (rc) return rc;
   { ProfScope ps(F_POINTWISE, st); }
   dtanh_inplace_kernel<<<256, 256, 0, st>>>(a->dpsi, a->psi, (size_t)B * Tp * M);
-  rc = gemm_f32(st, M, E, B * Tp, a->dpsi, M, 0, a->enc, E, 0, a->d_psi_w, E, nullptr, 0, 0);
+  rc = xty(a->dpsi, M, M, a->enc, E, E, (long long)B * Tp, a->BTp, a->d_psi_w);
   if (rc) return rc;
   rc = colsum(st, a->dpsi, a->d_psi_b, B * Tp, M, M, 0);
   if (rc) return rc;
-  rc = gemm_f32(st, B * Tp, E, M, a->dpsi, M, 1, a->psi_w, E, 0, a->denc, E, nullptr, 1, 0);
+  if (tc0) {      // denc += dpsi_pre @ Wpsi
+    __nv_bfloat16* wT = (__nv_bfloat16*)a->wsB;              // [E, M]
+    rc = cvt_bf16_t(st, a->psi_w, E, wT, M, M, E, 0, 0, 0, 0);
+    if (rc) return rc;
+    rc = cvt_bf16(st, a->dpsi, M, a->wsA, M, (long long)B * Tp, M);
+    if (rc) return rc;
+    rc = gemm_bf16_tc(st, B * Tp, E, M, a->wsA, M, 0, wT, M, 0, a->denc, E, nullptr, 1);
+  } else {
+    rc = gemm_f32(st, B * Tp, E, M, a->dpsi, M, 1, a->psi_w, E, 0, a->denc, E, nullptr, 1, 0);
+  }
   if (rc) return rc;
   SSASR_LAUNCH_CHECK();
   return 0;

@@ -158,10 +158,11 @@ class _Spell(torch.autograd.Function):
         q, alpha, logits = f(B, U, M), f(B, U, Tp), f(B, U, Cc)
         modes = (C.c_int * U)(*[int(m) for m in step_mode])
         bf16 = precision == 'bf16' and X1 % 8 == 0 and X2 % 8 == 0
-        w1b = w2b = wsb = None
+        w1b = w2b = wsb = encb = None
         if bf16:
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
             w1b, w2b, wsb = bf(4 * Sd, X1), bf(4 * Sd, X2), bf(B, max(X1, X2))
+            encb = bf((B * Tp + M) * E)
             check(lib.ssasr_cvt_bf16(ptr(w1cat), X1, ptr(w1b), X1, 4 * Sd, X1, st), 'ssasr_cvt_bf16')
             check(lib.ssasr_cvt_bf16(ptr(w2cat), X2, ptr(w2b), X2, 4 * Sd, X2, st), 'ssasr_cvt_bf16')
         ctx.bf16 = bf16
@@ -171,7 +172,7 @@ class _Spell(torch.autograd.Function):
                                 tok_in=ptr(tok_in), step_mode=C.cast(modes, C.c_void_p), seed=int(seed), psi=ptr(psi),
                                 xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
                                 h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits), w1cat_bf=ptr(w1b),
-                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb))
+                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb))
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
@@ -193,12 +194,15 @@ class _Spell(torch.autograd.Function):
         d_phi_w, d_psi_w, d_psi_b = f(M, Sd), f(M, E), f(M)
         d_w1cat, d_b1, d_w2cat, d_b2 = f(4 * Sd, X1), f(4 * Sd), f(4 * Sd, X2), f(4 * Sd)
         d_emb_w, d_wc, d_bc, denc = f(Cc, Sd), f(Cc, Sd), f(Cc), f(B, Tp, E)
-        scr = [f(B, U, Sd), f(B, X1), f(B, X2), f(B, Sd), f(B, Sd), f(B, Sd), f(B, Tp, M), f(B, U, M)]   # kept alive
+        scr = [f(B, U, Sd), f(B, U, X1), f(B, X2), f(B, Sd), f(B, Sd), f(B, Sd), f(B, Tp, M), f(B, U, M), f(B, U, Tp)]   # kept alive
         w1T = w2T = wsA = wsB = None
         BUp = (B * U + 7) // 8 * 8
+        BTp = (B * Tp + 7) // 8 * 8
         if ctx.bf16:
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
-            w1T, w2T, wsA, wsB = bf(X1, 4 * Sd), bf(X2, 4 * Sd), bf(4 * Sd, max(BUp, B)), bf(X1, BUp)
+            w1T, w2T = bf(X1, 4 * Sd), bf(X2, 4 * Sd)
+            wsA = bf(max(4 * Sd * max(BUp, B), max(M, Cc, Sd) * max(BTp, BUp)))
+            wsB = bf(max(X1 * BUp, E * BTp + E * M, Sd * BUp))
             check(lib.ssasr_cvt_bf16_t(ptr(w1cat), X1, ptr(w1T), 4 * Sd, 4 * Sd, X1, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
             check(lib.ssasr_cvt_bf16_t(ptr(w2cat), X2, ptr(w2T), 4 * Sd, 4 * Sd, X2, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
         a = _lib.SpellerBwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
@@ -209,8 +213,8 @@ class _Spell(torch.autograd.Function):
                                 d_w1cat=ptr(d_w1cat), d_b1=ptr(d_b1), d_w2cat=ptr(d_w2cat), d_b2=ptr(d_b2),
                                 d_emb_w=ptr(d_emb_w), d_wc=ptr(d_wc), d_bc=ptr(d_bc), denc=ptr(denc),
                                 dh2all=ptr(scr[0]), dxin1=ptr(scr[1]), dxin2=ptr(scr[2]), dc1s=ptr(scr[3]),
-                                dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]),
-                                w1catT_bf=ptr(w1T), w2catT_bf=ptr(w2T), wsA=ptr(wsA), wsB=ptr(wsB), BUp=BUp)
+                                dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]), de_all=ptr(scr[8]),
+                                w1catT_bf=ptr(w1T), w2catT_bf=ptr(w2T), wsA=ptr(wsA), wsB=ptr(wsB), BUp=BUp, BTp=BTp)
         check(lib.ssasr_speller_bwd_f32(C.byref(a), st), 'ssasr_speller_bwd_f32')
         z = lambda *s: torch.zeros(*s, device=dev)
         g1 = [z(4 * Sd, K1), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
