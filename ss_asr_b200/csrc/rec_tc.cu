@@ -65,6 +65,23 @@ __device__ __forceinline__ float tanh_apx(float x) {
 }
 __device__ __forceinline__ float sigmoid_apx(float x) { return fmaf(tanh_apx(0.5f * x), 0.5f, 0.5f); }
 
+// Step barrier, split: the epilogue ARRIVES as soon as this CTA's slice of the exchange buffer is written; only
+// the TMA producer WAITS (it is the only consumer of other CTAs' data), so the rest of the epilogue (saved-tensor
+// write-out, next-step prefetch) overlaps the barrier latency and the next step's TMA + MMA.
+__device__ __forceinline__ void step_arrive(unsigned* counter) {
+  fence_proxy_async_all();
+  __threadfence();
+  atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ void step_wait(unsigned* counter, unsigned target) {
+  unsigned v, spins = 0;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (++spins > (1u << 26)) __trap();
+  } while (v < target);
+  fence_proxy_async_all();          // acquired generic-proxy writes -> ordered before this thread's TMA (async proxy) reads
+}
+
 constexpr int RT_UNITS = 16;           // hidden units per CTA slice
 constexpr int RT_THREADS = 192;        // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 
@@ -117,7 +134,8 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
   uint64_t* mma_done = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* tmem_free = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int S = p.S;
   const int slice = blockIdx.x, dir = blockIdx.y, z = blockIdx.z, Z = gridDim.z;
@@ -128,6 +146,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
     mbar_init(w_full, 1);
     mbar_init(a_full, 1);
     mbar_init(mma_done, 1);
+    mbar_init(tmem_free, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<64>(tmem_slot);
@@ -174,6 +193,8 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
       if (s > 0) {
         if (warp == 0) {
           if (elect_one()) {
+            if (bt == z) step_wait(gbar, (unsigned)s * G);       // every CTA of the group has published step s-1
+            if (it > 0) mbar_wait(mma_done, (it - 1) & 1);       // previous MMAs have consumed the A tile
             DBG_STAMP(0);
             mbar_expect_tx(a_full, KB * A_BLK);
             for (int kb = 0; kb < KB; ++kb)
@@ -183,6 +204,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           if (elect_one()) {
             if (!w_ready) { mbar_wait(w_full, 0); w_ready = true; }
             mbar_wait(a_full, it & 1);
+            if (it > 0) mbar_wait(tmem_free, (it - 1) & 1);      // epilogue has drained the accumulator
             DBG_STAMP(1);
             tc_fence_after();
             const uint32_t a0 = smem_u32(Asm), w0 = smem_u32(Wsm);
@@ -229,12 +251,13 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           tmem_ld16(ta + 32, v + 32);
           tmem_ld16(ta + 48, v + 48);
           tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(tmem_free);
           if (warp == 2 && lane == 0) DBG_STAMP(4);
         } else {
 #pragma unroll
           for (int j = 0; j < 64; ++j) v[j] = 0u;
         }
-        tc_fence_before();
         float* xrow = xs + r * XS_P;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -263,6 +286,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           pk.y = *reinterpret_cast<uint32_t*>(&b23);
           *reinterpret_cast<uint2*>(hbst + r * HB_P + q * 4) = pk;
         }
+        if (warp == 2 && lane == 0) DBG_STAMP(5);
         epi_bar();
         // coalesced write-out: exchange buffer first, then the saved tensors
         {
@@ -273,6 +297,13 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             if (nn < p.n_batch)
               *reinterpret_cast<uint4*>(p.xb + (rbase + (size_t)nn * p.rs_batch) * 2 * S + hoff + hh * 8) =
                   *reinterpret_cast<const uint4*>(hbst + rr * HB_P + hh * 8);
+          }
+          if (bt + Z >= p.n_tiles && s + 1 < p.n_seq) {   // last tile of this step: publish
+            epi_bar();
+            if (te == 0) {
+              step_arrive(gbar);
+              DBG_STAMP(6);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -291,7 +322,6 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                      *reinterpret_cast<const float4*>(xs + rr * XS_P + c4 * 4));
           }
         }
-        if (warp == 2 && lane == 0) DBG_STAMP(5);
         epi_bar();                                // staging buffers drained
         // prefetch the xp tile of the next (step, tile) iteration
         {
@@ -299,14 +329,10 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           if (bn >= p.n_tiles) { bn = z; sn = s + 1; }
           if (sn < p.n_seq) prefetch_x(dir == 0 ? sn : p.n_seq - 1 - sn, bn);
         }
+        if (warp == 2 && lane == 0) DBG_STAMP(7);
       }
       if (s > 0) ++it;
-      __syncthreads();                      // A tile and TMEM accumulator are free again
-      tc_fence_after();
     }
-    if (s + 1 < p.n_seq)
-      group_barrier(gbar, (unsigned)(s + 1) * G,
-                    (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg + (size_t)s * 8 : nullptr);
   }
   cp_async_wait_all();
   tc_fence_before();
@@ -336,7 +362,8 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(gbs + 128 * GB_P);
   uint64_t* w_full = bars;
   uint64_t* mma_done = bars + 1;
-  uint64_t* full = bars + 2;
+  uint64_t* tmem_free = bars + 2;
+  uint64_t* full = bars + 3;
   uint64_t* empty = full + NST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + NST);
 
@@ -347,6 +374,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     tma_prefetch_desc(&tmW);
     mbar_init(w_full, 1);
     mbar_init(mma_done, 1);
+    mbar_init(tmem_free, 128);
     for (int i = 0; i < NST; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     fence_barrier_init();
   }
@@ -415,6 +443,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       if (s > 0) {
         if (warp == 0) {
           if (elect_one()) {
+            if (bt == z) step_wait(gbar, (unsigned)s * G);
             DBG_STAMP(0);
             uint32_t kc = kcount;
             for (int kb = 0; kb < KB; ++kb, ++kc) {
@@ -433,7 +462,10 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             for (int kb = 0; kb < KB; ++kb, ++kc) {
               const int st = kc % NST;
               mbar_wait(full + st, (kc / NST) & 1);
-              if (kb == 0) DBG_STAMP(1);
+              if (kb == 0) {
+                if (it > 0) mbar_wait(tmem_free, (it - 1) & 1);
+                DBG_STAMP(1);
+              }
               tc_fence_after();
               const uint64_t da = umma_desc_k128(a0 + st * A_BLK), db = umma_desc_k128(w0 + kb * W_BLK);
 #pragma unroll
@@ -474,12 +506,13 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           tc_fence_after();
           tmem_ld16(tmem + ((uint32_t)(eg * 32) << 16), v);
           tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(tmem_free);
           if (warp == 2 && lane == 0) DBG_STAMP(4);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
-        tc_fence_before();
         float* arow = as + r * XS_P;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -518,6 +551,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           for (int q = 0; q < 4; ++q)
             *(reinterpret_cast<float4*>(dcs) + q) = make_float4(dcreg[q * 4], dcreg[q * 4 + 1], dcreg[q * 4 + 2], dcreg[q * 4 + 3]);
         }
+        if (warp == 2 && lane == 0) DBG_STAMP(5);
         epi_bar();
         {
           const size_t rbase = (size_t)t * p.rs_seq;
@@ -528,6 +562,13 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
               *reinterpret_cast<uint4*>(p.xb + (rbase + (size_t)nb * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c8 * 8) =
                   *reinterpret_cast<const uint4*>(gbs + rr * GB_P + c8 * 8);
           }
+          if (bt + Z >= p.n_tiles && s + 1 < p.n_seq) {   // last tile of this step: publish
+            epi_bar();
+            if (te == 0) {
+              step_arrive(gbar);
+              DBG_STAMP(6);
+            }
+          }
 #pragma unroll 4
           for (int i = 0; i < 16; ++i) {
             const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nb = bt * 128 + rr;
@@ -536,21 +577,16 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                      *reinterpret_cast<const float4*>(as + rr * XS_P + c4 * 4));
           }
         }
-        if (warp == 2 && lane == 0) DBG_STAMP(5);
         epi_bar();
         {
           int bn = bt + Z, sn = s;
           if (bn >= p.n_tiles) { bn = z; sn = s + 1; }
           if (sn < p.n_seq) prefetch_in(sn, bn);
         }
+        if (warp == 2 && lane == 0) DBG_STAMP(7);
       }
       if (s > 0) ++it;
-      __syncthreads();
-      tc_fence_after();
     }
-    if (s + 1 < p.n_seq)
-      group_barrier(gbar, (unsigned)(s + 1) * G,
-                    (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg + (size_t)s * 8 : nullptr);
   }
   cp_async_wait_all();
   tc_fence_before();
@@ -619,7 +655,7 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,
                const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar) {
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_bwd: unsupported state size %d", S);
-  constexpr int NST = 5;
+  constexpr int NST = 6;
   RecTcParams p;
   p.xp = act; p.hout = nullptr; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dcstate = dcstate;
   p.lens = lens; p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + 127) / 128;
@@ -634,7 +670,7 @@ int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
   rc = make_tmap_bf16(&tmW, whhT_bf, 2 * S, 4 * S, 4 * S, 16);
   if (rc) return rc;
   const size_t smem = (size_t)NST * 128 * 128 + (size_t)(4 * S / 64) * 16 * 128 + (size_t)128 * (XS_P + 3 * HS_P) * 4 +
-                      (size_t)128 * GB_P * 2 + (2 + 2 * NST) * 8 + 16 + 1024;
+                      (size_t)128 * GB_P * 2 + (3 + 2 * NST) * 8 + 16 + 1024;
   SSASR_REQUIRE(smem <= 227 * 1024, "rec_tc_bwd: %zu B shared memory needed (S=%d)", smem, S);
   SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_bwd_kernel<NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(S / RT_UNITS, 2, Z);
