@@ -274,3 +274,69 @@ def test_teacher_forcing_draws_follow_python_rng():
     for t in range(8):
         if mask[t]:
             assert torch.equal(toks[:, t + 1], y[:, t + 1])
+
+
+# ------------------------------------------------------------------------------------------------ bf16 / tcgen05 path
+@pytest.mark.parametrize('M,N,K,ak,bk', [(128, 128, 64, 0, 0), (300, 200, 80, 0, 0), (1024, 2048, 1024, 0, 0),
+                                         (128, 128, 512, 16, 0), (256, 128, 1000, 0, 8), (2048, 80, 4096, 0, 0), (50, 256, 333, 0, 0)])
+def test_gemm_bf16_tcgen05(M, N, K, ak, bk):
+    """tcgen05+TMA GEMM against an fp64 product of the same bf16-rounded operands (fp32 accumulation tolerance)."""
+    from ss_asr_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N + K)
+    Kp = (K + max(ak, bk) + 7) // 8 * 8
+    Ab = torch.randn(M, Kp, generator=g).to(DEV).to(torch.bfloat16)
+    Bb = torch.randn(N, Kp, generator=g).to(DEV).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    ref = Ab[:, ak:ak + K].double() @ Bb[:, bk:bk + K].double().t() + bias.double()
+    C = torch.zeros(M, N, device=DEV)
+    _lib.check(lib.ssasr_gemm_bf16_tc(M, N, K, Ab.data_ptr(), Kp, ak, Bb.data_ptr(), Kp, bk, C.data_ptr(), N, bias.data_ptr(), 0,
+                                      _lib.stream()), 'gemm_tc')
+    assert float((C.double() - ref).abs().max()) < 2e-5 * K ** 0.5 * 4
+    C2 = C.clone()
+    _lib.check(lib.ssasr_gemm_bf16_tc(M, N, K, Ab.data_ptr(), Kp, ak, Bb.data_ptr(), Kp, bk, C2.data_ptr(), N, None, 1,
+                                      _lib.stream()), 'gemm_tc accumulate')
+    assert float((C2.double() - (2 * ref - bias.double())).abs().max()) < 4e-5 * K ** 0.5 * 4
+
+
+def test_cvt_bf16_transposed_shifted_masked():
+    from ss_asr_b200 import _lib
+    lib = _lib.load()
+    R, Cc, T = 96, 40, 12                       # 8 utterances x 12 frames
+    src = torch.randn(R, Cc, device=DEV)
+    Rp = (R + 7) // 8 * 8
+    dst = torch.zeros(Cc, Rp, device=DEV, dtype=torch.bfloat16)
+    _lib.check(lib.ssasr_cvt_bf16_t(src.data_ptr(), Cc, dst.data_ptr(), Rp, R, Cc, 0, 0, 0, 0, _lib.stream()), 'cvt_t')
+    assert torch.equal(dst[:, :R], src.t().to(torch.bfloat16))
+
+
+# bf16 training-path tolerances (SURVEY §8c): logits atol 1e-2, loss rel 1e-3, gradients rel-L2 3e-2 and cosine >= 0.999
+@pytest.mark.parametrize('dims,B,T,U', [((50, 256, 256, 128, 80), 8, 128, 20), ((50, 64, 64, 32, 40), 140, 48, 6),
+                                        ((50, 128, 32, 16, 24), 5, 91, 7), ((50, 32, 48, 16, 20), 7, 64, 9)])
+def test_bf16_training_path(dims, B, T, U):
+    """tcgen05 gate GEMMs (+ tensor-core recurrence when S % 64 == 0) against the fp32 CPU oracle."""
+    from ss_asr_b200.functional import asr_loss
+    sd = O.make_state_dict(*dims, seed=1)
+    x, lens, y = O.synth_batch(B, T, dims[4], U, seed=1234)
+    loss_o, logits_o, att_o, enc_o, grads_o = O.train_step_grads(sd, x, lens, y)
+    m = _model(dims, sd)
+    m.train_precision = 'bf16'
+    m.train()
+    el, logits, att = m(x.to(DEV), logits_o.shape[1], teacher=y.to(DEV), state_len=lens)
+    assert float((logits.detach().cpu() - logits_o).abs().max()) < 1e-2
+    assert float((att - att_o).abs().max()) < 1e-3
+    loss = asr_loss(logits, y.to(DEV))
+    assert abs(float(loss) - float(loss_o)) < 1e-3 * float(loss_o)
+    loss.backward()
+    gtot = float(torch.sqrt(sum(v.double().pow(2).sum() for v in grads_o.values())))
+    for k, p in m.named_parameters():
+        a, b = p.grad.cpu().double(), grads_o[k].double()
+        assert float((a - b).norm()) <= 3e-2 * float(b.norm()) + 1e-4 * gtot, k
+        if float(b.norm()) > 1e-3 * gtot:
+            assert float((a * b).sum() / (a.norm() * b.norm())) >= 0.999, k
+    # eval / no-grad calls stay on the exact fp32 path even when train_precision is bf16
+    m.eval()
+    with torch.no_grad():
+        _, gl, _ = m(x.to(DEV), 4, state_len=lens)
+        _, gl_o, _, _ = O.asr_forward(sd, x, lens, 4)
+    assert float((gl.cpu() - gl_o).abs().max()) < 1e-5
