@@ -365,12 +365,13 @@ def run_extras(model, dev, args, peaks, shard=(0, 1), dist=None):
     n = 160000
     audio = 0.1 * torch.randn(n_utt * n, device=dev, generator=torch.Generator(device=dev).manual_seed(1234 + rank))
     off = [i * n for i in range(n_utt + 1)]
-    fb, _ = PP.log_fbank_device(audio, off, 16000, 80)
+    plan = PP.FbankPlan(off, 16000, 80, device=dev)
+    fb = plan.run(audio)
     torch.cuda.synchronize()
     reps = 5
     e0.record()
     for _ in range(reps):
-        PP.log_fbank_device(audio, off, 16000, 80, out=fb)
+        plan.run(audio, out=fb)
     e1.record()
     torch.cuda.synchronize()
     ms = tmax(e0.elapsed_time(e1)) / reps

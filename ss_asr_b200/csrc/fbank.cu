@@ -109,23 +109,24 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-// one Stockham stage of radix R over `nfr` frames of N=200 complex points (src -> dst), twiddles tw200
-template <int R>
+// one Stockham stage of radix R (sub-transform length Ns so far) over `nfr` frames of N=200 complex points
+// (src -> dst); everything but nfr is a compile-time constant, so the index arithmetic is mul/shift only.
+template <int R, int Ns>
 __device__ __forceinline__ void stockham_stage(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw200,
-                                               int Ns, int nfr) {
+                                               int nfr) {
   constexpr int N = 200;
   constexpr int NB = N / R;
+  constexpr int TS = N / (Ns * R);      // twiddle index step per unit k: W_{Ns*R}^{k r} = W_200^{k r TS}  (k r TS < N)
   for (int w = threadIdx.x; w < nfr * NB; w += NT) {
-    const int f = w / NB, j = w % NB;
+    const int f = w / NB, j = w - f * NB;
     const float2* x = src + f * N;
     float2* y = dst + f * N;
     const int k = j % Ns;
-    const int tstep = k * (N / (Ns * R));       // twiddle index step: W_{Ns*R}^{k} = W_200^{k*200/(Ns*R)}
     float2 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       v[r] = x[j + r * NB];
-      if (r > 0 && Ns > 1) v[r] = cmul(v[r], tw200[(tstep * r) % N]);
+      if (r > 0 && Ns > 1) v[r] = cmul(v[r], tw200[k * TS * r]);
     }
     float2 o[R];
     if constexpr (R == 2) {
@@ -150,7 +151,7 @@ __device__ __forceinline__ void stockham_stage(const float2* __restrict__ src, f
       o[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
       o[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
     }
-    const int j0 = (j / Ns) * Ns * R + k;
+    const int j0 = (j - k) * R + k;
 #pragma unroll
     for (int r = 0; r < R; ++r) y[j0 + r * Ns] = o[r];
   }
@@ -164,7 +165,83 @@ struct FbankParams {
   const int *mel_start, *mel_cnt, *mel_off; const float* mel_w;
 };
 
-__global__ void __launch_bounds__(NT) fbank_kernel(FbankParams p) {
+// ---- 16 kHz / 25 ms fast path: 400-sample frames, hop 160 ----------------------------------------------------
+// shared: A [FPB][200] float2 | B [FPB][200] float2 (also: audio span before the FFT, power spectrum after) |
+//         twiddles [401] float2 | window [400] float
+__global__ void __launch_bounds__(NT, 4) fbank400_kernel(FbankParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float2* A = reinterpret_cast<float2*>(smem);
+  float2* Bf = A + FPB * 200;
+  float* span = reinterpret_cast<float*>(Bf);                 // aliases B until the first FFT stage writes it
+  float* P = reinterpret_cast<float*>(Bf);                    // aliases B after the last FFT stage (result is in A)
+  float2* tws = Bf + FPB * 200;
+  float* win = reinterpret_cast<float*>(tws + 401);
+  const int u = blockIdx.y;
+  const long long a0 = p.offsets[u];
+  const int n = (int)(p.offsets[u + 1] - a0);
+  constexpr int ws = 400, st = 160, half = 200;
+  const int nframes = 1 + n / st;
+  const int f0 = blockIdx.x * FPB;
+  if (f0 >= nframes) return;
+  const int nfr = min(FPB, nframes - f0);
+  for (int i = threadIdx.x; i < 401; i += NT) tws[i] = p.tw[i];
+  for (int i = threadIdx.x; i < ws; i += NT) win[i] = p.window[i];
+  const float* au = p.audio + a0;
+  const int s0 = f0 * st - half;
+  const int need = (nfr - 1) * st + ws;
+  if (s0 >= 0 && s0 + need <= n) {          // interior block: straight coalesced copy
+    for (int i = threadIdx.x; i < need; i += NT) span[i] = __ldcs(au + s0 + i);
+  } else {                                  // utterance edges: numpy 'reflect' padding
+    for (int i = threadIdx.x; i < need; i += NT) {
+      int idx = s0 + i;
+      if (idx < 0) idx = -idx;
+      if (idx >= n) idx = 2 * (n - 1) - idx;
+      span[i] = au[idx];
+    }
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < nfr * 200; w += NT) {          // window and pack z[m] = xw[2m] + i*xw[2m+1]
+    const int f = w / 200, m = w - f * 200;
+    const float2 sv = *reinterpret_cast<const float2*>(span + f * st + 2 * m);
+    const float2 wv = *reinterpret_cast<const float2*>(win + 2 * m);
+    A[w] = make_float2(sv.x * wv.x, sv.y * wv.y);
+  }
+  __syncthreads();
+  stockham_stage<5, 1>(A, Bf, tws, nfr);
+  __syncthreads();
+  stockham_stage<5, 5>(Bf, A, tws, nfr);
+  __syncthreads();
+  stockham_stage<4, 25>(A, Bf, tws, nfr);
+  __syncthreads();
+  stockham_stage<2, 100>(Bf, A, tws, nfr);
+  __syncthreads();
+  // real-input split: X[k] = E[k] + W_400^k * O[k], k = 0..200; power spectrum
+  constexpr int PB = 202;
+  const float2* w400 = tws + 200;
+  for (int w = threadIdx.x; w < nfr * 201; w += NT) {
+    const int f = w / 201, k = w - f * 201;
+    const float2 zk = A[f * 200 + (k == 200 ? 0 : k)];
+    const float2 zn = A[f * 200 + (k == 0 ? 0 : 200 - k)];
+    const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+    const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // (zk - conj(zn)) / (2i)
+    const float2 x = cadd(e, cmul(w400[k], o));
+    P[f * PB + k] = x.x * x.x + x.y * x.y;
+  }
+  __syncthreads();
+  float* outp = p.out + (size_t)(p.out_offsets[u] + f0) * p.n_mels;
+  for (int w = threadIdx.x; w < nfr * p.n_mels; w += NT) {
+    const int f = w / p.n_mels, i = w - f * p.n_mels;
+    const int b0 = __ldg(p.mel_start + i), c = __ldg(p.mel_cnt + i);
+    const float* wt = p.mel_w + __ldg(p.mel_off + i);
+    const float* pr = P + f * PB + b0;
+    float s = 0.f;
+    for (int b = 0; b < c; ++b) s = fmaf(__ldg(wt + b), pr[b], s);
+    __stcs(outp + w, logf(s + 2.220446049250313e-16f));
+  }
+}
+
+// ---- any other window length (the reference's default 22.05 kHz gives 551 = 19*29): direct DFT ---------------
+__global__ void __launch_bounds__(NT) fbank_generic_kernel(FbankParams p) {
   extern __shared__ __align__(16) float smem[];
   const int u = blockIdx.y;
   const long long a0 = p.offsets[u];
@@ -174,18 +251,12 @@ __global__ void __launch_bounds__(NT) fbank_kernel(FbankParams p) {
   const int f0 = blockIdx.x * FPB;
   if (f0 >= nframes) return;
   const int nfr = min(FPB, nframes - f0);
-  const bool fast = (ws == 400);
-  // shared layout: span | bufA | bufB | P | tw
   const int span_len = (FPB - 1) * st + ws;
   float* span = smem;                                            // [span_len]
-  float* bufA = span + ((span_len + 3) & ~3);                    // fast: FPB*200 float2 ; generic: FPB*ws floats
-  const int bufA_floats = fast ? FPB * 400 : FPB * ws;
-  float* bufB = bufA + ((bufA_floats + 3) & ~3);                 // fast only: FPB*200 float2
-  float* P = bufB + (fast ? FPB * 400 : 0);                      // [FPB][nbins+1]
-  float2* tws = reinterpret_cast<float2*>(P + ((FPB * (p.nbins + 1) + 3) & ~3));   // twiddles
-  const int ntw = fast ? 401 : ws;
-  for (int i = threadIdx.x; i < ntw; i += NT) tws[i] = p.tw[i];
-  // 1. audio span with numpy 'reflect' padding at the utterance edges
+  float* bufA = span + ((span_len + 3) & ~3);                    // [FPB][ws] windowed frames
+  float* P = bufA + ((FPB * ws + 3) & ~3);                       // [FPB][nbins+1]
+  float2* tws = reinterpret_cast<float2*>(P + ((FPB * (p.nbins + 1) + 3) & ~3));
+  for (int i = threadIdx.x; i < ws; i += NT) tws[i] = p.tw[i];
   const float* au = p.audio + a0;
   const int s0 = f0 * st - half;
   const int need = (nfr - 1) * st + ws;
@@ -197,59 +268,26 @@ __global__ void __launch_bounds__(NT) fbank_kernel(FbankParams p) {
   }
   __syncthreads();
   const int PB = p.nbins + 1;
-  if (fast) {
-    float2* A = reinterpret_cast<float2*>(bufA);
-    float2* Bf = reinterpret_cast<float2*>(bufB);
-    // 2. window and pack z[m] = xw[2m] + i*xw[2m+1]
-    for (int w = threadIdx.x; w < nfr * 200; w += NT) {
-      const int f = w / 200, m = w % 200;
-      const float* s = span + f * st + 2 * m;
-      A[f * 200 + m] = make_float2(s[0] * p.window[2 * m], s[1] * p.window[2 * m + 1]);
-    }
-    __syncthreads();
-    stockham_stage<5>(A, Bf, tws, 1, nfr);
-    __syncthreads();
-    stockham_stage<5>(Bf, A, tws, 5, nfr);
-    __syncthreads();
-    stockham_stage<4>(A, Bf, tws, 25, nfr);
-    __syncthreads();
-    stockham_stage<2>(Bf, A, tws, 100, nfr);
-    __syncthreads();
-    // 3. real-input split: X[k] = E[k] + W_400^k * O[k],  k = 0..200
-    const float2* w400 = tws + 200;
-    for (int w = threadIdx.x; w < nfr * 201; w += NT) {
-      const int f = w / 201, k = w % 201;
-      const float2 zk = A[f * 200 + (k % 200)];
-      const float2 zn = A[f * 200 + ((200 - k) % 200)];
-      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // (zk - conj(zn)) / (2i)
-      const float2 x = cadd(e, cmul(w400[k], o));
-      P[f * PB + k] = x.x * x.x + x.y * x.y;
-    }
-  } else {
-    // generic window length: direct DFT, one (frame, bin) per thread
-    for (int w = threadIdx.x; w < nfr * ws; w += NT) {
-      const int f = w / ws, i = w % ws;
-      bufA[f * ws + i] = span[f * st + i] * p.window[i];
-    }
-    __syncthreads();
-    for (int w = threadIdx.x; w < nfr * p.nbins; w += NT) {
-      const int f = w / p.nbins, k = w % p.nbins;
-      const float* x = bufA + f * ws;
-      float re = 0.f, im = 0.f;
-      int idx = 0;
-      for (int i = 0; i < ws; ++i) {
-        const float2 t = tws[idx];
-        re = fmaf(x[i], t.x, re);
-        im = fmaf(x[i], t.y, im);
-        idx += k;
-        if (idx >= ws) idx -= ws;
-      }
-      P[f * PB + k] = re * re + im * im;
-    }
+  for (int w = threadIdx.x; w < nfr * ws; w += NT) {
+    const int f = w / ws, i = w % ws;
+    bufA[f * ws + i] = span[f * st + i] * p.window[i];
   }
   __syncthreads();
-  // 4. sparse mel projection + log, coalesced [frame, mel] store
+  for (int w = threadIdx.x; w < nfr * p.nbins; w += NT) {
+    const int f = w / p.nbins, k = w % p.nbins;
+    const float* x = bufA + f * ws;
+    float re = 0.f, im = 0.f;
+    int idx = 0;
+    for (int i = 0; i < ws; ++i) {
+      const float2 t = tws[idx];
+      re = fmaf(x[i], t.x, re);
+      im = fmaf(x[i], t.y, im);
+      idx += k;
+      if (idx >= ws) idx -= ws;
+    }
+    P[f * PB + k] = re * re + im * im;
+  }
+  __syncthreads();
   float* outp = p.out + (size_t)(p.out_offsets[u] + f0) * p.n_mels;
   for (int w = threadIdx.x; w < nfr * p.n_mels; w += NT) {
     const int f = w / p.n_mels, i = w % p.n_mels;
@@ -289,16 +327,20 @@ int ssasr_fbank(const float* audio, const long long* offsets, int n_utt, int sam
   p.audio = audio; p.offsets = offsets; p.n_utt = n_utt; p.out = out; p.out_offsets = out_offsets;
   p.ws = t.ws; p.st = t.st; p.nbins = t.nbins; p.n_mels = n_mels;
   p.window = t.window; p.tw = t.tw; p.mel_start = t.mel_start; p.mel_cnt = t.mel_cnt; p.mel_off = t.mel_off; p.mel_w = t.mel_w;
-  const bool fast = t.ws == 400;
-  const int span_len = (FPB - 1) * t.st + t.ws;
-  size_t floats = ((span_len + 3) & ~3) + (((fast ? FPB * 400 : FPB * t.ws) + 3) & ~3) + (fast ? FPB * 400 : 0) +
-                  ((FPB * (t.nbins + 1) + 3) & ~3) + 2 * (fast ? 401 : t.ws);
-  const size_t smem = floats * sizeof(float);
-  SSASR_REQUIRE(smem <= 227 * 1024, "fbank: window of %d samples needs %zu B shared memory", t.ws, smem);
-  SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((max_frames + FPB - 1) / FPB, n_utt);
   ProfScope ps(F_FBANK, st);
-  fbank_kernel<<<grid, NT, smem, st>>>(p);
+  if (t.ws == 400) {
+    const size_t smem = (size_t)(2 * FPB * 200 + 401) * sizeof(float2) + 400 * sizeof(float);
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fbank400_kernel<<<grid, NT, smem, st>>>(p);
+  } else {
+    const int span_len = (FPB - 1) * t.st + t.ws;
+    const size_t floats = ((span_len + 3) & ~3) + ((FPB * t.ws + 3) & ~3) + ((FPB * (t.nbins + 1) + 3) & ~3) + 2 * (size_t)t.ws;
+    const size_t smem = floats * sizeof(float);
+    SSASR_REQUIRE(smem <= 227 * 1024, "fbank: window of %d samples needs %zu B shared memory", t.ws, smem);
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fbank_generic_kernel<<<grid, NT, smem, st>>>(p);
+  }
   SSASR_LAUNCH_CHECK();
   return 0;
 }

@@ -20,34 +20,50 @@ def num_frames(n_samples, sample_rate):
     return int(_lib.load().ssasr_fbank_num_frames(int(n_samples), int(sample_rate)))
 
 
+class FbankPlan:
+    """Device-side offsets for one batch geometry, so that repeated extraction (preprocessing loop, benchmark) costs one
+    kernel launch per <= 65535 utterances and no per-call host work."""
+
+    def __init__(self, offsets, sample_rate, n_mels=None, device='cuda'):
+        self.sample_rate = int(sample_rate)
+        self.n_mels = N_DIMS if n_mels is None else int(n_mels)
+        off = [int(v) for v in (offsets.tolist() if torch.is_tensor(offsets) else offsets)]
+        self.n_utt = len(off) - 1
+        ws = int(sample_rate * 0.001 * WIN_SIZE)
+        st = int(sample_rate * 0.001 * STRIDE)
+        lens = [off[i + 1] - off[i] for i in range(self.n_utt)]
+        if min(lens) <= ws // 2:
+            raise ValueError('log_fbank: every utterance needs more than %d samples (reflect padding), got %d'
+                             % (ws // 2, min(lens)))
+        self.frames = [1 + (n + 2 * (ws // 2) - ws) // st for n in lens]       # == ssasr_fbank_num_frames
+        self.foff = [0]
+        for f in self.frames:
+            self.foff.append(self.foff[-1] + f)
+        self.off_d = torch.tensor(off, dtype=torch.int64, device=device)
+        self.foff_d = torch.tensor(self.foff, dtype=torch.int64, device=device)
+        self.n_samples = off[-1]
+        self.chunks = [(u0, min(self.n_utt, u0 + MAX_UTT_PER_CALL)) for u0 in range(0, self.n_utt, MAX_UTT_PER_CALL)]
+        self.chunk_max = [max(self.frames[a:b]) for a, b in self.chunks]
+
+    def run(self, audio, out=None):
+        lib = _lib.load()
+        _lib.require_cuda(audio, 'log_fbank')
+        if out is None:
+            out = torch.empty(self.foff[-1], self.n_mels, device=audio.device, dtype=torch.float32)
+        audio = audio.contiguous()
+        st = stream()
+        for (u0, u1), mx in zip(self.chunks, self.chunk_max):
+            check(lib.ssasr_fbank(ptr(audio), self.off_d.data_ptr() + 8 * u0, u1 - u0, self.sample_rate, self.n_mels, ptr(out),
+                                  self.foff_d.data_ptr() + 8 * u0, mx, st), 'ssasr_fbank')
+        return out
+
+
 def log_fbank_device(audio, offsets, sample_rate, n_mels=None, out=None):
     """audio: 1-D float32 CUDA tensor holding all utterances back to back; offsets: int64 CPU tensor/list
     [n_utt+1].  Returns (fbank [total_frames, n_mels] CUDA float32, frame_offsets list)."""
-    lib = _lib.load()
     _lib.require_cuda(audio, 'log_fbank')
-    n_mels = N_DIMS if n_mels is None else int(n_mels)
-    off = [int(v) for v in (offsets.tolist() if torch.is_tensor(offsets) else offsets)]
-    n_utt = len(off) - 1
-    ws = int(sample_rate * 0.001 * WIN_SIZE)
-    lens = [off[i + 1] - off[i] for i in range(n_utt)]
-    if min(lens) <= ws // 2:
-        raise ValueError('log_fbank: every utterance needs more than %d samples (reflect padding), got %d'
-                         % (ws // 2, min(lens)))
-    frames = [num_frames(n, sample_rate) for n in lens]
-    foff = [0]
-    for f in frames:
-        foff.append(foff[-1] + f)
-    dev = audio.device
-    if out is None:
-        out = torch.empty(foff[-1], n_mels, device=dev, dtype=torch.float32)
-    off_d = torch.tensor(off, dtype=torch.int64, device=dev)
-    foff_d = torch.tensor(foff, dtype=torch.int64, device=dev)
-    audio = audio.contiguous()
-    for u0 in range(0, n_utt, MAX_UTT_PER_CALL):
-        u1 = min(n_utt, u0 + MAX_UTT_PER_CALL)
-        check(lib.ssasr_fbank(ptr(audio), off_d.data_ptr() + 8 * u0, u1 - u0, int(sample_rate), n_mels, ptr(out),
-                              foff_d.data_ptr() + 8 * u0, max(frames[u0:u1]), stream()), 'ssasr_fbank')
-    return out, foff
+    plan = FbankPlan(offsets, sample_rate, n_mels, device=audio.device)
+    return plan.run(audio, out), plan.foff
 
 
 def log_fbank_batch(ys, sample_rate, n_mels=None, device='cuda'):
