@@ -86,12 +86,18 @@ typedef struct {
   const float* enc;         /* [B,Tp,E] listener output */
   const int* enc_lens;      /* [B] */
   int* tok_in;              /* [B,U] input token per step (col 0 = <sos>=0; teacher columns pre-filled) */
-  const int* step_mode;     /* HOST [U] or NULL: token after step t: 0 teacher, 1 argmax, 2 sample */
+  const int* step_mode;     /* HOST [U] or NULL: token after step t: 0 teacher, 1 argmax, 2 sample, 3 argmax with LM */
   unsigned long long seed;
   float *psi, *xin1, *xin2, *act1, *act2, *c1, *c2, *h2all, *q, *alpha, *logits; /* outputs + saved state */
   const void *w1cat_bf, *w2cat_bf; /* bf16 copies of w1cat/w2cat, or NULL (fp32 path) */
   void* ws_bf;                     /* bf16 scratch [B, max(X1,X2)], or NULL */
   void* enc_bf;                    /* bf16 scratch [(B*Tp + M) * E], or NULL */
+  /* character LM for step mode 3 (ASR.decode with lm_weight != 0, asr.py:153-162 + charlm.py:46-57):
+     GRU / output weights TRANSPOSED to [in,out], biases, and the two [B,H] hidden states (updated in place) */
+  int lm_H;
+  float lm_weight;
+  const float *lm_emb, *lm_w1i, *lm_w1h, *lm_b1i, *lm_b1h, *lm_w2i, *lm_w2h, *lm_b2i, *lm_b2h, *lm_wo, *lm_bo;
+  float *lm_h1, *lm_h2;
 } ssasr_speller_fwd_args;
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
 

@@ -16,7 +16,10 @@ class SpellerFwdArgs(C.Structure):
                                            'enc', 'enc_lens', 'tok_in', 'step_mode')] +
                 [('seed', C.c_ulonglong)] +
                 [(n, C.c_void_p) for n in ('psi', 'xin1', 'xin2', 'act1', 'act2', 'c1', 'c2', 'h2all', 'q', 'alpha',
-                                           'logits', 'w1cat_bf', 'w2cat_bf', 'ws_bf', 'enc_bf')])
+                                           'logits', 'w1cat_bf', 'w2cat_bf', 'ws_bf', 'enc_bf')] +
+                [('lm_H', C.c_int), ('lm_weight', C.c_float)] +
+                [(n, C.c_void_p) for n in ('lm_emb', 'lm_w1i', 'lm_w1h', 'lm_b1i', 'lm_b1h', 'lm_w2i', 'lm_w2h', 'lm_b2i',
+                                           'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2')])
 
 
 class SpellerBwdArgs(C.Structure):

@@ -194,12 +194,12 @@ class ASR(nn.Module):
         self.init_parameters()
 
     # ------------------------------------------------------------------------------------------
-    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32'):
+    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None):
         lens_dev = torch.tensor(enc_len, dtype=torch.int32, device=enc.device)
         params = self.attention.params() + self.decoder.params() + (self.embed.weight, self.char_trans.weight,
                                                                     self.char_trans.bias)
         self.sample_seed += 1
-        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision)
+        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision, lm)
 
     def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
         """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
@@ -225,9 +225,10 @@ class ASR(nn.Module):
         return encode_len, logits, (att if self.att_on_device else att.cpu())
 
     @torch.no_grad()
-    def decode_batch(self, xs, x_lens, max_steps=200):
+    def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0):
         """Greedy decoding of many utterances at once with the per-utterance (bs=1) semantics of ASR.decode:
-        xs [N,T,F] zero-padded, x_lens sorted in decreasing order.  Returns a list of token-id lists."""
+        xs [N,T,F] zero-padded, x_lens sorted in decreasing order; optional CharLM rescoring (asr.py:153-159).
+        Returns a list of token-id lists."""
         prev = self.encoder.utterance_independent
         self.encoder.utterance_independent = True
         try:
@@ -236,7 +237,10 @@ class ASR(nn.Module):
             self.encoder.utterance_independent = prev
         N = xs.shape[0]
         tok_in = torch.zeros(N, max_steps + 1, dtype=torch.int32, device=enc.device)
-        _, _, toks = self._spell(enc, enc_len, tok_in, [1] * (max_steps + 1))
+        lm = None
+        if rnn_lm is not None and lm_weight != 0:
+            lm = (Fk.pack_charlm(rnn_lm, enc.device), lm_weight)
+        _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), lm=lm)
         toks = toks[:, 1:].cpu().tolist()
         out = []
         for row in toks:
@@ -251,9 +255,7 @@ class ASR(nn.Module):
     def decode(self, x, x_len, rnn_lm, mapper, lm_weight):
         """asr.py:112-173 (bs=1).  lm_weight == 0 runs entirely in the fused kernels."""
         assert len(x.shape) == 3 and x.shape[0] == 1
-        if lm_weight != 0:
-            raise NotImplementedError('decode with a language model (lm_weight != 0) is not wired yet')
-        ids = self.decode_batch(x, x_len)[0]
+        ids = self.decode_batch(x, x_len, rnn_lm=rnn_lm, lm_weight=lm_weight)[0]
         return ''.join(mapper.ind_to_char(i) for i in ids)
 
     # ------------------------------------------------------------------------------------------

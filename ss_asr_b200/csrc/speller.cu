@@ -287,6 +287,89 @@ __global__ void pick_token_kernel(int B, int C, const float* __restrict__ logits
 }
 
 // ------------------------------------------------------------------------------------------------
+// greedy step with the character LM of ASR.decode (asr.py:153-162, charlm.py:46-57): one CTA per utterance runs
+// Embedding -> GRUCell -> GRUCell -> Linear, combines log_softmax(asr) + w * log_softmax(lm) and takes the argmax.
+// Weights are passed transposed ([in, out]) so that the per-unit dot products read coalesced columns.
+// ------------------------------------------------------------------------------------------------
+struct LmStep {
+  int C, H;
+  const float *emb, *w1i, *w1h, *b1i, *b1h, *w2i, *w2h, *b2i, *b2h, *wo, *bo;   // w*: [H,3H] transposed, wo: [H,C]
+  float *h1, *h2;                  // [B,H] state, updated in place
+  float weight;
+  const float* logits; long long logits_ld;
+  const int* tok_in; int* tok_out; long long tok_ld;
+};
+
+__device__ __forceinline__ float gru_unit(const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ wi,
+                                          const float* __restrict__ wh, const float* __restrict__ bi, const float* __restrict__ bh,
+                                          int H, int j) {
+  float ir = bi[j], iz = bi[H + j], in = bi[2 * H + j], hr = bh[j], hz = bh[H + j], hn = bh[2 * H + j];
+  for (int k = 0; k < H; ++k) {
+    const float xv = x[k], hv = h[k];
+    const float* wik = wi + (size_t)k * 3 * H;
+    const float* whk = wh + (size_t)k * 3 * H;
+    ir = fmaf(xv, wik[j], ir); iz = fmaf(xv, wik[H + j], iz); in = fmaf(xv, wik[2 * H + j], in);
+    hr = fmaf(hv, whk[j], hr); hz = fmaf(hv, whk[H + j], hz); hn = fmaf(hv, whk[2 * H + j], hn);
+  }
+  const float r = sigmoidf_acc(ir + hr), z = sigmoidf_acc(iz + hz);
+  const float n = tanhf(in + r * hn);
+  return (1.f - z) * n + z * h[j];
+}
+
+__global__ void lm_pick_kernel(LmStep a) {
+  extern __shared__ float sm[];
+  float* x = sm;                 // [H]
+  float* h1 = x + a.H;           // [H]
+  float* h2 = h1 + a.H;          // [H]
+  float* h1n = h2 + a.H;         // [H]
+  float* h2n = h1n + a.H;        // [H]
+  float* lm = h2n + a.H;         // [C]
+  float* scratch = lm + a.C;     // [32]
+  const int b = blockIdx.x, tid = threadIdx.x, H = a.H, C = a.C;
+  const int tok = a.tok_in[(size_t)b * a.tok_ld];
+  for (int j = tid; j < H; j += blockDim.x) {
+    x[j] = a.emb[(size_t)tok * H + j];
+    h1[j] = a.h1[(size_t)b * H + j];
+    h2[j] = a.h2[(size_t)b * H + j];
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += blockDim.x) h1n[j] = gru_unit(x, h1, a.w1i, a.w1h, a.b1i, a.b1h, H, j);
+  __syncthreads();
+  for (int j = tid; j < H; j += blockDim.x) h2n[j] = gru_unit(h1n, h2, a.w2i, a.w2h, a.b2i, a.b2h, H, j);
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = a.bo[c];
+    for (int k = 0; k < H; ++k) s = fmaf(h2n[k], a.wo[(size_t)k * C + c], s);
+    lm[c] = s;
+  }
+  for (int j = tid; j < H; j += blockDim.x) {
+    a.h1[(size_t)b * H + j] = h1n[j];
+    a.h2[(size_t)b * H + j] = h2n[j];
+  }
+  __syncthreads();
+  const float* lg = a.logits + (size_t)b * a.logits_ld;
+  float ml = -INFINITY, ma = -INFINITY;
+  for (int c = tid; c < C; c += blockDim.x) { ml = fmaxf(ml, lm[c]); ma = fmaxf(ma, lg[c]); }
+  ml = block_max(ml, scratch);
+  ma = block_max(ma, scratch);
+  float sl = 0.f, sa = 0.f;
+  for (int c = tid; c < C; c += blockDim.x) { sl += expf(lm[c] - ml); sa += expf(lg[c] - ma); }
+  sl = block_sum(sl, scratch);
+  sa = block_sum(sa, scratch);
+  const float lse_l = ml + logf(sl), lse_a = ma + logf(sa);
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) lm[c] = (lg[c] - lse_a) + a.weight * (lm[c] - lse_l);
+  __syncthreads();
+  if (tid == 0) {
+    int best = 0;
+    float mx = lm[0];
+    for (int c = 1; c < C; ++c)
+      if (lm[c] > mx) { mx = lm[c]; best = c; }
+    a.tok_out[(size_t)b * a.tok_ld] = best;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused cross-entropy (trainer.py:426-434): loss and dL/dlogits in one pass.  One CTA per utterance.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ce_kernel(int B, int U, int C, int L, const float* __restrict__ logits,
@@ -355,6 +438,11 @@ typedef struct {
   const void *w1cat_bf, *w2cat_bf;
   void* ws_bf;
   void* enc_bf;   // bf16 scratch [(B*Tp + M) * E], or NULL
+  // character LM for step_mode 3 (ASR.decode with lm_weight != 0): transposed GRU / output weights, state [B,H]
+  int lm_H;
+  float lm_weight;
+  const float *lm_emb, *lm_w1i, *lm_w1h, *lm_b1i, *lm_b1h, *lm_w2i, *lm_w2h, *lm_b2i, *lm_b2h, *lm_wo, *lm_bo;
+  float *lm_h1, *lm_h2;
 } ssasr_speller_fwd_args;
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
@@ -424,8 +512,21 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
                     0, 0);
       if (rc) return rc;
       { ProfScope ps(F_POINTWISE, st); }
-      pick_token_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
-                                                         (unsigned long long)t, a->tok_in + t + 1, U);
+      if (mode == 3) {
+        SSASR_REQUIRE(a->lm_emb && a->lm_h1 && a->lm_h2 && a->lm_H > 0, "speller: step mode 3 needs the language-model arguments");
+        LmStep l;
+        l.C = C; l.H = a->lm_H;
+        l.emb = a->lm_emb; l.w1i = a->lm_w1i; l.w1h = a->lm_w1h; l.b1i = a->lm_b1i; l.b1h = a->lm_b1h;
+        l.w2i = a->lm_w2i; l.w2h = a->lm_w2h; l.b2i = a->lm_b2i; l.b2h = a->lm_b2h; l.wo = a->lm_wo; l.bo = a->lm_bo;
+        l.h1 = a->lm_h1; l.h2 = a->lm_h2; l.weight = a->lm_weight;
+        l.logits = a->logits + (size_t)t * C; l.logits_ld = (long long)U * C;
+        l.tok_in = a->tok_in + t; l.tok_out = a->tok_in + t + 1; l.tok_ld = U;
+        const int nt = ((a->lm_H + 31) / 32) * 32 > 256 ? 256 : ((a->lm_H + 31) / 32) * 32;
+        lm_pick_kernel<<<B, nt, (size_t)(5 * a->lm_H + C + 32) * sizeof(float), st>>>(l);
+      } else {
+        pick_token_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
+                                                           (unsigned long long)t, a->tok_in + t + 1, U);
+      }
     }
   }
   rc = gemm_f32(st, B * U, C, Sd, a->h2all, Sd, 1, a->wc, Sd, 1, a->logits, C, a->bc, 0, 0);

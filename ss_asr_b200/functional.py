@@ -132,7 +132,7 @@ class _Spell(torch.autograd.Function):
     """U steps of attention + 2 LSTM cells + character projection (asr.py:65-110)."""
 
     @staticmethod
-    def forward(ctx, enc, enc_lens_dev, tok_in, step_mode, seed, precision, phi_w, psi_w, psi_b, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2,
+    def forward(ctx, enc, enc_lens_dev, tok_in, step_mode, seed, precision, lm, phi_w, psi_w, psi_b, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2,
                 w_hh2, b_ih2, b_hh2, emb_w, wc, bc):
         lib = _lib.load()
         _lib.require_cuda(enc, 'Speller')
@@ -166,13 +166,20 @@ class _Spell(torch.autograd.Function):
             check(lib.ssasr_cvt_bf16(ptr(w1cat), X1, ptr(w1b), X1, 4 * Sd, X1, st), 'ssasr_cvt_bf16')
             check(lib.ssasr_cvt_bf16(ptr(w2cat), X2, ptr(w2b), X2, 4 * Sd, X2, st), 'ssasr_cvt_bf16')
         ctx.bf16 = bf16
+        lmk = {}
+        if lm is not None:      # (dict of transposed fp32 tensors, weight): greedy decode with the character LM
+            lmt, lm_weight = lm
+            H = lmt['emb'].shape[1]
+            lm_state = [torch.zeros(B, H, device=dev), torch.zeros(B, H, device=dev)]
+            lmk = dict(lm_H=H, lm_weight=float(lm_weight), lm_h1=ptr(lm_state[0]), lm_h2=ptr(lm_state[1]),
+                       **{'lm_' + k: ptr(v) for k, v in lmt.items()})
         a = _lib.SpellerFwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
                                 psi_b=ptr(psi_b), w1cat=ptr(w1cat), b1=ptr(b1), w2cat=ptr(w2cat), b2=ptr(b2),
                                 emb_w=ptr(emb_w), wc=ptr(wc), bc=ptr(bc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
                                 tok_in=ptr(tok_in), step_mode=C.cast(modes, C.c_void_p), seed=int(seed), psi=ptr(psi),
                                 xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
                                 h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits), w1cat_bf=ptr(w1b),
-                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb))
+                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), **lmk)
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
@@ -221,11 +228,21 @@ class _Spell(torch.autograd.Function):
         g2 = [z(4 * Sd, Sd), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
         check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w1cat), ptr(d_b1), Sd, K1, *[ptr(t) for t in g1], st), 'unpack1')
         check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w2cat), ptr(d_b2), Sd, Sd, *[ptr(t) for t in g2], st), 'unpack2')
-        return (denc, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
+        return (denc, None, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
 
 
-def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32'):
-    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, *params)
+def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32', lm=None):
+    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, lm, *params)
+
+
+def pack_charlm(rnn_lm, device):
+    """CharLM (charlm.py:5-44) parameters -> the transposed fp32 tensors the LM step kernel reads."""
+    sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in rnn_lm.state_dict().items()}
+    t = lambda k: sd[k].t().contiguous()
+    return {'emb': sd['emb.weight'].contiguous(), 'w1i': t('layer_1.weight_ih'), 'w1h': t('layer_1.weight_hh'),
+            'b1i': sd['layer_1.bias_ih'].contiguous(), 'b1h': sd['layer_1.bias_hh'].contiguous(),
+            'w2i': t('layer_2.weight_ih'), 'w2h': t('layer_2.weight_hh'), 'b2i': sd['layer_2.bias_ih'].contiguous(),
+            'b2h': sd['layer_2.bias_hh'].contiguous(), 'wo': t('out.weight'), 'bo': sd['out.bias'].contiguous()}
 
 
 # --------------------------------------------------------------------------------------------------

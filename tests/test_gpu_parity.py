@@ -24,6 +24,17 @@ def _model(dims, sd, tf=1.0):
     return m
 
 
+class _CharLM(torch.nn.Module):
+    """Same parameter structure as the reference CharLM (charlm.py:5-44); only its state_dict is consumed."""
+
+    def __init__(self, n=50, h=128):
+        super().__init__()
+        self.emb = torch.nn.Embedding(n, h)
+        self.layer_1 = torch.nn.GRUCell(h, h)
+        self.layer_2 = torch.nn.GRUCell(h, h)
+        self.out = torch.nn.Linear(h, n)
+
+
 def _check_grads(model, ref_grads, rel=1e-4):
     gtot = float(torch.sqrt(sum(torch.as_tensor(v).double().pow(2).sum() for v in ref_grads.values())))
     for k, p in model.named_parameters():
@@ -163,9 +174,16 @@ def test_tiny_golden_greedy_and_decode(golden_dir):
     class Mapper:
         def ind_to_char(self, i):
             return O.TOKENS[i]
+    lm = _CharLM()
+    lm.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('lm.')})
     for i in range(len(z['decode_lm0'])):
         xi = x[i:i + 1, :lens[i]].to(DEV)
         assert m.decode(xi, [lens[i]], None, Mapper(), 0.0) == str(z['decode_lm0'][i])
+        got, want = m.decode(xi, [lens[i]], lm, Mapper(), 0.5), str(z['decode_lm05'][i])
+        ids, margin = O.decode_greedy(sd, x[i:i + 1, :lens[i]], [lens[i]], {k[3:]: torch.from_numpy(z[k]) for k in z.files
+                                                                             if k.startswith('lm.')}, 0.5, return_margin=True)
+        n = min(len(got), len(want), 20)
+        assert got[:n] == want[:n] and (margin < 1e-4 or got == want)
 
 
 def test_default_dims_golden(golden_dir):
@@ -250,6 +268,11 @@ def test_decode_default_margin_strings(golden_dir):
     ids = m.decode_batch(xb.to(DEV), [Ts[i] for i in order])
     for j, i in enumerate(order):
         assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
+    lm = _CharLM()
+    lm.load_state_dict(O.make_charlm_state_dict(50, 128, seed=7))
+    ids = m.decode_batch(xb.to(DEV), [Ts[i] for i in order], rnn_lm=lm, lm_weight=0.5)
+    for j, i in enumerate(order):
+        assert O.ids_to_str(ids[j]) == str(z['margin_lm05'][i]), i
 
 
 def test_teacher_forcing_draws_follow_python_rng():
@@ -340,3 +363,24 @@ def test_bf16_training_path(dims, B, T, U):
         _, gl, _ = m(x.to(DEV), 4, state_len=lens)
         _, gl_o, _, _ = O.asr_forward(sd, x, lens, 4)
     assert float((gl.cpu() - gl_o).abs().max()) < 1e-5
+
+
+def test_tc_recurrence_many_tiles_per_cta():
+    """Encoder with more 128-row batch tiles than tile groups (each CTA loops over several tiles)."""
+    dims = (50, 256, 32, 16, 16)
+    sd = O.make_state_dict(*dims, seed=2)
+    B, T = 600, 16
+    x, lens, _ = O.synth_batch(B, T, 16, 4, seed=9)
+    m = _model(dims, sd)
+    with torch.no_grad():
+        eo, _ = O.listener(sd, x, lens)
+    m.encoder.set_precision('bf16')
+    xd = x.to(DEV).requires_grad_(True)
+    e, el = m.encoder(xd, lens)
+    assert float((e.detach().cpu() - eo).abs().max()) < 2e-2
+    e.sum().backward()
+    xg = x.clone().requires_grad_(True)
+    p = {k: v.clone() for k, v in sd.items()}
+    O.listener(p, xg, lens)[0].sum().backward()
+    a, b = xd.grad.cpu().double(), xg.grad.double()
+    assert float((a - b).norm()) <= 3e-2 * float(b.norm())
