@@ -61,6 +61,9 @@ int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
  *      inside nn.LSTM forward/backward (asr.py:414,262; trainer.py:437). ---- */
 int ssasr_gemm_bf16_tc(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                        int b_koff, float* C, int ldc, const float* bias, int accumulate, void* stream);
+/* C[M,N] fp32 (+)= A^T B; A stored [K,M], B stored [K,N] row-major bf16 (the weight-gradient form dW = dG^T X) */
+int ssasr_gemm_bf16_tc_tn(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
+                          int b_koff, float* C, int ldc, int accumulate, void* stream);
 int ssasr_cvt_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream);
 int ssasr_cvt_bf16_t(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
                      int mask_period, int mask_pos_lo, int mask_pos_hi, int mask_split, void* stream);
@@ -76,6 +79,10 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf 
                          float* dbias_p, float* dwhh_p, float* dcstate, unsigned* bar, int zero_period, long long Rp,
                          void* dgb_ws /*[n_rows,8S]*/, void* dgT_ws /*[8S,Rp]*/, void* xT_ws /*[K,Rp]*/,
                          void* hT_ws /*[2S,Rp]*/, const void* whhT_bf /*[2S,4S] bf16 or NULL => fp32 recurrence*/,
+                         const void* xb_saved /*[n_rows,Kp] bf16 x of the forward pass, or NULL*/, int Kp,
+                         void* hb_saved /*[n_rows,2S] bf16 h of the forward pass (masked in place), or NULL;
+                                          with both set the weight gradients use the MN-major GEMM and dgT/xT/hT_ws
+                                          may be NULL*/,
                          void* stream);
 
 /* ---- attend-and-spell loop: Attention.forward asr.py:343-392 + Speller.forward asr.py:314-326 + the decode loop

@@ -68,6 +68,23 @@ def tc_check():
     print('gemm_tc %dx%dx%d: %.3f ms, %.1f TFLOP/s' % (M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
 
 
+def tn_check():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K, ak, bk) in [(128, 128, 64, 0, 0), (128, 128, 128, 0, 0), (256, 256, 512, 0, 0), (2048, 80, 4096, 0, 0),
+                              (1024, 256, 1000, 1, 0), (1024, 256, 1000, 0, 3), (50, 256, 333, 0, 0)]:
+        Kt = K + max(ak, bk)
+        Mp, Np = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+        A = torch.randn(Kt, Mp, generator=g).to(dev).to(torch.bfloat16)
+        B = torch.randn(Kt, Np, generator=g).to(dev).to(torch.bfloat16)
+        ref = A[ak:ak + K, :M].double().t() @ B[bk:bk + K, :N].double()
+        C = torch.zeros(M, N, device=dev)
+        _lib.check(lib.ssasr_gemm_bf16_tc_tn(M, N, K, A.data_ptr(), Mp, ak, B.data_ptr(), Np, bk, C.data_ptr(), N, 0, _lib.stream()),
+                   'gemm_tc_tn')
+        torch.cuda.synchronize()
+        print('gemm_tc_tn', (M, N, K, ak, bk), 'max err', float((C.double() - ref).abs().max()), 'ref max', float(ref.abs().max()))
+
+
 def bf16_check(dims=(50, 256, 256, 128, 80), B=8, T=128, U=20):
     sd = O.make_state_dict(*dims, seed=1)
     x, lens, y = O.synth_batch(B, T, dims[4], U, seed=1234)
@@ -174,6 +191,8 @@ if __name__ == '__main__':
         gemm_check()
     if 'tc' in which:
         tc_check()
+    if 'tn' in which:
+        tn_check()
     if 'bf16' in which:
         bf16_check()
         bf16_check((50, 32, 48, 16, 20), 7, 64, 9)

@@ -48,11 +48,12 @@ SIGNATURES = {
     'ssasr_blstm_bwd_f32': (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _I, _P]),
     'ssasr_gemm_bf16_tc': (_I, [_I, _I, _I, _P, _LL, _I, _P, _LL, _I, _P, _I, _P, _I, _P]),
+    'ssasr_gemm_bf16_tc_tn': (_I, [_I, _I, _I, _P, _LL, _I, _P, _LL, _I, _P, _I, _I, _P]),
     'ssasr_cvt_bf16': (_I, [_P, _LL, _P, _LL, _LL, _I, _P]),
     'ssasr_cvt_bf16_t': (_I, [_P, _LL, _P, _LL, _LL, _I, _I, _I, _I, _I, _P]),
     'ssasr_blstm_fwd_bf16': (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_blstm_bwd_bf16': (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                  _I, _LL, _P, _P, _P, _P, _P, _P]),
+                                  _I, _LL, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     'ssasr_speller_fwd_f32': (_I, [C.POINTER(SpellerFwdArgs), _P]),
     'ssasr_speller_bwd_f32': (_I, [C.POINTER(SpellerBwdArgs), _P]),
     'ssasr_ce_loss_f32': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P]),

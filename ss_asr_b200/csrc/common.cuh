@@ -88,6 +88,10 @@ int gemm_f32(cudaStream_t st, int M, int N, int K, const float* A, int lda, int 
 // a_koff/b_koff shift the reduction window inside each operand's rows.
 int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                  int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh = 0);
+// C[M,N] fp32 (+)= A^T B with A stored [K,M], B stored [K,N] (row-major bf16, 16-byte row pitches); koffs shift rows
+int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
+                    int b_koff, float* C, int ldc, int accumulate);
+int mask_rows_bf16(cudaStream_t st, void* x, long long rows, int cols, int period, int pos_lo, int pos_hi, int split);
 int cvt_bf16(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols);
 int cvt_bf16_t(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
                int mask_period, int mask_pos_lo, int mask_pos_hi, int mask_split, int shift_lo = 0, int shift_hi = 0);

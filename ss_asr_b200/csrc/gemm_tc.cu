@@ -135,6 +135,103 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tmem_dealloc<BN>(tmem_base);
 }
 
+// ---- TN variant: C[M,N] = A^T B with A stored [K,M] and B stored [K,N] (both M/N-contiguous, "MN-major") --------
+// Used for the weight gradients dW = dG^T X directly from the row-major bf16 activations / gate gradients, so no
+// transposed copies are needed.  a_koff / b_koff shift the reduction ROW window of each operand (any integer:
+// rows are the outer TMA dimension).
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+                  int ldc, int M, int N, int K, int a_koff, int b_koff, int accumulate) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  constexpr int BLK = 64 * GT_BK * 2;      // one {64 mn, 64 k} box = 8 KB
+
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * BN;
+  const int num_k = (K + GT_BK - 1) / GT_BK;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
+        uint8_t* st = smem + s * L::STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < GT_BM / 64; ++i) tma_load_2d(&tmA, full_bar + s, st + i * BLK, m0 + 64 * i, a_koff + kb * GT_BK);
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, full_bar + s, st + L::A_BYTES + i * BLK, n0 + 64 * i, b_koff + kb * GT_BK);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GT_BM, BN, 1, 1);
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t da = umma_desc_mn128(a_addr, BLK);
+        const uint64_t db = umma_desc_mn128(a_addr + L::A_BYTES, BLK);
+#pragma unroll
+        for (int k = 0; k < GT_BK / 16; ++k)   // 16 k rows = 2 swizzle atoms = 2048 B per K=16 step
+          mma_bf16_ss(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (kb | k) != 0);
+        mma_commit(empty_bar + s);
+      }
+      mma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = m0 + ew * 32 + (threadIdx.x & 31);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < N) {
+            float o = __uint_as_float(v[j]);
+            if (accumulate) o += crow[c0 + j];
+            crow[c0 + j] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<BN>(tmem_base);
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -164,6 +261,36 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long co
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SSASR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+  return 0;
+}
+
+// 2-D bf16 tensor [rows, cols] (row pitch ld) read as MN-major operand blocks: box = {64 cols, 64 rows}
+int make_tmap_bf16_mn(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld) {
+  return make_tmap_bf16(m, ptr, rows, cols, ld, GT_BK);
+}
+
+// C[M,N] fp32 (+)= A^T B;  A stored [>= a_koff+K rows, M cols] (lda), B stored [>= b_koff+K rows, N cols] (ldb), bf16
+int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
+                    int b_koff, float* C, int ldc, int accumulate) {
+  if (M <= 0 || N <= 0) return 0;
+  SSASR_REQUIRE(K > 0, "gemm_bf16_tc_tn: K must be positive");
+  constexpr int BN = 128, STAGES = 6;
+  using L = GemmSmem<BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_mn(&tmA, A, (long long)a_koff + K, M, lda);
+  if (rc) return rc;
+  rc = make_tmap_bf16_mn(&tmB, B, (long long)b_koff + K, N, ldb);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_tn_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024));
+    attr_set = true;
+  }
+  dim3 grid((M + GT_BM - 1) / GT_BM, (N + BN - 1) / BN);
+  SSASR_REQUIRE(grid.y <= 65535, "gemm_bf16_tc_tn: N=%d too large", N);
+  ProfScope ps(F_GEMM_TC, st);
+  gemm_tc_tn_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, accumulate);
+  SSASR_LAUNCH_CHECK();
   return 0;
 }
 
@@ -264,6 +391,27 @@ __global__ void cvt_bf16_t_kernel(const float* __restrict__ src, long long ld_sr
   }
 }
 
+// zeroes, in a bf16 [rows, cols] matrix, the rows with (r % period) == pos_lo for columns < split and the rows with
+// (r % period) == pos_hi for columns >= split
+__global__ void mask_rows_bf16_kernel(__nv_bfloat16* __restrict__ x, long long rows, int cols, int period, int pos_lo, int pos_hi,
+                                      int split) {
+  const long long nper = (rows + period - 1) / period;
+  const long long total = nper * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long u = i / cols;
+    const int c = (int)(i % cols);
+    const long long r = u * period + (c < split ? pos_lo : pos_hi);
+    if (r < rows) x[r * cols + c] = __float2bfloat16(0.f);
+  }
+}
+int mask_rows_bf16(cudaStream_t st, void* x, long long rows, int cols, int period, int pos_lo, int pos_hi, int split) {
+  if (period <= 0 || rows <= 0) return 0;
+  ProfScope ps(F_PACK, st);
+  mask_rows_bf16_kernel<<<256, 256, 0, st>>>((__nv_bfloat16*)x, rows, cols, period, pos_lo, pos_hi, split);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
 int cvt_bf16(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols) {
   if (rows <= 0 || cols <= 0) return 0;
   ProfScope ps(F_PACK, st);
@@ -292,6 +440,10 @@ extern "C" {
 int ssasr_gemm_bf16_tc(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb, int b_koff,
                        float* C, int ldc, const float* bias, int accumulate, void* stream) {
   return gemm_bf16_tc((cudaStream_t)stream, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, 0);
+}
+int ssasr_gemm_bf16_tc_tn(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb, int b_koff,
+                          float* C, int ldc, int accumulate, void* stream) {
+  return gemm_bf16_tc_tn((cudaStream_t)stream, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, accumulate);
 }
 int ssasr_cvt_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, void* stream) {
   return cvt_bf16((cudaStream_t)stream, src, ld_src, dst, ld_dst, rows, cols);

@@ -16,6 +16,7 @@
 // monotonic-counter barrier once per step.  No per-step launches, no pack/unpack copies: lengths
 // are masks.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace ssasr {
 
@@ -540,7 +541,7 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
                          int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* act, const float* hout,
                          const float* cbuf, const float* dhout, float* dx, float* dwih_p, float* dbias_p, float* dwhh_p,
                          float* dcstate, unsigned* bar, int zero_period, long long Rp, void* dgb_ws, void* dgT_ws, void* xT_ws,
-                         void* hT_ws, const void* whhT_bf, void* stream) {
+                         void* hT_ws, const void* whhT_bf, const void* xb_saved, int Kp, void* hb_saved, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(Rp % 8 == 0 && Rp >= n_rows, "blstm_bwd_bf16: bad Rp=%lld (n_rows=%d)", Rp, n_rows);
   int rc;
@@ -571,6 +572,27 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
     rc = gemm_bf16_tc(st, n_rows, K, 8 * S, dgb_ws, 8 * S, 0, wihT_bf, 8 * S, 0, dx, K, nullptr, 0);
     if (rc) return rc;
   }
+  const int sh = (int)rs_seq;
+  if (tc_rec && xb_saved && hb_saved && Kp % 8 == 0) {
+    // weight gradients straight from the row-major bf16 buffers (MN-major tcgen05 operands): no transposed copies.
+    // dgb_ws holds the complete bf16 dG (exchange buffer of the recurrent kernel), xb_saved / hb_saved the bf16 x and h
+    // of the forward pass; h rows without a forward-order predecessor are zeroed per direction first.
+    rc = gemm_bf16_tc_tn(st, 8 * S, K, n_rows, dgb_ws, 8 * S, 0, xb_saved, Kp, 0, dwih_p, K, 0);
+    if (rc) return rc;
+    rc = mask_rows_bf16(st, hb_saved, n_rows, 2 * S, zero_period, zero_period > 0 ? zero_period - 1 : 0, 0, S);
+    if (rc) return rc;
+    if (n_rows - sh > 0) {
+      const __nv_bfloat16* dgb = (const __nv_bfloat16*)dgb_ws;
+      const __nv_bfloat16* hb = (const __nv_bfloat16*)hb_saved;
+      rc = gemm_bf16_tc_tn(st, 4 * S, S, n_rows - sh, dgb, 8 * S, sh, hb, 2 * S, 0, dwhh_p, S, 0);
+      if (rc) return rc;
+      rc = gemm_bf16_tc_tn(st, 4 * S, S, n_rows - sh, dgb + 4 * S, 8 * S, 0, hb + S, 2 * S, sh, dwhh_p + (size_t)4 * S * S, S, 0);
+      if (rc) return rc;
+    } else {
+      SSASR_CHECK_CUDA(cudaMemsetAsync(dwhh_p, 0, sizeof(float) * 8 * S * S, st));
+    }
+    return 0;
+  }
   rc = cvt_bf16_t(st, dg, 8 * S, dgT_ws, Rp, n_rows, 8 * S, 0, 0, 0, 0);
   if (rc) return rc;
   rc = cvt_bf16_t(st, x, K, xT_ws, Rp, n_rows, K, 0, 0, 0, 0);
@@ -579,7 +601,6 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
   if (rc) return rc;
   // h transposed AND shifted to its consumer row (fwd: h[r-sh] -> column r, rev: h[r+sh] -> column r), with the frame
   // that has no forward-order predecessor zeroed per direction; then dW_hh[d] = dG_d^T . hshift_d over all rows.
-  const int sh = (int)rs_seq;
   SSASR_CHECK_CUDA(cudaMemsetAsync(hT_ws, 0, (size_t)2 * S * Rp * 2, st));
   rc = cvt_bf16_t(st, hout, 2 * S, hT_ws, Rp, n_rows, 2 * S, zero_period, zero_period > 0 ? zero_period - 1 : 0, 0, S, sh, -sh);
   if (rc) return rc;

@@ -569,12 +569,13 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                    a->BTp >= (long long)B * Tp && a->BTp % 8 == 0 && Sd % 8 == 0 && E % 8 == 0 && M % 8 == 0;
   // out[Mo,No] = X^T Y over R rows (X [R,Mo] ldx, Y [R,No] ldy): tensor cores through transposed bf16 copies, or fp32
   auto xty = [&](const float* X, int ldx, int Mo, const float* Y, int ldy, int No, long long R, long long Rp, float* out) -> int {
-    if (tc0) {
-      int r = cvt_bf16_t(st, X, ldx, a->wsA, Rp, R, Mo, 0, 0, 0, 0);
+    if (tc0) {     // row-major bf16 copies, MN-major tcgen05 operands
+      const int Mp = (Mo + 7) / 8 * 8, Np = (No + 7) / 8 * 8;
+      int r = cvt_bf16(st, X, ldx, a->wsA, Mp, R, Mo);
       if (r) return r;
-      r = cvt_bf16_t(st, Y, ldy, a->wsB, Rp, R, No, 0, 0, 0, 0);
+      r = cvt_bf16(st, Y, ldy, a->wsB, Np, R, No);
       if (r) return r;
-      return gemm_bf16_tc(st, Mo, No, (int)R, a->wsA, Rp, 0, a->wsB, Rp, 0, out, No, nullptr, 0);
+      return gemm_bf16_tc_tn(st, Mo, No, (int)R, a->wsA, Mp, 0, a->wsB, Np, 0, out, No, 0);
     }
     return gemm_f32(st, Mo, No, (int)R, X, ldx, 0, Y, ldy, 0, out, No, nullptr, 0, 0);
   };
@@ -602,11 +603,11 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   // dW = dG_all^T @ X_all over all B*U rows
   auto wgrad_gemm = [&](const float* dg, const float* x, int N, float* out) -> int {
     if (tc) {
-      int r = cvt_bf16_t(st, dg, 4 * Sd, a->wsA, a->BUp, (long long)B * U, 4 * Sd, 0, 0, 0, 0);
+      int r = cvt_bf16(st, dg, 4 * Sd, a->wsA, 4 * Sd, (long long)B * U, 4 * Sd);
       if (r) return r;
-      r = cvt_bf16_t(st, x, N, a->wsB, a->BUp, (long long)B * U, N, 0, 0, 0, 0);
+      r = cvt_bf16(st, x, N, a->wsB, N, (long long)B * U, N);
       if (r) return r;
-      return gemm_bf16_tc(st, 4 * Sd, N, B * U, a->wsA, a->BUp, 0, a->wsB, a->BUp, 0, out, N, nullptr, 0);
+      return gemm_bf16_tc_tn(st, 4 * Sd, N, B * U, a->wsA, 4 * Sd, 0, a->wsB, N, 0, out, N, 0);
     }
     return gemm_f32(st, 4 * Sd, N, B * U, dg, 4 * Sd, 0, x, N, 0, out, N, nullptr, 0, 0);
   };

@@ -129,9 +129,22 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B             bits [61,64)
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, shape M x N
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operand tile (the M/N index is the contiguous one in memory): rows of 64 bf16 (128 B) along M/N at fixed k,
+// 8 consecutive k rows form a 1024-B swizzle atom, the next 8 k rows follow at SBO = 1024 B, the next 64 M/N
+// elements at LBO = `mn_block_bytes` (one TMA box {64 mn, BK k-rows} with CU_TENSOR_MAP_SWIZZLE_128B per block).
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset: next 64-element M/N block
+  d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset: next group of 8 k rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, shape M x N; a_mn / b_mn = 1 for MN-major operands
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace tc

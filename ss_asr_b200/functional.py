@@ -73,6 +73,7 @@ class _BLSTM(torch.autograd.Function):
                                           rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
                                           ptr(bar), st), 'ssasr_blstm_fwd_f32')
         ctx.bf16 = bf16
+        ctx.fwd_bf = (xb, hb, Kp) if (bf16 and hb is not None) else None      # bf16 x / h copies reused by the weight gradients
         ctx.save_for_backward(x, wih_p, whhT_p, xp, hout, cbuf, lens_dev if time_major else torch.empty(0))
         ctx.geom = (n_rows, K, S, n_seq, n_batch, rs_seq, rs_batch, time_major, d1)
         ctx.need_dx = ctx.needs_input_grad[0]
@@ -102,12 +103,16 @@ class _BLSTM(torch.autograd.Function):
             if tc_rec:
                 whhT_bf = bf(2 * S, 4 * S)
                 check(lib.ssasr_cvt_bf16(ptr(whhT_p), 4 * S, ptr(whhT_bf), 4 * S, 2 * S, 4 * S, st), 'ssasr_cvt_bf16')
-            ws = [bf(n_rows, 8 * S) if (ctx.need_dx or tc_rec) else None, bf(8 * S, Rp), bf(K, Rp), bf(2 * S, Rp)]
+            direct = tc_rec and ctx.fwd_bf is not None
+            ws = [bf(n_rows, 8 * S) if (ctx.need_dx or tc_rec) else None] + \
+                ([None, None, None] if direct else [bf(8 * S, Rp), bf(K, Rp), bf(2 * S, Rp)])
+            xb_s, hb_s, Kp_s = ctx.fwd_bf if direct else (None, None, 0)
             check(lib.ssasr_blstm_bwd_bf16(ptr(x), n_rows, K, ptr(wihT_bf), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
                                            ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf),
                                            ptr(dhout), ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
                                            d1 if time_major else 0, Rp, ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]),
-                                           ptr(whhT_bf), st), 'ssasr_blstm_bwd_bf16')
+                                           ptr(whhT_bf), ptr(xb_s), Kp_s, ptr(hb_s), st), 'ssasr_blstm_bwd_bf16')
+            ctx.fwd_bf = None
         else:
             check(lib.ssasr_blstm_bwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
                                           ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf), ptr(dhout),
