@@ -12,7 +12,7 @@ m = pBLSTM(K, S).to(dev)
 m.precision = 'bf16'
 x = torch.randn(B, T, K, device=dev, requires_grad=True)
 lens = [T] * B
-dbg = torch.zeros(T, 8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(T, 12, dtype=torch.int64, device=dev)
 for which in ('fwd', 'bwd'):
     out, _, _ = m(x, state_len=lens, pack_input=True)
     torch.cuda.synchronize()

@@ -69,16 +69,19 @@ __device__ __forceinline__ float sigmoid_apx(float x) { return fmaf(tanh_apx(0.5
 // the TMA producer WAITS (it is the only consumer of other CTAs' data), so the rest of the epilogue (saved-tensor
 // write-out, next-step prefetch) overlaps the barrier latency and the next step's TMA + MMA.
 __device__ __forceinline__ void step_arrive(unsigned* counter) {
-  fence_proxy_async_all();
-  __threadfence();
-  atomicAdd(counter, 1u);
+  // release: orders this CTA's exchange-buffer stores (made visible to this thread by the preceding bar.sync) before
+  // the counter increment; no L1 invalidation needed on the producer side
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
 }
 __device__ __forceinline__ void step_wait(unsigned* counter, unsigned target) {
+  // poll with a relaxed load (an acquire load in the loop makes ptxas emit CCTL.IVALL + MEMBAR.GPU per iteration,
+  // which stalls the epilogue warps' global traffic); one acquire fence once the target is reached
   unsigned v, spins = 0;
   do {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     if (++spins > (1u << 26)) __trap();
   } while (v < target);
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   fence_proxy_async_all();          // acquired generic-proxy writes -> ordered before this thread's TMA (async proxy) reads
 }
 
@@ -97,7 +100,7 @@ struct RecTcParams {
   long long rs_seq, rs_batch;
   int seq_inner;             // 1: tensor-map dim1 = seq, dim2 = batch (time-major layers); 0: dim1 = batch, dim2 = seq
   unsigned* bar;             // [2 * gridDim.z]
-  long long* dbg;            // optional [n_seq][8] clock64 stamps of CTA (0,0,0); null = off
+  long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0); null = off
 };
 
 constexpr int XS_P = 68;    // fp32 row pitch of the 128 x 64 gate tile in smem (conflict-free float4 row access)
@@ -108,7 +111,7 @@ constexpr int GB_P = 72;    // bf16 row pitch of the 128 x 64 dG exchange tile
 static long long* g_dbg = nullptr;
 #define DBG_STAMP(idx)                                                                   \
   do {                                                                                   \
-    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 8 + (idx)] = clock64(); \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 12 + (idx)] = clock64(); \
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
@@ -314,6 +317,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
               *reinterpret_cast<float4*>(p.cbuf + o) = *reinterpret_cast<const float4*>(cst + rr * HS_P + c4 * 4);
             }
           }
+          if (warp == 2 && lane == 0) DBG_STAMP(8);
 #pragma unroll 4
           for (int i = 0; i < 16; ++i) {
             const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nn = bt * 128 + rr;
@@ -322,7 +326,9 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
                      *reinterpret_cast<const float4*>(xs + rr * XS_P + c4 * 4));
           }
         }
+        if (warp == 2 && lane == 0) DBG_STAMP(9);
         epi_bar();                                // staging buffers drained
+        if (warp == 2 && lane == 0) DBG_STAMP(10);
         // prefetch the xp tile of the next (step, tile) iteration
         {
           int bn = bt + Z, sn = s;
