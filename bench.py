@@ -292,8 +292,14 @@ def run_ours(args):
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md)'
     ach = (fam_flops.get(dom) or 0.0) / (fam_ms[dom] / 1e3) / 1e12 if fam_ms[dom] > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dom, {}).get('bytes_per_launch')
+    except Exception:
+        pass
     roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                'frac': ach / peak_tf, 'traffic': traffic, 'peak_source': peak_src,
+                'note': 'per-step recurrent product: latency-bound (T+T/2+T/4+B dependent steps per pass), see DESIGN.md §4',
                 'launches_per_step': fam_n[dom], 'ms_per_step_in_kernel': fam_ms[dom],
                 'share_of_step': fam_ms[dom] / (ms / args.steps),
                 'per_family_ms_per_step': {k: round(v, 3) for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])},
