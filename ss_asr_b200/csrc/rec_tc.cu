@@ -120,20 +120,20 @@ static long long* g_dbg = nullptr;
 // Epilogue data movement is staged through shared memory so that every global access is a contiguous 64-256 B
 // row segment: the xp tile of the NEXT step is prefetched with cp.async while the step barrier / TMA / MMA of
 // that step are in flight, the thread-per-batch-row cell math works on smem, results leave as coalesced stores.
-template <int KB>   // KB = S / 64 resident k-blocks
+template <int TM, int KB>   // TM = batch rows per tile (64 or 128), KB = S / 64 resident k-blocks
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW, RecTcParams p) {
   constexpr int W_BLK = 64 * 128;        // 64 gate rows x 128 B
-  constexpr int A_BLK = 128 * 128;       // 128 batch rows x 128 B
+  constexpr int A_BLK = TM * 128;        // TM batch rows x 128 B
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Wsm = smem;
   uint8_t* Asm = smem + KB * W_BLK;
   float* xs = reinterpret_cast<float*>(Asm + KB * A_BLK);                 // [128][XS_P]
-  float* hst = xs + 128 * XS_P;                                           // [128][HS_P]
-  float* cst = hst + 128 * HS_P;                                          // [128][HS_P]
-  __nv_bfloat16* hbst = reinterpret_cast<__nv_bfloat16*>(cst + 128 * HS_P);   // [128][HB_P]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hbst + 128 * HB_P);
+  float* hst = xs + TM * XS_P;                                           // [128][HS_P]
+  float* cst = hst + TM * HS_P;                                          // [128][HS_P]
+  __nv_bfloat16* hbst = reinterpret_cast<__nv_bfloat16*>(cst + TM * HS_P);   // [128][HB_P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hbst + TM * HB_P);
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
   uint64_t* mma_done = bars + 2;
@@ -168,7 +168,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   const int eg = warp & 3;                 // TMEM lane group of an epilogue warp
   const int te = threadIdx.x - 64;         // epilogue thread id 0..127 (warps 2-5)
   const bool single = p.n_tiles <= Z;      // one batch tile per CTA: cell state lives in registers
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+  constexpr uint32_t idesc = umma_idesc_bf16(TM, 64);
   float creg[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) creg[j] = 0.f;
@@ -176,9 +176,9 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   // coalesced prefetch of the xp tile of (time t_, tile bt_) into xs
   auto prefetch_x = [&](int t_, int bt_) {
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < TM / 8; ++i) {
       const int idx = i * 128 + te, r = idx >> 4, c4 = idx & 15;
-      const int n = bt_ * 128 + r;
+      const int n = bt_ * TM + r;
       float* dst = xs + r * XS_P + c4 * 4;
       if (n < p.n_batch)
         cp_async16(dst, p.xp + ((size_t)t_ * p.rs_seq + (size_t)n * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4);
@@ -201,7 +201,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             DBG_STAMP(0);
             mbar_expect_tx(a_full, KB * A_BLK);
             for (int kb = 0; kb < KB; ++kb)
-              tma_load_3d(&tmH, a_full, Asm + kb * A_BLK, dir * S + kb * 64, p.seq_inner ? tp : bt * 128, p.seq_inner ? bt * 128 : tp);
+              tma_load_3d(&tmH, a_full, Asm + kb * A_BLK, dir * S + kb * 64, p.seq_inner ? tp : bt * TM, p.seq_inner ? bt * TM : tp);
           }
         } else if (warp == 1) {
           if (elect_one()) {
@@ -223,9 +223,10 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
         }
       }
       if (warp >= 2) {
-        const int r = eg * 32 + lane;            // tile row == TMEM lane
-        const int n = bt * 128 + r;
-        const bool in_range = n < p.n_batch;
+        // tile row <-> TMEM lane: M=128 uses all 32 lanes of each sub-partition, M=64 the lower 16 (rows 16q..16q+15)
+        const int r = (TM == 128) ? eg * 32 + lane : eg * 16 + (lane & 15);
+        const int n = bt * TM + r;
+        const bool in_range = (TM == 128 || lane < 16) && n < p.n_batch;
         const bool valid = in_range && (p.lens ? (t < p.lens[in_range ? n : 0]) : true);
         const size_t hoff = (size_t)dir * S + slice * RT_UNITS;
         cp_async_wait_all();
@@ -262,6 +263,7 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           for (int j = 0; j < 64; ++j) v[j] = 0u;
         }
         float* xrow = xs + r * XS_P;
+        if (TM == 128 || lane < 16) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float hv[4], cv[4];
@@ -289,14 +291,15 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           pk.y = *reinterpret_cast<uint32_t*>(&b23);
           *reinterpret_cast<uint2*>(hbst + r * HB_P + q * 4) = pk;
         }
+        }
         if (warp == 2 && lane == 0) DBG_STAMP(5);
         epi_bar();
         // coalesced write-out: exchange buffer first, then the saved tensors
         {
           const size_t rbase = (size_t)t * p.rs_seq;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int idx = i * 128 + te, rr = idx >> 1, hh = idx & 1, nn = bt * 128 + rr;
+          for (int i = 0; i < TM / 64; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 1, hh = idx & 1, nn = bt * TM + rr;
             if (nn < p.n_batch)
               *reinterpret_cast<uint4*>(p.xb + (rbase + (size_t)nn * p.rs_batch) * 2 * S + hoff + hh * 8) =
                   *reinterpret_cast<const uint4*>(hbst + rr * HB_P + hh * 8);
@@ -309,8 +312,8 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             }
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int idx = i * 128 + te, rr = idx >> 2, c4 = idx & 3, nn = bt * 128 + rr;
+          for (int i = 0; i < TM / 32; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 2, c4 = idx & 3, nn = bt * TM + rr;
             if (nn < p.n_batch) {
               const size_t o = (rbase + (size_t)nn * p.rs_batch) * 2 * S + hoff + c4 * 4;
               *reinterpret_cast<float4*>(p.hout + o) = *reinterpret_cast<const float4*>(hst + rr * HS_P + c4 * 4);
@@ -319,8 +322,8 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           }
           if (warp == 2 && lane == 0) DBG_STAMP(8);
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nn = bt * 128 + rr;
+          for (int i = 0; i < TM / 8; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nn = bt * TM + rr;
             if (nn < p.n_batch)
               __stcs(reinterpret_cast<float4*>(p.xp + (rbase + (size_t)nn * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4),
                      *reinterpret_cast<const float4*>(xs + rr * XS_P + c4 * 4));
@@ -349,10 +352,10 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int NST>   // ring stages of 16 KB
+template <int TM, int NST>   // TM = batch rows per tile (64 or 128), NST = TMA ring stages
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmW, RecTcParams p) {
-  constexpr int A_BLK = 128 * 128;       // 128 batch rows x 128 B
+  constexpr int A_BLK = TM * 128;        // TM batch rows x 128 B
   constexpr int W_BLK = 16 * 128;        // 16 unit rows x 128 B
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -361,11 +364,11 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   uint8_t* Asm = smem;                    // NST stages
   uint8_t* Wsm = smem + NST * A_BLK;      // KB blocks of 2 KB
   float* as = reinterpret_cast<float*>(Wsm + KB * W_BLK);                 // [128][XS_P] activations -> dG
-  float* dhs = as + 128 * XS_P;                                           // [128][HS_P]
-  float* cs = dhs + 128 * HS_P;                                           // [128][HS_P] c(t)
-  float* cps = cs + 128 * HS_P;                                           // [128][HS_P] c(t_prev)
-  __nv_bfloat16* gbs = reinterpret_cast<__nv_bfloat16*>(cps + 128 * HS_P);    // [128][GB_P]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gbs + 128 * GB_P);
+  float* dhs = as + TM * XS_P;                                           // [128][HS_P]
+  float* cs = dhs + TM * HS_P;                                           // [128][HS_P] c(t)
+  float* cps = cs + TM * HS_P;                                           // [128][HS_P] c(t_prev)
+  __nv_bfloat16* gbs = reinterpret_cast<__nv_bfloat16*>(cps + TM * HS_P);    // [128][GB_P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gbs + TM * GB_P);
   uint64_t* w_full = bars;
   uint64_t* mma_done = bars + 1;
   uint64_t* tmem_free = bars + 2;
@@ -401,7 +404,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int eg = warp & 3;
   const int te = threadIdx.x - 64;
   const bool single = p.n_tiles <= Z;
-  constexpr uint32_t idesc = umma_idesc_bf16(128, 16);
+  constexpr uint32_t idesc = umma_idesc_bf16(TM, 16);
   const size_t hoff = (size_t)dir * S + slice * RT_UNITS;
   float dcreg[16];
 #pragma unroll
@@ -413,8 +416,8 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int tp_ = dir == 0 ? t_ - 1 : t_ + 1;
     const bool hp = dir == 0 ? (t_ > 0) : (t_ < p.n_seq - 1);
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int idx = i * 128 + te, r = idx >> 4, c4 = idx & 15, n = bt_ * 128 + r;
+    for (int i = 0; i < TM / 8; ++i) {
+      const int idx = i * 128 + te, r = idx >> 4, c4 = idx & 15, n = bt_ * TM + r;
       float* dst = as + r * XS_P + c4 * 4;
       if (n < p.n_batch)
         cp_async16(dst, p.xp + ((size_t)t_ * p.rs_seq + (size_t)n * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4);
@@ -422,8 +425,8 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = i * 128 + te, r = idx >> 2, c4 = idx & 3, n = bt_ * 128 + r;
+    for (int i = 0; i < TM / 32; ++i) {
+      const int idx = i * 128 + te, r = idx >> 2, c4 = idx & 3, n = bt_ * TM + r;
       if (n < p.n_batch) {
         const size_t o = ((size_t)t_ * p.rs_seq + (size_t)n * p.rs_batch) * 2 * S + hoff + c4 * 4;
         cp_async16(dhs + r * HS_P + c4 * 4, p.dhout + o);
@@ -456,8 +459,8 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
               const int st = kc % NST;
               mbar_wait(empty + st, ((kc / NST) & 1) ^ 1);
               mbar_expect_tx(full + st, A_BLK);
-              tma_load_3d(&tmG, full + st, Asm + st * A_BLK, dir * 4 * S + kb * 64, p.seq_inner ? tn : bt * 128,
-                          p.seq_inner ? bt * 128 : tn);
+              tma_load_3d(&tmG, full + st, Asm + st * A_BLK, dir * 4 * S + kb * 64, p.seq_inner ? tn : bt * TM,
+                          p.seq_inner ? bt * TM : tn);
             }
           }
         } else if (warp == 1) {
@@ -485,9 +488,9 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         kcount += KB;
       }
       if (warp >= 2) {
-        const int r = eg * 32 + lane;
-        const int n = bt * 128 + r;
-        const bool in_range = n < p.n_batch;
+        const int r = (TM == 128) ? eg * 32 + lane : eg * 16 + (lane & 15);
+        const int n = bt * TM + r;
+        const bool in_range = (TM == 128 || lane < 16) && n < p.n_batch;
         const int nn = in_range ? n : 0;
         const bool valid = in_range && (p.lens ? (t < p.lens[nn]) : true);
         const bool pv = valid && has_prev && (p.lens ? (tp < p.lens[nn]) : true);
@@ -520,6 +523,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
         float* arow = as + r * XS_P;
+        if (TM == 128 || lane < 16) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 dh4 = *reinterpret_cast<const float4*>(dhs + r * HS_P + q * 4);
@@ -552,6 +556,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             *reinterpret_cast<uint2*>(gbs + r * GB_P + j * 4) = pk;
           }
         }
+        }
         if (!single && in_range) {
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -562,8 +567,8 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         {
           const size_t rbase = (size_t)t * p.rs_seq;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {          // bf16 exchange tile first: 128 rows x 128 B
-            const int idx = i * 128 + te, rr = idx >> 3, c8 = idx & 7, nb = bt * 128 + rr;
+          for (int i = 0; i < TM / 16; ++i) {    // bf16 exchange tile first: TM rows x 128 B
+            const int idx = i * 128 + te, rr = idx >> 3, c8 = idx & 7, nb = bt * TM + rr;
             if (nb < p.n_batch)
               *reinterpret_cast<uint4*>(p.xb + (rbase + (size_t)nb * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c8 * 8) =
                   *reinterpret_cast<const uint4*>(gbs + rr * GB_P + c8 * 8);
@@ -576,8 +581,8 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
             }
           }
 #pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nb = bt * 128 + rr;
+          for (int i = 0; i < TM / 8; ++i) {
+            const int idx = i * 128 + te, rr = idx >> 4, c4 = idx & 15, nb = bt * TM + rr;
             if (nb < p.n_batch)
               __stcs(reinterpret_cast<float4*>(p.xp + (rbase + (size_t)nb * p.rs_batch) * 8 * S + (size_t)dir * 4 * S + slice * 64 + c4 * 4),
                      *reinterpret_cast<const float4*>(as + rr * XS_P + c4 * 4));
@@ -603,92 +608,99 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-static int pick_z(int S, int n_tiles) {
-  int slices2 = 2 * (S / RT_UNITS);
-  int z = sm_count() / slices2;
-  if (z < 1) z = 1;
-  if (z > n_tiles) z = n_tiles;
-  return z;
+static int max_z(int S) {
+  int z = sm_count() / (2 * (S / RT_UNITS));
+  return z < 1 ? 1 : z;
 }
-
-// scratch words needed for the step barriers of one launch
-int rec_tc_bar_words(int S, int n_batch) { return 2 * pick_z(S, (n_batch + 127) / 128); }
+// 64-row tiles whenever that still gives every tile its own CTA: twice the CTAs, half the per-SM exchange traffic
+static int pick_tm(int S, int n_batch) { return ((n_batch + 63) / 64 <= max_z(S)) ? 64 : 128; }
+static int pick_z(int S, int n_tiles) {
+  int z = max_z(S);
+  return z > n_tiles ? n_tiles : z;
+}
 
 int rec_tc_supported(int S) { return (S % 64 == 0 && S >= 64 && S <= 256) ? 1 : 0; }
 
-template <int KB>
+template <int TM, int KB>
 static int launch_fwd_tc(const CUtensorMap& tmH, const CUtensorMap& tmW, RecTcParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)KB * (64 * 128 + 128 * 128) + (size_t)128 * (XS_P + 2 * HS_P) * 4 + (size_t)128 * HB_P * 2 + 64 + 1024;
-  SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_fwd_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)KB * (64 * 128 + TM * 128) + (size_t)TM * (XS_P + 2 * HS_P) * 4 + (size_t)TM * HB_P * 2 + 64 + 1024;
+  SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_fwd_kernel<TM, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&tmH, (void*)&tmW, (void*)&p};
   ProfScope ps(F_REC_TC_FWD, st);
-  SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_tc_fwd_kernel<KB>, grid, dim3(RT_THREADS), args, smem, st));
+  SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_tc_fwd_kernel<TM, KB>, grid, dim3(RT_THREADS), args, smem, st));
   return 0;
+}
+template <int TM>
+static int launch_fwd_tc_kb(int kb, const CUtensorMap& tmH, const CUtensorMap& tmW, RecTcParams& p, dim3 grid, cudaStream_t st) {
+  switch (kb) {
+    case 1: return launch_fwd_tc<TM, 1>(tmH, tmW, p, grid, st);
+    case 2: return launch_fwd_tc<TM, 2>(tmH, tmW, p, grid, st);
+    case 3: return launch_fwd_tc<TM, 3>(tmH, tmW, p, grid, st);
+    case 4: return launch_fwd_tc<TM, 4>(tmH, tmW, p, grid, st);
+  }
+  return -1;
 }
 
 // hb: bf16 [rows,2S] h exchange buffer; whh_bf: bf16 [2*4S, S] (interleaved rows, both directions)
 int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
                int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar) {
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_fwd: unsupported state size %d", S);
+  const int TM = pick_tm(S, n_batch);
   RecTcParams p;
   p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.dhout = nullptr; p.dcstate = nullptr; p.lens = lens;
-  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + 127) / 128;
+  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + TM - 1) / TM;
   p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;
   const int Z = pick_z(S, p.n_tiles);
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned) * 2 * Z, st));
   CUtensorMap tmH, tmW;
   p.seq_inner = rs_seq < rs_batch ? 1 : 0;
-  int rc = p.seq_inner ? make_tmap_bf16_3d(&tmH, hb, 2 * S, n_seq, rs_seq * 2 * S, n_batch, rs_batch * 2 * S, 1, 128)
-                       : make_tmap_bf16_3d(&tmH, hb, 2 * S, n_batch, rs_batch * 2 * S, n_seq, rs_seq * 2 * S, 128, 1);
+  int rc = p.seq_inner ? make_tmap_bf16_3d(&tmH, hb, 2 * S, n_seq, rs_seq * 2 * S, n_batch, rs_batch * 2 * S, 1, TM)
+                       : make_tmap_bf16_3d(&tmH, hb, 2 * S, n_batch, rs_batch * 2 * S, n_seq, rs_seq * 2 * S, TM, 1);
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 64);
   if (rc) return rc;
   dim3 grid(S / RT_UNITS, 2, Z);
-  switch (S / 64) {
-    case 1: return launch_fwd_tc<1>(tmH, tmW, p, grid, st);
-    case 2: return launch_fwd_tc<2>(tmH, tmW, p, grid, st);
-    case 3: return launch_fwd_tc<3>(tmH, tmW, p, grid, st);
-    case 4: return launch_fwd_tc<4>(tmH, tmW, p, grid, st);
-    case 5: return launch_fwd_tc<5>(tmH, tmW, p, grid, st);
-    case 6: return launch_fwd_tc<6>(tmH, tmW, p, grid, st);
-    case 7: return launch_fwd_tc<7>(tmH, tmW, p, grid, st);
-    case 8: return launch_fwd_tc<8>(tmH, tmW, p, grid, st);
-  }
-  return -1;
+  return TM == 64 ? launch_fwd_tc_kb<64>(S / 64, tmH, tmW, p, grid, st) : launch_fwd_tc_kb<128>(S / 64, tmH, tmW, p, grid, st);
+}
+
+template <int TM, int NST>
+static int launch_bwd_tc(const CUtensorMap& tmG, const CUtensorMap& tmW, RecTcParams& p, dim3 grid, cudaStream_t st) {
+  const int S = p.S;
+  const size_t smem = (size_t)NST * TM * 128 + (size_t)(4 * S / 64) * 16 * 128 + (size_t)TM * (XS_P + 3 * HS_P) * 4 +
+                      (size_t)TM * GB_P * 2 + (3 + 2 * NST) * 8 + 16 + 1024;
+  SSASR_REQUIRE(smem <= 227 * 1024, "rec_tc_bwd: %zu B shared memory needed (S=%d)", smem, S);
+  SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_bwd_kernel<TM, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&tmG, (void*)&tmW, (void*)&p};
+  ProfScope ps(F_REC_TC_BWD, st);
+  SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_tc_bwd_kernel<TM, NST>, grid, dim3(RT_THREADS), args, smem, st));
+  return 0;
 }
 
 // dgb: bf16 [rows,8S] dG exchange buffer (on return: the complete bf16 copy of dG); whhT_bf: bf16 [2*S, 4S]
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,
                const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar) {
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_bwd: unsupported state size %d", S);
-  constexpr int NST = 6;
+  const int TM = pick_tm(S, n_batch);
   RecTcParams p;
   p.xp = act; p.hout = nullptr; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dcstate = dcstate;
-  p.lens = lens; p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + 127) / 128;
+  p.lens = lens; p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + TM - 1) / TM;
   p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;
   const int Z = pick_z(S, p.n_tiles);
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned) * 2 * Z, st));
   CUtensorMap tmG, tmW;
   p.seq_inner = rs_seq < rs_batch ? 1 : 0;
-  int rc = p.seq_inner ? make_tmap_bf16_3d(&tmG, dgb, 8 * S, n_seq, rs_seq * 8 * S, n_batch, rs_batch * 8 * S, 1, 128)
-                       : make_tmap_bf16_3d(&tmG, dgb, 8 * S, n_batch, rs_batch * 8 * S, n_seq, rs_seq * 8 * S, 128, 1);
+  int rc = p.seq_inner ? make_tmap_bf16_3d(&tmG, dgb, 8 * S, n_seq, rs_seq * 8 * S, n_batch, rs_batch * 8 * S, 1, TM)
+                       : make_tmap_bf16_3d(&tmG, dgb, 8 * S, n_batch, rs_batch * 8 * S, n_seq, rs_seq * 8 * S, TM, 1);
   if (rc) return rc;
   rc = make_tmap_bf16(&tmW, whhT_bf, 2 * S, 4 * S, 4 * S, 16);
   if (rc) return rc;
-  const size_t smem = (size_t)NST * 128 * 128 + (size_t)(4 * S / 64) * 16 * 128 + (size_t)128 * (XS_P + 3 * HS_P) * 4 +
-                      (size_t)128 * GB_P * 2 + (3 + 2 * NST) * 8 + 16 + 1024;
-  SSASR_REQUIRE(smem <= 227 * 1024, "rec_tc_bwd: %zu B shared memory needed (S=%d)", smem, S);
-  SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_bwd_kernel<NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(S / RT_UNITS, 2, Z);
-  void* args[] = {(void*)&tmG, (void*)&tmW, (void*)&p};
-  ProfScope ps(F_REC_TC_BWD, st);
-  SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_tc_bwd_kernel<NST>, grid, dim3(RT_THREADS), args, smem, st));
-  return 0;
+  return TM == 64 ? launch_bwd_tc<64, 12>(tmG, tmW, p, grid, st) : launch_bwd_tc<128, 6>(tmG, tmW, p, grid, st);
 }
 
 }  // namespace ssasr
 
 extern "C" {
-// debug: device buffer [n_seq][8] of clock64 stamps written by CTA (0,0,0) of the next tensor-core recurrent launches
+// debug: device buffer [n_seq][12] of clock64 stamps written by CTA (0,0,0) of the next tensor-core recurrent launches
 void ssasr_rec_tc_set_debug(long long* dev_buf) { ssasr::g_dbg = dev_buf; }
 }
