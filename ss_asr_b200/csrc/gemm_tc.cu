@@ -142,7 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-                  int ldc, int M, int N, int K, int a_koff, int b_koff, int accumulate) {
+                  int ldc, int M, int N, int K, int a_koff, int b_koff, int accumulate, int kb_per_split) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -154,7 +154,13 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * BN;
-  const int num_k = (K + GT_BK - 1) / GT_BK;
+  // split-K: grid.z CTAs share one output tile, each reduces kb_per_split k-blocks and adds its partial with atomics
+  const int kb_all = (K + GT_BK - 1) / GT_BK;
+  const int kb_first = blockIdx.z * kb_per_split;
+  const int num_k = min(kb_per_split, kb_all - kb_first);
+  const bool atomic_out = gridDim.z > 1;
+  a_koff += kb_first * GT_BK;
+  b_koff += kb_first * GT_BK;
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -220,8 +226,12 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int n = n0 + c0 + j;
           if (n < N) {
             float o = __uint_as_float(v[j]);
-            if (accumulate) o += crow[c0 + j];
-            crow[c0 + j] = o;
+            if (atomic_out) {
+              atomicAdd(crow + c0 + j, o);
+            } else {
+              if (accumulate) o += crow[c0 + j];
+              crow[c0 + j] = o;
+            }
           }
         }
       }
@@ -288,8 +298,23 @@ int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long lo
   }
   dim3 grid((M + GT_BM - 1) / GT_BM, (N + BN - 1) / BN);
   SSASR_REQUIRE(grid.y <= 65535, "gemm_bf16_tc_tn: N=%d too large", N);
+  // split the (usually very long) reduction over grid.z when the output has too few tiles to fill the GPU
+  const int tiles = grid.x * grid.y, kb_all = (K + GT_BK - 1) / GT_BK;
+  int splits = (2 * sm_count()) / tiles;
+  if (splits > kb_all / 16) splits = kb_all / 16;
+  if (splits < 1) splits = 1;
+  const int kb_per = (kb_all + splits - 1) / splits;
+  splits = (kb_all + kb_per - 1) / kb_per;
+  grid.z = splits;
+  if (splits > 1 && !accumulate) {
+    if (ldc == N) {
+      SSASR_CHECK_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+    } else {
+      SSASR_CHECK_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+    }
+  }
   ProfScope ps(F_GEMM_TC, st);
-  gemm_tc_tn_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, accumulate);
+  gemm_tc_tn_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, M, N, K, a_koff, b_koff, accumulate, kb_per);
   SSASR_LAUNCH_CHECK();
   return 0;
 }
