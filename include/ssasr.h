@@ -97,7 +97,7 @@ typedef struct {
   unsigned long long seed;
   float *psi, *xin1, *xin2, *act1, *act2, *c1, *c2, *h2all, *q, *alpha, *logits; /* outputs + saved state */
   const void *w1cat_bf, *w2cat_bf; /* bf16 copies of w1cat/w2cat, or NULL (fp32 path) */
-  void* ws_bf;                     /* bf16 scratch [B, max(X1,X2)], or NULL */
+  void* ws_bf;                     /* bf16 scratch [B, X1 + X2], or NULL */
   void* enc_bf;                    /* bf16 scratch [(B*Tp + M) * E], or NULL */
   /* character LM for step mode 3 (ASR.decode with lm_weight != 0, asr.py:153-162 + charlm.py:46-57):
      GRU / output weights TRANSPOSED to [in,out], biases, and the two [B,H] hidden states (updated in place) */

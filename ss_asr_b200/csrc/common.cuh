@@ -101,6 +101,7 @@ int rec_tc_supported(int S);
 int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
                int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,
-               const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
+               const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar,
+               float* dbias /*[8S] pre-zeroed, or null*/);
 
 }  // namespace ssasr

@@ -547,7 +547,8 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
   int rc;
   const bool tc_rec = whhT_bf && dgb_ws && rec_tc_supported(S);
   if (tc_rec) {
-    rc = rec_tc_bwd(st, act, whhT_bf, cbuf, dhout, dgb_ws, dcstate, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar);
+    SSASR_CHECK_CUDA(cudaMemsetAsync(dbias_p, 0, sizeof(float) * 8 * S, st));     // bias gradient is reduced inside the kernel
+    rc = rec_tc_bwd(st, act, whhT_bf, cbuf, dhout, dgb_ws, dcstate, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar, dbias_p);
     if (rc) return rc;
   } else {
     SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
@@ -561,8 +562,10 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
     if (rc) return rc;
   }
   const float* dg = act;
-  rc = colsum(st, dg, dbias_p, n_rows, 8 * S, 8 * S, 0);
-  if (rc) return rc;
+  if (!tc_rec) {
+    rc = colsum(st, dg, dbias_p, n_rows, 8 * S, 8 * S, 0);
+    if (rc) return rc;
+  }
   if (dx) {
     if (!tc_rec) {
       SSASR_REQUIRE(dgb_ws != nullptr, "blstm_bwd_bf16: dgb_ws required when dx is requested");

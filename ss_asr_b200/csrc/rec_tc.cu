@@ -95,6 +95,7 @@ struct RecTcParams {
   __nv_bfloat16* xb;         // fwd: h exchange buffer [rows,2S] bf16.  bwd: dG exchange buffer [rows,8S] bf16
   const float* dhout;        // bwd
   float* dcstate;            // bwd [n_batch,2S]
+  float* dbias;              // bwd: [8S] bias gradient (column sums of dG), pre-zeroed, accumulated with atomics; may be null
   const int* lens;
   int S, n_seq, n_batch, n_tiles;
   long long rs_seq, rs_batch;
@@ -409,6 +410,9 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   float dcreg[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) dcreg[j] = 0.f;
+  float bsum[64];            // per-thread running column sums of dG (bias gradient), reduced across rows at the end
+#pragma unroll
+  for (int j = 0; j < 64; ++j) bsum[j] = 0.f;
 
   // coalesced prefetch of everything step (s_) of tile bt_ needs that does not depend on the recurrence
   auto prefetch_in = [&](int s_, int bt_) {
@@ -548,6 +552,7 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
               dco = dc * a.y;
             }
             dcreg[j] = dco;
+            bsum[j * 4 + 0] += dg.x; bsum[j * 4 + 1] += dg.y; bsum[j * 4 + 2] += dg.z; bsum[j * 4 + 3] += dg.w;
             *reinterpret_cast<float4*>(arow + j * 4) = dg;
             __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
             uint2 pk;
@@ -600,6 +605,20 @@ rec_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     }
   }
   cp_async_wait_all();
+  if (p.dbias) {                      // bias gradient: reduce the per-thread partial sums across the tile rows
+    __syncthreads();
+    if (warp >= 2 && (TM == 128 || lane < 16)) {
+      float* brow = as + ((TM == 128) ? eg * 32 + lane : eg * 16 + lane) * XS_P;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) *reinterpret_cast<float4*>(brow + j * 4) = make_float4(bsum[j * 4], bsum[j * 4 + 1], bsum[j * 4 + 2], bsum[j * 4 + 3]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float acc = 0.f;
+      for (int rr = 0; rr < TM; ++rr) acc += as[rr * XS_P + threadIdx.x];
+      atomicAdd(p.dbias + (size_t)dir * 4 * S + slice * 64 + threadIdx.x, acc);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<32>(tmem);
@@ -647,7 +666,8 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_fwd: unsupported state size %d", S);
   const int TM = pick_tm(S, n_batch);
   RecTcParams p;
-  p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.dhout = nullptr; p.dcstate = nullptr; p.lens = lens;
+  p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.dhout = nullptr; p.dcstate = nullptr; p.dbias = nullptr;
+  p.lens = lens;
   p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + TM - 1) / TM;
   p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;
   const int Z = pick_z(S, p.n_tiles);
@@ -678,11 +698,12 @@ static int launch_bwd_tc(const CUtensorMap& tmG, const CUtensorMap& tmW, RecTcPa
 
 // dgb: bf16 [rows,8S] dG exchange buffer (on return: the complete bf16 copy of dG); whhT_bf: bf16 [2*S, 4S]
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,
-               const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar) {
+               const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar, float* dbias) {
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_bwd: unsupported state size %d", S);
   const int TM = pick_tm(S, n_batch);
   RecTcParams p;
   p.xp = act; p.hout = nullptr; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dcstate = dcstate;
+  p.dbias = dbias;
   p.lens = lens; p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + TM - 1) / TM;
   p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;
   const int Z = pick_z(S, p.n_tiles);

@@ -25,6 +25,7 @@ struct AttnFwd {
   const int* enc_lens;                       // [B]
   const float* emb_w; const int* tok; long long tok_ld;   // embedding gather for the step input
   float* xin1; long long xin1_ld;            // row b: [emb(Sd) ; ctx(E) ; h1prev(Sd)]
+  __nv_bfloat16* xin1b; long long xin1b_ld;  // optional bf16 copy of the same row (tensor-core GEMM operand)
   float* q; long long q_ld;                  // [B,M]
   float* alpha; long long alpha_ld;          // [B,Tp]
 };
@@ -42,7 +43,12 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     const float h = a.h1prev ? a.h1prev[(size_t)b * a.h1_ld + k] : 0.f;
     hs[k] = h;
     xrow[a.Sd + a.E + k] = h;
-    xrow[k] = a.emb_w[(size_t)tk * a.Sd + k];
+    const float e = a.emb_w[(size_t)tk * a.Sd + k];
+    xrow[k] = e;
+    if (a.xin1b) {
+      a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + a.E + k] = __float2bfloat16(h);
+      a.xin1b[(size_t)b * a.xin1b_ld + k] = __float2bfloat16(e);
+    }
   }
   __syncthreads();
   for (int m = warp; m < a.M; m += nwarp) {
@@ -92,6 +98,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     float s = 0.f;
     for (int j = 0; j < len; ++j) s = fmaf(es[j], encb[(size_t)j * a.E + c], s);
     xrow[a.Sd + c] = s;
+    if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(s);
   }
 }
 
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(256) attn_outer_accum_kernel(int U, int Tp, in
 __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long long g_ld, const float* __restrict__ cprev,
                                 long long cp_ld, float* __restrict__ cout, long long c_ld, float* __restrict__ hout,
                                 long long h_ld, const float* __restrict__ cp_src, long long cps_ld, float* __restrict__ cp_dst,
-                                long long cpd_ld) {
+                                long long cpd_ld, __nv_bfloat16* __restrict__ hb_out, long long hb_ld, int hb_cp_off) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S) return;
   const int b = i / S, u = i % S;
@@ -214,14 +221,20 @@ __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long lo
   const float c = a.y * cp + a.x * a.z;
   *gp = a;
   cout[(size_t)b * c_ld + u] = c;
-  hout[(size_t)b * h_ld + u] = a.w * tanhf(c);
-  if (cp_dst) cp_dst[(size_t)b * cpd_ld + u] = cp_src ? cp_src[(size_t)b * cps_ld + u] : 0.f;
+  const float h = a.w * tanhf(c);
+  hout[(size_t)b * h_ld + u] = h;
+  if (hb_out) hb_out[(size_t)b * hb_ld + u] = __float2bfloat16(h);
+  if (cp_dst) {
+    const float v = cp_src ? cp_src[(size_t)b * cps_ld + u] : 0.f;
+    cp_dst[(size_t)b * cpd_ld + u] = v;
+    if (hb_out) hb_out[(size_t)b * hb_ld + hb_cp_off + u] = __float2bfloat16(v);
+  }
 }
 
 __global__ void cell_bwd_kernel(int B, int S, float* __restrict__ act, long long a_ld, const float* __restrict__ c, long long c_ld,
                                 const float* __restrict__ cprev, long long cp_ld, const float* __restrict__ dh_a, long long da_ld,
                                 const float* __restrict__ dh_b, long long db_ld, const float* __restrict__ dh_c, long long dc_ld,
-                                float* __restrict__ dcstate, int first) {
+                                float* __restrict__ dcstate, int first, __nv_bfloat16* __restrict__ dgb /*[B,4S] or null*/) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S) return;
   const int b = i / S, u = i % S;
@@ -242,6 +255,13 @@ __global__ void cell_bwd_kernel(int B, int S, float* __restrict__ act, long long
   dg.y = dc * cp * a.y * (1.f - a.y);
   *ap = dg;
   dcstate[i] = dc * a.y;
+  if (dgb) {
+    __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&b01);
+    pk.y = *reinterpret_cast<uint32_t*>(&b23);
+    *reinterpret_cast<uint2*>(dgb + (size_t)b * 4 * S + (size_t)u * 4) = pk;
+  }
 }
 
 __global__ void emb_grad_add_kernel(int B, int Sd, const float* __restrict__ demb, long long ld, const int* __restrict__ tok,
@@ -471,12 +491,13 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   const int cell_blocks = (B * Sd + 255) / 256;
   const bool tc = a->w1cat_bf && a->w2cat_bf && a->ws_bf && X1 % 8 == 0 && X2 % 8 == 0;
   // gates = x_t @ Wcat^T + b, fp32 SIMT or (bf16 mode) tcgen05 after a bf16 copy of the step's input rows
-  auto gate_gemm = [&](const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out) -> int {
-    if (tc) {
-      int r = cvt_bf16(st, x, ldx, a->ws_bf, K, B, K);
-      if (r) return r;
-      return gemm_bf16_tc(st, B, 4 * Sd, K, a->ws_bf, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0);
-    }
+  // bf16 mode: the attention / cell kernels also emit bf16 copies of the step's input rows into ws_bf
+  // ([B, X1] followed by [B, X2]), which feed the tcgen05 gate GEMMs directly
+  __nv_bfloat16* x1b = tc ? (__nv_bfloat16*)a->ws_bf : nullptr;
+  __nv_bfloat16* x2b = tc ? x1b + (size_t)B * X1 : nullptr;
+  auto gate_gemm = [&](const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out,
+                       const __nv_bfloat16* xb) -> int {
+    if (tc) return gemm_bf16_tc(st, B, 4 * Sd, K, xb, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0);
     return gemm_f32(st, B, 4 * Sd, K, x, ldx, 1, w, K, 1, out, U * 4 * Sd, bias, 0, 0);
   };
   for (int t = 0; t < U; ++t) {
@@ -486,26 +507,27 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     f.phi_w = a->phi_w; f.psi = a->psi; f.enc = a->enc; f.enc_lens = a->enc_lens;
     f.emb_w = a->emb_w; f.tok = a->tok_in + t; f.tok_ld = U;
     f.xin1 = a->xin1 + (size_t)t * X1; f.xin1_ld = (long long)U * X1;
+    f.xin1b = x1b; f.xin1b_ld = X1;
     f.q = a->q + (size_t)t * M; f.q_ld = (long long)U * M;
     f.alpha = a->alpha + (size_t)t * Tp; f.alpha_ld = (long long)U * Tp;
     { ProfScope ps(F_ATTN_FWD, st); attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f); }
     // layer 1
-    rc = gate_gemm(a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd);
+    rc = gate_gemm(a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd, a->xin2 + (size_t)t * X2,
                                                  (long long)U * X2, t ? a->h2all + (size_t)(t - 1) * Sd : nullptr,
-                                                 (long long)U * Sd, a->xin2 + (size_t)t * X2 + Sd, (long long)U * X2);
+                                                 (long long)U * Sd, a->xin2 + (size_t)t * X2 + Sd, (long long)U * X2, x2b, X2, Sd);
     // layer 2
-    rc = gate_gemm(a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd);
+    rc = gate_gemm(a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd, x2b);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c2 + (size_t)t * Sd, (long long)U * Sd, a->h2all + (size_t)t * Sd,
-                                                 (long long)U * Sd, nullptr, 0, nullptr, 0);
+                                                 (long long)U * Sd, nullptr, 0, nullptr, 0, nullptr, 0, 0);
     const int mode = a->step_mode ? a->step_mode[t] : 0;
     if (mode != 0 && t + 1 < U) {
       rc = gemm_f32(st, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
@@ -592,12 +614,9 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   const bool tc = a->w1catT_bf && a->w2catT_bf && a->wsA && a->wsB && X1 % 8 == 0 && X2 % 8 == 0 && a->BUp >= (long long)B * U &&
                   a->BUp % 8 == 0;
   // dx = dG_t @ Wcat (through the cells' input weights), fp32 SIMT or tcgen05
+  __nv_bfloat16* dgb = tc ? (__nv_bfloat16*)a->wsA : nullptr;     // [B,4Sd] bf16 copy of the step's gate gradients
   auto dgrad_gemm = [&](const float* dg, int N, const float* w, const void* wT_bf, float* out, int ldo) -> int {
-    if (tc) {
-      int r = cvt_bf16(st, dg, U * 4 * Sd, a->wsA, 4 * Sd, B, 4 * Sd);
-      if (r) return r;
-      return gemm_bf16_tc(st, B, N, 4 * Sd, a->wsA, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, ldo, nullptr, 0);
-    }
+    if (tc) return gemm_bf16_tc(st, B, N, 4 * Sd, dgb, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, ldo, nullptr, 0);
     return gemm_f32(st, B, N, 4 * Sd, dg, U * 4 * Sd, 1, w, N, 0, out, ldo, nullptr, 0, 0);
   };
   // dW = dG_all^T @ X_all over all B*U rows
@@ -618,7 +637,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                                                  a->c2 + (size_t)t * Sd, (long long)U * Sd,
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->dh2all + (size_t)t * Sd, (long long)U * Sd, last ? nullptr : a->dxin2 + Sd,
-                                                 (long long)X2, nullptr, 0, a->dc2s, last);
+                                                 (long long)X2, nullptr, 0, a->dc2s, last, dgb);
     rc = dgrad_gemm(a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, a->dxin2, X2);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
@@ -626,7 +645,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, a->dxin2,
                                                  (long long)X2, last ? nullptr : a->dxin1 + (size_t)(t + 1) * X1 + K1,
-                                                 (long long)U * X1, last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last);
+                                                 (long long)U * X1, last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last, dgb);
     rc = dgrad_gemm(a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
     if (rc) return rc;
     AttnBwd g;

@@ -166,7 +166,7 @@ class _Spell(torch.autograd.Function):
         w1b = w2b = wsb = encb = None
         if bf16:
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
-            w1b, w2b, wsb = bf(4 * Sd, X1), bf(4 * Sd, X2), bf(B, max(X1, X2))
+            w1b, w2b, wsb = bf(4 * Sd, X1), bf(4 * Sd, X2), bf(B, X1 + X2)
             encb = bf((B * Tp + M) * E)
             check(lib.ssasr_cvt_bf16(ptr(w1cat), X1, ptr(w1b), X1, 4 * Sd, X1, st), 'ssasr_cvt_bf16')
             check(lib.ssasr_cvt_bf16(ptr(w2cat), X2, ptr(w2b), X2, 4 * Sd, X2, st), 'ssasr_cvt_bf16')
