@@ -365,7 +365,29 @@ def run_extras(model, dev, args, peaks, shard=(0, 1), dist=None):
     out['decode'] = {'workload': 'C3 greedy decode, %d utterances T~U[256,512], bs=1 semantics, 200-char cap, lm_weight 0'
                                  % n_total, 'utt_per_s': n_total / (ms / 1e3), 'ms': ms,
                      'chars_per_s': sum(len(i) for i in ids) * world / (ms / 1e3)}
+    if rank == 0 and world == 1:
+        # secondary: same utterances with the (randomly initialised, as in ASRTester) CharLM at lm_weight 0.5
+        import torch.nn as nn
+
+        class _LM(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.emb = nn.Embedding(50, 128)
+                self.layer_1 = nn.GRUCell(128, 128)
+                self.layer_2 = nn.GRUCell(128, 128)
+                self.out = nn.Linear(128, 50)
+        torch.manual_seed(7)
+        lm = _LM().to(dev)
+        model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5)
+        torch.cuda.synchronize()
+        e0.record()
+        model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5)
+        e1.record()
+        torch.cuda.synchronize()
+        out['decode']['utt_per_s_lm05'] = n_total / (e0.elapsed_time(e1) / 1e3)
     del xb
+    if rank == 0 and world == 1 and not args.small:
+        out['long_c5'] = run_c5(dev)
     # ---- fbank
     n_utt = (4096 if not args.small else 256) // world
     n = 160000
@@ -388,6 +410,40 @@ def run_extras(model, dev, args, peaks, shard=(0, 1), dist=None):
                     'roofline': {'bound': 'hbm', 'achieved': byts / (ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
                                  'frac': byts / (ms / 1e3) / 1e9 / hbm, 'traffic': None}}
     return out
+
+
+def run_c5(dev):
+    """C5 (BASELINE.json configs[4]): long utterances (1600 frames), 512-dim BLSTM, B=32, U=100 -- train step timing."""
+    from ss_asr_b200.asr import ASR
+    from ss_asr_b200.functional import asr_loss
+    torch.manual_seed(1)
+    m = ASR(50, 512, 256, 128, 80, 0.9).to(dev)
+    m.train_precision = 'bf16'
+    m.train()
+    m.att_on_device = True
+    opt = torch.optim.Adadelta(m.parameters(), lr=1.0, eps=1e-8)
+    x, lens, y = synth_batch(32, 1600, 80, 100)
+    xd, yd = x.to(dev), y.to(dev)
+    ans = int(max((y != 0).sum(-1) + 1)) - 1
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        _, logits, _ = m(xd, ans, teacher=yd, state_len=lens)
+        asr_loss(logits, yd).backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+        opt.step()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return {'workload': 'C5 long-utterance LAS train step: B=32, T=1600, F=80, S_enc=512, S_dec=256, U=100',
+            'ms_per_step': ms, 'utt_per_s': 32 / ms * 1e3}
 
 
 def main():

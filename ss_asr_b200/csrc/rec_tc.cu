@@ -632,13 +632,13 @@ static int max_z(int S) {
   return z < 1 ? 1 : z;
 }
 // 64-row tiles whenever that still gives every tile its own CTA: twice the CTAs, half the per-SM exchange traffic
-static int pick_tm(int S, int n_batch) { return ((n_batch + 63) / 64 <= max_z(S)) ? 64 : 128; }
+static int pick_tm(int S, int n_batch) { return (S > 256 || (n_batch + 63) / 64 <= max_z(S)) ? 64 : 128; }   // S > 256: only 64-row tiles fit in smem
 static int pick_z(int S, int n_tiles) {
   int z = max_z(S);
   return z > n_tiles ? n_tiles : z;
 }
 
-int rec_tc_supported(int S) { return (S % 64 == 0 && S >= 64 && S <= 256) ? 1 : 0; }
+int rec_tc_supported(int S) { return (S % 64 == 0 && S >= 64 && S <= 512) ? 1 : 0; }
 
 template <int TM, int KB>
 static int launch_fwd_tc(const CUtensorMap& tmH, const CUtensorMap& tmW, RecTcParams& p, dim3 grid, cudaStream_t st) {
@@ -656,6 +656,14 @@ static int launch_fwd_tc_kb(int kb, const CUtensorMap& tmH, const CUtensorMap& t
     case 2: return launch_fwd_tc<TM, 2>(tmH, tmW, p, grid, st);
     case 3: return launch_fwd_tc<TM, 3>(tmH, tmW, p, grid, st);
     case 4: return launch_fwd_tc<TM, 4>(tmH, tmW, p, grid, st);
+  }
+  if constexpr (TM == 64) {
+    switch (kb) {
+      case 5: return launch_fwd_tc<TM, 5>(tmH, tmW, p, grid, st);
+      case 6: return launch_fwd_tc<TM, 6>(tmH, tmW, p, grid, st);
+      case 7: return launch_fwd_tc<TM, 7>(tmH, tmW, p, grid, st);
+      case 8: return launch_fwd_tc<TM, 8>(tmH, tmW, p, grid, st);
+    }
   }
   return -1;
 }

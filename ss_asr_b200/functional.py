@@ -58,7 +58,7 @@ class _BLSTM(torch.autograd.Function):
             check(lib.ssasr_cvt_bf16(ptr(wih_p), K, ptr(wih_bf), Kp, 8 * S, K, st), 'ssasr_cvt_bf16')
             xb = torch.zeros(n_rows, Kp, device=dev, dtype=torch.bfloat16) if Kp != K else \
                 torch.empty(n_rows, Kp, device=dev, dtype=torch.bfloat16)
-            tc_rec = S % 64 == 0 and S <= 256 and _TC_RECURRENCE
+            tc_rec = S % 64 == 0 and S <= 512 and _TC_RECURRENCE
             whh_bf = hb = None
             if tc_rec:
                 whh_bf = torch.empty(8 * S, S, device=dev, dtype=torch.bfloat16)
@@ -98,7 +98,7 @@ class _BLSTM(torch.autograd.Function):
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
             wihT_bf = bf(K, 8 * S)
             check(lib.ssasr_cvt_bf16_t(ptr(wih_p), K, ptr(wihT_bf), 8 * S, 8 * S, K, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
-            tc_rec = S % 64 == 0 and S <= 256 and _TC_RECURRENCE
+            tc_rec = S % 64 == 0 and S <= 512 and _TC_RECURRENCE
             whhT_bf = None
             if tc_rec:
                 whhT_bf = bf(2 * S, 4 * S)

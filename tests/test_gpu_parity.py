@@ -335,6 +335,7 @@ def test_cvt_bf16_transposed_shifted_masked():
 
 # bf16 training-path tolerances: logits atol 1e-2, loss rel 1e-3, gradients rel-L2 3e-2 and cosine >= 0.999
 @pytest.mark.parametrize('dims,B,T,U', [((50, 256, 256, 128, 80), 8, 128, 20), ((50, 64, 64, 32, 40), 140, 48, 6),
+                                        ((50, 512, 256, 128, 80), 3, 160, 6),        # C5 model: 512-dim BLSTM (64-row tiles)
                                         ((50, 128, 32, 16, 24), 5, 91, 7), ((50, 32, 48, 16, 20), 7, 64, 9)])
 def test_bf16_training_path(dims, B, T, U):
     """tcgen05 gate GEMMs (+ tensor-core recurrence when S % 64 == 0) against the fp32 CPU oracle."""
