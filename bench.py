@@ -364,7 +364,17 @@ def run_extras(model, dev, args, peaks, shard=(0, 1), dist=None):
     ms = tmax(e0.elapsed_time(e1))
     out['decode'] = {'workload': 'C3 greedy decode, %d utterances T~U[256,512], bs=1 semantics, 200-char cap, lm_weight 0'
                                  % n_total, 'utt_per_s': n_total / (ms / 1e3), 'ms': ms,
-                     'chars_per_s': sum(len(i) for i in ids) * world / (ms / 1e3)}
+                     'chars_per_s': sum(len(i) for i in ids) * world / (ms / 1e3),
+                     'precision': 'fp32 SIMT exact path'}
+    model.decode_batch(xb, mine, precision='tf32x3')
+    torch.cuda.synchronize()
+    e0.record()
+    ids2 = model.decode_batch(xb, mine, precision='tf32x3')
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = tmax(e0.elapsed_time(e1))
+    out['decode']['utt_per_s_tf32x3'] = n_total / (ms2 / 1e3)
+    out['decode']['tf32x3_identical_transcripts'] = sum(a == b for a, b in zip(ids, ids2)) / max(1, len(ids))
     if rank == 0 and world == 1:
         # secondary: same utterances with the (randomly initialised, as in ASRTester) CharLM at lm_weight 0.5
         import torch.nn as nn

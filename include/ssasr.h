@@ -47,7 +47,10 @@ int ssasr_unpack_lstmcell_grads(const float* dwcat, const float* dbcat, int S, i
 int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* bias_p, const float* whh_p,
                         int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, const int* lens,
                         float* xp /*[n_rows,8S] out: gate activations*/, float* hout /*[n_rows,2S], pre-zeroed*/,
-                        float* cbuf /*[n_rows,2S]*/, unsigned* bar /*2 words scratch*/, void* stream);
+                        float* cbuf /*[n_rows,2S]*/, unsigned* bar /*2 words scratch*/,
+                        float* tf32_ws /*NULL: fp32 SIMT input projection; else 2*(n_rows+8S)*K floats scratch: the
+                                         projection runs on tensor cores with the tf32 x 3 split (K % 4 == 0)*/,
+                        void* stream);
 int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* whhT_p, int S, int n_seq,
                         int n_batch, long long rs_seq, long long rs_batch, const int* lens,
                         float* act /*in: activations, out: gate grads*/, const float* hout, const float* cbuf,
@@ -61,6 +64,10 @@ int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
  *      inside nn.LSTM forward/backward (asr.py:414,262; trainer.py:437). ---- */
 int ssasr_gemm_bf16_tc(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                        int b_koff, float* C, int ldc, const float* bias, int accumulate, void* stream);
+/* fp32-ACCURATE tensor-core GEMM for the exact path: tf32 x 3 split (hi*hi + hi*lo + lo*hi), dense fp32 operands with
+   K % 4 == 0; A_ws / B_ws are caller scratch of TWICE the operands' sizes (hi | lo).  C = A B^T (+bias)(+tanh). */
+int ssasr_gemm_tf32x3(int M, int N, int K, const float* A, float* A_ws, long long lda, const float* B, float* B_ws,
+                      long long ldb, float* C, int ldc, const float* bias, int act_tanh, void* stream);
 /* C[M,N] fp32 (+)= A^T B; A stored [K,M], B stored [K,N] row-major bf16 (the weight-gradient form dW = dG^T X) */
 int ssasr_gemm_bf16_tc_tn(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                           int b_koff, float* C, int ldc, int accumulate, void* stream);

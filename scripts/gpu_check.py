@@ -68,6 +68,35 @@ def tc_check():
     print('gemm_tc %dx%dx%d: %.3f ms, %.1f TFLOP/s' % (M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
 
 
+def tf32_check():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K) in [(128, 128, 32), (256, 256, 256), (300, 200, 80), (1024, 2048, 1024), (4096, 2048, 1024)]:
+        A = torch.randn(M, K, generator=g).to(dev)
+        B = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        ref = A.double() @ B.double().t() + bias.double()
+        C = torch.zeros(M, N, device=dev)
+        Al, Bl = torch.empty(2 * M * K, device=dev), torch.empty(2 * N * K, device=dev)
+        _lib.check(lib.ssasr_gemm_tf32x3(M, N, K, A.data_ptr(), Al.data_ptr(), K, B.data_ptr(), Bl.data_ptr(), K, C.data_ptr(), N,
+                                         bias.data_ptr(), 0, _lib.stream()), 'tf32x3')
+        torch.cuda.synchronize()
+        f32 = (A @ B.t() + bias)
+        print('tf32x3', (M, N, K), 'max err vs fp64', float((C.double() - ref).abs().max()), ' torch fp32 err', float((f32.double() - ref).abs().max()))
+    M, N, K = 131072, 2048, 1024
+    A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); C = torch.empty(M, N, device=dev)
+    Al, Bl = torch.empty(2 * M * K, device=dev), torch.empty(2 * N * K, device=dev)
+    for _ in range(2):
+        lib.ssasr_gemm_tf32x3(M, N, K, A.data_ptr(), Al.data_ptr(), K, B.data_ptr(), Bl.data_ptr(), K, C.data_ptr(), N, None, 0, _lib.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        lib.ssasr_gemm_tf32x3(M, N, K, A.data_ptr(), Al.data_ptr(), K, B.data_ptr(), Bl.data_ptr(), K, C.data_ptr(), N, None, 0, _lib.stream())
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print('tf32x3 %dx%dx%d: %.3f ms, %.1f effective TFLOP/s' % (M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
+
+
 def tn_check():
     lib = _lib.load()
     g = torch.Generator().manual_seed(0)
@@ -191,6 +220,8 @@ if __name__ == '__main__':
         gemm_check()
     if 'tc' in which:
         tc_check()
+    if 'tf32' in which:
+        tf32_check()
     if 'tn' in which:
         tn_check()
     if 'bf16' in which:

@@ -44,10 +44,11 @@ SIGNATURES = {
     'ssasr_unpack_blstm_grads': (_I, [_P] * 3 + [_I, _I] + [_P] * 9),
     'ssasr_pack_lstmcell': (_I, [_P] * 4 + [_I, _I] + [_P] * 3),
     'ssasr_unpack_lstmcell_grads': (_I, [_P, _P, _I, _I] + [_P] * 5),
-    'ssasr_blstm_fwd_f32': (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P]),
+    'ssasr_blstm_fwd_f32': (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_blstm_bwd_f32': (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _I, _P]),
     'ssasr_gemm_bf16_tc': (_I, [_I, _I, _I, _P, _LL, _I, _P, _LL, _I, _P, _I, _P, _I, _P]),
+    'ssasr_gemm_tf32x3': (_I, [_I, _I, _I, _P, _P, _LL, _P, _P, _LL, _P, _I, _P, _I, _P]),
     'ssasr_gemm_bf16_tc_tn': (_I, [_I, _I, _I, _P, _LL, _I, _P, _LL, _I, _P, _I, _I, _P]),
     'ssasr_cvt_bf16': (_I, [_P, _LL, _P, _LL, _LL, _I, _P]),
     'ssasr_cvt_bf16_t': (_I, [_P, _LL, _P, _LL, _LL, _I, _I, _I, _I, _I, _P]),

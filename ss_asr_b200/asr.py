@@ -101,7 +101,7 @@ class Listener(nn.Module):
 
     def set_precision(self, precision):
         """'fp32': exact SIMT path (decode / validation / tight parity); 'bf16': tcgen05 gate GEMMs (training)."""
-        assert precision in ('fp32', 'bf16')
+        assert precision in ('fp32', 'bf16', 'tf32x3')
         self.precision = precision
         for m in (self.blstm_1, self.blstm_2, self.blstm_3):
             m.precision = precision
@@ -189,6 +189,7 @@ class ASR(nn.Module):
         self.tf_rate = tf_rate
         self.att_on_device = False       # True: keep attention maps on the GPU (skips the reference's D2H copy)
         self.train_precision = 'fp32'    # 'bf16': tensor-core gate GEMMs when training with grad enabled
+        self.decode_precision = 'fp32'   # 'tf32x3': encoder input projections of decode_batch on tensor cores
         self.sample_seed = 0
         self.last_tokens = None          # [B,U] int32: the input token of every step of the last forward
         self.init_parameters()
@@ -225,16 +226,20 @@ class ASR(nn.Module):
         return encode_len, logits, (att if self.att_on_device else att.cpu())
 
     @torch.no_grad()
-    def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0):
+    def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None):
         """Greedy decoding of many utterances at once with the per-utterance (bs=1) semantics of ASR.decode:
         xs [N,T,F] zero-padded, x_lens sorted in decreasing order; optional CharLM rescoring (asr.py:153-159).
         Returns a list of token-id lists."""
         prev = self.encoder.utterance_independent
         self.encoder.utterance_independent = True
+        # 'fp32': SIMT input projections (bit-for-tolerance exact path); 'tf32x3': the same projections on tensor cores
+        # with the 3-term tf32 split (~5e-5 absolute on the gate pre-activations, set by the tensor core's accumulator)
+        self.encoder.set_precision(precision or self.decode_precision)
         try:
             enc, enc_len = self.encoder(xs, x_lens)
         finally:
             self.encoder.utterance_independent = prev
+            self.encoder.set_precision('fp32')
         N = xs.shape[0]
         tok_in = torch.zeros(N, max_steps + 1, dtype=torch.int32, device=enc.device)
         lm = None

@@ -91,6 +91,10 @@ int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long 
 // C[M,N] fp32 (+)= A^T B with A stored [K,M], B stored [K,N] (row-major bf16, 16-byte row pitches); koffs shift rows
 int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                     int b_koff, float* C, int ldc, int accumulate);
+// fp32-accurate tensor-core GEMM: tf32 x 3 split (gemm_tc.cu)
+int split_hi_lo(cudaStream_t st, const float* x, float* hi, float* lo, size_t n);
+int gemm_tf32x3(cudaStream_t st, int M, int N, int K, const float* A, const float* A_lo, long long lda, const float* B,
+                const float* B_lo, long long ldb, float* C, int ldc, const float* bias, int act_tanh);
 int mask_rows_bf16(cudaStream_t st, void* x, long long rows, int cols, int period, int pos_lo, int pos_hi, int split);
 int cvt_bf16(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols);
 int cvt_bf16_t(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,

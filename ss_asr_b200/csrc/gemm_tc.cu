@@ -135,6 +135,117 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tmem_dealloc<BN>(tmem_base);
 }
 
+// ---- fp32-accurate variant ("tf32x3"): C = A·B^T with fp32 operands split as x = hi + lo, hi = the upper 19 bits the
+// tf32 tensor core reads, lo = x - hi (computed once per operand by split_lo_kernel); three MMAs per K step
+// (hi·hi + hi·lo + lo·hi) accumulate in the same TMEM tile.  Dropped terms are O(2^-21) relative: fp32-level accuracy
+// for the exact path (validation / greedy decode) at tensor-core speed.
+template <int STAGES>
+__global__ void __launch_bounds__(256, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl, float* __restrict__ C, int ldc,
+                   const float* __restrict__ bias, int M, int N, int K, int act_tanh) {
+  constexpr int BN = 128, BKF = 32;             // 32 fp32 = 128 B = one swizzle row
+  constexpr int T_BYTES = 128 * 128;            // one 128-row operand tile
+  constexpr int STAGE_BYTES = 4 * T_BYTES;      // A_hi, A_lo, B_hi, B_lo
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * BN;
+  const int num_k = (K + BKF - 1) / BKF;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBl);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(empty_bar + s, ((kb / STAGES) & 1) ^ 1);
+        mbar_expect_tx(full_bar + s, STAGE_BYTES);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_2d(&tmA, full_bar + s, st, kb * BKF, m0);
+        tma_load_2d(&tmAl, full_bar + s, st + T_BYTES, kb * BKF, m0);
+        tma_load_2d(&tmB, full_bar + s, st + 2 * T_BYTES, kb * BKF, n0);
+        tma_load_2d(&tmBl, full_bar + s, st + 3 * T_BYTES, kb * BKF, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_tf32(GT_BM, BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(full_bar + s, (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t dah = umma_desc_k128(base), dal = umma_desc_k128(base + T_BYTES);
+        const uint64_t dbh = umma_desc_k128(base + 2 * T_BYTES), dbl = umma_desc_k128(base + 3 * T_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKF / 8; ++k) {      // K = 8 fp32 = 32 B per step
+          const uint64_t o = (uint64_t)(k * 2);
+          mma_tf32_ss(tmem_base, dah + o, dbh + o, idesc, (kb | k) != 0);
+          mma_tf32_ss(tmem_base, dah + o, dbl + o, idesc, 1);
+          mma_tf32_ss(tmem_base, dal + o, dbh + o, idesc, 1);
+        }
+        mma_commit(empty_bar + s);
+      }
+      mma_commit(tmem_full);
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = m0 + ew * 32 + (threadIdx.x & 31);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < N) {
+            float o = __uint_as_float(v[j]) + (bias ? bias[n] : 0.f);
+            if (act_tanh) o = tanhf(o);
+            crow[c0 + j] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<BN>(tmem_base);
+}
+
+// hi = rn_tf32(x), lo = rn_tf32(x - hi): both exactly representable in tf32, so the tensor core's own truncation of
+// its fp32 inputs is a no-op and the only errors left are the unbiased roundings (2^-22 relative) and lo*lo.
+__device__ __forceinline__ float rn_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__global__ void split_hi_lo_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float h = rn_tf32(v);
+    hi[i] = h;
+    lo[i] = rn_tf32(v - h);
+  }
+}
+
 // ---- TN variant: C[M,N] = A^T B with A stored [K,M] and B stored [K,N] (both M/N-contiguous, "MN-major") --------
 // Used for the weight gradients dW = dG^T X directly from the row-major bf16 activations / gate gradients, so no
 // transposed copies are needed.  a_koff / b_koff shift the reduction ROW window of each operand (any integer:
@@ -319,6 +430,56 @@ int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long lo
   return 0;
 }
 
+static int make_tmap_f32(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  SSASR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  SSASR_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, "TMA operand needs a 16-byte aligned base and row pitch (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSASR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+  return 0;
+}
+
+int split_hi_lo(cudaStream_t st, const float* x, float* hi, float* lo, size_t n) {
+  if (n == 0) return 0;
+  ProfScope ps(F_PACK, st);
+  split_hi_lo_kernel<<<1184, 256, 0, st>>>(x, hi, lo, n);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+// C[M,N] fp32 = A[M,K] x B[N,K]^T (+bias)(+tanh); operands given as tf32-exact (hi, lo) pairs (K contiguous, ld % 4 == 0)
+int gemm_tf32x3(cudaStream_t st, int M, int N, int K, const float* A, const float* A_lo, long long lda, const float* B,
+                const float* B_lo, long long ldb, float* C, int ldc, const float* bias, int act_tanh) {
+  if (M <= 0 || N <= 0) return 0;
+  constexpr int STAGES = 3;
+  constexpr size_t SMEM = (size_t)STAGES * 4 * 128 * 128 + (2 * STAGES + 1) * 8 + 16 + 1024;
+  CUtensorMap tA, tAl, tB, tBl;
+  int rc = make_tmap_f32(&tA, A, M, K, lda);
+  if (rc) return rc;
+  rc = make_tmap_f32(&tAl, A_lo, M, K, lda);
+  if (rc) return rc;
+  rc = make_tmap_f32(&tB, B, N, K, ldb);
+  if (rc) return rc;
+  rc = make_tmap_f32(&tBl, B_lo, N, K, ldb);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr_set = true;
+  }
+  dim3 grid((M + GT_BM - 1) / GT_BM, (N + 127) / 128);
+  ProfScope ps(F_GEMM_TC, st);
+  gemm_tf32x3_kernel<STAGES><<<grid, 256, SMEM, st>>>(tA, tAl, tB, tBl, C, ldc, bias, M, N, K, act_tanh);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
 // 3-D bf16 tensor: dim0 = cols (contiguous), dim1 = nA entries strideA elements apart, dim2 = nB entries strideB
 // elements apart (strideA <= strideB expected); box = {64, boxA, boxB}; 128-B swizzle.
 int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long cols, long long nA, long long strideA, long long nB,
@@ -465,6 +626,19 @@ extern "C" {
 int ssasr_gemm_bf16_tc(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb, int b_koff,
                        float* C, int ldc, const float* bias, int accumulate, void* stream) {
   return gemm_bf16_tc((cudaStream_t)stream, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, 0);
+}
+// fp32-accurate tensor-core GEMM (tf32 x 3); A_ws / B_ws are scratch buffers of TWICE the operands' sizes (hi | lo)
+int ssasr_gemm_tf32x3(int M, int N, int K, const float* A, float* A_ws, long long lda, const float* B, float* B_ws, long long ldb,
+                      float* C, int ldc, const float* bias, int act_tanh, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSASR_REQUIRE(lda == K && ldb == K && K % 4 == 0, "ssasr_gemm_tf32x3: operands must be dense (lda == ldb == K) with K %% 4 == 0");
+  float* A_lo = A_ws + (size_t)M * K;
+  float* B_lo = B_ws + (size_t)N * K;
+  int rc = split_hi_lo(st, A, A_ws, A_lo, (size_t)M * K);
+  if (rc) return rc;
+  rc = split_hi_lo(st, B, B_ws, B_lo, (size_t)N * K);
+  if (rc) return rc;
+  return gemm_tf32x3(st, M, N, K, A_ws, A_lo, lda, B_ws, B_lo, ldb, C, ldc, bias, act_tanh);
 }
 int ssasr_gemm_bf16_tc_tn(int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb, int b_koff,
                           float* C, int ldc, int accumulate, void* stream) {

@@ -444,10 +444,24 @@ int ssasr_unpack_lstmcell_grads(const float* dwcat, const float* dbcat, int S, i
 //   bar  2 x uint32 scratch
 int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* bias_p, const float* whh_p,
                         int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* xp,
-                        float* hout, float* cbuf, unsigned* bar, void* stream) {
+                        float* hout, float* cbuf, unsigned* bar, float* tf32_ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(S % 16 == 0, "blstm_fwd: S=%d must be a multiple of 16", S);
-  int rc = gemm_f32(st, n_rows, 8 * S, K, x, K, 1, wih_p, K, 1, xp, 8 * S, bias_p, 0, 0);
+  int rc;
+  if (tf32_ws && K % 4 == 0) {
+    // input projection on tensor cores with the tf32 x 3 split (hi/lo pairs of x and W_ih in tf32_ws)
+    float* xh = tf32_ws;
+    float* xl = xh + (size_t)n_rows * K;
+    float* wh = xl + (size_t)n_rows * K;
+    float* wl = wh + (size_t)8 * S * K;
+    rc = split_hi_lo(st, x, xh, xl, (size_t)n_rows * K);
+    if (rc) return rc;
+    rc = split_hi_lo(st, wih_p, wh, wl, (size_t)8 * S * K);
+    if (rc) return rc;
+    rc = gemm_tf32x3(st, n_rows, 8 * S, K, xh, xl, K, wh, wl, K, xp, 8 * S, bias_p, 0);
+  } else {
+    rc = gemm_f32(st, n_rows, 8 * S, K, x, K, 1, wih_p, K, 1, xp, 8 * S, bias_p, 0, 0);
+  }
   if (rc) return rc;
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
   RecFwdParams p;

@@ -69,9 +69,12 @@ class _BLSTM(torch.autograd.Function):
                                            ptr(hout), ptr(cbuf), ptr(bar), ptr(whh_bf), ptr(hb), st),
                   'ssasr_blstm_fwd_bf16')
         else:
+            tws = None
+            if precision == 'tf32x3' and K % 4 == 0 and not torch.is_grad_enabled():
+                tws = torch.empty(2 * (n_rows + 8 * S) * K, device=dev)
             check(lib.ssasr_blstm_fwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch, rs_seq,
                                           rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
-                                          ptr(bar), st), 'ssasr_blstm_fwd_f32')
+                                          ptr(bar), ptr(tws), st), 'ssasr_blstm_fwd_f32')
         ctx.bf16 = bf16
         ctx.fwd_bf = (xb, hb, Kp) if (bf16 and hb is not None) else None      # bf16 x / h copies reused by the weight gradients
         ctx.save_for_backward(x, wih_p, whhT_p, xp, hout, cbuf, lens_dev if time_major else torch.empty(0))

@@ -385,3 +385,32 @@ def test_tc_recurrence_many_tiles_per_cta():
     O.listener(p, xg, lens)[0].sum().backward()
     a, b = xd.grad.cpu().double(), xg.grad.double()
     assert float((a - b).norm()) <= 3e-2 * float(b.norm())
+
+
+def test_decode_tf32x3_strings_and_gemm(golden_dir):
+    """Opt-in tensor-core exact path (tf32 x 3 split) for the decode encoder: GEMM within 1e-4 of fp64 at K=1024 and
+    greedy transcripts identical to the unmodified reference on the margin variant."""
+    from ss_asr_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 512, 384, 1024
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    C = torch.zeros(M, N, device=DEV)
+    Aw, Bw = torch.empty(2 * M * K, device=DEV), torch.empty(2 * N * K, device=DEV)
+    _lib.check(lib.ssasr_gemm_tf32x3(M, N, K, A.data_ptr(), Aw.data_ptr(), K, B.data_ptr(), Bw.data_ptr(), K, C.data_ptr(), N, None, 0,
+                                     _lib.stream()), 'tf32x3')
+    assert float((C.double() - A.double() @ B.double().t()).abs().max()) < 1e-4
+    z = np.load(os.path.join(golden_dir, 'decode_default.npz'))
+    sd = O.make_state_dict(50, 256, 256, 128, 80, seed=1)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 20.0
+    m = _model((50, 256, 256, 128, 80), sd)
+    Ts = [int(v) for v in z['Ts']]
+    xs = [torch.randn(1, Ti, 80, generator=torch.Generator().manual_seed(7000 + i)) for i, Ti in enumerate(Ts)]
+    order = sorted(range(len(Ts)), key=lambda i: -Ts[i])
+    xb = torch.zeros(len(Ts), max(Ts), 80)
+    for j, i in enumerate(order):
+        xb[j, :Ts[i]] = xs[i][0]
+    ids = m.decode_batch(xb.to(DEV), [Ts[i] for i in order], precision='tf32x3')
+    for j, i in enumerate(order):
+        assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
