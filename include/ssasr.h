@@ -50,6 +50,8 @@ int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
                         float* cbuf /*[n_rows,2S]*/, unsigned* bar /*2 words scratch*/,
                         float* tf32_ws /*NULL: fp32 SIMT input projection; else 2*(n_rows+8S)*K floats scratch: the
                                          projection runs on tensor cores with the tf32 x 3 split (K % 4 == 0)*/,
+                        void* x3_ws /*NULL: fp32 SIMT recurrence; else (16*S*S + 4*n_rows*S) bf16 scratch and `bar` of 4096
+                                      words: recurrence on tensor cores with the bf16 hi/lo x 3 split (S % 64 == 0, S <= 256)*/,
                         void* stream);
 int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* whhT_p, int S, int n_seq,
                         int n_batch, long long rs_seq, long long rs_batch, const int* lens,
@@ -112,6 +114,7 @@ typedef struct {
   float lm_weight;
   const float *lm_emb, *lm_w1i, *lm_w1h, *lm_b1i, *lm_b1h, *lm_w2i, *lm_w2h, *lm_b2i, *lm_b2h, *lm_wo, *lm_bo;
   float *lm_h1, *lm_h2;
+  float* x3_ws; /* NULL, or 2*B*max(X1,X2) + 8*Sd*(X1+X2) floats: forward-only gate GEMMs on tensor cores (tf32 x 3) */
 } ssasr_speller_fwd_args;
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
 

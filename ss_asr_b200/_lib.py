@@ -19,7 +19,7 @@ class SpellerFwdArgs(C.Structure):
                                            'logits', 'w1cat_bf', 'w2cat_bf', 'ws_bf', 'enc_bf')] +
                 [('lm_H', C.c_int), ('lm_weight', C.c_float)] +
                 [(n, C.c_void_p) for n in ('lm_emb', 'lm_w1i', 'lm_w1h', 'lm_b1i', 'lm_b1h', 'lm_w2i', 'lm_w2h', 'lm_b2i',
-                                           'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2')])
+                                           'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2', 'x3_ws')])
 
 
 class SpellerBwdArgs(C.Structure):
@@ -44,7 +44,7 @@ SIGNATURES = {
     'ssasr_unpack_blstm_grads': (_I, [_P] * 3 + [_I, _I] + [_P] * 9),
     'ssasr_pack_lstmcell': (_I, [_P] * 4 + [_I, _I] + [_P] * 3),
     'ssasr_unpack_lstmcell_grads': (_I, [_P, _P, _I, _I] + [_P] * 5),
-    'ssasr_blstm_fwd_f32': (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P]),
+    'ssasr_blstm_fwd_f32': (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_blstm_bwd_f32': (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _I, _P]),
     'ssasr_gemm_bf16_tc': (_I, [_I, _I, _I, _P, _LL, _I, _P, _LL, _I, _P, _I, _P, _I, _P]),

@@ -234,7 +234,8 @@ class ASR(nn.Module):
         self.encoder.utterance_independent = True
         # 'fp32': SIMT input projections (bit-for-tolerance exact path); 'tf32x3': the same projections on tensor cores
         # with the 3-term tf32 split (~5e-5 absolute on the gate pre-activations, set by the tensor core's accumulator)
-        self.encoder.set_precision(precision or self.decode_precision)
+        prec = precision or self.decode_precision
+        self.encoder.set_precision(prec)
         try:
             enc, enc_len = self.encoder(xs, x_lens)
         finally:
@@ -245,7 +246,7 @@ class ASR(nn.Module):
         lm = None
         if rnn_lm is not None and lm_weight != 0:
             lm = (Fk.pack_charlm(rnn_lm, enc.device), lm_weight)
-        _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), lm=lm)
+        _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), precision=prec, lm=lm)
         toks = toks[:, 1:].cpu().tolist()
         out = []
         for row in toks:

@@ -445,6 +445,43 @@ static int make_tmap_f32(CUtensorMap* m, const void* ptr, long long rows, long l
   return 0;
 }
 
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+// x = hi + lo with hi, lo in bf16 (relative residual 2^-17)
+int split_bf16(cudaStream_t st, const float* x, void* hi, void* lo, size_t n) {
+  if (n == 0) return 0;
+  ProfScope ps(F_PACK, st);
+  split_bf16_kernel<<<592, 256, 0, st>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void split_hi_lo_2d_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ hi,
+                                      float* __restrict__ lo) {
+  const long long n = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[(i / cols) * ld + (i % cols)];
+    const float h = rn_tf32(v);
+    hi[i] = h;
+    lo[i] = rn_tf32(v - h);
+  }
+}
+// strided rows [rows, cols] (pitch ld) -> dense tf32-exact hi / lo
+int split_hi_lo_2d(cudaStream_t st, const float* x, long long ld, int rows, int cols, float* hi, float* lo) {
+  if (rows <= 0 || cols <= 0) return 0;
+  ProfScope ps(F_PACK, st);
+  const long long n = (long long)rows * cols;
+  split_hi_lo_2d_kernel<<<(unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, st>>>(x, ld, rows, cols, hi, lo);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
 int split_hi_lo(cudaStream_t st, const float* x, float* hi, float* lo, size_t n) {
   if (n == 0) return 0;
   ProfScope ps(F_PACK, st);

@@ -444,7 +444,7 @@ int ssasr_unpack_lstmcell_grads(const float* dwcat, const float* dbcat, int S, i
 //   bar  2 x uint32 scratch
 int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* bias_p, const float* whh_p,
                         int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* xp,
-                        float* hout, float* cbuf, unsigned* bar, float* tf32_ws, void* stream) {
+                        float* hout, float* cbuf, unsigned* bar, float* tf32_ws, void* x3_ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(S % 16 == 0, "blstm_fwd: S=%d must be a multiple of 16", S);
   int rc;
@@ -463,6 +463,16 @@ int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
     rc = gemm_f32(st, n_rows, 8 * S, K, x, K, 1, wih_p, K, 1, xp, 8 * S, bias_p, 0, 0);
   }
   if (rc) return rc;
+  if (x3_ws && S % 64 == 0 && S <= 256) {
+    // recurrence on tensor cores with the bf16 hi/lo split of h and W_hh (fp32-accurate: 3 MMAs per K step)
+    __nv_bfloat16* wh = (__nv_bfloat16*)x3_ws;
+    __nv_bfloat16* wl = wh + (size_t)8 * S * S;
+    __nv_bfloat16* hh = wl + (size_t)8 * S * S;
+    __nv_bfloat16* hl = hh + (size_t)n_rows * 2 * S;
+    rc = split_bf16(st, whh_p, wh, wl, (size_t)8 * S * S);
+    if (rc) return rc;
+    return rec_tc_fwd_x3(st, xp, wh, wl, hout, cbuf, hh, hl, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar);
+  }
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
   RecFwdParams p;
   p.xp = xp; p.whh = whh_p; p.hout = hout; p.cbuf = cbuf; p.lens = lens;

@@ -93,6 +93,7 @@ struct RecTcParams {
   float* hout;               // fwd out [rows,2S] fp32
   float* cbuf;               // fwd out / bwd in
   __nv_bfloat16* xb;         // fwd: h exchange buffer [rows,2S] bf16.  bwd: dG exchange buffer [rows,8S] bf16
+  __nv_bfloat16* xb2;        // fwd, X3 mode: low part of the h exchange buffer (h = hi + lo, both bf16)
   const float* dhout;        // bwd
   float* dcstate;            // bwd [n_batch,2S]
   float* dbias;              // bwd: [8S] bias gradient (column sums of dG), pre-zeroed, accumulated with atomics; may be null
@@ -121,20 +122,24 @@ static long long* g_dbg = nullptr;
 // Epilogue data movement is staged through shared memory so that every global access is a contiguous 64-256 B
 // row segment: the xp tile of the NEXT step is prefetched with cp.async while the step barrier / TMA / MMA of
 // that step are in flight, the thread-per-batch-row cell math works on smem, results leave as coalesced stores.
-template <int TM, int KB>   // TM = batch rows per tile (64 or 128), KB = S / 64 resident k-blocks
+// X3: fp32-accurate mode for the exact (validation / decode) path: h and W_hh are split into bf16 hi + lo parts and the
+// product is hi*hi + hi*lo + lo*hi (3 MMAs per K step); precise expf/tanhf activations.
+template <int TM, int KB, bool X3>   // TM = batch rows per tile (64 or 128), KB = S / 64 resident k-blocks
 __global__ void __launch_bounds__(RT_THREADS, 1)
-rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW, RecTcParams p) {
+rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmH2, const __grid_constant__ CUtensorMap tmW2, RecTcParams p) {
+  constexpr int NP = X3 ? 2 : 1;         // operand parts (hi [, lo])
   constexpr int W_BLK = 64 * 128;        // 64 gate rows x 128 B
   constexpr int A_BLK = TM * 128;        // TM batch rows x 128 B
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Wsm = smem;
-  uint8_t* Asm = smem + KB * W_BLK;
-  float* xs = reinterpret_cast<float*>(Asm + KB * A_BLK);                 // [128][XS_P]
+  uint8_t* Asm = smem + NP * KB * W_BLK;                                 // parts are laid out [part][kb]
+  float* xs = reinterpret_cast<float*>(Asm + NP * KB * A_BLK);            // [TM][XS_P]
   float* hst = xs + TM * XS_P;                                           // [128][HS_P]
   float* cst = hst + TM * HS_P;                                          // [128][HS_P]
-  __nv_bfloat16* hbst = reinterpret_cast<__nv_bfloat16*>(cst + TM * HS_P);   // [128][HB_P]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hbst + TM * HB_P);
+  __nv_bfloat16* hbst = reinterpret_cast<__nv_bfloat16*>(cst + TM * HS_P);   // [NP][TM][HB_P]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hbst + NP * TM * HB_P);
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
   uint64_t* mma_done = bars + 2;
@@ -159,8 +164,10 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp == 0 && elect_one()) {
-    mbar_expect_tx(w_full, KB * W_BLK);
+    mbar_expect_tx(w_full, NP * KB * W_BLK);
     for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * 4 * S + slice * 64);
+    if (X3)
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmW2, w_full, Wsm + (KB + kb) * W_BLK, kb * 64, dir * 4 * S + slice * 64);
   }
   unsigned* gbar = p.bar + dir * Z + z;
   const unsigned G = gridDim.x;
@@ -200,9 +207,13 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             if (bt == z) step_wait(gbar, (unsigned)s * G);       // every CTA of the group has published step s-1
             if (it > 0) mbar_wait(mma_done, (it - 1) & 1);       // previous MMAs have consumed the A tile
             DBG_STAMP(0);
-            mbar_expect_tx(a_full, KB * A_BLK);
+            mbar_expect_tx(a_full, NP * KB * A_BLK);
             for (int kb = 0; kb < KB; ++kb)
               tma_load_3d(&tmH, a_full, Asm + kb * A_BLK, dir * S + kb * 64, p.seq_inner ? tp : bt * TM, p.seq_inner ? bt * TM : tp);
+            if (X3)
+              for (int kb = 0; kb < KB; ++kb)
+                tma_load_3d(&tmH2, a_full, Asm + (KB + kb) * A_BLK, dir * S + kb * 64, p.seq_inner ? tp : bt * TM,
+                            p.seq_inner ? bt * TM : tp);
           }
         } else if (warp == 1) {
           if (elect_one()) {
@@ -217,6 +228,14 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
               const uint64_t da = umma_desc_k128(a0 + kb * A_BLK), db = umma_desc_k128(w0 + kb * W_BLK);
 #pragma unroll
               for (int k = 0; k < 4; ++k) mma_bf16_ss(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              if (X3) {
+                const uint64_t dal = umma_desc_k128(a0 + (KB + kb) * A_BLK), dbl = umma_desc_k128(w0 + (KB + kb) * W_BLK);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  mma_bf16_ss(tmem, da + (uint64_t)(k * 2), dbl + (uint64_t)(k * 2), idesc, 1);
+                  mma_bf16_ss(tmem, dal + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1);
+                }
+              }
             }
             mma_commit(mma_done);
             DBG_STAMP(2);
@@ -277,9 +296,15 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             if (valid) {
               g.x += __uint_as_float(v[j * 4 + 0]); g.y += __uint_as_float(v[j * 4 + 1]);
               g.z += __uint_as_float(v[j * 4 + 2]); g.w += __uint_as_float(v[j * 4 + 3]);
-              a.x = sigmoid_apx(g.x); a.y = sigmoid_apx(g.y); a.z = tanh_apx(g.z); a.w = sigmoid_apx(g.w);
-              cv[u] = fmaf(a.y, cpv[j], a.x * a.z);
-              hv[u] = a.w * tanh_apx(cv[u]);
+              if (X3) {
+                a.x = sigmoidf_acc(g.x); a.y = sigmoidf_acc(g.y); a.z = tanhf(g.z); a.w = sigmoidf_acc(g.w);
+                cv[u] = a.y * cpv[j] + a.x * a.z;
+                hv[u] = a.w * tanhf(cv[u]);
+              } else {
+                a.x = sigmoid_apx(g.x); a.y = sigmoid_apx(g.y); a.z = tanh_apx(g.z); a.w = sigmoid_apx(g.w);
+                cv[u] = fmaf(a.y, cpv[j], a.x * a.z);
+                hv[u] = a.w * tanh_apx(cv[u]);
+              }
             }
             creg[j] = cv[u];
             *reinterpret_cast<float4*>(xrow + j * 4) = a;
@@ -291,6 +316,15 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
           pk.x = *reinterpret_cast<uint32_t*>(&b01);
           pk.y = *reinterpret_cast<uint32_t*>(&b23);
           *reinterpret_cast<uint2*>(hbst + r * HB_P + q * 4) = pk;
+          if (X3) {      // low parts: h - float(bf16(h))
+            const float l0 = hv[0] - __bfloat162float(b01.x), l1 = hv[1] - __bfloat162float(b01.y);
+            const float l2 = hv[2] - __bfloat162float(b23.x), l3 = hv[3] - __bfloat162float(b23.y);
+            __nv_bfloat162 c01 = __floats2bfloat162_rn(l0, l1), c23 = __floats2bfloat162_rn(l2, l3);
+            uint2 pl;
+            pl.x = *reinterpret_cast<uint32_t*>(&c01);
+            pl.y = *reinterpret_cast<uint32_t*>(&c23);
+            *reinterpret_cast<uint2*>(hbst + (TM + r) * HB_P + q * 4) = pl;
+          }
         }
         }
         if (warp == 2 && lane == 0) DBG_STAMP(5);
@@ -304,6 +338,9 @@ rec_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant
             if (nn < p.n_batch)
               *reinterpret_cast<uint4*>(p.xb + (rbase + (size_t)nn * p.rs_batch) * 2 * S + hoff + hh * 8) =
                   *reinterpret_cast<const uint4*>(hbst + rr * HB_P + hh * 8);
+            if (X3 && nn < p.n_batch)
+              *reinterpret_cast<uint4*>(p.xb2 + (rbase + (size_t)nn * p.rs_batch) * 2 * S + hoff + hh * 8) =
+                  *reinterpret_cast<const uint4*>(hbst + (TM + rr) * HB_P + hh * 8);
           }
           if (bt + Z >= p.n_tiles && s + 1 < p.n_seq) {   // last tile of this step: publish
             epi_bar();
@@ -640,14 +677,21 @@ static int pick_z(int S, int n_tiles) {
 
 int rec_tc_supported(int S) { return (S % 64 == 0 && S >= 64 && S <= 512) ? 1 : 0; }
 
+template <int TM, int KB, bool X3>
+static int launch_fwd_tc_x(const CUtensorMap& tmH, const CUtensorMap& tmW, const CUtensorMap& tmH2, const CUtensorMap& tmW2,
+                           RecTcParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int NP = X3 ? 2 : 1;
+  const size_t smem = (size_t)NP * KB * (64 * 128 + TM * 128) + (size_t)TM * (XS_P + 2 * HS_P) * 4 + (size_t)NP * TM * HB_P * 2 + 64 + 1024;
+  SSASR_REQUIRE(smem <= 227 * 1024, "rec_tc_fwd: %zu B shared memory needed (S=%d)", smem, p.S);
+  SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_fwd_kernel<TM, KB, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* args[] = {(void*)&tmH, (void*)&tmW, (void*)&tmH2, (void*)&tmW2, (void*)&p};
+  ProfScope ps(F_REC_TC_FWD, st);
+  SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_tc_fwd_kernel<TM, KB, X3>, grid, dim3(RT_THREADS), args, smem, st));
+  return 0;
+}
 template <int TM, int KB>
 static int launch_fwd_tc(const CUtensorMap& tmH, const CUtensorMap& tmW, RecTcParams& p, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)KB * (64 * 128 + TM * 128) + (size_t)TM * (XS_P + 2 * HS_P) * 4 + (size_t)TM * HB_P * 2 + 64 + 1024;
-  SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_tc_fwd_kernel<TM, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  void* args[] = {(void*)&tmH, (void*)&tmW, (void*)&p};
-  ProfScope ps(F_REC_TC_FWD, st);
-  SSASR_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)rec_tc_fwd_kernel<TM, KB>, grid, dim3(RT_THREADS), args, smem, st));
-  return 0;
+  return launch_fwd_tc_x<TM, KB, false>(tmH, tmW, tmH, tmW, p, grid, st);
 }
 template <int TM>
 static int launch_fwd_tc_kb(int kb, const CUtensorMap& tmH, const CUtensorMap& tmW, RecTcParams& p, dim3 grid, cudaStream_t st) {
@@ -674,7 +718,7 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_fwd: unsupported state size %d", S);
   const int TM = pick_tm(S, n_batch);
   RecTcParams p;
-  p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.dhout = nullptr; p.dcstate = nullptr; p.dbias = nullptr;
+  p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.xb2 = nullptr; p.dhout = nullptr; p.dcstate = nullptr; p.dbias = nullptr;
   p.lens = lens;
   p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + TM - 1) / TM;
   p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;
@@ -689,6 +733,42 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
   if (rc) return rc;
   dim3 grid(S / RT_UNITS, 2, Z);
   return TM == 64 ? launch_fwd_tc_kb<64>(S / 64, tmH, tmW, p, grid, st) : launch_fwd_tc_kb<128>(S / 64, tmH, tmW, p, grid, st);
+}
+
+// fp32-accurate forward (exact path): hb_hi/hb_lo exchange buffers, whh_hi/whh_lo bf16 [8S,S]; 64-row tiles, S <= 256
+int rec_tc_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, float* cbuf, void* hb_hi,
+                  void* hb_lo, const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar) {
+  SSASR_REQUIRE(S % 64 == 0 && S >= 64 && S <= 256, "rec_tc_fwd_x3: unsupported state size %d", S);
+  constexpr int TM = 64;
+  RecTcParams p;
+  p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb_hi; p.xb2 = (__nv_bfloat16*)hb_lo; p.dhout = nullptr;
+  p.dcstate = nullptr; p.dbias = nullptr; p.lens = lens;
+  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + TM - 1) / TM;
+  p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = nullptr;
+  const int Z = pick_z(S, p.n_tiles);
+  SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned) * 2 * Z, st));
+  CUtensorMap tmH, tmH2, tmW, tmW2;
+  p.seq_inner = rs_seq < rs_batch ? 1 : 0;
+  int rc = 0;
+  for (int i = 0; i < 2 && !rc; ++i) {
+    void* hb = i ? hb_lo : hb_hi;
+    CUtensorMap* tm = i ? &tmH2 : &tmH;
+    rc = p.seq_inner ? make_tmap_bf16_3d(tm, hb, 2 * S, n_seq, rs_seq * 2 * S, n_batch, rs_batch * 2 * S, 1, TM)
+                     : make_tmap_bf16_3d(tm, hb, 2 * S, n_batch, rs_batch * 2 * S, n_seq, rs_seq * 2 * S, TM, 1);
+  }
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmW, whh_hi, 8 * S, S, S, 64);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmW2, whh_lo, 8 * S, S, S, 64);
+  if (rc) return rc;
+  dim3 grid(S / RT_UNITS, 2, Z);
+  switch (S / 64) {
+    case 1: return launch_fwd_tc_x<TM, 1, true>(tmH, tmW, tmH2, tmW2, p, grid, st);
+    case 2: return launch_fwd_tc_x<TM, 2, true>(tmH, tmW, tmH2, tmW2, p, grid, st);
+    case 3: return launch_fwd_tc_x<TM, 3, true>(tmH, tmW, tmH2, tmW2, p, grid, st);
+    case 4: return launch_fwd_tc_x<TM, 4, true>(tmH, tmW, tmH2, tmW2, p, grid, st);
+  }
+  return -1;
 }
 
 template <int TM, int NST>
@@ -710,7 +790,7 @@ int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_bwd: unsupported state size %d", S);
   const int TM = pick_tm(S, n_batch);
   RecTcParams p;
-  p.xp = act; p.hout = nullptr; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dcstate = dcstate;
+  p.xp = act; p.hout = nullptr; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.xb2 = nullptr; p.dhout = dhout; p.dcstate = dcstate;
   p.dbias = dbias;
   p.lens = lens; p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.n_tiles = (n_batch + TM - 1) / TM;
   p.rs_seq = rs_seq; p.rs_batch = rs_batch; p.bar = bar; p.dbg = g_dbg;

@@ -463,6 +463,9 @@ typedef struct {
   float lm_weight;
   const float *lm_emb, *lm_w1i, *lm_w1h, *lm_b1i, *lm_b1h, *lm_w2i, *lm_w2h, *lm_b2i, *lm_b2h, *lm_wo, *lm_bo;
   float *lm_h1, *lm_h2;
+  // forward-only fast exact mode: gate GEMMs on tensor cores with the tf32 x 3 split;
+  // scratch of 2*B*max(X1,X2) + 2*4Sd*(X1+X2) floats, or NULL
+  float* x3_ws;
 } ssasr_speller_fwd_args;
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
@@ -495,9 +498,27 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   // ([B, X1] followed by [B, X2]), which feed the tcgen05 gate GEMMs directly
   __nv_bfloat16* x1b = tc ? (__nv_bfloat16*)a->ws_bf : nullptr;
   __nv_bfloat16* x2b = tc ? x1b + (size_t)B * X1 : nullptr;
+  const bool x3 = !tc && a->x3_ws && X1 % 4 == 0 && X2 % 4 == 0;
+  float *xh = nullptr, *xl = nullptr, *w1h = nullptr, *w1l = nullptr, *w2h = nullptr, *w2l = nullptr;
+  if (x3) {
+    const int Xm = X1 > X2 ? X1 : X2;
+    xh = a->x3_ws; xl = xh + (size_t)B * Xm;
+    w1h = xl + (size_t)B * Xm; w1l = w1h + (size_t)4 * Sd * X1;
+    w2h = w1l + (size_t)4 * Sd * X1; w2l = w2h + (size_t)4 * Sd * X2;
+    rc = split_hi_lo(st, a->w1cat, w1h, w1l, (size_t)4 * Sd * X1);
+    if (rc) return rc;
+    rc = split_hi_lo(st, a->w2cat, w2h, w2l, (size_t)4 * Sd * X2);
+    if (rc) return rc;
+  }
   auto gate_gemm = [&](const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out,
                        const __nv_bfloat16* xb) -> int {
     if (tc) return gemm_bf16_tc(st, B, 4 * Sd, K, xb, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0);
+    if (x3) {
+      int r = split_hi_lo_2d(st, x, ldx, B, K, xh, xl);
+      if (r) return r;
+      const bool first = (K == X1);
+      return gemm_tf32x3(st, B, 4 * Sd, K, xh, xl, K, first ? w1h : w2h, first ? w1l : w2l, K, out, U * 4 * Sd, bias, 0);
+    }
     return gemm_f32(st, B, 4 * Sd, K, x, ldx, 1, w, K, 1, out, U * 4 * Sd, bias, 0, 0);
   };
   for (int t = 0; t < U; ++t) {

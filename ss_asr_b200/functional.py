@@ -46,7 +46,7 @@ class _BLSTM(torch.autograd.Function):
         xp = torch.empty(n_rows, 8 * S, device=dev)
         hout = torch.empty(d0, d1, 2 * S, device=dev)
         cbuf = torch.empty(d0, d1, 2 * S, device=dev)
-        bar = torch.zeros(512, dtype=torch.int32, device=dev)
+        bar = torch.zeros(4096, dtype=torch.int32, device=dev)
         if time_major:
             n_seq, n_batch, rs_seq, rs_batch = d1, d0, 1, d1
         else:
@@ -69,12 +69,15 @@ class _BLSTM(torch.autograd.Function):
                                            ptr(hout), ptr(cbuf), ptr(bar), ptr(whh_bf), ptr(hb), st),
                   'ssasr_blstm_fwd_bf16')
         else:
-            tws = None
-            if precision == 'tf32x3' and K % 4 == 0 and not torch.is_grad_enabled():
-                tws = torch.empty(2 * (n_rows + 8 * S) * K, device=dev)
+            tws = x3 = None
+            if precision == 'tf32x3' and not torch.is_grad_enabled():       # forward-only fast exact path
+                if K % 4 == 0:
+                    tws = torch.empty(2 * (n_rows + 8 * S) * K, device=dev)
+                if S % 64 == 0 and S <= 256:
+                    x3 = torch.empty(16 * S * S + 4 * n_rows * S, device=dev, dtype=torch.bfloat16)
             check(lib.ssasr_blstm_fwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch, rs_seq,
                                           rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
-                                          ptr(bar), ptr(tws), st), 'ssasr_blstm_fwd_f32')
+                                          ptr(bar), ptr(tws), ptr(x3), st), 'ssasr_blstm_fwd_f32')
         ctx.bf16 = bf16
         ctx.fwd_bf = (xb, hb, Kp) if (bf16 and hb is not None) else None      # bf16 x / h copies reused by the weight gradients
         ctx.save_for_backward(x, wih_p, whhT_p, xp, hout, cbuf, lens_dev if time_major else torch.empty(0))
@@ -174,6 +177,9 @@ class _Spell(torch.autograd.Function):
             check(lib.ssasr_cvt_bf16(ptr(w1cat), X1, ptr(w1b), X1, 4 * Sd, X1, st), 'ssasr_cvt_bf16')
             check(lib.ssasr_cvt_bf16(ptr(w2cat), X2, ptr(w2b), X2, 4 * Sd, X2, st), 'ssasr_cvt_bf16')
         ctx.bf16 = bf16
+        x3ws = None
+        if precision == 'tf32x3' and not torch.is_grad_enabled() and X1 % 4 == 0 and X2 % 4 == 0:
+            x3ws = torch.empty(2 * B * max(X1, X2) + 8 * Sd * (X1 + X2), device=dev)
         lmk = {}
         if lm is not None:      # (dict of transposed fp32 tensors, weight): greedy decode with the character LM
             lmt, lm_weight = lm
@@ -187,7 +193,7 @@ class _Spell(torch.autograd.Function):
                                 tok_in=ptr(tok_in), step_mode=C.cast(modes, C.c_void_p), seed=int(seed), psi=ptr(psi),
                                 xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
                                 h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits), w1cat_bf=ptr(w1b),
-                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), **lmk)
+                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), x3_ws=ptr(x3ws), **lmk)
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
