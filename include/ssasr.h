@@ -135,6 +135,22 @@ typedef struct {
 } ssasr_speller_bwd_args;
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream);
 
+/* ---- single-step module API: Attention.forward (asr.py:343-392) and Speller.forward / nn.LSTMCell (asr.py:314-326) as
+ *      called one decoding step at a time by the reference's other trainers (text_autoencoder.py:52-94) ---- */
+int ssasr_attn_step_fwd(int B, int Tp, int E, int Sd, int M, const float* h, const float* phi_w, const float* psi,
+                        const float* enc, const int* enc_lens, float* xrow /*[B,Sd+E+Sd] scratch; ctx = cols Sd..Sd+E*/,
+                        float* q /*[B,M]*/, float* alpha /*[B,Tp]*/, void* stream);
+int ssasr_attn_step_bwd(int B, int Tp, int E, int Sd, int M, const float* dctx, const float* dalpha /*or NULL*/,
+                        const float* alpha, const float* q, const float* phi_w, const float* psi, const float* enc,
+                        const int* enc_lens, float* de /*[B,Tp]*/, float* dqpre /*[B,M]*/, float* dh /*[B,Sd]*/,
+                        float* denc /*[B,Tp,E]*/, float* dpsi /*[B,Tp,M]*/, void* stream);
+int ssasr_lstmcell_fwd(int B, int S, float* gates /*[B,4S] interleaved: pre-activations in, activations out*/,
+                       const float* c_prev /*or NULL*/, float* c_out, float* h_out, void* stream);
+int ssasr_lstmcell_bwd(int B, int S, float* act /*activations in, gate gradients out*/, const float* c, const float* c_prev,
+                       const float* dh, float* dc /*in: dL/dc_out, out: dL/dc_prev*/, void* stream);
+int ssasr_dtanh_mul(float* d, const float* y, long long n, void* stream);
+int ssasr_colsum(const float* src, float* out, int R, int C, int ld, int accumulate, void* stream);
+
 /* ---- ASR loss: trainer.py:394-395,426-434 (CrossEntropyLoss(ignore_index=0,'none'), per-utterance length
  *      normalisation, batch mean), fused with its gradient ---- */
 int ssasr_ce_loss_f32(const float* logits, const long long* y, int B, int U, int C, int L, float* loss_b /*[B]*/,

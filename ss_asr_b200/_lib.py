@@ -57,6 +57,12 @@ SIGNATURES = {
                                   _I, _LL, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     'ssasr_speller_fwd_f32': (_I, [C.POINTER(SpellerFwdArgs), _P]),
     'ssasr_speller_bwd_f32': (_I, [C.POINTER(SpellerBwdArgs), _P]),
+    'ssasr_attn_step_fwd': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'ssasr_attn_step_bwd': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'ssasr_lstmcell_fwd': (_I, [_I, _I, _P, _P, _P, _P, _P]),
+    'ssasr_lstmcell_bwd': (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
+    'ssasr_dtanh_mul': (_I, [_P, _P, _LL, _P]),
+    'ssasr_colsum': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'ssasr_ce_loss_f32': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P]),
     'ssasr_num_families': (_I, []),
     'ssasr_family_name': (C.c_char_p, [_I]),

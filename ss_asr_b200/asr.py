@@ -151,6 +151,12 @@ class Speller(nn.Module):
         self.state_list = [s.to(device) for s in state[0]]
         self.cell_list = [c.to(device) for c in state[1]]
 
+    def forward(self, input_context):
+        """One decoding step of both cells (asr.py:314-326); state lives on self.state_list / self.cell_list."""
+        self.state_list[0], self.cell_list[0] = Fk.lstm_cell(input_context, self.state_list[0], self.cell_list[0], self.layer_1)
+        self.state_list[1], self.cell_list[1] = Fk.lstm_cell(self.state_list[0], self.state_list[1], self.cell_list[1], self.layer_2)
+        return self.state_list[-1]
+
     def params(self):
         l1, l2 = self.layer_1, self.layer_2
         return (l1.weight_ih, l1.weight_hh, l1.bias_ih, l1.bias_hh, l2.weight_ih, l2.weight_hh, l2.bias_ih, l2.bias_hh)
@@ -166,10 +172,22 @@ class Attention(nn.Module):
         self.psi = nn.Linear(encoder_out_size, mlp_out_size)
         self.comp_listener_feature = None
         self.state_mask = None
+        self._lens_dev = None
 
     def reset_enc_mem(self):
         self.comp_listener_feature = None
         self.state_mask = None
+        self._lens_dev = None
+
+    def forward(self, decoder_state, listener_feature, state_len):
+        """-> (attention_score [B,T'], context [B,E])   asr.py:343-392 (memory and pad mask cached across steps)."""
+        if self.comp_listener_feature is None:
+            B, Tp = listener_feature.shape[0], listener_feature.shape[1]
+            lens = _lens_list(state_len)
+            self._lens_dev = torch.tensor(lens, dtype=torch.int32, device=listener_feature.device)
+            self.state_mask = torch.arange(Tp, device=listener_feature.device)[None, :] >= self._lens_dev[:, None]
+            self.comp_listener_feature = Fk.psi_memory(listener_feature, self.psi.weight, self.psi.bias)
+        return Fk.attn_step(decoder_state, listener_feature, self.comp_listener_feature, self._lens_dev, self.phi.weight)
 
     def params(self):
         return (self.phi.weight, self.psi.weight, self.psi.bias)

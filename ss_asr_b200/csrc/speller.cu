@@ -38,12 +38,12 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
   float* scratch = es + a.Tp;     // [32]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   float* xrow = a.xin1 + (size_t)b * a.xin1_ld;
-  const int tk = a.tok[(size_t)b * a.tok_ld];
+  const int tk = a.tok ? a.tok[(size_t)b * a.tok_ld] : 0;
   for (int k = tid; k < a.Sd; k += blockDim.x) {
     const float h = a.h1prev ? a.h1prev[(size_t)b * a.h1_ld + k] : 0.f;
     hs[k] = h;
     xrow[a.Sd + a.E + k] = h;
-    const float e = a.emb_w[(size_t)tk * a.Sd + k];
+    const float e = a.emb_w ? a.emb_w[(size_t)tk * a.Sd + k] : 0.f;
     xrow[k] = e;
     if (a.xin1b) {
       a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + a.E + k] = __float2bfloat16(h);
@@ -114,6 +114,7 @@ struct AttnBwd {
   const float* psi;                          // [B,Tp,M]
   const float* enc;                          // [B,Tp,E]
   const int* enc_lens;
+  const float* dalpha; long long dalpha_ld;  // optional [B,Tp]: extra gradient arriving on the attention scores
   float* de; long long de_ld;                // [B,Tp] out: dL/d(energy) of this step (accumulated into denc/dpsi later)
   float* dqpre; long long dqpre_ld;          // [B,M] out
   float* dh1att;                             // [B,Sd] out
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
       for (int c = lane; c < a.E; c += 32) s = fmaf(dcs[c], encb[(size_t)j * a.E + c], s);
       s = warp_sum(s);
     }
-    if (lane == 0) das[j] = s;
+    if (lane == 0) das[j] = s + ((a.dalpha && j < len) ? a.dalpha[(size_t)b * a.dalpha_ld + j] : 0.f);
   }
   __syncthreads();
   float dot = 0.f;
@@ -675,6 +676,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     g.alpha = a->alpha + (size_t)t * Tp; g.alpha_ld = (long long)U * Tp;
     g.q = a->q + (size_t)t * M; g.q_ld = (long long)U * M;
     g.phi_w = a->phi_w; g.psi = a->psi; g.enc = a->enc; g.enc_lens = a->enc_lens;
+    g.dalpha = nullptr; g.dalpha_ld = 0;
     g.de = a->de_all + (size_t)t * Tp; g.de_ld = (long long)U * Tp;
     g.dqpre = a->dqpre + (size_t)t * M; g.dqpre_ld = (long long)U * M;
     g.dh1att = a->dh1att;
@@ -719,6 +721,76 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   if (rc) return rc;
   SSASR_LAUNCH_CHECK();
   return 0;
+}
+
+// ---- single-step module API (Attention.forward asr.py:343-392, Speller.forward asr.py:314-326 as called one step at a
+// time by the reference's other trainers, text_autoencoder.py:52-94) -------------------------------------------------
+// xrow scratch [B, Sd+E+Sd]: on return ctx = xrow[:, Sd:Sd+E]
+int ssasr_attn_step_fwd(int B, int Tp, int E, int Sd, int M, const float* h, const float* phi_w, const float* psi,
+                        const float* enc, const int* enc_lens, float* xrow, float* q, float* alpha, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnFwd f;
+  f.Tp = Tp; f.E = E; f.Sd = Sd; f.M = M;
+  f.h1prev = h; f.h1_ld = Sd; f.phi_w = phi_w; f.psi = psi; f.enc = enc; f.enc_lens = enc_lens;
+  f.emb_w = nullptr; f.tok = nullptr; f.tok_ld = 0;
+  f.xin1 = xrow; f.xin1_ld = 2 * Sd + E; f.xin1b = nullptr; f.xin1b_ld = 0;
+  f.q = q; f.q_ld = M; f.alpha = alpha; f.alpha_ld = Tp;
+  const size_t smem = (size_t)(Sd + M + Tp + 32) * sizeof(float);
+  SSASR_REQUIRE(smem <= 200 * 1024, "attn_step_fwd: working set too large (Tp=%d)", Tp);
+  if (smem > 48 * 1024) SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(F_ATTN_FWD, st);
+  attn_fwd_kernel<<<B, 256, smem, st>>>(f);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+// dctx [B,E], dalpha [B,Tp] or NULL -> dh [B,Sd], dqpre [B,M], de [B,Tp], denc [B,Tp,E] (overwritten), dpsi [B,Tp,M] (overwritten)
+int ssasr_attn_step_bwd(int B, int Tp, int E, int Sd, int M, const float* dctx, const float* dalpha, const float* alpha,
+                        const float* q, const float* phi_w, const float* psi, const float* enc, const int* enc_lens, float* de,
+                        float* dqpre, float* dh, float* denc, float* dpsi, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnBwd g;
+  g.Tp = Tp; g.E = E; g.Sd = Sd; g.M = M;
+  g.dctx = dctx; g.dctx_ld = E; g.alpha = alpha; g.alpha_ld = Tp; g.q = q; g.q_ld = M;
+  g.phi_w = phi_w; g.psi = psi; g.enc = enc; g.enc_lens = enc_lens;
+  g.dalpha = dalpha; g.dalpha_ld = Tp; g.de = de; g.de_ld = Tp; g.dqpre = dqpre; g.dqpre_ld = M; g.dh1att = dh;
+  const size_t smem = (size_t)(E + 2 * Tp + M + 32) * sizeof(float);
+  SSASR_REQUIRE(smem <= 200 * 1024, "attn_step_bwd: working set too large (Tp=%d)", Tp);
+  if (smem > 48 * 1024) SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(F_ATTN_BWD, st);
+  attn_bwd_kernel<<<B, 256, smem, st>>>(g);
+  attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, 8 * sizeof(float), st>>>(1, Tp, E, alpha, dctx, E, E, denc, enc_lens);
+  attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, 8 * sizeof(float), st>>>(1, Tp, M, de, q, M, M, dpsi, enc_lens);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+// gates [B,4S] interleaved pre-activations (in) -> activations (out); c_prev may be NULL (zero state)
+int ssasr_lstmcell_fwd(int B, int S, float* gates, const float* c_prev, float* c_out, float* h_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSASR_REQUIRE(S % 4 == 0, "lstmcell: S=%d must be a multiple of 4", S);
+  ProfScope ps(F_POINTWISE, st);
+  cell_fwd_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(B, S, gates, 4 * S, c_prev, S, c_out, S, h_out, S, nullptr, 0, nullptr, 0, nullptr,
+                                                       0, 0);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+// act [B,4S] activations (in) -> dL/d(pre-activations) (out); dc [B,S]: in = dL/dc_out, out = dL/dc_prev
+int ssasr_lstmcell_bwd(int B, int S, float* act, const float* c, const float* c_prev, const float* dh, float* dc, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(F_POINTWISE, st);
+  cell_bwd_kernel<<<(B * S + 255) / 256, 256, 0, st>>>(B, S, act, 4 * S, c, S, c_prev, S, dh, S, nullptr, 0, nullptr, 0, dc, 0, nullptr);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+// d *= (1 - y*y)  (backward of tanh given its output y)
+int ssasr_dtanh_mul(float* d, const float* y, long long n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(F_POINTWISE, st);
+  dtanh_inplace_kernel<<<256, 256, 0, st>>>(d, y, (size_t)n);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+int ssasr_colsum(const float* src, float* out, int R, int C, int ld, int accumulate, void* stream) {
+  return colsum((cudaStream_t)stream, src, out, R, C, ld, accumulate);
 }
 
 // Fused loss of trainer.py:426-434: per-utterance sum of CE(ignore_index=0) / count(y != 0), batch mean.

@@ -290,3 +290,144 @@ class _ASRLoss(torch.autograd.Function):
 def asr_loss(logits, y):
     """loss of ASRTrainer.exec (trainer.py:426-434): logits [B,U,C], y [B,L] (label of step t = y[:, t+1])."""
     return _ASRLoss.apply(logits, y)
+
+
+# --------------------------------------------------------------------------------------------------
+# single-step module API (Attention.forward / Speller.forward called one decoding step at a time,
+# text_autoencoder.py:52-94).  Not the hot path of ASR.forward, but the same kernels.
+# --------------------------------------------------------------------------------------------------
+def _gemm(lib, M, N, K, A, lda, akm, B, ldb, bkm, Cm, ldc, bias=None, acc=0, tanh=0):
+    check(lib.ssasr_gemm_f32(M, N, K, ptr(A) if not isinstance(A, int) else A, lda, akm, ptr(B) if not isinstance(B, int) else B,
+                             ldb, bkm, ptr(Cm), ldc, ptr(bias), acc, tanh, stream()), 'ssasr_gemm_f32')
+
+
+class _PsiMemory(torch.autograd.Function):
+    """comp_listener_feature = tanh(psi(listener_feature))   (asr.py:381)."""
+
+    @staticmethod
+    def forward(ctx, enc, psi_w, psi_b):
+        lib = _lib.load()
+        _lib.require_cuda(enc, 'Attention')
+        enc, psi_w, psi_b = _f32c(enc), _f32c(psi_w), _f32c(psi_b)
+        B, Tp, E = enc.shape
+        M = psi_w.shape[0]
+        out = torch.empty(B, Tp, M, device=enc.device)
+        _gemm(lib, B * Tp, M, E, enc, E, 1, psi_w, E, 1, out, M, psi_b, 0, 1)
+        ctx.save_for_backward(enc, psi_w, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        lib = _lib.load()
+        enc, psi_w, out = ctx.saved_tensors
+        B, Tp, E = enc.shape
+        M = psi_w.shape[0]
+        d = _f32c(d).clone()
+        check(lib.ssasr_dtanh_mul(ptr(d), ptr(out), d.numel(), stream()), 'ssasr_dtanh_mul')
+        denc = torch.empty_like(enc)
+        dw = torch.empty_like(psi_w)
+        db = torch.empty(M, device=enc.device)
+        _gemm(lib, B * Tp, E, M, d, M, 1, psi_w, E, 0, denc, E)
+        _gemm(lib, M, E, B * Tp, d, M, 0, enc, E, 0, dw, E)
+        check(lib.ssasr_colsum(ptr(d), ptr(db), B * Tp, M, M, 0, stream()), 'ssasr_colsum')
+        return denc, dw, db
+
+
+class _AttnStep(torch.autograd.Function):
+    """One call of Attention.forward after the memory is cached (asr.py:383-392)."""
+
+    @staticmethod
+    def forward(ctx, h, enc, psi_t, lens_dev, phi_w):
+        lib = _lib.load()
+        _lib.require_cuda(h, 'Attention')
+        h, enc, psi_t, phi_w = _f32c(h), _f32c(enc), _f32c(psi_t), _f32c(phi_w)
+        B, Tp, E = enc.shape
+        Sd, M = h.shape[1], phi_w.shape[0]
+        dev = h.device
+        xrow = torch.empty(B, 2 * Sd + E, device=dev)
+        q = torch.empty(B, M, device=dev)
+        alpha = torch.empty(B, Tp, device=dev)
+        check(lib.ssasr_attn_step_fwd(B, Tp, E, Sd, M, ptr(h), ptr(phi_w), ptr(psi_t), ptr(enc), ptr(lens_dev), ptr(xrow), ptr(q),
+                                      ptr(alpha), stream()), 'ssasr_attn_step_fwd')
+        ctxv = xrow[:, Sd:Sd + E].contiguous()
+        ctx.save_for_backward(h, enc, psi_t, lens_dev, phi_w, q, alpha)
+        return alpha, ctxv
+
+    @staticmethod
+    def backward(ctx, dalpha, dctx):
+        lib = _lib.load()
+        h, enc, psi_t, lens_dev, phi_w, q, alpha = ctx.saved_tensors
+        B, Tp, E = enc.shape
+        Sd, M = h.shape[1], phi_w.shape[0]
+        dev = h.device
+        f = lambda *s: torch.empty(*s, device=dev)
+        de, dqpre, dh, denc, dpsi = f(B, Tp), f(B, M), f(B, Sd), f(B, Tp, E), f(B, Tp, M)
+        dctx = _f32c(dctx) if dctx is not None else torch.zeros(B, E, device=dev)
+        dal = _f32c(dalpha) if dalpha is not None else None
+        check(lib.ssasr_attn_step_bwd(B, Tp, E, Sd, M, ptr(dctx), ptr(dal), ptr(alpha), ptr(q), ptr(phi_w), ptr(psi_t), ptr(enc),
+                                      ptr(lens_dev), ptr(de), ptr(dqpre), ptr(dh), ptr(denc), ptr(dpsi), stream()),
+              'ssasr_attn_step_bwd')
+        dphi = f(M, Sd)
+        _gemm(lib, M, Sd, B, dqpre, M, 0, h, Sd, 0, dphi, Sd)
+        return dh, denc, dpsi, None, dphi
+
+
+class _LSTMCell(torch.autograd.Function):
+    """nn.LSTMCell(x, (h, c)) -> (h', c')   (asr.py:320-324)."""
+
+    @staticmethod
+    def forward(ctx, x, h, c, w_ih, w_hh, b_ih, b_hh):
+        lib = _lib.load()
+        _lib.require_cuda(x, 'Speller')
+        x, h, c = _f32c(x), _f32c(h), _f32c(c)
+        B, Kin = x.shape
+        S = w_hh.shape[1]
+        dev = x.device
+        st = stream()
+        wcat = torch.empty(4 * S, Kin + S, device=dev)
+        bcat = torch.empty(4 * S, device=dev)
+        check(lib.ssasr_pack_lstmcell(ptr(_f32c(w_ih)), ptr(_f32c(w_hh)), ptr(_f32c(b_ih)), ptr(_f32c(b_hh)), S, Kin, ptr(wcat),
+                                      ptr(bcat), st), 'ssasr_pack_lstmcell')
+        xin = torch.cat([x, h], dim=1).contiguous()
+        act = torch.empty(B, 4 * S, device=dev)
+        _gemm(lib, B, 4 * S, Kin + S, xin, Kin + S, 1, wcat, Kin + S, 1, act, 4 * S, bcat)
+        h2, c2 = torch.empty(B, S, device=dev), torch.empty(B, S, device=dev)
+        check(lib.ssasr_lstmcell_fwd(B, S, ptr(act), ptr(c), ptr(c2), ptr(h2), st), 'ssasr_lstmcell_fwd')
+        ctx.save_for_backward(xin, wcat, act, c, c2)
+        ctx.dims = (B, Kin, S)
+        return h2, c2
+
+    @staticmethod
+    def backward(ctx, dh2, dc2):
+        lib = _lib.load()
+        xin, wcat, act, c, c2 = ctx.saved_tensors
+        B, Kin, S = ctx.dims
+        dev = xin.device
+        st = stream()
+        dh2 = _f32c(dh2) if dh2 is not None else torch.zeros(B, S, device=dev)
+        dc = _f32c(dc2).clone() if dc2 is not None else torch.zeros(B, S, device=dev)
+        dg = act.clone()
+        check(lib.ssasr_lstmcell_bwd(B, S, ptr(dg), ptr(c2), ptr(c), ptr(dh2), ptr(dc), st), 'ssasr_lstmcell_bwd')
+        X = Kin + S
+        dxin = torch.empty(B, X, device=dev)
+        dw = torch.empty(4 * S, X, device=dev)
+        db = torch.empty(4 * S, device=dev)
+        _gemm(lib, B, X, 4 * S, dg, 4 * S, 1, wcat, X, 0, dxin, X)
+        _gemm(lib, 4 * S, X, B, dg, 4 * S, 0, xin, X, 0, dw, X)
+        check(lib.ssasr_colsum(ptr(dg), ptr(db), B, 4 * S, 4 * S, 0, st), 'ssasr_colsum')
+        g = [torch.zeros(4 * S, Kin, device=dev), torch.zeros(4 * S, S, device=dev), torch.zeros(4 * S, device=dev),
+             torch.zeros(4 * S, device=dev)]
+        check(lib.ssasr_unpack_lstmcell_grads(ptr(dw), ptr(db), S, Kin, *[ptr(t) for t in g], st), 'ssasr_unpack_lstmcell_grads')
+        return (dxin[:, :Kin].contiguous(), dxin[:, Kin:].contiguous(), dc) + tuple(g)
+
+
+def psi_memory(enc, psi_w, psi_b):
+    return _PsiMemory.apply(enc, psi_w, psi_b)
+
+
+def attn_step(h, enc, psi_t, lens_dev, phi_w):
+    return _AttnStep.apply(h, enc, psi_t, lens_dev, phi_w)
+
+
+def lstm_cell(x, h, c, cell):
+    return _LSTMCell.apply(x, h, c, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)

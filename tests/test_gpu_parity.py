@@ -414,3 +414,36 @@ def test_decode_tf32x3_strings_and_gemm(golden_dir):
     ids = m.decode_batch(xb.to(DEV), [Ts[i] for i in order], precision='tf32x3')
     for j, i in enumerate(order):
         assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
+
+
+def test_per_step_module_api_matches_fused_forward():
+    """Attention.forward / Speller.forward called one step at a time (text_autoencoder.py:52-94 usage) reproduce the
+    oracle's logits and gradients, i.e. the TAE/SAE/ADV trainers' call pattern keeps working on the drop-in modules."""
+    dims = (50, 32, 48, 16, 20)
+    sd = O.make_state_dict(*dims, seed=3)
+    x, lens, y = O.synth_batch(5, 64, 20, 6, seed=21)
+    loss_o, logits_o, att_o, enc_o, grads_o = O.train_step_grads(sd, x, lens, y)
+    m = _model(dims, sd)
+    U = logits_o.shape[1]
+    yd = y.to(DEV)
+    enc, enc_len = m.encoder(x.to(DEV), lens)
+    teacher = m.embed(yd)
+    m.decoder.init_rnn(enc.shape[0], enc.device)
+    m.attention.reset_enc_mem()
+    last = m.embed(torch.zeros(enc.shape[0], dtype=torch.long, device=DEV))
+    outs, atts = [], []
+    for t in range(U):
+        a, ctxv = m.attention(m.decoder.state_list[0], enc, enc_len)
+        dec_out = m.decoder(torch.cat([last, ctxv], dim=-1))
+        outs.append(m.char_trans(dec_out))
+        atts.append(a)
+        last = teacher[:, t + 1, :]
+    logits = torch.stack(outs, 1)
+    assert float((logits.detach().cpu() - logits_o).abs().max()) < 1e-5
+    assert float((torch.stack(atts, 1).detach().cpu() - att_o).abs().max()) < 1e-5
+    assert m.attention.comp_listener_feature is not None and m.attention.state_mask.dtype == torch.bool
+    h, c = m.decoder.hidden_state
+    assert len(h) == 2 and not h[0].is_cuda
+    from ss_asr_b200.functional import asr_loss
+    asr_loss(logits, yd).backward()
+    _check_grads(m, grads_o)
