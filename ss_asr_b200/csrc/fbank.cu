@@ -12,6 +12,7 @@
 // applied in its sparse (two triangles per bin) form.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 
@@ -24,6 +25,7 @@ struct FbankTables {
   int sr = 0, n_mels = 0, ws = 0, st = 0, nbins = 0;
   float* window = nullptr;     // [ws]
   float2* tw = nullptr;        // fast path: [200] W_200^m then [201] W_400^k ; generic: [ws] W_ws^m
+  float2* tw400 = nullptr;     // 16 kHz register-FFT path: [400] W_400^e
   int* mel_start = nullptr;    // [n_mels]
   int* mel_cnt = nullptr;      // [n_mels]
   int* mel_off = nullptr;      // [n_mels]
@@ -88,6 +90,12 @@ static int get_tables(int sr, int n_mels, FbankTables* out) {
     if (cnt[i] > t.max_cnt) t.max_cnt = cnt[i];
   }
   if (wts.empty()) wts.push_back(0.f);
+  if (ws == 400) {
+    std::vector<float2> t4(400);
+    for (int e = 0; e < 400; ++e) t4[e] = make_float2((float)cos(2.0 * M_PI * e / 400), (float)-sin(2.0 * M_PI * e / 400));
+    SSASR_CHECK_CUDA(cudaMalloc(&t.tw400, sizeof(float2) * 400));
+    SSASR_CHECK_CUDA(cudaMemcpy(t.tw400, t4.data(), sizeof(float2) * 400, cudaMemcpyHostToDevice));
+  }
   SSASR_CHECK_CUDA(cudaMalloc(&t.window, sizeof(float) * ws));
   SSASR_CHECK_CUDA(cudaMalloc(&t.tw, sizeof(float2) * tw.size()));
   SSASR_CHECK_CUDA(cudaMalloc(&t.mel_start, sizeof(int) * n_mels));
@@ -157,6 +165,65 @@ __device__ __forceinline__ void stockham_stage(const float2* __restrict__ src, f
   }
 }
 
+// ---- register-resident 20-point DFT (4 x 5 Cooley-Tukey, compile-time twiddles) --------------------------------
+__device__ __forceinline__ float2 w20(int e) {     // W_20^e = exp(-2 pi i e / 20); e is a compile-time constant after unrolling
+  switch (e) {
+    case 0: return make_float2(1.000000000e+00f, -0.000000000e+00f);
+    case 1: return make_float2(9.510565163e-01f, -3.090169944e-01f);
+    case 2: return make_float2(8.090169944e-01f, -5.877852523e-01f);
+    case 3: return make_float2(5.877852523e-01f, -8.090169944e-01f);
+    case 4: return make_float2(3.090169944e-01f, -9.510565163e-01f);
+    case 5: return make_float2(6.123233996e-17f, -1.000000000e+00f);
+    case 6: return make_float2(-3.090169944e-01f, -9.510565163e-01f);
+    case 7: return make_float2(-5.877852523e-01f, -8.090169944e-01f);
+    case 8: return make_float2(-8.090169944e-01f, -5.877852523e-01f);
+    case 9: return make_float2(-9.510565163e-01f, -3.090169944e-01f);
+    case 10: return make_float2(-1.000000000e+00f, -1.224646799e-16f);
+    case 11: return make_float2(-9.510565163e-01f, 3.090169944e-01f);
+    case 12: return make_float2(-8.090169944e-01f, 5.877852523e-01f);
+  }
+  return make_float2(1.f, 0.f);
+}
+__device__ __forceinline__ void dft4r(float2& a, float2& b, float2& c, float2& d) {     // in place, forward
+  const float2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d), t3 = csub(b, d);
+  a = cadd(t0, t2);
+  c = csub(t0, t2);
+  b = make_float2(t1.x + t3.y, t1.y - t3.x);
+  d = make_float2(t1.x - t3.y, t1.y + t3.x);
+}
+__device__ __forceinline__ void dft5r(float2& v0, float2& v1, float2& v2, float2& v3, float2& v4) {
+  const float c1 = 0.30901699437494745f, c2 = -0.8090169943749475f, s1 = 0.9510565162951535f, s2 = 0.5877852522924731f;
+  const float2 t1 = cadd(v1, v4), t2 = cadd(v2, v3), t3 = csub(v1, v4), t4 = csub(v2, v3);
+  const float2 a1 = make_float2(v0.x + c1 * t1.x + c2 * t2.x, v0.y + c1 * t1.y + c2 * t2.y);
+  const float2 a2 = make_float2(v0.x + c2 * t1.x + c1 * t2.x, v0.y + c2 * t1.y + c1 * t2.y);
+  const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+  const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+  v0 = make_float2(v0.x + t1.x + t2.x, v0.y + t1.y + t2.y);
+  v1 = make_float2(a1.x + b1.y, a1.y - b1.x);
+  v4 = make_float2(a1.x - b1.y, a1.y + b1.x);
+  v2 = make_float2(a2.x + b2.y, a2.y - b2.x);
+  v3 = make_float2(a2.x - b2.y, a2.y + b2.x);
+}
+// x[n], n = 5a + b  ->  X[k], k = c + 4d, returned in place as x[c + 4d]
+__device__ __forceinline__ void dft20(float2 (&x)[20]) {
+  float2 t[5][4];
+#pragma unroll
+  for (int b = 0; b < 5; ++b) {
+    float2 r0 = x[b], r1 = x[5 + b], r2 = x[10 + b], r3 = x[15 + b];
+    dft4r(r0, r1, r2, r3);
+    t[b][0] = r0;
+    t[b][1] = b ? cmul(r1, w20(b)) : r1;
+    t[b][2] = b ? cmul(r2, w20(2 * b)) : r2;
+    t[b][3] = b ? cmul(r3, w20(3 * b)) : r3;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    dft5r(t[0][c], t[1][c], t[2][c], t[3][c], t[4][c]);
+#pragma unroll
+    for (int d = 0; d < 5; ++d) x[c + 4 * d] = t[d][c];
+  }
+}
+
 struct FbankParams {
   const float* audio; const long long* offsets; int n_utt;
   float* out; const long long* out_offsets;
@@ -164,6 +231,89 @@ struct FbankParams {
   const float* window; const float2* tw;
   const int *mel_start, *mel_cnt, *mel_off; const float* mel_w;
 };
+
+// ---- 16 kHz / 25 ms fast path, register FFT: two real frames are packed into one 400-point complex FFT
+// (z = x_a + i x_b, |X_a[k]|^2 = |Z[k] + conj Z[400-k]|^2 / 4, |X_b[k]|^2 = |Z[k] - conj Z[400-k]|^2 / 4), and
+// 400 = 20 x 20: 20 threads per frame pair each run one register-resident 20-point DFT per pass, with one exchange
+// through shared memory in between.  8 pairs (16 frames) per CTA of 160 threads.
+constexpr int FPAIRS = 8;
+constexpr int NTP = FPAIRS * 20;
+constexpr int EXP = 21;            // row pitch (complex) of the 20 x 20 exchange tile: conflict-free both ways
+__global__ void __launch_bounds__(NTP, 4) fbank400p_kernel(FbankParams p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int ws = 400, st = 160, half = 200, NF = 2 * FPAIRS, PB = 202;
+  float* span = smem;                                             // [(NF-1)*160 + 400]
+  float* win = span + (NF - 1) * st + ws;                         // [400]
+  float2* tw = reinterpret_cast<float2*>(win + ws);               // [400] W_400^e
+  float2* ex = tw + 400;                                          // [FPAIRS][20*EXP]
+  float* P = reinterpret_cast<float*>(ex + FPAIRS * 20 * EXP);    // [NF][PB]
+  const int u = blockIdx.y;
+  const long long a0 = p.offsets[u];
+  const int n = (int)(p.offsets[u + 1] - a0);
+  const int nframes = 1 + n / st;
+  const int f0 = blockIdx.x * NF;
+  if (f0 >= nframes) return;
+  const int nfr = min(NF, nframes - f0);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 400; i += NTP) { tw[i] = p.tw[i]; win[i] = p.window[i]; }
+  const float* au = p.audio + a0;
+  const int s0 = f0 * st - half;
+  const int need = (nfr - 1) * st + ws;
+  if (s0 >= 0 && s0 + need <= n) {
+    for (int i = tid; i < need; i += NTP) span[i] = __ldcs(au + s0 + i);
+  } else {
+    for (int i = tid; i < need; i += NTP) {
+      int idx = s0 + i;
+      if (idx < 0) idx = -idx;
+      if (idx >= n) idx = 2 * (n - 1) - idx;
+      span[i] = au[idx];
+    }
+  }
+  __syncthreads();
+  const int pr = tid / 20, c = tid - pr * 20;       // pair, column (n2 in pass 1, k1 in pass 2)
+  const bool has_a = 2 * pr < nfr, has_b = 2 * pr + 1 < nfr;
+  float2 x[20];
+  {
+    const float* sa = span + (2 * pr) * st + c;
+    const float* sb = sa + st;
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+      const float w = win[20 * n1 + c];
+      x[n1] = make_float2(has_a ? sa[20 * n1] * w : 0.f, has_b ? sb[20 * n1] * w : 0.f);
+    }
+  }
+  dft20(x);                                         // over n1 (stride 20): X[k1] for this n2
+  float2* exp_ = ex + pr * 20 * EXP;
+#pragma unroll
+  for (int k1 = 0; k1 < 20; ++k1) exp_[k1 * EXP + c] = k1 ? cmul(x[k1], tw[c * k1]) : x[k1];
+  __syncthreads();
+#pragma unroll
+  for (int n2 = 0; n2 < 20; ++n2) x[n2] = exp_[c * EXP + n2];
+  dft20(x);                                         // over n2: Z[k1 + 20 k2] = x[k2]
+  __syncthreads();
+#pragma unroll
+  for (int k2 = 0; k2 < 20; ++k2) exp_[c + 20 * k2] = x[k2];      // linear [400] inside the pair's region
+  __syncthreads();
+  for (int k = c; k <= 200; k += 20) {
+    const float2 zk = exp_[k == 400 ? 0 : k];
+    const float2 zn = exp_[k == 0 ? 0 : 400 - k];
+    const float ar = zk.x + zn.x, ai = zk.y - zn.y;              // Z[k] + conj Z[400-k] = 2 X_a[k]
+    const float br = zk.x - zn.x, bi = zk.y + zn.y;              // Z[k] - conj Z[400-k] = 2i X_b[k]
+    P[(2 * pr) * PB + k] = 0.25f * (ar * ar + ai * ai);
+    P[(2 * pr + 1) * PB + k] = 0.25f * (br * br + bi * bi);
+  }
+  __syncthreads();
+  float* outp = p.out + (size_t)(p.out_offsets[u] + f0) * p.n_mels;
+  for (int w = tid; w < nfr * p.n_mels; w += NTP) {
+    const int f = w / p.n_mels, i = w - f * p.n_mels;
+    const int b0 = __ldg(p.mel_start + i), cnt = __ldg(p.mel_cnt + i);
+    const float* wt = p.mel_w + __ldg(p.mel_off + i);
+    const float* prw = P + f * PB + b0;
+    float s = 0.f;
+    for (int b = 0; b < cnt; ++b) s = fmaf(__ldg(wt + b), prw[b], s);
+    __stcs(outp + w, logf(s + 2.220446049250313e-16f));
+  }
+}
 
 // ---- 16 kHz / 25 ms fast path: 400-sample frames, hop 160 ----------------------------------------------------
 // shared: A [FPB][200] float2 | B [FPB][200] float2 (also: audio span before the FFT, power spectrum after) |
@@ -329,7 +479,16 @@ int ssasr_fbank(const float* audio, const long long* offsets, int n_utt, int sam
   p.window = t.window; p.tw = t.tw; p.mel_start = t.mel_start; p.mel_cnt = t.mel_cnt; p.mel_off = t.mel_off; p.mel_w = t.mel_w;
   dim3 grid((max_frames + FPB - 1) / FPB, n_utt);
   ProfScope ps(F_FBANK, st);
-  if (t.ws == 400) {
+  static const bool use_stockham = getenv("SSASR_FBANK_STOCKHAM") != nullptr;   // previous smem-FFT kernel, kept for A/B timing
+  if (t.ws == 400 && !use_stockham) {
+    p.tw = t.tw400;
+    constexpr int NF = 2 * FPAIRS;
+    const size_t smem = (size_t)((NF - 1) * 160 + 400 + 400) * sizeof(float) + (size_t)(400 + FPAIRS * 20 * EXP) * sizeof(float2) +
+                        (size_t)NF * 202 * sizeof(float);
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank400p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 g2((max_frames + NF - 1) / NF, n_utt);
+    fbank400p_kernel<<<g2, NTP, smem, st>>>(p);
+  } else if (t.ws == 400) {
     const size_t smem = (size_t)(2 * FPB * 200 + 401) * sizeof(float2) + 400 * sizeof(float);
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fbank400_kernel<<<grid, NT, smem, st>>>(p);
