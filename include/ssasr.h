@@ -163,7 +163,9 @@ long long ssasr_launch_count(void);
 void ssasr_launch_count_reset(void);
 void ssasr_profile_enable(int enable);
 int ssasr_profile_read(double* ms /*[num_families]*/, long long* launches /*[num_families]*/);
-void ssasr_rec_tc_set_debug(long long* dev_buf /*[n_seq][8] clock64 stamps of CTA 0, or NULL*/);
+void ssasr_rec_tc_set_debug(long long* dev_buf /*[n_seq][12] clock64 stamps of CTA 0, or NULL*/);
+void ssasr_rec_cl_set_debug(long long* dev_buf /*[n_seq][12], cluster recurrent kernels (rec_cl.cu)*/);
+int ssasr_rec_cl_capacity(int S, int backward); /* co-resident (direction, tile) clusters of the cluster recurrence; 0 = unavailable */
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,8 @@ SIGNATURES = {
     'ssasr_profile_enable': (None, [_I]),
     'ssasr_profile_read': (_I, [_P, _P]),
     'ssasr_rec_tc_set_debug': (None, [_P]),
+    'ssasr_rec_cl_set_debug': (None, [_P]),
+    'ssasr_rec_cl_capacity': (_I, [_I, _I]),
 }
 
 

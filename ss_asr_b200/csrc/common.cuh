@@ -110,6 +110,13 @@ int rec_tc_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* wh
                   void* hb_lo, const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,
                const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar,
-               float* dbias /*[8S] pre-zeroed, or null*/);
+               float* dbias /*[8S] pre-zeroed, or null*/, int need_dg32 = 1 /*0: only the bf16 dG (dgb) is consumed*/);
+
+// cluster recurrent kernels (rec_cl.cu): multicast-TMA exchange inside one thread-block cluster per (direction, batch tile)
+int rec_cl_supported(int S, int n_batch, int backward);
+int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
+               int n_seq, int n_batch, long long rs_seq, long long rs_batch);
+int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
+               int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias);
 
 }  // namespace ssasr

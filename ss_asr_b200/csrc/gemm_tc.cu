@@ -537,6 +537,29 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long cols, long long
   return 0;
 }
 
+// Same 3-D view with a caller-chosen box width and swizzle (box_cols * 2 bytes must equal swizzle_bytes: 32 / 64 / 128):
+// the cluster recurrent kernels multicast a 16-column (32 B, SWIZZLE_32B) slice of h per producer CTA.
+int make_tmap_bf16_3d_ex(CUtensorMap* m, const void* ptr, long long cols, long long nA, long long strideA, long long nB,
+                         long long strideB, int box_cols, int boxA, int boxB, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  SSASR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  SSASR_REQUIRE(((uintptr_t)ptr & 15) == 0 && (strideA * 2) % 16 == 0 && (strideB * 2) % 16 == 0,
+                "TMA operand needs 16-byte aligned base and strides");
+  SSASR_REQUIRE(box_cols * 2 == swizzle_bytes && (swizzle_bytes == 32 || swizzle_bytes == 64 || swizzle_bytes == 128),
+                "make_tmap_bf16_3d_ex: box of %d columns does not match a %d-byte swizzle", box_cols, swizzle_bytes);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)nA, (cuuint64_t)nB};
+  cuuint64_t strides[2] = {(cuuint64_t)strideA * 2, (cuuint64_t)strideB * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)boxA, (cuuint32_t)boxB};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSASR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d ex) failed (%d) cols=%lld nA=%lld sA=%lld nB=%lld sB=%lld", (int)r,
+                cols, nA, strideA, nB, strideB);
+  return 0;
+}
+
 int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                  int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
   if (M <= 0 || N <= 0) return 0;

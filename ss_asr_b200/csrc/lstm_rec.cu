@@ -572,7 +572,9 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
   const bool tc_rec = whhT_bf && dgb_ws && rec_tc_supported(S);
   if (tc_rec) {
     SSASR_CHECK_CUDA(cudaMemsetAsync(dbias_p, 0, sizeof(float) * 8 * S, st));     // bias gradient is reduced inside the kernel
-    rc = rec_tc_bwd(st, act, whhT_bf, cbuf, dhout, dgb_ws, dcstate, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar, dbias_p);
+    const int direct = (xb_saved && hb_saved && Kp % 8 == 0) ? 1 : 0;     // weight gradients read only the bf16 dG
+    rc = rec_tc_bwd(st, act, whhT_bf, cbuf, dhout, dgb_ws, dcstate, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar, dbias_p,
+                    direct ? 0 : 1);
     if (rc) return rc;
   } else {
     SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));

@@ -1,0 +1,801 @@
+// Cluster recurrent BLSTM kernels (bf16 training path).  The CTAs that share one (direction, 64-row batch tile) form ONE
+// thread-block cluster (S/32 CTAs, 32 hidden units each) and exchange the per-step h / dG tile without any grid-wide
+// barrier and without a generic-proxy global store on the dependent chain:
+//
+//   epilogue warps   TMEM accumulator -> cell math in registers -> this CTA's slice of the exchange tile written to a
+//                    shared-memory IMAGE (already in the swizzled UMMA operand layout) -> arrive on `stage_ready`
+//   exchange thread  bulk-stores the image to a small L2-resident ring slot (cp.async.bulk.global.shared::cta), waits for
+//                    that bulk group, then reads the slot back with ONE multicast bulk copy
+//                    (cp.async.bulk.shared::cluster.global ... .multicast::cluster) that lands it in the operand buffer of
+//                    EVERY CTA of the cluster and completes transaction bytes on every CTA's mbarrier
+//   MMA thread       waits on its local mbarrier(s) until all S/32 slices have landed, issues the step's tcgen05.mma
+//
+// so the producer->consumer dependency is carried entirely by mbarrier transaction counts.  Measured on B200
+// (scripts/exch_bench.cu, 8-CTA cluster, 4 KB per CTA): bulk store + multicast read-back 1.0 k cycles per dependent step,
+// st.global + fence + multicast 1.6 k, DSMEM bulk copies 2.1 k, st.shared::cluster 5.3 k; the counter barrier + per-CTA TMA
+// reload of rec_tc.cu costs ~8 k.  16-CTA clusters (16 units per CTA) would halve the per-CTA work but only 7 of them
+// are co-resident on a B200 (one GPC is short), 8 are needed for 256 utterances x 2 directions.
+//
+// Everything that is NOT on the dependent chain (pre-activations / saved activations / c / dhout in, h / c / activations /
+// row-major bf16 copies out) moves with plain 128-bit global loads issued at the top of a step (their latency hides
+// behind the exchange + MMA) and plain stores issued after the `stage_ready` arrive.  The step loop has no block barrier.
+//
+// Row <-> thread mapping: M=64 accumulators occupy the lower 16 lanes of each TMEM sub-partition; lane l < 16 of an
+// epilogue warp reads row r's values and hands half of them to lane l + 16 by shuffle, so both half-warps work on the
+// same row (8 hidden units each).  Two epilogue groups of 4 warps own the two 16-unit halves of the CTA's 32 units.
+//
+// Operand layouts.  Forward: A = h(t-1) tile, [64 rows x S] bf16 as S/32 k-blocks of 64 x 64 B with the 64-byte swizzle
+// (one k-block = one producer's image), double-buffered; B = W_hh slice, 128 gate rows x S, 128-byte swizzle, resident.
+// Backward: A = dG(t+1) tile, [64 x 4S] bf16 as S/16 k-blocks of 64 x 128 B (a producer's image = two k-blocks = its
+// 32 units x 4 gates), single-buffered behind the `a_free` cluster barrier; B = W_hh^T slice, 32 unit rows x 4S.
+//
+// Reference semantics: nn.LSTM(bidirectional) packed (asr.py:410-418) and blstm_4 (asr.py:262); masking and row-stride
+// conventions, operand rounding (bf16), accumulation (fp32) and cell math (tanh.approx) as in rec_tc.cu.
+#include <limits.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ssasr {
+
+using namespace tc;
+
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+int make_tmap_bf16_3d_ex(CUtensorMap* m, const void* ptr, long long cols, long long nA, long long strideA, long long nB,
+                         long long strideB, int box_cols, int boxA, int boxB, int swizzle_bytes);
+
+namespace {
+
+constexpr int CL_UNITS = 32;       // hidden units per CTA (two 16-unit halves, one per epilogue warp group)
+constexpr int CL_THREADS = 320;    // warp 0: exchange, warp 1: MMA + TMEM alloc, warps 2-5 / 6-9: epilogue groups 0 / 1
+constexpr int CL_TM = 64;          // batch rows per tile
+constexpr int CL_RING = 4;         // global exchange ring depth (2 would do, see the hazard notes)
+constexpr int FW_IMG = CL_TM * 64;        // forward image: 64 rows x 32 bf16
+constexpr int BW_IMG = 2 * CL_TM * 128;   // backward image: two k-blocks of 64 rows x 64 bf16
+constexpr int BW_MAXNC = 8;
+constexpr int FW_WSTG = 4096 + 1024 + 1024;   // forward per-warp staging: gate tile + h tile + c tile
+
+struct RecClParams {
+  float* xp;                 // fwd: [rows,8S] pre-activations in / activations out.  bwd: activations in
+  float* hout;               // fwd out [rows,2S]
+  float* cbuf;               // fwd out / bwd in [rows,2S]
+  __nv_bfloat16* xb;         // fwd out: bf16 h [rows,2S].  bwd out: bf16 dG [rows,8S]
+  const float* dhout;        // bwd
+  float* dbias;              // bwd: [8S] pre-zeroed, atomically accumulated; may be null
+  uint8_t* ring;             // [CL_RING][n_cta][image bytes] exchange slots
+  const int* lens;
+  int S, n_seq, n_batch;
+  long long rs_seq, rs_batch;
+  long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0)
+};
+
+#define CL_STAMP(idx)                                                                                            \
+  do {                                                                                                           \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 12 + (idx)] = clock64(); \
+  } while (0)
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_apx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_apx(float x) { return fmaf(tanh_apx(0.5f * x), 0.5f, 0.5f); }
+
+// time-bounded mbarrier wait (a protocol bug must trap, not hang the GPU): ~2 s at 2 GHz
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster_t(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// arrive on the mbarrier at the same CTA-relative offset in cluster CTA `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// image (shared) -> ring slot (global), then wait until the bulk store has completed
+__device__ __forceinline__ void bulk_store_wait(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// ring slot (global) -> the same CTA-relative smem offset in every CTA of `mask`; completes its bytes on the mbarrier at
+// the same offset in each of them
+__device__ __forceinline__ void bulk_load_mc(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+// swizzled shared-memory tile -> global tensor (rows outside the tensor are clipped); joins the thread's bulk group
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* ssrc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(ssrc)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// K-major operand k-block of 32 bf16 (64-byte rows, 64-byte swizzle), 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;            // layout type SWIZZLE_64B
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CL_THREADS, 1)
+rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
+  constexpr int TM = CL_TM;
+  constexpr int W_BLK = 128 * 128;       // 128 gate rows x 64 bf16
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.S, KB = S / 64, NC = S / 32;                           // NC = cluster size = producers per tile
+  uint8_t* Wsm = smem;                                                   // [KB] blocks of W_BLK
+  uint8_t* Asm = Wsm + KB * W_BLK;                                       // [2][NC] k-blocks of FW_IMG
+  uint8_t* img = Asm + 2 * NC * FW_IMG;                                  // this CTA's outgoing image
+  uint8_t* stg = img + FW_IMG;                                           // [8 epilogue warps] staging tiles of FW_WSTG bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 8 * FW_WSTG);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;           // [2]
+  uint64_t* mma_done = bars + 3;
+  uint64_t* tmem_free = bars + 4;
+  uint64_t* stage_ready = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int slice = blockIdx.x, dir = blockIdx.y, bt = blockIdx.z;      // cluster = the NC CTAs along x
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile_bytes = (uint32_t)TM * S * 2;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmW);
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(a_full + 1, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(tmem_free, 256);
+    mbar_init(stage_ready, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, KB * W_BLK);
+    for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * 4 * S + slice * 128);
+    mbar_expect_tx(a_full, tile_bytes);          // h(0) and h(1); re-armed by the MMA thread after each wait
+    mbar_expect_tx(a_full + 1, tile_bytes);
+  }
+  cluster_sync_all();                            // every CTA's barriers exist before any multicast can signal them
+
+  if (warp == 0) {
+    // ---------------- exchange thread ----------------
+    if (elect_one()) {
+      const uint16_t cmask = (uint16_t)((1u << NC) - 1u);
+      const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      for (int s = 0; s + 1 < p.n_seq; ++s) {
+        uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * FW_IMG;
+        mbar_wait_t(stage_ready, s & 1);                           // all 256 epilogue threads have written the image
+        CL_STAMP(8);
+        bulk_store_wait(slot, img, FW_IMG);
+        CL_STAMP(9);
+        bulk_load_mc(Asm + ((s & 1) * NC + slice) * FW_IMG, slot, FW_IMG, a_full + (s & 1), cmask);
+        CL_STAMP(6);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA thread ----------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TM, 128);
+      const int nk = S / 16;
+      for (int s = 1; s < p.n_seq; ++s) {
+        const int b = (s - 1) & 1;
+        if (s == 1) mbar_wait_t(w_full, 0);
+        mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // all NC slices of h(s-1) have landed
+        if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
+        if (s > 1) mbar_wait_t(tmem_free, (s - 2) & 1);            // epilogue has drained the accumulator
+        CL_STAMP(1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(Asm + b * NC * FW_IMG), w0 = smem_u32(Wsm);
+#pragma unroll 4
+        for (int kk = 0; kk < nk; ++kk) {
+          const uint64_t da = umma_desc_k64(a0 + (kk >> 1) * FW_IMG) + (uint64_t)((kk & 1) * 2);
+          const uint64_t db = umma_desc_k128(w0 + (kk >> 2) * W_BLK) + (uint64_t)((kk & 3) * 2);
+          mma_bf16_ss(tmem, da, db, idesc, kk != 0);
+        }
+        mma_commit(mma_done);
+        CL_STAMP(2);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: lane = (row r, 8 of the group's 16 units) ----------------
+    const int q = warp & 3;                        // TMEM sub-partition
+    const int hh = warp >= 6 ? 1 : 0;              // epilogue group = 16-unit half of the CTA's 32 units
+    const int uh = lane >> 4;                      // 8-unit half inside the group
+    const int l16 = lane & 15;
+    const int r = q * 16 + l16;
+    const int n = bt * TM + r;
+    const bool in_range = n < p.n_batch;
+    const int len = (in_range && p.lens) ? p.lens[n] : INT_MAX;
+    const int wcol = slice * CL_UNITS + hh * 16;                      // first of this WARP's 16 units inside the direction
+    const size_t hoff_w = (size_t)dir * S + wcol;
+    const size_t goff_w = (size_t)dir * 4 * S + (size_t)wcol * 4;
+    // image: row r, 16-byte chunk c = hh*2 + uh of the 64-byte row, 64-byte swizzle
+    uint4* img_dst = reinterpret_cast<uint4*>(img + r * 64 + (((hh * 2 + uh) ^ ((r >> 1) & 3)) << 4));
+    // Per-warp staging: the warp's 16 rows x 64 gate columns (fp32, 256 B per row) and 16 rows x 16 units of h / c.
+    // Global accesses are coalesced (half-warp = one contiguous 256-byte / 64-byte row segment), the lane <-> (row, 8 units)
+    // re-distribution happens through these tiles; 16-byte chunks are XOR-swizzled so both access patterns are
+    // bank-conflict free.  Only __syncwarp is needed: a warp only ever touches its own tiles.
+    uint8_t* wst = stg + (warp - 2) * FW_WSTG;
+    float* gs = reinterpret_cast<float*>(wst);                         // [16][64]  chunk c of row l at (c ^ l)
+    float* hs = reinterpret_cast<float*>(wst + 4096);                  // [16][16]  chunk c of row l at (c ^ ((l >> 1) & 3))
+    float* cs = reinterpret_cast<float*>(wst + 5120);                  // [16][16]
+    float creg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) creg[j] = 0.f;
+
+    // coalesced async copy of the warp's pre-activation tile of time t_ into gs (instruction i: rows 2i, 2i+1)
+    auto prefetch_g = [&](int t_) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = 2 * i + uh, nn = bt * TM + q * 16 + rl;
+        if (nn < p.n_batch)
+          cp_async16(gs + rl * 64 + ((l16 ^ rl) << 2),
+                     p.xp + ((size_t)t_ * p.rs_seq + (size_t)nn * p.rs_batch) * 8 * S + goff_w + l16 * 4);
+      }
+      cp_async_commit();
+    };
+    prefetch_g(dir == 0 ? 0 : p.n_seq - 1);
+
+    for (int s = 0; s < p.n_seq; ++s) {
+      const int t = dir == 0 ? s : p.n_seq - 1 - s;
+      const bool valid = in_range && t < len;
+      float4 g[8];                                 // pre-activations of this lane's 8 units (i,f,g,o each)
+      cp_async_wait_all();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        g[j] = valid ? *reinterpret_cast<const float4*>(gs + l16 * 64 + (((uh * 8 + j) ^ l16) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s > 0) {
+        uint32_t v[32];
+        mbar_wait_t(mma_done, (s - 1) & 1);
+        if (threadIdx.x == 64) CL_STAMP(3);
+        tc_fence_after();
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
+        // columns 32..63 (units 8..15 of the row) belong to the upper half-warp: fetched by the row's lane, handed over
+        tmem_ld16(ta + 32, v);
+        tmem_ld16(ta + 48, v + 16);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float u0 = __shfl_sync(0xffffffffu, __uint_as_float(v[j * 4 + 0]), l16);
+          const float u1 = __shfl_sync(0xffffffffu, __uint_as_float(v[j * 4 + 1]), l16);
+          const float u2 = __shfl_sync(0xffffffffu, __uint_as_float(v[j * 4 + 2]), l16);
+          const float u3 = __shfl_sync(0xffffffffu, __uint_as_float(v[j * 4 + 3]), l16);
+          if (uh) { g[j].x += u0; g[j].y += u1; g[j].z += u2; g[j].w += u3; }
+        }
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + 16, v + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tmem_free);
+        if (!uh) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            g[j].x += __uint_as_float(v[j * 4 + 0]); g[j].y += __uint_as_float(v[j * 4 + 1]);
+            g[j].z += __uint_as_float(v[j * 4 + 2]); g[j].w += __uint_as_float(v[j * 4 + 3]);
+          }
+        }
+      }
+      float hv[8], cv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[j] = 0.f; cv[j] = 0.f;
+        if (valid) {
+          a.x = sigmoid_apx(g[j].x); a.y = sigmoid_apx(g[j].y); a.z = tanh_apx(g[j].z); a.w = sigmoid_apx(g[j].w);
+          cv[j] = fmaf(a.y, creg[j], a.x * a.z);
+          hv[j] = a.w * tanh_apx(cv[j]);
+        }
+        creg[j] = cv[j];
+        g[j] = a;
+      }
+      uint4 hb;
+      {
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(hv[0], hv[1]), b1 = __floats2bfloat162_rn(hv[2], hv[3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(hv[4], hv[5]), b3 = __floats2bfloat162_rn(hv[6], hv[7]);
+        hb = make_uint4(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1), *reinterpret_cast<uint32_t*>(&b2),
+                        *reinterpret_cast<uint32_t*>(&b3));
+      }
+      if (s + 1 < p.n_seq) {
+        *img_dst = hb;
+        fence_proxy_async();                       // generic-proxy smem write -> visible to the bulk (async proxy) store
+        mbar_arrive(stage_ready);
+      }
+      if (threadIdx.x == 64) CL_STAMP(5);
+      // ---- off the dependent chain: saved tensors, re-distributed through the warp's staging tiles ----
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(gs + l16 * 64 + (((uh * 8 + j) ^ l16) << 2)) = g[j];
+      {
+        const int sw = (l16 >> 1) & 3;
+        *reinterpret_cast<float4*>(hs + l16 * 16 + (((uh * 2 + 0) ^ sw) << 2)) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<float4*>(hs + l16 * 16 + (((uh * 2 + 1) ^ sw) << 2)) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        *reinterpret_cast<float4*>(cs + l16 * 16 + (((uh * 2 + 0) ^ sw) << 2)) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        *reinterpret_cast<float4*>(cs + l16 * 16 + (((uh * 2 + 1) ^ sw) << 2)) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+      }
+      __syncwarp();
+      {
+        if (in_range) *reinterpret_cast<uint4*>(p.xb + ((size_t)t * p.rs_seq + (size_t)n * p.rs_batch) * 2 * S + hoff_w + uh * 8) = hb;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {            // h / c: 8 rows x 64 contiguous bytes per instruction
+          const int rl = 8 * i + (lane >> 2), c = lane & 3, nn = bt * TM + q * 16 + rl;
+          if (nn < p.n_batch) {
+            const size_t o = ((size_t)t * p.rs_seq + (size_t)nn * p.rs_batch) * 2 * S + hoff_w + c * 4;
+            const int so = rl * 16 + ((c ^ ((rl >> 1) & 3)) << 2);
+            *reinterpret_cast<float4*>(p.hout + o) = *reinterpret_cast<const float4*>(hs + so);
+            *reinterpret_cast<float4*>(p.cbuf + o) = *reinterpret_cast<const float4*>(cs + so);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {            // activations: 2 rows x 256 contiguous bytes per instruction
+          const int rl = 2 * i + uh, nn = bt * TM + q * 16 + rl;
+          if (nn < p.n_batch)
+            __stcs(reinterpret_cast<float4*>(p.xp + ((size_t)t * p.rs_seq + (size_t)nn * p.rs_batch) * 8 * S + goff_w + l16 * 4),
+                   *reinterpret_cast<const float4*>(gs + rl * 64 + ((l16 ^ rl) << 2)));
+        }
+      }
+      __syncwarp();                                // staging tiles drained
+      if (s + 1 < p.n_seq) prefetch_g(dir == 0 ? s + 1 : p.n_seq - 2 - s);
+      if (threadIdx.x == 64) CL_STAMP(7);
+    }
+  }
+  cp_async_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem);
+  cluster_sync_all();                            // no CTA leaves while a peer could still address its shared memory
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CL_THREADS, 1)
+rec_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, RecClParams p) {
+  constexpr int TM = CL_TM;
+  constexpr int A_BLK = TM * 128;        // one k-block: TM rows x 64 bf16 (a producer contributes two)
+  constexpr int W_BLK = 32 * 128;        // 32 unit rows x 64 bf16
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.S, NC = S / 32, NKB = S / 16;   // NKB = 4S/64 k-blocks of the 4S-long reduction
+  const int slice_ = blockIdx.x;
+  uint8_t* Asm = smem;                    // [NKB] k-blocks of A_BLK
+  uint8_t* Wsm = Asm + NKB * A_BLK;       // [NKB] blocks of W_BLK
+  uint8_t* img = Asm + slice_ * BW_IMG;   // this CTA's outgoing image = its OWN two k-blocks of the A tile: free once the
+                                          // local MMAs are done; the multicast later re-delivers the same bytes to it
+  uint8_t* stg = Wsm + NKB * W_BLK;       // [8 epilogue warps] activation staging tiles of 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 8 * 4096);
+  uint64_t* w_full = bars;
+  uint64_t* mma_done = bars + 1;
+  uint64_t* tmem_free = bars + 2;
+  uint64_t* a_free = bars + 3;            // NC remote arrivals per step: every CTA's MMAs have consumed the A tile
+  uint64_t* stage_ready = bars + 4;
+  uint64_t* img_free = bars + 5;          // the row-major copy of the image has been read out: the image may be rewritten
+  uint64_t* full = bars + 6;              // [NC] one per producer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + BW_MAXNC);
+
+  const int slice = blockIdx.x, dir = blockIdx.y, bt = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmG);
+    mbar_init(w_full, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(tmem_free, 256);
+    mbar_init(a_free, NC);
+    mbar_init(stage_ready, 256);
+    mbar_init(img_free, 1);
+    for (int i = 0; i < NC; ++i) mbar_init(full + i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<32>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, NKB * W_BLK);
+    for (int kb = 0; kb < NKB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * S + slice * CL_UNITS);
+    if (p.n_seq > 1)
+      for (int i = 0; i < NC; ++i) mbar_expect_tx(full + i, BW_IMG);
+  }
+  cluster_sync_all();
+
+  float bsum[32];            // epilogue lanes: running column sums of dG (bias gradient), reduced across rows at the end
+#pragma unroll
+  for (int j = 0; j < 32; ++j) bsum[j] = 0.f;
+
+  if (warp == 0) {
+    // ---------------- exchange thread ----------------
+    if (elect_one()) {
+      const uint16_t cmask = (uint16_t)((1u << NC) - 1u);
+      const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      const int seq_inner = p.rs_seq < p.rs_batch ? 1 : 0;
+      for (int s = 0; s < p.n_seq; ++s) {
+        const int t = dir == 0 ? p.n_seq - 1 - s : s;
+        uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * BW_IMG;
+        mbar_wait_t(stage_ready, s & 1);
+        CL_STAMP(8);
+        if (s + 1 < p.n_seq) {
+          bulk_store_wait(slot, img, BW_IMG);
+          CL_STAMP(9);
+          if (s > 0) mbar_wait_cluster_t(a_free, (s - 1) & 1);   // every CTA of the cluster has finished reading dG(t_next)
+          bulk_load_mc(Asm + slice * BW_IMG, slot, BW_IMG, full + slice, cmask);
+          CL_STAMP(6);
+        }
+        // row-major bf16 dG for the batched weight / input gradient GEMMs: the image IS the swizzled TMA box
+        {
+          const int c1 = seq_inner ? t : bt * TM, c2 = seq_inner ? bt * TM : t;
+          tma_store_3d(&tmG, img, dir * 4 * S + slice * 128, c1, c2);
+          tma_store_3d(&tmG, img + A_BLK, dir * 4 * S + slice * 128 + 64, c1, c2);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        mbar_arrive(img_free);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA thread ----------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TM, 32);
+      const uint32_t a0 = smem_u32(Asm), w0 = smem_u32(Wsm);
+      for (int s = 1; s < p.n_seq; ++s) {
+        if (s == 1) mbar_wait_t(w_full, 0);
+        if (s > 1) mbar_wait_t(tmem_free, (s - 2) & 1);
+        for (int pc = 0; pc < NC; ++pc) {
+          mbar_wait_t(full + pc, (s - 1) & 1);                          // producer pc's two k-blocks of dG(t_next) have landed
+          if (s + 1 < p.n_seq) mbar_expect_tx(full + pc, BW_IMG);       // re-arm for the next step
+          if (pc == 0) CL_STAMP(1);
+          tc_fence_after();
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int kb = pc * 2 + h2;
+            const uint64_t da = umma_desc_k128(a0 + kb * A_BLK), db = umma_desc_k128(w0 + kb * W_BLK);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_bf16_ss(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+        }
+        mma_commit(mma_done);
+        CL_STAMP(2);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: lane = (row r, 8 of the group's 16 units) ----------------
+    const int q = warp & 3;
+    const int hh = warp >= 6 ? 1 : 0;
+    const int uh = lane >> 4;
+    const int r = q * 16 + (lane & 15);
+    const int n = bt * TM + r;
+    const bool in_range = n < p.n_batch;
+    const int len = (in_range && p.lens) ? p.lens[n] : INT_MAX;
+    const int l16 = lane & 15;
+    const int ucol = slice * CL_UNITS + hh * 16 + uh * 8;
+    const size_t hoff = (size_t)dir * S + ucol;
+    const size_t goff_w = (size_t)dir * 4 * S + (size_t)(slice * CL_UNITS + hh * 16) * 4;
+    // image: k-block hh, row r, 16-byte chunks uh*4 .. uh*4+3 of the 128-byte row, 128-byte swizzle
+    uint8_t* img_row = img + hh * A_BLK + r * 128;
+    // per-warp staging of the warp's 16 rows x 64 saved activations (coalesced cp.async in, row-per-lane reads out;
+    // chunk c of row l sits at chunk c ^ l: both patterns are bank-conflict free)
+    float* gs = reinterpret_cast<float*>(stg + (warp - 2) * 4096);
+    auto prefetch_a = [&](int t_) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = 2 * i + uh, nn = bt * TM + q * 16 + rl;
+        if (nn < p.n_batch)
+          cp_async16(gs + rl * 64 + ((l16 ^ rl) << 2),
+                     p.xp + ((size_t)t_ * p.rs_seq + (size_t)nn * p.rs_batch) * 8 * S + goff_w + l16 * 4);
+      }
+      cp_async_commit();
+    };
+    prefetch_a(dir == 0 ? p.n_seq - 1 : 0);
+    float dcreg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dcreg[j] = 0.f;
+
+    for (int s = 0; s < p.n_seq; ++s) {
+      const int t = dir == 0 ? p.n_seq - 1 - s : s;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      const bool has_prev = dir == 0 ? (t > 0) : (t < p.n_seq - 1);
+      const bool valid = in_range && t < len;
+      const bool pv = valid && has_prev && tp < len;
+      const size_t row = (size_t)t * p.rs_seq + (size_t)(in_range ? n : 0) * p.rs_batch;
+      // everything of this step that does not depend on the recurrence, to registers
+      float4 a[8], dh4[2], c4r[2], cp4[2];
+      {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        cp_async_wait_all();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          a[j] = valid ? *reinterpret_cast<const float4*>(gs + l16 * 64 + (((uh * 8 + j) ^ l16) << 2)) : z4;
+        __syncwarp();
+        if (s + 1 < p.n_seq) prefetch_a(dir == 0 ? t - 1 : t + 1);     // a whole step of lead time
+        const float4* dp = reinterpret_cast<const float4*>(p.dhout + row * 2 * S + hoff);
+        const float4* cp = reinterpret_cast<const float4*>(p.cbuf + row * 2 * S + hoff);
+        const float4* pp = reinterpret_cast<const float4*>(
+            p.cbuf + ((size_t)(pv ? tp : t) * p.rs_seq + (size_t)(in_range ? n : 0) * p.rs_batch) * 2 * S + hoff);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dh4[j] = valid ? __ldcs(dp + j) : z4;
+          c4r[j] = valid ? __ldg(cp + j) : z4;
+          cp4[j] = pv ? __ldg(pp + j) : z4;
+        }
+      }
+      float dhm[8];                             // recurrent part of dh for this lane's 8 units
+      if (s > 0) {
+        uint32_t v[16];
+        mbar_wait_t(mma_done, (s - 1) & 1);
+        if (warp == 2 && lane < NC) mbar_arrive_remote(a_free, lane);   // this CTA no longer reads its A tile
+        if (threadIdx.x == 64) CL_STAMP(3);
+        tc_fence_after();
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 16), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tmem_free);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float up = __shfl_sync(0xffffffffu, __uint_as_float(v[8 + k]), lane & 15);
+          dhm[k] = uh ? up : __uint_as_float(v[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dhm[k] = 0.f;
+      }
+      uint4 gq[4];                              // this lane's 8 units x 4 gates of dG, bf16
+#pragma unroll
+      for (int qd = 0; qd < 2; ++qd) {
+        const float dhv[4] = {dh4[qd].x, dh4[qd].y, dh4[qd].z, dh4[qd].w};
+        const float cv[4] = {c4r[qd].x, c4r[qd].y, c4r[qd].z, c4r[qd].w};
+        const float cpv[4] = {cp4[qd].x, cp4[qd].y, cp4[qd].z, cp4[qd].w};
+        uint32_t gb[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = qd * 4 + u;
+          float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+          float dco = 0.f;
+          if (valid) {
+            const float4 aa = a[j];
+            const float dh = dhv[u] + dhm[j];
+            const float tc_ = tanh_apx(cv[u]);
+            const float dc = fmaf(dh * aa.w, 1.f - tc_ * tc_, dcreg[j]);
+            dg.w = dh * tc_ * aa.w * (1.f - aa.w);
+            dg.x = dc * aa.z * aa.x * (1.f - aa.x);
+            dg.z = dc * aa.x * (1.f - aa.z * aa.z);
+            dg.y = pv ? dc * cpv[u] * aa.y * (1.f - aa.y) : 0.f;
+            dco = dc * aa.y;
+          }
+          dcreg[j] = dco;
+          bsum[j * 4 + 0] += dg.x; bsum[j * 4 + 1] += dg.y; bsum[j * 4 + 2] += dg.z; bsum[j * 4 + 3] += dg.w;
+          __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+          gb[u * 2 + 0] = *reinterpret_cast<uint32_t*>(&b01);
+          gb[u * 2 + 1] = *reinterpret_cast<uint32_t*>(&b23);
+        }
+        gq[qd * 2 + 0] = make_uint4(gb[0], gb[1], gb[2], gb[3]);
+        gq[qd * 2 + 1] = make_uint4(gb[4], gb[5], gb[6], gb[7]);
+      }
+      if (s > 0) mbar_wait_t(img_free, (s - 1) & 1);     // the previous image has been read out (long done in practice)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(img_row + (((uh * 4 + c) ^ (r & 7)) << 4)) = gq[c];
+      fence_proxy_async();
+      mbar_arrive(stage_ready);
+      if (threadIdx.x == 64) CL_STAMP(5);
+    }
+  }
+  cp_async_wait_all();
+  if (p.dbias) {                      // bias gradient: reduce the per-lane partial sums across the tile rows
+    __syncthreads();                  // all MMAs have been consumed: the A tile is free to serve as scratch
+    float* scr = reinterpret_cast<float*>(Asm);     // [TM][128]
+    if (warp >= 2) {
+      const int q = warp & 3, hh = warp >= 6 ? 1 : 0, uh = lane >> 4, r = q * 16 + (lane & 15);
+      float* dst = scr + r * 128 + hh * 64 + uh * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(dst + ((j ^ (r & 7)) << 2)) = make_float4(bsum[j * 4], bsum[j * 4 + 1], bsum[j * 4 + 2], bsum[j * 4 + 3]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int col = threadIdx.x, blk = col >> 5, j = (col >> 2) & 7, e = col & 3;
+      float acc = 0.f;
+      for (int rr = 0; rr < TM; ++rr) acc += scr[rr * 128 + blk * 32 + ((j ^ (rr & 7)) << 2) + e];
+      atomicAdd(p.dbias + (size_t)dir * 4 * S + (size_t)slice * 128 + col, acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<32>(tmem);
+  cluster_sync_all();
+}
+
+static long long* g_cl_dbg = nullptr;
+
+template <typename Kern, typename... Args>
+static int cluster_launch(Kern kern, dim3 grid, int cluster_x, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  return 0;
+}
+
+static size_t fwd_smem(int S) {
+  return (size_t)(S / 64) * 16384 + (size_t)2 * CL_TM * S * 2 + FW_IMG + 8 * FW_WSTG + 7 * 8 + 16 + 1024;
+}
+static size_t bwd_smem(int S) {
+  return (size_t)CL_TM * 4 * S * 2 + (size_t)(S / 16) * 4096 + 8 * 4096 + (6 + BW_MAXNC) * 8 + 16 + 1024;
+}
+
+template <typename Kern>
+static int prepare(Kern kern, int cluster_x, size_t smem, size_t smem_max, int* max_clusters) {
+  // the attribute is per kernel, not per launch: always allow the largest supported state size
+  SSASR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cluster_x, 2, 1);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nc = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); nc = 0; }
+  *max_clusters = nc;
+  return 0;
+}
+
+// co-resident cluster capacity per state size, queried once (index = S / 64): [0] forward, [1] backward
+static int g_cap[2][5] = {{-1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1}};
+
+static bool cl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SSASR_REC_CLUSTER");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// exchange ring: internal, L2-resident scratch (a few MB), one per stream that ever launched a cluster recurrence
+constexpr size_t RING_BYTES = (size_t)CL_RING * 148 * BW_IMG;
+struct RingSlot { cudaStream_t st; int dev; uint8_t* buf; };
+static RingSlot g_rings[16];
+static int g_nrings = 0;
+
+static uint8_t* ring_for(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < g_nrings; ++i)
+    if (g_rings[i].st == st && g_rings[i].dev == dev) return g_rings[i].buf;
+  if (g_nrings == 16) return nullptr;
+  uint8_t* b = nullptr;
+  if (cudaMalloc(&b, RING_BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  g_rings[g_nrings++] = {st, dev, b};
+  return b;
+}
+
+}  // namespace
+
+// 1 when the cluster kernels can run this layer with every (direction, 64-row tile) cluster co-resident
+int rec_cl_supported(int S, int n_batch, int backward) {
+  if (!cl_enabled()) return 0;
+  if (!(S == 64 || S == 128 || S == 256)) return 0;
+  const int idx = S / 64, w = backward ? 1 : 0;
+  if (g_cap[w][idx] < 0) {
+    int nc = 0;
+    const int rc = backward ? prepare(rec_cl_bwd_kernel, S / CL_UNITS, bwd_smem(S), bwd_smem(256), &nc)
+                            : prepare(rec_cl_fwd_kernel, S / CL_UNITS, fwd_smem(S), fwd_smem(256), &nc);
+    g_cap[w][idx] = rc ? 0 : nc;
+  }
+  const int tiles = (n_batch + CL_TM - 1) / CL_TM;
+  return (2 * tiles <= g_cap[w][idx] && 2 * tiles * (S / CL_UNITS) <= 148) ? 1 : 0;
+}
+
+// co-resident cluster capacity (0 = cluster kernels unavailable for this state size)
+int rec_cl_capacity(int S, int backward) {
+  if (!(S == 64 || S == 128 || S == 256)) return 0;
+  rec_cl_supported(S, 1, backward);
+  return g_cap[backward ? 1 : 0][S / 64];
+}
+
+int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
+               int n_seq, int n_batch, long long rs_seq, long long rs_batch) {
+  RecClParams p = {};
+  p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.lens = lens;
+  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
+  p.dbg = g_cl_dbg;
+  p.ring = ring_for(st);
+  SSASR_REQUIRE(p.ring != nullptr, "rec_cl_fwd: cannot allocate the exchange ring");
+  CUtensorMap tmW;
+  int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 128);
+  if (rc) return rc;
+  dim3 grid(S / CL_UNITS, 2, (n_batch + CL_TM - 1) / CL_TM);
+  ProfScope ps(F_REC_TC_FWD, st);
+  return cluster_launch(rec_cl_fwd_kernel, grid, S / CL_UNITS, fwd_smem(S), st, tmW, p);
+}
+
+int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
+               int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias) {
+  RecClParams p = {};
+  p.xp = act; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dbias = dbias; p.lens = lens;
+  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
+  p.dbg = g_cl_dbg;
+  p.ring = ring_for(st);
+  SSASR_REQUIRE(p.ring != nullptr, "rec_cl_bwd: cannot allocate the exchange ring");
+  CUtensorMap tmW, tmG;
+  int rc = make_tmap_bf16(&tmW, whhT_bf, 2 * S, 4 * S, 4 * S, 32);
+  if (rc) return rc;
+  rc = rs_seq < rs_batch ? make_tmap_bf16_3d_ex(&tmG, dgb, 8 * S, n_seq, rs_seq * 8 * S, n_batch, rs_batch * 8 * S, 64, 1, CL_TM, 128)
+                         : make_tmap_bf16_3d_ex(&tmG, dgb, 8 * S, n_batch, rs_batch * 8 * S, n_seq, rs_seq * 8 * S, 64, CL_TM, 1, 128);
+  if (rc) return rc;
+  dim3 grid(S / CL_UNITS, 2, (n_batch + CL_TM - 1) / CL_TM);
+  ProfScope ps(F_REC_TC_BWD, st);
+  return cluster_launch(rec_cl_bwd_kernel, grid, S / CL_UNITS, bwd_smem(S), st, tmW, tmG, p);
+}
+
+}  // namespace ssasr
+
+extern "C" {
+// debug: device buffer [n_seq][12] of clock64 stamps written by CTA (0,0,0) of the next cluster recurrent launches
+void ssasr_rec_cl_set_debug(long long* dev_buf) { ssasr::g_cl_dbg = dev_buf; }
+// how many (direction, 64-row tile) clusters of the cluster recurrent kernels can be co-resident (0: not available)
+int ssasr_rec_cl_capacity(int S, int backward) { return ssasr::rec_cl_capacity(S, backward); }
+}
