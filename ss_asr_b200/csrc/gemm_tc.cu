@@ -26,8 +26,67 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
 };
 
+
+// Coalesced epilogue of one 32-row x 32-column fp32 chunk.  tcgen05.ld hands every lane one ROW of the accumulator; written
+// straight to global that is 32 different 128-byte lines per store instruction (LSU-bound: a 128 x 128 tile took as long as
+// its K = 1024 main loop).  The chunk is therefore transposed through a per-warp 4 KB shared-memory tile (16-byte chunk c of
+// row r at chunk c ^ (r & 7): conflict-free both ways) so that every global instruction covers 4 rows x 128 contiguous bytes.
+template <bool ATOMIC>
+__device__ __forceinline__ void epi_chunk(float* stage, const uint32_t* v, float* __restrict__ C, int ldc, int row0, int col0,
+                                          int M, int N, const float* __restrict__ bias, int accumulate, int act_tanh) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(stage + lane * 32 + ((c ^ (lane & 7)) << 2)) =
+        make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
+  __syncwarp();
+  const int rr = lane >> 3, cc = lane & 7;
+  const int n = col0 + cc * 4;
+  const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && n + 3 < N;
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) {
+    if (n < N) bb.x = __ldg(bias + n);
+    if (n + 1 < N) bb.y = __ldg(bias + n + 1);
+    if (n + 2 < N) bb.z = __ldg(bias + n + 2);
+    if (n + 3 < N) bb.w = __ldg(bias + n + 3);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + rr, row = row0 + r;
+    float4 o = *reinterpret_cast<const float4*>(stage + r * 32 + ((cc ^ (r & 7)) << 2));
+    if (row >= M) continue;
+    float* dst = C + (size_t)row * ldc + n;
+    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+    if (vec_ok) {
+      if (ATOMIC) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+      } else {
+        if (accumulate) { const float4 q = *reinterpret_cast<const float4*>(dst); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+        if (act_tanh) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+        *reinterpret_cast<float4*>(dst) = o;
+      }
+    } else {
+      const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (n + e < N) {
+          float x = ov[e];
+          if (ATOMIC) {
+            atomicAdd(dst + e, x);
+          } else {
+            if (accumulate) x += dst[e];
+            if (act_tanh) x = tanhf(x);
+            dst[e] = x;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, (BN * 64 + 8192) * STAGES * 2 <= 100 * 1024 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                int ldc, const float* __restrict__ bias, int M, int N, int K, int a_koff, int b_koff, int accumulate, int act_tanh) {
   using L = GemmSmem<BN, STAGES>;
@@ -39,7 +98,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * BN;
+  // blockIdx.x (fastest in launch order) walks the N tiles of one 128-row block of A: the block is read from HBM once and
+  // serves all its column tiles out of L2, B (the weights) stays L2-resident throughout
+  const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * BN;
   const int num_k = (K + GT_BK - 1) / GT_BK;
 
   if (warp == 0 && elect_one()) {
@@ -90,44 +151,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;                 // TMEM lanes [32*ew, 32*ew+32)
-    const int row = m0 + ew * 32 + (threadIdx.x & 31);
-    mbar_wait(tmem_full, 0);
+    mbar_wait(tmem_full, 0);                 // every MMA has completed: the pipeline stages are free, stage 0 becomes staging
     tc_fence_after();
-    float* crow = C + (size_t)row * ldc + n0;
+    float* stage = reinterpret_cast<float*>(smem) + ew * 1024;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (row < M) {
-        if (n0 + c0 + 32 <= N && (ldc & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
-            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-            if (bias) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + c0 + j);
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            }
-            float4* dst = reinterpret_cast<float4*>(crow + c0 + j);
-            if (accumulate) { const float4 p = *dst; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-            if (act_tanh) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
-            *dst = o;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < N) {
-              float o = __uint_as_float(v[j]) + (bias ? bias[n] : 0.f);
-              if (accumulate) o += crow[c0 + j];
-              if (act_tanh) o = tanhf(o);
-              crow[c0 + j] = o;
-            }
-          }
-        }
-      }
+      epi_chunk<false>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, bias, accumulate, act_tanh);
     }
   }
   tc_fence_before();
@@ -202,27 +235,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mma_commit(tmem_full);
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
-    const int row = m0 + ew * 32 + (threadIdx.x & 31);
-    mbar_wait(tmem_full, 0);
+    const int ew = warp - 4;                 // TMEM lanes [32*ew, 32*ew+32)
+    mbar_wait(tmem_full, 0);                 // every MMA has completed: the pipeline stages are free, stage 0 becomes staging
     tc_fence_after();
-    float* crow = C + (size_t)row * ldc + n0;
+    float* stage = reinterpret_cast<float*>(smem) + ew * 1024;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (row < M) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < N) {
-            float o = __uint_as_float(v[j]) + (bias ? bias[n] : 0.f);
-            if (act_tanh) o = tanhf(o);
-            crow[c0 + j] = o;
-          }
-        }
-      }
+      epi_chunk<false>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, bias, 0, act_tanh);
     }
   }
   tc_fence_before();
@@ -251,7 +274,7 @@ __global__ void split_hi_lo_kernel(const float* __restrict__ x, float* __restric
 // transposed copies are needed.  a_koff / b_koff shift the reduction ROW window of each operand (any integer:
 // rows are the outer TMA dimension).
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, (BN * 64 + 8192) * STAGES * 2 <= 100 * 1024 ? 2 : 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                   int ldc, int M, int N, int K, int a_koff, int b_koff, int accumulate, int kb_per_split) {
   using L = GemmSmem<BN, STAGES>;
@@ -322,30 +345,17 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
-    const int row = m0 + ew * 32 + (threadIdx.x & 31);
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    float* crow = C + (size_t)row * ldc + n0;
+    float* stage = reinterpret_cast<float*>(smem) + ew * 1024;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (row < M) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < N) {
-            float o = __uint_as_float(v[j]);
-            if (atomic_out) {
-              atomicAdd(crow + c0 + j, o);
-            } else {
-              if (accumulate) o += crow[c0 + j];
-              crow[c0 + j] = o;
-            }
-          }
-        }
-      }
+      if (atomic_out) epi_chunk<true>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, nullptr, 0, 0);
+      else epi_chunk<false>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, nullptr, accumulate, 0);
     }
   }
   tc_fence_before();
@@ -395,7 +405,7 @@ int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long lo
                     int b_koff, float* C, int ldc, int accumulate) {
   if (M <= 0 || N <= 0) return 0;
   SSASR_REQUIRE(K > 0, "gemm_bf16_tc_tn: K must be positive");
-  constexpr int BN = 128, STAGES = 6;
+  constexpr int BN = 128, STAGES = 3;      // 3 x 32 KB stages: two CTAs per SM, one's epilogue overlaps the other's main loop
   using L = GemmSmem<BN, STAGES>;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16_mn(&tmA, A, (long long)a_koff + K, M, lda);
@@ -560,13 +570,9 @@ int make_tmap_bf16_3d_ex(CUtensorMap* m, const void* ptr, long long cols, long l
   return 0;
 }
 
-int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
-                 int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
-  if (M <= 0 || N <= 0) return 0;
-  SSASR_REQUIRE(K > 0, "gemm_bf16_tc: K must be positive");
-  SSASR_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0, "gemm_bf16_tc: reduction offsets must be multiples of 8 elements (TMA 16-byte "
-                "box alignment), got %d / %d", a_koff, b_koff);
-  constexpr int BN = 128, STAGES = 6;
+template <int BN, int STAGES>
+static int launch_gemm_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
+                          int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
   using L = GemmSmem<BN, STAGES>;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16(&tmA, A, M, (long long)a_koff + K, lda, GT_BM);
@@ -578,12 +584,26 @@ int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long 
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024));
     attr_set = true;
   }
-  dim3 grid((M + GT_BM - 1) / GT_BM, (N + BN - 1) / BN);
-  SSASR_REQUIRE(grid.y <= 65535, "gemm_bf16_tc: N=%d too large", N);
+  dim3 grid((N + BN - 1) / BN, (M + GT_BM - 1) / GT_BM);
+  SSASR_REQUIRE(grid.y <= 65535, "gemm_bf16_tc: M=%d too large", M);
   ProfScope ps(F_GEMM_TC, st);
   gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, bias, M, N, K, a_koff, b_koff, accumulate, act_tanh);
   SSASR_LAUNCH_CHECK();
   return 0;
+}
+
+int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
+                 int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
+  if (M <= 0 || N <= 0) return 0;
+  SSASR_REQUIRE(K > 0, "gemm_bf16_tc: K must be positive");
+  SSASR_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0, "gemm_bf16_tc: reduction offsets must be multiples of 8 elements (TMA 16-byte "
+                "box alignment), got %d / %d", a_koff, b_koff);
+  // 128 x 128 tiles, 3 x 32 KB stages: two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
+  // Small products (the per-step speller GEMMs, 256 rows) use 128 x 32 tiles to spread over 4x as many SMs.
+  const long long tiles128 = (long long)((M + GT_BM - 1) / GT_BM) * ((N + 127) / 128);
+  if (tiles128 < sm_count() / 2 && N >= 64)
+    return launch_gemm_tc<32, 4>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh);
+  return launch_gemm_tc<128, 3>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh);
 }
 
 // ---- fp32 -> bf16 conversion (optionally transposed, optionally masking a periodic column) ----------
