@@ -30,12 +30,25 @@ struct AttnFwd {
   float* alpha; long long alpha_ld;          // [B,Tp]
 };
 
+// 16-byte alignment of a row pointer / leading dimension pair
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float s) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s))));
+}
+
+// shared memory (floats): hs[Sd] qs[M] es[Tp] scratch[32] part[2*E]
+static size_t attn_fwd_smem_bytes(int Sd, int M, int Tp, int E) { return (size_t)(Sd + M + ((Tp + 3) & ~3) + 32 + 2 * E) * sizeof(float); }
+
+// Every phase is a batch of INDEPENDENT 128-bit loads issued before the first use (the per-utterance working set - phi 128 KB,
+// psi~ 32 KB, encoder states 128 KB at the default sizes - streams from L2, so the phases are latency-bound unless many loads
+// are in flight), followed by the arithmetic and a shuffle / shared-memory reduction.
 __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
   extern __shared__ float sm[];
   float* hs = sm;                 // [Sd]
   float* qs = hs + a.Sd;          // [M]
   float* es = qs + a.M;           // [Tp]
-  float* scratch = es + a.Tp;     // [32]
+  float* scratch = es + ((a.Tp + 3) & ~3);     // [32] (kept 16-byte aligned together with everything behind it)
+  float* part = scratch + 32;     // [2][E] context partial sums of the two frame halves
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   float* xrow = a.xin1 + (size_t)b * a.xin1_ld;
   const int tk = a.tok ? a.tok[(size_t)b * a.tok_ld] : 0;
@@ -51,28 +64,95 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     }
   }
   __syncthreads();
-  for (int m = warp; m < a.M; m += nwarp) {
-    float s = 0.f;
-    for (int k = lane; k < a.Sd; k += 32) s = fmaf(a.phi_w[(size_t)m * a.Sd + k], hs[k], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      const float qv = tanhf(s);
-      qs[m] = qv;
-      a.q[(size_t)b * a.q_ld + m] = qv;
+  const int len = a.enc_lens[b];
+  const float* psib = a.psi + (size_t)b * a.Tp * a.M;
+  const float* encb = a.enc + (size_t)b * a.Tp * a.E;
+  const bool vec = ((a.Sd | a.M | a.E) & 3) == 0 && al16(a.phi_w) && al16(psib) && al16(encb);
+  // ---- q = tanh(phi h): a warp takes 4 rows of phi at a time ----
+  if (vec && a.Sd <= 512) {
+    const int nk = a.Sd >> 7;                           // float4 per lane per row (Sd = 128 * nk + remainder handled below)
+    for (int m0 = warp * 4; m0 < a.M; m0 += nwarp * 4) {
+      float4 w[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = (i * 32 + lane) * 4;
+          w[r][i] = (m0 + r < a.M && k < a.Sd) ? __ldg(reinterpret_cast<const float4*>(a.phi_w + (size_t)(m0 + r) * a.Sd + k))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = (i * 32 + lane) * 4;
+        if (k < a.Sd) {
+          const float4 h4 = *reinterpret_cast<const float4*>(hs + k);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] = dot4(w[r][i], h4, acc[r]);
+        }
+      }
+      (void)nk;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
+      if (lane < 4 && m0 + lane < a.M) {
+        const float qv = tanhf(lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]);
+        qs[m0 + lane] = qv;
+        a.q[(size_t)b * a.q_ld + m0 + lane] = qv;
+      }
+    }
+  } else {
+    for (int m = warp; m < a.M; m += nwarp) {
+      float s = 0.f;
+      for (int k = lane; k < a.Sd; k += 32) s = fmaf(a.phi_w[(size_t)m * a.Sd + k], hs[k], s);
+      s = warp_sum(s);
+      if (lane == 0) {
+        const float qv = tanhf(s);
+        qs[m] = qv;
+        a.q[(size_t)b * a.q_ld + m] = qv;
+      }
     }
   }
   __syncthreads();
-  const int len = a.enc_lens[b];
-  const float* psib = a.psi + (size_t)b * a.Tp * a.M;
-  for (int j = warp; j < a.Tp; j += nwarp) {
-    float s = 0.f;
-    if (j < len) {
-      for (int m = lane; m < a.M; m += 32) s = fmaf(psib[(size_t)j * a.M + m], qs[m], s);
-      s = warp_sum(s);
-    } else {
-      s = -INFINITY;
+  // ---- energies e_j = psi~_j . q: a warp takes 4 frames at a time ----
+  if (vec && a.M <= 256) {
+    for (int j0 = warp * 4; j0 < a.Tp; j0 += nwarp * 4) {
+      float4 w[4][2];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int m = (i * 32 + lane) * 4;
+          w[r][i] = (j0 + r < len && m < a.M) ? __ldg(reinterpret_cast<const float4*>(psib + (size_t)(j0 + r) * a.M + m))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = (i * 32 + lane) * 4;
+        if (m < a.M) {
+          const float4 q4 = *reinterpret_cast<const float4*>(qs + m);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[r] = dot4(w[r][i], q4, acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
+      if (lane < 4 && j0 + lane < a.Tp) {
+        const float sv = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        es[j0 + lane] = (j0 + lane < len) ? sv : -INFINITY;
+      }
     }
-    if (lane == 0) es[j] = s;
+  } else {
+    for (int j = warp; j < a.Tp; j += nwarp) {
+      float s = 0.f;
+      if (j < len) {
+        for (int m = lane; m < a.M; m += 32) s = fmaf(psib[(size_t)j * a.M + m], qs[m], s);
+        s = warp_sum(s);
+      } else {
+        s = -INFINITY;
+      }
+      if (lane == 0) es[j] = s;
+    }
   }
   __syncthreads();
   float mx = -INFINITY;
@@ -93,12 +173,41 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     a.alpha[(size_t)b * a.alpha_ld + j] = al;
   }
   __syncthreads();
-  const float* encb = a.enc + (size_t)b * a.Tp * a.E;
-  for (int c = tid; c < a.E; c += blockDim.x) {
-    float s = 0.f;
-    for (int j = 0; j < len; ++j) s = fmaf(es[j], encb[(size_t)j * a.E + c], s);
-    xrow[a.Sd + c] = s;
-    if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(s);
+  // ---- context c = sum_j alpha_j h_j: thread = (4 columns, frame parity), 8 frames of loads in flight ----
+  if (vec) {
+    const int half = tid >> 7, c4 = tid & 127;
+    for (int c = c4 * 4; c < a.E; c += 512) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j0 = half; j0 < len; j0 += 16) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 2 * u;
+          v[u] = (j < len) ? __ldg(reinterpret_cast<const float4*>(encb + (size_t)j * a.E + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 2 * u;
+          const float al = (j < len) ? es[j] : 0.f;
+          acc.x = fmaf(al, v[u].x, acc.x); acc.y = fmaf(al, v[u].y, acc.y);
+          acc.z = fmaf(al, v[u].z, acc.z); acc.w = fmaf(al, v[u].w, acc.w);
+        }
+      }
+      *reinterpret_cast<float4*>(part + half * a.E + c) = acc;
+    }
+    __syncthreads();
+    for (int c = tid; c < a.E; c += blockDim.x) {
+      const float sv = part[c] + part[a.E + c];
+      xrow[a.Sd + c] = sv;
+      if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(sv);
+    }
+  } else {
+    for (int c = tid; c < a.E; c += blockDim.x) {
+      float sv = 0.f;
+      for (int j = 0; j < len; ++j) sv = fmaf(es[j], encb[(size_t)j * a.E + c], sv);
+      xrow[a.Sd + c] = sv;
+      if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(sv);
+    }
   }
 }
 
@@ -120,26 +229,67 @@ struct AttnBwd {
   float* dh1att;                             // [B,Sd] out
 };
 
+// shared memory (floats): dcs[E] als[Tp] das[Tp] dqs[M] scratch[32] part[max(8*M, 4*Sd)]
+static size_t attn_bwd_smem_bytes(int Sd, int M, int Tp, int E) {
+  const int pm = 8 * M > 4 * Sd ? 8 * M : 4 * Sd;
+  return (size_t)(E + 2 * ((Tp + 3) & ~3) + M + 32 + pm) * sizeof(float);
+}
+
 __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
   extern __shared__ float sm[];
   float* dcs = sm;                 // [E]
   float* als = dcs + a.E;          // [Tp]  alpha, then de
-  float* das = als + a.Tp;         // [Tp]  dalpha
-  float* dqs = das + a.Tp;         // [M]
+  float* das = als + ((a.Tp + 3) & ~3);    // [Tp]  dalpha
+  float* dqs = das + ((a.Tp + 3) & ~3);    // [M]
   float* scratch = dqs + a.M;      // [32]
+  float* part = scratch + 32;      // [8][M] / [4][Sd] partial sums
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int len = a.enc_lens[b];
   for (int c = tid; c < a.E; c += blockDim.x) dcs[c] = a.dctx[(size_t)b * a.dctx_ld + c];
   for (int j = tid; j < a.Tp; j += blockDim.x) als[j] = a.alpha[(size_t)b * a.alpha_ld + j];
   __syncthreads();
   const float* encb = a.enc + (size_t)b * a.Tp * a.E;
-  for (int j = warp; j < a.Tp; j += nwarp) {
-    float s = 0.f;
-    if (j < len) {
-      for (int c = lane; c < a.E; c += 32) s = fmaf(dcs[c], encb[(size_t)j * a.E + c], s);
-      s = warp_sum(s);
+  const float* psib = a.psi + (size_t)b * a.Tp * a.M;
+  const bool vec = ((a.Sd | a.M | a.E) & 3) == 0 && al16(a.phi_w) && al16(psib) && al16(encb);
+  // ---- dalpha_j = dctx . h_j: a warp takes 2 frames at a time, up to 8 float4 per lane and frame in flight ----
+  if (vec && a.E <= 1024) {
+    for (int j0 = warp * 2; j0 < a.Tp; j0 += nwarp * 2) {
+      float4 w[2][8];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          w[r][i] = (j0 + r < len && c < a.E) ? __ldg(reinterpret_cast<const float4*>(encb + (size_t)(j0 + r) * a.E + c))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      float acc[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < a.E) {
+          const float4 d4 = *reinterpret_cast<const float4*>(dcs + c);
+          acc[0] = dot4(w[0][i], d4, acc[0]);
+          acc[1] = dot4(w[1][i], d4, acc[1]);
+        }
+      }
+      acc[0] = warp_sum(acc[0]);
+      acc[1] = warp_sum(acc[1]);
+      if (lane < 2 && j0 + lane < a.Tp) {
+        const int j = j0 + lane;
+        const float sv = (j < len) ? (lane == 0 ? acc[0] : acc[1]) : 0.f;
+        das[j] = sv + ((a.dalpha && j < len) ? a.dalpha[(size_t)b * a.dalpha_ld + j] : 0.f);
+      }
     }
-    if (lane == 0) das[j] = s + ((a.dalpha && j < len) ? a.dalpha[(size_t)b * a.dalpha_ld + j] : 0.f);
+  } else {
+    for (int j = warp; j < a.Tp; j += nwarp) {
+      float sv = 0.f;
+      if (j < len) {
+        for (int c = lane; c < a.E; c += 32) sv = fmaf(dcs[c], encb[(size_t)j * a.E + c], sv);
+        sv = warp_sum(sv);
+      }
+      if (lane == 0) das[j] = sv + ((a.dalpha && j < len) ? a.dalpha[(size_t)b * a.dalpha_ld + j] : 0.f);
+    }
   }
   __syncthreads();
   float dot = 0.f;
@@ -152,20 +302,80 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
     a.de[(size_t)b * a.de_ld + j] = de;
   }
   __syncthreads();
-  const float* psib = a.psi + (size_t)b * a.Tp * a.M;
-  for (int m = tid; m < a.M; m += blockDim.x) {
-    const float qv = a.q[(size_t)b * a.q_ld + m];
-    float s = 0.f;
-    for (int j = 0; j < len; ++j) s = fmaf(als[j], psib[(size_t)j * a.M + m], s);
-    const float dq = s * (1.f - qv * qv);
-    dqs[m] = dq;
-    a.dqpre[(size_t)b * a.dqpre_ld + m] = dq;
+  // ---- dq_m = (sum_j de_j psi~_jm)(1 - q_m^2): thread = (4 columns of psi~, one of 8 frame groups) ----
+  if (vec && a.M <= 128) {
+    const int grp = tid >> 5, m = lane * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < a.M) {
+      for (int j0 = grp; j0 < len; j0 += 64) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 8 * u;
+          v[u] = (j < len) ? __ldg(reinterpret_cast<const float4*>(psib + (size_t)j * a.M + m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 8 * u;
+          const float de = (j < len) ? als[j] : 0.f;
+          acc.x = fmaf(de, v[u].x, acc.x); acc.y = fmaf(de, v[u].y, acc.y);
+          acc.z = fmaf(de, v[u].z, acc.z); acc.w = fmaf(de, v[u].w, acc.w);
+        }
+      }
+      *reinterpret_cast<float4*>(part + grp * a.M + m) = acc;
+    }
+    __syncthreads();
+    for (int mm = tid; mm < a.M; mm += blockDim.x) {
+      float sv = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sv += part[g * a.M + mm];
+      const float qv = a.q[(size_t)b * a.q_ld + mm];
+      const float dq = sv * (1.f - qv * qv);
+      dqs[mm] = dq;
+      a.dqpre[(size_t)b * a.dqpre_ld + mm] = dq;
+    }
+  } else {
+    for (int m = tid; m < a.M; m += blockDim.x) {
+      const float qv = a.q[(size_t)b * a.q_ld + m];
+      float sv = 0.f;
+      for (int j = 0; j < len; ++j) sv = fmaf(als[j], psib[(size_t)j * a.M + m], sv);
+      const float dq = sv * (1.f - qv * qv);
+      dqs[m] = dq;
+      a.dqpre[(size_t)b * a.dqpre_ld + m] = dq;
+    }
   }
   __syncthreads();
-  for (int k = tid; k < a.Sd; k += blockDim.x) {
-    float s = 0.f;
-    for (int m = 0; m < a.M; ++m) s = fmaf(dqs[m], a.phi_w[(size_t)m * a.Sd + k], s);
-    a.dh1att[(size_t)b * a.Sd + k] = s;
+  // ---- dh = phi^T dq: thread = (4 columns of phi, one of 4 row groups) ----
+  if (vec && a.Sd <= 256) {
+    const int grp = tid >> 6, k = (tid & 63) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < a.Sd) {
+      for (int m0 = grp; m0 < a.M; m0 += 32) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int m = m0 + 4 * u;
+          v[u] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.phi_w + (size_t)m * a.Sd + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int m = m0 + 4 * u;
+          const float dq = (m < a.M) ? dqs[m] : 0.f;
+          acc.x = fmaf(dq, v[u].x, acc.x); acc.y = fmaf(dq, v[u].y, acc.y);
+          acc.z = fmaf(dq, v[u].z, acc.z); acc.w = fmaf(dq, v[u].w, acc.w);
+        }
+      }
+      *reinterpret_cast<float4*>(part + grp * a.Sd + k) = acc;
+    }
+    __syncthreads();
+    for (int kk = tid; kk < a.Sd; kk += blockDim.x)
+      a.dh1att[(size_t)b * a.Sd + kk] = part[kk] + part[a.Sd + kk] + part[2 * a.Sd + kk] + part[3 * a.Sd + kk];
+  } else {
+    for (int k = tid; k < a.Sd; k += blockDim.x) {
+      float sv = 0.f;
+      for (int m = 0; m < a.M; ++m) sv = fmaf(dqs[m], a.phi_w[(size_t)m * a.Sd + k], sv);
+      a.dh1att[(size_t)b * a.Sd + k] = sv;
+    }
   }
 }
 
@@ -488,7 +698,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     rc = gemm_f32(st, B * Tp, M, E, a->enc, E, 1, a->psi_w, E, 1, a->psi, M, a->psi_b, 0, 1);
   }
   if (rc) return rc;
-  const size_t attn_smem = (size_t)(Sd + M + Tp + 32) * sizeof(float);
+  const size_t attn_smem = attn_fwd_smem_bytes(Sd, M, Tp, E);
   SSASR_REQUIRE(attn_smem <= 200 * 1024, "speller: attention working set too large (Tp=%d)", Tp);
   if (attn_smem > 48 * 1024)
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
@@ -628,7 +838,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   rc = colsum(st, a->dlogits, a->d_bc, B * U, C, C, 0);
   if (rc) return rc;
   SSASR_CHECK_CUDA(cudaMemsetAsync(a->d_emb_w, 0, sizeof(float) * (size_t)C * Sd, st));
-  const size_t attn_smem = (size_t)(E + 2 * Tp + M + 32) * sizeof(float);
+  const size_t attn_smem = attn_bwd_smem_bytes(Sd, M, Tp, E);
   SSASR_REQUIRE(attn_smem <= 200 * 1024 && (size_t)U * 8 * sizeof(float) <= 48 * 1024, "speller bwd: attention working set too large (Tp=%d, U=%d)", Tp, U);
   if (attn_smem > 48 * 1024)
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
@@ -735,7 +945,7 @@ int ssasr_attn_step_fwd(int B, int Tp, int E, int Sd, int M, const float* h, con
   f.emb_w = nullptr; f.tok = nullptr; f.tok_ld = 0;
   f.xin1 = xrow; f.xin1_ld = 2 * Sd + E; f.xin1b = nullptr; f.xin1b_ld = 0;
   f.q = q; f.q_ld = M; f.alpha = alpha; f.alpha_ld = Tp;
-  const size_t smem = (size_t)(Sd + M + Tp + 32) * sizeof(float);
+  const size_t smem = attn_fwd_smem_bytes(Sd, M, Tp, E);
   SSASR_REQUIRE(smem <= 200 * 1024, "attn_step_fwd: working set too large (Tp=%d)", Tp);
   if (smem > 48 * 1024) SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(F_ATTN_FWD, st);
@@ -753,7 +963,7 @@ int ssasr_attn_step_bwd(int B, int Tp, int E, int Sd, int M, const float* dctx, 
   g.dctx = dctx; g.dctx_ld = E; g.alpha = alpha; g.alpha_ld = Tp; g.q = q; g.q_ld = M;
   g.phi_w = phi_w; g.psi = psi; g.enc = enc; g.enc_lens = enc_lens;
   g.dalpha = dalpha; g.dalpha_ld = Tp; g.de = de; g.de_ld = Tp; g.dqpre = dqpre; g.dqpre_ld = M; g.dh1att = dh;
-  const size_t smem = (size_t)(E + 2 * Tp + M + 32) * sizeof(float);
+  const size_t smem = attn_bwd_smem_bytes(Sd, M, Tp, E);
   SSASR_REQUIRE(smem <= 200 * 1024, "attn_step_bwd: working set too large (Tp=%d)", Tp);
   if (smem > 48 * 1024) SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(F_ATTN_BWD, st);
