@@ -681,7 +681,9 @@ int mask_rows_bf16(cudaStream_t st, void* x, long long rows, int cols, int perio
 int cvt_bf16(cudaStream_t st, const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols) {
   if (rows <= 0 || cols <= 0) return 0;
   ProfScope ps(F_PACK, st);
-  cvt_bf16_kernel<<<1184, 256, 0, st>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
+  const long long pairs = rows * (long long)((cols + 1) / 2);
+  const int blocks = (int)(pairs / 256 + 1 < 1184 ? pairs / 256 + 1 : 1184);      // small operands: no idle CTAs to schedule
+  cvt_bf16_kernel<<<blocks, 256, 0, st>>>(src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
   SSASR_LAUNCH_CHECK();
   return 0;
 }
