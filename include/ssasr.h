@@ -166,6 +166,7 @@ int ssasr_profile_read(double* ms /*[num_families]*/, long long* launches /*[num
 void ssasr_rec_tc_set_debug(long long* dev_buf /*[n_seq][12] clock64 stamps of CTA 0, or NULL*/);
 void ssasr_rec_cl_set_debug(long long* dev_buf /*[n_seq][12], cluster recurrent kernels (rec_cl.cu)*/);
 int ssasr_rec_cl_capacity(int S, int backward); /* co-resident (direction, tile) clusters of the cluster recurrence; 0 = unavailable */
+void ssasr_rec_cl_enable(int on);              /* 0: counter-barrier recurrent kernels everywhere (A/B comparison) */
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,7 @@ SIGNATURES = {
     'ssasr_rec_tc_set_debug': (None, [_P]),
     'ssasr_rec_cl_set_debug': (None, [_P]),
     'ssasr_rec_cl_capacity': (_I, [_I, _I]),
+    'ssasr_rec_cl_enable': (None, [_I]),
 }
 
 

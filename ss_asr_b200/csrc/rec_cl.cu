@@ -705,13 +705,13 @@ static int prepare(Kern kern, int cluster_x, size_t smem, size_t smem_max, int* 
 // co-resident cluster capacity per state size, queried once (index = S / 64): [0] forward, [1] backward
 static int g_cap[2][5] = {{-1, -1, -1, -1, -1}, {-1, -1, -1, -1, -1}};
 
+static int g_cl_on = -1;      // -1: not decided yet (environment SSASR_REC_CLUSTER=0 disables), 0 / 1: set
 static bool cl_enabled() {
-  static int on = -1;
-  if (on < 0) {
+  if (g_cl_on < 0) {
     const char* e = getenv("SSASR_REC_CLUSTER");
-    on = (e && e[0] == '0') ? 0 : 1;
+    g_cl_on = (e && e[0] == '0') ? 0 : 1;
   }
-  return on == 1;
+  return g_cl_on == 1;
 }
 
 // exchange ring: internal, L2-resident scratch (a few MB), one per stream that ever launched a cluster recurrence
@@ -748,6 +748,8 @@ int rec_cl_supported(int S, int n_batch, int backward) {
   const int tiles = (n_batch + CL_TM - 1) / CL_TM;
   return (2 * tiles <= g_cap[w][idx] && 2 * tiles * (S / CL_UNITS) <= 148) ? 1 : 0;
 }
+
+void rec_cl_enable(int on) { g_cl_on = on ? 1 : 0; }
 
 // co-resident cluster capacity (0 = cluster kernels unavailable for this state size)
 int rec_cl_capacity(int S, int backward) {
@@ -798,4 +800,6 @@ extern "C" {
 void ssasr_rec_cl_set_debug(long long* dev_buf) { ssasr::g_cl_dbg = dev_buf; }
 // how many (direction, 64-row tile) clusters of the cluster recurrent kernels can be co-resident (0: not available)
 int ssasr_rec_cl_capacity(int S, int backward) { return ssasr::rec_cl_capacity(S, backward); }
+// 0: use the counter-barrier kernels of rec_tc.cu even where the cluster kernels apply (A/B comparison in tests and scripts)
+void ssasr_rec_cl_enable(int on) { ssasr::rec_cl_enable(on); }
 }

@@ -447,3 +447,47 @@ def test_per_step_module_api_matches_fused_forward():
     from ss_asr_b200.functional import asr_loss
     asr_loss(logits, yd).backward()
     _check_grads(m, grads_o)
+
+
+@pytest.mark.parametrize('S,B,T,K', [(256, 200, 48, 64), (128, 70, 33, 40), (64, 9, 21, 24)])
+def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
+    """The cluster recurrent kernels (rec_cl.cu: multicast exchange inside an 8/4/2-CTA cluster) against the counter-barrier
+    kernels (rec_tc.cu) on ragged lengths: same bf16 operand rounding and fp32 accumulation, so they agree far inside
+    the bf16-path tolerance; the debug stamps prove which kernel ran."""
+    from ss_asr_b200 import _lib
+    from ss_asr_b200.asr import pBLSTM
+    lib = _lib.load()
+    assert lib.ssasr_rec_cl_capacity(S, 0) >= 2 * ((B + 63) // 64) and lib.ssasr_rec_cl_capacity(S, 1) >= 2 * ((B + 63) // 64)
+    torch.manual_seed(3)
+    m = pBLSTM(K, S).to(DEV)
+    m.precision = 'bf16'
+    g = torch.Generator().manual_seed(5)
+    lens = sorted([int(v) for v in torch.randint(max(2, T // 3), T + 1, (B,), generator=g)], reverse=True)
+    lens[0] = T
+    x0 = torch.randn(B, T, K, generator=g)
+    x0 = x0 * (torch.arange(T)[None, :, None] < torch.tensor(lens)[:, None, None])
+    res = {}
+    stamps = torch.zeros(T, 12, dtype=torch.int64, device=DEV)
+    try:
+        for on in (1, 0):
+            lib.ssasr_rec_cl_enable(on)
+            stamps.zero_()
+            lib.ssasr_rec_cl_set_debug(stamps.data_ptr())
+            x = x0.clone().to(DEV).requires_grad_(True)
+            m.zero_grad()
+            out, _, _ = m(x, state_len=lens, pack_input=True)
+            w = torch.linspace(-1, 1, out.numel(), device=DEV).view_as(out)
+            (out * w).sum().backward()
+            torch.cuda.synchronize()
+            lib.ssasr_rec_cl_set_debug(None)
+            ran_cluster = bool((stamps != 0).any())
+            assert ran_cluster == bool(on)
+            res[on] = (out.detach().clone(), x.grad.clone(), [p.grad.clone() for p in m.parameters()])
+    finally:
+        lib.ssasr_rec_cl_enable(1)
+        lib.ssasr_rec_cl_set_debug(None)
+    a, b = res[1], res[0]
+    assert float((a[0] - b[0]).abs().max()) < 2e-3
+    assert float(a[1].norm()) > 0 and float((a[1] - b[1]).norm()) <= 5e-3 * float(b[1].norm())
+    for ga, gb in zip(a[2], b[2]):
+        assert float((ga - gb).norm()) <= 5e-3 * float(gb.norm()) + 1e-6
