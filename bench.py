@@ -267,14 +267,40 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else {}
     value = world * B * args.steps / (ms / 1e3)
 
-    # e2e: host buffers in, loss + attention maps out, through the drop-in module API
+    # e2e: host buffers in, loss + attention maps out, through the drop-in module API.  Every step copies its batch
+    # from pinned host memory (on the copy stream of HostBatchPipeline, overlapping the previous step) and reads the loss
+    # and the attention maps back to the host (the maps land in pinned memory without blocking; they are read after the
+    # loss sync).
+    from ss_asr_b200.parallel import HostBatchPipeline
+    pipe = HostBatchPipeline(dev)
+    model.att_async = True
+    e2e_state = {'left': 0, 'att_probe': 0.0}
+
     def e2e_step():
-        xd = x_host.to(dev, non_blocking=True)
-        yd = y_host.to(dev, non_blocking=True)
-        loss = step(xd, yd, False)
-        return float(loss)
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+        xd, yd = pipe.take()
+        e2e_state['left'] -= 1
+        if e2e_state['left'] > 0:
+            pipe.submit(x_host, y_host)
+        model.att_on_device = False
+        optim.zero_grad(set_to_none=True)
+        _, logits, att = model(xd, ans_len, teacher=yd, state_len=lens)
+        loss = asr_loss(logits, yd)
+        sync.backward(loss)
+        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+        if not torch.isnan(gn):
+            optim.step()
+        v = float(loss.detach())                 # host sync: the loss and the attention maps of this step are on the host
+        e2e_state['att_probe'] = float(att[0, 0, 0])
+        return v
+
+    def e2e_run(n):
+        e2e_state['left'] = n
+        pipe.submit(x_host, y_host)              # the first batch's copy is inside the timed region as well
+        for _ in range(n):
+            e2e_step()
+    e2e_run(2)
+    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
+    model.att_async = False
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = x_host.numel() * 4 + y_host.numel() * 8
     d2h = 4 + B * ans_len * (T // 8) * 4

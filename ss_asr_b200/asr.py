@@ -206,6 +206,10 @@ class ASR(nn.Module):
         self.char_trans = nn.Linear(decoder_state_size, output_dim)
         self.tf_rate = tf_rate
         self.att_on_device = False       # True: keep attention maps on the GPU (skips the reference's D2H copy)
+        self.att_async = False           # True: the D2H copy of the attention maps goes to a pinned buffer without blocking the
+                                         # host (valid after the next stream sync, e.g. the loss read of trainer.py:440);
+                                         # False: the reference's blocking .cpu() (asr.py:104)
+        self._att_pinned = None
         self.train_precision = 'fp32'    # 'bf16': tensor-core gate GEMMs when training with grad enabled
         self.decode_precision = 'fp32'   # 'tf32x3': encoder input projections of decode_batch on tensor cores
         self.sample_seed = 0
@@ -241,7 +245,14 @@ class ASR(nn.Module):
         logits, att, toks = self._spell(encode_feature, encode_len, tok_in, modes, 'bf16' if use_bf16 else 'fp32')
         self.last_tokens = toks
         att = att.detach()
-        return encode_len, logits, (att if self.att_on_device else att.cpu())
+        if self.att_on_device:
+            return encode_len, logits, att
+        if self.att_async:
+            if self._att_pinned is None or self._att_pinned.shape != att.shape:
+                self._att_pinned = torch.empty(att.shape, dtype=att.dtype, pin_memory=True)
+            self._att_pinned.copy_(att, non_blocking=True)
+            return encode_len, logits, self._att_pinned
+        return encode_len, logits, att.cpu()
 
     @torch.no_grad()
     def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None):

@@ -75,3 +75,30 @@ class GradSync:
         for h in self._handles:
             h.remove()
         self._handles = []
+
+
+class HostBatchPipeline:
+    """Double-buffered host -> device staging of training batches (the DataLoader hand-off of trainer.py:415-418):
+    the pinned-memory copy of batch i+1 runs on a copy stream while batch i is computing, so the H2D transfer (42 MB per
+    256-utterance batch) leaves the critical path.  `submit` enqueues the copies, `take` makes the compute stream wait for
+    them and returns the device tensors."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._queue = []
+
+    def submit(self, *host_tensors):
+        with torch.cuda.stream(self.stream):
+            devs = [t.to(self.device, non_blocking=True) for t in host_tensors]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._queue.append((devs, ev))
+
+    def take(self):
+        devs, ev = self._queue.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for d in devs:
+            d.record_stream(cur)
+        return devs

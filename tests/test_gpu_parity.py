@@ -491,3 +491,29 @@ def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
     assert float(a[1].norm()) > 0 and float((a[1] - b[1]).norm()) <= 5e-3 * float(b[1].norm())
     for ga, gb in zip(a[2], b[2]):
         assert float((ga - gb).norm()) <= 5e-3 * float(gb.norm()) + 1e-6
+
+
+def test_host_batch_pipeline_and_async_attention_maps(golden_dir):
+    """The e2e helpers: double-buffered pinned-host -> device batches and the non-blocking D2H of the attention maps
+    deliver the same values as the blocking reference behaviour (asr.py:104 `.cpu()`)."""
+    from ss_asr_b200.parallel import HostBatchPipeline
+    dims = (50, 64, 64, 32, 40)
+    sd = O.make_state_dict(*dims, seed=1)
+    x, lens, y = O.synth_batch(6, 48, dims[4], 7, seed=11)
+    m = _model(dims, sd)
+    m.eval()
+    pipe = HostBatchPipeline(DEV)
+    xh, yh = x.pin_memory(), y.pin_memory()
+    pipe.submit(xh, yh)
+    pipe.submit(xh, yh)
+    outs = []
+    with torch.no_grad():
+        for use_async in (False, True):
+            xd, yd = pipe.take()
+            assert xd.is_cuda and torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
+            m.att_async = use_async
+            _, logits, att = m(xd, 8, teacher=yd, state_len=lens)
+            torch.cuda.synchronize()
+            assert not att.is_cuda
+            outs.append((logits.cpu().clone(), att.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
