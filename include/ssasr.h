@@ -115,6 +115,7 @@ typedef struct {
   const float *lm_emb, *lm_w1i, *lm_w1h, *lm_b1i, *lm_b1h, *lm_w2i, *lm_w2h, *lm_b2i, *lm_b2h, *lm_wo, *lm_bo;
   float *lm_h1, *lm_h2;
   float* x3_ws; /* NULL, or 2*B*max(X1,X2) + 8*Sd*(X1+X2) floats: forward-only gate GEMMs on tensor cores (tf32 x 3) */
+  int skip_final_logits; /* 1: do not recompute the [B,U,C] logits after the loop (greedy decoding only needs tok_in) */
 } ssasr_speller_fwd_args;
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
 

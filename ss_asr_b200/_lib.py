@@ -19,7 +19,8 @@ class SpellerFwdArgs(C.Structure):
                                            'logits', 'w1cat_bf', 'w2cat_bf', 'ws_bf', 'enc_bf')] +
                 [('lm_H', C.c_int), ('lm_weight', C.c_float)] +
                 [(n, C.c_void_p) for n in ('lm_emb', 'lm_w1i', 'lm_w1h', 'lm_b1i', 'lm_b1h', 'lm_w2i', 'lm_w2h', 'lm_b2i',
-                                           'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2', 'x3_ws')])
+                                           'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2', 'x3_ws')] +
+                [('skip_final_logits', C.c_int)])
 
 
 class SpellerBwdArgs(C.Structure):

@@ -217,12 +217,12 @@ class ASR(nn.Module):
         self.init_parameters()
 
     # ------------------------------------------------------------------------------------------
-    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None):
+    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None, need_logits=True):
         lens_dev = torch.tensor(enc_len, dtype=torch.int32, device=enc.device)
         params = self.attention.params() + self.decoder.params() + (self.embed.weight, self.char_trans.weight,
                                                                     self.char_trans.bias)
         self.sample_seed += 1
-        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision, lm)
+        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision, lm, need_logits)
 
     def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
         """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
@@ -275,7 +275,8 @@ class ASR(nn.Module):
         lm = None
         if rnn_lm is not None and lm_weight != 0:
             lm = (Fk.pack_charlm(rnn_lm, enc.device), lm_weight)
-        _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), precision=prec, lm=lm)
+        _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), precision=prec, lm=lm,
+                                 need_logits=False)
         toks = toks[:, 1:].cpu().tolist()
         out = []
         for row in toks:

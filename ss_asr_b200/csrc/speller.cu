@@ -26,10 +26,20 @@ struct AttnFwd {
   const float* emb_w; const int* tok; long long tok_ld;   // embedding gather for the step input
   float* xin1; long long xin1_ld;            // row b: [emb(Sd) ; ctx(E) ; h1prev(Sd)]
   __nv_bfloat16* xin1b; long long xin1b_ld;  // optional bf16 copy of the same row (tensor-core GEMM operand)
+  float* x3h; float* x3l; long long x3_ld;   // optional tf32 hi / lo split of the same row (tf32 x 3 GEMM operands)
   float* q; long long q_ld;                  // [B,M]
   float* alpha; long long alpha_ld;          // [B,Tp]
 };
 
+// hi = rn_tf32(v), lo = rn_tf32(v - hi): the operand split of the tf32 x 3 GEMM (gemm_tc.cu), fused into the producers
+__device__ __forceinline__ void put_hi_lo(float* hi, float* lo, size_t i, float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  const float h = __uint_as_float(r);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v - h));
+  hi[i] = h;
+  lo[i] = __uint_as_float(r);
+}
 // 16-byte alignment of a row pointer / leading dimension pair
 __device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 __device__ __forceinline__ float dot4(const float4 a, const float4 b, float s) {
@@ -61,6 +71,10 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     if (a.xin1b) {
       a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + a.E + k] = __float2bfloat16(h);
       a.xin1b[(size_t)b * a.xin1b_ld + k] = __float2bfloat16(e);
+    }
+    if (a.x3h) {
+      put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + a.Sd + a.E + k, h);
+      put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + k, e);
     }
   }
   __syncthreads();
@@ -200,6 +214,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
       const float sv = part[c] + part[a.E + c];
       xrow[a.Sd + c] = sv;
       if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(sv);
+      if (a.x3h) put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + a.Sd + c, sv);
     }
   } else {
     for (int c = tid; c < a.E; c += blockDim.x) {
@@ -207,6 +222,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
       for (int j = 0; j < len; ++j) sv = fmaf(es[j], encb[(size_t)j * a.E + c], sv);
       xrow[a.Sd + c] = sv;
       if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(sv);
+      if (a.x3h) put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + a.Sd + c, sv);
     }
   }
 }
@@ -420,7 +436,8 @@ __global__ void __launch_bounds__(256) attn_outer_accum_kernel(int U, int Tp, in
 __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long long g_ld, const float* __restrict__ cprev,
                                 long long cp_ld, float* __restrict__ cout, long long c_ld, float* __restrict__ hout,
                                 long long h_ld, const float* __restrict__ cp_src, long long cps_ld, float* __restrict__ cp_dst,
-                                long long cpd_ld, __nv_bfloat16* __restrict__ hb_out, long long hb_ld, int hb_cp_off) {
+                                long long cpd_ld, __nv_bfloat16* __restrict__ hb_out, long long hb_ld, int hb_cp_off,
+                                float* __restrict__ x3h = nullptr, float* __restrict__ x3l = nullptr, long long x3_ld = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S) return;
   const int b = i / S, u = i % S;
@@ -435,10 +452,12 @@ __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long lo
   const float h = a.w * tanhf(c);
   hout[(size_t)b * h_ld + u] = h;
   if (hb_out) hb_out[(size_t)b * hb_ld + u] = __float2bfloat16(h);
+  if (x3h) put_hi_lo(x3h, x3l, (size_t)b * x3_ld + u, h);
   if (cp_dst) {
     const float v = cp_src ? cp_src[(size_t)b * cps_ld + u] : 0.f;
     cp_dst[(size_t)b * cpd_ld + u] = v;
     if (hb_out) hb_out[(size_t)b * hb_ld + hb_cp_off + u] = __float2bfloat16(v);
+    if (x3h) put_hi_lo(x3h, x3l, (size_t)b * x3_ld + hb_cp_off + u, v);
   }
 }
 
@@ -487,6 +506,111 @@ __global__ void dtanh_inplace_kernel(float* __restrict__ d, const float* __restr
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = y[i];
     d[i] *= (1.f - v * v);
+  }
+}
+
+// Character projection (asr.py:79 char_trans) fused with the next-token selection: one warp per utterance, the [C,Sd]
+// weight matrix staged once per CTA in shared memory, fp32 throughout.  Replaces a 16-CTA SIMT GEMM + pick launch per step
+// of greedy decoding / sampling.  mode 0: logits only, 1: argmax (first max index), 2: sample from softmax (Philox).
+constexpr int LP_UPW = 1;      // utterances per warp (8 per CTA): the projection is shared-memory-bandwidth bound per SM, so spread wide
+__host__ __device__ inline int lp_cp(int C) { return C | 1; }     // odd row pitch of the transposed weights: conflict-free staging
+static size_t lp_smem_bytes(int C, int Sd) { return ((size_t)Sd * lp_cp(C) + 8 * (size_t)Sd + C) * sizeof(float); }
+
+// lane = class (C <= 64: classes lane and lane + 32): no cross-lane reduction in the projection, h broadcast from smem
+__global__ void __launch_bounds__(256) logits_pick_kernel(int B, int C, int Sd, const float* __restrict__ h, long long h_ld,
+                                                          const float* __restrict__ wc, const float* __restrict__ bc,
+                                                          float* __restrict__ logits, long long l_ld, int mode,
+                                                          unsigned long long seed, unsigned long long step,
+                                                          int* __restrict__ tok_out, long long tok_ld) {
+  extern __shared__ float sm[];
+  const int Cp = lp_cp(C);
+  float* wt = sm;                           // [Sd][Cp]  transposed weights
+  float* hs = wt + (size_t)Sd * Cp;         // [8][Sd]   one h row per warp
+  float* bs = hs + 8 * (size_t)Sd;          // [C]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = C * Sd;
+  if ((Sd & 3) == 0 && (reinterpret_cast<uintptr_t>(wc) & 15) == 0) {
+#pragma unroll 4
+    for (int i = tid * 4; i < n; i += 1024) {
+      const int c = i / Sd, k = i - c * Sd;
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wc + i));
+      wt[(size_t)k * Cp + c] = w4.x; wt[(size_t)(k + 1) * Cp + c] = w4.y;
+      wt[(size_t)(k + 2) * Cp + c] = w4.z; wt[(size_t)(k + 3) * Cp + c] = w4.w;
+    }
+  } else {
+    for (int i = tid; i < n; i += 256) {
+      const int c = i / Sd, k = i - c * Sd;
+      wt[(size_t)k * Cp + c] = __ldg(wc + i);
+    }
+  }
+  for (int c = tid; c < C; c += 256) bs[c] = bc ? __ldg(bc + c) : 0.f;
+  __syncthreads();
+  float* hrow = hs + (size_t)warp * Sd;
+  const int c0 = lane, c1 = lane + 32;
+  for (int u = 0; u < LP_UPW; ++u) {
+    const int b = (blockIdx.x * 8 + warp) * LP_UPW + u;
+    if (b >= B) return;
+    const float* hb = h + (size_t)b * h_ld;
+    for (int k = lane; k < Sd; k += 32) hrow[k] = __ldg(hb + k);
+    __syncwarp();
+    float s0 = 0.f, s1 = 0.f;
+    if (c1 < C) {
+#pragma unroll 8
+      for (int k = 0; k < Sd; ++k) {
+        const float hv = hrow[k];
+        s0 = fmaf(hv, wt[(size_t)k * Cp + c0], s0);
+        s1 = fmaf(hv, wt[(size_t)k * Cp + c1], s1);
+      }
+    } else if (c0 < C) {
+#pragma unroll 8
+      for (int k = 0; k < Sd; ++k) s0 = fmaf(hrow[k], wt[(size_t)k * Cp + c0], s0);
+    }
+    float best_v = -INFINITY;
+    int best = 0x7fffffff;
+    if (c0 < C) {
+      s0 += bs[c0];
+      logits[(size_t)b * l_ld + c0] = s0;
+      best_v = s0; best = c0;
+    }
+    if (c1 < C) {
+      s1 += bs[c1];
+      logits[(size_t)b * l_ld + c1] = s1;
+      if (s1 > best_v) { best_v = s1; best = c1; }
+    }
+    if (mode != 0) {
+      // argmax with torch.argmax tie-breaking (first maximal index)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ov > best_v || (ov == best_v && oi < best)) { best_v = ov; best = oi; }
+      }
+      if (mode == 2) {      // sample from softmax (Philox; the one intentionally non-bit-reproducible branch, asr.py:97)
+        const float mx = best_v;
+        const float e0 = c0 < C ? expf(s0 - mx) : 0.f, e1 = c1 < C ? expf(s1 - mx) : 0.f;
+        // inclusive prefix sums in class order: classes 0..31 first, then 32..63
+        float p0 = e0, p1 = e1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float a0 = __shfl_up_sync(0xffffffffu, p0, o), a1 = __shfl_up_sync(0xffffffffu, p1, o);
+          if (lane >= o) { p0 += a0; p1 += a1; }
+        }
+        const float tot0 = __shfl_sync(0xffffffffu, p0, 31), tot = tot0 + __shfl_sync(0xffffffffu, p1, 31);
+        p1 += tot0;
+        curandStatePhilox4_32_10_t rs;
+        curand_init(seed, (unsigned long long)b, step, &rs);
+        const float r = curand_uniform(&rs) * tot;
+        // first class whose inclusive prefix reaches r
+        int cand = 0x7fffffff;
+        if (c0 < C && r <= p0) cand = c0;
+        else if (c1 < C && r <= p1) cand = c1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        best = cand == 0x7fffffff ? C - 1 : cand;
+      }
+      if (lane == 0) tok_out[(size_t)b * tok_ld] = best;
+    }
+    __syncwarp();
   }
 }
 
@@ -677,6 +801,7 @@ typedef struct {
   // forward-only fast exact mode: gate GEMMs on tensor cores with the tf32 x 3 split;
   // scratch of 2*B*max(X1,X2) + 2*4Sd*(X1+X2) floats, or NULL
   float* x3_ws;
+  int skip_final_logits;
 } ssasr_speller_fwd_args;
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
@@ -724,9 +849,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   auto gate_gemm = [&](const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out,
                        const __nv_bfloat16* xb) -> int {
     if (tc) return gemm_bf16_tc(st, B, 4 * Sd, K, xb, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0);
-    if (x3) {
-      int r = split_hi_lo_2d(st, x, ldx, B, K, xh, xl);
-      if (r) return r;
+    if (x3) {                  // xh / xl were written by the kernel that produced x (attention step / layer-1 cell)
       const bool first = (K == X1);
       return gemm_tf32x3(st, B, 4 * Sd, K, xh, xl, K, first ? w1h : w2h, first ? w1l : w2l, K, out, U * 4 * Sd, bias, 0);
     }
@@ -740,6 +863,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     f.emb_w = a->emb_w; f.tok = a->tok_in + t; f.tok_ld = U;
     f.xin1 = a->xin1 + (size_t)t * X1; f.xin1_ld = (long long)U * X1;
     f.xin1b = x1b; f.xin1b_ld = X1;
+    f.x3h = x3 ? xh : nullptr; f.x3l = x3 ? xl : nullptr; f.x3_ld = X1;
     f.q = a->q + (size_t)t * M; f.q_ld = (long long)U * M;
     f.alpha = a->alpha + (size_t)t * Tp; f.alpha_ld = (long long)U * Tp;
     { ProfScope ps(F_ATTN_FWD, st); attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f); }
@@ -751,7 +875,8 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd, a->xin2 + (size_t)t * X2,
                                                  (long long)U * X2, t ? a->h2all + (size_t)(t - 1) * Sd : nullptr,
-                                                 (long long)U * Sd, a->xin2 + (size_t)t * X2 + Sd, (long long)U * X2, x2b, X2, Sd);
+                                                 (long long)U * Sd, a->xin2 + (size_t)t * X2 + Sd, (long long)U * X2, x2b, X2, Sd,
+                                                 x3 ? xh : nullptr, x3 ? xl : nullptr, X2);
     // layer 2
     rc = gate_gemm(a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd, x2b);
     if (rc) return rc;
@@ -762,9 +887,23 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
                                                  (long long)U * Sd, nullptr, 0, nullptr, 0, nullptr, 0, 0);
     const int mode = a->step_mode ? a->step_mode[t] : 0;
     if (mode != 0 && t + 1 < U) {
-      rc = gemm_f32(st, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
-                    0, 0);
-      if (rc) return rc;
+      const size_t lp_smem = lp_smem_bytes(C, Sd);
+      const bool fused = C <= 64 && lp_smem <= 160 * 1024;
+      if (fused) {          // projection + selection in one launch (mode 3: projection only, the LM kernel selects)
+        static size_t lp_attr = 0;
+        if (lp_smem > 48 * 1024 && lp_smem > lp_attr) {
+          SSASR_CHECK_CUDA(cudaFuncSetAttribute(logits_pick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
+          lp_attr = lp_smem;
+        }
+        ProfScope ps(F_POINTWISE, st);
+        logits_pick_kernel<<<(B + 8 * LP_UPW - 1) / (8 * LP_UPW), 256, lp_smem, st>>>(B, C, Sd, a->h2all + (size_t)t * Sd, (long long)U * Sd, a->wc, a->bc,
+                                                              a->logits + (size_t)t * C, (long long)U * C, mode == 3 ? 0 : mode,
+                                                              a->seed, (unsigned long long)t, a->tok_in + t + 1, U);
+      } else {
+        rc = gemm_f32(st, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
+                      0, 0);
+        if (rc) return rc;
+      }
       { ProfScope ps(F_POINTWISE, st); }
       if (mode == 3) {
         SSASR_REQUIRE(a->lm_emb && a->lm_h1 && a->lm_h2 && a->lm_H > 0, "speller: step mode 3 needs the language-model arguments");
@@ -777,11 +916,15 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
         l.tok_in = a->tok_in + t; l.tok_out = a->tok_in + t + 1; l.tok_ld = U;
         const int nt = ((a->lm_H + 31) / 32) * 32 > 256 ? 256 : ((a->lm_H + 31) / 32) * 32;
         lm_pick_kernel<<<B, nt, (size_t)(5 * a->lm_H + C + 32) * sizeof(float), st>>>(l);
-      } else {
+      } else if (!fused) {
         pick_token_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
                                                            (unsigned long long)t, a->tok_in + t + 1, U);
       }
     }
+  }
+  if (a->skip_final_logits) {        // greedy decoding only consumes the tokens
+    SSASR_LAUNCH_CHECK();
+    return 0;
   }
   rc = gemm_f32(st, B * U, C, Sd, a->h2all, Sd, 1, a->wc, Sd, 1, a->logits, C, a->bc, 0, 0);
   if (rc) return rc;
@@ -944,6 +1087,7 @@ int ssasr_attn_step_fwd(int B, int Tp, int E, int Sd, int M, const float* h, con
   f.h1prev = h; f.h1_ld = Sd; f.phi_w = phi_w; f.psi = psi; f.enc = enc; f.enc_lens = enc_lens;
   f.emb_w = nullptr; f.tok = nullptr; f.tok_ld = 0;
   f.xin1 = xrow; f.xin1_ld = 2 * Sd + E; f.xin1b = nullptr; f.xin1b_ld = 0;
+  f.x3h = nullptr; f.x3l = nullptr; f.x3_ld = 0;
   f.q = q; f.q_ld = M; f.alpha = alpha; f.alpha_ld = Tp;
   const size_t smem = attn_fwd_smem_bytes(Sd, M, Tp, E);
   SSASR_REQUIRE(smem <= 200 * 1024, "attn_step_fwd: working set too large (Tp=%d)", Tp);

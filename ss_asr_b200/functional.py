@@ -147,6 +147,10 @@ class _Spell(torch.autograd.Function):
                 w_hh2, b_ih2, b_hh2, emb_w, wc, bc):
         lib = _lib.load()
         _lib.require_cuda(enc, 'Speller')
+        skip_final = 0
+        if isinstance(lm, dict):          # {'lm': (weights, weight) or None, 'need_logits': bool}
+            skip_final = 0 if lm.get('need_logits', True) else 1
+            lm = lm.get('lm')
         enc = _f32c(enc)
         B, Tp, E = enc.shape
         Sd = w_hh1.shape[1]
@@ -193,7 +197,8 @@ class _Spell(torch.autograd.Function):
                                 tok_in=ptr(tok_in), step_mode=C.cast(modes, C.c_void_p), seed=int(seed), psi=ptr(psi),
                                 xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
                                 h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits), w1cat_bf=ptr(w1b),
-                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), x3_ws=ptr(x3ws), **lmk)
+                                w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), x3_ws=ptr(x3ws),
+                                skip_final_logits=skip_final, **lmk)
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
@@ -245,8 +250,10 @@ class _Spell(torch.autograd.Function):
         return (denc, None, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
 
 
-def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32', lm=None):
-    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, lm, *params)
+def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32', lm=None, need_logits=True):
+    """need_logits=False (greedy decoding): the [B,U,C] logits tensor is not recomputed after the loop (left undefined)."""
+    opts = lm if need_logits else {'lm': lm, 'need_logits': False}
+    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, opts, *params)
 
 
 def pack_charlm(rnn_lm, device):
