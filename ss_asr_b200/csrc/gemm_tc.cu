@@ -7,6 +7,8 @@
 //
 // Reference call sites replaced: the cuDNN/ATen input-projection GEMMs inside nn.LSTM (asr.py:234-238,414,262)
 // and their dgrad/wgrad in loss.backward() (trainer.py:437) -- SURVEY.md §2.2 K2a/K4/K17.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -187,7 +189,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tmem_full = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   const int warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.x * GT_BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * BN;     // N tiles fastest: a 128-row block of A (hi + lo) is read from HBM once
   const int num_k = (K + BKF - 1) / BKF;
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBl);
@@ -520,7 +522,8 @@ int gemm_tf32x3(cudaStream_t st, int M, int N, int K, const float* A, const floa
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;
   }
-  dim3 grid((M + GT_BM - 1) / GT_BM, (N + 127) / 128);
+  dim3 grid((N + 127) / 128, (M + GT_BM - 1) / GT_BM);
+  SSASR_REQUIRE(grid.y <= 65535, "gemm_tf32x3: M=%d too large", M);
   ProfScope ps(F_GEMM_TC, st);
   gemm_tf32x3_kernel<STAGES><<<grid, 256, SMEM, st>>>(tA, tAl, tB, tBl, C, ldc, bias, M, N, K, act_tanh);
   SSASR_LAUNCH_CHECK();
