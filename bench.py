@@ -220,7 +220,8 @@ def run_ours(args):
     model = ASR(tf_rate=0.9, **DIMS).to(dev)
     model.train_precision = args.precision
     model.train()
-    optim = torch.optim.Adadelta(model.parameters(), lr=1.0, eps=1e-8)
+    from ss_asr_b200.optim import FusedAdadelta
+    optim = FusedAdadelta(model.parameters(), lr=1.0, eps=1e-8)     # torch.optim.Adadelta + Solver.step fused on the device
     sync = GradSync(model, world)
     x, lens, y = synth_batch(B, T, F, U, seed=1234 + rank)
     ans_len = int(max((y != 0).sum(-1) + 1)) - 1
@@ -233,9 +234,7 @@ def run_ours(args):
         _, logits, att = model(xd, ans_len, teacher=yd, state_len=lens)
         loss = asr_loss(logits, yd)
         sync.backward(loss)
-        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
-        if not torch.isnan(gn):            # trainer.py:144-148 NaN-skip (one host sync, as in the reference)
-            optim.step()
+        optim.step_clipped(5.0)            # trainer.py:144-148: clip_grad_norm_(5) + NaN-skip + Adadelta step, on the device
         return loss
 
     def barrier():
@@ -286,9 +285,7 @@ def run_ours(args):
         _, logits, att = model(xd, ans_len, teacher=yd, state_len=lens)
         loss = asr_loss(logits, yd)
         sync.backward(loss)
-        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
-        if not torch.isnan(gn):
-            optim.step()
+        optim.step_clipped(5.0)
         v = float(loss.detach())                 # host sync: the loss and the attention maps of this step are on the host
         e2e_state['att_probe'] = float(att[0, 0, 0])
         return v

@@ -157,6 +157,20 @@ int ssasr_colsum(const float* src, float* out, int R, int C, int ld, int accumul
 int ssasr_ce_loss_f32(const float* logits, const long long* y, int B, int U, int C, int L, float* loss_b /*[B]*/,
                       float* loss_out /*[1]*/, float* dlogits /*[B,U,C] or NULL*/, float grad_scale, void* stream);
 
+/* ---- Solver.step (trainer.py:131-148: clip_grad_norm_ + NaN skip + optimiser step) with the Adadelta of trainer.py:401-403,
+ *      for all parameter tensors in two launches and without the host sync of the NaN test ---- */
+typedef struct {
+  float* p;          /* parameter, updated in place */
+  float* g;          /* gradient (rescaled in place only if write_clipped_grads) */
+  float* sq;         /* Adadelta square_avg */
+  float* acc;        /* Adadelta acc_delta */
+  long long n;       /* elements */
+} ssasr_optim_tensor;
+long long ssasr_adadelta_scratch_floats(const ssasr_optim_tensor* tensors /*HOST array*/, int n_tensors);
+int ssasr_adadelta_clip_step(const ssasr_optim_tensor* tensors /*HOST array of device pointers*/, int n_tensors, float lr, float rho,
+                             float eps, float max_norm /*<= 0: no clipping*/, float* scratch, float* norm_out /*device [2]: norm, applied*/,
+                             int write_clipped_grads, void* stream);
+
 /* ---- launch accounting and per-family CUDA-event timing (used by bench.py; no reference counterpart) ---- */
 int ssasr_num_families(void);
 const char* ssasr_family_name(int i);

@@ -35,6 +35,10 @@ class SpellerBwdArgs(C.Structure):
                 [('BUp', C.c_longlong), ('BTp', C.c_longlong)])
 
 
+class OptimTensor(C.Structure):
+    _fields_ = [('p', C.c_void_p), ('g', C.c_void_p), ('sq', C.c_void_p), ('acc', C.c_void_p), ('n', C.c_longlong)]
+
+
 _P, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     'ssasr_last_error': (C.c_char_p, []),
@@ -65,6 +69,8 @@ SIGNATURES = {
     'ssasr_dtanh_mul': (_I, [_P, _P, _LL, _P]),
     'ssasr_colsum': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'ssasr_ce_loss_f32': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _F, _P]),
+    'ssasr_adadelta_scratch_floats': (_LL, [C.POINTER(OptimTensor), _I]),
+    'ssasr_adadelta_clip_step': (_I, [C.POINTER(OptimTensor), _I, _F, _F, _F, _F, _P, _P, _I, _P]),
     'ssasr_num_families': (_I, []),
     'ssasr_family_name': (C.c_char_p, [_I]),
     'ssasr_launch_count': (_LL, []),

@@ -518,3 +518,46 @@ def test_host_batch_pipeline_and_async_attention_maps(golden_dir):
             assert not att.is_cuda
             outs.append((logits.cpu().clone(), att.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_fused_adadelta_clip_step_matches_torch():
+    """Solver.step (trainer.py:131-148) fused on the device against clip_grad_norm_ + torch.optim.Adadelta, several steps,
+    odd tensor sizes, clipping active and inactive, and the NaN-skip branch."""
+    from ss_asr_b200.optim import FusedAdadelta
+    g = torch.Generator().manual_seed(0)
+    shapes = [(1,), (3,), (257, 129), (70001,), (64, 1024), (5, 7, 3)]
+    ref_p = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.Adadelta(ref_p, lr=1.0, eps=1e-8)
+    ours = FusedAdadelta(our_p, lr=1.0, eps=1e-8)
+    for it, scale in enumerate([10.0, 0.01, 3.0, 1.0]):          # norm far above / far below the clip threshold
+        grads = [scale * torch.randn(*s, generator=g).to(DEV) for s in shapes]
+        for p, q, gr in zip(ref_p, our_p, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        gn = torch.nn.utils.clip_grad_norm_(ref_p, 5.0)
+        ref.step()
+        got = ours.step_clipped(5.0, write_clipped_grads=(it == 0))
+        assert abs(float(got) - float(gn)) <= 1e-5 * float(gn)
+        assert float(ours.last_applied) == 1.0
+        for p, q in zip(ref_p, our_p):
+            assert float((p - q).abs().max()) <= 2e-6 * (1.0 + float(p.abs().max()))
+        if it == 0:
+            for p, q in zip(ref_p, our_p):
+                assert float((p.grad - q.grad).abs().max()) <= 1e-6 * (1.0 + float(p.grad.abs().max()))
+    for k in ('square_avg', 'acc_delta'):
+        for p, q in zip(ref_p, our_p):
+            a, b = ref.state[p][k], ours.state[q][k]
+            assert float((a - b).abs().max()) <= 1e-5 * (1e-6 + float(a.abs().max()))
+    # NaN gradient: the step is cancelled on the device
+    before = [q.detach().clone() for q in our_p]
+    for q in our_p:
+        q.grad = torch.randn_like(q)
+    our_p[2].grad[0, 0] = float('nan')
+    ours.step_clipped(5.0)
+    assert float(ours.last_applied) == 0.0 and bool(torch.isnan(ours.last_grad_norm))
+    for b, q in zip(before, our_p):
+        assert torch.equal(b, q.detach())
+    # state_dict round trip into torch.optim.Adadelta
+    ref2 = torch.optim.Adadelta(our_p, lr=1.0, eps=1e-8)
+    ref2.load_state_dict(ours.state_dict())
