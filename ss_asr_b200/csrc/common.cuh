@@ -115,7 +115,9 @@ int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
 // cluster recurrent kernels (rec_cl.cu): multicast-TMA exchange inside one thread-block cluster per (direction, batch tile)
 int rec_cl_supported(int S, int n_batch, int backward);
 int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
-               int n_seq, int n_batch, long long rs_seq, long long rs_batch);
+               int n_seq, int n_batch, long long rs_seq, long long rs_batch, const void* x_bf = nullptr, int Kp = 0,
+               const void* wih_bf = nullptr, const float* bias = nullptr);
+int rec_cl_fused_kp_max();
 int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
                int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias);
 

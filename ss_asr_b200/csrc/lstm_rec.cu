@@ -545,6 +545,10 @@ int ssasr_blstm_fwd_bf16(const float* x, int n_rows, int K, int Kp, const void* 
   SSASR_REQUIRE(S % 16 == 0 && Kp % 8 == 0 && Kp >= K, "blstm_fwd_bf16: bad S=%d / Kp=%d (K=%d)", S, Kp, K);
   int rc = cvt_bf16(st, x, K, xb_ws, Kp, n_rows, K);
   if (rc) return rc;
+  if (whh_bf && hb_ws && rec_tc_supported(S) && Kp <= rec_cl_fused_kp_max() && rec_cl_supported(S, n_batch, 0))
+    // narrow layer input (layer 1: the fbank features): the projection runs inside the cluster recurrent kernel, the
+    // [rows, 8S] pre-activation buffer is never materialised (xp only receives the saved activations)
+    return rec_cl_fwd(st, xp, whh_bf, hout, cbuf, hb_ws, lens, S, n_seq, n_batch, rs_seq, rs_batch, xb_ws, Kp, wih_bf, bias_p);
   rc = gemm_bf16_tc(st, n_rows, 8 * S, K, xb_ws, Kp, 0, wih_bf, Kp, 0, xp, 8 * S, bias_p, 0);
   if (rc) return rc;
   if (whh_bf && hb_ws && rec_tc_supported(S))   // recurrence on tensor cores

@@ -54,6 +54,7 @@ constexpr int CL_RING = 4;         // global exchange ring depth (2 would do, se
 constexpr int FW_IMG = CL_TM * 64;        // forward image: 64 rows x 32 bf16
 constexpr int BW_IMG = 2 * CL_TM * 128;   // backward image: two k-blocks of 64 rows x 64 bf16
 constexpr int BW_MAXNC = 8;
+constexpr int FW_MAXKX = 5;         // fused input projection: up to 80 input features
 constexpr int FW_WSTG = 4096 + 1024 + 1024;   // forward per-warp staging: gate tile + h tile + c tile
 
 struct RecClParams {
@@ -64,6 +65,9 @@ struct RecClParams {
   const float* dhout;        // bwd
   float* dbias;              // bwd: [8S] pre-zeroed, atomically accumulated; may be null
   uint8_t* ring;             // [CL_RING][n_cta][image bytes] exchange slots
+  const float* bias;         // fwd, fused input projection: packed gate bias [8S]
+  int nkx;                   // fwd, fused input projection: 16-column k-blocks of the layer input (ceil(Kp / 16) <= FW_MAXKX)
+  int seq_inner;             // fwd, fused input projection: tensor-map dim1 = seq (1) or batch (0)
   const int* lens;
   int S, n_seq, n_batch;
   long long rs_seq, rs_batch;
@@ -139,6 +143,22 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// K-major operand k-block of 16 bf16 (32-byte rows, 32-byte swizzle), 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t umma_desc_k32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;            // layout type SWIZZLE_32B
+  return d;
+}
 // K-major operand k-block of 32 bf16 (64-byte rows, 64-byte swizzle), 8-row groups 512 B apart
 __device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -153,10 +173,18 @@ __device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// XF: the layer's INPUT projection is fused in (layer 1: <= 80 features).  The CTA keeps its 128 x Kp slice of W_ih in smem,
+// the layer input arrives by TMA two steps ahead, and the x(t) W_ih^T MMAs are issued BEFORE the wait for the exchanged h tile
+// (they do not depend on it), so they run during the exchange: the [rows, 8S] fp32 pre-activation buffer is neither written by
+// a GEMM nor read here (2 x 1.07 GB per step at layer 1 of C4).
+template <bool XF>
 __global__ void __launch_bounds__(CL_THREADS, 1)
-rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
+rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmWx, RecClParams p) {
   constexpr int TM = CL_TM;
   constexpr int W_BLK = 128 * 128;       // 128 gate rows x 64 bf16
+  constexpr int WX_BLK = 128 * 32;       // fused projection: 128 gate rows x 16 bf16
+  constexpr int X_BLK = TM * 32;         // fused projection: TM rows x 16 bf16
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.S, KB = S / 64, NC = S / 32;                           // NC = cluster size = producers per tile
@@ -164,13 +192,17 @@ rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
   uint8_t* Asm = Wsm + KB * W_BLK;                                       // [2][NC] k-blocks of FW_IMG
   uint8_t* img = Asm + 2 * NC * FW_IMG;                                  // this CTA's outgoing image
   uint8_t* stg = img + FW_IMG;                                           // [8 epilogue warps] staging tiles of FW_WSTG bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 8 * FW_WSTG);
+  uint8_t* Wx = stg + 8 * FW_WSTG;                                       // XF: [nkx] k-blocks of WX_BLK
+  uint8_t* Xs = Wx + (XF ? FW_MAXKX * WX_BLK : 0);                       // XF: [2][nkx] k-blocks of X_BLK
+  float* bsm = reinterpret_cast<float*>(Xs + (XF ? 2 * FW_MAXKX * X_BLK : 0));   // XF: [128] gate bias slice
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + (XF ? 128 : 0));
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;           // [2]
   uint64_t* mma_done = bars + 3;
   uint64_t* tmem_free = bars + 4;
   uint64_t* stage_ready = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* x_full = bars + 6;           // [2] XF
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int slice = blockIdx.x, dir = blockIdx.y, bt = blockIdx.z;      // cluster = the NC CTAs along x
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,16 +215,22 @@ rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
     mbar_init(mma_done, 1);
     mbar_init(tmem_free, 256);
     mbar_init(stage_ready, 256);
+    mbar_init(x_full, 1);
+    mbar_init(x_full + 1, 1);
+    if (XF) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmWx); }
     fence_barrier_init();
   }
+  if (XF && threadIdx.x >= 64 && threadIdx.x < 192) bsm[threadIdx.x - 64] = p.bias[(size_t)dir * 4 * S + slice * 128 + threadIdx.x - 64];
   if (warp == 1) tmem_alloc<128>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp == 0 && elect_one()) {
-    mbar_expect_tx(w_full, KB * W_BLK);
+    mbar_expect_tx(w_full, KB * W_BLK + (XF ? p.nkx * WX_BLK : 0));
     for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * 4 * S + slice * 128);
+    if (XF)
+      for (int kx = 0; kx < p.nkx; ++kx) tma_load_3d(&tmWx, w_full, Wx + kx * WX_BLK, kx * 16, dir * 4 * S + slice * 128, 0);
     mbar_expect_tx(a_full, tile_bytes);          // h(0) and h(1); re-armed by the MMA thread after each wait
     mbar_expect_tx(a_full + 1, tile_bytes);
   }
@@ -204,6 +242,18 @@ rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
       const uint16_t cmask = (uint16_t)((1u << NC) - 1u);
       const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
       const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      // XF: the layer-input tile of step s_ -> Xs[s_ & 1] (one 16-column box per k-block)
+      auto load_x = [&](int s_) {
+        const int t_ = dir == 0 ? s_ : p.n_seq - 1 - s_;
+        uint64_t* xb = x_full + (s_ & 1);
+        mbar_expect_tx(xb, p.nkx * X_BLK);
+        for (int kx = 0; kx < p.nkx; ++kx)
+          tma_load_3d(&tmX, xb, Xs + ((s_ & 1) * FW_MAXKX + kx) * X_BLK, kx * 16, p.seq_inner ? t_ : bt * TM, p.seq_inner ? bt * TM : t_);
+      };
+      if (XF) {
+        load_x(0);
+        if (p.n_seq > 1) load_x(1);
+      }
       for (int s = 0; s + 1 < p.n_seq; ++s) {
         uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * FW_IMG;
         mbar_wait_t(stage_ready, s & 1);                           // all 256 epilogue threads have written the image
@@ -212,6 +262,7 @@ rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
         CL_STAMP(9);
         bulk_load_mc(Asm + ((s & 1) * NC + slice) * FW_IMG, slot, FW_IMG, a_full + (s & 1), cmask);
         CL_STAMP(6);
+        if (XF && s + 2 < p.n_seq) load_x(s + 2);                  // the MMAs of step s (reading Xs[s & 1]) completed before its epilogue
       }
     }
     __syncwarp();
@@ -220,20 +271,31 @@ rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(TM, 128);
       const int nk = S / 16;
-      for (int s = 1; s < p.n_seq; ++s) {
-        const int b = (s - 1) & 1;
-        if (s == 1) mbar_wait_t(w_full, 0);
-        mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // all NC slices of h(s-1) have landed
-        if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
-        if (s > 1) mbar_wait_t(tmem_free, (s - 2) & 1);            // epilogue has drained the accumulator
-        CL_STAMP(1);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(Asm + b * NC * FW_IMG), w0 = smem_u32(Wsm);
+      for (int s = XF ? 0 : 1; s < p.n_seq; ++s) {
+        if (s == (XF ? 0 : 1)) mbar_wait_t(w_full, 0);
+        if (XF) {
+          // input projection of step s: independent of the recurrence, issued (and executing) while h(s-1) is exchanged
+          if (s > 0) mbar_wait_t(tmem_free, (s - 1) & 1);          // epilogue has drained the accumulator
+          mbar_wait_t(x_full + (s & 1), (s >> 1) & 1);
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(Xs + (s & 1) * FW_MAXKX * X_BLK), wx0 = smem_u32(Wx);
+          for (int kx = 0; kx < p.nkx; ++kx)
+            mma_bf16_ss(tmem, umma_desc_k32(x0 + kx * X_BLK), umma_desc_k32(wx0 + kx * WX_BLK), idesc, kx != 0);
+        }
+        if (s > 0) {
+          const int b = (s - 1) & 1;
+          mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // all NC slices of h(s-1) have landed
+          if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
+          if (!XF && s > 1) mbar_wait_t(tmem_free, (s - 2) & 1);     // epilogue has drained the accumulator
+          CL_STAMP(1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(Asm + b * NC * FW_IMG), w0 = smem_u32(Wsm);
 #pragma unroll 4
-        for (int kk = 0; kk < nk; ++kk) {
-          const uint64_t da = umma_desc_k64(a0 + (kk >> 1) * FW_IMG) + (uint64_t)((kk & 1) * 2);
-          const uint64_t db = umma_desc_k128(w0 + (kk >> 2) * W_BLK) + (uint64_t)((kk & 3) * 2);
-          mma_bf16_ss(tmem, da, db, idesc, kk != 0);
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint64_t da = umma_desc_k64(a0 + (kk >> 1) * FW_IMG) + (uint64_t)((kk & 1) * 2);
+            const uint64_t db = umma_desc_k128(w0 + (kk >> 2) * W_BLK) + (uint64_t)((kk & 3) * 2);
+            mma_bf16_ss(tmem, da, db, idesc, (XF || kk != 0) ? 1u : 0u);
+          }
         }
         mma_commit(mma_done);
         CL_STAMP(2);
@@ -278,20 +340,26 @@ rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
       }
       cp_async_commit();
     };
-    prefetch_g(dir == 0 ? 0 : p.n_seq - 1);
+    if (!XF) prefetch_g(dir == 0 ? 0 : p.n_seq - 1);
 
     for (int s = 0; s < p.n_seq; ++s) {
       const int t = dir == 0 ? s : p.n_seq - 1 - s;
       const bool valid = in_range && t < len;
       float4 g[8];                                 // pre-activations of this lane's 8 units (i,f,g,o each)
-      cp_async_wait_all();
-      __syncwarp();
+      if (XF) {                                    // the projection comes out of the accumulator: start from the bias
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        g[j] = valid ? *reinterpret_cast<const float4*>(gs + l16 * 64 + (((uh * 8 + j) ^ l16) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (s > 0) {
+        for (int j = 0; j < 8; ++j)
+          g[j] = valid ? *reinterpret_cast<const float4*>(bsm + (hh * 16 + uh * 8 + j) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        cp_async_wait_all();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          g[j] = valid ? *reinterpret_cast<const float4*>(gs + l16 * 64 + (((uh * 8 + j) ^ l16) << 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (XF || s > 0) {
         uint32_t v[32];
-        mbar_wait_t(mma_done, (s - 1) & 1);
+        mbar_wait_t(mma_done, XF ? (s & 1) : ((s - 1) & 1));
         if (threadIdx.x == 64) CL_STAMP(3);
         tc_fence_after();
         const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
@@ -378,7 +446,7 @@ rec_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecClParams p) {
         }
       }
       __syncwarp();                                // staging tiles drained
-      if (s + 1 < p.n_seq) prefetch_g(dir == 0 ? s + 1 : p.n_seq - 2 - s);
+      if (!XF && s + 1 < p.n_seq) prefetch_g(dir == 0 ? s + 1 : p.n_seq - 2 - s);
       if (threadIdx.x == 64) CL_STAMP(7);
     }
   }
@@ -673,8 +741,9 @@ static int cluster_launch(Kern kern, dim3 grid, int cluster_x, size_t smem, cuda
   return 0;
 }
 
-static size_t fwd_smem(int S) {
-  return (size_t)(S / 64) * 16384 + (size_t)2 * CL_TM * S * 2 + FW_IMG + 8 * FW_WSTG + 7 * 8 + 16 + 1024;
+static size_t fwd_smem(int S, bool xf = false) {
+  return (size_t)(S / 64) * 16384 + (size_t)2 * CL_TM * S * 2 + FW_IMG + 8 * FW_WSTG + 8 * 8 + 16 + 1024 +
+         (xf ? (size_t)FW_MAXKX * 4096 + 2 * FW_MAXKX * CL_TM * 32 + 512 : 0);
 }
 static size_t bwd_smem(int S) {
   return (size_t)CL_TM * 4 * S * 2 + (size_t)(S / 16) * 4096 + 8 * 4096 + (6 + BW_MAXNC) * 8 + 16 + 1024;
@@ -742,7 +811,9 @@ int rec_cl_supported(int S, int n_batch, int backward) {
   if (g_cap[w][idx] < 0) {
     int nc = 0;
     const int rc = backward ? prepare(rec_cl_bwd_kernel, S / CL_UNITS, bwd_smem(S), bwd_smem(256), &nc)
-                            : prepare(rec_cl_fwd_kernel, S / CL_UNITS, fwd_smem(S), fwd_smem(256), &nc);
+                            : prepare(rec_cl_fwd_kernel<false>, S / CL_UNITS, fwd_smem(S), fwd_smem(256), &nc);
+    if (!backward && !rc)
+      SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_cl_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(256, true)));
     g_cap[w][idx] = rc ? 0 : nc;
   }
   const int tiles = (n_batch + CL_TM - 1) / CL_TM;
@@ -758,21 +829,42 @@ int rec_cl_capacity(int S, int backward) {
   return g_cap[backward ? 1 : 0][S / 64];
 }
 
+// x_bf / wih_bf / bias non-null: the input projection is fused in (x_bf [rows, Kp] bf16, wih_bf [8S, Kp] bf16, bias [8S]);
+// xp then is an output only (saved activations).  Otherwise xp holds the pre-activations computed by the batched GEMM.
 int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
-               int n_seq, int n_batch, long long rs_seq, long long rs_batch) {
+               int n_seq, int n_batch, long long rs_seq, long long rs_batch, const void* x_bf, int Kp, const void* wih_bf,
+               const float* bias) {
   RecClParams p = {};
   p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.lens = lens;
   p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
   p.dbg = g_cl_dbg;
   p.ring = ring_for(st);
   SSASR_REQUIRE(p.ring != nullptr, "rec_cl_fwd: cannot allocate the exchange ring");
-  CUtensorMap tmW;
+  CUtensorMap tmW, tmX, tmWx;
   int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 128);
   if (rc) return rc;
   dim3 grid(S / CL_UNITS, 2, (n_batch + CL_TM - 1) / CL_TM);
+  const bool xf = x_bf && wih_bf && bias;
+  if (!xf) {
+    ProfScope ps(F_REC_TC_FWD, st);
+    return cluster_launch(rec_cl_fwd_kernel<false>, grid, S / CL_UNITS, fwd_smem(S), st, tmW, tmW, tmW, p);
+  }
+  SSASR_REQUIRE(Kp % 8 == 0 && Kp > 0 && Kp <= 16 * FW_MAXKX, "rec_cl_fwd: fused input projection needs Kp %% 8 == 0 and Kp <= %d (got %d)",
+                16 * FW_MAXKX, Kp);
+  p.bias = bias;
+  p.nkx = (Kp + 15) / 16;
+  p.seq_inner = rs_seq < rs_batch ? 1 : 0;
+  rc = p.seq_inner ? make_tmap_bf16_3d_ex(&tmX, x_bf, Kp, n_seq, rs_seq * Kp, n_batch, rs_batch * Kp, 16, 1, CL_TM, 32)
+                   : make_tmap_bf16_3d_ex(&tmX, x_bf, Kp, n_batch, rs_batch * Kp, n_seq, rs_seq * Kp, 16, CL_TM, 1, 32);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d_ex(&tmWx, wih_bf, Kp, 8 * S, Kp, 1, (long long)8 * S * Kp, 16, 128, 1, 32);
+  if (rc) return rc;
   ProfScope ps(F_REC_TC_FWD, st);
-  return cluster_launch(rec_cl_fwd_kernel, grid, S / CL_UNITS, fwd_smem(S), st, tmW, p);
+  return cluster_launch(rec_cl_fwd_kernel<true>, grid, S / CL_UNITS, fwd_smem(S, true), st, tmW, tmX, tmWx, p);
 }
+
+// largest padded input width the fused forward projection accepts
+int rec_cl_fused_kp_max() { return 16 * FW_MAXKX; }
 
 int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
                int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias) {
