@@ -223,6 +223,8 @@ def run_ours(args):
     from ss_asr_b200.optim import FusedAdadelta
     optim = FusedAdadelta(model.parameters(), lr=1.0, eps=1e-8)     # torch.optim.Adadelta + Solver.step fused on the device
     sync = GradSync(model, world)
+    from ss_asr_b200 import functional as Fk
+    Fk.set_overlap_wgrad(True)     # encoder weight-gradient GEMMs on a second stream under the next layer's recurrent kernel
     x, lens, y = synth_batch(B, T, F, U, seed=1234 + rank)
     ans_len = int(max((y != 0).sum(-1) + 1)) - 1
     x_host, y_host = x.pin_memory(), y.pin_memory()

@@ -92,7 +92,9 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf 
                          void* hb_saved /*[n_rows,2S] bf16 h of the forward pass (masked in place), or NULL;
                                           with both set the weight gradients use the MN-major GEMM and dgT/xT/hT_ws
                                           may be NULL*/,
-                         void* stream);
+                         void* stream,
+                         void* wgrad_stream /*NULL, or a second stream for the weight-gradient GEMMs: the caller joins it
+                                              before reading dwih_p / dwhh_p*/);
 
 /* ---- attend-and-spell loop: Attention.forward asr.py:343-392 + Speller.forward asr.py:314-326 + the decode loop
  *      of ASR.forward asr.py:65-110 (teacher forcing / greedy / sampled), all U steps on the device ---- */

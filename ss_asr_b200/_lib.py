@@ -59,7 +59,7 @@ SIGNATURES = {
     'ssasr_cvt_bf16_t': (_I, [_P, _LL, _P, _LL, _LL, _I, _I, _I, _I, _I, _P]),
     'ssasr_blstm_fwd_bf16': (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_blstm_bwd_bf16': (_I, [_P, _I, _I, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                  _I, _LL, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+                                  _I, _LL, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     'ssasr_speller_fwd_f32': (_I, [C.POINTER(SpellerFwdArgs), _P]),
     'ssasr_speller_bwd_f32': (_I, [C.POINTER(SpellerBwdArgs), _P]),
     'ssasr_attn_step_fwd': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

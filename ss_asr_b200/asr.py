@@ -226,6 +226,7 @@ class ASR(nn.Module):
 
     def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
         """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
+        Fk.join_deferred()
         use_bf16 = self.train_precision == 'bf16' and self.training and torch.is_grad_enabled() and teacher is not None
         self.encoder.set_precision('bf16' if use_bf16 else 'fp32')
         try:

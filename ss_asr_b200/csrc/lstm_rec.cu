@@ -15,6 +15,8 @@
 // through L2 (the output tensor itself) and the CTAs of one direction meet at a per-direction
 // monotonic-counter barrier once per step.  No per-step launches, no pack/unpack copies: lengths
 // are masks.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include <cuda_bf16.h>
 
@@ -569,7 +571,8 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
                          int n_batch, long long rs_seq, long long rs_batch, const int* lens, float* act, const float* hout,
                          const float* cbuf, const float* dhout, float* dx, float* dwih_p, float* dbias_p, float* dwhh_p,
                          float* dcstate, unsigned* bar, int zero_period, long long Rp, void* dgb_ws, void* dgT_ws, void* xT_ws,
-                         void* hT_ws, const void* whhT_bf, const void* xb_saved, int Kp, void* hb_saved, void* stream) {
+                         void* hT_ws, const void* whhT_bf, const void* xb_saved, int Kp, void* hb_saved, void* stream,
+                         void* wgrad_stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(Rp % 8 == 0 && Rp >= n_rows, "blstm_bwd_bf16: bad Rp=%lld (n_rows=%d)", Rp, n_rows);
   int rc;
@@ -606,6 +609,22 @@ int ssasr_blstm_bwd_bf16(const float* x, int n_rows, int K, const void* wihT_bf,
     if (rc) return rc;
   }
   const int sh = (int)rs_seq;
+  // The weight gradients are not needed before the optimiser: on request they run on a second stream, ordered after
+  // everything enqueued so far, so that they overlap the NEXT layer's recurrent kernel (which occupies 64 of the 148 SMs).
+  // The caller joins that stream before it consumes dwih_p / dwhh_p (see functional.join_deferred).
+  if (wgrad_stream && tc_rec && xb_saved && hb_saved && Kp % 8 == 0) {
+    static cudaEvent_t evs[32];
+    static int ev_i = -1;
+    if (ev_i < 0) {
+      for (int i = 0; i < 32; ++i) SSASR_CHECK_CUDA(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
+      ev_i = 0;
+    }
+    cudaEvent_t ev = evs[ev_i];
+    ev_i = (ev_i + 1) & 31;
+    SSASR_CHECK_CUDA(cudaEventRecord(ev, st));
+    st = (cudaStream_t)wgrad_stream;
+    SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  }
   if (tc_rec && xb_saved && hb_saved && Kp % 8 == 0) {
     // weight gradients straight from the row-major bf16 buffers (MN-major tcgen05 operands): no transposed copies.
     // dgb_ws holds the complete bf16 dG (exchange buffer of the recurrent kernel), xb_saved / hb_saved the bf16 x and h

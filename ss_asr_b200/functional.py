@@ -19,6 +19,42 @@ def _f32c(t):
 # --------------------------------------------------------------------------------------------------
 # bidirectional LSTM layer
 # --------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------
+# Deferred weight gradients.  The encoder's weight-gradient GEMMs (dW_ih, dW_hh) and their un-packing are not needed
+# before the optimiser, while the next layer's recurrent backward kernel is latency-bound and occupies 64 of the 148
+# SMs.  With `set_overlap_wgrad(True)` they are enqueued on a second stream (ordered after everything the layer's backward
+# has launched) and `join_deferred()` makes the current stream wait for them.  OPT-IN: whoever reads `param.grad` must join
+# first -- FusedAdadelta.step_clipped, GradSync and ASR.forward do; torch's own clip_grad_norm_ / optimisers do not.
+# --------------------------------------------------------------------------------------------------
+_OVERLAP = {'on': False, 'streams': {}, 'pending': []}
+
+
+def set_overlap_wgrad(on):
+    join_deferred()
+    _OVERLAP['on'] = bool(on)
+
+
+def overlap_wgrad_enabled():
+    return _OVERLAP['on']
+
+
+def side_stream(device):
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _OVERLAP['streams']:
+        _OVERLAP['streams'][key] = torch.cuda.Stream(device)
+    return _OVERLAP['streams'][key]
+
+
+def join_deferred():
+    """The current stream waits for every deferred weight-gradient computation; their workspaces are released."""
+    if _OVERLAP['pending']:
+        cur = torch.cuda.current_stream()
+        for ev, _keep in _OVERLAP['pending']:
+            cur.wait_event(ev)
+        _OVERLAP['pending'] = []
+
+
 class _BLSTM(torch.autograd.Function):
     """One bidirectional LSTM layer over rows indexed (seq, batch) -- see ssasr_blstm_fwd_f32.
 
@@ -40,6 +76,7 @@ class _BLSTM(torch.autograd.Function):
         bias_p = torch.empty(8 * S, device=dev)
         whh_p = torch.empty(2, 4 * S, S, device=dev)
         whhT_p = torch.empty(2, S, 4 * S, device=dev)
+        ctx.param_refs = (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         ws = [_f32c(w) for w in (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
         check(lib.ssasr_pack_blstm(*[ptr(w) for w in ws], S, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), ptr(whhT_p), st),
               'ssasr_pack_blstm')
@@ -113,12 +150,31 @@ class _BLSTM(torch.autograd.Function):
             ws = [bf(n_rows, 8 * S) if (ctx.need_dx or tc_rec) else None] + \
                 ([None, None, None] if direct else [bf(8 * S, Rp), bf(K, Rp), bf(2 * S, Rp)])
             xb_s, hb_s, Kp_s = ctx.fwd_bf if direct else (None, None, 0)
+            # deferring is only safe when autograd will ADOPT the returned buffers (fresh .grad, i.e. zero_grad(set_to_none=True)):
+            # accumulating into an existing .grad would read them on the main stream before the side stream has written them
+            fresh = all(getattr(w, 'grad', None) is None for w in ctx.param_refs)
+            side = side_stream(dev) if (direct and _OVERLAP['on'] and fresh) else None
+            # gradient outputs are zero-filled on the main stream BEFORE the call, so the fill is ordered before the side stream
+            g = [torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev), torch.zeros(4 * S, device=dev),
+                 torch.zeros(4 * S, device=dev), torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev),
+                 torch.zeros(4 * S, device=dev), torch.zeros(4 * S, device=dev)]
             check(lib.ssasr_blstm_bwd_bf16(ptr(x), n_rows, K, ptr(wihT_bf), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
                                            ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf),
                                            ptr(dhout), ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
                                            d1 if time_major else 0, Rp, ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]),
-                                           ptr(whhT_bf), ptr(xb_s), Kp_s, ptr(hb_s), st), 'ssasr_blstm_bwd_bf16')
+                                           ptr(whhT_bf), ptr(xb_s), Kp_s, ptr(hb_s), st, side.cuda_stream if side else None),
+                  'ssasr_blstm_bwd_bf16')
             ctx.fwd_bf = None
+            ust = side.cuda_stream if side else st
+            check(lib.ssasr_unpack_blstm_grads(ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), S, K, *[ptr(t) for t in g], ust),
+                  'ssasr_unpack_blstm_grads')
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                # NOT `g`: AccumulateGrad only adopts a gradient buffer it holds the sole reference to (otherwise it clones it --
+                # on the main stream, before the side stream has written it)
+                _OVERLAP['pending'].append((ev, (ws, xb_s, hb_s, dwih_p, dbias_p, dwhh_p, wihT_bf, whhT_bf)))
+            return (dx, None, None, None) + tuple(g)
         else:
             check(lib.ssasr_blstm_bwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
                                           ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf), ptr(dhout),

@@ -31,6 +31,8 @@ class FusedAdadelta(torch.optim.Adadelta):
     @torch.no_grad()
     def step_clipped(self, max_norm=None, write_clipped_grads=False):
         """One fused Solver.step.  max_norm None / <= 0: no clipping.  Returns the device tensor of the total gradient norm."""
+        from . import functional as _F
+        _F.join_deferred()                   # deferred weight gradients (functional.set_overlap_wgrad) must have landed
         lib = _lib.load()
         entries, keep = [], []
         dev = None

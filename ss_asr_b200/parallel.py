@@ -42,8 +42,18 @@ class GradSync:
         return hook
 
     def _launch(self, bucket):
-        flat = torch.cat([p.grad.reshape(-1) for p in bucket['params']])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        from . import functional as Fk
+        if Fk.overlap_wgrad_enabled() and bucket['params'][0].is_cuda:
+            # the bucket's gradients may still be in flight on the deferred weight-gradient stream: gather and reduce THERE
+            # (ordered after them) instead of making the main stream -- and with it the rest of the backward pass -- wait
+            side = Fk.side_stream(bucket['params'][0].device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                flat = torch.cat([p.grad.reshape(-1) for p in bucket['params']])
+                work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            flat = torch.cat([p.grad.reshape(-1) for p in bucket['params']])
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.pending.append((bucket, flat, work))
 
     def backward(self, loss):
@@ -54,6 +64,8 @@ class GradSync:
         loss.backward()
         if self.world <= 1:
             return
+        from . import functional as Fk
+        Fk.join_deferred()
         for b in self.buckets.values():          # parameters that received no gradient this step
             if 0 < b['ready'] < len(b['params']) or (b['ready'] == 0 and any(p.grad is not None for p in b['params'])):
                 for p in b['params']:

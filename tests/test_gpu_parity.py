@@ -561,3 +561,40 @@ def test_fused_adadelta_clip_step_matches_torch():
     # state_dict round trip into torch.optim.Adadelta
     ref2 = torch.optim.Adadelta(our_p, lr=1.0, eps=1e-8)
     ref2.load_state_dict(ours.state_dict())
+
+
+def test_deferred_weight_gradients_match():
+    """functional.set_overlap_wgrad: encoder weight-gradient GEMMs on a second stream, joined by the consumers
+    (FusedAdadelta.step_clipped / join_deferred).  Same gradients and same parameter update as the in-order schedule."""
+    from ss_asr_b200 import functional as Fk
+    from ss_asr_b200.functional import asr_loss
+    from ss_asr_b200.optim import FusedAdadelta
+    dims = (50, 64, 64, 32, 40)
+    sd = O.make_state_dict(*dims, seed=1)
+    x, lens, y = O.synth_batch(70, 64, dims[4], 6, seed=21)
+    out = {}
+    try:
+        for on in (False, True):
+            Fk.set_overlap_wgrad(on)
+            m = _model(dims, sd)
+            m.train_precision = 'bf16'
+            m.train()
+            opt = FusedAdadelta(m.parameters(), lr=1.0, eps=1e-8)
+            for _ in range(2):
+                opt.zero_grad(set_to_none=True)
+                _, logits, _ = m(x.to(DEV), 7, teacher=y.to(DEV), state_len=lens)
+                asr_loss(logits, y.to(DEV)).backward()
+                if on:
+                    assert len(Fk._OVERLAP['pending']) == 4          # one deferred batch per encoder layer
+                Fk.join_deferred()
+                grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+                opt.step_clipped(5.0)
+            torch.cuda.synchronize()
+            out[on] = (grads, {k: p.detach().clone() for k, p in m.named_parameters()})
+    finally:
+        Fk.set_overlap_wgrad(False)
+    for k in out[False][0]:
+        a, b = out[True][0][k], out[False][0][k]
+        assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-7, k
+        a, b = out[True][1][k], out[False][1][k]
+        assert float((a - b).abs().max()) <= 1e-4 * (1e-3 + float(b.abs().max())), k
