@@ -430,6 +430,11 @@ def run_extras(model, dev, args, peaks, shard=(0, 1), dist=None):
     ms2 = tmax(e0.elapsed_time(e1))
     out['decode']['utt_per_s_tf32x3'] = n_total / (ms2 / 1e3)
     out['decode']['tf32x3_identical_transcripts'] = sum(a == b for a, b in zip(ids, ids2)) / max(1, len(ids))
+    # headline decode figure: the fastest path whose transcripts are identical to the fp32 SIMT path in this very run
+    out['decode']['utt_per_s_fp32_simt'] = out['decode']['utt_per_s']
+    if out['decode']['tf32x3_identical_transcripts'] == 1.0 and ms2 < ms:
+        out['decode'].update(utt_per_s=n_total / (ms2 / 1e3), ms=ms2, chars_per_s=sum(len(i) for i in ids2) * world / (ms2 / 1e3),
+                             precision='tf32x3 / bf16x3 tensor-core exact path (transcripts identical to the fp32 SIMT path)')
     if rank == 0 and world == 1:
         # secondary: same utterances with the (randomly initialised, as in ASRTester) CharLM at lm_weight 0.5
         import torch.nn as nn
