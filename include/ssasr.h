@@ -32,6 +32,15 @@ int ssasr_pack_blstm(const float* w_ih_f, const float* w_hh_f, const float* b_ih
                      const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r, int S, int K,
                      float* wih_p /*[8S,K]*/, float* bias_p /*[8S]*/, float* whh_p /*[2,4S,S]*/,
                      float* whhT_p /*[2,S,4S] or NULL*/, void* stream);
+/* bf16 training path: the same packing straight to the bf16 operands of the tensor-core kernels, one launch:
+ * bias_p [8S] fp32, wih_bf [8S,Kp] (Kp = K rounded up to 8, zero-padded), whh_bf [8S,S], wihT_bf [K,8S], whhT_bf [2S,4S] */
+int ssasr_pack_blstm_bf16(const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+                          const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r, int S, int K, int Kp,
+                          float* bias_p, void* wih_bf, void* whh_bf, void* wihT_bf, void* whhT_bf, void* stream);
+/* like ssasr_unpack_blstm_grads but WRITES the eight gradients (no zero-fill needed), one launch */
+int ssasr_unpack_blstm_grads_set(const float* dwih_p, const float* dbias_p, const float* dwhh_p, int S, int K, float* g_w_ih_f,
+                                 float* g_w_hh_f, float* g_b_ih_f, float* g_b_hh_f, float* g_w_ih_r, float* g_w_hh_r,
+                                 float* g_b_ih_r, float* g_b_hh_r, void* stream);
 int ssasr_unpack_blstm_grads(const float* dwih_p, const float* dbias_p, const float* dwhh_p, int S, int K,
                              float* g_w_ih_f, float* g_w_hh_f, float* g_b_ih_f, float* g_b_hh_f, float* g_w_ih_r,
                              float* g_w_hh_r, float* g_b_ih_r, float* g_b_hh_r, void* stream);

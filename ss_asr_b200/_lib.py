@@ -47,6 +47,8 @@ SIGNATURES = {
     'ssasr_gemm_f32': (_I, [_I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P]),
     'ssasr_pack_blstm': (_I, [_P] * 8 + [_I, _I] + [_P] * 5),
     'ssasr_unpack_blstm_grads': (_I, [_P] * 3 + [_I, _I] + [_P] * 9),
+    'ssasr_pack_blstm_bf16': (_I, [_P] * 8 + [_I, _I, _I] + [_P] * 6),
+    'ssasr_unpack_blstm_grads_set': (_I, [_P] * 3 + [_I, _I] + [_P] * 9),
     'ssasr_pack_lstmcell': (_I, [_P] * 4 + [_I, _I] + [_P] * 3),
     'ssasr_unpack_lstmcell_grads': (_I, [_P, _P, _I, _I] + [_P] * 5),
     'ssasr_blstm_fwd_f32': (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -333,6 +333,81 @@ int colsum(cudaStream_t st, const float* src, float* out, int R, int C, int ld, 
   return 0;
 }
 
+// ---- bf16 training path: every packed operand of one BLSTM layer in ONE launch (was: 8 pack launches + 4 conversions) -----
+// blocks [0, nt_ih): 32 x 32 tiles of W_ih -> wih_bf [8S,Kp] (packed rows, zero-padded columns) and wihT_bf [K,8S];
+// blocks [nt_ih, nt_ih + nt_hh): tiles of W_hh -> whh_bf [8S,S] and whhT_bf [2S,4S]; the remaining blocks: bias_p = b_ih + b_hh.
+struct PackBf16 {
+  const float* wih[2]; const float* whh[2]; const float* bih[2]; const float* bhh[2];
+  int S, K, Kp, nt_ih, nt_hh;
+  float* bias_p; __nv_bfloat16 *wih_bf, *whh_bf, *wihT_bf, *whhT_bf;
+};
+__global__ void __launch_bounds__(256) pack_blstm_bf16_kernel(PackBf16 a) {
+  __shared__ float tile[32][33];
+  const int S = a.S, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8 threads
+  int b = blockIdx.x;
+  if (b < a.nt_ih + a.nt_hh) {
+    const bool ih = b < a.nt_ih;
+    if (!ih) b -= a.nt_ih;
+    const int C = ih ? a.K : S;                        // source columns
+    const int ct = ih ? (a.Kp + 31) / 32 : (S + 31) / 32;
+    const int c0 = (b % ct) * 32, pr0 = (b / ct) * 32; // packed-row tile never straddles a direction (4S % 32 == 0)
+    const int d = pr0 / (4 * S);
+    const float* src = ih ? a.wih[d] : a.whh[d];
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+      const int r4 = (pr0 + i) % (4 * S), u = r4 >> 2, g = r4 & 3, c = c0 + tx;
+      const float v = c < C ? src[((size_t)g * S + u) * C + c] : 0.f;
+      tile[i][tx] = v;
+      if (ih) { if (c < a.Kp) a.wih_bf[(size_t)(pr0 + i) * a.Kp + c] = __float2bfloat16(v); }
+      else if (c < S) a.whh_bf[(size_t)(pr0 + i) * S + c] = __float2bfloat16(v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {                 // transposed copies: column c0 + i, packed rows pr0 + tx
+      const int c = c0 + i;
+      if (c >= C) continue;
+      const __nv_bfloat16 v = __float2bfloat16(tile[tx][i]);
+      if (ih) a.wihT_bf[(size_t)c * 8 * S + pr0 + tx] = v;
+      else a.whhT_bf[((size_t)d * S + c) * 4 * S + (pr0 % (4 * S)) + tx] = v;
+    }
+  } else {
+    const int i = (b - a.nt_ih - a.nt_hh) * 256 + threadIdx.x;
+    if (i < 8 * S) {
+      const int d = i / (4 * S), r4 = i % (4 * S), u = r4 >> 2, g = r4 & 3;
+      a.bias_p[i] = a.bih[d][g * S + u] + a.bhh[d][g * S + u];
+    }
+  }
+}
+
+// all eight PyTorch-layout gradients of one BLSTM layer WRITTEN (not added) in one launch
+struct UnpackSet {
+  const float *dwih_p, *dbias_p, *dwhh_p;
+  float* gwih[2]; float* gwhh[2]; float* gbih[2]; float* gbhh[2];
+  int S, K;
+};
+__global__ void __launch_bounds__(256) unpack_blstm_set_kernel(UnpackSet a) {
+  const int S = a.S, K = a.K;
+  const size_t n_ih = (size_t)8 * S * K, n_hh = (size_t)8 * S * S, total = n_ih + n_hh + 8 * S;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < n_ih + n_hh) {
+      const bool ih = i < n_ih;
+      const size_t j = ih ? i : i - n_ih;
+      const int C = ih ? K : S;
+      const int c = (int)(j % C);
+      const int row = (int)(j / C);                    // destination row: d*4S + g*S + u
+      const int d = row / (4 * S), rg = row % (4 * S), g = rg / S, u = rg % S;
+      const float v = (ih ? a.dwih_p : a.dwhh_p)[((size_t)d * 4 * S + u * 4 + g) * C + c];
+      (ih ? a.gwih[d] : a.gwhh[d])[(size_t)rg * C + c] = v;
+    } else {
+      const int r = (int)(i - n_ih - n_hh);
+      const int d = r / (4 * S), rg = r % (4 * S), g = rg / S, u = rg % S;
+      const float v = a.dbias_p[d * 4 * S + u * 4 + g];
+      a.gbih[d][rg] = v;
+      a.gbhh[d][rg] = v;
+    }
+  }
+}
+
 static int pick_upc(int S) {
   // smallest UPC in {4, 8} such that both directions fit co-resident on the device
   if (2 * (S / 4) <= sm_count()) return 4;
@@ -411,6 +486,45 @@ int ssasr_unpack_blstm_grads(const float* dwih_p, const float* dbias_p, const fl
     unpack_rows_add_kernel<<<256, 256, 0, st>>>(dwhh_p + (size_t)d * 4 * S * S, gwhh[d], S, S, S, 0);
     unpack_bias_add_kernel<<<(4 * S + 255) / 256, 256, 0, st>>>(dbias_p + (size_t)d * 4 * S, gbih[d], gbhh[d], S);
   }
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+// bf16 training path: bias_p [8S] fp32, wih_bf [8S,Kp], whh_bf [8S,S], wihT_bf [K,8S], whhT_bf [2S,4S] (all bf16) in one launch
+int ssasr_pack_blstm_bf16(const float* w_ih_f, const float* w_hh_f, const float* b_ih_f, const float* b_hh_f,
+                          const float* w_ih_r, const float* w_hh_r, const float* b_ih_r, const float* b_hh_r, int S, int K, int Kp,
+                          float* bias_p, void* wih_bf, void* whh_bf, void* wihT_bf, void* whhT_bf, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  SSASR_REQUIRE(S > 0 && S % 8 == 0 && Kp >= K && Kp % 8 == 0, "pack_blstm_bf16: bad S=%d / K=%d / Kp=%d", S, K, Kp);
+  PackBf16 a;
+  a.wih[0] = w_ih_f; a.wih[1] = w_ih_r; a.whh[0] = w_hh_f; a.whh[1] = w_hh_r;
+  a.bih[0] = b_ih_f; a.bih[1] = b_ih_r; a.bhh[0] = b_hh_f; a.bhh[1] = b_hh_r;
+  a.S = S; a.K = K; a.Kp = Kp;
+  a.nt_ih = ((Kp + 31) / 32) * (8 * S / 32);
+  a.nt_hh = ((S + 31) / 32) * (8 * S / 32);
+  a.bias_p = bias_p;
+  a.wih_bf = (__nv_bfloat16*)wih_bf; a.whh_bf = (__nv_bfloat16*)whh_bf;
+  a.wihT_bf = (__nv_bfloat16*)wihT_bf; a.whhT_bf = (__nv_bfloat16*)whhT_bf;
+  ProfScope ps(F_PACK, st);
+  pack_blstm_bf16_kernel<<<a.nt_ih + a.nt_hh + (8 * S + 255) / 256, 256, 0, st>>>(a);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
+// Writes (does not add) the eight PyTorch-layout gradients of one BLSTM from the packed-layout ones, in one launch.
+int ssasr_unpack_blstm_grads_set(const float* dwih_p, const float* dbias_p, const float* dwhh_p, int S, int K, float* g_w_ih_f,
+                                 float* g_w_hh_f, float* g_b_ih_f, float* g_b_hh_f, float* g_w_ih_r, float* g_w_hh_r,
+                                 float* g_b_ih_r, float* g_b_hh_r, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UnpackSet a;
+  a.dwih_p = dwih_p; a.dbias_p = dbias_p; a.dwhh_p = dwhh_p;
+  a.gwih[0] = g_w_ih_f; a.gwih[1] = g_w_ih_r; a.gwhh[0] = g_w_hh_f; a.gwhh[1] = g_w_hh_r;
+  a.gbih[0] = g_b_ih_f; a.gbih[1] = g_b_ih_r; a.gbhh[0] = g_b_hh_f; a.gbhh[1] = g_b_hh_r;
+  a.S = S; a.K = K;
+  const size_t total = (size_t)8 * S * (K + S + 1);
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  ProfScope ps(F_PACK, st);
+  unpack_blstm_set_kernel<<<blocks, 256, 0, st>>>(a);
   SSASR_LAUNCH_CHECK();
   return 0;
 }

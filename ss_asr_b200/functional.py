@@ -72,14 +72,25 @@ class _BLSTM(torch.autograd.Function):
         dev = x.device
         n_rows = d0 * d1
         st = stream()
-        wih_p = torch.empty(8 * S, K, device=dev)
-        bias_p = torch.empty(8 * S, device=dev)
-        whh_p = torch.empty(2, 4 * S, S, device=dev)
-        whhT_p = torch.empty(2, S, 4 * S, device=dev)
+        bf16 = precision == 'bf16'
+        tc_rec = bf16 and S % 64 == 0 and S <= 512 and _TC_RECURRENCE
         ctx.param_refs = (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
         ws = [_f32c(w) for w in (w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r)]
-        check(lib.ssasr_pack_blstm(*[ptr(w) for w in ws], S, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), ptr(whhT_p), st),
-              'ssasr_pack_blstm')
+        bias_p = torch.empty(8 * S, device=dev)
+        wih_p = whh_p = whhT_p = wih_bf = whh_bf = wihT_bf = whhT_bf = None
+        Kp = (K + 7) // 8 * 8
+        if tc_rec:
+            # tensor-core path: every packed bf16 operand of the layer (forward and backward) in ONE launch
+            bfe = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.bfloat16)
+            wih_bf, whh_bf, wihT_bf, whhT_bf = bfe(8 * S, Kp), bfe(8 * S, S), bfe(K, 8 * S), bfe(2 * S, 4 * S)
+            check(lib.ssasr_pack_blstm_bf16(*[ptr(w) for w in ws], S, K, Kp, ptr(bias_p), ptr(wih_bf), ptr(whh_bf), ptr(wihT_bf),
+                                            ptr(whhT_bf), st), 'ssasr_pack_blstm_bf16')
+        else:
+            wih_p = torch.empty(8 * S, K, device=dev)
+            whh_p = torch.empty(2, 4 * S, S, device=dev)
+            whhT_p = torch.empty(2, S, 4 * S, device=dev)
+            check(lib.ssasr_pack_blstm(*[ptr(w) for w in ws], S, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), ptr(whhT_p), st),
+                  'ssasr_pack_blstm')
         xp = torch.empty(n_rows, 8 * S, device=dev)
         hout = torch.empty(d0, d1, 2 * S, device=dev)
         cbuf = torch.empty(d0, d1, 2 * S, device=dev)
@@ -88,19 +99,15 @@ class _BLSTM(torch.autograd.Function):
             n_seq, n_batch, rs_seq, rs_batch = d1, d0, 1, d1
         else:
             n_seq, n_batch, rs_seq, rs_batch = d0, d1, d1, 1
-        bf16 = precision == 'bf16'
         if bf16:
-            Kp = (K + 7) // 8 * 8
-            wih_bf = torch.zeros(8 * S, Kp, device=dev, dtype=torch.bfloat16)
-            check(lib.ssasr_cvt_bf16(ptr(wih_p), K, ptr(wih_bf), Kp, 8 * S, K, st), 'ssasr_cvt_bf16')
             xb = torch.zeros(n_rows, Kp, device=dev, dtype=torch.bfloat16) if Kp != K else \
                 torch.empty(n_rows, Kp, device=dev, dtype=torch.bfloat16)
-            tc_rec = S % 64 == 0 and S <= 512 and _TC_RECURRENCE
-            whh_bf = hb = None
+            hb = None
             if tc_rec:
-                whh_bf = torch.empty(8 * S, S, device=dev, dtype=torch.bfloat16)
-                check(lib.ssasr_cvt_bf16(ptr(whh_p), S, ptr(whh_bf), S, 8 * S, S, st), 'ssasr_cvt_bf16')
                 hb = torch.empty(n_rows, 2 * S, device=dev, dtype=torch.bfloat16)
+            else:
+                wih_bf = torch.zeros(8 * S, Kp, device=dev, dtype=torch.bfloat16)
+                check(lib.ssasr_cvt_bf16(ptr(wih_p), K, ptr(wih_bf), Kp, 8 * S, K, st), 'ssasr_cvt_bf16')
             check(lib.ssasr_blstm_fwd_bf16(ptr(x), n_rows, K, Kp, ptr(wih_bf), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch,
                                            rs_seq, rs_batch, ptr(lens_dev) if time_major else None, ptr(xb), ptr(xp),
                                            ptr(hout), ptr(cbuf), ptr(bar), ptr(whh_bf), ptr(hb), st),
@@ -117,7 +124,10 @@ class _BLSTM(torch.autograd.Function):
                                           ptr(bar), ptr(tws), ptr(x3), st), 'ssasr_blstm_fwd_f32')
         ctx.bf16 = bf16
         ctx.fwd_bf = (xb, hb, Kp) if (bf16 and hb is not None) else None      # bf16 x / h copies reused by the weight gradients
-        ctx.save_for_backward(x, wih_p, whhT_p, xp, hout, cbuf, lens_dev if time_major else torch.empty(0))
+        ctx.packed_bf = (wihT_bf, whhT_bf) if tc_rec else None                # backward operands packed with the forward ones
+        e0 = torch.empty(0, device=dev)
+        ctx.save_for_backward(x, wih_p if wih_p is not None else e0, whhT_p if whhT_p is not None else e0, xp, hout, cbuf,
+                              lens_dev if time_major else torch.empty(0))
         ctx.geom = (n_rows, K, S, n_seq, n_batch, rs_seq, rs_batch, time_major, d1)
         ctx.need_dx = ctx.needs_input_grad[0]
         return hout
@@ -139,13 +149,16 @@ class _BLSTM(torch.autograd.Function):
         if ctx.bf16:
             Rp = (n_rows + 7) // 8 * 8
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
-            wihT_bf = bf(K, 8 * S)
-            check(lib.ssasr_cvt_bf16_t(ptr(wih_p), K, ptr(wihT_bf), 8 * S, 8 * S, K, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
             tc_rec = S % 64 == 0 and S <= 512 and _TC_RECURRENCE
-            whhT_bf = None
-            if tc_rec:
-                whhT_bf = bf(2 * S, 4 * S)
-                check(lib.ssasr_cvt_bf16(ptr(whhT_p), 4 * S, ptr(whhT_bf), 4 * S, 2 * S, 4 * S, st), 'ssasr_cvt_bf16')
+            if ctx.packed_bf is not None:
+                wihT_bf, whhT_bf = ctx.packed_bf
+            else:
+                wihT_bf = bf(K, 8 * S)
+                check(lib.ssasr_cvt_bf16_t(ptr(wih_p), K, ptr(wihT_bf), 8 * S, 8 * S, K, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
+                whhT_bf = None
+                if tc_rec:
+                    whhT_bf = bf(2 * S, 4 * S)
+                    check(lib.ssasr_cvt_bf16(ptr(whhT_p), 4 * S, ptr(whhT_bf), 4 * S, 2 * S, 4 * S, st), 'ssasr_cvt_bf16')
             direct = tc_rec and ctx.fwd_bf is not None
             ws = [bf(n_rows, 8 * S) if (ctx.need_dx or tc_rec) else None] + \
                 ([None, None, None] if direct else [bf(8 * S, Rp), bf(K, Rp), bf(2 * S, Rp)])
@@ -154,10 +167,10 @@ class _BLSTM(torch.autograd.Function):
             # accumulating into an existing .grad would read them on the main stream before the side stream has written them
             fresh = all(getattr(w, 'grad', None) is None for w in ctx.param_refs)
             side = side_stream(dev) if (direct and _OVERLAP['on'] and fresh) else None
-            # gradient outputs are zero-filled on the main stream BEFORE the call, so the fill is ordered before the side stream
-            g = [torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev), torch.zeros(4 * S, device=dev),
-                 torch.zeros(4 * S, device=dev), torch.zeros(4 * S, K, device=dev), torch.zeros(4 * S, S, device=dev),
-                 torch.zeros(4 * S, device=dev), torch.zeros(4 * S, device=dev)]
+            # gradient outputs are allocated BEFORE the call: anything still using that memory is ordered before the side stream
+            g = [torch.empty(4 * S, K, device=dev), torch.empty(4 * S, S, device=dev), torch.empty(4 * S, device=dev),
+                 torch.empty(4 * S, device=dev), torch.empty(4 * S, K, device=dev), torch.empty(4 * S, S, device=dev),
+                 torch.empty(4 * S, device=dev), torch.empty(4 * S, device=dev)]
             check(lib.ssasr_blstm_bwd_bf16(ptr(x), n_rows, K, ptr(wihT_bf), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
                                            ptr(lens_dev) if time_major else None, ptr(act), ptr(hout), ptr(cbuf),
                                            ptr(dhout), ptr(dx), ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), ptr(dcs), ptr(bar),
@@ -166,8 +179,8 @@ class _BLSTM(torch.autograd.Function):
                   'ssasr_blstm_bwd_bf16')
             ctx.fwd_bf = None
             ust = side.cuda_stream if side else st
-            check(lib.ssasr_unpack_blstm_grads(ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), S, K, *[ptr(t) for t in g], ust),
-                  'ssasr_unpack_blstm_grads')
+            check(lib.ssasr_unpack_blstm_grads_set(ptr(dwih_p), ptr(dbias_p), ptr(dwhh_p), S, K, *[ptr(t) for t in g], ust),
+                  'ssasr_unpack_blstm_grads_set')
             if side is not None:
                 ev = torch.cuda.Event()
                 ev.record(side)
