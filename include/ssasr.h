@@ -182,6 +182,11 @@ int ssasr_adadelta_clip_step(const ssasr_optim_tensor* tensors /*HOST array of d
                              float eps, float max_norm /*<= 0: no clipping*/, float* scratch, float* norm_out /*device [2]: norm, applied*/,
                              int write_clipped_grads, void* stream);
 
+/* ---- prepare_x (ASRDataset.py:297-316): fp64/fp32 batch -> fp32 + per-utterance count of the frames
+ *      whose feature sum is non-zero, on the device (the reference copies the whole batch back to the host to count) ---- */
+int ssasr_prepare_x(const void* src /*[B,T,F] device*/, int src_is_f64, long long B, long long T, int F, float* dst /*[B,T,F] or NULL*/,
+                    int* lens /*int32 [B], overwritten*/, void* stream);
+
 /* ---- launch accounting and per-family CUDA-event timing (used by bench.py; no reference counterpart) ---- */
 int ssasr_num_families(void);
 const char* ssasr_family_name(int i);

@@ -190,3 +190,45 @@ int ssasr_adadelta_clip_step(const ssasr_optim_tensor* tensors, int n_tensors, f
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// prepare_x of the reference (ASRDataset.py:297-316): cast the DataLoader's (float64) batch to fp32 and count, per utterance,
+// the frames whose feature sum is not zero (the zero-padding rule of preprocess.py).  The reference copies the whole batch back
+// to the host for the count; here only the B lengths travel.  One warp per frame.
+// ------------------------------------------------------------------------------------------------
+namespace ssasr {
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_x_kernel(const T* __restrict__ src, float* __restrict__ dst, int* __restrict__ lens,
+                                                        long long n_frames, long long frames_per_utt, int F) {
+  const long long f = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (f >= n_frames) return;
+  const int lane = threadIdx.x & 31;
+  const T* s = src + f * F;
+  float* d = dst ? dst + f * F : nullptr;
+  float sum = 0.f;
+  for (int k = lane; k < F; k += 32) {
+    const float v = (float)s[k];
+    if (d) d[k] = v;
+    sum += v;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0 && sum != 0.f) atomicAdd(lens + f / frames_per_utt, 1);
+}
+}  // namespace ssasr
+
+extern "C" {
+// src: [B, T, F] float64 (src_is_f64) or float32, device; dst: [B, T, F] fp32 or NULL (count only); lens: int32 [B], overwritten
+int ssasr_prepare_x(const void* src, int src_is_f64, long long B, long long T, int F, float* dst, int* lens, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= 0) return 0;
+  SSASR_REQUIRE(T > 0 && F > 0 && src && lens, "prepare_x: bad arguments");
+  SSASR_CHECK_CUDA(cudaMemsetAsync(lens, 0, sizeof(int) * B, st));
+  const long long n = B * T;
+  const unsigned blocks = (unsigned)((n + 7) / 8);
+  ProfScope ps(F_PACK, st);
+  if (src_is_f64) prepare_x_kernel<double><<<blocks, 256, 0, st>>>((const double*)src, dst, lens, n, T, F);
+  else prepare_x_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, dst, lens, n, T, F);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+}

@@ -598,3 +598,23 @@ def test_deferred_weight_gradients_match():
         assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-7, k
         a, b = out[True][1][k], out[False][1][k]
         assert float((a - b).abs().max()) <= 1e-4 * (1e-3 + float(b.abs().max())), k
+
+
+def test_prepare_x_prepare_y_match_reference_glue():
+    """ASRDataset.py:297-340 restated inline (numpy count on the host) against the device-side prepare_x / prepare_y."""
+    from ss_asr_b200.dataset import prepare_x, prepare_y
+    g = torch.Generator().manual_seed(7)
+    B, T, F = 9, 57, 40
+    lens = sorted([int(v) for v in torch.randint(5, T + 1, (B,), generator=g)], reverse=True)
+    x = torch.randn(1, B, T, F, generator=g, dtype=torch.float64) * 4 - 10
+    x = x * (torch.arange(T)[None, None, :, None] < torch.tensor(lens)[None, :, None, None])
+    y = torch.randint(0, 30, (1, B, 13), generator=g).to(torch.float64)
+    for dt in (torch.float64, torch.float32):
+        xr = x.to(dt).squeeze(0).to(torch.float32)
+        want_lens = [int(v) for v in np.sum(np.sum(xr.numpy(), axis=-1) != 0, axis=-1)]
+        got, got_lens = prepare_x(x.to(dt), device=torch.device(DEV))
+        assert got.dtype == torch.float32 and got.is_cuda and torch.equal(got.cpu(), xr)
+        assert got_lens == want_lens == lens
+    yr = y.squeeze(0).to(torch.long)
+    gy, gl = prepare_y(y, device=torch.device(DEV))
+    assert torch.equal(gy.cpu(), yr) and gl == [int(v) + 1 for v in torch.sum(yr != 0, dim=-1)]
