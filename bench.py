@@ -77,10 +77,12 @@ def train_flops(B, T, F, U, S=256, Sd=256, M=128, C=50):
 
 def train_bytes(B, T, F, U, S=256):
     """Algorithmic HBM bytes of one training step for the streaming part of the recurrent kernels (per row of a layer:
-    forward = pre-activations in, activations / h / c fp32 + bf16 h out; backward = activations, dhout, c in, bf16 dG out)."""
-    rows = B * (T + T // 2 + T // 4 + T // 8)
-    fwd = rows * (8 * S * 4 + 8 * S * 4 + 2 * S * 4 + 2 * S * 4 + 2 * S * 2)
-    bwd = rows * (8 * S * 4 + 2 * S * 4 + 2 * S * 4 + 8 * S * 2)
+    forward = pre-activations in (layer 1: the bf16 features, its projection is fused in), activations / h / c fp32 + bf16 h
+    out; backward = activations, dhout, c in, bf16 dG out)."""
+    rows_l = [B * T, B * (T // 2), B * (T // 4), B * (T // 8)]
+    out_b = 8 * S * 4 + 2 * S * 4 + 2 * S * 4 + 2 * S * 2
+    fwd = rows_l[0] * (((F + 7) // 8 * 8) * 2 + out_b) + sum(r * (8 * S * 4 + out_b) for r in rows_l[1:])
+    bwd = sum(rows_l) * (8 * S * 4 + 2 * S * 4 + 2 * S * 4 + 8 * S * 2)
     return {'rec_fwd_tc': float(fwd), 'rec_bwd_tc': float(bwd)}
 
 
