@@ -187,6 +187,15 @@ int ssasr_adadelta_clip_step(const ssasr_optim_tensor* tensors /*HOST array of d
 int ssasr_prepare_x(const void* src /*[B,T,F] device*/, int src_is_f64, long long B, long long T, int F, float* dst /*[B,T,F] or NULL*/,
                     int* lens /*int32 [B], overwritten*/, void* stream);
 
+/* ---- validation metrics (postprocess.py:7-50 calc_acc / calc_err, called at trainer.py:493-494):
+ *      per-utterance argmax, character-accuracy counts and word-level Levenshtein distance on the device; the reference
+ *      copies the whole [B,U,C] prediction to the host and loops in Python.  Mapper.translate (ASRDataset.py:240-252) and
+ *      trim_eos (postprocess.py:68-75) define the token -> word-list rule. ---- */
+int ssasr_calc_acc_err(const float* predict /*[B,U,C] device*/, long long p_bstride, long long p_ustride, int B, int U, int C,
+                       const long long* label /*int64 [B,L] device*/, long long l_bstride, int L, int sos_id, int eos_id,
+                       int space_id /*-1: no word separator*/, int* stats /*int32 [B,4]: correct, total, edit distance, label words*/,
+                       int* tokens_out /*int32 [B,U] or NULL*/, void* stream);
+
 /* ---- launch accounting and per-family CUDA-event timing (used by bench.py; no reference counterpart) ---- */
 int ssasr_num_families(void);
 const char* ssasr_family_name(int i);

@@ -74,6 +74,7 @@ SIGNATURES = {
     'ssasr_adadelta_scratch_floats': (_LL, [C.POINTER(OptimTensor), _I]),
     'ssasr_adadelta_clip_step': (_I, [C.POINTER(OptimTensor), _I, _F, _F, _F, _F, _P, _P, _I, _P]),
     'ssasr_prepare_x': (_I, [_P, _I, _LL, _LL, _I, _P, _P, _P]),
+    'ssasr_calc_acc_err': (_I, [_P, _LL, _LL, _I, _I, _I, _P, _LL, _I, _I, _I, _I, _P, _P, _P]),
     'ssasr_num_families': (_I, []),
     'ssasr_family_name': (C.c_char_p, [_I]),
     'ssasr_launch_count': (_LL, []),

@@ -618,3 +618,84 @@ def test_prepare_x_prepare_y_match_reference_glue():
     yr = y.squeeze(0).to(torch.long)
     gy, gl = prepare_y(y, device=torch.device(DEV))
     assert torch.equal(gy.cpu(), yr) and gl == [int(v) + 1 for v in torch.sum(yr != 0, dim=-1)]
+
+
+# ------------------------------------------------------------------------------------------------ validation metrics (f4)
+class _Mapper:
+    """ASRDataset.Mapper (ASRDataset.py:228-262) over the default token table."""
+
+    def __init__(self, tokens=O.TOKENS):
+        self.mapping = {c: i for i, c in enumerate(tokens)}
+
+    def char_to_ind(self, c):
+        return self.mapping[c]
+
+    def ind_to_char(self, i):
+        return O.TOKENS[i]
+
+
+def test_calc_acc_err_match_oracle_and_reference_golden(golden_dir):
+    """Integer work: per-utterance counts bit-exact against the oracle; batch results identical (==) to the committed outputs
+    of the unmodified reference."""
+    from oracle import postprocess_oracle as PO
+    from ss_asr_b200 import postprocess as PPc
+    z = np.load(os.path.join(golden_dir, 'postprocess.npz'))
+    for k in range(4):
+        seed, B, U, L = (int(v) for v in z['case_%d' % k])
+        predict, label, pred_tok = PO.synth_cases(seed=seed, B=B, U=U, L=L)
+        pd_, ld_ = torch.from_numpy(predict).to(DEV), torch.from_numpy(label).to(DEV)
+        stats, toks = PPc.utterance_stats(pd_, ld_, _Mapper(), return_tokens=True)
+        assert np.array_equal(toks.cpu().numpy(), pred_tok)
+        assert np.array_equal(stats.numpy(), PO.utterance_stats(predict, label))
+        assert PPc.calc_acc(pd_, ld_) == float(z['acc_%d' % k])
+        assert PPc.calc_err(pd_, ld_, _Mapper()) == float(z['err_%d' % k])
+        assert PPc.calc_acc_err(pd_, ld_, _Mapper()) == (float(z['acc_%d' % k]), float(z['err_%d' % k]))
+
+
+def test_calc_acc_err_edge_cases():
+    from oracle import postprocess_oracle as PO
+    from ss_asr_b200 import postprocess as PPc
+    # NaN rows (np.argmax: the first NaN wins), -inf rows (index 0), long sequences, strided (sliced) inputs
+    rng = np.random.RandomState(5)
+    predict, label, _ = PO.synth_cases(seed=21, B=7, U=300, L=260)
+    predict[0, 3, 17] = np.nan
+    predict[0, 3, 40] = np.nan
+    predict[1, 0, :] = -np.inf
+    predict[2, 5, :] = 1.25
+    want = PO.utterance_stats(predict, label)
+    big = torch.from_numpy(rng.randn(7, 310, 64).astype(np.float32)).to(DEV)
+    big[:, :300, :50] = torch.from_numpy(predict).to(DEV)
+    lab = torch.zeros(7, 270, dtype=torch.int64, device=DEV)
+    lab[:, 5:265] = torch.from_numpy(label).to(DEV)
+    stats, toks = PPc.utterance_stats(big[:, :300, :50], lab[:, 5:265], None, return_tokens=True)
+    assert np.array_equal(toks.cpu().numpy(), np.argmax(predict, axis=-1))
+    assert np.array_equal(stats.numpy(), want)
+    # an empty label (first token 0) divides by zero in the reference (postprocess.py:27); same exception here
+    lab0 = torch.zeros(2, 4, dtype=torch.int64, device=DEV)
+    with pytest.raises(ZeroDivisionError):
+        PPc.calc_acc(torch.zeros(2, 4, 50, device=DEV), lab0)
+    with pytest.raises(RuntimeError):
+        PPc.calc_acc(torch.zeros(2, 4, 50), lab0.cpu())
+
+
+def test_valid_step_matches_oracle():
+    """Body of ASRTrainer.valid (trainer.py:472-494): batched greedy forward for ans_len + 30 steps without a teacher, loss
+    on the first ans_len steps, calc_acc / calc_err -- against the oracle's no-teacher forward."""
+    from oracle import postprocess_oracle as PO
+    from ss_asr_b200 import postprocess as PPc
+    dims = (50, 32, 32, 16, 20)
+    sd = O.make_state_dict(*dims, seed=1)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 20          # margins between classes (SURVEY §8d "margin" variant)
+    x, lens, y = O.synth_batch(6, 48, 20, 6, seed=3)
+    y_lens = [int(v) + 1 for v in (y != 0).sum(-1)]
+    ans_len = max(y_lens) - 1
+    _, logits_o, att_o, _ = O.asr_forward(sd, x, lens, ans_len + 30)
+    loss_o = O.asr_loss(logits_o[:, :ans_len], y)
+    label = y[:, 1:ans_len + 1]
+    m = _model(dims, sd).eval()
+    loss, acc, err, pred, att, toks = PPc.valid_step(m, x.to(DEV), y.to(DEV), lens, y_lens, _Mapper())
+    assert float((pred.cpu() - logits_o).abs().max()) < 1e-4
+    assert abs(float(loss) - float(loss_o)) < 1e-5 * abs(float(loss_o)) + 1e-6
+    assert np.array_equal(toks.cpu().numpy(), np.argmax(logits_o.numpy(), -1))
+    assert acc == PO.calc_acc(logits_o.numpy(), label.numpy())
+    assert err == PO.calc_err(logits_o.numpy(), label.numpy())

@@ -193,3 +193,48 @@ def test_oracle_vs_reference_live():
         el2, logits, att2, _ = O.asr_forward(sd, x, lens, U + 1, teacher=y)
     assert el == el2
     assert float((pred - logits).abs().max()) < 1e-5 and float((att - att2).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ validation metrics
+def test_postprocess_oracle_matches_reference_outputs(golden_dir):
+    """oracle/postprocess_oracle.py against postprocess.calc_acc / calc_err + ASRDataset.Mapper of the unmodified reference
+    (tests/golden/postprocess.npz): Python-float results identical, hypotheses string-identical."""
+    from oracle import postprocess_oracle as PO
+    z = np.load(os.path.join(golden_dir, 'postprocess.npz'))
+    k = 0
+    while 'case_%d' % k in z.files:
+        seed, B, U, L = (int(v) for v in z['case_%d' % k])
+        predict, label, pred_tok = PO.synth_cases(seed=seed, B=B, U=U, L=L)
+        assert np.array_equal(PO.argmax_tokens(predict), pred_tok)                 # ties resolve to the first maximum
+        assert PO.calc_acc(predict, label) == float(z['acc_%d' % k])
+        assert PO.calc_err(predict, label) == float(z['err_%d' % k])
+        st = PO.utterance_stats(predict, label)
+        assert np.array_equal(st[:, 0] / st[:, 1], z['acc_utt_%d' % k])
+        assert np.array_equal(st[:, 2] / st[:, 3], z['err_utt_%d' % k])
+        assert [PO.translate(p) for p in pred_tok] == [str(s) for s in z['hyp_%d' % k]]
+        k += 1
+    assert k == 4
+
+
+def test_postprocess_oracle_known_answers():
+    from oracle import postprocess_oracle as PO
+    assert PO.levenshtein('kitten', 'sitting') == 3 and PO.levenshtein([], ['a']) == 1 and PO.levenshtein(['a'], ['a']) == 0
+    assert PO.translate([3, 46, 46, 4, 1, 5]) == 'a  b' and PO.translate([0, 1]) == '' and PO.translate([3, 0, 4]) == 'ab'
+    assert ''.split(' ') == [''] and 'a  b'.split(' ') == ['a', '', 'b']
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/src/postprocess.py'), reason='reference sources not present')
+def test_postprocess_oracle_vs_reference_live(golden_dir):
+    import sys
+    sys.path.insert(0, golden_dir)
+    import ref_shim
+    from oracle import postprocess_oracle as PO
+    ref_shim.load()
+    import ASRDataset
+    import postprocess
+    mapper = ASRDataset.Mapper()
+    for seed in (11, 12):
+        predict, label, _ = PO.synth_cases(seed=seed, B=12, U=23, L=14)
+        pt, lt = torch.from_numpy(predict), torch.from_numpy(label)
+        assert postprocess.calc_acc(pt, lt) == PO.calc_acc(predict, label)
+        assert postprocess.calc_err(pt, lt, mapper) == PO.calc_err(predict, label)
