@@ -127,6 +127,8 @@ typedef struct {
   float *lm_h1, *lm_h2;
   float* x3_ws; /* NULL, or 2*B*max(X1,X2) + 8*Sd*(X1+X2) floats: forward-only gate GEMMs on tensor cores (tf32 x 3) */
   int skip_final_logits; /* 1: do not recompute the [B,U,C] logits after the loop (greedy decoding only needs tok_in) */
+  int dual_stream;       /* bf16 mode: ws_bf holds B*X1 + U*B*X2 elements (a layer-2 input block per step) and the layer-2
+                            chain (asr.py:322-324) runs on an internal second stream, joined into `stream` before returning */
 } ssasr_speller_fwd_args;
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
 
@@ -144,6 +146,7 @@ typedef struct {
   const void *w1catT_bf, *w2catT_bf; /* bf16 [X1,4Sd] / [X2,4Sd] transposed weights, or NULL (fp32 path) */
   void *wsA, *wsB;                   /* bf16 scratch: >= max(4Sd*BUp, M*BTp) and >= max(X1*BUp, E*BTp + E*M) elements */
   long long BUp, BTp;                /* B*U and B*Tp rounded up to multiples of 8 */
+  int dual_stream;                   /* bf16 mode: dxin2 holds U*B*X2 floats; layer-2 chain on an internal second stream */
 } ssasr_speller_bwd_args;
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream);
 

@@ -20,7 +20,7 @@ class SpellerFwdArgs(C.Structure):
                 [('lm_H', C.c_int), ('lm_weight', C.c_float)] +
                 [(n, C.c_void_p) for n in ('lm_emb', 'lm_w1i', 'lm_w1h', 'lm_b1i', 'lm_b1h', 'lm_w2i', 'lm_w2h', 'lm_b2i',
                                            'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2', 'x3_ws')] +
-                [('skip_final_logits', C.c_int)])
+                [('skip_final_logits', C.c_int), ('dual_stream', C.c_int)])
 
 
 class SpellerBwdArgs(C.Structure):
@@ -32,7 +32,7 @@ class SpellerBwdArgs(C.Structure):
                                            'd_emb_w', 'd_wc', 'd_bc', 'denc',
                                            'dh2all', 'dxin1', 'dxin2', 'dc1s', 'dc2s', 'dh1att', 'dpsi', 'dqpre', 'de_all',
                                            'w1catT_bf', 'w2catT_bf', 'wsA', 'wsB')] +
-                [('BUp', C.c_longlong), ('BTp', C.c_longlong)])
+                [('BUp', C.c_longlong), ('BTp', C.c_longlong), ('dual_stream', C.c_int)])
 
 
 class OptimTensor(C.Structure):

@@ -214,6 +214,7 @@ class ASR(nn.Module):
         self.decode_precision = 'fp32'   # 'tf32x3': encoder input projections of decode_batch on tensor cores
         self.sample_seed = 0
         self.last_tokens = None          # [B,U] int32: the input token of every step of the last forward
+        self.decode_encoder_chunk = 256  # decode_batch: utterances per Listener pass (0 = one pass over the whole batch)
         self.init_parameters()
 
     # ------------------------------------------------------------------------------------------
@@ -266,12 +267,27 @@ class ASR(nn.Module):
         # with the 3-term tf32 split (~5e-5 absolute on the gate pre-activations, set by the tensor core's accumulator)
         prec = precision or self.decode_precision
         self.encoder.set_precision(prec)
+        N = xs.shape[0]
+        lens = _lens_list(x_lens)
+        chunk = int(self.decode_encoder_chunk or 0)
         try:
-            enc, enc_len = self.encoder(xs, x_lens)
+            if chunk <= 0 or N <= chunk:
+                enc, enc_len = self.encoder(xs, x_lens)
+            else:
+                # utterances are independent and sorted by length: the Listener runs over groups of `chunk` utterances, each
+                # only as many frames deep as ITS longest utterance (the recurrent kernels are bound by dependent steps, so
+                # the padded tail of a short group is pure waste); one tile per CTA in the recurrent kernels at <= 256 rows
+                enc, enc_len = None, []
+                for r0 in range(0, N, chunk):
+                    r1 = min(N, r0 + chunk)
+                    e, el = self.encoder(xs[r0:r1, :lens[r0]], lens[r0:r1])
+                    if enc is None:
+                        enc = torch.zeros(N, e.shape[1], e.shape[2], dtype=e.dtype, device=e.device)
+                    enc[r0:r1, :e.shape[1]] = e
+                    enc_len += list(el)
         finally:
             self.encoder.utterance_independent = prev
             self.encoder.set_precision('fp32')
-        N = xs.shape[0]
         tok_in = torch.zeros(N, max_steps + 1, dtype=torch.int32, device=enc.device)
         lm = None
         if rnn_lm is not None and lm_weight != 0:

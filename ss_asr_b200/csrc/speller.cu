@@ -437,7 +437,9 @@ __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long lo
                                 long long cp_ld, float* __restrict__ cout, long long c_ld, float* __restrict__ hout,
                                 long long h_ld, const float* __restrict__ cp_src, long long cps_ld, float* __restrict__ cp_dst,
                                 long long cpd_ld, __nv_bfloat16* __restrict__ hb_out, long long hb_ld, int hb_cp_off,
-                                float* __restrict__ x3h = nullptr, float* __restrict__ x3l = nullptr, long long x3_ld = 0) {
+                                float* __restrict__ x3h = nullptr, float* __restrict__ x3l = nullptr, long long x3_ld = 0,
+                                float* __restrict__ h_dst2 = nullptr, long long hd2_ld = 0,
+                                __nv_bfloat16* __restrict__ hb_dst2 = nullptr, long long hbd2_ld = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * S) return;
   const int b = i / S, u = i % S;
@@ -453,6 +455,8 @@ __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long lo
   hout[(size_t)b * h_ld + u] = h;
   if (hb_out) hb_out[(size_t)b * hb_ld + u] = __float2bfloat16(h);
   if (x3h) put_hi_lo(x3h, x3l, (size_t)b * x3_ld + u, h);
+  if (h_dst2) h_dst2[(size_t)b * hd2_ld + u] = h;
+  if (hb_dst2) hb_dst2[(size_t)b * hbd2_ld + u] = __float2bfloat16(h);
   if (cp_dst) {
     const float v = cp_src ? cp_src[(size_t)b * cps_ld + u] : 0.f;
     cp_dst[(size_t)b * cpd_ld + u] = v;
@@ -770,6 +774,33 @@ __global__ void mean_kernel(const float* __restrict__ v, int n, float* __restric
   }
 }
 
+// Second stream + event pool of the decoder loops (bf16 training mode).  The layer-2 cell chain of the Speller never feeds
+// the attention query (asr.py:84 takes state_list[0], the layer-1 state), so it only joins the layer-1 / attention chain
+// where a sampled token is needed; run on its own stream it disappears from the dependent chain of a step.
+struct SideStream {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[512];
+  int n_ev = 0;
+};
+static SideStream* side_stream(int n_events) {
+  static SideStream pool[32];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32 || n_events > 512) return nullptr;
+  SideStream* ss = &pool[dev];
+  if (!ss->s && cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) { ss->s = nullptr; return nullptr; }
+  while (ss->n_ev < n_events) {
+    if (cudaEventCreateWithFlags(&ss->ev[ss->n_ev], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ++ss->n_ev;
+  }
+  return ss;
+}
+// `waiter` continues only after everything enqueued on `src` so far
+#define SSASR_HANDOVER(event, src, waiter)                   \
+  do {                                                       \
+    SSASR_CHECK_CUDA(cudaEventRecord((event), (src)));       \
+    SSASR_CHECK_CUDA(cudaStreamWaitEvent((waiter), (event), 0)); \
+  } while (0)
+
 }  // namespace ssasr
 
 using namespace ssasr;
@@ -802,6 +833,9 @@ typedef struct {
   // scratch of 2*B*max(X1,X2) + 2*4Sd*(X1+X2) floats, or NULL
   float* x3_ws;
   int skip_final_logits;
+  // bf16 mode only: ws_bf holds B*X1 + U*B*X2 elements (one layer-2 input block per step) and the layer-2 chain may run on
+  // an internal second stream, joined into `stream` before the call returns
+  int dual_stream;
 } ssasr_speller_fwd_args;
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
@@ -846,7 +880,12 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     rc = split_hi_lo(st, a->w2cat, w2h, w2l, (size_t)4 * Sd * X2);
     if (rc) return rc;
   }
-  auto gate_gemm = [&](const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out,
+  // bf16 mode: layer-2 chain on a second stream (one layer-2 input block per step in ws_bf)
+  SideStream* side = (tc && a->dual_stream && U > 1) ? side_stream(2 * U + 2) : nullptr;
+  const bool dual = side != nullptr;
+  cudaStream_t sb = dual ? side->s : st;
+  auto x2b_at = [&](int t) { return (dual && x2b) ? x2b + (size_t)t * B * X2 : x2b; };
+  auto gate_gemm = [&](cudaStream_t st, const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out,
                        const __nv_bfloat16* xb) -> int {
     if (tc) return gemm_bf16_tc(st, B, 4 * Sd, K, xb, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0);
     if (x3) {                  // xh / xl were written by the kernel that produced x (attention step / layer-1 cell)
@@ -866,26 +905,35 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     f.x3h = x3 ? xh : nullptr; f.x3l = x3 ? xl : nullptr; f.x3_ld = X1;
     f.q = a->q + (size_t)t * M; f.q_ld = (long long)U * M;
     f.alpha = a->alpha + (size_t)t * Tp; f.alpha_ld = (long long)U * Tp;
+    // the token of this step was selected from the previous step's layer-2 output
+    if (dual && t > 0 && a->step_mode && a->step_mode[t - 1] != 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[U + t - 1], 0));
     { ProfScope ps(F_ATTN_FWD, st); attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f); }
     // layer 1
-    rc = gate_gemm(a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
+    rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
     if (rc) return rc;
     { ProfScope ps(F_POINTWISE, st); }
+    // writes h1(t) into the layer-2 input row; single stream (and step 0): also copies h2(t-1) next to it
+    const bool copy_h2 = !dual || t == 0;
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd, a->xin2 + (size_t)t * X2,
                                                  (long long)U * X2, t ? a->h2all + (size_t)(t - 1) * Sd : nullptr,
-                                                 (long long)U * Sd, a->xin2 + (size_t)t * X2 + Sd, (long long)U * X2, x2b, X2, Sd,
-                                                 x3 ? xh : nullptr, x3 ? xl : nullptr, X2);
+                                                 (long long)U * Sd, copy_h2 ? a->xin2 + (size_t)t * X2 + Sd : nullptr,
+                                                 (long long)U * X2, x2b_at(t), X2, Sd, x3 ? xh : nullptr, x3 ? xl : nullptr, X2);
+    if (dual) SSASR_HANDOVER(side->ev[t], st, sb);
     // layer 2
-    rc = gate_gemm(a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd, x2b);
+    rc = gate_gemm(sb, a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd, x2b_at(t));
     if (rc) return rc;
-    { ProfScope ps(F_POINTWISE, st); }
-    cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+    { ProfScope ps(F_POINTWISE, sb); }
+    const bool fwd_h2 = dual && t + 1 < U;      // h2(t) goes straight into the next step's layer-2 input row
+    cell_fwd_kernel<<<cell_blocks, 256, 0, sb>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c2 + (size_t)t * Sd, (long long)U * Sd, a->h2all + (size_t)t * Sd,
-                                                 (long long)U * Sd, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+                                                 (long long)U * Sd, nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0,
+                                                 fwd_h2 ? a->xin2 + (size_t)(t + 1) * X2 + Sd : nullptr, (long long)U * X2,
+                                                 fwd_h2 ? x2b_at(t + 1) + Sd : nullptr, X2);
     const int mode = a->step_mode ? a->step_mode[t] : 0;
+    // token selection consumes h2(t): it runs on the layer-2 stream
     if (mode != 0 && t + 1 < U) {
       const size_t lp_smem = lp_smem_bytes(C, Sd);
       const bool fused = C <= 64 && lp_smem <= 160 * 1024;
@@ -895,16 +943,16 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
           SSASR_CHECK_CUDA(cudaFuncSetAttribute(logits_pick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
           lp_attr = lp_smem;
         }
-        ProfScope ps(F_POINTWISE, st);
-        logits_pick_kernel<<<(B + 8 * LP_UPW - 1) / (8 * LP_UPW), 256, lp_smem, st>>>(B, C, Sd, a->h2all + (size_t)t * Sd, (long long)U * Sd, a->wc, a->bc,
+        ProfScope ps(F_POINTWISE, sb);
+        logits_pick_kernel<<<(B + 8 * LP_UPW - 1) / (8 * LP_UPW), 256, lp_smem, sb>>>(B, C, Sd, a->h2all + (size_t)t * Sd, (long long)U * Sd, a->wc, a->bc,
                                                               a->logits + (size_t)t * C, (long long)U * C, mode == 3 ? 0 : mode,
                                                               a->seed, (unsigned long long)t, a->tok_in + t + 1, U);
       } else {
-        rc = gemm_f32(st, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
+        rc = gemm_f32(sb, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
                       0, 0);
         if (rc) return rc;
       }
-      { ProfScope ps(F_POINTWISE, st); }
+      { ProfScope ps(F_POINTWISE, sb); }
       if (mode == 3) {
         SSASR_REQUIRE(a->lm_emb && a->lm_h1 && a->lm_h2 && a->lm_H > 0, "speller: step mode 3 needs the language-model arguments");
         LmStep l;
@@ -915,13 +963,15 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
         l.logits = a->logits + (size_t)t * C; l.logits_ld = (long long)U * C;
         l.tok_in = a->tok_in + t; l.tok_out = a->tok_in + t + 1; l.tok_ld = U;
         const int nt = ((a->lm_H + 31) / 32) * 32 > 256 ? 256 : ((a->lm_H + 31) / 32) * 32;
-        lm_pick_kernel<<<B, nt, (size_t)(5 * a->lm_H + C + 32) * sizeof(float), st>>>(l);
+        lm_pick_kernel<<<B, nt, (size_t)(5 * a->lm_H + C + 32) * sizeof(float), sb>>>(l);
       } else if (!fused) {
-        pick_token_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
+        pick_token_kernel<<<(B + 127) / 128, 128, 0, sb>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
                                                            (unsigned long long)t, a->tok_in + t + 1, U);
       }
+      if (dual) SSASR_CHECK_CUDA(cudaEventRecord(side->ev[U + t], sb));   // next step's token is ready
     }
   }
+  if (dual) SSASR_HANDOVER(side->ev[2 * U], sb, st);
   if (a->skip_final_logits) {        // greedy decoding only consumes the tokens
     SSASR_LAUNCH_CHECK();
     return 0;
@@ -952,6 +1002,9 @@ typedef struct {
   const void *w1catT_bf, *w2catT_bf;
   void *wsA, *wsB;   // element counts: wsA >= max(4Sd*BUp, M*BTp), wsB >= max(X1*BUp, E*BTp + E*M)
   long long BUp, BTp;
+  // bf16 mode only: dxin2 holds U*B*X2 floats (one block per step) and the layer-2 chain may run on an internal second
+  // stream, joined into `stream` before the call returns
+  int dual_stream;
 } ssasr_speller_bwd_args;
 
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
@@ -990,10 +1043,19 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
                   a->BUp % 8 == 0;
   // dx = dG_t @ Wcat (through the cells' input weights), fp32 SIMT or tcgen05
   __nv_bfloat16* dgb = tc ? (__nv_bfloat16*)a->wsA : nullptr;     // [B,4Sd] bf16 copy of the step's gate gradients
-  auto dgrad_gemm = [&](const float* dg, int N, const float* w, const void* wT_bf, float* out, int ldo) -> int {
+  // bf16 mode: the layer-2 backward chain depends on nothing but dh2all and itself -- it runs ahead on a second stream
+  // (own gate-gradient scratch, one dxin2 block per step) and hands dh1(t) to the layer-1 / attention chain by event
+  SideStream* side = (tc && a->dual_stream && U > 1) ? side_stream(U + 2) : nullptr;
+  const bool dual = side != nullptr;
+  cudaStream_t sb = dual ? side->s : st;
+  __nv_bfloat16* dgb2 = dual ? dgb + (size_t)B * 4 * Sd : dgb;
+  auto dxin2_at = [&](int t) { return dual ? a->dxin2 + (size_t)t * B * X2 : a->dxin2; };
+  auto dgrad_gemm = [&](cudaStream_t st, const __nv_bfloat16* dgb, const float* dg, int N, const float* w, const void* wT_bf,
+                        float* out, int ldo) -> int {
     if (tc) return gemm_bf16_tc(st, B, N, 4 * Sd, dgb, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, ldo, nullptr, 0);
     return gemm_f32(st, B, N, 4 * Sd, dg, U * 4 * Sd, 1, w, N, 0, out, ldo, nullptr, 0, 0);
   };
+  if (dual) SSASR_HANDOVER(side->ev[U], st, sb);
   // dW = dG_all^T @ X_all over all B*U rows
   auto wgrad_gemm = [&](const float* dg, const float* x, int N, float* out) -> int {
     if (tc) {
@@ -1007,21 +1069,22 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   };
   for (int t = U - 1; t >= 0; --t) {
     const int last = (t == U - 1);
-    { ProfScope ps(F_POINTWISE, st); }
-    cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+    { ProfScope ps(F_POINTWISE, sb); }
+    cell_bwd_kernel<<<cell_blocks, 256, 0, sb>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  a->c2 + (size_t)t * Sd, (long long)U * Sd,
                                                  t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
-                                                 a->dh2all + (size_t)t * Sd, (long long)U * Sd, last ? nullptr : a->dxin2 + Sd,
-                                                 (long long)X2, nullptr, 0, a->dc2s, last, dgb);
-    rc = dgrad_gemm(a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, a->dxin2, X2);
+                                                 a->dh2all + (size_t)t * Sd, (long long)U * Sd,
+                                                 last ? nullptr : dxin2_at(t + 1) + Sd, (long long)X2, nullptr, 0, a->dc2s, last, dgb2);
+    rc = dgrad_gemm(sb, dgb2, a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, dxin2_at(t), X2);
     if (rc) return rc;
+    if (dual) SSASR_HANDOVER(side->ev[t], sb, st);
     { ProfScope ps(F_POINTWISE, st); }
     cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd,
-                                                 t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, a->dxin2,
+                                                 t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, dxin2_at(t),
                                                  (long long)X2, last ? nullptr : a->dxin1 + (size_t)(t + 1) * X1 + K1,
                                                  (long long)U * X1, last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last, dgb);
-    rc = dgrad_gemm(a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
+    rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
     if (rc) return rc;
     AttnBwd g;
     g.Tp = Tp; g.E = E; g.Sd = Sd; g.M = M;

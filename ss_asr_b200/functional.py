@@ -10,6 +10,14 @@ from ._lib import check, ptr, stream
 
 
 _TC_RECURRENCE = os.environ.get('SSASR_TC_RECURRENCE', '1') != '0'   # bf16 path: recurrence on tcgen05
+# bf16 path: the Speller's layer-2 cell chain (forward and backward) on a second stream inside the C call -- it never feeds
+# the attention query (asr.py:84), so it leaves the dependent chain of a decoding step
+_DUAL_STREAM_SPELLER = os.environ.get('SSASR_DUAL_STREAM_SPELLER', '1') != '0'
+
+
+def set_dual_stream_speller(on):
+    global _DUAL_STREAM_SPELLER
+    _DUAL_STREAM_SPELLER = bool(on)
 
 
 def _f32c(t):
@@ -245,7 +253,8 @@ class _Spell(torch.autograd.Function):
         w1b = w2b = wsb = encb = None
         if bf16:
             bf = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
-            w1b, w2b, wsb = bf(4 * Sd, X1), bf(4 * Sd, X2), bf(B, X1 + X2)
+            # step-input rows for the tcgen05 gate GEMMs: [B, X1] + one [B, X2] block per step (layer-2 chain on its own stream)
+            w1b, w2b, wsb = bf(4 * Sd, X1), bf(4 * Sd, X2), bf(B * X1 + (U if _DUAL_STREAM_SPELLER else 1) * B * X2)
             encb = bf((B * Tp + M) * E)
             check(lib.ssasr_cvt_bf16(ptr(w1cat), X1, ptr(w1b), X1, 4 * Sd, X1, st), 'ssasr_cvt_bf16')
             check(lib.ssasr_cvt_bf16(ptr(w2cat), X2, ptr(w2b), X2, 4 * Sd, X2, st), 'ssasr_cvt_bf16')
@@ -267,7 +276,8 @@ class _Spell(torch.autograd.Function):
                                 xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
                                 h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits), w1cat_bf=ptr(w1b),
                                 w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), x3_ws=ptr(x3ws),
-                                skip_final_logits=skip_final, **lmk)
+                                skip_final_logits=skip_final, dual_stream=int(bf16 and _DUAL_STREAM_SPELLER), **lmk)
+        ctx.dual = bool(bf16 and _DUAL_STREAM_SPELLER)
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
@@ -289,7 +299,7 @@ class _Spell(torch.autograd.Function):
         d_phi_w, d_psi_w, d_psi_b = f(M, Sd), f(M, E), f(M)
         d_w1cat, d_b1, d_w2cat, d_b2 = f(4 * Sd, X1), f(4 * Sd), f(4 * Sd, X2), f(4 * Sd)
         d_emb_w, d_wc, d_bc, denc = f(Cc, Sd), f(Cc, Sd), f(Cc), f(B, Tp, E)
-        scr = [f(B, U, Sd), f(B, U, X1), f(B, X2), f(B, Sd), f(B, Sd), f(B, Sd), f(B, Tp, M), f(B, U, M), f(B, U, Tp)]   # kept alive
+        scr = [f(B, U, Sd), f(B, U, X1), f(U if ctx.dual else 1, B, X2), f(B, Sd), f(B, Sd), f(B, Sd), f(B, Tp, M), f(B, U, M), f(B, U, Tp)]   # kept alive
         w1T = w2T = wsA = wsB = None
         BUp = (B * U + 7) // 8 * 8
         BTp = (B * Tp + 7) // 8 * 8
@@ -309,7 +319,8 @@ class _Spell(torch.autograd.Function):
                                 d_emb_w=ptr(d_emb_w), d_wc=ptr(d_wc), d_bc=ptr(d_bc), denc=ptr(denc),
                                 dh2all=ptr(scr[0]), dxin1=ptr(scr[1]), dxin2=ptr(scr[2]), dc1s=ptr(scr[3]),
                                 dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]), de_all=ptr(scr[8]),
-                                w1catT_bf=ptr(w1T), w2catT_bf=ptr(w2T), wsA=ptr(wsA), wsB=ptr(wsB), BUp=BUp, BTp=BTp)
+                                w1catT_bf=ptr(w1T), w2catT_bf=ptr(w2T), wsA=ptr(wsA), wsB=ptr(wsB), BUp=BUp, BTp=BTp,
+                                dual_stream=int(ctx.dual))
         check(lib.ssasr_speller_bwd_f32(C.byref(a), st), 'ssasr_speller_bwd_f32')
         z = lambda *s: torch.zeros(*s, device=dev)
         g1 = [z(4 * Sd, K1), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]

@@ -699,3 +699,60 @@ def test_valid_step_matches_oracle():
     assert np.array_equal(toks.cpu().numpy(), np.argmax(logits_o.numpy(), -1))
     assert acc == PO.calc_acc(logits_o.numpy(), label.numpy())
     assert err == PO.calc_err(logits_o.numpy(), label.numpy())
+
+
+def test_decode_batch_encoder_chunking_is_invisible():
+    """decode_batch runs the Listener over length-sorted groups of utterances (each only as deep as its longest member);
+    tokens must be identical to the single-pass result and to the oracle's bs=1 decode, on both exact paths."""
+    dims = (50, 64, 64, 32, 40)
+    sd = O.make_state_dict(*dims, seed=1)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 20
+    g = torch.Generator().manual_seed(7)
+    Ts = sorted([int(v) for v in torch.randint(17, 72, (11,), generator=g)], reverse=True)
+    xb = torch.zeros(len(Ts), Ts[0], 40)
+    for i, t in enumerate(Ts):
+        xb[i, :t] = torch.randn(t, 40, generator=g)
+    m = _model(dims, sd).eval()
+    want = [O.decode_greedy(sd, xb[i:i + 1, :t], [t], max_steps=12) for i, t in enumerate(Ts)]
+    for prec in ('fp32', 'tf32x3'):
+        outs = []
+        for chunk in (0, 4, 5, 64):
+            m.decode_encoder_chunk = chunk
+            outs.append(m.decode_batch(xb.to(DEV), Ts, max_steps=12, precision=prec))
+        assert outs[0] == outs[1] == outs[2] == outs[3], prec
+        assert outs[0] == [list(w) for w in want], prec
+
+
+@pytest.mark.parametrize('tf_rate', [1.0, 0.6])
+def test_dual_stream_speller_is_invisible(tf_rate):
+    """bf16 path: the Speller's layer-2 chain on the internal second stream (forward and backward) runs the same kernels on the
+    same data as the single-stream loop -- logits, sampled tokens, attention maps and every gradient must be bit-identical,
+    with teacher forcing and with sampled steps (which join the two streams), several times in a row (race check)."""
+    import random
+    from ss_asr_b200 import functional as Fk
+    from ss_asr_b200.functional import asr_loss
+    dims = (50, 64, 64, 32, 40)
+    sd = O.make_state_dict(*dims, seed=1)
+    x, lens, y = O.synth_batch(70, 48, 40, 17, seed=11)
+
+    def run(dual):
+        Fk.set_dual_stream_speller(dual)
+        m = _model(dims, sd, tf=tf_rate)
+        m.train_precision = 'bf16'
+        m.train()
+        m.sample_seed = 5
+        random.seed(3)
+        _, logits, att = m(x.to(DEV), 18, teacher=y.to(DEV), state_len=lens)
+        asr_loss(logits, y.to(DEV)).backward()
+        torch.cuda.synchronize()
+        return logits.detach().clone(), att.clone(), m.last_tokens.clone(), {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    try:
+        want = run(False)
+        for _ in range(3):
+            got = run(True)
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]) and torch.equal(got[2], want[2])
+            for k in want[3]:
+                assert torch.equal(got[3][k], want[3][k]), k
+    finally:
+        Fk.set_dual_stream_speller(True)
