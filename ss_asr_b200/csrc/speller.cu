@@ -29,7 +29,25 @@ struct AttnFwd {
   float* x3h; float* x3l; long long x3_ld;   // optional tf32 hi / lo split of the same row (tf32 x 3 GEMM operands)
   float* q; long long q_ld;                  // [B,M]
   float* alpha; long long alpha_ld;          // [B,Tp]
+  // optional: the layer-1 cell of the PREVIOUS step fused into this kernel's prologue (row b is private to the CTA): h1prev
+  // is then computed from the gate pre-activations instead of being read, and the cell's outputs are written from here
+  float* cell_gates; long long cg_ld;        // [B,4Sd] pre-activations (col = unit*4 + gate) -> activations, in place
+  const float* cell_cprev; long long ccp_ld; // [B,Sd] c1 of the step before, or null (zero state)
+  float* cell_cout; long long cco_ld;        // [B,Sd] c1 of the previous step
+  float* cell_hout; long long cho_ld;        // [B,Sd] h1 of the previous step, fp32 (layer-2 input row)
+  __nv_bfloat16* cell_hb; long long chb_ld;  // [B,Sd] the same in bf16 (layer-2 GEMM operand), or null
 };
+
+// LSTM cell, one unit: gates (i,f,g,o pre-activations) -> activations in place; returns h, writes c
+__device__ __forceinline__ float lstm_cell_unit(float4* gp, float cp, float* c_out) {
+  const float4 g = *gp;
+  float4 a;
+  a.x = sigmoidf_acc(g.x); a.y = sigmoidf_acc(g.y); a.z = tanhf(g.z); a.w = sigmoidf_acc(g.w);
+  const float c = a.y * cp + a.x * a.z;
+  *gp = a;
+  *c_out = c;
+  return a.w * tanhf(c);
+}
 
 // hi = rn_tf32(v), lo = rn_tf32(v - hi): the operand split of the tf32 x 3 GEMM (gemm_tc.cu), fused into the producers
 __device__ __forceinline__ void put_hi_lo(float* hi, float* lo, size_t i, float v) {
@@ -63,7 +81,15 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
   float* xrow = a.xin1 + (size_t)b * a.xin1_ld;
   const int tk = a.tok ? a.tok[(size_t)b * a.tok_ld] : 0;
   for (int k = tid; k < a.Sd; k += blockDim.x) {
-    const float h = a.h1prev ? a.h1prev[(size_t)b * a.h1_ld + k] : 0.f;
+    float h;
+    if (a.cell_gates) {
+      const float cp = a.cell_cprev ? a.cell_cprev[(size_t)b * a.ccp_ld + k] : 0.f;
+      h = lstm_cell_unit(reinterpret_cast<float4*>(a.cell_gates + (size_t)b * a.cg_ld) + k, cp, a.cell_cout + (size_t)b * a.cco_ld + k);
+      a.cell_hout[(size_t)b * a.cho_ld + k] = h;
+      if (a.cell_hb) a.cell_hb[(size_t)b * a.chb_ld + k] = __float2bfloat16(h);
+    } else {
+      h = a.h1prev ? a.h1prev[(size_t)b * a.h1_ld + k] : 0.f;
+    }
     hs[k] = h;
     xrow[a.Sd + a.E + k] = h;
     const float e = a.emb_w ? a.emb_w[(size_t)tk * a.Sd + k] : 0.f;
@@ -243,7 +269,38 @@ struct AttnBwd {
   float* de; long long de_ld;                // [B,Tp] out: dL/d(energy) of this step (accumulated into denc/dpsi later)
   float* dqpre; long long dqpre_ld;          // [B,M] out
   float* dh1att;                             // [B,Sd] out
+  // optional: the layer-1 cell backward of the PREVIOUS step (the one whose h1 was this step's query) fused into the epilogue:
+  // dh1 = dh1att (local) + cb_dh_a + cb_dh_b; dh1att is then not written
+  float* cb_act; long long cba_ld;           // [B,4Sd] activations -> gate gradients, in place
+  const float* cb_c; long long cbc_ld;       // [B,Sd] c1 of that step
+  const float* cb_cprev; long long cbp_ld;   // [B,Sd] c1 of the step before it, or null
+  const float* cb_dh_a; long long cbda_ld;   // [B,Sd] dh1 from layer 2
+  const float* cb_dh_b; long long cbdb_ld;   // [B,Sd] dh1 from the recurrent input of this step's layer-1 cell
+  float* cb_dcstate;                         // [B,Sd] running dc1
+  __nv_bfloat16* cb_dgb;                     // [B,4Sd] bf16 copy of the gate gradients, or null
 };
+
+// LSTM cell backward, one unit (act = activations i,f,g,o -> gate gradients in place)
+__device__ __forceinline__ void lstm_cell_unit_bwd(float4* ap, float dh, float cv, float cp, float dcr, float* dc_out,
+                                                   __nv_bfloat16* dgb4 /*4 bf16 of this unit, or null*/) {
+  const float4 a = *ap;
+  const float tc = tanhf(cv);
+  const float dc = dh * a.w * (1.f - tc * tc) + dcr;
+  float4 dg;
+  dg.w = dh * tc * a.w * (1.f - a.w);
+  dg.x = dc * a.z * a.x * (1.f - a.x);
+  dg.z = dc * a.x * (1.f - a.z * a.z);
+  dg.y = dc * cp * a.y * (1.f - a.y);
+  *ap = dg;
+  *dc_out = dc * a.y;
+  if (dgb4) {
+    __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&b01);
+    pk.y = *reinterpret_cast<uint32_t*>(&b23);
+    *reinterpret_cast<uint2*>(dgb4) = pk;
+  }
+}
 
 // shared memory (floats): dcs[E] als[Tp] das[Tp] dqs[M] scratch[32] part[max(8*M, 4*Sd)]
 static size_t attn_bwd_smem_bytes(int Sd, int M, int Tp, int E) {
@@ -361,6 +418,21 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
     }
   }
   __syncthreads();
+  // unit k of this utterance: publish dh1att, or run the previous step's layer-1 cell backward with it right here
+  auto finish = [&](int k, float dh_att) {
+    if (!a.cb_act) {
+      a.dh1att[(size_t)b * a.Sd + k] = dh_att;
+      return;
+    }
+    // same summation order as cell_bwd_kernel: dh_a + dh_b + dh_c
+    float dh = a.cb_dh_a[(size_t)b * a.cbda_ld + k];
+    dh += a.cb_dh_b[(size_t)b * a.cbdb_ld + k];
+    dh += dh_att;
+    const size_t i = (size_t)b * a.Sd + k;
+    lstm_cell_unit_bwd(reinterpret_cast<float4*>(a.cb_act + (size_t)b * a.cba_ld) + k, dh, a.cb_c[(size_t)b * a.cbc_ld + k],
+                       a.cb_cprev ? a.cb_cprev[(size_t)b * a.cbp_ld + k] : 0.f, a.cb_dcstate[i], a.cb_dcstate + i,
+                       a.cb_dgb ? a.cb_dgb + i * 4 : nullptr);
+  };
   // ---- dh = phi^T dq: thread = (4 columns of phi, one of 4 row groups) ----
   if (vec && a.Sd <= 256) {
     const int grp = tid >> 6, k = (tid & 63) * 4;
@@ -385,12 +457,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
     }
     __syncthreads();
     for (int kk = tid; kk < a.Sd; kk += blockDim.x)
-      a.dh1att[(size_t)b * a.Sd + kk] = part[kk] + part[a.Sd + kk] + part[2 * a.Sd + kk] + part[3 * a.Sd + kk];
+      finish(kk, part[kk] + part[a.Sd + kk] + part[2 * a.Sd + kk] + part[3 * a.Sd + kk]);
   } else {
     for (int k = tid; k < a.Sd; k += blockDim.x) {
       float sv = 0.f;
       for (int m = 0; m < a.M; ++m) sv = fmaf(dqs[m], a.phi_w[(size_t)m * a.Sd + k], sv);
-      a.dh1att[(size_t)b * a.Sd + k] = sv;
+      finish(k, sv);
     }
   }
 }
@@ -444,14 +516,8 @@ __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long lo
   if (i >= B * S) return;
   const int b = i / S, u = i % S;
   float4* gp = reinterpret_cast<float4*>(gates + (size_t)b * g_ld) + u;
-  const float4 g = *gp;
-  float4 a;
-  a.x = sigmoidf_acc(g.x); a.y = sigmoidf_acc(g.y); a.z = tanhf(g.z); a.w = sigmoidf_acc(g.w);
   const float cp = cprev ? cprev[(size_t)b * cp_ld + u] : 0.f;
-  const float c = a.y * cp + a.x * a.z;
-  *gp = a;
-  cout[(size_t)b * c_ld + u] = c;
-  const float h = a.w * tanhf(c);
+  const float h = lstm_cell_unit(gp, cp, cout + (size_t)b * c_ld + u);
   hout[(size_t)b * h_ld + u] = h;
   if (hb_out) hb_out[(size_t)b * hb_ld + u] = __float2bfloat16(h);
   if (x3h) put_hi_lo(x3h, x3l, (size_t)b * x3_ld + u, h);
@@ -475,27 +541,9 @@ __global__ void cell_bwd_kernel(int B, int S, float* __restrict__ act, long long
   float dh = dh_a[(size_t)b * da_ld + u];
   if (dh_b) dh += dh_b[(size_t)b * db_ld + u];
   if (dh_c) dh += dh_c[(size_t)b * dc_ld + u];
-  float4* ap = reinterpret_cast<float4*>(act + (size_t)b * a_ld) + u;
-  const float4 a = *ap;
-  const float cv = c[(size_t)b * c_ld + u];
-  const float cp = cprev ? cprev[(size_t)b * cp_ld + u] : 0.f;
-  const float dcr = first ? 0.f : dcstate[i];
-  const float tc = tanhf(cv);
-  const float dc = dh * a.w * (1.f - tc * tc) + dcr;
-  float4 dg;
-  dg.w = dh * tc * a.w * (1.f - a.w);
-  dg.x = dc * a.z * a.x * (1.f - a.x);
-  dg.z = dc * a.x * (1.f - a.z * a.z);
-  dg.y = dc * cp * a.y * (1.f - a.y);
-  *ap = dg;
-  dcstate[i] = dc * a.y;
-  if (dgb) {
-    __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&b01);
-    pk.y = *reinterpret_cast<uint32_t*>(&b23);
-    *reinterpret_cast<uint2*>(dgb + (size_t)b * 4 * S + (size_t)u * 4) = pk;
-  }
+  lstm_cell_unit_bwd(reinterpret_cast<float4*>(act + (size_t)b * a_ld) + u, dh, c[(size_t)b * c_ld + u],
+                     cprev ? cprev[(size_t)b * cp_ld + u] : 0.f, first ? 0.f : dcstate[i], dcstate + i,
+                     dgb ? dgb + (size_t)b * 4 * S + (size_t)u * 4 : nullptr);
 }
 
 __global__ void emb_grad_add_kernel(int B, int Sd, const float* __restrict__ demb, long long ld, const int* __restrict__ tok,
@@ -894,8 +942,19 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     }
     return gemm_f32(st, B, 4 * Sd, K, x, ldx, 1, w, K, 1, out, U * 4 * Sd, bias, 0, 0);
   };
-  for (int t = 0; t < U; ++t) {
-    AttnFwd f;
+  const size_t lp_smem = lp_smem_bytes(C, Sd);
+  const bool lp_fused = C <= 64 && lp_smem <= 160 * 1024;
+  if (lp_fused && lp_smem > 48 * 1024) {
+    static size_t lp_attr = 0;
+    if (lp_smem > lp_attr) {
+      SSASR_CHECK_CUDA(cudaFuncSetAttribute(logits_pick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
+      lp_attr = lp_smem;
+    }
+  }
+  auto mode_of = [&](int t) { return a->step_mode ? a->step_mode[t] : 0; };
+  // attention step t (+ the step's input row); fuse_prev: the layer-1 cell of step t-1 runs in its prologue
+  auto attn_step = [&](int t, bool fuse_prev) {
+    AttnFwd f{};
     f.Tp = Tp; f.E = E; f.Sd = Sd; f.M = M;
     f.h1prev = t ? a->xin2 + (size_t)(t - 1) * X2 : nullptr; f.h1_ld = (long long)U * X2;
     f.phi_w = a->phi_w; f.psi = a->psi; f.enc = a->enc; f.enc_lens = a->enc_lens;
@@ -905,70 +964,104 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     f.x3h = x3 ? xh : nullptr; f.x3l = x3 ? xl : nullptr; f.x3_ld = X1;
     f.q = a->q + (size_t)t * M; f.q_ld = (long long)U * M;
     f.alpha = a->alpha + (size_t)t * Tp; f.alpha_ld = (long long)U * Tp;
-    // the token of this step was selected from the previous step's layer-2 output
-    if (dual && t > 0 && a->step_mode && a->step_mode[t - 1] != 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[U + t - 1], 0));
-    { ProfScope ps(F_ATTN_FWD, st); attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f); }
-    // layer 1
-    rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
-    if (rc) return rc;
-    { ProfScope ps(F_POINTWISE, st); }
-    // writes h1(t) into the layer-2 input row; single stream (and step 0): also copies h2(t-1) next to it
-    const bool copy_h2 = !dual || t == 0;
+    if (fuse_prev) {
+      f.cell_gates = a->act1 + (size_t)(t - 1) * 4 * Sd; f.cg_ld = (long long)U * 4 * Sd;
+      f.cell_cprev = t > 1 ? a->c1 + (size_t)(t - 2) * Sd : nullptr; f.ccp_ld = (long long)U * Sd;
+      f.cell_cout = a->c1 + (size_t)(t - 1) * Sd; f.cco_ld = (long long)U * Sd;
+      f.cell_hout = a->xin2 + (size_t)(t - 1) * X2; f.cho_ld = (long long)U * X2;
+      f.cell_hb = x2b_at(t - 1); f.chb_ld = X2;
+    }
+    ProfScope ps(F_ATTN_FWD, st);
+    attn_fwd_kernel<<<B, 256, attn_smem, st>>>(f);
+  };
+  // layer-1 cell of step t as its own launch: h1(t) into the layer-2 input row; copy_h2: h2(t-1) (or zeros) next to it
+  auto cell1 = [&](int t, bool copy_h2) {
+    ProfScope ps(F_POINTWISE, st);
     cell_fwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd, a->xin2 + (size_t)t * X2,
                                                  (long long)U * X2, t ? a->h2all + (size_t)(t - 1) * Sd : nullptr,
                                                  (long long)U * Sd, copy_h2 ? a->xin2 + (size_t)t * X2 + Sd : nullptr,
                                                  (long long)U * X2, x2b_at(t), X2, Sd, x3 ? xh : nullptr, x3 ? xl : nullptr, X2);
-    if (dual) SSASR_HANDOVER(side->ev[t], st, sb);
-    // layer 2
-    rc = gate_gemm(sb, a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd, x2b_at(t));
-    if (rc) return rc;
-    { ProfScope ps(F_POINTWISE, sb); }
-    const bool fwd_h2 = dual && t + 1 < U;      // h2(t) goes straight into the next step's layer-2 input row
-    cell_fwd_kernel<<<cell_blocks, 256, 0, sb>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
-                                                 t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
-                                                 a->c2 + (size_t)t * Sd, (long long)U * Sd, a->h2all + (size_t)t * Sd,
-                                                 (long long)U * Sd, nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0,
-                                                 fwd_h2 ? a->xin2 + (size_t)(t + 1) * X2 + Sd : nullptr, (long long)U * X2,
-                                                 fwd_h2 ? x2b_at(t + 1) + Sd : nullptr, X2);
-    const int mode = a->step_mode ? a->step_mode[t] : 0;
-    // token selection consumes h2(t): it runs on the layer-2 stream
-    if (mode != 0 && t + 1 < U) {
-      const size_t lp_smem = lp_smem_bytes(C, Sd);
-      const bool fused = C <= 64 && lp_smem <= 160 * 1024;
-      if (fused) {          // projection + selection in one launch (mode 3: projection only, the LM kernel selects)
-        static size_t lp_attr = 0;
-        if (lp_smem > 48 * 1024 && lp_smem > lp_attr) {
-          SSASR_CHECK_CUDA(cudaFuncSetAttribute(logits_pick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp_smem));
-          lp_attr = lp_smem;
-        }
-        ProfScope ps(F_POINTWISE, sb);
-        logits_pick_kernel<<<(B + 8 * LP_UPW - 1) / (8 * LP_UPW), 256, lp_smem, sb>>>(B, C, Sd, a->h2all + (size_t)t * Sd, (long long)U * Sd, a->wc, a->bc,
-                                                              a->logits + (size_t)t * C, (long long)U * C, mode == 3 ? 0 : mode,
-                                                              a->seed, (unsigned long long)t, a->tok_in + t + 1, U);
-      } else {
-        rc = gemm_f32(sb, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc,
-                      0, 0);
+  };
+  // layer 2 of step t on stream s2 (+ token selection for step t+1, which consumes h2(t))
+  auto layer2 = [&](int t, cudaStream_t s2) -> int {
+    int r = gate_gemm(s2, a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd, x2b_at(t));
+    if (r) return r;
+    const bool fwd_h2 = dual && t + 1 < U;      // two streams: h2(t) goes straight into the next step's layer-2 input row
+    {
+      ProfScope ps(F_POINTWISE, s2);
+      cell_fwd_kernel<<<cell_blocks, 256, 0, s2>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+                                                   t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
+                                                   a->c2 + (size_t)t * Sd, (long long)U * Sd, a->h2all + (size_t)t * Sd,
+                                                   (long long)U * Sd, nullptr, 0, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0,
+                                                   fwd_h2 ? a->xin2 + (size_t)(t + 1) * X2 + Sd : nullptr, (long long)U * X2,
+                                                   fwd_h2 ? x2b_at(t + 1) + Sd : nullptr, X2);
+    }
+    const int mode = mode_of(t);
+    if (mode == 0 || t + 1 >= U) return 0;
+    if (lp_fused) {          // projection + selection in one launch (mode 3: projection only, the LM kernel selects)
+      ProfScope ps(F_POINTWISE, s2);
+      logits_pick_kernel<<<(B + 8 * LP_UPW - 1) / (8 * LP_UPW), 256, lp_smem, s2>>>(
+          B, C, Sd, a->h2all + (size_t)t * Sd, (long long)U * Sd, a->wc, a->bc, a->logits + (size_t)t * C, (long long)U * C,
+          mode == 3 ? 0 : mode, a->seed, (unsigned long long)t, a->tok_in + t + 1, U);
+    } else {
+      r = gemm_f32(s2, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc, 0, 0);
+      if (r) return r;
+    }
+    if (mode == 3) {
+      SSASR_REQUIRE(a->lm_emb && a->lm_h1 && a->lm_h2 && a->lm_H > 0, "speller: step mode 3 needs the language-model arguments");
+      LmStep l;
+      l.C = C; l.H = a->lm_H;
+      l.emb = a->lm_emb; l.w1i = a->lm_w1i; l.w1h = a->lm_w1h; l.b1i = a->lm_b1i; l.b1h = a->lm_b1h;
+      l.w2i = a->lm_w2i; l.w2h = a->lm_w2h; l.b2i = a->lm_b2i; l.b2h = a->lm_b2h; l.wo = a->lm_wo; l.bo = a->lm_bo;
+      l.h1 = a->lm_h1; l.h2 = a->lm_h2; l.weight = a->lm_weight;
+      l.logits = a->logits + (size_t)t * C; l.logits_ld = (long long)U * C;
+      l.tok_in = a->tok_in + t; l.tok_out = a->tok_in + t + 1; l.tok_ld = U;
+      const int nt = ((a->lm_H + 31) / 32) * 32 > 256 ? 256 : ((a->lm_H + 31) / 32) * 32;
+      ProfScope ps(F_POINTWISE, s2);
+      lm_pick_kernel<<<B, nt, (size_t)(5 * a->lm_H + C + 32) * sizeof(float), s2>>>(l);
+    } else if (!lp_fused) {
+      ProfScope ps(F_POINTWISE, s2);
+      pick_token_kernel<<<(B + 127) / 128, 128, 0, s2>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
+                                                         (unsigned long long)t, a->tok_in + t + 1, U);
+    }
+    if (dual) SSASR_CHECK_CUDA(cudaEventRecord(side->ev[U + t], s2));   // the next step's token is ready
+    return 0;
+  };
+  if (!dual) {
+    for (int t = 0; t < U; ++t) {
+      attn_step(t, false);
+      rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
+      if (rc) return rc;
+      cell1(t, true);
+      rc = layer2(t, st);
+      if (rc) return rc;
+    }
+  } else {
+    // Two streams.  `st`: attention -> layer-1 gate GEMM (-> layer-1 cell); `sb`: layer-2 GEMM -> cell (-> token selection).
+    // The layer-1 cell of a teacher-forced step is deferred into the prologue of the next attention step (one launch less on
+    // the dependent chain); where the next token is sampled from this step's output it must run now, because the selection
+    // (on `sb`) needs h1(t) -> h2(t) before the next attention step can start.
+    auto deferred = [&](int t) { return t >= 1 && t + 1 < U && mode_of(t) == 0; };
+    for (int t = 0; t < U; ++t) {
+      const bool prev_def = t > 0 && deferred(t - 1);
+      // the token of this step was selected from the previous step's layer-2 output
+      if (t > 0 && mode_of(t - 1) != 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[U + t - 1], 0));
+      attn_step(t, prev_def);
+      if (prev_def) {
+        SSASR_HANDOVER(side->ev[t - 1], st, sb);
+        rc = layer2(t - 1, sb);
         if (rc) return rc;
       }
-      { ProfScope ps(F_POINTWISE, sb); }
-      if (mode == 3) {
-        SSASR_REQUIRE(a->lm_emb && a->lm_h1 && a->lm_h2 && a->lm_H > 0, "speller: step mode 3 needs the language-model arguments");
-        LmStep l;
-        l.C = C; l.H = a->lm_H;
-        l.emb = a->lm_emb; l.w1i = a->lm_w1i; l.w1h = a->lm_w1h; l.b1i = a->lm_b1i; l.b1h = a->lm_b1h;
-        l.w2i = a->lm_w2i; l.w2h = a->lm_w2h; l.b2i = a->lm_b2i; l.b2h = a->lm_b2h; l.wo = a->lm_wo; l.bo = a->lm_bo;
-        l.h1 = a->lm_h1; l.h2 = a->lm_h2; l.weight = a->lm_weight;
-        l.logits = a->logits + (size_t)t * C; l.logits_ld = (long long)U * C;
-        l.tok_in = a->tok_in + t; l.tok_out = a->tok_in + t + 1; l.tok_ld = U;
-        const int nt = ((a->lm_H + 31) / 32) * 32 > 256 ? 256 : ((a->lm_H + 31) / 32) * 32;
-        lm_pick_kernel<<<B, nt, (size_t)(5 * a->lm_H + C + 32) * sizeof(float), sb>>>(l);
-      } else if (!fused) {
-        pick_token_kernel<<<(B + 127) / 128, 128, 0, sb>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, mode, a->seed,
-                                                           (unsigned long long)t, a->tok_in + t + 1, U);
+      rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
+      if (rc) return rc;
+      if (!deferred(t)) {
+        cell1(t, t == 0);
+        SSASR_HANDOVER(side->ev[t], st, sb);
+        rc = layer2(t, sb);
+        if (rc) return rc;
       }
-      if (dual) SSASR_CHECK_CUDA(cudaEventRecord(side->ev[U + t], sb));   // next step's token is ready
     }
   }
   if (dual) SSASR_HANDOVER(side->ev[2 * U], sb, st);
@@ -1067,26 +1160,32 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     }
     return gemm_f32(st, 4 * Sd, N, B * U, dg, 4 * Sd, 0, x, N, 0, out, N, nullptr, 0, 0);
   };
-  for (int t = U - 1; t >= 0; --t) {
+  // layer-2 cell backward + its dgrad GEMM for step t on stream s2 (two streams: own gate-gradient scratch, one dxin2 block per step)
+  auto layer2_bwd = [&](int t, cudaStream_t s2) -> int {
     const int last = (t == U - 1);
-    { ProfScope ps(F_POINTWISE, sb); }
-    cell_bwd_kernel<<<cell_blocks, 256, 0, sb>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
-                                                 a->c2 + (size_t)t * Sd, (long long)U * Sd,
-                                                 t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
-                                                 a->dh2all + (size_t)t * Sd, (long long)U * Sd,
-                                                 last ? nullptr : dxin2_at(t + 1) + Sd, (long long)X2, nullptr, 0, a->dc2s, last, dgb2);
-    rc = dgrad_gemm(sb, dgb2, a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, dxin2_at(t), X2);
-    if (rc) return rc;
-    if (dual) SSASR_HANDOVER(side->ev[t], sb, st);
-    { ProfScope ps(F_POINTWISE, st); }
+    {
+      ProfScope ps(F_POINTWISE, s2);
+      cell_bwd_kernel<<<cell_blocks, 256, 0, s2>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
+                                                   a->c2 + (size_t)t * Sd, (long long)U * Sd,
+                                                   t ? a->c2 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd,
+                                                   a->dh2all + (size_t)t * Sd, (long long)U * Sd,
+                                                   last ? nullptr : dxin2_at(t + 1) + Sd, (long long)X2, nullptr, 0, a->dc2s, last, dgb2);
+    }
+    return dgrad_gemm(s2, dgb2, a->act2 + (size_t)t * 4 * Sd, X2, a->w2cat, a->w2catT_bf, dxin2_at(t), X2);
+  };
+  // layer-1 cell backward of step t as its own launch
+  auto cell1_bwd = [&](int t) {
+    const int last = (t == U - 1);
+    ProfScope ps(F_POINTWISE, st);
     cell_bwd_kernel<<<cell_blocks, 256, 0, st>>>(B, Sd, a->act1 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd,
                                                  t ? a->c1 + (size_t)(t - 1) * Sd : nullptr, (long long)U * Sd, dxin2_at(t),
                                                  (long long)X2, last ? nullptr : a->dxin1 + (size_t)(t + 1) * X1 + K1,
                                                  (long long)U * X1, last ? nullptr : a->dh1att, (long long)Sd, a->dc1s, last, dgb);
-    rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
-    if (rc) return rc;
-    AttnBwd g;
+  };
+  // attention backward of step t; fuse_prev: the layer-1 cell backward of step t-1 (whose h1 was this step's query) in its epilogue
+  auto attn_bwd = [&](int t, bool fuse_prev) {
+    AttnBwd g{};
     g.Tp = Tp; g.E = E; g.Sd = Sd; g.M = M;
     g.dctx = a->dxin1 + (size_t)t * X1 + Sd; g.dctx_ld = (long long)U * X1;
     g.alpha = a->alpha + (size_t)t * Tp; g.alpha_ld = (long long)U * Tp;
@@ -1096,7 +1195,48 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     g.de = a->de_all + (size_t)t * Tp; g.de_ld = (long long)U * Tp;
     g.dqpre = a->dqpre + (size_t)t * M; g.dqpre_ld = (long long)U * M;
     g.dh1att = a->dh1att;
-    { ProfScope ps(F_ATTN_BWD, st); attn_bwd_kernel<<<B, 256, attn_smem, st>>>(g); }
+    if (fuse_prev) {
+      g.cb_act = a->act1 + (size_t)(t - 1) * 4 * Sd; g.cba_ld = (long long)U * 4 * Sd;
+      g.cb_c = a->c1 + (size_t)(t - 1) * Sd; g.cbc_ld = (long long)U * Sd;
+      g.cb_cprev = t > 1 ? a->c1 + (size_t)(t - 2) * Sd : nullptr; g.cbp_ld = (long long)U * Sd;
+      g.cb_dh_a = dxin2_at(t - 1); g.cbda_ld = X2;
+      g.cb_dh_b = a->dxin1 + (size_t)t * X1 + K1; g.cbdb_ld = (long long)U * X1;
+      g.cb_dcstate = a->dc1s;
+      g.cb_dgb = dgb;
+    }
+    ProfScope ps(F_ATTN_BWD, st);
+    attn_bwd_kernel<<<B, 256, attn_smem, st>>>(g);
+  };
+  if (!dual) {
+    for (int t = U - 1; t >= 0; --t) {
+      rc = layer2_bwd(t, st);
+      if (rc) return rc;
+      cell1_bwd(t);
+      rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
+      if (rc) return rc;
+      attn_bwd(t, false);
+    }
+  } else {
+    // Two streams.  `sb`: the layer-2 chain, issued one step ahead of its consumer; `st`: layer-1 dgrad GEMM -> attention
+    // backward, whose epilogue runs the layer-1 cell backward of the step below it (one launch less on the dependent chain).
+    rc = layer2_bwd(U - 1, sb);
+    if (rc) return rc;
+    SSASR_CHECK_CUDA(cudaEventRecord(side->ev[U - 1], sb));
+    for (int t = U - 1; t >= 0; --t) {
+      if (t > 0) {
+        rc = layer2_bwd(t - 1, sb);
+        if (rc) return rc;
+        SSASR_CHECK_CUDA(cudaEventRecord(side->ev[t - 1], sb));
+      }
+      if (t == U - 1) {
+        SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[t], 0));
+        cell1_bwd(t);
+      }
+      rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
+      if (rc) return rc;
+      if (t > 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[t - 1], 0));   // dh1(t-1) from layer 2
+      attn_bwd(t, t > 0);
+    }
   }
   // attention memory gradients, accumulated over all steps at once
   {
@@ -1145,7 +1285,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
 int ssasr_attn_step_fwd(int B, int Tp, int E, int Sd, int M, const float* h, const float* phi_w, const float* psi,
                         const float* enc, const int* enc_lens, float* xrow, float* q, float* alpha, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  AttnFwd f;
+  AttnFwd f{};
   f.Tp = Tp; f.E = E; f.Sd = Sd; f.M = M;
   f.h1prev = h; f.h1_ld = Sd; f.phi_w = phi_w; f.psi = psi; f.enc = enc; f.enc_lens = enc_lens;
   f.emb_w = nullptr; f.tok = nullptr; f.tok_ld = 0;
@@ -1165,7 +1305,7 @@ int ssasr_attn_step_bwd(int B, int Tp, int E, int Sd, int M, const float* dctx, 
                         const float* q, const float* phi_w, const float* psi, const float* enc, const int* enc_lens, float* de,
                         float* dqpre, float* dh, float* denc, float* dpsi, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  AttnBwd g;
+  AttnBwd g{};
   g.Tp = Tp; g.E = E; g.Sd = Sd; g.M = M;
   g.dctx = dctx; g.dctx_ld = E; g.alpha = alpha; g.alpha_ld = Tp; g.q = q; g.q_ld = M;
   g.phi_w = phi_w; g.psi = psi; g.enc = enc; g.enc_lens = enc_lens;
