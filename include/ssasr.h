@@ -147,6 +147,8 @@ typedef struct {
   void *wsA, *wsB;                   /* bf16 scratch: >= max(4Sd*BUp, M*BTp) and >= max(X1*BUp, E*BTp + E*M) elements */
   long long BUp, BTp;                /* B*U and B*Tp rounded up to multiples of 8 */
   int dual_stream;                   /* bf16 mode: dxin2 holds U*B*X2 floats; layer-2 chain on an internal second stream */
+  void* wgrad_stream;                /* optional, with dual_stream: the products only the optimiser consumes (all weight / bias /
+                                        embedding gradients) go to this stream, ordered after the loop and NOT joined into `stream` */
 } ssasr_speller_bwd_args;
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream);
 

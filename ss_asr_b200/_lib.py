@@ -32,7 +32,7 @@ class SpellerBwdArgs(C.Structure):
                                            'd_emb_w', 'd_wc', 'd_bc', 'denc',
                                            'dh2all', 'dxin1', 'dxin2', 'dc1s', 'dc2s', 'dh1att', 'dpsi', 'dqpre', 'de_all',
                                            'w1catT_bf', 'w2catT_bf', 'wsA', 'wsB')] +
-                [('BUp', C.c_longlong), ('BTp', C.c_longlong), ('dual_stream', C.c_int)])
+                [('BUp', C.c_longlong), ('BTp', C.c_longlong), ('dual_stream', C.c_int), ('wgrad_stream', C.c_void_p)])
 
 
 class OptimTensor(C.Structure):

@@ -1098,6 +1098,10 @@ typedef struct {
   // bf16 mode only: dxin2 holds U*B*X2 floats (one block per step) and the layer-2 chain may run on an internal second
   // stream, joined into `stream` before the call returns
   int dual_stream;
+  // optional (two-stream bf16 mode only): every product that only the optimiser consumes (all weight / bias / embedding
+  // gradients) is enqueued on this stream, ordered after the loop, and NOT joined into `stream`: the caller joins it before it
+  // reads the gradients.  `stream` then carries just what the encoder's backward needs (denc).
+  void* wgrad_stream;
 } ssasr_speller_bwd_args;
 
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
@@ -1111,7 +1115,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   const bool tc0 = a->w1catT_bf && a->w2catT_bf && a->wsA && a->wsB && a->BUp >= (long long)B * U && a->BUp % 8 == 0 &&
                    a->BTp >= (long long)B * Tp && a->BTp % 8 == 0 && Sd % 8 == 0 && E % 8 == 0 && M % 8 == 0;
   // out[Mo,No] = X^T Y over R rows (X [R,Mo] ldx, Y [R,No] ldy): tensor cores through transposed bf16 copies, or fp32
-  auto xty = [&](const float* X, int ldx, int Mo, const float* Y, int ldy, int No, long long R, long long Rp, float* out) -> int {
+  auto xty = [&](cudaStream_t st, const float* X, int ldx, int Mo, const float* Y, int ldy, int No, long long R, long long Rp, float* out) -> int {
     if (tc0) {     // row-major bf16 copies, MN-major tcgen05 operands
       const int Mp = (Mo + 7) / 8 * 8, Np = (No + 7) / 8 * 8;
       int r = cvt_bf16(st, X, ldx, a->wsA, Mp, R, Mo);
@@ -1122,11 +1126,6 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     }
     return gemm_f32(st, Mo, No, (int)R, X, ldx, 0, Y, ldy, 0, out, No, nullptr, 0, 0);
   };
-  rc = xty(a->dlogits, C, C, a->h2all, Sd, Sd, (long long)B * U, a->BUp, a->d_wc);
-  if (rc) return rc;
-  rc = colsum(st, a->dlogits, a->d_bc, B * U, C, C, 0);
-  if (rc) return rc;
-  SSASR_CHECK_CUDA(cudaMemsetAsync(a->d_emb_w, 0, sizeof(float) * (size_t)C * Sd, st));
   const size_t attn_smem = attn_bwd_smem_bytes(Sd, M, Tp, E);
   SSASR_REQUIRE(attn_smem <= 200 * 1024 && (size_t)U * 8 * sizeof(float) <= 48 * 1024, "speller bwd: attention working set too large (Tp=%d, U=%d)", Tp, U);
   if (attn_smem > 48 * 1024)
@@ -1150,7 +1149,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   };
   if (dual) SSASR_HANDOVER(side->ev[U], st, sb);
   // dW = dG_all^T @ X_all over all B*U rows
-  auto wgrad_gemm = [&](const float* dg, const float* x, int N, float* out) -> int {
+  auto wgrad_gemm = [&](cudaStream_t st, const float* dg, const float* x, int N, float* out) -> int {
     if (tc) {
       int r = cvt_bf16(st, dg, 4 * Sd, a->wsA, 4 * Sd, (long long)B * U, 4 * Sd);
       if (r) return r;
@@ -1238,33 +1237,19 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
       attn_bwd(t, t > 0);
     }
   }
-  // attention memory gradients, accumulated over all steps at once
+  // attention memory gradients, accumulated over all steps at once; then denc += dpsi_pre @ Wpsi completes what the encoder needs
   {
     ProfScope ps(F_ATTN_BWD, st);
     attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, (size_t)U * 8 * sizeof(float), st>>>(
         U, Tp, E, a->alpha, a->dxin1 + Sd, X1, (long long)U * X1, a->denc, a->enc_lens);
     attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, (size_t)U * 8 * sizeof(float), st>>>(
         U, Tp, M, a->de_all, a->q, M, (long long)U * M, a->dpsi, a->enc_lens);
-    emb_grad_add_kernel<<<(B * U * Sd + 255) / 256, 256, 0, st>>>(B * U, Sd, a->dxin1, X1, a->tok_in, 1, a->d_emb_w);
   }
-  // weight gradients, batched over all steps
-  rc = wgrad_gemm(a->act1, a->xin1, X1, a->d_w1cat);
-  if (rc) return rc;
-  rc = colsum(st, a->act1, a->d_b1, B * U, 4 * Sd, 4 * Sd, 0);
-  if (rc) return rc;
-  rc = wgrad_gemm(a->act2, a->xin2, X2, a->d_w2cat);
-  if (rc) return rc;
-  rc = colsum(st, a->act2, a->d_b2, B * U, 4 * Sd, 4 * Sd, 0);
-  if (rc) return rc;
-  rc = xty(a->dqpre, M, M, a->xin1 + K1, X1, Sd, (long long)B * U, a->BUp, a->d_phi_w);
-  if (rc) return rc;
-  { ProfScope ps(F_POINTWISE, st); }
-  dtanh_inplace_kernel<<<256, 256, 0, st>>>(a->dpsi, a->psi, (size_t)B * Tp * M);
-  rc = xty(a->dpsi, M, M, a->enc, E, E, (long long)B * Tp, a->BTp, a->d_psi_w);
-  if (rc) return rc;
-  rc = colsum(st, a->dpsi, a->d_psi_b, B * Tp, M, M, 0);
-  if (rc) return rc;
-  if (tc0) {      // denc += dpsi_pre @ Wpsi
+  {
+    ProfScope ps(F_POINTWISE, st);
+    dtanh_inplace_kernel<<<256, 256, 0, st>>>(a->dpsi, a->psi, (size_t)B * Tp * M);
+  }
+  if (tc0) {
     __nv_bfloat16* wT = (__nv_bfloat16*)a->wsB;              // [E, M]
     rc = cvt_bf16_t(st, a->psi_w, E, wT, M, M, E, 0, 0, 0, 0);
     if (rc) return rc;
@@ -1274,6 +1259,36 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   } else {
     rc = gemm_f32(st, B * Tp, E, M, a->dpsi, M, 1, a->psi_w, E, 0, a->denc, E, nullptr, 1, 0);
   }
+  if (rc) return rc;
+  // everything below is consumed by the optimiser only
+  cudaStream_t sw = st;
+  if (dual && a->wgrad_stream && (cudaStream_t)a->wgrad_stream != st) {
+    sw = (cudaStream_t)a->wgrad_stream;
+    SSASR_HANDOVER(side->ev[U + 1], st, sw);      // also orders the scratch (wsA / wsB) reuse below after the GEMM above
+  }
+  rc = xty(sw, a->dlogits, C, C, a->h2all, Sd, Sd, (long long)B * U, a->BUp, a->d_wc);
+  if (rc) return rc;
+  rc = colsum(sw, a->dlogits, a->d_bc, B * U, C, C, 0);
+  if (rc) return rc;
+  SSASR_CHECK_CUDA(cudaMemsetAsync(a->d_emb_w, 0, sizeof(float) * (size_t)C * Sd, sw));
+  {
+    ProfScope ps(F_POINTWISE, sw);
+    emb_grad_add_kernel<<<(B * U * Sd + 255) / 256, 256, 0, sw>>>(B * U, Sd, a->dxin1, X1, a->tok_in, 1, a->d_emb_w);
+  }
+  // weight gradients, batched over all steps
+  rc = wgrad_gemm(sw, a->act1, a->xin1, X1, a->d_w1cat);
+  if (rc) return rc;
+  rc = colsum(sw, a->act1, a->d_b1, B * U, 4 * Sd, 4 * Sd, 0);
+  if (rc) return rc;
+  rc = wgrad_gemm(sw, a->act2, a->xin2, X2, a->d_w2cat);
+  if (rc) return rc;
+  rc = colsum(sw, a->act2, a->d_b2, B * U, 4 * Sd, 4 * Sd, 0);
+  if (rc) return rc;
+  rc = xty(sw, a->dqpre, M, M, a->xin1 + K1, X1, Sd, (long long)B * U, a->BUp, a->d_phi_w);
+  if (rc) return rc;
+  rc = xty(sw, a->dpsi, M, M, a->enc, E, E, (long long)B * Tp, a->BTp, a->d_psi_w);
+  if (rc) return rc;
+  rc = colsum(sw, a->dpsi, a->d_psi_b, B * Tp, M, M, 0);
   if (rc) return rc;
   SSASR_LAUNCH_CHECK();
   return 0;

@@ -224,6 +224,7 @@ class _Spell(torch.autograd.Function):
                 w_hh2, b_ih2, b_hh2, emb_w, wc, bc):
         lib = _lib.load()
         _lib.require_cuda(enc, 'Speller')
+        ctx.param_refs = (phi_w, psi_w, psi_b, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2, w_hh2, b_ih2, b_hh2, emb_w, wc, bc)
         skip_final = 0
         if isinstance(lm, dict):          # {'lm': (weights, weight) or None, 'need_logits': bool}
             skip_final = 0 if lm.get('need_logits', True) else 1
@@ -310,6 +311,15 @@ class _Spell(torch.autograd.Function):
             wsB = bf(max(X1 * BUp, E * BTp + E * M, Sd * BUp))
             check(lib.ssasr_cvt_bf16_t(ptr(w1cat), X1, ptr(w1T), 4 * Sd, 4 * Sd, X1, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
             check(lib.ssasr_cvt_bf16_t(ptr(w2cat), X2, ptr(w2T), 4 * Sd, 4 * Sd, X2, 0, 0, 0, 0, st), 'ssasr_cvt_bf16_t')
+        # The gradients only the optimiser reads can be left to the side stream of the deferred encoder weight gradients (same
+        # opt-in, same conditions: fresh .grad so that autograd adopts the returned buffers, joined by join_deferred()); they
+        # then run under the latency-bound recurrent backward of encoder.blstm_4 (16 of 148 SMs busy).  Outputs are allocated
+        # BEFORE the call: whatever used that memory earlier is ordered before the side stream's first write.
+        fresh = all(getattr(w, 'grad', None) is None for w in ctx.param_refs)
+        side = side_stream(dev) if (ctx.dual and _OVERLAP['on'] and fresh) else None
+        z = lambda *s: torch.zeros(*s, device=dev)
+        g1 = [z(4 * Sd, K1), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
+        g2 = [z(4 * Sd, Sd), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
         a = _lib.SpellerBwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
                                 w1cat=ptr(w1cat), w2cat=ptr(w2cat), wc=ptr(wc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
                                 tok_in=ptr(tok_in), psi=ptr(psi), xin1=ptr(xin1), xin2=ptr(xin2), c1=ptr(c1), c2=ptr(c2),
@@ -320,13 +330,17 @@ class _Spell(torch.autograd.Function):
                                 dh2all=ptr(scr[0]), dxin1=ptr(scr[1]), dxin2=ptr(scr[2]), dc1s=ptr(scr[3]),
                                 dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]), de_all=ptr(scr[8]),
                                 w1catT_bf=ptr(w1T), w2catT_bf=ptr(w2T), wsA=ptr(wsA), wsB=ptr(wsB), BUp=BUp, BTp=BTp,
-                                dual_stream=int(ctx.dual))
+                                dual_stream=int(ctx.dual), wgrad_stream=side.cuda_stream if side else None)
         check(lib.ssasr_speller_bwd_f32(C.byref(a), st), 'ssasr_speller_bwd_f32')
-        z = lambda *s: torch.zeros(*s, device=dev)
-        g1 = [z(4 * Sd, K1), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
-        g2 = [z(4 * Sd, Sd), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
-        check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w1cat), ptr(d_b1), Sd, K1, *[ptr(t) for t in g1], st), 'unpack1')
-        check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w2cat), ptr(d_b2), Sd, Sd, *[ptr(t) for t in g2], st), 'unpack2')
+        ust = side.cuda_stream if side else st
+        check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w1cat), ptr(d_b1), Sd, K1, *[ptr(t) for t in g1], ust), 'unpack1')
+        check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w2cat), ptr(d_b2), Sd, Sd, *[ptr(t) for t in g2], ust), 'unpack2')
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            # everything the side stream still reads or writes, EXCEPT the returned gradient buffers (AccumulateGrad only adopts
+            # a buffer it holds the sole reference to; otherwise it clones it on the main stream, before it has been written)
+            _OVERLAP['pending'].append((ev, (ctx.saved_tensors, dlogits, scr, wsA, wsB, w1T, w2T, d_w1cat, d_b1, d_w2cat, d_b2)))
         return (denc, None, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
 
 

@@ -564,7 +564,7 @@ def test_fused_adadelta_clip_step_matches_torch():
 
 
 def test_deferred_weight_gradients_match():
-    """functional.set_overlap_wgrad: encoder weight-gradient GEMMs on a second stream, joined by the consumers
+    """functional.set_overlap_wgrad: Speller and encoder weight-gradient GEMMs on a second stream, joined by the consumers
     (FusedAdadelta.step_clipped / join_deferred).  Same gradients and same parameter update as the in-order schedule."""
     from ss_asr_b200 import functional as Fk
     from ss_asr_b200.functional import asr_loss
@@ -585,7 +585,7 @@ def test_deferred_weight_gradients_match():
                 _, logits, _ = m(x.to(DEV), 7, teacher=y.to(DEV), state_len=lens)
                 asr_loss(logits, y.to(DEV)).backward()
                 if on:
-                    assert len(Fk._OVERLAP['pending']) == 4          # one deferred batch per encoder layer
+                    assert len(Fk._OVERLAP['pending']) == 5          # the Speller's + one deferred batch per encoder layer
                 Fk.join_deferred()
                 grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
                 opt.step_clipped(5.0)
