@@ -214,7 +214,7 @@ class ASR(nn.Module):
         self.decode_precision = 'fp32'   # 'tf32x3': encoder input projections of decode_batch on tensor cores
         self.sample_seed = 0
         self.last_tokens = None          # [B,U] int32: the input token of every step of the last forward
-        self.decode_encoder_chunk = 256  # decode_batch: utterances per Listener pass (0 = one pass over the whole batch)
+        self.decode_encoder_chunk = 512  # decode_batch: utterances per Listener pass (0 = one pass over the whole batch)
         self.init_parameters()
 
     # ------------------------------------------------------------------------------------------
@@ -276,7 +276,7 @@ class ASR(nn.Module):
             else:
                 # utterances are independent and sorted by length: the Listener runs over groups of `chunk` utterances, each
                 # only as many frames deep as ITS longest utterance (the recurrent kernels are bound by dependent steps, so
-                # the padded tail of a short group is pure waste); one tile per CTA in the recurrent kernels at <= 256 rows
+                # the padded tail of a short group is pure waste)
                 enc, enc_len = None, []
                 for r0 in range(0, N, chunk):
                     r1 = min(N, r0 + chunk)
