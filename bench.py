@@ -176,7 +176,7 @@ def run_reference(args):
             'cpu_baseline': {'value': v, 'unit': 'utt/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 def workload_config(n):
@@ -395,7 +395,7 @@ def run_ours(args):
                 'e2e': {'value': e2e_value, 'unit': 'utt/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'extra': extra}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -528,6 +528,9 @@ def run_c5(dev):
             'ms_per_step': ms, 'utt_per_s': 32 / ms * 1e3}
 
 
+_JSON_OUT = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -540,10 +543,18 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help='bf16: tcgen05 gate GEMMs (fp32 accumulate, fp32 recurrence); fp32: exact SIMT path')
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL's version banner when NCCL_DEBUG=VERSION comes
+    # from the environment or from nccl.conf): file descriptor 1 is pointed at stderr for the whole run and the JSON line goes
+    # to a private duplicate of the original stdout.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:
         run_ours(args)
+    _JSON_OUT.flush()
 
 
 if __name__ == '__main__':

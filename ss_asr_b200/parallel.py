@@ -76,10 +76,13 @@ class GradSync:
         inv = 1.0 / self.world
         for bucket, flat, work in self.pending:
             work.wait()
+            if flat.is_cuda:
+                flat.record_stream(torch.cuda.current_stream())
+            flat.mul_(inv)                      # one launch per bucket; the gradients become views of the reduced buffer
             off = 0
             for p in bucket['params']:
                 n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad)).mul_(inv)
+                p.grad = flat[off:off + n].view_as(p)
                 off += n
         self.pending = []
 
