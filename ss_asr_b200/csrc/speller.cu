@@ -67,6 +67,43 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b, float s) {
 // shared memory (floats): hs[Sd] qs[M] es[Tp] scratch[32] part[2*E]
 static size_t attn_fwd_smem_bytes(int Sd, int M, int Tp, int E) { return (size_t)(Sd + M + ((Tp + 3) & ~3) + 32 + 2 * E) * sizeof(float); }
 
+// rows[m0 .. m0+R) . x for a warp: lane holds I float4 of each row (row length K <= 128 * I), all R * I loads are issued
+// before the first use; returns the R warp-reduced dot products in out[] (every lane holds all of them).
+// R x I is chosen per shape so that a lane keeps 16 independent 128-bit loads in flight.
+template <int R, int I>
+__device__ __forceinline__ void warp_rows_dot(const float* __restrict__ rows, int ld, int K, int r0, int r_end, const float* xs /*smem*/,
+                                              int lane, float* out) {
+  float4 w[R][I];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int i = 0; i < I; ++i) {
+      const int k = (i * 32 + lane) * 4;
+      w[r][i] = (r0 + r < r_end && k < K) ? __ldg(reinterpret_cast<const float4*>(rows + (size_t)(r0 + r) * ld + k))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = 0.f;
+#pragma unroll
+  for (int i = 0; i < I; ++i) {
+    const int k = (i * 32 + lane) * 4;
+    if (k < K) {
+      const float4 x4 = *reinterpret_cast<const float4*>(xs + k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = dot4(w[r][i], x4, out[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = warp_sum(out[r]);
+}
+template <int R>
+__device__ __forceinline__ float pick_lane(const float* v, int lane) {
+  float s = v[0];
+#pragma unroll
+  for (int r = 1; r < R; ++r) s = (lane == r) ? v[r] : s;
+  return s;
+}
+
 // Every phase is a batch of INDEPENDENT 128-bit loads issued before the first use (the per-utterance working set - phi 128 KB,
 // psi~ 32 KB, encoder states 128 KB at the default sizes - streams from L2, so the phases are latency-bound unless many loads
 // are in flight), followed by the arithmetic and a shuffle / shared-memory reduction.
@@ -108,36 +145,24 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
   const float* psib = a.psi + (size_t)b * a.Tp * a.M;
   const float* encb = a.enc + (size_t)b * a.Tp * a.E;
   const bool vec = ((a.Sd | a.M | a.E) & 3) == 0 && al16(a.phi_w) && al16(psib) && al16(encb);
-  // ---- q = tanh(phi h): a warp takes 4 rows of phi at a time ----
+  // ---- q = tanh(phi h): a warp takes 8 (Sd <= 256) or 4 rows of phi at a time ----
   if (vec && a.Sd <= 512) {
-    const int nk = a.Sd >> 7;                           // float4 per lane per row (Sd = 128 * nk + remainder handled below)
-    for (int m0 = warp * 4; m0 < a.M; m0 += nwarp * 4) {
-      float4 w[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = (i * 32 + lane) * 4;
-          w[r][i] = (m0 + r < a.M && k < a.Sd) ? __ldg(reinterpret_cast<const float4*>(a.phi_w + (size_t)(m0 + r) * a.Sd + k))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = (i * 32 + lane) * 4;
-        if (k < a.Sd) {
-          const float4 h4 = *reinterpret_cast<const float4*>(hs + k);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) acc[r] = dot4(w[r][i], h4, acc[r]);
-        }
+    auto put_q = [&](int m, float acc) {
+      const float qv = tanhf(acc);
+      qs[m] = qv;
+      a.q[(size_t)b * a.q_ld + m] = qv;
+    };
+    if (a.Sd <= 256) {
+      for (int m0 = warp * 8; m0 < a.M; m0 += nwarp * 8) {
+        float acc[8];
+        warp_rows_dot<8, 2>(a.phi_w, a.Sd, a.Sd, m0, a.M, hs, lane, acc);
+        if (lane < 8 && m0 + lane < a.M) put_q(m0 + lane, pick_lane<8>(acc, lane));
       }
-      (void)nk;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
-      if (lane < 4 && m0 + lane < a.M) {
-        const float qv = tanhf(lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]);
-        qs[m0 + lane] = qv;
-        a.q[(size_t)b * a.q_ld + m0 + lane] = qv;
+    } else {
+      for (int m0 = warp * 4; m0 < a.M; m0 += nwarp * 4) {
+        float acc[4];
+        warp_rows_dot<4, 4>(a.phi_w, a.Sd, a.Sd, m0, a.M, hs, lane, acc);
+        if (lane < 4 && m0 + lane < a.M) put_q(m0 + lane, pick_lane<4>(acc, lane));
       }
     }
   } else {
@@ -153,33 +178,19 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     }
   }
   __syncthreads();
-  // ---- energies e_j = psi~_j . q: a warp takes 4 frames at a time ----
+  // ---- energies e_j = psi~_j . q: a warp takes 8 (M <= 128) or 4 frames at a time; frames >= len are never loaded ----
   if (vec && a.M <= 256) {
-    for (int j0 = warp * 4; j0 < a.Tp; j0 += nwarp * 4) {
-      float4 w[4][2];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int m = (i * 32 + lane) * 4;
-          w[r][i] = (j0 + r < len && m < a.M) ? __ldg(reinterpret_cast<const float4*>(psib + (size_t)(j0 + r) * a.M + m))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int m = (i * 32 + lane) * 4;
-        if (m < a.M) {
-          const float4 q4 = *reinterpret_cast<const float4*>(qs + m);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) acc[r] = dot4(w[r][i], q4, acc[r]);
-        }
+    if (a.M <= 128) {
+      for (int j0 = warp * 8; j0 < a.Tp; j0 += nwarp * 8) {
+        float acc[8];
+        warp_rows_dot<8, 1>(psib, a.M, a.M, j0, len, qs, lane, acc);
+        if (lane < 8 && j0 + lane < a.Tp) es[j0 + lane] = (j0 + lane < len) ? pick_lane<8>(acc, lane) : -INFINITY;
       }
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
-      if (lane < 4 && j0 + lane < a.Tp) {
-        const float sv = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-        es[j0 + lane] = (j0 + lane < len) ? sv : -INFINITY;
+    } else {
+      for (int j0 = warp * 4; j0 < a.Tp; j0 += nwarp * 4) {
+        float acc[4];
+        warp_rows_dot<4, 2>(psib, a.M, a.M, j0, len, qs, lane, acc);
+        if (lane < 4 && j0 + lane < a.Tp) es[j0 + lane] = (j0 + lane < len) ? pick_lane<4>(acc, lane) : -INFINITY;
       }
     }
   } else {
@@ -213,20 +224,20 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     a.alpha[(size_t)b * a.alpha_ld + j] = al;
   }
   __syncthreads();
-  // ---- context c = sum_j alpha_j h_j: thread = (4 columns, frame parity), 8 frames of loads in flight ----
+  // ---- context c = sum_j alpha_j h_j: thread = (4 columns, frame parity), 16 frames of loads in flight ----
   if (vec) {
     const int half = tid >> 7, c4 = tid & 127;
     for (int c = c4 * 4; c < a.E; c += 512) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int j0 = half; j0 < len; j0 += 16) {
-        float4 v[8];
+      for (int j0 = half; j0 < len; j0 += 32) {
+        float4 v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const int j = j0 + 2 * u;
           v[u] = (j < len) ? __ldg(reinterpret_cast<const float4*>(encb + (size_t)j * a.E + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const int j = j0 + 2 * u;
           const float al = (j < len) ? es[j] : 0.f;
           acc.x = fmaf(al, v[u].x, acc.x); acc.y = fmaf(al, v[u].y, acc.y);
@@ -324,34 +335,22 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
   const float* encb = a.enc + (size_t)b * a.Tp * a.E;
   const float* psib = a.psi + (size_t)b * a.Tp * a.M;
   const bool vec = ((a.Sd | a.M | a.E) & 3) == 0 && al16(a.phi_w) && al16(psib) && al16(encb);
-  // ---- dalpha_j = dctx . h_j: a warp takes 2 frames at a time, up to 8 float4 per lane and frame in flight ----
+  // ---- dalpha_j = dctx . h_j: a warp takes 4 (E <= 512) or 2 frames at a time, 16 float4 per lane in flight ----
   if (vec && a.E <= 1024) {
-    for (int j0 = warp * 2; j0 < a.Tp; j0 += nwarp * 2) {
-      float4 w[2][8];
-#pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = (i * 32 + lane) * 4;
-          w[r][i] = (j0 + r < len && c < a.E) ? __ldg(reinterpret_cast<const float4*>(encb + (size_t)(j0 + r) * a.E + c))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      float acc[2] = {0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = (i * 32 + lane) * 4;
-        if (c < a.E) {
-          const float4 d4 = *reinterpret_cast<const float4*>(dcs + c);
-          acc[0] = dot4(w[0][i], d4, acc[0]);
-          acc[1] = dot4(w[1][i], d4, acc[1]);
-        }
+    auto put_da = [&](int j, float dot) {
+      das[j] = ((j < len) ? dot : 0.f) + ((a.dalpha && j < len) ? a.dalpha[(size_t)b * a.dalpha_ld + j] : 0.f);
+    };
+    if (a.E <= 512) {
+      for (int j0 = warp * 4; j0 < a.Tp; j0 += nwarp * 4) {
+        float acc[4];
+        warp_rows_dot<4, 4>(encb, a.E, a.E, j0, len, dcs, lane, acc);
+        if (lane < 4 && j0 + lane < a.Tp) put_da(j0 + lane, pick_lane<4>(acc, lane));
       }
-      acc[0] = warp_sum(acc[0]);
-      acc[1] = warp_sum(acc[1]);
-      if (lane < 2 && j0 + lane < a.Tp) {
-        const int j = j0 + lane;
-        const float sv = (j < len) ? (lane == 0 ? acc[0] : acc[1]) : 0.f;
-        das[j] = sv + ((a.dalpha && j < len) ? a.dalpha[(size_t)b * a.dalpha_ld + j] : 0.f);
+    } else {
+      for (int j0 = warp * 2; j0 < a.Tp; j0 += nwarp * 2) {
+        float acc[2];
+        warp_rows_dot<2, 8>(encb, a.E, a.E, j0, len, dcs, lane, acc);
+        if (lane < 2 && j0 + lane < a.Tp) put_da(j0 + lane, pick_lane<2>(acc, lane));
       }
     }
   } else {
@@ -438,15 +437,15 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
     const int grp = tid >> 6, k = (tid & 63) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < a.Sd) {
-      for (int m0 = grp; m0 < a.M; m0 += 32) {
-        float4 v[8];
+      for (int m0 = grp; m0 < a.M; m0 += 64) {
+        float4 v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const int m = m0 + 4 * u;
           v[u] = (m < a.M) ? __ldg(reinterpret_cast<const float4*>(a.phi_w + (size_t)m * a.Sd + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const int m = m0 + 4 * u;
           const float dq = (m < a.M) ? dqs[m] : 0.f;
           acc.x = fmaf(dq, v[u].x, acc.x); acc.y = fmaf(dq, v[u].y, acc.y);
