@@ -110,9 +110,13 @@ class Listener(nn.Module):
         return self.out_dim
 
     def forward(self, x, state_len, pack_input=True):
+        t_in = x.shape[1]
         x, _, state_len = self.blstm_1(x, state_len=state_len, pack_input=pack_input)
         x, _, state_len = self.blstm_2(x, state_len=state_len, pack_input=pack_input)
         x, _, state_len = self.blstm_3(x, state_len=state_len, pack_input=pack_input)
+        if x.shape[1] == 0:
+            raise RuntimeError('Listener: at least 8 input frames are needed (three frame-pair reductions leave none of %d); '
+                               'the reference fails in nn.LSTM at the same point (asr.py:262)' % int(t_in))
         x = x.contiguous()
         if self.utterance_independent:
             # bs=1 semantics for every utterance at once: one cell step from zero state per frame

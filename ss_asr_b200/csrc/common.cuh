@@ -87,7 +87,9 @@ int gemm_f32(cudaStream_t st, int M, int N, int K, const float* A, int lda, int 
 // bf16 tensor-core GEMM (gemm_tc.cu): C[M,N] fp32 (+)= A[M,K] x B[N,K]^T (+bias); A,B bf16 with K contiguous;
 // a_koff/b_koff shift the reduction window inside each operand's rows.
 int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
-                 int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh = 0);
+                 int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh = 0, int splits = 1);
+//   splits > 1 (small products on 128 x 32 tiles only): split-K, every split ADDS its partial to C with red.add -- the caller
+//   pre-zeroes C; with two splits the sum is order-independent, i.e. still deterministic
 // C[M,N] fp32 (+)= A^T B with A stored [K,M], B stored [K,N] (row-major bf16, 16-byte row pitches); koffs shift rows
 int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                     int b_koff, float* C, int ldc, int accumulate);

@@ -90,7 +90,8 @@ __device__ __forceinline__ void epi_chunk(float* stage, const uint32_t* v, float
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(256, (BN * 64 + 8192) * STAGES * 2 <= 100 * 1024 ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-               int ldc, const float* __restrict__ bias, int M, int N, int K, int a_koff, int b_koff, int accumulate, int act_tanh) {
+               int ldc, const float* __restrict__ bias, int M, int N, int K, int a_koff, int b_koff, int accumulate, int act_tanh,
+               int kb_per_split) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -103,7 +104,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // blockIdx.x (fastest in launch order) walks the N tiles of one 128-row block of A: the block is read from HBM once and
   // serves all its column tiles out of L2, B (the weights) stays L2-resident throughout
   const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * BN;
-  const int num_k = (K + GT_BK - 1) / GT_BK;
+  // split-K (grid.z > 1, the latency-bound per-step products of the decoder loop: halves the bytes every SM has to pull
+  // through its L2 port): each CTA reduces kb_per_split k-blocks and adds its partial to the pre-zeroed output with red.add
+  const int kb_all = (K + GT_BK - 1) / GT_BK;
+  const int kb_first = blockIdx.z * kb_per_split;
+  const int num_k = min(kb_per_split, kb_all - kb_first);
+  const bool atomic_out = gridDim.z > 1;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -129,8 +135,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty_bar + s, ph ^ 1);
         mbar_expect_tx(full_bar + s, L::STAGE_BYTES);
         uint8_t* st = smem + s * L::STAGE_BYTES;
-        tma_load_2d(&tmA, full_bar + s, st, a_koff + kb * GT_BK, m0);
-        tma_load_2d(&tmB, full_bar + s, st + L::A_BYTES, b_koff + kb * GT_BK, n0);
+        tma_load_2d(&tmA, full_bar + s, st, a_koff + (kb_first + kb) * GT_BK, m0);
+        tma_load_2d(&tmB, full_bar + s, st + L::A_BYTES, b_koff + (kb_first + kb) * GT_BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -162,7 +168,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      epi_chunk<false>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, bias, accumulate, act_tanh);
+      if (atomic_out) epi_chunk<true>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, blockIdx.z == 0 ? bias : nullptr, 0, 0);
+      else epi_chunk<false>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, bias, accumulate, act_tanh);
     }
   }
   tc_fence_before();
@@ -575,7 +582,7 @@ int make_tmap_bf16_3d_ex(CUtensorMap* m, const void* ptr, long long cols, long l
 
 template <int BN, int STAGES>
 static int launch_gemm_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
-                          int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
+                          int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh, int splits) {
   using L = GemmSmem<BN, STAGES>;
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16(&tmA, A, M, (long long)a_koff + K, lda, GT_BM);
@@ -589,14 +596,21 @@ static int launch_gemm_tc(cudaStream_t st, int M, int N, int K, const void* A, l
   }
   dim3 grid((N + BN - 1) / BN, (M + GT_BM - 1) / GT_BM);
   SSASR_REQUIRE(grid.y <= 65535, "gemm_bf16_tc: M=%d too large", M);
+  const int kb_all = (K + GT_BK - 1) / GT_BK;
+  if (splits > kb_all) splits = kb_all;
+  if (splits < 1) splits = 1;
+  const int kb_per = (kb_all + splits - 1) / splits;
+  grid.z = (kb_all + kb_per - 1) / kb_per;
+  SSASR_REQUIRE(grid.z == 1 || (!accumulate && !act_tanh), "gemm_bf16_tc: split-K adds into a pre-zeroed output (no accumulate / tanh)");
   ProfScope ps(F_GEMM_TC, st);
-  gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, bias, M, N, K, a_koff, b_koff, accumulate, act_tanh);
+  gemm_tc_kernel<BN, STAGES><<<grid, 256, L::TOTAL + 1024, st>>>(tmA, tmB, C, ldc, bias, M, N, K, a_koff, b_koff, accumulate, act_tanh,
+                                                                  kb_per);
   SSASR_LAUNCH_CHECK();
   return 0;
 }
 
 int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
-                 int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
+                 int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh, int splits) {
   if (M <= 0 || N <= 0) return 0;
   SSASR_REQUIRE(K > 0, "gemm_bf16_tc: K must be positive");
   SSASR_REQUIRE(a_koff % 8 == 0 && b_koff % 8 == 0, "gemm_bf16_tc: reduction offsets must be multiples of 8 elements (TMA 16-byte "
@@ -605,8 +619,8 @@ int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long 
   // Small products (the per-step speller GEMMs, 256 rows) use 128 x 32 tiles to spread over 4x as many SMs.
   const long long tiles128 = (long long)((M + GT_BM - 1) / GT_BM) * ((N + 127) / 128);
   if (tiles128 < sm_count() / 2 && N >= 64)
-    return launch_gemm_tc<32, 4>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh);
-  return launch_gemm_tc<128, 3>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh);
+    return launch_gemm_tc<32, 4>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh, splits);
+  return launch_gemm_tc<128, 3>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh, 1);
 }
 
 // ---- fp32 -> bf16 conversion (optionally transposed, optionally masking a periodic column) ----------

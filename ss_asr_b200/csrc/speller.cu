@@ -6,6 +6,7 @@
 // Everything stays on the device for all U steps (the reference syncs to the host every step,
 // asr.py:103); attention maps are written straight into the stacked [B,U,T'] layout.
 #include "common.cuh"
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <curand_kernel.h>
 
@@ -841,6 +842,15 @@ static SideStream* side_stream(int n_events) {
   }
   return ss;
 }
+static int step_gemm_splits() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSASR_STEP_GEMM_SPLITS");
+    v = e ? atoi(e) : 1;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
 // `waiter` continues only after everything enqueued on `src` so far
 #define SSASR_HANDOVER(event, src, waiter)                   \
   do {                                                       \
@@ -932,9 +942,13 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   const bool dual = side != nullptr;
   cudaStream_t sb = dual ? side->s : st;
   auto x2b_at = [&](int t) { return (dual && x2b) ? x2b + (size_t)t * B * X2 : x2b; };
+  // the layer-1 product sits on the dependent chain and is bound by what one SM can pull through its L2 port (128 x 32 tiles:
+  // 320 KB per CTA, 64 CTAs): split-K over twice the SMs, partials added into the pre-zeroed gate buffer
+  const int chain_splits = tc ? step_gemm_splits() : 1;
+  if (chain_splits > 1) SSASR_CHECK_CUDA(cudaMemsetAsync(a->act1, 0, sizeof(float) * (size_t)B * U * 4 * Sd, st));
   auto gate_gemm = [&](cudaStream_t st, const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out,
-                       const __nv_bfloat16* xb) -> int {
-    if (tc) return gemm_bf16_tc(st, B, 4 * Sd, K, xb, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0);
+                       const __nv_bfloat16* xb, int splits = 1) -> int {
+    if (tc) return gemm_bf16_tc(st, B, 4 * Sd, K, xb, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0, 0, splits);
     if (x3) {                  // xh / xl were written by the kernel that produced x (attention step / layer-1 cell)
       const bool first = (K == X1);
       return gemm_tf32x3(st, B, 4 * Sd, K, xh, xl, K, first ? w1h : w2h, first ? w1l : w2l, K, out, U * 4 * Sd, bias, 0);
@@ -1031,7 +1045,8 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   if (!dual) {
     for (int t = 0; t < U; ++t) {
       attn_step(t, false);
-      rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
+      rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b,
+                     chain_splits);
       if (rc) return rc;
       cell1(t, true);
       rc = layer2(t, st);
@@ -1053,7 +1068,8 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
         rc = layer2(t - 1, sb);
         if (rc) return rc;
       }
-      rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b);
+      rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b,
+                     chain_splits);
       if (rc) return rc;
       if (!deferred(t)) {
         cell1(t, t == 0);
@@ -1141,9 +1157,11 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   cudaStream_t sb = dual ? side->s : st;
   __nv_bfloat16* dgb2 = dual ? dgb + (size_t)B * 4 * Sd : dgb;
   auto dxin2_at = [&](int t) { return dual ? a->dxin2 + (size_t)t * B * X2 : a->dxin2; };
+  const int chain_splits = tc ? step_gemm_splits() : 1;        // see ssasr_speller_fwd_f32
+  if (chain_splits > 1) SSASR_CHECK_CUDA(cudaMemsetAsync(a->dxin1, 0, sizeof(float) * (size_t)B * U * X1, st));
   auto dgrad_gemm = [&](cudaStream_t st, const __nv_bfloat16* dgb, const float* dg, int N, const float* w, const void* wT_bf,
-                        float* out, int ldo) -> int {
-    if (tc) return gemm_bf16_tc(st, B, N, 4 * Sd, dgb, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, ldo, nullptr, 0);
+                        float* out, int ldo, int splits = 1) -> int {
+    if (tc) return gemm_bf16_tc(st, B, N, 4 * Sd, dgb, 4 * Sd, 0, wT_bf, 4 * Sd, 0, out, ldo, nullptr, 0, 0, splits);
     return gemm_f32(st, B, N, 4 * Sd, dg, U * 4 * Sd, 1, w, N, 0, out, ldo, nullptr, 0, 0);
   };
   if (dual) SSASR_HANDOVER(side->ev[U], st, sb);
@@ -1210,7 +1228,8 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
       rc = layer2_bwd(t, st);
       if (rc) return rc;
       cell1_bwd(t);
-      rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
+      rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1,
+                      chain_splits);
       if (rc) return rc;
       attn_bwd(t, false);
     }
@@ -1230,7 +1249,8 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
         SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[t], 0));
         cell1_bwd(t);
       }
-      rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1);
+      rc = dgrad_gemm(st, dgb, a->act1 + (size_t)t * 4 * Sd, X1, a->w1cat, a->w1catT_bf, a->dxin1 + (size_t)t * X1, U * X1,
+                      chain_splits);
       if (rc) return rc;
       if (t > 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, side->ev[t - 1], 0));   // dh1(t-1) from layer 2
       attn_bwd(t, t > 0);

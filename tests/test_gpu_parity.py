@@ -758,3 +758,28 @@ def test_dual_stream_speller_is_invisible(tf_rate):
                 assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12, k
     finally:
         Fk.set_dual_stream_speller(True)
+
+
+def _pending_test_error_behaviour_matches_reference_contract():
+    """SURVEY §8b 'Errors': unsorted / zero lengths and T < 8 raise RuntimeError (pack_padded_sequence / nn.LSTM in the
+    reference, asr.py:413-418), missing lengths and bs != 1 decoding assert (asr.py:411, asr.py:125)."""
+    dims = (50, 16, 16, 8, 12)
+    sd = O.make_state_dict(*dims, seed=1)
+    m = _model(dims, sd)
+    x, lens, y = O.synth_batch(3, 32, 12, 4, seed=5)
+    with pytest.raises(RuntimeError):
+        m(x.to(DEV), 4, teacher=y.to(DEV), state_len=[20, 32, 25])          # not sorted in decreasing order
+    with pytest.raises(RuntimeError):
+        m(x.to(DEV), 4, teacher=y.to(DEV), state_len=[32, 20, 0])           # zero-length utterance
+    with pytest.raises(RuntimeError):
+        m(x[:, :7].to(DEV), 4, teacher=y.to(DEV), state_len=[7, 7, 7])      # fewer than 8 frames: nothing left after 3 halvings
+    with pytest.raises(AssertionError):
+        m.encoder.blstm_1(x.to(DEV), state_len=None, pack_input=True)
+    with pytest.raises(AssertionError):
+        m.decode(x.to(DEV), lens, None, None, 0.0)                          # ASR.decode is bs=1 only
+    # the shortest usable input: 8 frames -> one encoder frame
+    x8, l8, y8 = O.synth_batch(2, 8, 12, 3, seed=6)
+    l8 = [8, 8]
+    _, logits_o, att_o, _ = O.asr_forward(sd, x8, l8, 3, teacher=y8)
+    _, logits, att = m(x8.to(DEV), 3, teacher=y8.to(DEV), state_len=l8)
+    assert float((logits.detach().cpu() - logits_o).abs().max()) < 1e-5 and att.shape[-1] == 1
