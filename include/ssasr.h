@@ -129,6 +129,10 @@ typedef struct {
   int skip_final_logits; /* 1: do not recompute the [B,U,C] logits after the loop (greedy decoding only needs tok_in) */
   int dual_stream;       /* bf16 mode: ws_bf holds B*X1 + U*B*X2 elements (a layer-2 input block per step) and the layer-2
                             chain (asr.py:322-324) runs on an internal second stream, joined into `stream` before returning */
+  int stop_token, stop_check_every; /* greedy decoding: every `stop_check_every` steps (0 = never) the call reads back whether EVERY
+                                       utterance has emitted `stop_token` (asr.py:161-162) and stops early if so */
+  int* stop_scratch;                /* device int */
+  int* steps_run;                   /* HOST int out or NULL: decoding steps executed */
 } ssasr_speller_fwd_args;
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
 

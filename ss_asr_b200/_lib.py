@@ -20,7 +20,8 @@ class SpellerFwdArgs(C.Structure):
                 [('lm_H', C.c_int), ('lm_weight', C.c_float)] +
                 [(n, C.c_void_p) for n in ('lm_emb', 'lm_w1i', 'lm_w1h', 'lm_b1i', 'lm_b1h', 'lm_w2i', 'lm_w2h', 'lm_b2i',
                                            'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2', 'x3_ws')] +
-                [('skip_final_logits', C.c_int), ('dual_stream', C.c_int)])
+                [('skip_final_logits', C.c_int), ('dual_stream', C.c_int), ('stop_token', C.c_int), ('stop_check_every', C.c_int),
+                 ('stop_scratch', C.c_void_p), ('steps_run', C.c_void_p)])
 
 
 class SpellerBwdArgs(C.Structure):

@@ -218,16 +218,19 @@ class ASR(nn.Module):
         self.decode_precision = 'fp32'   # 'tf32x3': encoder input projections of decode_batch on tensor cores
         self.sample_seed = 0
         self.last_tokens = None          # [B,U] int32: the input token of every step of the last forward
+        self.decode_stop_check = 0       # decode_batch: steps between 'has every utterance emitted EOS?' checks (0 = never)
+        self.last_decode_steps = 0
         self.decode_encoder_chunk = 512  # decode_batch: utterances per Listener pass (0 = one pass over the whole batch)
         self.init_parameters()
 
     # ------------------------------------------------------------------------------------------
-    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None, need_logits=True):
+    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None, need_logits=True, stop_every=0):
         lens_dev = torch.tensor(enc_len, dtype=torch.int32, device=enc.device)
         params = self.attention.params() + self.decoder.params() + (self.embed.weight, self.char_trans.weight,
                                                                     self.char_trans.bias)
         self.sample_seed += 1
-        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision, lm, need_logits)
+        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision, lm, need_logits, stop_token=1,
+                        stop_every=stop_every)
 
     def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
         """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
@@ -296,8 +299,10 @@ class ASR(nn.Module):
         lm = None
         if rnn_lm is not None and lm_weight != 0:
             lm = (Fk.pack_charlm(rnn_lm, enc.device), lm_weight)
+        # the loop stops as soon as every utterance has emitted EOS (checked every `decode_stop_check` steps; asr.py:161-162)
         _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), precision=prec, lm=lm,
-                                 need_logits=False)
+                                 need_logits=False, stop_every=int(self.decode_stop_check or 0))
+        self.last_decode_steps = Fk.LAST_SPELL['steps_run']
         toks = toks[:, 1:].cpu().tolist()
         out = []
         for row in toks:

@@ -666,6 +666,19 @@ __global__ void __launch_bounds__(256) logits_pick_kernel(int B, int C, int Sd, 
   }
 }
 
+// greedy decoding: number of utterances whose selected tokens tok[b, 1 .. upto] do not contain `eos` yet
+__global__ void count_unfinished_kernel(int B, const int* __restrict__ tok, long long tok_ld, int upto, int eos, int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  bool open = false;
+  if (b < B) {
+    open = true;
+    for (int t = 1; t <= upto; ++t)
+      if (tok[(size_t)b * tok_ld + t] == eos) { open = false; break; }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, open);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+}
+
 // next-token selection from logits row (C <= 1024): mode 1 = argmax (first max index, torch.argmax),
 // mode 2 = sample from softmax (Philox; the one intentionally non-bit-reproducible branch, asr.py:97)
 __global__ void pick_token_kernel(int B, int C, const float* __restrict__ logits, long long ld, int mode, unsigned long long seed,
@@ -893,6 +906,12 @@ typedef struct {
   // bf16 mode only: ws_bf holds B*X1 + U*B*X2 elements (one layer-2 input block per step) and the layer-2 chain may run on
   // an internal second stream, joined into `stream` before the call returns
   int dual_stream;
+  // greedy decoding (every step selects its successor's token): stop as soon as EVERY utterance has emitted `stop_token`
+  // (asr.py:161-162 stops each bs=1 call at EOS; a batch is done when all of its utterances are).  Checked every
+  // `stop_check_every` steps with a 4-byte read-back and a stream synchronisation; 0 = run all U steps.
+  int stop_token, stop_check_every;
+  int* stop_scratch;      // device int
+  int* steps_run;         // HOST int out (may be NULL): decoding steps actually executed
 } ssasr_speller_fwd_args;
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
@@ -1042,6 +1061,9 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     if (dual) SSASR_CHECK_CUDA(cudaEventRecord(side->ev[U + t], s2));   // the next step's token is ready
     return 0;
   };
+  int steps_done = U;
+  const int stop_every = (!dual && a->stop_check_every > 0 && a->stop_scratch && a->skip_final_logits && a->step_mode &&
+                          a->step_mode[0] != 0 && a->step_mode[0] != 2) ? a->stop_check_every : 0;
   if (!dual) {
     for (int t = 0; t < U; ++t) {
       attn_step(t, false);
@@ -1051,6 +1073,16 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
       cell1(t, true);
       rc = layer2(t, st);
       if (rc) return rc;
+      steps_done = t + 1;
+      if (stop_every > 0 && t + 1 < U && (t + 1) % stop_every == 0) {
+        // tokens 1 .. t+1 have been selected: has every utterance emitted the stop token?
+        SSASR_CHECK_CUDA(cudaMemsetAsync(a->stop_scratch, 0, sizeof(int), st));
+        count_unfinished_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, a->tok_in, U, t + 1, a->stop_token, a->stop_scratch);
+        int open_utts = 1;
+        SSASR_CHECK_CUDA(cudaMemcpyAsync(&open_utts, a->stop_scratch, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSASR_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (open_utts == 0) break;
+      }
     }
   } else {
     // Two streams.  `st`: attention -> layer-1 gate GEMM (-> layer-1 cell); `sb`: layer-2 GEMM -> cell (-> token selection).
@@ -1080,6 +1112,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     }
   }
   if (dual) SSASR_HANDOVER(side->ev[2 * U], sb, st);
+  if (a->steps_run) *a->steps_run = steps_done;
   if (a->skip_final_logits) {        // greedy decoding only consumes the tokens
     SSASR_LAUNCH_CHECK();
     return 0;

@@ -226,8 +226,10 @@ class _Spell(torch.autograd.Function):
         _lib.require_cuda(enc, 'Speller')
         ctx.param_refs = (phi_w, psi_w, psi_b, w_ih1, w_hh1, b_ih1, b_hh1, w_ih2, w_hh2, b_ih2, b_hh2, emb_w, wc, bc)
         skip_final = 0
-        if isinstance(lm, dict):          # {'lm': (weights, weight) or None, 'need_logits': bool}
+        stop_token, stop_every = 0, 0
+        if isinstance(lm, dict):          # {'lm': (weights, weight) or None, 'need_logits': bool, 'stop_token', 'stop_every'}
             skip_final = 0 if lm.get('need_logits', True) else 1
+            stop_token, stop_every = int(lm.get('stop_token', 0)), int(lm.get('stop_every', 0))
             lm = lm.get('lm')
         enc = _f32c(enc)
         B, Tp, E = enc.shape
@@ -270,6 +272,7 @@ class _Spell(torch.autograd.Function):
             lm_state = [torch.zeros(B, H, device=dev), torch.zeros(B, H, device=dev)]
             lmk = dict(lm_H=H, lm_weight=float(lm_weight), lm_h1=ptr(lm_state[0]), lm_h2=ptr(lm_state[1]),
                        **{'lm_' + k: ptr(v) for k, v in lmt.items()})
+        steps_run = C.c_int(U)
         a = _lib.SpellerFwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
                                 psi_b=ptr(psi_b), w1cat=ptr(w1cat), b1=ptr(b1), w2cat=ptr(w2cat), b2=ptr(b2),
                                 emb_w=ptr(emb_w), wc=ptr(wc), bc=ptr(bc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
@@ -277,9 +280,13 @@ class _Spell(torch.autograd.Function):
                                 xin1=ptr(xin1), xin2=ptr(xin2), act1=ptr(act1), act2=ptr(act2), c1=ptr(c1), c2=ptr(c2),
                                 h2all=ptr(h2all), q=ptr(q), alpha=ptr(alpha), logits=ptr(logits), w1cat_bf=ptr(w1b),
                                 w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), x3_ws=ptr(x3ws),
-                                skip_final_logits=skip_final, dual_stream=int(bf16 and _DUAL_STREAM_SPELLER), **lmk)
+                                skip_final_logits=skip_final, dual_stream=int(bf16 and _DUAL_STREAM_SPELLER),
+                                stop_token=stop_token, stop_check_every=stop_every if skip_final else 0,
+                                stop_scratch=ptr(torch.zeros(1, dtype=torch.int32, device=dev)) if stop_every else None,
+                                steps_run=C.addressof(steps_run), **lmk)
         ctx.dual = bool(bf16 and _DUAL_STREAM_SPELLER)
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
+        LAST_SPELL['steps_run'] = int(steps_run.value)
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
         ctx.dims = (B, Tp, E, Sd, M, Cc, U)
@@ -344,9 +351,13 @@ class _Spell(torch.autograd.Function):
         return (denc, None, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
 
 
-def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32', lm=None, need_logits=True):
+LAST_SPELL = {'steps_run': 0}     # decoding steps the last attend-and-spell call executed (early stop of greedy decoding)
+
+
+def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32', lm=None, need_logits=True, stop_token=0,
+          stop_every=0):
     """need_logits=False (greedy decoding): the [B,U,C] logits tensor is not recomputed after the loop (left undefined)."""
-    opts = lm if need_logits else {'lm': lm, 'need_logits': False}
+    opts = lm if need_logits else {'lm': lm, 'need_logits': False, 'stop_token': stop_token, 'stop_every': stop_every}
     return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, opts, *params)
 
 

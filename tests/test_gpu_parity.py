@@ -783,3 +783,33 @@ def _pending_test_error_behaviour_matches_reference_contract():
     _, logits_o, att_o, _ = O.asr_forward(sd, x8, l8, 3, teacher=y8)
     _, logits, att = m(x8.to(DEV), 3, teacher=y8.to(DEV), state_len=l8)
     assert float((logits.detach().cpu() - logits_o).abs().max()) < 1e-5 and att.shape[-1] == 1
+
+
+def _pending_test_decode_batch_stops_when_every_utterance_has_emitted_eos():
+    """decode_batch leaves the attend-and-spell loop once all utterances have produced EOS (asr.py:161-162 per utterance);
+    the transcripts are those of the full-length loop and of the oracle's bs=1 decode."""
+    dims = (50, 32, 32, 16, 20)
+    sd = O.make_state_dict(*dims, seed=1)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 20
+    g = torch.Generator().manual_seed(9)
+    Ts = sorted([int(v) for v in torch.randint(16, 60, (9,), generator=g)], reverse=True)
+    xb = torch.zeros(len(Ts), Ts[0], 20)
+    for i, t in enumerate(Ts):
+        xb[i, :t] = torch.randn(t, 20, generator=g)
+    for eos_bias, expect_early in ((0.0, False), (2.5, True), (50.0, True)):
+        sd2 = dict(sd)
+        b = sd['char_trans.bias'].clone()
+        b[1] = eos_bias
+        sd2['char_trans.bias'] = b
+        m = _model(dims, sd2).eval()
+        want = [O.decode_greedy(sd2, xb[i:i + 1, :t], [t], max_steps=40) for i, t in enumerate(Ts)]
+        m.decode_stop_check = 0
+        full = m.decode_batch(xb.to(DEV), Ts, max_steps=40)
+        assert m.last_decode_steps == 41
+        m.decode_stop_check = 4
+        early = m.decode_batch(xb.to(DEV), Ts, max_steps=40)
+        assert full == early == [list(w) for w in want], eos_bias
+        if expect_early and max(len(w) for w in want) < 30:
+            assert m.last_decode_steps % 4 == 0 and max(len(w) for w in want) < m.last_decode_steps <= max(len(w) for w in want) + 5
+        if eos_bias == 50.0:
+            assert all(len(w) == 0 for w in want) and m.last_decode_steps == 4
