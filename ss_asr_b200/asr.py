@@ -218,7 +218,7 @@ class ASR(nn.Module):
         self.decode_precision = 'fp32'   # 'tf32x3': encoder input projections of decode_batch on tensor cores
         self.sample_seed = 0
         self.last_tokens = None          # [B,U] int32: the input token of every step of the last forward
-        self.decode_stop_check = 0       # decode_batch: steps between 'has every utterance emitted EOS?' checks (0 = never)
+        self.decode_stop_check = 16      # decode_batch: steps between 'has every utterance emitted EOS?' checks (0 = never)
         self.last_decode_steps = 0
         self.decode_encoder_chunk = 512  # decode_batch: utterances per Listener pass (0 = one pass over the whole batch)
         self.init_parameters()

@@ -859,7 +859,7 @@ static int step_gemm_splits() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SSASR_STEP_GEMM_SPLITS");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 2;
     if (v < 1) v = 1;
   }
   return v;

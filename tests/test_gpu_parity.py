@@ -760,7 +760,7 @@ def test_dual_stream_speller_is_invisible(tf_rate):
         Fk.set_dual_stream_speller(True)
 
 
-def _pending_test_error_behaviour_matches_reference_contract():
+def test_error_behaviour_matches_reference_contract():
     """SURVEY §8b 'Errors': unsorted / zero lengths and T < 8 raise RuntimeError (pack_padded_sequence / nn.LSTM in the
     reference, asr.py:413-418), missing lengths and bs != 1 decoding assert (asr.py:411, asr.py:125)."""
     dims = (50, 16, 16, 8, 12)
@@ -785,7 +785,7 @@ def _pending_test_error_behaviour_matches_reference_contract():
     assert float((logits.detach().cpu() - logits_o).abs().max()) < 1e-5 and att.shape[-1] == 1
 
 
-def _pending_test_decode_batch_stops_when_every_utterance_has_emitted_eos():
+def test_decode_batch_stops_when_every_utterance_has_emitted_eos():
     """decode_batch leaves the attend-and-spell loop once all utterances have produced EOS (asr.py:161-162 per utterance);
     the transcripts are those of the full-length loop and of the oracle's bs=1 decode."""
     dims = (50, 32, 32, 16, 20)
