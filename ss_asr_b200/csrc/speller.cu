@@ -468,10 +468,64 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwd a) {
 }
 
 // After the loop: out[b,j,:] = sum_t w[b,t,j] * v[b,t,:]   (denc from alpha x dctx, dpsi from de x q).
-// One CTA per (utterance, 8-frame block); w tile in smem, v streamed with coalesced loads.
+// One CTA per (utterance, 16-frame block): w tile in smem; thread = (4 columns of v, one group of the block's frames), v
+// streamed as 128-bit loads, four decoding steps in flight per thread.  D % 4 == 0 and D / 4 <= 256.
+constexpr int OA_FB = 16;     // frames per CTA
+constexpr int OA_FPG = 8;     // at most this many frames per thread
 __global__ void __launch_bounds__(256) attn_outer_accum_kernel(int U, int Tp, int D, const float* __restrict__ w /*[B,U,Tp]*/,
                                                                const float* __restrict__ v, long long v_ld_t, long long v_ld_b,
                                                                float* __restrict__ out /*[B,Tp,D]*/, const int* __restrict__ lens) {
+  extern __shared__ float ws[];     // [U][OA_FB]
+  const int b = blockIdx.y, j0 = blockIdx.x * OA_FB;
+  const int len = lens[b];
+  float* ob = out + ((size_t)b * Tp + j0) * D;
+  const int nf = min(OA_FB, Tp - j0);      // frames of this block
+  if (j0 >= len) {                  // fully padded frame block: gradient is exactly zero
+    for (int i = threadIdx.x; i < nf * D; i += blockDim.x) ob[i] = 0.f;
+    return;
+  }
+  for (int i = threadIdx.x; i < U * OA_FB; i += blockDim.x) {
+    const int t = i / OA_FB, jj = i % OA_FB;
+    ws[i] = (jj < nf) ? w[((size_t)b * U + t) * Tp + j0 + jj] : 0.f;
+  }
+  __syncthreads();
+  const int d4 = D >> 2;                           // float4 columns
+  const int groups = max(1, min((int)blockDim.x / d4, OA_FB));   // frame groups that fit beside the columns
+  const int fpg = (OA_FB + groups - 1) / groups;   // frames per group (<= OA_FPG by the launcher's contract)
+  const int c4 = threadIdx.x % d4, g = threadIdx.x / d4;
+  if (g >= groups) return;
+  const int f0 = g * fpg;
+  const float* vb = v + (size_t)b * v_ld_b + (size_t)c4 * 4;
+  float4 acc[OA_FPG];
+#pragma unroll
+  for (int jj = 0; jj < OA_FPG; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = 0; t0 < U; t0 += 4) {
+    float4 d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      d[k] = (t0 + k < U) ? __ldg(reinterpret_cast<const float4*>(vb + (size_t)(t0 + k) * v_ld_t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (t0 + k >= U) break;
+      const float* wr = ws + (t0 + k) * OA_FB + f0;
+#pragma unroll
+      for (int jj = 0; jj < OA_FPG; ++jj) {
+        if (jj < fpg) {
+          const float wv = wr[jj];
+          acc[jj].x = fmaf(wv, d[k].x, acc[jj].x); acc[jj].y = fmaf(wv, d[k].y, acc[jj].y);
+          acc[jj].z = fmaf(wv, d[k].z, acc[jj].z); acc[jj].w = fmaf(wv, d[k].w, acc[jj].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < OA_FPG; ++jj)
+    if (jj < fpg && f0 + jj < nf) *reinterpret_cast<float4*>(ob + (size_t)(f0 + jj) * D + (size_t)c4 * 4) = acc[jj];
+}
+// generic fallback (any D): one CTA per (utterance, 8-frame block), scalar columns
+__global__ void __launch_bounds__(256) attn_outer_accum8_kernel(int U, int Tp, int D, const float* __restrict__ w /*[B,U,Tp]*/,
+                                                                const float* __restrict__ v, long long v_ld_t, long long v_ld_b,
+                                                                float* __restrict__ out /*[B,Tp,D]*/, const int* __restrict__ lens) {
   extern __shared__ float ws[];     // [U][8]
   const int b = blockIdx.y, j0 = blockIdx.x * 8;
   const int len = lens[b];
@@ -500,6 +554,22 @@ __global__ void __launch_bounds__(256) attn_outer_accum_kernel(int U, int Tp, in
     for (int jj = 0; jj < 8; ++jj)
       if (j0 + jj < Tp) ob[(size_t)jj * D + c] = acc[jj];
   }
+}
+// out[b,j,:] = sum_t w[b,t,j] * v[b,t,:] on stream st
+static int attn_outer_accum(cudaStream_t st, int B, int U, int Tp, int D, const float* w, const float* v, long long v_ld_t, long long v_ld_b,
+                            float* out, const int* lens) {
+  const int d4 = D / 4;
+  const bool fast = D % 4 == 0 && d4 >= 32 && d4 <= 256 && 256 % d4 == 0 && (v_ld_t % 4) == 0 && (v_ld_b % 4) == 0 &&
+                    (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                    (OA_FB + (256 / d4 > OA_FB ? OA_FB : 256 / d4) - 1) / (256 / d4 > OA_FB ? OA_FB : 256 / d4) <= OA_FPG;
+  ProfScope ps(F_ATTN_BWD, st);
+  if (fast)
+    attn_outer_accum_kernel<<<dim3((Tp + OA_FB - 1) / OA_FB, B), 256, (size_t)U * OA_FB * sizeof(float), st>>>(U, Tp, D, w, v, v_ld_t, v_ld_b,
+                                                                                                              out, lens);
+  else
+    attn_outer_accum8_kernel<<<dim3((Tp + 7) / 8, B), 256, (size_t)U * 8 * sizeof(float), st>>>(U, Tp, D, w, v, v_ld_t, v_ld_b, out, lens);
+  SSASR_LAUNCH_CHECK();
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1175,7 +1245,7 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     return gemm_f32(st, Mo, No, (int)R, X, ldx, 0, Y, ldy, 0, out, No, nullptr, 0, 0);
   };
   const size_t attn_smem = attn_bwd_smem_bytes(Sd, M, Tp, E);
-  SSASR_REQUIRE(attn_smem <= 200 * 1024 && (size_t)U * 8 * sizeof(float) <= 48 * 1024, "speller bwd: attention working set too large (Tp=%d, U=%d)", Tp, U);
+  SSASR_REQUIRE(attn_smem <= 200 * 1024 && (size_t)U * OA_FB * sizeof(float) <= 48 * 1024, "speller bwd: attention working set too large (Tp=%d, U=%d)", Tp, U);
   if (attn_smem > 48 * 1024)
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   const int cell_blocks = (B * Sd + 255) / 256;
@@ -1290,25 +1360,29 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     }
   }
   // attention memory gradients, accumulated over all steps at once; then denc += dpsi_pre @ Wpsi completes what the encoder needs
+  // (two streams: the dpsi branch -- accumulate, tanh', bf16 copy -- runs beside the denc accumulation)
+  cudaStream_t sp = dual ? sb : st;
+  if (dual) SSASR_HANDOVER(side->ev[U], st, sp);
+  rc = attn_outer_accum(sp, B, U, Tp, M, a->de_all, a->q, M, (long long)U * M, a->dpsi, a->enc_lens);
+  if (rc) return rc;
   {
-    ProfScope ps(F_ATTN_BWD, st);
-    attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, (size_t)U * 8 * sizeof(float), st>>>(
-        U, Tp, E, a->alpha, a->dxin1 + Sd, X1, (long long)U * X1, a->denc, a->enc_lens);
-    attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, (size_t)U * 8 * sizeof(float), st>>>(
-        U, Tp, M, a->de_all, a->q, M, (long long)U * M, a->dpsi, a->enc_lens);
+    ProfScope ps(F_POINTWISE, sp);
+    dtanh_inplace_kernel<<<256, 256, 0, sp>>>(a->dpsi, a->psi, (size_t)B * Tp * M);
   }
-  {
-    ProfScope ps(F_POINTWISE, st);
-    dtanh_inplace_kernel<<<256, 256, 0, st>>>(a->dpsi, a->psi, (size_t)B * Tp * M);
+  if (tc0) {
+    rc = cvt_bf16(sp, a->dpsi, M, a->wsA, M, (long long)B * Tp, M);
+    if (rc) return rc;
   }
+  rc = attn_outer_accum(st, B, U, Tp, E, a->alpha, a->dxin1 + Sd, X1, (long long)U * X1, a->denc, a->enc_lens);
+  if (rc) return rc;
   if (tc0) {
     __nv_bfloat16* wT = (__nv_bfloat16*)a->wsB;              // [E, M]
     rc = cvt_bf16_t(st, a->psi_w, E, wT, M, M, E, 0, 0, 0, 0);
     if (rc) return rc;
-    rc = cvt_bf16(st, a->dpsi, M, a->wsA, M, (long long)B * Tp, M);
-    if (rc) return rc;
+    if (dual) SSASR_HANDOVER(side->ev[U], sp, st);
     rc = gemm_bf16_tc(st, B * Tp, E, M, a->wsA, M, 0, wT, M, 0, a->denc, E, nullptr, 1);
   } else {
+    if (dual) SSASR_HANDOVER(side->ev[U], sp, st);
     rc = gemm_f32(st, B * Tp, E, M, a->dpsi, M, 1, a->psi_w, E, 0, a->denc, E, nullptr, 1, 0);
   }
   if (rc) return rc;
@@ -1382,8 +1456,10 @@ int ssasr_attn_step_bwd(int B, int Tp, int E, int Sd, int M, const float* dctx, 
   if (smem > 48 * 1024) SSASR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(F_ATTN_BWD, st);
   attn_bwd_kernel<<<B, 256, smem, st>>>(g);
-  attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, 8 * sizeof(float), st>>>(1, Tp, E, alpha, dctx, E, E, denc, enc_lens);
-  attn_outer_accum_kernel<<<dim3((Tp + 7) / 8, B), 256, 8 * sizeof(float), st>>>(1, Tp, M, de, q, M, M, dpsi, enc_lens);
+  int rc = attn_outer_accum(st, B, 1, Tp, E, alpha, dctx, E, E, denc, enc_lens);
+  if (rc) return rc;
+  rc = attn_outer_accum(st, B, 1, Tp, M, de, q, M, M, dpsi, enc_lens);
+  if (rc) return rc;
   SSASR_LAUNCH_CHECK();
   return 0;
 }
