@@ -86,7 +86,7 @@ int ssasr_cvt_bf16(const float* src, long long ld_src, void* dst, long long ld_d
 int ssasr_cvt_bf16_t(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols,
                      int mask_period, int mask_pos_lo, int mask_pos_hi, int mask_split, void* stream);
 /* same contracts as ssasr_blstm_fwd_f32 / _bwd_f32 plus caller-provided bf16 operands and workspaces */
-int ssasr_blstm_fwd_bf16(const float* x, int n_rows, int K, int Kp, const void* wih_bf /*[8S,Kp]*/, const float* bias_p,
+int ssasr_blstm_fwd_bf16(const float* x /*NULL: xb_ws already holds the bf16 input*/, int n_rows, int K, int Kp, const void* wih_bf /*[8S,Kp]*/, const float* bias_p,
                          const float* whh_p, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch,
                          const int* lens, void* xb_ws /*[n_rows,Kp]*/, float* xp, float* hout, float* cbuf,
                          unsigned* bar /*512 words*/, const void* whh_bf /*[8S,S] bf16 or NULL*/,

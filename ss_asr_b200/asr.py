@@ -46,6 +46,8 @@ class pBLSTM(nn.Module):
         super(pBLSTM, self).__init__()
         self.layer = nn.LSTM(in_dim, out_dim, bidirectional=True, batch_first=True)   # parameter holder
         self.precision = 'fp32'
+        self.bf16_input = None      # set by Listener: bf16 twin of the next forward's input (consumed by that call)
+        self.bf16_output = None     # bf16 twin of the last forward's output, when the recurrent kernel produced one
 
     def forward(self, input_x, state=None, state_len=None, pack_input=False):
         if state is not None:
@@ -68,8 +70,15 @@ class pBLSTM(nn.Module):
         t_h = t_max + (t_max & 1)
         x = _fit_time(input_x, t_h)
         lens_dev = torch.tensor(run_lens, dtype=torch.int32, device=input_x.device)
+        if self.bf16_input is not None and x is input_x:
+            Fk.hint_bf16_input(self.bf16_input)       # the previous layer's bf16 output (tensor-core path): no conversion pass
+        self.bf16_input = None
         hout = Fk.blstm(x, lens_dev, True, _blstm_params(self.layer), self.precision)   # [B, t_h, 2S]
         out = hout.view(B, t_h // 2, 2 * hout.shape[2])[:, :t_max // 2]              # downsample = a view
+        hb = Fk.LAST_BLSTM['hb']
+        # bf16 twin of `out`, valid only when the view above drops nothing
+        self.bf16_output = hb.view(B, t_h // 2, 2 * hout.shape[2]) if (hb is not None and t_max == t_h) else None
+        Fk.LAST_BLSTM['hb'] = None
         hidden = None   # (h_n, c_n) is discarded by every caller on the ASR path (asr.py:256-262)
         if state_len is not None:
             if pack_input:
@@ -112,8 +121,13 @@ class Listener(nn.Module):
     def forward(self, x, state_len, pack_input=True):
         t_in = x.shape[1]
         x, _, state_len = self.blstm_1(x, state_len=state_len, pack_input=pack_input)
+        self.blstm_2.bf16_input = self.blstm_1.bf16_output
         x, _, state_len = self.blstm_2(x, state_len=state_len, pack_input=pack_input)
+        self.blstm_3.bf16_input = self.blstm_2.bf16_output
         x, _, state_len = self.blstm_3(x, state_len=state_len, pack_input=pack_input)
+        x_bf = self.blstm_3.bf16_output
+        for m in (self.blstm_1, self.blstm_2, self.blstm_3):
+            m.bf16_output = None
         if x.shape[1] == 0:
             raise RuntimeError('Listener: at least 8 input frames are needed (three frame-pair reductions leave none of %d); '
                                'the reference fails in nn.LSTM at the same point (asr.py:262)' % int(t_in))
@@ -124,6 +138,8 @@ class Listener(nn.Module):
             x = Fk.blstm(x.view(1, B * Tp, K), None, False, _blstm_params(self.blstm_4), self.precision).view(B, Tp, -1)
         else:
             # seq-first quirk (asr.py:237-238,262): dim 0 (utterances) is the time axis of blstm_4
+            if x_bf is not None and x_bf.shape == x.shape:
+                Fk.hint_bf16_input(x_bf)
             x = Fk.blstm(x, None, False, _blstm_params(self.blstm_4), self.precision)
         return x, state_len
 

@@ -659,7 +659,8 @@ int ssasr_blstm_fwd_bf16(const float* x, int n_rows, int K, int Kp, const void* 
                          const void* whh_bf, void* hb_ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(S % 16 == 0 && Kp % 8 == 0 && Kp >= K, "blstm_fwd_bf16: bad S=%d / Kp=%d (K=%d)", S, Kp, K);
-  int rc = cvt_bf16(st, x, K, xb_ws, Kp, n_rows, K);
+  int rc = 0;
+  if (x) rc = cvt_bf16(st, x, K, xb_ws, Kp, n_rows, K);    // x == NULL: xb_ws already holds the bf16 input (the previous layer's bf16 h)
   if (rc) return rc;
   if (whh_bf && hb_ws && rec_tc_supported(S) && Kp <= rec_cl_fused_kp_max() && rec_cl_supported(S, n_batch, 0))
     // narrow layer input (layer 1: the fbank features): the projection runs inside the cluster recurrent kernel, the

@@ -63,6 +63,18 @@ def join_deferred():
         _OVERLAP['pending'] = []
 
 
+# Side channel between consecutive encoder layers on the tensor-core path: the recurrent kernel of layer l also writes a bf16
+# copy of its output (exchange buffer / weight-gradient operand).  Viewed [B, T/2, 4S] that copy IS the bf16 input of layer l+1,
+# so the fp32 -> bf16 conversion of the layer input (268 MB read + 134 MB written at layer 2 of C4) is skipped when the caller
+# hands it over with `hint_bf16_input` right before `blstm(...)`; `LAST_BLSTM['hb']` exposes the copy after the call.
+_XBF_HINT = {'t': None}
+LAST_BLSTM = {'hb': None}
+
+
+def hint_bf16_input(t):
+    _XBF_HINT['t'] = t
+
+
 class _BLSTM(torch.autograd.Function):
     """One bidirectional LSTM layer over rows indexed (seq, batch) -- see ssasr_blstm_fwd_f32.
 
@@ -74,6 +86,8 @@ class _BLSTM(torch.autograd.Function):
     def forward(ctx, x, lens_dev, time_major, precision, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         lib = _lib.load()
         _lib.require_cuda(x, 'BLSTM')
+        x_bf, _XBF_HINT['t'] = _XBF_HINT['t'], None
+        LAST_BLSTM['hb'] = None
         x = _f32c(x)
         d0, d1, K = x.shape
         S = w_hh_f.shape[1]
@@ -108,15 +122,21 @@ class _BLSTM(torch.autograd.Function):
         else:
             n_seq, n_batch, rs_seq, rs_batch = d0, d1, d1, 1
         if bf16:
-            xb = torch.zeros(n_rows, Kp, device=dev, dtype=torch.bfloat16) if Kp != K else \
-                torch.empty(n_rows, Kp, device=dev, dtype=torch.bfloat16)
+            given = (tc_rec and x_bf is not None and Kp == K and x_bf.dtype == torch.bfloat16 and x_bf.is_cuda and
+                     x_bf.is_contiguous() and x_bf.numel() == n_rows * K)
+            if given:
+                xb = x_bf.view(n_rows, Kp)            # the previous layer's bf16 output: no conversion pass
+            else:
+                xb = torch.zeros(n_rows, Kp, device=dev, dtype=torch.bfloat16) if Kp != K else \
+                    torch.empty(n_rows, Kp, device=dev, dtype=torch.bfloat16)
             hb = None
             if tc_rec:
                 hb = torch.empty(n_rows, 2 * S, device=dev, dtype=torch.bfloat16)
+                LAST_BLSTM['hb'] = hb
             else:
                 wih_bf = torch.zeros(8 * S, Kp, device=dev, dtype=torch.bfloat16)
                 check(lib.ssasr_cvt_bf16(ptr(wih_p), K, ptr(wih_bf), Kp, 8 * S, K, st), 'ssasr_cvt_bf16')
-            check(lib.ssasr_blstm_fwd_bf16(ptr(x), n_rows, K, Kp, ptr(wih_bf), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch,
+            check(lib.ssasr_blstm_fwd_bf16(None if given else ptr(x), n_rows, K, Kp, ptr(wih_bf), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch,
                                            rs_seq, rs_batch, ptr(lens_dev) if time_major else None, ptr(xb), ptr(xp),
                                            ptr(hout), ptr(cbuf), ptr(bar), ptr(whh_bf), ptr(hb), st),
                   'ssasr_blstm_fwd_bf16')
