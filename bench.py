@@ -447,6 +447,8 @@ def run_extras(model, dev, args, peaks, shard=(0, 1), dist=None):
     torch.cuda.synchronize()
     ms2 = tmax(e0.elapsed_time(e1))
     out['decode']['utt_per_s_tf32x3'] = n_total / (ms2 / 1e3)
+    # decoding steps actually executed (the loop stops once every utterance has emitted EOS; 201 = nobody did before the cap)
+    out['decode']['steps_run'] = int(getattr(model, 'last_decode_steps', 0))
     out['decode']['tf32x3_identical_transcripts'] = sum(a == b for a, b in zip(ids, ids2)) / max(1, len(ids))
     # headline decode figure: the fastest path whose transcripts are identical to the fp32 SIMT path in this very run
     out['decode']['utt_per_s_fp32_simt'] = out['decode']['utt_per_s']
