@@ -106,7 +106,24 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def lines(self):
+        try:
+            with open(self.path) as f:
+                return sum(1 for _ in f)
+        except OSError:
+            return 0
+
+    def wait_ready(self, timeout=2.0):
+        """Blocks until nvidia-smi has written its first sample: its start-up (NVML initialisation over every GPU of the box,
+        hundreds of ms in the first process on a fresh box) stalls kernel submission and must not fall into the timed region."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while self.lines() == 0 and time.time() - t0 < timeout and self.proc.poll() is None:
+            time.sleep(0.02)
+
+    def stop(self, first_line=0):
+        """first_line: number of samples already in the file when the timed region started (they are not reported)."""
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.proc is None:
             return out
@@ -118,7 +135,10 @@ class ClockSampler:
             self.proc.kill()
         self.f.close()
         sm, mx, reasons = [], [], set()
-        for line in open(self.path):
+        all_lines = open(self.path).read().splitlines()
+        if len(all_lines) >= first_line > 0:      # keep the last sample of the warm-up (under load) for very short timed regions
+            all_lines = all_lines[first_line - 1:]
+        for line in all_lines:
             p = [v.strip() for v in line.split(',')]
             if len(p) < 9:
                 continue
@@ -259,15 +279,17 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev, True)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()            # started (and waited for) BEFORE the warm-up: it samples every 200 ms from here on
+        sampler.wait_ready()
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev, True)
+    first_sample = sampler.lines() if rank == 0 else 0
     lib.ssasr_launch_count_reset()
     ms = timed(lambda: step(x_dev, y_dev, True), args.steps)
     launches = int(lib.ssasr_launch_count())
-    clocks = sampler.stop() if rank == 0 else {}
+    clocks = sampler.stop(first_sample) if rank == 0 else {}
     value = world * B * args.steps / (ms / 1e3)
 
     # e2e: host buffers in, loss + attention maps out, through the drop-in module API.  Every step copies its batch
