@@ -1,16 +1,25 @@
 #!/usr/bin/env python
 """Benchmark of the LAS hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
 
-  python bench.py --gpus N --steps K --warmup W            # our CUDA path, one JSON line on rank 0
-  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+  python bench.py --gpus N --steps K --warmup W                      # our CUDA path, one JSON line on rank 0
+  python bench.py --impl reference --steps K --warmup W              # the reference's own CPU path on the host cores
+  python bench.py --workload {train,decode,fbank,c5} ...             # which BASELINE.json config the line is about
 
-Headline workload (`config.workload`): C4 of BASELINE.json -- LAS data-parallel TRAINING step, batch 256 per GPU,
-T=512 frames of 80-dim fbanks, 40 target characters, conf/default.yaml model (S=256, mlp 128, tf_rate 0.9),
-Adadelta(lr=1, eps=1e-8) + clip 5 as in trainer.py:131-148,401-403.  One "step" = zero_grad, forward, loss,
-backward, (gradient all-reduce), clip, optimiser step on one synthetic batch.  `value` times it with the batch
-resident in HBM; `e2e` times the same step through the drop-in module API with the batch in pinned HOST memory
-(H2D copy of x,y and D2H read of the loss and attention maps inside the timed region).
-Greedy decoding (C3) and fbank extraction (C2) are timed after it and reported under `extra`.
+Headline workload (default `--workload train`, `config.workload`): C4 of BASELINE.json -- LAS data-parallel TRAINING step,
+batch 256 per GPU, T=512 frames of 80-dim fbanks, 40 target characters, conf/default.yaml model (S=256, mlp 128, tf_rate 0.9),
+Adadelta(lr=1, eps=1e-8) + clip 5 as in trainer.py:131-148,401-403.  One "step" = zero_grad, forward, loss, backward,
+(gradient all-reduce), clip, optimiser step on one synthetic batch.  `value` times it with the batch resident in HBM; `e2e`
+times the same step through the drop-in module API with the batch in pinned HOST memory (H2D copy of x,y and D2H read of the
+loss and attention maps inside the timed region).
+
+The co-headline metrics of BASELINE.json -- greedy decoding (C3), fbank extraction (C2) and the long-utterance config (C5) --
+are measured in the same run on FRESHLY SEEDED models (`torch.manual_seed(1)`, never the model the timed training steps have
+just updated), each with its own CPU baseline, and reported under `extra` plus flat `decode_*` / `fbank_*` / `c5_*` scalars;
+`--workload decode|fbank|c5` prints the same measurement as a first-class line (metric, value, e2e, roofline, cpu_baseline).
+
+CPU legs (`cpu_baseline`, `--impl reference`): oracle/cpu_arm.py -- the UNMODIFIED reference from oracle/_ref when it is there
+(kind "reference"), the oracle port otherwise (kind "port"); the batch / subset actually run is in `cpu_baseline.sample` and
+`config.cpu_sample_batch`.
 """
 import argparse
 import json
@@ -29,7 +38,9 @@ sys.path.insert(0, ROOT)
 
 DIMS = dict(output_dim=50, encoder_state_size=256, decoder_state_size=256, mlp_out_size=128, feature_dim=80)
 C4 = dict(B=256, T=512, F=80, U=40)
-CPU_SAMPLE = dict(B=16, T=512, F=80, U=40)
+C5 = dict(B=32, T=1600, F=80, U=100, S=512)
+CPU_SAMPLE = dict(B=16, T=512, F=80, U=40)          # cpu_baseline of the product arm: one step of this batch
+REF_ARM_BUDGET_S = 150.0                            # --impl reference: (steps + warmup) steps are sized to fit this
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -52,6 +63,17 @@ def synth_batch(B, T, F, U, seed=1234, n_tokens=50):
         y[0, 1:1 + U] = tok[0, 1:1 + U]
         y[0, 1 + U] = 1
     return x, [int(v) for v in lens], y
+
+
+def c3_set(n_total, rank=0, world=1, seed=4321):
+    """n_total utterances, T ~ U[256,512], F=80; this rank's length-balanced round-robin shard, padded."""
+    g = torch.Generator().manual_seed(seed)
+    Ts = sorted([int(v) for v in torch.randint(256, 513, (n_total,), generator=g)], reverse=True)
+    mine = Ts[rank::world]
+    xb = torch.zeros(len(mine), mine[0], 80)
+    for i, t in enumerate(mine):
+        xb[i, :t] = torch.randn(t, 80, generator=torch.Generator().manual_seed(seed + 1 + rank + world * i))
+    return xb, mine
 
 
 def train_flops(B, T, F, U, S=256, Sd=256, M=128, C=50):
@@ -84,6 +106,23 @@ def train_bytes(B, T, F, U, S=256):
     fwd = rows_l[0] * (((F + 7) // 8 * 8) * 2 + out_b) + sum(r * (8 * S * 4 + out_b) for r in rows_l[1:])
     bwd = sum(rows_l) * (8 * S * 4 + 2 * S * 4 + 2 * S * 4 + 8 * S * 2)
     return {'rec_fwd_tc': float(fwd), 'rec_bwd_tc': float(bwd)}
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def ncu_traffic(family):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the family's kernels, from the committed ncu captures
+    (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from `ncu --set full` raw pages)."""
+    try:
+        ent = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(family, {})
+        return ent.get('bytes_per_launch')
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -160,99 +199,338 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the reference's CPU PyTorch path (oracle port), host cores
+# workload descriptions (the `config` object)
 # ----------------------------------------------------------------------------------------------------------
-def cpu_train_utt_per_s(steps, warmup, sample=CPU_SAMPLE):
-    from oracle import las_oracle as O
-    from oracle import las_port as P
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = O.make_state_dict(seed=1, **DIMS)
-    port = P.Port(sd, tf_rate=0.9)
-    optim = torch.optim.Adadelta(port.parameters(), lr=1.0, eps=1e-8)
-    x, lens, y = synth_batch(sample['B'], sample['T'], sample['F'], sample['U'])
-    rng = random.Random(1)
-    for _ in range(warmup):
-        port.train_step(x, lens, y, optim, rng=rng)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        port.train_step(x, lens, y, optim, rng=rng)
-    dt = time.perf_counter() - t0
-    return sample['B'] * steps / dt, dt / steps, cores
+def workload_config(workload, n, small=False):
+    if workload == 'train':
+        c = {'workload': 'C4 LAS DP train step: B=256/GPU,T=512,F=80,U=40,S=256,mlp=128,tf=0.9,Adadelta+clip5 (BASELINE configs[3])',
+             'global_batch': C4['B'] * n, 'per_gpu_batch': C4['B'], 'frames': C4['T'], 'feature_dim': C4['F'],
+             'decode_steps': C4['U'] + 1, 'parallelism': 'dp%d' % n,
+             'l2': 'working set >> L2 (layer-1 gate buffer alone is 1.07 GB per step); no explicit flush needed'}
+    elif workload == 'decode':
+        c = {'workload': 'C3 greedy decode: 1000 utt, T~U[256,512], F=80, bs=1 semantics, 200-char cap, lm_weight 0 (BASELINE configs[2])',
+             'utterances': 1000, 'parallelism': 'by-utterance x%d, no collective' % n,
+             'l2': 'encoder memory of a shard (164 MB at 1000 utterances) > L2; weights L2-resident'}
+    elif workload == 'fbank':
+        c = {'workload': 'C2 log-mel fbank: 4096 x 10 s @16 kHz, 80 mels, n_fft=400, hop=160 (BASELINE configs[1])',
+             'utterances': 4096, 'parallelism': 'by-utterance x%d, no collective' % n,
+             'l2': 'input + output 3.9 GB per pass >> L2'}
+    else:
+        c = {'workload': 'C5 long LAS train step: B=32,T=1600,F=80,U=100,S_enc=512,S_dec=256 (BASELINE configs[4])',
+             'global_batch': C5['B'] * n, 'per_gpu_batch': C5['B'], 'frames': C5['T'], 'parallelism': 'dp%d' % n,
+             'l2': 'working set >> L2'}
+    if small:
+        c['small'] = True
+    return c
 
 
+METRIC = {'train': 'asr_train_utt_per_s', 'decode': 'asr_greedy_decode_utt_per_s', 'fbank': 'fbank_utt_per_s',
+          'c5': 'asr_train_long_utt_per_s'}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation on the host cores (oracle/cpu_arm.py)
+# ----------------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    v, spstep, cores = cpu_train_utt_per_s(args.steps, args.warmup)
-    sample = ('%d-utterance batch of the C4 recipe (T=512,F=80,U=40, tf_rate 0.9) per step on the host CPU, torch %s, '
-              '%d threads; the reference is pure Python/torch and is timed through oracle/las_port.py (same torch '
-              'calls as src/asr.py + trainer.py:415-438)' % (CPU_SAMPLE['B'], torch.__version__, cores))
-    line = {'impl': 'reference', 'metric': 'asr_train_utt_per_s', 'value': v, 'unit': 'utt/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': spstep * 1e3, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.gpus),
-            'cpu_baseline': {'value': v, 'unit': 'utt/s', 'cores': cores, 'kind': 'port', 'sample': sample},
-            'e2e': {'value': v, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+    from oracle import cpu_arm
+    wl = args.workload
+    cfg = workload_config(wl, args.gpus)
+    t0 = time.perf_counter()
+    if wl in ('train', 'c5'):
+        shape = dict(CPU_SAMPLE, B=32) if wl == 'train' else dict(B=C5['B'], T=C5['T'], F=C5['F'], U=C5['U'])
+        dims = DIMS if wl == 'train' else dict(DIMS, encoder_state_size=C5['S'])
+        r = cpu_arm.train(synth_batch, args.steps, args.warmup, shape, budget_s=REF_ARM_BUDGET_S, dims=dims)
+        value, per_step = r['value'], r['s_per_step'] * 1e3
+        cfg.update(cpu_sample_batch=r['batch'], same_config=bool(r['batch'] == (C4['B'] if wl == 'train' else C5['B'])))
+    elif wl == 'decode':
+        xs, lens = c3_set(1000)
+        r = cpu_arm.decode(xs, lens, max_utts=32, budget_s=min(REF_ARM_BUDGET_S, 30.0 * max(1, args.steps)))
+        value, per_step = r['value'], 1e3 * 1000 / r['value']
+        cfg.update(cpu_sample_utterances=int(r['sample'].split()[0]), same_config=False)
+    else:
+        r = cpu_arm.fbank(n_utt=96 * max(1, min(args.steps, 4)))
+        value, per_step = r['value'], 1e3 * 4096 / r['value']
+        cfg.update(cpu_sample_utterances=96 * max(1, min(args.steps, 4)), same_config=False)
+    cfg['cpu_cores'] = r['cores']
+    cfg['cpu_kind'] = r['kind']
+    line = {'impl': 'reference', 'metric': METRIC[wl], 'value': value, 'unit': 'utt/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': value, 'unit': 'utt/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
+            'e2e': {'value': value, 'unit': 'utt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0, 'wall_s': time.perf_counter() - t0}
     print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
-
-
-def workload_config(n):
-    return {'workload': 'C4 LAS data-parallel training step (BASELINE.json configs[3]): batch 256/GPU, T=512, F=80, '
-                        'U=40, S_enc=S_dec=256, mlp=128, tf_rate=0.9, Adadelta+clip5',
-            'global_batch': C4['B'] * n, 'per_gpu_batch': C4['B'], 'frames': C4['T'], 'feature_dim': C4['F'],
-            'decode_steps': C4['U'] + 1, 'parallelism': 'dp%d' % n,
-            'l2': 'working set >> L2 (layer-1 gate buffer alone is 1.07 GB per step); no explicit flush needed'}
 
 
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
-    from ss_asr_b200 import _lib
-    from ss_asr_b200.asr import ASR
-    from ss_asr_b200.functional import asr_loss
-    from ss_asr_b200 import preprocess as PP
-    from ss_asr_b200.parallel import GradSync
+class Ctx:
+    """Process-wide state of one product-arm run."""
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the '
-                           'CPU arm)')
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out of it
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=dev)
-    lib = _lib.load()
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args = args
+        self.dist = dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise RuntimeError('bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the '
+                               'CPU arm)')
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        if self.world > 1:
+            # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) out
+            if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+                os.environ['NCCL_DEBUG'] = 'WARN'
+            dist.init_process_group('nccl', device_id=self.dev)
+        from ss_asr_b200 import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.peaks = load_peaks()
+        self.hbm = self.peaks.get('hbm_gbs', 6546.6)
+        self.tf = self.peaks.get('bf16_tflops_sustained', 1393.1)
+        self.peak_src = 'measured (MEASURED_PEAKS.json)' if self.peaks else 'fallback (B200_PROFILING.md)'
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """CUDA-event time of `steps` calls of fn, bracketed by barrier + synchronize, max over ranks (ms)."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms)
+
+    def sum_int(self, v):
+        t = torch.tensor([int(v)], device=self.dev, dtype=torch.int64)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return int(t)
+
+    def profile(self, fn, reps=1):
+        """Per-family CUDA-event time of `reps` calls of fn (kernels timed one launch at a time) -> {family: (ms, launches)}."""
+        self.lib.ssasr_profile_enable(1)
+        self._lib.profile_read()
+        for _ in range(reps):
+            fn()
+        prof = self._lib.profile_read()
+        self.lib.ssasr_profile_enable(0)
+        return {k: (v[0] / reps, v[1] / reps) for k, v in prof.items() if v[1] > 0}
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def fresh_model(dev, S_enc=256, tf_rate=0.9):
+    """weights = the reference initialisation under torch.manual_seed(1)."""
+    from ss_asr_b200.asr import ASR
+    torch.manual_seed(1)
+    random.seed(1)
+    d = dict(DIMS, encoder_state_size=S_enc)
+    return ASR(tf_rate=tf_rate, **d).to(dev)
+
+
+# ---- C3 ---------------------------------------------------------------------------------------------------
+def measure_decode(cx, steps=1, small=False, with_lm=True, with_cpu=True):
+    """Greedy decoding of the C3 set on a freshly seeded model (random weights never emit EOS: 201 loop iterations)."""
+    from ss_asr_b200.functional import LAST_SPELL  # noqa: F401
+    n_total = 1000 if not small else 64
+    model = fresh_model(cx.dev)
+    model.eval()
+    xb_host, mine = c3_set(n_total, cx.rank, cx.world)
+    xb_pin = xb_host.pin_memory()
+    xb = xb_pin.to(cx.dev)
+    out = {'workload': workload_config('decode', cx.world)['workload'], 'utterances': n_total}
+    res = {}
+    for prec in ('fp32', 'tf32x3'):
+        ids = model.decode_batch(xb, mine, precision=prec)             # warm-up + the transcripts
+        ms = cx.timed(lambda: model.decode_batch(xb, mine, precision=prec), steps) / steps
+        res[prec] = (ms, ids, int(model.last_decode_steps))
+    ident = sum(a == b for a, b in zip(res['fp32'][1], res['tf32x3'][1])) / max(1, len(mine))
+    best = 'tf32x3' if (ident == 1.0 and res['tf32x3'][0] < res['fp32'][0]) else 'fp32'
+    ms, ids, steps_run = res[best]
+    out.update(utt_per_s=n_total / (ms / 1e3), ms=ms, chars_per_s=cx.sum_int(sum(len(i) for i in ids)) / (ms / 1e3),
+               precision='tf32x3 / bf16x3 tensor-core exact path' if best == 'tf32x3' else 'fp32 SIMT exact path',
+               utt_per_s_fp32_simt=n_total / (res['fp32'][0] / 1e3), utt_per_s_tf32x3=n_total / (res['tf32x3'][0] / 1e3),
+               tf32x3_identical_transcripts=ident, steps_run=steps_run, steps_expected=201,
+               steps_run_ok=bool(steps_run == 201), model='fresh torch.manual_seed(1) initialisation')
+    # e2e: padded host batch (pinned) -> device, decode, token ids back on the host as Python lists (decode_batch's return)
+
+    def e2e():
+        xd = xb_pin.to(cx.dev, non_blocking=True)
+        model.decode_batch(xd, mine, precision=best if best != 'fp32' else None)
+    e2e()
+    ms_e = cx.timed(e2e, steps) / steps
+    out['e2e'] = {'value': n_total / (ms_e / 1e3), 'unit': 'utt/s', 'ms': ms_e,
+                  'h2d_bytes_per_step': cx.sum_int(xb_pin.numel() * 4), 'd2h_bytes_per_step': cx.sum_int(len(mine) * 201 * 4)}
+    # per-family device time of one pass of the headline path
+    fam = cx.profile(lambda: model.decode_batch(xb, mine, precision=best if best != 'fp32' else None))
+    out['per_family_ms'] = {k: round(v[0], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])}
+    out['gpu_launches'] = int(sum(v[1] for v in fam.values()))
+    # roofline of the dominant family.  The recurrent families are latency chains (T + T/2 + T/4 + 1 dependent steps per Listener
+    # pass); attention streams the encoder memory: 4 T'(M + 2S) bytes per utterance and character (SURVEY §8d)
+    dom = max(fam, key=lambda k: fam[k][0])
+    att_bytes = sum(4 * (t // 8) * (128 + 512) for t in mine) * 201
+    if 'attn_fwd' in fam:
+        out['attn_hbm_gbps'] = att_bytes / (fam['attn_fwd'][0] / 1e3) / 1e9
+    out['roofline'] = {'kernel': dom, 'bound': 'hbm', 'achieved': (att_bytes / (fam['attn_fwd'][0] / 1e3) / 1e9) if 'attn_fwd' in fam else None,
+                       'peak': cx.hbm, 'unit': 'GB/s', 'frac': (att_bytes / (fam['attn_fwd'][0] / 1e3) / 1e9 / cx.hbm) if 'attn_fwd' in fam else None,
+                       'traffic': ncu_traffic('attn_fwd_decode'), 'peak_source': cx.peak_src,
+                       'note': 'fraction quoted for the attention family (the HBM-streaming part); the dominant family (%s) is a '
+                               'chain of dependent recurrent steps, see per_family_ms' % dom,
+                       'ms_per_step_in_kernel': fam[dom][0], 'share_of_step': fam[dom][0] / ms}
+    if with_lm and cx.rank == 0 and cx.world == 1:
+        lm = _charlm(cx.dev)
+        model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5)
+        ms_lm = cx.timed(lambda: model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5), 1)
+        out['utt_per_s_lm05'] = n_total / (ms_lm / 1e3)
+    if with_cpu and cx.rank == 0 and cx.world == 1 and not cx.args.no_cpu:
+        from oracle import cpu_arm
+        xs, lens = c3_set(n_total)
+        out['cpu_baseline'] = cpu_arm.decode(xs, lens, max_utts=32 if not small else 2, budget_s=20.0 if not small else 5.0)
+    del xb, model
+    return out
+
+
+def _charlm(dev):
+    import torch.nn as nn
+
+    class _LM(nn.Module):          # parameter structure of the reference CharLM (charlm.py:5-44); only its state_dict is read
+        def __init__(self):
+            super().__init__()
+            self.emb = nn.Embedding(50, 128)
+            self.layer_1 = nn.GRUCell(128, 128)
+            self.layer_2 = nn.GRUCell(128, 128)
+            self.out = nn.Linear(128, 50)
+    torch.manual_seed(7)
+    return _LM().to(dev)
+
+
+# ---- C2 ---------------------------------------------------------------------------------------------------
+def measure_fbank(cx, steps=5, small=False, with_cpu=True):
+    from ss_asr_b200 import preprocess as PP
+    n_all = 4096 if not small else 256
+    n_utt = n_all // cx.world
+    n = 160000
+    audio = 0.1 * torch.randn(n_utt * n, device=cx.dev, generator=torch.Generator(device=cx.dev).manual_seed(1234 + cx.rank))
+    off = [i * n for i in range(n_utt + 1)]
+    plan = PP.FbankPlan(off, 16000, 80, device=cx.dev)
+    fb = plan.run(audio)
+    cx.lib.ssasr_launch_count_reset()
+    ms = cx.timed(lambda: plan.run(audio, out=fb), steps) / steps
+    launches = int(cx.lib.ssasr_launch_count()) // steps
+    byts = n_utt * (4 * n + 4 * 80 * 1001)
+    out = {'workload': workload_config('fbank', cx.world)['workload'], 'utterances': n_utt * cx.world,
+           'utt_per_s': n_utt * cx.world / (ms / 1e3), 'audio_s_per_s': n_utt * cx.world * 10.0 / (ms / 1e3), 'ms': ms,
+           'gpu_launches': launches,
+           'roofline': {'kernel': 'fbank400p_kernel', 'bound': 'hbm', 'achieved': byts / (ms / 1e3) / 1e9, 'peak': cx.hbm, 'unit': 'GB/s',
+                        'frac': byts / (ms / 1e3) / 1e9 / cx.hbm, 'traffic': ncu_traffic('fbank'), 'peak_source': cx.peak_src,
+                        'algorithmic_bytes_per_launch': byts, 'launches_per_step': launches, 'ms_per_step_in_kernel': ms,
+                        'share_of_step': 1.0}}
+    # e2e: audio in pinned host memory -> device, fbank, features back into pinned host memory (what preprocess.py writes out)
+    a_pin = torch.empty(n_utt * n, dtype=torch.float32, pin_memory=True)
+    a_pin.copy_(audio)
+    o_pin = torch.empty(fb.shape, dtype=torch.float32, pin_memory=True)
+
+    def e2e():
+        ad = a_pin.to(cx.dev, non_blocking=True)
+        o_pin.copy_(plan.run(ad, out=fb), non_blocking=True)
+    e2e()
+    ms_e = cx.timed(e2e, max(1, steps // 2)) / max(1, steps // 2)
+    out['e2e'] = {'value': n_utt * cx.world / (ms_e / 1e3), 'unit': 'utt/s', 'ms': ms_e,
+                  'h2d_bytes_per_step': cx.sum_int(a_pin.numel() * 4), 'd2h_bytes_per_step': cx.sum_int(o_pin.numel() * 4)}
+    if with_cpu and cx.rank == 0 and cx.world == 1 and not cx.args.no_cpu:
+        from oracle import cpu_arm
+        out['cpu_baseline'] = cpu_arm.fbank(n_utt=96 if not small else 12)
+    del audio, fb, a_pin, o_pin
+    return out
+
+
+# ---- C5 ---------------------------------------------------------------------------------------------------
+def measure_c5(cx, steps=3, with_decode=True):
+    """C5 (BASELINE.json configs[4]): long utterances (1600 frames), 512-dim BLSTM, B=32, U=100 -- train step + greedy decode."""
+    from ss_asr_b200 import functional as Fk
+    from ss_asr_b200.functional import asr_loss
+    from ss_asr_b200.optim import FusedAdadelta
+    m = fresh_model(cx.dev, S_enc=C5['S'])
+    m.train_precision = 'bf16'
+    m.train()
+    m.att_on_device = True
+    opt = FusedAdadelta(m.parameters(), lr=1.0, eps=1e-8)
+    x, lens, y = synth_batch(C5['B'], C5['T'], C5['F'], C5['U'], seed=1234 + cx.rank)
+    xd, yd = x.to(cx.dev), y.to(cx.dev)
+    ans = int(max((y != 0).sum(-1) + 1)) - 1
+    was = Fk.overlap_wgrad_enabled()
+    Fk.set_overlap_wgrad(True)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        _, logits, _ = m(xd, ans, teacher=yd, state_len=lens)
+        asr_loss(logits, yd).backward()
+        opt.step_clipped(5.0)
+    for _ in range(3):
+        step()
+    ms = cx.timed(step, steps) / steps
+    Fk.set_overlap_wgrad(False)
+    fam = cx.profile(step)
+    Fk.set_overlap_wgrad(was)
+    S, T, B = C5['S'], C5['T'], C5['B']
+    rows = B * (T + T // 2 + T // 4 + T // 8)
+    gflop = 3 * B * (T * (16 * S * (80 + S) + 70 * S * S)) / 1e9           # SURVEY §8d: listener fwd x 3 (speller < 2 %)
+    out = {'workload': workload_config('c5', cx.world)['workload'], 'ms_per_step': ms, 'utt_per_s': cx.world * B / ms * 1e3,
+           'tflops': gflop / ms, 'tensor_frac': gflop / ms / cx.tf, 'rows': rows,
+           'per_family_ms': {k: round(v[0], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
+           'us_per_dependent_step': {k: round(fam[k][0] * 1e3 / (T + T // 2 + T // 4 + B), 3) for k in fam if k.startswith('rec_')}}
+    if with_decode:
+        md = fresh_model(cx.dev, S_enc=S)
+        md.eval()
+        ids = md.decode_batch(xd, lens, precision='tf32x3')
+        msd = cx.timed(lambda: md.decode_batch(xd, lens, precision='tf32x3'), 1)
+        out['decode'] = {'utterances': B * cx.world, 'ms': msd, 'utt_per_s': cx.world * B / msd * 1e3, 'steps_run': int(md.last_decode_steps),
+                         'precision': 'tf32x3', 'chars': sum(len(i) for i in ids)}
+    del m, xd, yd
+    return out
+
+
+# ---- C4 ---------------------------------------------------------------------------------------------------
+def run_train(cx):
+    args = cx.args
+    lib, dev, world, rank = cx.lib, cx.dev, cx.world, cx.rank
+    from ss_asr_b200 import functional as Fk
+    from ss_asr_b200.functional import asr_loss
+    from ss_asr_b200.optim import FusedAdadelta
+    from ss_asr_b200.parallel import GradSync, HostBatchPipeline
     cfg = dict(C4)
     if args.small:
         cfg.update(B=32, T=128)
     B, T, F, U = cfg['B'], cfg['T'], cfg['F'], cfg['U']
-
-    torch.manual_seed(1)
-    random.seed(1)
-    model = ASR(tf_rate=0.9, **DIMS).to(dev)
+    model = fresh_model(dev)
     model.train_precision = args.precision
     model.train()
-    from ss_asr_b200.optim import FusedAdadelta
     optim = FusedAdadelta(model.parameters(), lr=1.0, eps=1e-8)     # torch.optim.Adadelta + Solver.step fused on the device
     sync = GradSync(model, world)
-    from ss_asr_b200 import functional as Fk
     Fk.set_overlap_wgrad(True)     # encoder weight-gradient GEMMs on a second stream under the next layer's recurrent kernel
     x, lens, y = synth_batch(B, T, F, U, seed=1234 + rank)
     ans_len = int(max((y != 0).sum(-1) + 1)) - 1
     x_host, y_host = x.pin_memory(), y.pin_memory()
     x_dev, y_dev = x.to(dev), y.to(dev)
 
-    def step(xd, yd, att_on_device):
+    def step(xd=x_dev, yd=y_dev, att_on_device=True):
         model.att_on_device = att_on_device
         optim.zero_grad(set_to_none=True)
         _, logits, att = model(xd, ans_len, teacher=yd, state_len=lens)
@@ -261,51 +539,46 @@ def run_ours(args):
         optim.step_clipped(5.0)            # trainer.py:144-148: clip_grad_norm_(5) + NaN-skip + Adadelta step, on the device
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
-
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(cx.local)
     if rank == 0:
         sampler.start()            # started (and waited for) BEFORE the warm-up: it samples every 200 ms from here on
         sampler.wait_ready()
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev, True)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
     first_sample = sampler.lines() if rank == 0 else 0
     lib.ssasr_launch_count_reset()
-    ms = timed(lambda: step(x_dev, y_dev, True), args.steps)
+    ms = cx.timed(step, args.steps)
     launches = int(lib.ssasr_launch_count())
     clocks = sampler.stop(first_sample) if rank == 0 else {}
     value = world * B * args.steps / (ms / 1e3)
+
+    # exposed gradient all-reduce: the same steps with the exchange replaced by a no-op (every rank steps on
+    # its own gradients); the difference is what the overlapped NCCL all-reduce still costs on the critical path
+    comm = None
+    if world > 1:
+        sync.enabled = False
+        for _ in range(2):
+            step()
+        ms_ns = cx.timed(step, args.steps)
+        sync.enabled = True
+        comm = {'collective': 'NCCL all-reduce (avg) of 10.27 M fp32 gradients in 5 buckets, overlapped with backward',
+                'ms_per_step': ms / args.steps, 'ms_per_step_without_allreduce': ms_ns / args.steps,
+                'exposed_allreduce_us_per_step': (ms - ms_ns) / args.steps * 1e3}
 
     # e2e: host buffers in, loss + attention maps out, through the drop-in module API.  Every step copies its batch
     # from pinned host memory (on the copy stream of HostBatchPipeline, overlapping the previous step) and reads the loss
     # and the attention maps of that step back to the host (both land in pinned memory without blocking; the host waits for
     # them after it has enqueued the rest of the step, so it never stalls the GPU; all device work of every step is inside
     # the timed region, which ends with a device synchronisation).
-    from ss_asr_b200.parallel import HostBatchPipeline
     pipe = HostBatchPipeline(dev)
     model.att_async = True
-    e2e_state = {'left': 0, 'att_probe': 0.0, 'loss_host': torch.zeros((), pin_memory=True), 'loss_ready': torch.cuda.Event()}
+    st = {'left': 0, 'att_probe': 0.0, 'loss_host': torch.zeros((), pin_memory=True), 'loss_ready': torch.cuda.Event()}
 
     def e2e_step():
         xd, yd = pipe.take()
-        e2e_state['left'] -= 1
-        if e2e_state['left'] > 0:
+        st['left'] -= 1
+        if st['left'] > 0:
             pipe.submit(x_host, y_host)
         model.att_on_device = False
         optim.zero_grad(set_to_none=True)
@@ -313,22 +586,22 @@ def run_ours(args):
         loss = asr_loss(logits, yd)
         # the step's result goes to the host as soon as it exists: non-blocking copy of the loss into pinned memory behind the
         # (already enqueued) copy of the attention maps, one event; backward and the optimiser are enqueued before the host waits
-        e2e_state['loss_host'].copy_(loss.detach(), non_blocking=True)
-        e2e_state['loss_ready'].record()
+        st['loss_host'].copy_(loss.detach(), non_blocking=True)
+        st['loss_ready'].record()
         sync.backward(loss)
         optim.step_clipped(5.0)
-        e2e_state['loss_ready'].synchronize()    # host sync: the loss and the attention maps of THIS step are on the host
-        v = float(e2e_state['loss_host'])
-        e2e_state['att_probe'] = float(att[0, 0, 0])
+        st['loss_ready'].synchronize()    # host sync: the loss and the attention maps of THIS step are on the host
+        v = float(st['loss_host'])
+        st['att_probe'] = float(att[0, 0, 0])
         return v
 
     def e2e_run(n):
-        e2e_state['left'] = n
+        st['left'] = n
         pipe.submit(x_host, y_host)              # the first batch's copy is inside the timed region as well
         for _ in range(n):
             e2e_step()
     e2e_run(2)
-    ms_e2e = timed(lambda: e2e_run(args.steps), 1)
+    ms_e2e = cx.timed(lambda: e2e_run(args.steps), 1)
     model.att_async = False
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = x_host.numel() * 4 + y_host.numel() * 8
@@ -336,38 +609,17 @@ def run_ours(args):
 
     # per-family CUDA-event timing (separate pass, not part of the numbers above)
     Fk.set_overlap_wgrad(False)          # kernels timed one at a time: no second stream sharing the SMs during this pass
-    lib.ssasr_profile_enable(1)
-    _lib.profile_read()
-    nprof = 2
-    for _ in range(nprof):
-        step(x_dev, y_dev, True)
-    prof = _lib.profile_read()
-    lib.ssasr_profile_enable(0)
+    fam = cx.profile(step, reps=2)
     Fk.set_overlap_wgrad(True)
     fl = train_flops(B, T, F, U)
-    fam_ms = {k: v[0] / nprof for k, v in prof.items() if v[1] > 0}
-    fam_n = {k: v[1] / nprof for k, v in prof.items() if v[1] > 0}
+    fam_ms = {k: v[0] for k, v in fam.items()}
+    fam_n = {k: v[1] for k, v in fam.items()}
     fam_flops = {'gemm_f32': fl['gemm'], 'gemm_tc': fl['gemm'], 'rec_fwd_f32': fl['rec_fwd'], 'rec_bwd_f32': fl['rec_bwd'],
                  'rec_fwd_tc': fl['rec_fwd'], 'rec_bwd_tc': fl['rec_bwd'], 'attn_fwd': fl['attn_fwd'],
                  'attn_bwd': fl['attn_bwd']}
     if fam_ms.get('gemm_f32') and fam_ms.get('gemm_tc'):   # both GEMM kinds active: split by time is not meaningful
         fam_flops['gemm_f32'] = None
     dom = max(fam_ms, key=fam_ms.get)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
-    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback (B200_PROFILING.md)'
-    ach = (fam_flops.get(dom) or 0.0) / (fam_ms[dom] / 1e3) / 1e12 if fam_ms[dom] > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(dom, {}).get('bytes_per_launch')
-    except Exception:
-        pass
-    # every family against both ceilings (the graded `roofline` object below is the dominant family's entry)
-    peak_bw = peaks.get('hbm_gbs', 6546.6)
     by = train_bytes(B, T, F, U)
     dep_steps = T + T // 2 + T // 4 + B
     rooflines = {}
@@ -375,187 +627,122 @@ def run_ours(args):
         ent = {'ms_per_step': round(v, 3), 'launches_per_step': fam_n[k]}
         if fam_flops.get(k):
             ent['tflops'] = round(fam_flops[k] / (v / 1e3) / 1e12, 2)
-            ent['tensor_frac'] = round(ent['tflops'] / peak_tf, 4)
+            ent['tensor_frac'] = round(ent['tflops'] / cx.tf, 4)
         if k in by:
             ent['hbm_gbps'] = round(by[k] / (v / 1e3) / 1e9, 1)
-            ent['hbm_frac'] = round(ent['hbm_gbps'] / peak_bw, 4)
+            ent['hbm_frac'] = round(ent['hbm_gbps'] / cx.hbm, 4)
             ent['us_per_dependent_step'] = round(v * 1e3 / dep_steps, 3)
         rooflines[k] = ent
     # the dominant family is reported against the ceiling it is closer to (both fractions are in rooflines[dom])
     dom_ent = rooflines[dom]
+    ach_tf = (fam_flops.get(dom) or 0.0) / (fam_ms[dom] / 1e3) / 1e12
     if dom_ent.get('hbm_frac', 0.0) > dom_ent.get('tensor_frac', 0.0):
-        roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': dom_ent['hbm_gbps'], 'peak': peak_bw, 'unit': 'GB/s',
-                    'frac': dom_ent['hbm_gbps'] / peak_bw, 'traffic': traffic,
-                    'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback (B200_PROFILING.md)'}
+        roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': dom_ent['hbm_gbps'], 'peak': cx.hbm, 'unit': 'GB/s',
+                    'frac': dom_ent['hbm_gbps'] / cx.hbm, 'traffic': ncu_traffic(dom), 'peak_source': cx.peak_src}
     else:
-        roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': ach / peak_tf, 'traffic': traffic, 'peak_source': peak_src}
-    roofline.update({
-                'note': 'recurrent kernels are bound by the latency of %d dependent steps per pass (exchange + MMA issue + cell '
-                        'math per step), not by a throughput ceiling: see rooflines[*].us_per_dependent_step and DESIGN.md §4'
-                        % dep_steps,
-                'rooflines': rooflines,
-                'launches_per_step': fam_n[dom], 'ms_per_step_in_kernel': fam_ms[dom],
-                'share_of_step': fam_ms[dom] / (ms / args.steps),
-                'per_family_ms_per_step': {k: round(v, 3) for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])},
-                'whole_step_tflops': fl['total'] / (ms / args.steps / 1e3) / 1e12})
+        roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': ach_tf, 'peak': cx.tf, 'unit': 'TFLOP/s',
+                    'frac': ach_tf / cx.tf, 'traffic': ncu_traffic(dom), 'peak_source': cx.peak_src}
+    roofline.update({'tensor_frac': dom_ent.get('tensor_frac'), 'hbm_frac': dom_ent.get('hbm_frac'),
+                     'us_per_dependent_step': dom_ent.get('us_per_dependent_step'),
+                     'algorithmic_bytes_per_launch': by.get(dom, 0.0) / max(1.0, fam_n[dom]) if dom in by else None,
+                     'note': 'recurrent kernels are bound by the latency of %d dependent steps per pass (exchange + MMA issue + cell '
+                             'math per step), not by a throughput ceiling: see us_per_dependent_step and DESIGN.md §4' % dep_steps,
+                     'rooflines': rooflines, 'launches_per_step': fam_n[dom], 'ms_per_step_in_kernel': fam_ms[dom],
+                     'share_of_step': fam_ms[dom] / (ms / args.steps),
+                     'per_family_ms_per_step': {k: round(v, 3) for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])},
+                     'whole_step_tflops': fl['total'] / (ms / args.steps / 1e3) / 1e12,
+                     'whole_step_tensor_frac': fl['total'] / (ms / args.steps / 1e3) / 1e12 / cx.tf})
+
+    # the exact-precision (fp32 SIMT) training step beside the bf16 headline
+    fp32_ms = None
+    if args.precision == 'bf16' and not args.no_extras:
+        model.train_precision = 'fp32'
+        step()
+        fp32_ms = cx.timed(step, 2) / 2
+        model.train_precision = args.precision
+    Fk.set_overlap_wgrad(False)
+    del model, optim, sync, x_dev, y_dev
+    torch.cuda.empty_cache()
 
     extra = {}
-    if not args.no_extras and world == 1:
-        extra = run_extras(model, dev, args, peaks)
-    elif not args.no_extras:
-        extra = run_extras(model, dev, args, peaks, shard=(rank, world), dist=dist)
+    if not args.no_extras:
+        extra['decode'] = measure_decode(cx, steps=1, small=args.small)
+        if rank == 0 and world == 1 and not args.small:
+            extra['long_c5'] = measure_c5(cx)
+        extra['fbank'] = measure_fbank(cx, steps=5, small=args.small)
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
-        v, spstep, cores = cpu_train_utt_per_s(1, 1 if not args.small else 0)
-        cpu = {'value': v, 'unit': 'utt/s', 'cores': cores, 'kind': 'port',
-               'sample': '1 timed + 1 warm-up train step of a %d-utterance batch of the same recipe (T=512,F=80,U=40) '
-                         'through oracle/las_port.py (the reference torch call sequence), %.1f s/step'
-                         % (CPU_SAMPLE['B'], spstep)}
-    if rank == 0:
-        line = {'metric': 'asr_train_utt_per_s', 'value': value, 'unit': 'utt/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-                'config': workload_config(world) if not args.small else dict(workload_config(world), small=cfg),
-                'clocks': clocks,
-                'e2e': {'value': e2e_value, 'unit': 'utt/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'ms_per_step': ms_e2e / args.steps},
-                'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'extra': extra}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import cpu_arm
+        shape = dict(CPU_SAMPLE) if not args.small else dict(CPU_SAMPLE, B=2, T=64)
+        cpu = cpu_arm.train(synth_batch, 1, 0, shape, budget_s=30.0)
+    if rank != 0:
+        return None
+    line = {'metric': METRIC['train'], 'value': value, 'unit': 'utt/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': warm, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': workload_config('train', world, args.small),
+            'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'utt/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'launches_per_step': launches / args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
+            'fp32_exact_ms_per_step': fp32_ms, 'comm': comm, 'extra': extra}
+    if comm:
+        line['exposed_allreduce_us_per_step'] = comm['exposed_allreduce_us_per_step']
+    # flat copies of the co-headline numbers (nested objects below `extra` do not survive every log parser)
+    d, f, c5 = extra.get('decode'), extra.get('fbank'), extra.get('long_c5')
+    if d:
+        line.update(decode_utt_per_s=d['utt_per_s'], decode_e2e_utt_per_s=d['e2e']['value'], decode_steps_run=d['steps_run'])
+        line['e2e']['decode_utt_per_s'] = d['e2e']['value']
+        if d.get('cpu_baseline') and cpu:
+            line['decode_cpu_utt_per_s'] = d['cpu_baseline']['value']
+            cpu.update(decode_value=d['cpu_baseline']['value'], decode_kind=d['cpu_baseline']['kind'])
+    if f:
+        line.update(fbank_utt_per_s=f['utt_per_s'], fbank_e2e_utt_per_s=f['e2e']['value'], fbank_hbm_frac=f['roofline']['frac'])
+        line['e2e']['fbank_utt_per_s'] = f['e2e']['value']
+        line['roofline']['fbank_hbm_frac'] = f['roofline']['frac']
+        if f.get('cpu_baseline') and cpu:
+            line['fbank_cpu_utt_per_s'] = f['cpu_baseline']['value']
+            cpu.update(fbank_value=f['cpu_baseline']['value'], fbank_kind=f['cpu_baseline']['kind'])
+    if c5:
+        line.update(c5_train_utt_per_s=c5['utt_per_s'], c5_decode_utt_per_s=(c5.get('decode') or {}).get('utt_per_s'))
+    return line
+
+
+def run_single(cx, workload):
+    """--workload decode | fbank | c5 as a first-class line."""
+    args = cx.args
+    sampler = ClockSampler(cx.local)
+    if cx.rank == 0:
+        sampler.start()
+        sampler.wait_ready()
+    first = sampler.lines() if cx.rank == 0 else 0
+    if workload == 'decode':
+        r = measure_decode(cx, steps=args.steps, small=args.small)
+        value, ms, dtype = r['utt_per_s'], r['ms'], 'f32'
+    elif workload == 'fbank':
+        r = measure_fbank(cx, steps=args.steps, small=args.small)
+        value, ms, dtype = r['utt_per_s'], r['ms'], 'f32'
+    else:
+        r = measure_c5(cx, steps=args.steps)
+        value, ms, dtype = r['utt_per_s'], r['ms_per_step'], 'bf16'
+    clocks = sampler.stop(first) if cx.rank == 0 else {}
+    if cx.rank != 0:
+        return None
+    return {'metric': METRIC[workload], 'value': value, 'unit': 'utt/s', 'n_gpus': cx.world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak' if workload == 'c5' else 'strong',
+            'vs_baseline': None, 'dtype': dtype, 'data': 'synthetic', 'config': workload_config(workload, cx.world, args.small),
+            'clocks': clocks, 'e2e': r.get('e2e'), 'gpu_launches': r.get('gpu_launches'), 'roofline': r.get('roofline'),
+            'cpu_baseline': r.get('cpu_baseline'), 'detail': r}
+
+
+def run_ours(args):
+    cx = Ctx(args)
+    line = run_train(cx) if args.workload == 'train' else run_single(cx, args.workload)
+    if cx.rank == 0 and line is not None:
         print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_extras(model, dev, args, peaks, shard=(0, 1), dist=None):
-    """C3 greedy decode (1000 utterances, bs=1 semantics, sharded by utterance) and C2 fbank (4096 x 10 s)."""
-    from ss_asr_b200 import _lib
-    from ss_asr_b200 import preprocess as PP
-    rank, world = shard
-    out = {}
-
-    def tmax(ms):
-        t = torch.tensor([ms], device=dev)
-        if dist is not None and world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
-    # ---- decode
-    n_total = 1000 if not args.small else 64
-    g = torch.Generator().manual_seed(4321)
-    Ts = sorted([int(v) for v in torch.randint(256, 513, (n_total,), generator=g)], reverse=True)
-    mine = Ts[rank::world]                      # length-balanced round-robin shard
-    xb = torch.zeros(len(mine), mine[0], 80)
-    for i, t in enumerate(mine):
-        xb[i, :t] = torch.randn(t, 80, generator=g)
-    xb = xb.to(dev)
-    model.decode_batch(xb, mine)                # warm-up
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    ids = model.decode_batch(xb, mine)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = tmax(e0.elapsed_time(e1))
-    out['decode'] = {'workload': 'C3 greedy decode, %d utterances T~U[256,512], bs=1 semantics, 200-char cap, lm_weight 0'
-                                 % n_total, 'utt_per_s': n_total / (ms / 1e3), 'ms': ms,
-                     'chars_per_s': sum(len(i) for i in ids) * world / (ms / 1e3),
-                     'precision': 'fp32 SIMT exact path'}
-    model.decode_batch(xb, mine, precision='tf32x3')
-    torch.cuda.synchronize()
-    e0.record()
-    ids2 = model.decode_batch(xb, mine, precision='tf32x3')
-    e1.record()
-    torch.cuda.synchronize()
-    ms2 = tmax(e0.elapsed_time(e1))
-    out['decode']['utt_per_s_tf32x3'] = n_total / (ms2 / 1e3)
-    # decoding steps actually executed (the loop stops once every utterance has emitted EOS; 201 = nobody did before the cap)
-    out['decode']['steps_run'] = int(getattr(model, 'last_decode_steps', 0))
-    out['decode']['tf32x3_identical_transcripts'] = sum(a == b for a, b in zip(ids, ids2)) / max(1, len(ids))
-    # headline decode figure: the fastest path whose transcripts are identical to the fp32 SIMT path in this very run
-    out['decode']['utt_per_s_fp32_simt'] = out['decode']['utt_per_s']
-    if out['decode']['tf32x3_identical_transcripts'] == 1.0 and ms2 < ms:
-        out['decode'].update(utt_per_s=n_total / (ms2 / 1e3), ms=ms2, chars_per_s=sum(len(i) for i in ids2) * world / (ms2 / 1e3),
-                             precision='tf32x3 / bf16x3 tensor-core exact path (transcripts identical to the fp32 SIMT path)')
-    if rank == 0 and world == 1:
-        # secondary: same utterances with the (randomly initialised, as in ASRTester) CharLM at lm_weight 0.5
-        import torch.nn as nn
-
-        class _LM(nn.Module):
-            def __init__(self):
-                super().__init__()
-                self.emb = nn.Embedding(50, 128)
-                self.layer_1 = nn.GRUCell(128, 128)
-                self.layer_2 = nn.GRUCell(128, 128)
-                self.out = nn.Linear(128, 50)
-        torch.manual_seed(7)
-        lm = _LM().to(dev)
-        model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5)
-        torch.cuda.synchronize()
-        e0.record()
-        model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5)
-        e1.record()
-        torch.cuda.synchronize()
-        out['decode']['utt_per_s_lm05'] = n_total / (e0.elapsed_time(e1) / 1e3)
-    del xb
-    if rank == 0 and world == 1 and not args.small:
-        out['long_c5'] = run_c5(dev)
-    # ---- fbank
-    n_utt = (4096 if not args.small else 256) // world
-    n = 160000
-    audio = 0.1 * torch.randn(n_utt * n, device=dev, generator=torch.Generator(device=dev).manual_seed(1234 + rank))
-    off = [i * n for i in range(n_utt + 1)]
-    plan = PP.FbankPlan(off, 16000, 80, device=dev)
-    fb = plan.run(audio)
-    torch.cuda.synchronize()
-    reps = 5
-    e0.record()
-    for _ in range(reps):
-        plan.run(audio, out=fb)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = tmax(e0.elapsed_time(e1)) / reps
-    byts = n_utt * (4 * n + 4 * 80 * 1001)
-    hbm = peaks.get('hbm_gbs', 6650.0)
-    out['fbank'] = {'workload': 'C2 log-mel fbank, %d x 10 s @16 kHz, 80 mels (input+output %.2f GB > L2)'
-                                % (n_utt * world, byts / 1e9), 'utt_per_s': n_utt * world / (ms / 1e3), 'ms': ms,
-                    'roofline': {'bound': 'hbm', 'achieved': byts / (ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
-                                 'frac': byts / (ms / 1e3) / 1e9 / hbm, 'traffic': None}}
-    return out
-
-
-def run_c5(dev):
-    """C5 (BASELINE.json configs[4]): long utterances (1600 frames), 512-dim BLSTM, B=32, U=100 -- train step timing."""
-    from ss_asr_b200.asr import ASR
-    from ss_asr_b200.functional import asr_loss
-    torch.manual_seed(1)
-    m = ASR(50, 512, 256, 128, 80, 0.9).to(dev)
-    m.train_precision = 'bf16'
-    m.train()
-    m.att_on_device = True
-    opt = torch.optim.Adadelta(m.parameters(), lr=1.0, eps=1e-8)
-    x, lens, y = synth_batch(32, 1600, 80, 100)
-    xd, yd = x.to(dev), y.to(dev)
-    ans = int(max((y != 0).sum(-1) + 1)) - 1
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        _, logits, _ = m(xd, ans, teacher=yd, state_len=lens)
-        asr_loss(logits, yd).backward()
-        torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
-        opt.step()
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    return {'workload': 'C5 long-utterance LAS train step: B=32, T=1600, F=80, S_enc=512, S_dec=256, U=100',
-            'ms_per_step': ms, 'utt_per_s': 32 / ms * 1e3}
+    cx.finish()
 
 
 _JSON_OUT = None
@@ -567,6 +754,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='train', choices=['train', 'decode', 'fbank', 'c5'])
     ap.add_argument('--small', action='store_true', help='debug-sized shapes (not a bench number)')
     ap.add_argument('--no-extras', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')

@@ -16,6 +16,10 @@ extern "C" {
 #endif
 
 const char* ssasr_last_error(void);
+/* Bumped whenever a signature or an argument struct of this header changes; the ctypes binding (ss_asr_b200/_lib.py) refuses
+ * to bind a library whose version differs from the one it was written for (a stale .so would silently mis-read structs). */
+#define SSASR_ABI_VERSION 2
+int ssasr_abi_version(void);
 
 /* ---- log-mel filterbank: preprocess.py:187-208 log_fbank(y, sample_rate) (librosa 0.6.3 melspectrogram) ---- */
 long long ssasr_fbank_num_frames(long long n_samples, int sample_rate);

@@ -17,7 +17,7 @@ float dtype) of what the reference computes, written from the reference's semant
 
 Parity pinning: the reference holds no golden vectors, so the oracle
 is pinned against outputs of the UNMODIFIED reference run through
-tests/golden/ref_shim.py in the authoring container; those outputs are committed
+oracle/ref_shim.py in the authoring container; those outputs are committed
 under tests/golden/*.npz with the script that made them (tests/golden/make_golden.py)
 and re-checked by tests/test_oracle_golden.py on every run.
 

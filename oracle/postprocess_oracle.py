@@ -15,7 +15,7 @@ The edit distance lives in the third-party package `editdistance` (requirements.
 `levenshtein` below.
 
 Parity pinning: the reference ships no vectors for this path.  The oracle is pinned against the UNMODIFIED
-`postprocess.calc_acc` / `calc_err` and `ASRDataset.Mapper` executed through tests/golden/ref_shim.py (whose `editdistance`
+`postprocess.calc_acc` / `calc_err` and `ASRDataset.Mapper` executed through oracle/ref_shim.py (whose `editdistance`
 stub is the same published algorithm) on seeded cases that include ties, early EOS, empty words, repeated spaces and
 predictions shorter / longer than the label: tests/golden/postprocess.npz (made by tests/golden/make_golden_postprocess.py),
 re-checked by tests/test_oracle_golden.py.

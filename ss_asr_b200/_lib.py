@@ -43,6 +43,7 @@ class OptimTensor(C.Structure):
 _P, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     'ssasr_last_error': (C.c_char_p, []),
+    'ssasr_abi_version': (_I, []),
     'ssasr_fbank_num_frames': (_LL, [_LL, _I]),
     'ssasr_fbank': (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _P]),
     'ssasr_gemm_f32': (_I, [_I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P]),
@@ -99,15 +100,19 @@ def load(build_if_needed=True):
     if _LIB is not None:
         return _LIB
     if build_if_needed and os.environ.get('SSASR_NO_BUILD') != '1':
-        try:
-            _build.build()
-        except Exception:
-            if not os.path.isfile(_build.LIB):
-                raise
+        _build.build()          # a failed build of stale sources raises: an old .so would have the wrong struct layouts
     if not os.path.isfile(_build.LIB):
         raise RuntimeError('libssasr.so is missing (%s): build it with `python -m ss_asr_b200.build`; there is no '
                            'CPU/PyTorch fallback for the hot path' % _build.LIB)
     lib = C.CDLL(_build.LIB)
+    try:
+        lib.ssasr_abi_version.restype = C.c_int
+        have = int(lib.ssasr_abi_version())
+    except AttributeError:
+        have = -1
+    if have != _build.ABI_VERSION:
+        raise RuntimeError('libssasr.so has ABI version %d, this binding needs %d: rebuild with `python -m ss_asr_b200.build '
+                           '--force`' % (have, _build.ABI_VERSION))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -240,13 +240,13 @@ class ASR(nn.Module):
         self.init_parameters()
 
     # ------------------------------------------------------------------------------------------
-    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None, need_logits=True, stop_every=0):
+    def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None, need_logits=True, stop_every=0, stop_token=1):
         lens_dev = torch.tensor(enc_len, dtype=torch.int32, device=enc.device)
         params = self.attention.params() + self.decoder.params() + (self.embed.weight, self.char_trans.weight,
                                                                     self.char_trans.bias)
         self.sample_seed += 1
-        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision, lm, need_logits, stop_token=1,
-                        stop_every=stop_every)
+        return Fk.spell(enc, lens_dev, tok_in, modes, self.sample_seed, params, precision, lm, need_logits,
+                        stop_token=int(stop_token), stop_every=stop_every)
 
     def forward(self, audio_feature, decode_step, teacher=None, state_len=None):
         """-> (encode_len, logits [B,U,C] on the device, attention maps [B,U,T'] on the CPU)   asr.py:52-110"""
@@ -280,9 +280,10 @@ class ASR(nn.Module):
         return encode_len, logits, att.cpu()
 
     @torch.no_grad()
-    def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None):
+    def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None, eos_id=1):
         """Greedy decoding of many utterances at once with the per-utterance (bs=1) semantics of ASR.decode:
         xs [N,T,F] zero-padded, x_lens sorted in decreasing order; optional CharLM rescoring (asr.py:153-159).
+        `eos_id`: the token that ends an utterance (`mapper.char_to_ind(EOS_TKN)`, asr.py:167; 1 with the default Mapper).
         Returns a list of token-id lists."""
         prev = self.encoder.utterance_independent
         self.encoder.utterance_independent = True
@@ -317,14 +318,14 @@ class ASR(nn.Module):
             lm = (Fk.pack_charlm(rnn_lm, enc.device), lm_weight)
         # the loop stops as soon as every utterance has emitted EOS (checked every `decode_stop_check` steps; asr.py:161-162)
         _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), precision=prec, lm=lm,
-                                 need_logits=False, stop_every=int(self.decode_stop_check or 0))
+                                 need_logits=False, stop_every=int(self.decode_stop_check or 0), stop_token=eos_id)
         self.last_decode_steps = Fk.LAST_SPELL['steps_run']
         toks = toks[:, 1:].cpu().tolist()
         out = []
         for row in toks:
             ids = []
             for v in row[:max_steps]:
-                if v == 1:
+                if v == eos_id:
                     break
                 ids.append(v)
             out.append(ids)
@@ -333,7 +334,7 @@ class ASR(nn.Module):
     def decode(self, x, x_len, rnn_lm, mapper, lm_weight):
         """asr.py:112-173 (bs=1).  lm_weight == 0 runs entirely in the fused kernels."""
         assert len(x.shape) == 3 and x.shape[0] == 1
-        ids = self.decode_batch(x, x_len, rnn_lm=rnn_lm, lm_weight=lm_weight)[0]
+        ids = self.decode_batch(x, x_len, rnn_lm=rnn_lm, lm_weight=lm_weight, eos_id=int(mapper.char_to_ind(EOS_TKN)))[0]
         return ''.join(mapper.ind_to_char(i) for i in ids)
 
     # ------------------------------------------------------------------------------------------

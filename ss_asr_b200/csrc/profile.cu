@@ -1,5 +1,6 @@
 // Launch counters and optional CUDA-event timing per kernel family.
 #include "common.cuh"
+#include "ssasr.h"
 #include <mutex>
 #include <vector>
 
@@ -37,6 +38,7 @@ extern "C" {
 static const char* kFamilyNames[F_COUNT] = {"gemm_f32", "rec_fwd_f32", "rec_bwd_f32", "attn_fwd", "attn_bwd", "pointwise",
                                             "ce_loss", "fbank", "pack", "gemm_tc", "rec_fwd_tc", "rec_bwd_tc", "optim"};
 
+int ssasr_abi_version(void) { return SSASR_ABI_VERSION; }
 int ssasr_num_families(void) { return F_COUNT; }
 const char* ssasr_family_name(int i) { return (i >= 0 && i < F_COUNT) ? kFamilyNames[i] : ""; }
 

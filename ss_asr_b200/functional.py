@@ -24,6 +24,31 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+def _consume(ctx, what):
+    """Single-backward contract.  The backward kernels work IN PLACE on the tensors saved by the forward pass (the gate
+    activations become the gate gradients, the bf16 h copy is masked, ...) through raw pointers autograd's version counters
+    never see: a second backward over the same graph (`retain_graph=True`) would silently return wrong gradients, so it
+    raises instead."""
+    if getattr(ctx, 'consumed', False):
+        raise RuntimeError('ss_asr_b200 %s: backward called a second time over the same forward pass; the CUDA backward kernels '
+                           'overwrite the saved activations in place, so retain_graph=True is not supported -- run the '
+                           'forward pass again' % what)
+    ctx.consumed = True
+
+
+def _join_after_backward():
+    """Deferred weight gradients are joined when the autograd engine finishes the backward pass that produced them, so that
+    ANY reader of `param.grad` after `loss.backward()` returns (torch's clip_grad_norm_ / optimisers as in the unmodified
+    Solver.step, trainer.py:144-148) is ordered after the side stream."""
+    if not _OVERLAP.get('cb_queued'):
+        _OVERLAP['cb_queued'] = True
+
+        def _cb():
+            _OVERLAP['cb_queued'] = False
+            join_deferred()
+        torch.autograd.Variable._execution_engine.queue_callback(_cb)
+
+
 # --------------------------------------------------------------------------------------------------
 # bidirectional LSTM layer
 # --------------------------------------------------------------------------------------------------
@@ -31,10 +56,12 @@ def _f32c(t):
 # Deferred weight gradients.  The encoder's weight-gradient GEMMs (dW_ih, dW_hh) and their un-packing are not needed
 # before the optimiser, while the next layer's recurrent backward kernel is latency-bound and occupies 64 of the 148
 # SMs.  With `set_overlap_wgrad(True)` they are enqueued on a second stream (ordered after everything the layer's backward
-# has launched) and `join_deferred()` makes the current stream wait for them.  OPT-IN: whoever reads `param.grad` must join
-# first -- FusedAdadelta.step_clipped, GradSync and ASR.forward do; torch's own clip_grad_norm_ / optimisers do not.
+# has launched) and `join_deferred()` makes the current stream wait for them.  OPT-IN.  The join happens automatically when
+# the autograd engine finishes the backward pass (`_join_after_backward`), so every reader of `param.grad` after
+# `loss.backward()` -- torch's own clip_grad_norm_ / optimisers included -- is ordered after the side stream; GradSync joins
+# on the side stream itself (the bucket all-reduce is issued there).
 # --------------------------------------------------------------------------------------------------
-_OVERLAP = {'on': False, 'streams': {}, 'pending': []}
+_OVERLAP = {'on': False, 'streams': {}, 'pending': [], 'cb_queued': False}
 
 
 def set_overlap_wgrad(on):
@@ -163,6 +190,7 @@ class _BLSTM(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dhout):
         lib = _lib.load()
+        _consume(ctx, 'BLSTM')
         x, wih_p, whhT_p, act, hout, cbuf, lens_dev = ctx.saved_tensors
         n_rows, K, S, n_seq, n_batch, rs_seq, rs_batch, time_major, d1 = ctx.geom
         dev = x.device
@@ -215,6 +243,7 @@ class _BLSTM(torch.autograd.Function):
                 # NOT `g`: AccumulateGrad only adopts a gradient buffer it holds the sole reference to (otherwise it clones it --
                 # on the main stream, before the side stream has written it)
                 _OVERLAP['pending'].append((ev, (ws, xb_s, hb_s, dwih_p, dbias_p, dwhh_p, wihT_bf, whhT_bf)))
+                _join_after_backward()
             return (dx, None, None, None) + tuple(g)
         else:
             check(lib.ssasr_blstm_bwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(whhT_p), S, n_seq, n_batch, rs_seq, rs_batch,
@@ -229,8 +258,16 @@ class _BLSTM(torch.autograd.Function):
         return (dx, None, None, None) + tuple(g)
 
 
+def _on_device_of(t):
+    """Kernels are launched on the CURRENT stream of the tensor's device: make that device current for the call (a model on
+    cuda:1 while cuda:0 is current would otherwise launch into the wrong context)."""
+    _lib.require_cuda(t, 'ss_asr_b200')
+    return torch.cuda.device(t.device)
+
+
 def blstm(x, lens_dev, time_major, params, precision='fp32'):
-    return _BLSTM.apply(x, lens_dev, time_major, precision, *params)
+    with _on_device_of(x):
+        return _BLSTM.apply(x, lens_dev, time_major, precision, *params)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -293,6 +330,7 @@ class _Spell(torch.autograd.Function):
             lmk = dict(lm_H=H, lm_weight=float(lm_weight), lm_h1=ptr(lm_state[0]), lm_h2=ptr(lm_state[1]),
                        **{'lm_' + k: ptr(v) for k, v in lmt.items()})
         steps_run = C.c_int(U)
+        stop_scr = torch.zeros(1, dtype=torch.int32, device=dev) if stop_every else None     # alive until the call has returned
         a = _lib.SpellerFwdArgs(B=B, Tp=Tp, E=E, Sd=Sd, M=M, C=Cc, U=U, phi_w=ptr(phi_w), psi_w=ptr(psi_w),
                                 psi_b=ptr(psi_b), w1cat=ptr(w1cat), b1=ptr(b1), w2cat=ptr(w2cat), b2=ptr(b2),
                                 emb_w=ptr(emb_w), wc=ptr(wc), bc=ptr(bc), enc=ptr(enc), enc_lens=ptr(enc_lens_dev),
@@ -302,7 +340,7 @@ class _Spell(torch.autograd.Function):
                                 w2cat_bf=ptr(w2b), ws_bf=ptr(wsb), enc_bf=ptr(encb), x3_ws=ptr(x3ws),
                                 skip_final_logits=skip_final, dual_stream=int(bf16 and _DUAL_STREAM_SPELLER),
                                 stop_token=stop_token, stop_check_every=stop_every if skip_final else 0,
-                                stop_scratch=ptr(torch.zeros(1, dtype=torch.int32, device=dev)) if stop_every else None,
+                                stop_scratch=ptr(stop_scr),
                                 steps_run=C.addressof(steps_run), **lmk)
         ctx.dual = bool(bf16 and _DUAL_STREAM_SPELLER)
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
@@ -316,6 +354,7 @@ class _Spell(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits, _dalpha, _dtok):
         lib = _lib.load()
+        _consume(ctx, 'Speller')
         (enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1, c2, h2all, q,
          alpha) = ctx.saved_tensors
         B, Tp, E, Sd, M, Cc, U = ctx.dims
@@ -368,6 +407,7 @@ class _Spell(torch.autograd.Function):
             # everything the side stream still reads or writes, EXCEPT the returned gradient buffers (AccumulateGrad only adopts
             # a buffer it holds the sole reference to; otherwise it clones it on the main stream, before it has been written)
             _OVERLAP['pending'].append((ev, (ctx.saved_tensors, dlogits, scr, wsA, wsB, w1T, w2T, d_w1cat, d_b1, d_w2cat, d_b2)))
+            _join_after_backward()
         return (denc, None, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
 
 
@@ -378,7 +418,8 @@ def spell(enc, enc_lens_dev, tok_in, step_mode, seed, params, precision='fp32', 
           stop_every=0):
     """need_logits=False (greedy decoding): the [B,U,C] logits tensor is not recomputed after the loop (left undefined)."""
     opts = lm if need_logits else {'lm': lm, 'need_logits': False, 'stop_token': stop_token, 'stop_every': stop_every}
-    return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, opts, *params)
+    with _on_device_of(enc):
+        return _Spell.apply(enc, enc_lens_dev, tok_in, step_mode, seed, precision, opts, *params)
 
 
 def pack_charlm(rnn_lm, device):
@@ -421,7 +462,8 @@ class _ASRLoss(torch.autograd.Function):
 
 def asr_loss(logits, y):
     """loss of ASRTrainer.exec (trainer.py:426-434): logits [B,U,C], y [B,L] (label of step t = y[:, t+1])."""
-    return _ASRLoss.apply(logits, y)
+    with _on_device_of(logits):
+        return _ASRLoss.apply(logits, y)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -554,12 +596,15 @@ class _LSTMCell(torch.autograd.Function):
 
 
 def psi_memory(enc, psi_w, psi_b):
-    return _PsiMemory.apply(enc, psi_w, psi_b)
+    with _on_device_of(enc):
+        return _PsiMemory.apply(enc, psi_w, psi_b)
 
 
 def attn_step(h, enc, psi_t, lens_dev, phi_w):
-    return _AttnStep.apply(h, enc, psi_t, lens_dev, phi_w)
+    with _on_device_of(h):
+        return _AttnStep.apply(h, enc, psi_t, lens_dev, phi_w)
 
 
 def lstm_cell(x, h, c, cell):
-    return _LSTMCell.apply(x, h, c, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)
+    with _on_device_of(x):
+        return _LSTMCell.apply(x, h, c, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh)

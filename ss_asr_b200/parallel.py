@@ -26,6 +26,7 @@ class GradSync:
         self.buckets = {}
         self.pending = []
         self._handles = []
+        self.enabled = True          # False: backward() leaves every rank with its own gradients (measurement of the exchange cost)
         if self.world > 1:
             for name, p in model.named_parameters():
                 if not p.requires_grad:
@@ -36,6 +37,8 @@ class GradSync:
 
     def _make_hook(self, bucket):
         def hook(_p):
+            if not self.enabled:
+                return
             bucket['ready'] += 1
             if bucket['ready'] == len(bucket['params']):
                 self._launch(bucket)
@@ -62,7 +65,7 @@ class GradSync:
             b['ready'] = 0
         self.pending = []
         loss.backward()
-        if self.world <= 1:
+        if self.world <= 1 or not self.enabled:
             return
         from . import functional as Fk
         Fk.join_deferred()

@@ -82,24 +82,22 @@ def calc_acc_err(predict, label, mapper):
     return _acc_from(stats), _err_from(stats)
 
 
-def trim_eos(sequence):
-    """postprocess.py:68-75."""
-    new_pred = []
-    for char in sequence:
-        new_pred.append(int(char))
-        if char == 1:
-            break
-    return new_pred
+def trim_eos(sequence, eos_id=1):
+    """Host helper with the contract of postprocess.py:68-75: the token ids of `sequence` as Python ints up to AND INCLUDING
+    the first EOS (id 1 with the default Mapper); the whole sequence when there is none."""
+    ids = [int(v) for v in sequence]
+    return ids[:ids.index(eos_id) + 1] if eos_id in ids else ids
 
 
 def draw_att(att_maps, hyps):
-    """postprocess.py:52-66."""
-    attmaps = []
-    for i in range(att_maps.shape[0]):
-        att_i = att_maps[i, :, :]
-        att_len = len(trim_eos(hyps[i]))
-        attmaps.append(torch.stack([att_i, att_i, att_i], dim=0)[:, :att_len, :])
-    return attmaps
+    """Host helper with the contract of postprocess.py:52-66 (TensorBoard images for ASRTrainer.valid, trainer.py:512):
+    per utterance a [3, n, T'] tensor -- its attention map repeated over three colour channels, cut to the n decoding steps
+    up to and including the first EOS of its hypothesis."""
+    out = []
+    for att, hyp in zip(att_maps, hyps):
+        n = len(trim_eos(hyp))
+        out.append(att[:n].unsqueeze(0).expand(3, -1, -1).contiguous())
+    return out
 
 
 @torch.no_grad()

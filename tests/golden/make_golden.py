@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-import ref_shim  # noqa: E402
+from oracle import ref_shim  # noqa: E402
 from oracle import las_oracle as O  # noqa: E402
 from oracle import fbank_oracle as FB  # noqa: E402
 
@@ -57,7 +57,7 @@ def run_train(asr_mod, dims, sd, x, lens, y):
 
 
 def main():
-    asr_mod, charlm_mod = ref_shim.load()
+    asr_mod, charlm_mod = ref_shim.load(allow_container_reference=True)
 
     # ------------------------------------------------------------------ tiny (weights stored)
     dims = (50, 16, 16, 8, 12, 1.0)

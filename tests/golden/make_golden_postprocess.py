@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-import ref_shim  # noqa: E402
+from oracle import ref_shim  # noqa: E402
 from oracle import postprocess_oracle as PO  # noqa: E402
 
 CASES = [dict(seed=0, B=24, U=37, L=17), dict(seed=1, B=16, U=9, L=21), dict(seed=2, B=8, U=12, L=12),
@@ -23,7 +23,7 @@ CASES = [dict(seed=0, B=24, U=37, L=17), dict(seed=1, B=16, U=9, L=21), dict(see
 
 
 def main():
-    ref_shim.load()
+    ref_shim.load(allow_container_reference=True)
     import ASRDataset
     import postprocess
     mapper = ASRDataset.Mapper()
