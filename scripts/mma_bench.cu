@@ -19,12 +19,14 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, int sw_bytes) {
 }
 
 // n_mma MMAs of shape M x N x 16; A k-steps advance through `a_sw`-byte swizzled k-blocks, B likewise
-__global__ void __launch_bounds__(128, 1) bench(int M, int N, int n_mma, int a_sw, int b_sw, long long* out) {
+// spin_warps: extra warps that wait on an mbarrier that completes only at the end (the epilogue warps of the recurrent
+// kernels do this during the MMA phase); grid > 1: the same CTA on many SMs at once
+__global__ void __launch_bounds__(384, 1) bench(int M, int N, int n_mma, int a_sw, int b_sw, int spin_warps, long long* out) {
   extern __shared__ __align__(1024) uint8_t sm[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_barrier_init(); }
   if (warp == 1) tmem_alloc<256>(&slot);
   tc_fence_before();
   __syncthreads();
@@ -49,8 +51,11 @@ __global__ void __launch_bounds__(128, 1) bench(int M, int N, int n_mma, int a_s
       long long t1 = clock64();
       mbar_wait(&bar, rep & 1);
       long long t2 = clock64();
-      if (rep == 2) { out[0] = t1 - t0; out[1] = t2 - t0; }
+      if (rep == 2 && blockIdx.x == gridDim.x / 2) { out[0] = t1 - t0; out[1] = t2 - t0; }
     }
+    mbar_arrive(&bar2);
+  } else if (warp >= 2 && warp < 2 + spin_warps) {
+    mbar_wait(&bar2, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -71,13 +76,17 @@ int main() {
       {128, 128, 16, 128, 128, "gemm      M=128 N=128 A SW128 B SW128"}, {128, 256, 8, 128, 128, "gemm      M=128 N=256 A SW128 B SW128"},
       {64, 64, 16, 32, 128, "          M=64  N=64  A SW32  B SW128"},   {64, 16, 64, 128, 128, "          M=64  N=16  A SW128 B SW128"},
   };
-  for (auto& c : cfgs) {
-    bench<<<1, 128, 192 * 1024>>>(c.M, c.N, c.n, c.a_sw, c.b_sw, d);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("%s: %s\n", c.what, cudaGetErrorString(e)); return 1; }
-    long long h[2];
-    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-    printf("%s: %3d MMAs issue %6lld cyc, complete %6lld cyc = %5.1f cyc/MMA\n", c.what, c.n, h[0], h[1], (double)h[1] / c.n);
-  }
+  const int grids[] = {1, 2, 64, 148};
+  for (int spin = 0; spin <= 8; spin += 8)
+    for (int gi = 0; gi < 4; ++gi)
+      for (auto& c : cfgs) {
+        bench<<<grids[gi], 384, 192 * 1024>>>(c.M, c.N, c.n, c.a_sw, c.b_sw, spin, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("%s: %s\n", c.what, cudaGetErrorString(e)); return 1; }
+        long long h[2];
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("grid %3d spin %d %s: %3d MMAs issue %6lld cyc, complete %6lld cyc = %5.1f cyc/MMA\n", grids[gi], spin, c.what, c.n, h[0], h[1],
+               (double)h[1] / c.n);
+      }
   return 0;
 }

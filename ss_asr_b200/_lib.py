@@ -87,6 +87,7 @@ SIGNATURES = {
     'ssasr_rec_cl_set_debug': (None, [_P]),
     'ssasr_rec_cl_capacity': (_I, [_I, _I]),
     'ssasr_rec_cl_enable': (None, [_I]),
+    'ssasr_rec_q_set_rows': (None, [_I]),
 }
 
 

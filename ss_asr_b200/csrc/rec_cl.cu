@@ -118,6 +118,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
+// Same, relaxed: for "I have finished READING" notifications.  The reads in question have completed before the arriving thread
+// observed their completion barrier, and the arrive is control-dependent on that observation, so no release fence is needed
+// -- and a cluster-scope release costs 1-3 k cycles here (it drains every outstanding global access of the thread).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
 // image (shared) -> ring slot (global), then wait until the bulk store has completed
 __device__ __forceinline__ void bulk_store_wait(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
@@ -721,6 +729,263 @@ rec_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   cluster_sync_all();
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, "quad" formulation: 64 hidden units per CTA, S/64 CTAs per cluster, R (32 or 16) batch rows per tile,
+// TRANSPOSED product.  Why: the kernel above is bound by what every SM has to ingest per dependent step -- the all-gathered
+// dG tile is rows x 4S bf16 = 128 KB at 64 rows, and 64 MMAs of N=32 wait on it.  Here
+//     dh^T [64 units (M) x R rows (N)] = W_hh^T slice [64 x 4S] (A, resident, K-major)  x  dG tile [R rows x 4S] (B, K-major)
+// so the tile an SM ingests per step shrinks with R (64 KB at R=32, 32 KB at R=16) while the MMA count stays 4S/16 and the
+// per-instruction cost stays at the ~27-cycle issue floor (N <= 32).  Half as many CTAs per cluster (4 at S=256) also halves
+// the number of producers every step has to wait for.  The accumulator's TMEM lane is now a UNIT and its column a batch
+// row: an epilogue thread owns one unit x R/4 rows, so (a) all streaming operands (saved activations, dhout, c) are read
+// straight from global memory with unit-contiguous (coalesced) accesses one whole exchange ahead of their use -- no
+// staging tiles -- and (b) the bias gradient is 4 registers per thread instead of 32.
+// Exchange protocol, image = own slot of the operand tile, `a_free` / `img_free` hand-shakes: exactly as above.
+// ------------------------------------------------------------------------------------------------
+constexpr int Q_UNITS = 64;
+constexpr int Q_MAXNC = 4;
+
+template <int R>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, RecClParams p) {
+  constexpr int B_BLK = R * 128;          // one k-block of the dG tile: R rows x 64 bf16
+  constexpr int W_BLK = Q_UNITS * 128;    // one k-block of the weight slice: 64 unit rows x 64 bf16
+  constexpr int IMG = 4 * B_BLK;          // a producer's image: its 64 units x 4 gates = 4 k-blocks
+  constexpr int CPT = R / 4;              // cells (batch rows of ONE unit) per epilogue thread
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.S, NC = S / Q_UNITS, NKB = S / 16;     // NKB = 4S/64 k-blocks of the 4S-long reduction
+  const int slice = blockIdx.x, dir = blockIdx.y, bt = blockIdx.z;
+  uint8_t* Wsm = smem;                    // [NKB] blocks of W_BLK
+  uint8_t* Bsm = Wsm + NKB * W_BLK;       // [NKB] blocks of B_BLK
+  uint8_t* img = Bsm + slice * IMG;       // own slot of the tile = outgoing image
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bsm + NKB * B_BLK);
+  uint64_t* w_full = bars;
+  uint64_t* mma_done = bars + 1;
+  uint64_t* tmem_free = bars + 2;
+  uint64_t* a_free = bars + 3;            // NC remote arrivals per step: every CTA's MMAs have consumed its tile
+  uint64_t* stage_ready = bars + 4;
+  uint64_t* img_free = bars + 5;
+  uint64_t* full = bars + 6;              // [NC] one per producer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + Q_MAXNC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmG);
+    mbar_init(w_full, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(tmem_free, 256);
+    mbar_init(a_free, NC);
+    mbar_init(stage_ready, 256);
+    mbar_init(img_free, 1);
+    for (int i = 0; i < NC; ++i) mbar_init(full + i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<32>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, NKB * W_BLK);
+    for (int kb = 0; kb < NKB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * S + slice * Q_UNITS);
+    if (p.n_seq > 1)
+      for (int i = 0; i < NC; ++i) mbar_expect_tx(full + i, IMG);
+  }
+  cluster_sync_all();
+
+  if (warp == 0) {
+    // ---------------- exchange thread ----------------
+    if (elect_one()) {
+      const uint16_t cmask = (uint16_t)((1u << NC) - 1u);
+      const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      const int seq_inner = p.rs_seq < p.rs_batch ? 1 : 0;
+      for (int s = 0; s < p.n_seq; ++s) {
+        const int t = dir == 0 ? p.n_seq - 1 - s : s;
+        uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * IMG;
+        mbar_wait_t(stage_ready, s & 1);
+        CL_STAMP(8);
+        if (s + 1 < p.n_seq) {
+          bulk_store_wait(slot, img, IMG);
+          CL_STAMP(9);
+          if (s > 0) mbar_wait_t(a_free, (s - 1) & 1);           // every CTA of the cluster has finished reading dG(t_next)
+          CL_STAMP(11);
+          bulk_load_mc(img, slot, IMG, full + slice, cmask);
+          CL_STAMP(6);
+        }
+        // row-major bf16 dG for the batched weight / input gradient GEMMs: each image k-block IS a swizzled TMA box
+        {
+          const int c1 = seq_inner ? t : bt * R, c2 = seq_inner ? bt * R : t;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_store_3d(&tmG, img + i * B_BLK, dir * 4 * S + slice * 256 + i * 64, c1, c2);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        mbar_arrive(img_free);
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA warp: one elected lane issues, lanes 0..NC-1 release the tile to the cluster ----------------
+    constexpr uint32_t idesc = umma_idesc_bf16(Q_UNITS, R);
+    const uint32_t b0 = smem_u32(Bsm), w0 = smem_u32(Wsm);
+    const bool leader = elect_one();
+    for (int s = 1; s < p.n_seq; ++s) {
+      if (leader) {
+        if (s == 1) mbar_wait_t(w_full, 0);
+        if (s > 1) mbar_wait_t(tmem_free, (s - 2) & 1);
+        // The issuing thread runs only ~6 MMAs ahead of the tensor pipe, so whatever it does between two producers' groups
+        // must stay below ~150 cycles or the pipe drains: one (usually already complete) barrier wait and a fence only; the
+        // barriers are re-armed after the last MMA has been issued (no producer can deliver the next tile before this CTA's
+        // a_free arrive, which follows mma_done).
+        for (int pc = 0; pc < NC; ++pc) {
+          mbar_wait_t(full + pc, (s - 1) & 1);                          // producer pc's four k-blocks of dG(t_next) have landed
+          if (pc == 0) CL_STAMP(1);
+          tc_fence_after();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int kb = pc * 4 + i;
+            const uint64_t da = umma_desc_k128(w0 + kb * W_BLK), db = umma_desc_k128(b0 + kb * B_BLK);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_bf16_ss(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+        }
+        mma_commit(mma_done);
+        CL_STAMP(2);
+        if (s + 1 < p.n_seq)
+          for (int pc = 0; pc < NC; ++pc) mbar_expect_tx(full + pc, IMG);   // re-arm for the next step
+      }
+      __syncwarp();
+      // this CTA's tile is free again once its MMAs have completed: tell every producer of the cluster (one lane each).  Done
+      // HERE and not by an epilogue warp: a cluster-scope release there has to drain the warp's outstanding global loads
+      // (~1 k cycles on the dependent chain, measured); this warp has none and nothing waits for it before the next exchange.
+      if (lane < NC) {
+        mbar_wait_t(mma_done, (s - 1) & 1);
+        mbar_arrive_remote_relaxed(a_free, lane);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue: thread = (unit u, CPT batch rows) ----------------
+    const int q = warp & 3;                        // TMEM sub-partition: units q*16 .. q*16+15 of the CTA
+    const int cg = warp >= 6 ? 1 : 0;              // column group: batch rows cg*R/2 .. +R/2 of the tile
+    const int uh = lane >> 4, l16 = lane & 15;
+    const int ul = q * 16 + l16;                   // unit inside the CTA
+    const int r0 = cg * (R / 2) + uh * CPT;        // first of this thread's CPT tile rows
+    const size_t hcol = (size_t)dir * S + slice * Q_UNITS + ul;
+    const size_t gcol = (size_t)dir * 4 * S + (size_t)(slice * Q_UNITS + ul) * 4;
+    int len[CPT];
+    size_t rowb[CPT];                              // batch part of the row index
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int n = bt * R + r0 + j;
+      const bool in_range = n < p.n_batch;
+      len[j] = in_range ? (p.lens ? p.lens[n] : INT_MAX) : 0;          // out-of-range rows: never valid
+      rowb[j] = (size_t)(in_range ? n : 0) * p.rs_batch;
+    }
+    // image: k-block q, tile row r, bytes l16*8 .. +8 of the 128-byte row (16-byte chunk l16/2), 128-byte swizzle
+    uint8_t* img_u = img + q * B_BLK + (l16 & 1) * 8;
+    float dcreg[CPT], bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) dcreg[j] = 0.f;
+
+    for (int s = 0; s < p.n_seq; ++s) {
+      const int t = dir == 0 ? p.n_seq - 1 - s : s;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      const bool has_prev = dir == 0 ? (t > 0) : (t < p.n_seq - 1);
+      // everything of this step that does not depend on the recurrence, to registers (in flight during the exchange)
+      float4 a[CPT];
+      float dhv[CPT], cv[CPT], cpv[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const bool valid = t < len[j];
+        const bool pv = valid && has_prev && tp < len[j];
+        const size_t row = (size_t)t * p.rs_seq + rowb[j];
+        a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dhv[j] = 0.f; cv[j] = 0.f; cpv[j] = 0.f;
+        if (valid) {
+          a[j] = __ldcs(reinterpret_cast<const float4*>(p.xp + row * 8 * S + gcol));
+          dhv[j] = __ldcs(p.dhout + row * 2 * S + hcol);
+          cv[j] = __ldg(p.cbuf + row * 2 * S + hcol);
+        }
+        if (pv) cpv[j] = __ldg(p.cbuf + ((size_t)tp * p.rs_seq + rowb[j]) * 2 * S + hcol);
+      }
+      float dhm[CPT];                           // recurrent part of dh for this thread's cells
+      if (s > 0) {
+        uint32_t v[2 * CPT];
+        mbar_wait_t(mma_done, (s - 1) & 1);
+        if (threadIdx.x == 64) CL_STAMP(3);
+        tc_fence_after();
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * (R / 2));
+        if constexpr (R == 32) {
+          tmem_ld16(ta, v);
+        } else {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                       : "r"(ta) : "memory");
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tmem_free);
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+          const float up = __shfl_sync(0xffffffffu, __uint_as_float(v[CPT + k]), l16);
+          dhm[k] = uh ? up : __uint_as_float(v[k]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) dhm[k] = 0.f;
+      }
+      uint2 gq[CPT];                            // 4 gates of dG per cell, bf16
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const bool valid = t < len[j];
+        const bool pv = valid && has_prev && tp < len[j];
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dco = 0.f;
+        if (valid) {
+          const float4 aa = a[j];
+          const float dh = dhv[j] + dhm[j];
+          const float tc_ = tanh_apx(cv[j]);
+          const float dc = fmaf(dh * aa.w, 1.f - tc_ * tc_, dcreg[j]);
+          dg.w = dh * tc_ * aa.w * (1.f - aa.w);
+          dg.x = dc * aa.z * aa.x * (1.f - aa.x);
+          dg.z = dc * aa.x * (1.f - aa.z * aa.z);
+          dg.y = pv ? dc * cpv[j] * aa.y * (1.f - aa.y) : 0.f;
+          dco = dc * aa.y;
+        }
+        dcreg[j] = dco;
+        bsum[0] += dg.x; bsum[1] += dg.y; bsum[2] += dg.z; bsum[3] += dg.w;
+        __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+        gq[j] = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
+      }
+      if (s > 0) mbar_wait_t(img_free, (s - 1) & 1);     // the previous image has been read out (long done in practice)
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int r = r0 + j;
+        *reinterpret_cast<uint2*>(img_u + r * 128 + (((l16 >> 1) ^ (r & 7)) << 4)) = gq[j];
+      }
+      fence_proxy_async();
+      mbar_arrive(stage_ready);
+      if (threadIdx.x == 64) CL_STAMP(5);
+    }
+    if (p.dbias) {                      // bias gradient: the two half-warps hold the same unit, then one atomic per gate
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float v = bsum[g] + __shfl_xor_sync(0xffffffffu, bsum[g], 16);
+        if (!uh) atomicAdd(p.dbias + gcol + g, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<32>(tmem);
+  cluster_sync_all();
+}
+
 static long long* g_cl_dbg = nullptr;
 
 template <typename Kern, typename... Args>
@@ -866,6 +1131,38 @@ int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
 // largest padded input width the fused forward projection accepts
 int rec_cl_fused_kp_max() { return 16 * FW_MAXKX; }
 
+static size_t bwdq_smem(int S, int R) { return (size_t)8 * R * S + (size_t)512 * S + (6 + Q_MAXNC) * 8 + 16 + 1024; }
+
+// "quad" backward (rec_q_bwd_kernel): S in {128, 256}; rows per tile from SSASR_REC_Q_ROWS (32 default, 16; 0 = disabled)
+static int g_q_rows = -1;
+static int q_rows() {
+  if (g_q_rows < 0) {
+    const char* e = getenv("SSASR_REC_Q_ROWS");
+    g_q_rows = e ? atoi(e) : 32;
+    if (g_q_rows != 0 && g_q_rows != 16 && g_q_rows != 32) g_q_rows = 32;
+  }
+  return g_q_rows;
+}
+
+template <int R>
+static int rec_q_bwd_launch(cudaStream_t st, RecClParams& p, const void* whhT_bf, void* dgb) {
+  const int S = p.S;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_q_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdq_smem(256, R)));
+    attr_set = true;
+  }
+  CUtensorMap tmW, tmG;
+  int rc = make_tmap_bf16(&tmW, whhT_bf, 2 * S, 4 * S, 4 * S, Q_UNITS);
+  if (rc) return rc;
+  rc = p.rs_seq < p.rs_batch ? make_tmap_bf16_3d_ex(&tmG, dgb, 8 * S, p.n_seq, p.rs_seq * 8 * S, p.n_batch, p.rs_batch * 8 * S, 64, 1, R, 128)
+                             : make_tmap_bf16_3d_ex(&tmG, dgb, 8 * S, p.n_batch, p.rs_batch * 8 * S, p.n_seq, p.rs_seq * 8 * S, 64, R, 1, 128);
+  if (rc) return rc;
+  dim3 grid(S / Q_UNITS, 2, (p.n_batch + R - 1) / R);
+  ProfScope ps(F_REC_TC_BWD, st);
+  return cluster_launch(rec_q_bwd_kernel<R>, grid, S / Q_UNITS, bwdq_smem(S, R), st, tmW, tmG, p);
+}
+
 int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
                int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias) {
   RecClParams p = {};
@@ -874,6 +1171,9 @@ int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
   p.dbg = g_cl_dbg;
   p.ring = ring_for(st);
   SSASR_REQUIRE(p.ring != nullptr, "rec_cl_bwd: cannot allocate the exchange ring");
+  const int R = q_rows();
+  if (R && (S == 128 || S == 256) && 2 * ((n_batch + R - 1) / R) * (S / Q_UNITS) <= 148)
+    return R == 32 ? rec_q_bwd_launch<32>(st, p, whhT_bf, dgb) : rec_q_bwd_launch<16>(st, p, whhT_bf, dgb);
   CUtensorMap tmW, tmG;
   int rc = make_tmap_bf16(&tmW, whhT_bf, 2 * S, 4 * S, 4 * S, 32);
   if (rc) return rc;
@@ -885,6 +1185,8 @@ int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
   return cluster_launch(rec_cl_bwd_kernel, grid, S / CL_UNITS, bwd_smem(S), st, tmW, tmG, p);
 }
 
+void rec_q_set_rows(int rows) { g_q_rows = (rows == 16 || rows == 32) ? rows : 0; }
+
 }  // namespace ssasr
 
 extern "C" {
@@ -894,4 +1196,7 @@ void ssasr_rec_cl_set_debug(long long* dev_buf) { ssasr::g_cl_dbg = dev_buf; }
 int ssasr_rec_cl_capacity(int S, int backward) { return ssasr::rec_cl_capacity(S, backward); }
 // 0: use the counter-barrier kernels of rec_tc.cu even where the cluster kernels apply (A/B comparison in tests and scripts)
 void ssasr_rec_cl_enable(int on) { ssasr::rec_cl_enable(on); }
+// batch rows per tile of the quad-cluster recurrent kernels (64 units per CTA): 32 (default) or 16; 0 selects the older
+// 8-CTA / 64-row kernels (A/B comparison in tests and scripts)
+void ssasr_rec_q_set_rows(int rows) { ssasr::rec_q_set_rows(rows); }
 }

@@ -171,9 +171,12 @@ def test_tiny_golden_greedy_and_decode(golden_dir):
     assert np.abs(gl.cpu().numpy() - z['greedy_logits']).max() < 1e-4
     assert np.abs(ga.numpy() - z['greedy_att']).max() < 1e-5
 
-    class Mapper:
+    class Mapper:          # the two ASRDataset.Mapper methods ASR.decode uses (asr.py:167,171)
         def ind_to_char(self, i):
             return O.TOKENS[i]
+
+        def char_to_ind(self, c):
+            return O.TOKENS.index(c)
     lm = _CharLM()
     lm.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('lm.')})
     for i in range(len(z['decode_lm0'])):
