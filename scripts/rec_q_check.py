@@ -49,6 +49,36 @@ for (B, T, K, S) in shapes:
             r = d[T // 2]
             msg += ' | %.0f cycles/step; stamps(step %d rel. to MMA start) %s' % (per, T // 2, [int(v - r[1]) if v else None for v in r[:12]])
         print(msg, flush=True)
+    # forward: outputs of the four variants + timing / timeline of the recurrent forward kernel
+    fres = {}
+    for name, rows, cl in (('quad32', 32, 1), ('quad16', 16, 1), ('cl8', 0, 1), ('counter', 0, 0)):
+        lib.ssasr_rec_q_set_rows(rows)
+        lib.ssasr_rec_cl_enable(cl)
+        with torch.no_grad():
+            for it in range(3):
+                if it == 2 and cl:
+                    dbg = torch.zeros(T, 12, dtype=torch.int64, device=dev)
+                    lib.ssasr_rec_cl_set_debug(dbg.data_ptr())
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out, _, _ = m(x0, state_len=lens, pack_input=True)
+                e1.record()
+                torch.cuda.synchronize()
+                lib.ssasr_rec_cl_set_debug(None)
+        fres[name] = out.clone()
+        msg = '%-8s fwd B=%d T=%d S=%d: layer forward %.3f ms' % (name, B, T, S, e0.elapsed_time(e1))
+        if cl:
+            d = dbg.cpu()
+            lo, hi = T // 4, 3 * T // 4
+            per = (d[hi][1] - d[lo][1]).item() / (hi - lo)
+            r = d[T // 2]
+            msg += ' | %.0f cycles/step; stamps(step %d rel. to MMA start) %s' % (per, T // 2, [int(v - r[1]) if v else None for v in r[:12]])
+        print(msg, flush=True)
+    for name in ('quad32', 'quad16', 'cl8'):
+        dmax = float((fres[name] - fres['counter']).abs().max())
+        print('  fwd %s vs counter-barrier: max abs difference %.2e' % (name, dmax), flush=True)
+        assert dmax < 2e-3, name
     ref = res['counter']
     for name in ('quad32', 'quad16', 'cl8'):
         worst = float((res[name][0] - ref[0]).norm() / ref[0].norm())
@@ -56,6 +86,6 @@ for (B, T, K, S) in shapes:
             worst = max(worst, float((res[name][1][k] - ref[1][k]).norm() / (ref[1][k].norm() + 1e-20)))
         print('  %s vs counter-barrier: worst rel-L2 difference over dx and the 8 parameter gradients %.2e' % (name, worst), flush=True)
         assert worst < 2e-3, name
-lib.ssasr_rec_q_set_rows(32)
+lib.ssasr_rec_q_set_rows(16)
 lib.ssasr_rec_cl_enable(1)
 print('ok')

@@ -744,14 +744,36 @@ rec_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 constexpr int Q_UNITS = 64;
 constexpr int Q_MAXNC = 4;
+// 16 epilogue warps (4 per scheduler): with 8 the per-step cell math of a tile is issue- / latency-bound on two warps per
+// scheduler (measured: ~300 cycles per cell and thread); TMEM sub-partition = warp % 4, the four warps of a sub-partition
+// split the accumulator columns (and, forward, the two M=128 halves)
+constexpr int Q_EPW = 16;
+constexpr int Q_THREADS = 64 + 32 * Q_EPW;
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t ta, uint32_t* v) {
+  if constexpr (N == 32) {
+    tmem_ld32(ta, v);
+  } else if constexpr (N == 16) {
+    tmem_ld16(ta, v);
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(ta) : "memory");
+  } else {
+    static_assert(N == 4, "tmem_ld_n: 4 / 8 / 16 / 32 columns");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(ta) : "memory");
+  }
+}
 
 template <int R>
-__global__ void __launch_bounds__(CL_THREADS, 1)
+__global__ void __launch_bounds__(Q_THREADS, 1)
 rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG, RecClParams p) {
   constexpr int B_BLK = R * 128;          // one k-block of the dG tile: R rows x 64 bf16
   constexpr int W_BLK = Q_UNITS * 128;    // one k-block of the weight slice: 64 unit rows x 64 bf16
   constexpr int IMG = 4 * B_BLK;          // a producer's image: its 64 units x 4 gates = 4 k-blocks
-  constexpr int CPT = R / 4;              // cells (batch rows of ONE unit) per epilogue thread
+  constexpr int CPT = R / 8;              // cells (batch rows of ONE unit) per epilogue thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.S, NC = S / Q_UNITS, NKB = S / 16;     // NKB = 4S/64 k-blocks of the 4S-long reduction
@@ -775,9 +797,9 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     tma_prefetch_desc(&tmG);
     mbar_init(w_full, 1);
     mbar_init(mma_done, 1);
-    mbar_init(tmem_free, 256);
+    mbar_init(tmem_free, Q_EPW);          // one arrival per epilogue WARP (512 per-thread arrivals serialise on the barrier word)
     mbar_init(a_free, NC);
-    mbar_init(stage_ready, 256);
+    mbar_init(stage_ready, Q_EPW);
     mbar_init(img_free, 1);
     for (int i = 0; i < NC; ++i) mbar_init(full + i, 1);
     fence_barrier_init();
@@ -871,10 +893,10 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   } else {
     // ---------------- epilogue: thread = (unit u, CPT batch rows) ----------------
     const int q = warp & 3;                        // TMEM sub-partition: units q*16 .. q*16+15 of the CTA
-    const int cg = warp >= 6 ? 1 : 0;              // column group: batch rows cg*R/2 .. +R/2 of the tile
+    const int cg = (warp - 2) >> 2;                // column group: batch rows cg*R/4 .. +R/4 of the tile
     const int uh = lane >> 4, l16 = lane & 15;
     const int ul = q * 16 + l16;                   // unit inside the CTA
-    const int r0 = cg * (R / 2) + uh * CPT;        // first of this thread's CPT tile rows
+    const int r0 = cg * (R / 4) + uh * CPT;        // first of this thread's CPT tile rows
     const size_t hcol = (size_t)dir * S + slice * Q_UNITS + ul;
     const size_t gcol = (size_t)dir * 4 * S + (size_t)(slice * Q_UNITS + ul) * 4;
     int len[CPT];
@@ -913,23 +935,19 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         if (pv) cpv[j] = __ldg(p.cbuf + ((size_t)tp * p.rs_seq + rowb[j]) * 2 * S + hcol);
       }
+      if (s > 0) mbar_wait_t(img_free, (s - 1) & 1);     // the previous image has been read out: checked off the dependent chain
       float dhm[CPT];                           // recurrent part of dh for this thread's cells
       if (s > 0) {
         uint32_t v[2 * CPT];
         mbar_wait_t(mma_done, (s - 1) & 1);
         if (threadIdx.x == 64) CL_STAMP(3);
         tc_fence_after();
-        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * (R / 2));
-        if constexpr (R == 32) {
-          tmem_ld16(ta, v);
-        } else {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                       : "r"(ta) : "memory");
-        }
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * (R / 4));
+        tmem_ld_n<2 * CPT>(ta, v);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(tmem_free);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_free);
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const float up = __shfl_sync(0xffffffffu, __uint_as_float(v[CPT + k]), l16);
@@ -962,14 +980,14 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
         gq[j] = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
       }
-      if (s > 0) mbar_wait_t(img_free, (s - 1) & 1);     // the previous image has been read out (long done in practice)
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const int r = r0 + j;
         *reinterpret_cast<uint2*>(img_u + r * 128 + (((l16 >> 1) ^ (r & 7)) << 4)) = gq[j];
       }
       fence_proxy_async();
-      mbar_arrive(stage_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stage_ready);
       if (threadIdx.x == 64) CL_STAMP(5);
     }
     if (p.dbias) {                      // bias gradient: the two half-warps hold the same unit, then one atomic per gate
@@ -986,7 +1004,295 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   cluster_sync_all();
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, "quad" formulation (same decomposition as rec_q_bwd_kernel): 64 hidden units = 256 gate rows per CTA as two
+// M=128 halves, transposed product
+//     gates^T [128 gate rows (M) x R batch rows (N)] (+)= W_hh slice [128 x S] (A, resident)  x  h(t-1) tile [R rows x S] (B)
+// Per step an SM ingests R x S bf16 (16 KB at R=32) instead of 32 KB, exchanges a 4 KB image instead of 4 KB x 8 producers,
+// and waits for S/64 producers instead of S/32.  TMEM lane = gate row (unit*4 + gate), column = batch row: the four gates of
+// a unit sit in four adjacent lanes, a 4x4 shuffle transpose per four batch rows hands lane g' of the quad the cells
+// (unit, rows 4m + g'); every thread then owns ONE unit x R/4 rows, and all global traffic (pre-activations in; activations,
+// h, c out) is issued straight from registers with 8 consecutive units per row segment (128-byte lines for the gate
+// buffers) -- no staging tiles.  The bf16 h copy (next layer's input / weight-gradient operand) is TMA-stored from the image.
+// XF: the layer's input projection is fused in exactly as in rec_cl_fwd_kernel<true>.
+// ------------------------------------------------------------------------------------------------
+template <int R, bool XF>
+__global__ void __launch_bounds__(Q_THREADS, 1)
+rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmWx, const __grid_constant__ CUtensorMap tmH, RecClParams p) {
+  constexpr int W_BLK = 256 * 128;       // one k-block of the weight slice: 256 gate rows x 64 bf16
+  constexpr int IMG = R * 128;           // one k-block of the h tile = one producer's image: R rows x 64 units bf16
+  constexpr int WX_BLK = 256 * 32;       // fused projection: 256 gate rows x 16 bf16
+  constexpr int X_BLK = R * 32;          // fused projection: R rows x 16 bf16
+  constexpr int CPT = R / 8;             // cells (batch rows of ONE unit) per epilogue thread
+  constexpr int TCOLS = 2 * R < 32 ? 32 : 2 * R;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int S = p.S, KB = S / 64, NC = S / Q_UNITS;
+  uint8_t* Wsm = smem;                                                   // [KB] blocks of W_BLK
+  uint8_t* Hsm = Wsm + KB * W_BLK;                                       // [2][NC] k-blocks of IMG
+  uint8_t* img = Hsm + 2 * NC * IMG;                                     // this CTA's outgoing image
+  uint8_t* Wx = img + (IMG < 1024 ? 1024 : IMG);                         // XF: [nkx] k-blocks of WX_BLK
+  uint8_t* Xs = Wx + (XF ? FW_MAXKX * WX_BLK : 0);                       // XF: [2][nkx] k-blocks of X_BLK
+  float* bsm = reinterpret_cast<float*>(Xs + (XF ? 2 * FW_MAXKX * X_BLK : 0));   // XF: [256] gate bias slice
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bsm + (XF ? 256 : 0));
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;           // [2]
+  uint64_t* mma_done = bars + 3;
+  uint64_t* tmem_free = bars + 4;
+  uint64_t* stage_ready = bars + 5;
+  uint64_t* x_full = bars + 6;           // [2] XF
+  uint64_t* img_free = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int slice = blockIdx.x, dir = blockIdx.y, bt = blockIdx.z;      // cluster = the NC CTAs along x
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile_bytes = (uint32_t)NC * IMG;
+  const int seq_inner = p.rs_seq < p.rs_batch ? 1 : 0;
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmH);
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(a_full + 1, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(tmem_free, Q_EPW);          // one arrival per epilogue WARP (512 per-thread arrivals serialise on the barrier word)
+    mbar_init(stage_ready, Q_EPW);
+    mbar_init(x_full, 1);
+    mbar_init(x_full + 1, 1);
+    mbar_init(img_free, 1);
+    if (XF) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmWx); }
+    fence_barrier_init();
+  }
+  if (XF && threadIdx.x >= 64 && threadIdx.x < 320) bsm[threadIdx.x - 64] = p.bias[(size_t)dir * 4 * S + slice * 256 + threadIdx.x - 64];
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, KB * W_BLK + (XF ? p.nkx * WX_BLK : 0));
+    for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * 4 * S + slice * 256);
+    if (XF)
+      for (int kx = 0; kx < p.nkx; ++kx) tma_load_3d(&tmWx, w_full, Wx + kx * WX_BLK, kx * 16, dir * 4 * S + slice * 256, 0);
+    mbar_expect_tx(a_full, tile_bytes);          // h(0) and h(1); re-armed by the MMA thread after each wait
+    mbar_expect_tx(a_full + 1, tile_bytes);
+  }
+  cluster_sync_all();                            // every CTA's barriers exist before any multicast can signal them
+
+  if (warp == 0) {
+    // ---------------- exchange thread ----------------
+    if (elect_one()) {
+      const uint16_t cmask = (uint16_t)((1u << NC) - 1u);
+      const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      auto load_x = [&](int s_) {
+        const int t_ = dir == 0 ? s_ : p.n_seq - 1 - s_;
+        uint64_t* xb = x_full + (s_ & 1);
+        mbar_expect_tx(xb, p.nkx * X_BLK);
+        for (int kx = 0; kx < p.nkx; ++kx)
+          tma_load_3d(&tmX, xb, Xs + ((s_ & 1) * FW_MAXKX + kx) * X_BLK, kx * 16, seq_inner ? t_ : bt * R, seq_inner ? bt * R : t_);
+      };
+      if (XF) {
+        load_x(0);
+        if (p.n_seq > 1) load_x(1);
+      }
+      for (int s = 0; s < p.n_seq; ++s) {
+        const int t = dir == 0 ? s : p.n_seq - 1 - s;
+        uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * IMG;
+        mbar_wait_t(stage_ready, s & 1);                           // all 256 epilogue threads have written the image
+        CL_STAMP(8);
+        if (s + 1 < p.n_seq) {
+          bulk_store_wait(slot, img, IMG);
+          CL_STAMP(9);
+          bulk_load_mc(Hsm + ((s & 1) * NC + slice) * IMG, slot, IMG, a_full + (s & 1), cmask);
+          CL_STAMP(6);
+        }
+        // bf16 copy of h (next layer's input, weight-gradient operand): the image IS the swizzled TMA box
+        tma_store_3d(&tmH, img, dir * S + slice * Q_UNITS, seq_inner ? t : bt * R, seq_inner ? bt * R : t);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(img_free);
+        if (XF && s + 2 < p.n_seq) load_x(s + 2);                  // the MMAs of step s (reading Xs[s & 1]) completed before its epilogue
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA thread ----------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, R);
+      const int nk = S / 16;
+      for (int s = XF ? 0 : 1; s < p.n_seq; ++s) {
+        if (s == (XF ? 0 : 1)) mbar_wait_t(w_full, 0);
+        if (XF) {
+          // input projection of step s: independent of the recurrence, issued (and executing) while h(s-1) is exchanged
+          if (s > 0) mbar_wait_t(tmem_free, (s - 1) & 1);          // epilogue has drained the accumulators
+          mbar_wait_t(x_full + (s & 1), (s >> 1) & 1);
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(Xs + (s & 1) * FW_MAXKX * X_BLK), wx0 = smem_u32(Wx);
+          for (int kx = 0; kx < p.nkx; ++kx) {
+            mma_bf16_ss(tmem, umma_desc_k32(wx0 + kx * WX_BLK), umma_desc_k32(x0 + kx * X_BLK), idesc, kx != 0);
+            mma_bf16_ss(tmem + R, umma_desc_k32(wx0 + kx * WX_BLK + 128 * 32), umma_desc_k32(x0 + kx * X_BLK), idesc, kx != 0);
+          }
+        }
+        if (s > 0) {
+          const int b = (s - 1) & 1;
+          mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // all NC slices of h(s-1) have landed
+          if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
+          if (!XF && s > 1) mbar_wait_t(tmem_free, (s - 2) & 1);     // epilogue has drained the accumulators
+          CL_STAMP(1);
+          tc_fence_after();
+          const uint32_t h0 = smem_u32(Hsm + b * NC * IMG), w0 = smem_u32(Wsm);
+#pragma unroll 4
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint64_t dh = umma_desc_k128(h0 + (kk >> 2) * IMG) + (uint64_t)((kk & 3) * 2);
+            const uint64_t dw = umma_desc_k128(w0 + (kk >> 2) * W_BLK) + (uint64_t)((kk & 3) * 2);
+            mma_bf16_ss(tmem, dw, dh, idesc, (XF || kk != 0) ? 1u : 0u);
+            mma_bf16_ss(tmem + R, dw + (uint64_t)((128 * 128) >> 4), dh, idesc, (XF || kk != 0) ? 1u : 0u);
+          }
+        }
+        mma_commit(mma_done);
+        CL_STAMP(2);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: thread = (unit u, CPT batch rows 4m + gp) ----------------
+    const int q = warp & 3;                        // TMEM sub-partition: gate rows q*32 .. q*32+31 of the half
+    const int half = ((warp - 2) >> 2) & 1;        // M=128 half of the CTA's 256 gate rows
+    const int cgp = (warp - 2) >> 3;               // column group: batch rows cgp*R/2 .. +R/2 of the tile
+    const int uq = lane >> 2, gp = lane & 3;
+    const int ul = half * 32 + q * 8 + uq;         // unit inside the CTA
+    const size_t hcol = (size_t)dir * S + slice * Q_UNITS + ul;
+    const size_t gcol = (size_t)dir * 4 * S + (size_t)(slice * Q_UNITS + ul) * 4;
+    int len[CPT];
+    size_t rowb[CPT];
+    bool inr[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; ++m) {
+      const int n = bt * R + cgp * (R / 2) + 4 * m + gp;
+      inr[m] = n < p.n_batch;
+      len[m] = inr[m] ? (p.lens ? p.lens[n] : INT_MAX) : 0;
+      rowb[m] = (size_t)(inr[m] ? n : 0) * p.rs_batch;
+    }
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (XF) bias4 = *reinterpret_cast<const float4*>(bsm + ul * 4);
+    float creg[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; ++m) creg[m] = 0.f;
+    uint8_t* img_u = img + (ul & 7) * 2;           // + row*128 + swizzled 16-byte chunk (ul >> 3)
+
+    // pre-activations are fetched ONE WHOLE STEP ahead (registers): a load issued at the top of its own step is not back
+    // when the accumulator is (measured: the epilogue then stalls on HBM latency under the kernel's own store bursts)
+    float4 gn[CPT];
+    auto fetch_g = [&](int s_) {
+      const int t_ = dir == 0 ? s_ : p.n_seq - 1 - s_;
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) {
+        gn[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t_ < len[m]) gn[m] = __ldcs(reinterpret_cast<const float4*>(p.xp + ((size_t)t_ * p.rs_seq + rowb[m]) * 8 * S + gcol));
+      }
+    };
+    if (!XF) fetch_g(0);
+
+    for (int s = 0; s < p.n_seq; ++s) {
+      const int t = dir == 0 ? s : p.n_seq - 1 - s;
+      float4 g[CPT];                               // pre-activations of this thread's cells (i,f,g,o)
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) g[m] = XF ? ((t < len[m]) ? bias4 : make_float4(0.f, 0.f, 0.f, 0.f)) : gn[m];
+      if (!XF && s + 1 < p.n_seq) fetch_g(s + 1);
+      if (s > 0) mbar_wait_t(img_free, (s - 1) & 1);     // the previous image has been read out: checked off the dependent chain
+      if (XF || s > 0) {
+        uint32_t v[R / 2];
+        mbar_wait_t(mma_done, XF ? (s & 1) : ((s - 1) & 1));
+        if (threadIdx.x == 64) CL_STAMP(3);
+        tc_fence_after();
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * R + cgp * (R / 2));
+        tmem_ld_n<R / 2>(ta, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_free);
+        // 4x4 transposes inside the lane quad: lane gate g holds rows 4m..4m+3 of ITS gate; afterwards lane gp holds the four
+        // gates of row 4m + gp
+#pragma unroll
+        for (int m = 0; m < CPT; ++m) {
+          float a0 = __uint_as_float(v[4 * m]), a1 = __uint_as_float(v[4 * m + 1]), a2 = __uint_as_float(v[4 * m + 2]),
+                a3 = __uint_as_float(v[4 * m + 3]);
+          {
+            const float x = (gp & 1) ? a0 : a1, y = (gp & 1) ? a2 : a3;
+            const float xr = __shfl_xor_sync(0xffffffffu, x, 1), yr = __shfl_xor_sync(0xffffffffu, y, 1);
+            if (gp & 1) { a0 = xr; a2 = yr; } else { a1 = xr; a3 = yr; }
+          }
+          {
+            const float x = (gp & 2) ? a0 : a2, y = (gp & 2) ? a1 : a3;
+            const float xr = __shfl_xor_sync(0xffffffffu, x, 2), yr = __shfl_xor_sync(0xffffffffu, y, 2);
+            if (gp & 2) { a0 = xr; a1 = yr; } else { a2 = xr; a3 = yr; }
+          }
+          if (t < len[m]) { g[m].x += a0; g[m].y += a1; g[m].z += a2; g[m].w += a3; }
+        }
+      }
+      float hv[CPT], cv[CPT];
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[m] = 0.f; cv[m] = 0.f;
+        if (t < len[m]) {
+          a.x = sigmoid_apx(g[m].x); a.y = sigmoid_apx(g[m].y); a.z = tanh_apx(g[m].z); a.w = sigmoid_apx(g[m].w);
+          cv[m] = fmaf(a.y, creg[m], a.x * a.z);
+          hv[m] = a.w * tanh_apx(cv[m]);
+        }
+        creg[m] = cv[m];
+        g[m] = a;
+      }
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) {
+        const int r = cgp * (R / 2) + 4 * m + gp;
+        *reinterpret_cast<__nv_bfloat16*>(img_u + r * 128 + (((ul >> 3) ^ (r & 7)) << 4)) = __float2bfloat16_rn(hv[m]);
+      }
+      fence_proxy_async();                         // generic-proxy smem writes -> visible to the bulk (async proxy) copies
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stage_ready);
+      if (threadIdx.x == 64) CL_STAMP(5);
+      // ---- off the dependent chain: saved tensors ----
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) {
+        if (inr[m]) {
+          const size_t row = (size_t)t * p.rs_seq + rowb[m];
+          __stcs(reinterpret_cast<float4*>(p.xp + row * 8 * S + gcol), g[m]);
+          p.hout[row * 2 * S + hcol] = hv[m];
+          p.cbuf[row * 2 * S + hcol] = cv[m];
+        }
+      }
+      if (threadIdx.x == 64) CL_STAMP(7);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TCOLS>(tmem);
+  cluster_sync_all();                            // no CTA leaves while a peer could still address its shared memory
+}
+
 static long long* g_cl_dbg = nullptr;
+
+template <typename Kern, typename... Args>
+static int cluster_launch_t(int threads, Kern kern, dim3 grid, int cluster_x, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  return 0;
+}
 
 template <typename Kern, typename... Args>
 static int cluster_launch(Kern kern, dim3 grid, int cluster_x, size_t smem, cudaStream_t st, Args... args) {
@@ -1004,6 +1310,24 @@ static int cluster_launch(Kern kern, dim3 grid, int cluster_x, size_t smem, cuda
   cfg.numAttrs = 1;
   SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
   return 0;
+}
+
+// quad-cluster kernels (rec_q_*): S in {128, 256}; batch rows per tile from SSASR_REC_Q_ROWS / SSASR_REC_Q_ROWS_FWD
+// (16 default, 32; 0 = the 8-CTA kernels above)
+static int g_q_rows = -1, g_q_rows_fwd = -1;
+static int parse_rows(const char* name, int dflt) {
+  const char* e = getenv(name);
+  int r = e ? atoi(e) : dflt;
+  if (r != 0 && r != 16 && r != 32) r = dflt;
+  return r;
+}
+static int q_rows() {
+  if (g_q_rows < 0) g_q_rows = parse_rows("SSASR_REC_Q_ROWS", 16);
+  return g_q_rows;
+}
+static int q_rows_fwd() {
+  if (g_q_rows_fwd < 0) g_q_rows_fwd = parse_rows("SSASR_REC_Q_ROWS_FWD", q_rows());
+  return g_q_rows_fwd;
 }
 
 static size_t fwd_smem(int S, bool xf = false) {
@@ -1096,6 +1420,41 @@ int rec_cl_capacity(int S, int backward) {
 
 // x_bf / wih_bf / bias non-null: the input projection is fused in (x_bf [rows, Kp] bf16, wih_bf [8S, Kp] bf16, bias [8S]);
 // xp then is an output only (saved activations).  Otherwise xp holds the pre-activations computed by the batched GEMM.
+static size_t fwdq_smem(int S, int R, bool xf) {
+  return (size_t)(S / 64) * 32768 + (size_t)2 * (S / Q_UNITS) * R * 128 + (R * 128 < 1024 ? 1024 : R * 128) + 10 * 8 + 16 + 1024 +
+         (xf ? (size_t)FW_MAXKX * 256 * 32 + 2 * FW_MAXKX * R * 32 + 1024 : 0);
+}
+
+template <int R, bool XF>
+static int rec_q_fwd_launch(cudaStream_t st, RecClParams& p, const void* whh_bf, void* hb, const void* x_bf, int Kp, const void* wih_bf) {
+  const int S = p.S;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_q_fwd_kernel<R, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwdq_smem(256, R, XF)));
+    attr_set = true;
+  }
+  CUtensorMap tmW, tmX, tmWx, tmH;
+  int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 256);
+  if (rc) return rc;
+  const bool si = p.rs_seq < p.rs_batch;
+  rc = si ? make_tmap_bf16_3d_ex(&tmH, hb, 2 * S, p.n_seq, p.rs_seq * 2 * S, p.n_batch, p.rs_batch * 2 * S, 64, 1, R, 128)
+          : make_tmap_bf16_3d_ex(&tmH, hb, 2 * S, p.n_batch, p.rs_batch * 2 * S, p.n_seq, p.rs_seq * 2 * S, 64, R, 1, 128);
+  if (rc) return rc;
+  tmX = tmW; tmWx = tmW;
+  if (XF) {
+    rc = si ? make_tmap_bf16_3d_ex(&tmX, x_bf, Kp, p.n_seq, p.rs_seq * Kp, p.n_batch, p.rs_batch * Kp, 16, 1, R, 32)
+            : make_tmap_bf16_3d_ex(&tmX, x_bf, Kp, p.n_batch, p.rs_batch * Kp, p.n_seq, p.rs_seq * Kp, 16, R, 1, 32);
+    if (rc) return rc;
+    rc = make_tmap_bf16_3d_ex(&tmWx, wih_bf, Kp, 8 * S, Kp, 1, (long long)8 * S * Kp, 16, 256, 1, 32);
+    if (rc) return rc;
+  }
+  dim3 grid(S / Q_UNITS, 2, (p.n_batch + R - 1) / R);
+  ProfScope ps(F_REC_TC_FWD, st);
+  return cluster_launch_t(Q_THREADS, rec_q_fwd_kernel<R, XF>, grid, S / Q_UNITS, fwdq_smem(S, R, XF), st, tmW, tmX, tmWx, tmH, p);
+}
+
+// x_bf / wih_bf / bias non-null: the input projection is fused in (x_bf [rows, Kp] bf16, wih_bf [8S, Kp] bf16, bias [8S]);
+// xp then is an output only (saved activations).  Otherwise xp holds the pre-activations computed by the batched GEMM.
 int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
                int n_seq, int n_batch, long long rs_seq, long long rs_batch, const void* x_bf, int Kp, const void* wih_bf,
                const float* bias) {
@@ -1105,20 +1464,27 @@ int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
   p.dbg = g_cl_dbg;
   p.ring = ring_for(st);
   SSASR_REQUIRE(p.ring != nullptr, "rec_cl_fwd: cannot allocate the exchange ring");
+  const bool xf = x_bf && wih_bf && bias;
+  if (xf) {
+    SSASR_REQUIRE(Kp % 8 == 0 && Kp > 0 && Kp <= 16 * FW_MAXKX, "rec_cl_fwd: fused input projection needs Kp %% 8 == 0 and Kp <= %d (got %d)",
+                  16 * FW_MAXKX, Kp);
+    p.bias = bias;
+    p.nkx = (Kp + 15) / 16;
+    p.seq_inner = rs_seq < rs_batch ? 1 : 0;
+  }
+  const int R = q_rows_fwd();
+  if (R && (S == 128 || S == 256) && 2 * ((n_batch + R - 1) / R) * (S / Q_UNITS) <= 148) {
+    if (R == 32) return xf ? rec_q_fwd_launch<32, true>(st, p, whh_bf, hb, x_bf, Kp, wih_bf) : rec_q_fwd_launch<32, false>(st, p, whh_bf, hb, x_bf, Kp, wih_bf);
+    return xf ? rec_q_fwd_launch<16, true>(st, p, whh_bf, hb, x_bf, Kp, wih_bf) : rec_q_fwd_launch<16, false>(st, p, whh_bf, hb, x_bf, Kp, wih_bf);
+  }
   CUtensorMap tmW, tmX, tmWx;
   int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 128);
   if (rc) return rc;
   dim3 grid(S / CL_UNITS, 2, (n_batch + CL_TM - 1) / CL_TM);
-  const bool xf = x_bf && wih_bf && bias;
   if (!xf) {
     ProfScope ps(F_REC_TC_FWD, st);
     return cluster_launch(rec_cl_fwd_kernel<false>, grid, S / CL_UNITS, fwd_smem(S), st, tmW, tmW, tmW, p);
   }
-  SSASR_REQUIRE(Kp % 8 == 0 && Kp > 0 && Kp <= 16 * FW_MAXKX, "rec_cl_fwd: fused input projection needs Kp %% 8 == 0 and Kp <= %d (got %d)",
-                16 * FW_MAXKX, Kp);
-  p.bias = bias;
-  p.nkx = (Kp + 15) / 16;
-  p.seq_inner = rs_seq < rs_batch ? 1 : 0;
   rc = p.seq_inner ? make_tmap_bf16_3d_ex(&tmX, x_bf, Kp, n_seq, rs_seq * Kp, n_batch, rs_batch * Kp, 16, 1, CL_TM, 32)
                    : make_tmap_bf16_3d_ex(&tmX, x_bf, Kp, n_batch, rs_batch * Kp, n_seq, rs_seq * Kp, 16, CL_TM, 1, 32);
   if (rc) return rc;
@@ -1132,17 +1498,6 @@ int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
 int rec_cl_fused_kp_max() { return 16 * FW_MAXKX; }
 
 static size_t bwdq_smem(int S, int R) { return (size_t)8 * R * S + (size_t)512 * S + (6 + Q_MAXNC) * 8 + 16 + 1024; }
-
-// "quad" backward (rec_q_bwd_kernel): S in {128, 256}; rows per tile from SSASR_REC_Q_ROWS (32 default, 16; 0 = disabled)
-static int g_q_rows = -1;
-static int q_rows() {
-  if (g_q_rows < 0) {
-    const char* e = getenv("SSASR_REC_Q_ROWS");
-    g_q_rows = e ? atoi(e) : 32;
-    if (g_q_rows != 0 && g_q_rows != 16 && g_q_rows != 32) g_q_rows = 32;
-  }
-  return g_q_rows;
-}
 
 template <int R>
 static int rec_q_bwd_launch(cudaStream_t st, RecClParams& p, const void* whhT_bf, void* dgb) {
@@ -1160,7 +1515,7 @@ static int rec_q_bwd_launch(cudaStream_t st, RecClParams& p, const void* whhT_bf
   if (rc) return rc;
   dim3 grid(S / Q_UNITS, 2, (p.n_batch + R - 1) / R);
   ProfScope ps(F_REC_TC_BWD, st);
-  return cluster_launch(rec_q_bwd_kernel<R>, grid, S / Q_UNITS, bwdq_smem(S, R), st, tmW, tmG, p);
+  return cluster_launch_t(Q_THREADS, rec_q_bwd_kernel<R>, grid, S / Q_UNITS, bwdq_smem(S, R), st, tmW, tmG, p);
 }
 
 int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
@@ -1185,7 +1540,7 @@ int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
   return cluster_launch(rec_cl_bwd_kernel, grid, S / CL_UNITS, bwd_smem(S), st, tmW, tmG, p);
 }
 
-void rec_q_set_rows(int rows) { g_q_rows = (rows == 16 || rows == 32) ? rows : 0; }
+void rec_q_set_rows(int rows) { g_q_rows = g_q_rows_fwd = (rows == 16 || rows == 32) ? rows : 0; }
 
 }  // namespace ssasr
 

@@ -61,7 +61,7 @@ def _join_after_backward():
 # `loss.backward()` -- torch's own clip_grad_norm_ / optimisers included -- is ordered after the side stream; GradSync joins
 # on the side stream itself (the bucket all-reduce is issued there).
 # --------------------------------------------------------------------------------------------------
-_OVERLAP = {'on': False, 'streams': {}, 'pending': [], 'cb_queued': False}
+_OVERLAP = {'on': False, 'streams': {}, 'pending': [], 'cb_queued': False, 'deferred_total': 0}
 
 
 def set_overlap_wgrad(on):
@@ -243,6 +243,7 @@ class _BLSTM(torch.autograd.Function):
                 # NOT `g`: AccumulateGrad only adopts a gradient buffer it holds the sole reference to (otherwise it clones it --
                 # on the main stream, before the side stream has written it)
                 _OVERLAP['pending'].append((ev, (ws, xb_s, hb_s, dwih_p, dbias_p, dwhh_p, wihT_bf, whhT_bf)))
+                _OVERLAP['deferred_total'] += 1
                 _join_after_backward()
             return (dx, None, None, None) + tuple(g)
         else:
@@ -407,6 +408,7 @@ class _Spell(torch.autograd.Function):
             # everything the side stream still reads or writes, EXCEPT the returned gradient buffers (AccumulateGrad only adopts
             # a buffer it holds the sole reference to; otherwise it clones it on the main stream, before it has been written)
             _OVERLAP['pending'].append((ev, (ctx.saved_tensors, dlogits, scr, wsA, wsB, w1T, w2T, d_w1cat, d_b1, d_w2cat, d_b2)))
+            _OVERLAP['deferred_total'] += 1
             _join_after_backward()
         return (denc, None, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
 

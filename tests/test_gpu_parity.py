@@ -453,11 +453,12 @@ def test_per_step_module_api_matches_fused_forward():
     _check_grads(m, grads_o)
 
 
-@pytest.mark.parametrize('S,B,T,K', [(256, 200, 48, 64), (128, 70, 33, 40), (64, 9, 21, 24)])
+@pytest.mark.parametrize('S,B,T,K', [(256, 200, 48, 64), (256, 37, 20, 1024), (128, 70, 33, 40), (64, 9, 21, 24)])
 def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
-    """The cluster recurrent kernels (rec_cl.cu: multicast exchange inside an 8/4/2-CTA cluster) against the counter-barrier
-    kernels (rec_tc.cu) on ragged lengths: same bf16 operand rounding and fp32 accumulation, so they agree far inside
-    the bf16-path tolerance; the debug stamps prove which kernel ran."""
+    """The cluster recurrent kernels of rec_cl.cu -- the quad formulation (64 units per CTA, transposed product, 16- and 32-row
+    tiles; S in {128, 256}) and the 8-CTA / 64-row kernels -- against the counter-barrier kernels (rec_tc.cu) on ragged
+    lengths, with (K <= 80) and without the fused input projection: same bf16 operand rounding and fp32 accumulation, so they
+    agree far inside the bf16-path tolerance; the debug stamps prove which kernel ran."""
     from ss_asr_b200 import _lib
     from ss_asr_b200.asr import pBLSTM
     lib = _lib.load()
@@ -473,7 +474,8 @@ def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
     res = {}
     stamps = torch.zeros(T, 12, dtype=torch.int64, device=DEV)
     try:
-        for on in (1, 0):
+        for name, rows, on in (('quad16', 16, 1), ('quad32', 32, 1), ('cl8', 0, 1), ('counter', 0, 0)):
+            lib.ssasr_rec_q_set_rows(rows)
             lib.ssasr_rec_cl_enable(on)
             stamps.zero_()
             lib.ssasr_rec_cl_set_debug(stamps.data_ptr())
@@ -486,15 +488,18 @@ def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
             lib.ssasr_rec_cl_set_debug(None)
             ran_cluster = bool((stamps != 0).any())
             assert ran_cluster == bool(on)
-            res[on] = (out.detach().clone(), x.grad.clone(), [p.grad.clone() for p in m.parameters()])
+            res[name] = (out.detach().clone(), x.grad.clone(), [p.grad.clone() for p in m.parameters()])
     finally:
+        lib.ssasr_rec_q_set_rows(16)
         lib.ssasr_rec_cl_enable(1)
         lib.ssasr_rec_cl_set_debug(None)
-    a, b = res[1], res[0]
-    assert float((a[0] - b[0]).abs().max()) < 2e-3
-    assert float(a[1].norm()) > 0 and float((a[1] - b[1]).norm()) <= 5e-3 * float(b[1].norm())
-    for ga, gb in zip(a[2], b[2]):
-        assert float((ga - gb).norm()) <= 5e-3 * float(gb.norm()) + 1e-6
+    b = res['counter']
+    for name in ('quad16', 'quad32', 'cl8'):
+        a = res[name]
+        assert float((a[0] - b[0]).abs().max()) < 2e-3, name
+        assert float(a[1].norm()) > 0 and float((a[1] - b[1]).norm()) <= 5e-3 * float(b[1].norm()), name
+        for ga, gb in zip(a[2], b[2]):
+            assert float((ga - gb).norm()) <= 5e-3 * float(gb.norm()) + 1e-6, name
 
 
 def test_host_batch_pipeline_and_async_attention_maps(golden_dir):
@@ -586,10 +591,12 @@ def test_deferred_weight_gradients_match():
             for _ in range(2):
                 opt.zero_grad(set_to_none=True)
                 _, logits, _ = m(x.to(DEV), 7, teacher=y.to(DEV), state_len=lens)
+                n0 = Fk._OVERLAP['deferred_total']
                 asr_loss(logits, y.to(DEV)).backward()
                 if on:
-                    assert len(Fk._OVERLAP['pending']) == 5          # the Speller's + one deferred batch per encoder layer
-                Fk.join_deferred()
+                    assert Fk._OVERLAP['deferred_total'] - n0 == 5   # the Speller's + one deferred batch per encoder layer
+                # joined when the autograd engine finished the backward pass: any reader of .grad is ordered after the side stream
+                assert len(Fk._OVERLAP['pending']) == 0
                 grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
                 opt.step_clipped(5.0)
             torch.cuda.synchronize()
