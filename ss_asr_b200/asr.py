@@ -24,6 +24,16 @@ def _lens_list(state_len):
     return [int(s) for s in state_len]
 
 
+def _i32_dev(vals, device):
+    """Python ints -> int32 device tensor WITHOUT blocking the host.  `torch.tensor(list, device='cuda')` copies from pageable
+    memory: the host then waits until the stream has drained, once per layer, and the GPU idles while the next layer is being
+    enqueued (measured: 1.25 ms per call, 5 ms of an 10 ms C4 step).  Staged in pinned memory (torch's caching host allocator
+    keeps the block alive until the copy has run) and copied asynchronously on the current stream instead."""
+    h = torch.empty(len(vals), dtype=torch.int32, pin_memory=True)
+    h.numpy()[:] = vals
+    return h.to(device, non_blocking=True)
+
+
 def _blstm_params(lstm):
     return (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
             lstm.weight_ih_l0_reverse, lstm.weight_hh_l0_reverse, lstm.bias_ih_l0_reverse, lstm.bias_hh_l0_reverse)
@@ -69,7 +79,7 @@ class pBLSTM(nn.Module):
             raise RuntimeError('pBLSTM: length %d exceeds the padded time dimension %d' % (t_max, T))
         t_h = t_max + (t_max & 1)
         x = _fit_time(input_x, t_h)
-        lens_dev = torch.tensor(run_lens, dtype=torch.int32, device=input_x.device)
+        lens_dev = _i32_dev(run_lens, input_x.device)
         if self.bf16_input is not None and x is input_x:
             Fk.hint_bf16_input(self.bf16_input)       # the previous layer's bf16 output (tensor-core path): no conversion pass
         self.bf16_input = None
@@ -204,7 +214,7 @@ class Attention(nn.Module):
         if self.comp_listener_feature is None:
             B, Tp = listener_feature.shape[0], listener_feature.shape[1]
             lens = _lens_list(state_len)
-            self._lens_dev = torch.tensor(lens, dtype=torch.int32, device=listener_feature.device)
+            self._lens_dev = _i32_dev(lens, listener_feature.device)
             self.state_mask = torch.arange(Tp, device=listener_feature.device)[None, :] >= self._lens_dev[:, None]
             self.comp_listener_feature = Fk.psi_memory(listener_feature, self.psi.weight, self.psi.bias)
         return Fk.attn_step(decoder_state, listener_feature, self.comp_listener_feature, self._lens_dev, self.phi.weight)
@@ -241,7 +251,7 @@ class ASR(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _spell(self, enc, enc_len, tok_in, modes, precision='fp32', lm=None, need_logits=True, stop_every=0, stop_token=1):
-        lens_dev = torch.tensor(enc_len, dtype=torch.int32, device=enc.device)
+        lens_dev = _i32_dev(enc_len, enc.device)
         params = self.attention.params() + self.decoder.params() + (self.embed.weight, self.char_trans.weight,
                                                                     self.char_trans.bias)
         self.sample_seed += 1
