@@ -18,7 +18,7 @@ extern "C" {
 const char* ssasr_last_error(void);
 /* Bumped whenever a signature or an argument struct of this header changes; the ctypes binding (ss_asr_b200/_lib.py) refuses
  * to bind a library whose version differs from the one it was written for (a stale .so would silently mis-read structs). */
-#define SSASR_ABI_VERSION 2
+#define SSASR_ABI_VERSION 3
 int ssasr_abi_version(void);
 
 /* ---- log-mel filterbank: preprocess.py:187-208 log_fbank(y, sample_rate) (librosa 0.6.3 melspectrogram) ---- */
@@ -137,8 +137,16 @@ typedef struct {
                                        utterance has emitted `stop_token` (asr.py:161-162) and stops early if so */
   int* stop_scratch;                /* device int */
   int* steps_run;                   /* HOST int out or NULL: decoding steps executed */
+  /* bf16 mode, optional: workspace of ssasr_speller_cl_ws_bytes() bytes.  When given (and the dimensions are covered) the
+     teacher-forced runs of the loop execute in the cluster-persistent step kernel (csrc/spell_cl.cu): attention query, energies,
+     masked softmax, context and the layer-1 LSTMCell of asr.py:79-103 for a whole run of steps in ONE launch, decoder state and
+     query weights resident on chip.  Keep it alive until the backward pass has run. */
+  void* cl_ws;
+  long long cl_ws_bytes;
 } ssasr_speller_fwd_args;
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
+/* bytes of `cl_ws` for these dimensions; 0 = not covered by the cluster-persistent kernels (S_d = 256, mlp = 128, T' <= 64) */
+long long ssasr_speller_cl_ws_bytes(int B, int Tp, int E, int Sd, int M, int C, int U);
 
 typedef struct {
   int B, Tp, E, Sd, M, C, U;
@@ -220,6 +228,7 @@ void ssasr_rec_tc_set_debug(long long* dev_buf /*[n_seq][12] clock64 stamps of C
 void ssasr_rec_cl_set_debug(long long* dev_buf /*[n_seq][12], cluster recurrent kernels (rec_cl.cu)*/);
 int ssasr_rec_cl_capacity(int S, int backward); /* co-resident (direction, tile) clusters of the cluster recurrence; 0 = unavailable */
 void ssasr_rec_cl_enable(int on);              /* 0: counter-barrier recurrent kernels everywhere (A/B comparison) */
+void ssasr_spell_cl_set_debug(long long* dev_buf /*[steps][8], cluster decoder-step kernels (spell_cl.cu)*/);
 void ssasr_rec_q_set_rows(int rows);           /* batch rows per tile of the quad-cluster recurrence: 32 / 16; 0 = 8-CTA kernels */
 
 #ifdef __cplusplus

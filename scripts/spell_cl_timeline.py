@@ -1,0 +1,32 @@
+"""clock64 stamps of CTA 0 of the cluster decoder-step kernel (spell_cl.cu), averaged over the steps of one teacher-forced run:
+0 h tile landed (MMA thread), 1 query accumulator ready (epilogue), 2 alpha image written (exchange thread), 3 all alpha rows
+landed (MMA thread), 4 gate accumulator ready (epilogue), 5 h image written (exchange thread)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ss_asr_b200 import functional as Fk, _lib
+from ss_asr_b200.asr import ASR
+dev = 'cuda'
+torch.manual_seed(1)
+m = ASR(50, 256, 256, 128, 80, 0.9).to(dev).train()
+B, Tp, U = 256, 64, 41
+g = torch.Generator().manual_seed(1)
+enc = (0.3 * torch.randn(B, Tp, 512, generator=g)).to(dev)
+lens = sorted([int(v) for v in torch.randint(48, 65, (B,), generator=g)], reverse=True)
+tok = torch.randint(3, 50, (B, U), generator=g).to(torch.int32).to(dev)
+lib = _lib.load()
+Fk.set_cluster_speller(True)
+for _ in range(2):
+    m._spell(enc, lens, tok.clone(), [0] * U, 'bf16')
+dbg = torch.zeros(U, 8, dtype=torch.int64, device=dev)
+lib.ssasr_spell_cl_set_debug(dbg.data_ptr())
+with torch.no_grad():
+    pass
+m._spell(enc.clone().requires_grad_(True), lens, tok.clone(), [0] * U, 'bf16')
+torch.cuda.synchronize()
+lib.ssasr_spell_cl_set_debug(None)
+d = dbg.cpu()
+names = ['h landed', 'q ready', 'alpha img', 'alpha landed', 'gates ready', 'h img']
+print('step period (h landed -> h landed): %.0f cycles' % float((d[2:, 0] - d[1:-1, 0]).double().mean()))
+for i in range(1, 6):
+    print('%-14s +%.0f cycles after h landed' % (names[i], float((d[1:-1, i] - d[1:-1, 0]).double().mean())))
+print('h img -> next h landed: %.0f' % float((d[2:, 0] - d[1:-1, 5]).double().mean()))

@@ -21,7 +21,7 @@ class SpellerFwdArgs(C.Structure):
                 [(n, C.c_void_p) for n in ('lm_emb', 'lm_w1i', 'lm_w1h', 'lm_b1i', 'lm_b1h', 'lm_w2i', 'lm_w2h', 'lm_b2i',
                                            'lm_b2h', 'lm_wo', 'lm_bo', 'lm_h1', 'lm_h2', 'x3_ws')] +
                 [('skip_final_logits', C.c_int), ('dual_stream', C.c_int), ('stop_token', C.c_int), ('stop_check_every', C.c_int),
-                 ('stop_scratch', C.c_void_p), ('steps_run', C.c_void_p)])
+                 ('stop_scratch', C.c_void_p), ('steps_run', C.c_void_p), ('cl_ws', C.c_void_p), ('cl_ws_bytes', C.c_longlong)])
 
 
 class SpellerBwdArgs(C.Structure):
@@ -66,6 +66,7 @@ SIGNATURES = {
                                   _I, _LL, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     'ssasr_speller_fwd_f32': (_I, [C.POINTER(SpellerFwdArgs), _P]),
     'ssasr_speller_bwd_f32': (_I, [C.POINTER(SpellerBwdArgs), _P]),
+    'ssasr_speller_cl_ws_bytes': (_LL, [_I, _I, _I, _I, _I, _I, _I]),
     'ssasr_attn_step_fwd': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_attn_step_bwd': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_lstmcell_fwd': (_I, [_I, _I, _P, _P, _P, _P, _P]),
@@ -88,6 +89,7 @@ SIGNATURES = {
     'ssasr_rec_cl_capacity': (_I, [_I, _I]),
     'ssasr_rec_cl_enable': (None, [_I]),
     'ssasr_rec_q_set_rows': (None, [_I]),
+    'ssasr_spell_cl_set_debug': (None, [_P]),
 }
 
 

@@ -68,7 +68,7 @@ int sm_count();
 
 // Launch accounting / optional per-family CUDA-event timing (bench.py reads it through ssasr_profile_*).
 enum Family { F_GEMM_F32 = 0, F_REC_FWD, F_REC_BWD, F_ATTN_FWD, F_ATTN_BWD, F_POINTWISE, F_CE, F_FBANK, F_PACK,
-              F_GEMM_TC, F_REC_TC_FWD, F_REC_TC_BWD, F_OPTIM, F_COUNT };
+              F_GEMM_TC, F_REC_TC_FWD, F_REC_TC_BWD, F_OPTIM, F_SPELL_FWD, F_SPELL_BWD, F_COUNT };
 struct ProfScope {
   int fam; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
   ProfScope(int family, cudaStream_t stream);
@@ -122,5 +122,35 @@ int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
 int rec_cl_fused_kp_max();
 int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
                int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias);
+
+
+// cluster-persistent decoder-step kernels (spell_cl.cu): steps [t0, t1) of the attend-and-spell loop (attention + layer-1 cell)
+// in ONE launch.  Strides (`*_ldb` per utterance, `*_ldt` per step) are in elements.
+struct SpellClFwdArgs {
+  int B, U, Tp, t0, t1;
+  const void* w1cat_bf; int X1, K1;       // [4Sd, X1] bf16 (rows = unit*4 + gate); the recurrent block starts at column K1
+  const void* phi_bf;                     // [M, Sd] bf16
+  const void* P_bf;                       // [B*Tp, 4Sd] bf16: W_ctx enc
+  const void* psi_bf;                     // [B*Tp, M] bf16: tanh(psi(enc))
+  const float* gemb;                      // [C, 4Sd]: W_emb emb + b
+  const int* tok; long long tok_ld;       // [B, U] input token of every step
+  const int* enc_lens;
+  float* act1; long long act1_ldb, act1_ldt;     // out: gate activations (i, f, g, o per unit)
+  float* c1; long long c1_ldb, c1_ldt;           // out (and in at t0 - 1)
+  float* h1; long long h1_ldb, h1_ldt;           // out (and in at t0 - 1)
+  void* h1b; long long h1b_ldb, h1b_ldt;         // out, optional: bf16 copy of h1
+  float* q; long long q_ldb, q_ldt;              // out [.., M]
+  float* alpha; long long al_ldb, al_ldt;        // out [.., Tp]
+  // plain recurrence mode (xpre != NULL; the layer-2 cell chain): gates = W_hh h(t-1) + xpre[b, t]; the recurrent block of
+  // `w1cat_bf` (row pitch X1, starting at column K1) is then W_hh of that cell; the attention arguments are unused
+  const float* xpre; long long xpre_ldb, xpre_ldt;
+  float* h2nd; long long h2nd_ldb, h2nd_ldt; int h2nd_toff;   // optional second copy of h(t), written at step t + h2nd_toff (< U)
+};
+int spell_cl_supported(int B, int Tp, int E, int Sd, int M);
+int spell_cl_fwd(cudaStream_t st, const SpellClFwdArgs& a);
+// xin1[b, t, :] = [emb(tok[b, t]) ; sum_j alpha[b, t, j] enc[b, j, :] ; h1[b, t - 1, :]] for all steps (the operand of the
+// weight-gradient products; the loop kernels never materialise the context)
+int spell_fill_xin1(cudaStream_t st, int B, int U, int Tp, int E, int Sd, const float* alpha, const float* enc, const int* lens,
+                    const float* emb_w, const int* tok, const float* h1, long long h1_ldb, long long h1_ldt, float* xin1);
 
 }  // namespace ssasr

@@ -36,7 +36,7 @@ using namespace ssasr;
 extern "C" {
 
 static const char* kFamilyNames[F_COUNT] = {"gemm_f32", "rec_fwd_f32", "rec_bwd_f32", "attn_fwd", "attn_bwd", "pointwise",
-                                            "ce_loss", "fbank", "pack", "gemm_tc", "rec_fwd_tc", "rec_bwd_tc", "optim"};
+                                            "ce_loss", "fbank", "pack", "gemm_tc", "rec_fwd_tc", "rec_bwd_tc", "optim", "spell_fwd", "spell_bwd"};
 
 int ssasr_abi_version(void) { return SSASR_ABI_VERSION; }
 int ssasr_num_families(void) { return F_COUNT; }

@@ -36,6 +36,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "cl_common.cuh"
 
 namespace ssasr {
 
@@ -72,6 +73,7 @@ struct RecClParams {
   int S, n_seq, n_batch;
   long long rs_seq, rs_batch;
   long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0)
+  long long gld, hld;        // quad kernels: row pitch of the gate buffers (n_dir * 4S) and of the h / c / dh buffers (n_dir * S)
 };
 
 #define CL_STAMP(idx)                                                                                            \
@@ -79,104 +81,7 @@ struct RecClParams {
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 12 + (idx)] = clock64(); \
   } while (0)
 
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float tanh_apx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigmoid_apx(float x) { return fmaf(tanh_apx(0.5f * x), 0.5f, 0.5f); }
-
-// time-bounded mbarrier wait (a protocol bug must trap, not hang the GPU): ~2 s at 2 GHz
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-__device__ __forceinline__ void mbar_wait_cluster_t(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-// arrive on the mbarrier at the same CTA-relative offset in cluster CTA `rank`
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
-}
-// Same, relaxed: for "I have finished READING" notifications.  The reads in question have completed before the arriving thread
-// observed their completion barrier, and the arrive is control-dependent on that observation, so no release fence is needed
-// -- and a cluster-scope release costs 1-3 k cycles here (it drains every outstanding global access of the thread).
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
-  uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
-}
-// image (shared) -> ring slot (global), then wait until the bulk store has completed
-__device__ __forceinline__ void bulk_store_wait(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-// ring slot (global) -> the same CTA-relative smem offset in every CTA of `mask`; completes its bytes on the mbarrier at
-// the same offset in each of them
-__device__ __forceinline__ void bulk_load_mc(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-      : "memory");
-}
-// swizzled shared-memory tile -> global tensor (rows outside the tensor are clipped); joins the thread's bulk group
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* ssrc, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(ssrc)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// K-major operand k-block of 16 bf16 (32-byte rows, 32-byte swizzle), 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t umma_desc_k32(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(256 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61;            // layout type SWIZZLE_32B
-  return d;
-}
-// K-major operand k-block of 32 bf16 (64-byte rows, 64-byte swizzle), 8-row groups 512 B apart
-__device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;            // layout type SWIZZLE_64B
-  return d;
-}
+using namespace clx;
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -929,11 +834,11 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         dhv[j] = 0.f; cv[j] = 0.f; cpv[j] = 0.f;
         if (valid) {
-          a[j] = __ldcs(reinterpret_cast<const float4*>(p.xp + row * 8 * S + gcol));
-          dhv[j] = __ldcs(p.dhout + row * 2 * S + hcol);
-          cv[j] = __ldg(p.cbuf + row * 2 * S + hcol);
+          a[j] = __ldcs(reinterpret_cast<const float4*>(p.xp + row * p.gld + gcol));
+          dhv[j] = __ldcs(p.dhout + row * p.hld + hcol);
+          cv[j] = __ldg(p.cbuf + row * p.hld + hcol);
         }
-        if (pv) cpv[j] = __ldg(p.cbuf + ((size_t)tp * p.rs_seq + rowb[j]) * 2 * S + hcol);
+        if (pv) cpv[j] = __ldg(p.cbuf + ((size_t)tp * p.rs_seq + rowb[j]) * p.hld + hcol);
       }
       if (s > 0) mbar_wait_t(img_free, (s - 1) & 1);     // the previous image has been read out: checked off the dependent chain
       float dhm[CPT];                           // recurrent part of dh for this thread's cells
@@ -1191,7 +1096,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         gn[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t_ < len[m]) gn[m] = __ldcs(reinterpret_cast<const float4*>(p.xp + ((size_t)t_ * p.rs_seq + rowb[m]) * 8 * S + gcol));
+        if (t_ < len[m]) gn[m] = __ldcs(reinterpret_cast<const float4*>(p.xp + ((size_t)t_ * p.rs_seq + rowb[m]) * p.gld + gcol));
       }
     };
     if (!XF) fetch_g(0);
@@ -1260,9 +1165,9 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       for (int m = 0; m < CPT; ++m) {
         if (inr[m]) {
           const size_t row = (size_t)t * p.rs_seq + rowb[m];
-          __stcs(reinterpret_cast<float4*>(p.xp + row * 8 * S + gcol), g[m]);
-          p.hout[row * 2 * S + hcol] = hv[m];
-          p.cbuf[row * 2 * S + hcol] = cv[m];
+          __stcs(reinterpret_cast<float4*>(p.xp + row * p.gld + gcol), g[m]);
+          p.hout[row * p.hld + hcol] = hv[m];
+          p.cbuf[row * p.hld + hcol] = cv[m];
         }
       }
       if (threadIdx.x == 64) CL_STAMP(7);
@@ -1426,19 +1331,22 @@ static size_t fwdq_smem(int S, int R, bool xf) {
 }
 
 template <int R, bool XF>
-static int rec_q_fwd_launch(cudaStream_t st, RecClParams& p, const void* whh_bf, void* hb, const void* x_bf, int Kp, const void* wih_bf) {
+static int rec_q_fwd_launch(cudaStream_t st, RecClParams& p, const void* whh_bf, void* hb, const void* x_bf, int Kp, const void* wih_bf,
+                            int ndir = 2) {
   const int S = p.S;
+  p.gld = (long long)ndir * 4 * S;
+  p.hld = (long long)ndir * S;
   static bool attr_set = false;
   if (!attr_set) {
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_q_fwd_kernel<R, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwdq_smem(256, R, XF)));
     attr_set = true;
   }
   CUtensorMap tmW, tmX, tmWx, tmH;
-  int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 256);
+  int rc = make_tmap_bf16(&tmW, whh_bf, ndir * 4 * S, S, S, 256);
   if (rc) return rc;
   const bool si = p.rs_seq < p.rs_batch;
-  rc = si ? make_tmap_bf16_3d_ex(&tmH, hb, 2 * S, p.n_seq, p.rs_seq * 2 * S, p.n_batch, p.rs_batch * 2 * S, 64, 1, R, 128)
-          : make_tmap_bf16_3d_ex(&tmH, hb, 2 * S, p.n_batch, p.rs_batch * 2 * S, p.n_seq, p.rs_seq * 2 * S, 64, R, 1, 128);
+  rc = si ? make_tmap_bf16_3d_ex(&tmH, hb, ndir * S, p.n_seq, p.rs_seq * ndir * S, p.n_batch, p.rs_batch * ndir * S, 64, 1, R, 128)
+          : make_tmap_bf16_3d_ex(&tmH, hb, ndir * S, p.n_batch, p.rs_batch * ndir * S, p.n_seq, p.rs_seq * ndir * S, 64, R, 1, 128);
   if (rc) return rc;
   tmX = tmW; tmWx = tmW;
   if (XF) {
@@ -1448,7 +1356,7 @@ static int rec_q_fwd_launch(cudaStream_t st, RecClParams& p, const void* whh_bf,
     rc = make_tmap_bf16_3d_ex(&tmWx, wih_bf, Kp, 8 * S, Kp, 1, (long long)8 * S * Kp, 16, 256, 1, 32);
     if (rc) return rc;
   }
-  dim3 grid(S / Q_UNITS, 2, (p.n_batch + R - 1) / R);
+  dim3 grid(S / Q_UNITS, ndir, (p.n_batch + R - 1) / R);
   ProfScope ps(F_REC_TC_FWD, st);
   return cluster_launch_t(Q_THREADS, rec_q_fwd_kernel<R, XF>, grid, S / Q_UNITS, fwdq_smem(S, R, XF), st, tmW, tmX, tmWx, tmH, p);
 }
@@ -1500,20 +1408,23 @@ int rec_cl_fused_kp_max() { return 16 * FW_MAXKX; }
 static size_t bwdq_smem(int S, int R) { return (size_t)8 * R * S + (size_t)512 * S + (6 + Q_MAXNC) * 8 + 16 + 1024; }
 
 template <int R>
-static int rec_q_bwd_launch(cudaStream_t st, RecClParams& p, const void* whhT_bf, void* dgb) {
+static int rec_q_bwd_launch(cudaStream_t st, RecClParams& p, const void* whhT_bf, void* dgb, int ndir = 2) {
   const int S = p.S;
+  p.gld = (long long)ndir * 4 * S;
+  p.hld = (long long)ndir * S;
   static bool attr_set = false;
   if (!attr_set) {
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_q_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwdq_smem(256, R)));
     attr_set = true;
   }
   CUtensorMap tmW, tmG;
-  int rc = make_tmap_bf16(&tmW, whhT_bf, 2 * S, 4 * S, 4 * S, Q_UNITS);
+  int rc = make_tmap_bf16(&tmW, whhT_bf, ndir * S, 4 * S, 4 * S, Q_UNITS);
   if (rc) return rc;
-  rc = p.rs_seq < p.rs_batch ? make_tmap_bf16_3d_ex(&tmG, dgb, 8 * S, p.n_seq, p.rs_seq * 8 * S, p.n_batch, p.rs_batch * 8 * S, 64, 1, R, 128)
-                             : make_tmap_bf16_3d_ex(&tmG, dgb, 8 * S, p.n_batch, p.rs_batch * 8 * S, p.n_seq, p.rs_seq * 8 * S, 64, R, 1, 128);
+  const long long gl = (long long)ndir * 4 * S;
+  rc = p.rs_seq < p.rs_batch ? make_tmap_bf16_3d_ex(&tmG, dgb, gl, p.n_seq, p.rs_seq * gl, p.n_batch, p.rs_batch * gl, 64, 1, R, 128)
+                             : make_tmap_bf16_3d_ex(&tmG, dgb, gl, p.n_batch, p.rs_batch * gl, p.n_seq, p.rs_seq * gl, 64, R, 1, 128);
   if (rc) return rc;
-  dim3 grid(S / Q_UNITS, 2, (p.n_batch + R - 1) / R);
+  dim3 grid(S / Q_UNITS, ndir, (p.n_batch + R - 1) / R);
   ProfScope ps(F_REC_TC_BWD, st);
   return cluster_launch_t(Q_THREADS, rec_q_bwd_kernel<R>, grid, S / Q_UNITS, bwdq_smem(S, R), st, tmW, tmG, p);
 }

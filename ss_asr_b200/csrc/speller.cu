@@ -982,7 +982,35 @@ typedef struct {
   int stop_token, stop_check_every;
   int* stop_scratch;      // device int
   int* steps_run;         // HOST int out (may be NULL): decoding steps actually executed
+  // bf16 mode, optional: workspace of ssasr_speller_cl_ws_bytes() bytes.  When given (and the dimensions are covered) the
+  // teacher-forced runs of the loop execute in the cluster-persistent step kernel of spell_cl.cu: one launch per run of steps
+  // instead of two launches per step.  The caller keeps it alive until the backward pass has run (it holds P and psi~ in bf16).
+  void* cl_ws;
+  long long cl_ws_bytes;
 } ssasr_speller_fwd_args;
+
+// workspace layout of the cluster path
+struct SpellClWs {
+  size_t p_bf, psi_bf, phi_bf, gemb, p_f32, xp2, total;
+};
+static SpellClWs spell_cl_ws_layout(int B, int Tp, int Sd, int M, int C, int U) {
+  SpellClWs w;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = 0;
+  w.p_bf = o; o += up((size_t)B * Tp * 4 * Sd * 2);
+  w.psi_bf = o; o += up((size_t)B * Tp * M * 2);
+  w.phi_bf = o; o += up((size_t)M * Sd * 2);
+  w.gemb = o; o += up((size_t)C * 4 * Sd * 4);
+  w.p_f32 = o; o += up((size_t)B * Tp * 4 * Sd * 4);
+  w.xp2 = o; o += up((size_t)B * U * 4 * Sd * 4);      // layer-2 input projection, [U][B][4Sd]
+  w.total = o;
+  return w;
+}
+// bytes of `cl_ws` for these dimensions; 0 when the cluster path does not cover them (the per-step kernels run instead)
+long long ssasr_speller_cl_ws_bytes(int B, int Tp, int E, int Sd, int M, int C, int U) {
+  if (!spell_cl_supported(B, Tp, E, Sd, M)) return 0;
+  return (long long)spell_cl_ws_layout(B, Tp, Sd, M, C, U).total;
+}
 
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -1027,13 +1055,16 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     if (rc) return rc;
   }
   // bf16 mode: layer-2 chain on a second stream (one layer-2 input block per step in ws_bf)
-  SideStream* side = (tc && a->dual_stream && U > 1) ? side_stream(2 * U + 2) : nullptr;
+  // cluster-persistent step kernel for the teacher-forced runs (spell_cl.cu); needs one layer-2 input block per step in ws_bf
+  const bool cl = tc && a->dual_stream && a->cl_ws && a->enc_bf && E % 8 == 0 && spell_cl_supported(B, Tp, E, Sd, M) &&
+                  a->cl_ws_bytes >= (long long)spell_cl_ws_layout(B, Tp, Sd, M, C, U).total;
+  SideStream* side = (!cl && tc && a->dual_stream && U > 1) ? side_stream(2 * U + 2) : nullptr;
   const bool dual = side != nullptr;
   cudaStream_t sb = dual ? side->s : st;
-  auto x2b_at = [&](int t) { return (dual && x2b) ? x2b + (size_t)t * B * X2 : x2b; };
+  auto x2b_at = [&](int t) { return ((dual || cl) && x2b) ? x2b + (size_t)t * B * X2 : x2b; };
   // the layer-1 product sits on the dependent chain and is bound by what one SM can pull through its L2 port (128 x 32 tiles:
   // 320 KB per CTA, 64 CTAs): split-K over twice the SMs, partials added into the pre-zeroed gate buffer
-  const int chain_splits = tc ? step_gemm_splits() : 1;
+  const int chain_splits = (tc && !cl) ? step_gemm_splits() : 1;
   if (chain_splits > 1) SSASR_CHECK_CUDA(cudaMemsetAsync(a->act1, 0, sizeof(float) * (size_t)B * U * 4 * Sd, st));
   auto gate_gemm = [&](cudaStream_t st, const float* x, int ldx, int K, const float* w, const void* w_bf, const float* bias, float* out,
                        const __nv_bfloat16* xb, int splits = 1) -> int {
@@ -1087,10 +1118,10 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
                                                  (long long)U * X2, x2b_at(t), X2, Sd, x3 ? xh : nullptr, x3 ? xl : nullptr, X2);
   };
   // layer 2 of step t on stream s2 (+ token selection for step t+1, which consumes h2(t))
-  auto layer2 = [&](int t, cudaStream_t s2) -> int {
+  auto layer2_cell = [&](int t, cudaStream_t s2) -> int {
     int r = gate_gemm(s2, a->xin2 + (size_t)t * X2, U * X2, X2, a->w2cat, a->w2cat_bf, a->b2, a->act2 + (size_t)t * 4 * Sd, x2b_at(t));
     if (r) return r;
-    const bool fwd_h2 = dual && t + 1 < U;      // two streams: h2(t) goes straight into the next step's layer-2 input row
+    const bool fwd_h2 = (dual || cl) && t + 1 < U;   // per-step input blocks: h2(t) goes straight into the next step's layer-2 input row
     {
       ProfScope ps(F_POINTWISE, s2);
       cell_fwd_kernel<<<cell_blocks, 256, 0, s2>>>(B, Sd, a->act2 + (size_t)t * 4 * Sd, (long long)U * 4 * Sd,
@@ -1100,6 +1131,11 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
                                                    fwd_h2 ? a->xin2 + (size_t)(t + 1) * X2 + Sd : nullptr, (long long)U * X2,
                                                    fwd_h2 ? x2b_at(t + 1) + Sd : nullptr, X2);
     }
+    return 0;
+  };
+  // selection of the token that follows step t (consumes h2(t)) on stream s2; no-op for teacher-forced steps
+  auto select_token = [&](int t, cudaStream_t s2) -> int {
+    int r = 0;
     const int mode = mode_of(t);
     if (mode == 0 || t + 1 >= U) return 0;
     if (lp_fused) {          // projection + selection in one launch (mode 3: projection only, the LM kernel selects)
@@ -1131,7 +1167,77 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     if (dual) SSASR_CHECK_CUDA(cudaEventRecord(side->ev[U + t], s2));   // the next step's token is ready
     return 0;
   };
+  auto layer2 = [&](int t, cudaStream_t s2) -> int {
+    int r = layer2_cell(t, s2);
+    if (r) return r;
+    return select_token(t, s2);
+  };
   int steps_done = U;
+  if (cl) {
+    // ---- cluster-persistent path: P = enc W_ctx^T, psi~ and phi in bf16, the embedding table, then one launch per run ----
+    const SpellClWs wl = spell_cl_ws_layout(B, Tp, Sd, M, C, U);
+    uint8_t* ws = (uint8_t*)a->cl_ws;
+    __nv_bfloat16* p_bf = (__nv_bfloat16*)(ws + wl.p_bf);
+    __nv_bfloat16* psi_bf = (__nv_bfloat16*)(ws + wl.psi_bf);
+    __nv_bfloat16* phi_bf = (__nv_bfloat16*)(ws + wl.phi_bf);
+    float* gemb = (float*)(ws + wl.gemb);
+    float* p_f32 = (float*)(ws + wl.p_f32);
+    rc = cvt_bf16(st, a->psi, M, psi_bf, M, (long long)B * Tp, M);
+    if (rc) return rc;
+    rc = cvt_bf16(st, a->phi_w, Sd, phi_bf, Sd, M, Sd);
+    if (rc) return rc;
+    // G_emb[c, :] = W_emb emb[c] + b1 (fp32): the embedding part of the layer-1 gates is a table row per token
+    rc = gemm_f32(st, C, 4 * Sd, Sd, a->emb_w, Sd, 1, a->w1cat, X1, 1, gemb, 4 * Sd, a->b1, 0, 0);
+    if (rc) return rc;
+    // P[b, j, :] = W_ctx enc[b, j, :] on tensor cores (enc_bf was filled for the psi~ product above)
+    rc = gemm_bf16_tc(st, B * Tp, 4 * Sd, E, a->enc_bf, E, 0, a->w1cat_bf, X1, Sd, p_f32, 4 * Sd, nullptr, 0);
+    if (rc) return rc;
+    rc = cvt_bf16(st, p_f32, 4 * Sd, p_bf, 4 * Sd, (long long)B * Tp, 4 * Sd);
+    if (rc) return rc;
+    // h2(-1) = 0: the recurrent half of the first layer-2 input block
+    SSASR_CHECK_CUDA(cudaMemset2DAsync(a->xin2 + Sd, sizeof(float) * (size_t)U * X2, 0, sizeof(float) * Sd, B, st));
+    SpellClFwdArgs f = {};
+    f.B = B; f.U = U; f.Tp = Tp;
+    f.w1cat_bf = a->w1cat_bf; f.X1 = X1; f.K1 = K1; f.phi_bf = phi_bf; f.P_bf = p_bf; f.psi_bf = psi_bf; f.gemb = gemb;
+    f.tok = a->tok_in; f.tok_ld = U; f.enc_lens = a->enc_lens;
+    f.act1 = a->act1; f.act1_ldb = (long long)U * 4 * Sd; f.act1_ldt = 4 * Sd;
+    f.c1 = a->c1; f.c1_ldb = (long long)U * Sd; f.c1_ldt = Sd;
+    f.h1 = a->xin2; f.h1_ldb = (long long)U * X2; f.h1_ldt = X2;
+    f.h1b = x2b; f.h1b_ldb = X2; f.h1b_ldt = (long long)B * X2;
+    f.q = a->q; f.q_ldb = (long long)U * M; f.q_ldt = M;
+    f.alpha = a->alpha; f.al_ldb = (long long)U * Tp; f.al_ldt = Tp;
+    float* xp2 = (float*)(ws + wl.xp2);
+    SpellClFwdArgs g = {};                   // the layer-2 chain: plain recurrence mode of the same kernel
+    g.B = B; g.U = U; g.Tp = Tp;
+    g.w1cat_bf = a->w2cat_bf; g.X1 = X2; g.K1 = Sd;
+    g.xpre = xp2; g.xpre_ldb = 4 * Sd; g.xpre_ldt = (long long)B * 4 * Sd;
+    g.act1 = a->act2; g.act1_ldb = (long long)U * 4 * Sd; g.act1_ldt = 4 * Sd;
+    g.c1 = a->c2; g.c1_ldb = (long long)U * Sd; g.c1_ldt = Sd;
+    g.h1 = a->h2all; g.h1_ldb = (long long)U * Sd; g.h1_ldt = Sd;
+    g.h2nd = a->xin2 + Sd; g.h2nd_ldb = (long long)U * X2; g.h2nd_ldt = X2; g.h2nd_toff = 1;
+    for (int t0 = 0; t0 < U;) {
+      int t1 = t0 + 1;                       // a run ends behind the first step whose successor token is selected on the device
+      while (t1 < U && mode_of(t1 - 1) == 0) ++t1;
+      f.t0 = t0; f.t1 = t1;
+      rc = spell_cl_fwd(st, f);
+      if (rc) return rc;
+      // layer 2 of the run: input projection of all its steps in one product (rows [t0 B, t1 B) of the time-major blocks), then
+      // the cell chain in the cluster recurrence, then the token that follows the run if it is selected on the device
+      rc = gemm_bf16_tc(st, (t1 - t0) * B, 4 * Sd, Sd, x2b + (size_t)t0 * B * X2, X2, 0, a->w2cat_bf, X2, 0,
+                        xp2 + (size_t)t0 * B * 4 * Sd, 4 * Sd, a->b2, 0);
+      if (rc) return rc;
+      g.t0 = t0; g.t1 = t1;
+      rc = spell_cl_fwd(st, g);
+      if (rc) return rc;
+      rc = select_token(t1 - 1, st);
+      if (rc) return rc;
+      t0 = t1;
+    }
+    // the operand rows of the weight-gradient products (the loop never materialises the context)
+    rc = spell_fill_xin1(st, B, U, Tp, E, Sd, a->alpha, a->enc, a->enc_lens, a->emb_w, a->tok_in, a->xin2, (long long)U * X2, X2, a->xin1);
+    if (rc) return rc;
+  } else
+  {
   const int stop_every = (!dual && a->stop_check_every > 0 && a->stop_scratch && a->skip_final_logits && a->step_mode &&
                           a->step_mode[0] != 0 && a->step_mode[0] != 2) ? a->stop_check_every : 0;
   if (!dual) {
@@ -1182,6 +1288,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     }
   }
   if (dual) SSASR_HANDOVER(side->ev[2 * U], sb, st);
+  }
   if (a->steps_run) *a->steps_run = steps_done;
   if (a->skip_final_logits) {        // greedy decoding only consumes the tokens
     SSASR_LAUNCH_CHECK();

@@ -13,6 +13,13 @@ _TC_RECURRENCE = os.environ.get('SSASR_TC_RECURRENCE', '1') != '0'   # bf16 path
 # bf16 path: the Speller's layer-2 cell chain (forward and backward) on a second stream inside the C call -- it never feeds
 # the attention query (asr.py:84), so it leaves the dependent chain of a decoding step
 _DUAL_STREAM_SPELLER = os.environ.get('SSASR_DUAL_STREAM_SPELLER', '1') != '0'
+# bf16 path: teacher-forced runs of the attend-and-spell loop in ONE cluster-persistent kernel launch per run (spell_cl.cu)
+_CLUSTER_SPELLER = os.environ.get('SSASR_SPELL_CL', '1') != '0'
+
+
+def set_cluster_speller(on):
+    global _CLUSTER_SPELLER
+    _CLUSTER_SPELLER = bool(on)
 
 
 def set_dual_stream_speller(on):
@@ -323,6 +330,11 @@ class _Spell(torch.autograd.Function):
         x3ws = None
         if precision == 'tf32x3' and not torch.is_grad_enabled() and X1 % 4 == 0 and X2 % 4 == 0:
             x3ws = torch.empty(2 * B * max(X1, X2) + 8 * Sd * (X1 + X2), device=dev)
+        cl_ws = None
+        if bf16 and _DUAL_STREAM_SPELLER and _CLUSTER_SPELLER:
+            nb = int(lib.ssasr_speller_cl_ws_bytes(B, Tp, E, Sd, M, Cc, U))
+            if nb > 0:       # cluster-persistent decoder-step kernel (spell_cl.cu): P = enc W_ctx^T, psi~, phi in bf16, G_emb
+                cl_ws = torch.empty(nb, dtype=torch.uint8, device=dev)
         lmk = {}
         if lm is not None:      # (dict of transposed fp32 tensors, weight): greedy decode with the character LM
             lmt, lm_weight = lm
@@ -342,13 +354,15 @@ class _Spell(torch.autograd.Function):
                                 skip_final_logits=skip_final, dual_stream=int(bf16 and _DUAL_STREAM_SPELLER),
                                 stop_token=stop_token, stop_check_every=stop_every if skip_final else 0,
                                 stop_scratch=ptr(stop_scr),
-                                steps_run=C.addressof(steps_run), **lmk)
+                                steps_run=C.addressof(steps_run), cl_ws=ptr(cl_ws), cl_ws_bytes=cl_ws.numel() if cl_ws is not None else 0,
+                                **lmk)
         ctx.dual = bool(bf16 and _DUAL_STREAM_SPELLER)
         check(lib.ssasr_speller_fwd_f32(C.byref(a), st), 'ssasr_speller_fwd_f32')
         LAST_SPELL['steps_run'] = int(steps_run.value)
         ctx.save_for_backward(enc, enc_lens_dev, tok_in, phi_w, psi_w, w1cat, w2cat, wc, psi, xin1, xin2, act1, act2, c1,
                               c2, h2all, q, alpha)
         ctx.dims = (B, Tp, E, Sd, M, Cc, U)
+        ctx.cl_ws = cl_ws
         ctx.mark_non_differentiable(alpha, tok_in)
         return logits, alpha, tok_in
 
