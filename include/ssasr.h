@@ -147,6 +147,7 @@ typedef struct {
 int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream);
 /* bytes of `cl_ws` for these dimensions; 0 = not covered by the cluster-persistent kernels (S_d = 256, mlp = 128, T' <= 64) */
 long long ssasr_speller_cl_ws_bytes(int B, int Tp, int E, int Sd, int M, int C, int U);
+long long ssasr_speller_cl_bwd_ws_bytes(int B, int Tp, int E, int Sd, int M, int U);
 
 typedef struct {
   int B, Tp, E, Sd, M, C, U;
@@ -165,6 +166,13 @@ typedef struct {
   int dual_stream;                   /* bf16 mode: dxin2 holds U*B*X2 floats; layer-2 chain on an internal second stream */
   void* wgrad_stream;                /* optional, with dual_stream: the products only the optimiser consumes (all weight / bias /
                                         embedding gradients) go to this stream, ordered after the loop and NOT joined into `stream` */
+  /* cluster-persistent path (csrc/spell_cl.cu), all optional: the forward call's `cl_ws`, the forward bf16 weights
+     [4Sd, X1] / [4Sd, X2] and a scratch of ssasr_speller_cl_bwd_ws_bytes() bytes: both cell chains and the attention backward
+     (asr.py:79-103 under loss.backward(), trainer.py:437) then run as ONE launch each over all steps */
+  const void* cl_ws;
+  const void *w1cat_bf, *w2cat_bf;
+  void* cl_ws_bwd;
+  long long cl_ws_bwd_bytes;
 } ssasr_speller_bwd_args;
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream);
 

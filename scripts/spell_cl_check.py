@@ -8,6 +8,7 @@ dev = 'cuda'
 torch.manual_seed(1)
 m = ASR(50, 256, 256, 128, 80, 0.9).to(dev).train()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+CLB = (sys.argv[2] != '0') if len(sys.argv) > 2 else True
 Tp, U = 64, 41
 g = torch.Generator().manual_seed(1)
 enc0 = (0.3 * torch.randn(B, Tp, 512, generator=g)).to(dev)
@@ -18,8 +19,8 @@ tok = torch.randint(3, 50, (B, U), generator=g).to(torch.int32).to(dev)
 gl = torch.randn(B, U, 50, generator=g).to(dev) * 1e-2
 
 
-def run(cl, modes):
-    Fk.set_cluster_speller(cl)
+def run(cl, modes, clb=None):
+    Fk.set_cluster_speller(cl, clb)
     enc = enc0.clone().requires_grad_(True)
     m.zero_grad(set_to_none=True)
     logits, att, toks = m._spell(enc, lens, tok.clone(), modes, 'bf16')
@@ -30,7 +31,7 @@ def run(cl, modes):
 
 
 ref = run(False, [0] * U)
-new = run(True, [0] * U)
+new = run(True, [0] * U, CLB)
 print('logits max|d| %.3e (max|ref| %.3e)' % (float((ref[0] - new[0]).abs().max()), float(ref[0].abs().max())))
 print('att    max|d| %.3e (max ref %.3e)' % (float((ref[1] - new[1]).abs().max()), float(ref[1].max())))
 print('denc   rel-L2 %.3e' % (float((ref[2] - new[2]).norm() / ref[2].norm())))
@@ -40,7 +41,7 @@ for k in ref[3]:
 print('nan check', bool(torch.isnan(new[0]).any()), bool(torch.isnan(new[1]).any()))
 
 for cl in (False, True, False, True):
-    Fk.set_cluster_speller(cl)
+    Fk.set_cluster_speller(cl, cl and CLB)
     res = []
     for it in range(6):
         random.seed(it)
@@ -61,7 +62,7 @@ for cl in (False, True, False, True):
 from ss_asr_b200 import _lib
 lib = _lib.load()
 for cl in (False, True):
-    Fk.set_cluster_speller(cl)
+    Fk.set_cluster_speller(cl, cl and CLB)
     random.seed(3)
     modes = [0 if random.random() <= 0.9 else 2 for _ in range(U)]
     lib.ssasr_profile_enable(1)

@@ -33,7 +33,9 @@ class SpellerBwdArgs(C.Structure):
                                            'd_emb_w', 'd_wc', 'd_bc', 'denc',
                                            'dh2all', 'dxin1', 'dxin2', 'dc1s', 'dc2s', 'dh1att', 'dpsi', 'dqpre', 'de_all',
                                            'w1catT_bf', 'w2catT_bf', 'wsA', 'wsB')] +
-                [('BUp', C.c_longlong), ('BTp', C.c_longlong), ('dual_stream', C.c_int), ('wgrad_stream', C.c_void_p)])
+                [('BUp', C.c_longlong), ('BTp', C.c_longlong), ('dual_stream', C.c_int), ('wgrad_stream', C.c_void_p),
+                 ('cl_ws', C.c_void_p), ('w1cat_bf', C.c_void_p), ('w2cat_bf', C.c_void_p), ('cl_ws_bwd', C.c_void_p),
+                 ('cl_ws_bwd_bytes', C.c_longlong)])
 
 
 class OptimTensor(C.Structure):
@@ -67,6 +69,7 @@ SIGNATURES = {
     'ssasr_speller_fwd_f32': (_I, [C.POINTER(SpellerFwdArgs), _P]),
     'ssasr_speller_bwd_f32': (_I, [C.POINTER(SpellerBwdArgs), _P]),
     'ssasr_speller_cl_ws_bytes': (_LL, [_I, _I, _I, _I, _I, _I, _I]),
+    'ssasr_speller_cl_bwd_ws_bytes': (_LL, [_I, _I, _I, _I, _I, _I]),
     'ssasr_attn_step_fwd': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_attn_step_bwd': (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'ssasr_lstmcell_fwd': (_I, [_I, _I, _P, _P, _P, _P, _P]),

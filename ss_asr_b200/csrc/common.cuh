@@ -146,6 +146,24 @@ struct SpellClFwdArgs {
   const float* xpre; long long xpre_ldb, xpre_ldt;
   float* h2nd; long long h2nd_ldb, h2nd_ldt; int h2nd_toff;   // optional second copy of h(t), written at step t + h2nd_toff (< U)
 };
+// backward chain of the same loop over ALL steps (t1 - 1 down to 0).  P_bf == NULL: plain recurrence (the layer-2 chain).
+struct SpellClBwdArgs {
+  int B, U, Tp, t0, t1;
+  const void* wcat_bf; int X, Kcol;       // [4Sd, X] bf16 forward weights; the recurrent block starts at column Kcol
+  const void* phi_bf;                     // [M, Sd] bf16
+  const void* P_bf;                       // [B*Tp, 4Sd] bf16
+  const void* psi_bf;                     // [B*Tp, M] bf16
+  const int* enc_lens;
+  float* act; long long act_ldb, act_ldt;           // in: gate activations; out: gate gradients (in place)
+  const float* c; long long c_ldb, c_ldt;
+  const float* dh_in; long long dh_ldb, dh_ldt;     // gradient arriving on h(t) from outside the chain
+  void* dgb; long long dgb_ldb, dgb_ldt;            // out: bf16 copy of the gate gradients
+  const float* alpha; long long al_ldb, al_ldt;
+  const float* q; long long q_ldb, q_ldt;
+  float* de; long long de_ldb, de_ldt;              // out: dL/d(energy) [.., Tp]
+  float* dqpre; long long dq_ldb, dq_ldt;           // out: dL/d(query pre-activation) [.., M]
+};
+int spell_cl_bwd(cudaStream_t st, const SpellClBwdArgs& a);
 int spell_cl_supported(int B, int Tp, int E, int Sd, int M);
 int spell_cl_fwd(cudaStream_t st, const SpellClFwdArgs& a);
 // xin1[b, t, :] = [emb(tok[b, t]) ; sum_j alpha[b, t, j] enc[b, j, :] ; h1[b, t - 1, :]] for all steps (the operand of the

@@ -480,6 +480,444 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   cluster_sync_all();                      // no CTA leaves while a peer could still address its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward.  Same decomposition: CTA r owns gate rows [128 r, 128 r + 128) (its 32 hidden units) for every utterance of the
+// cluster and the attention of utterance slots r, r + 8, ...  Per step t (descending):
+//   1. cells      dh1(t) = dh_in[b, t] (from the layer above) + the 8 partial sums pushed by the previous step; cell backward
+//                 -> the CTA's slice of dG(t) [utterances x 128 gate rows]: fp32 in place of the saved activations, bf16 to the
+//                 weight-gradient operand and to a shared-memory operand tile
+//   2. dalpha     (ATT) partial dalpha[u, j] = sum over the CTA's 128 gate rows of dG[u, .] P[u, j, .] on the CUDA cores, the P
+//                 tiles streaming through the TMA ring exactly as in the forward kernel; partials pushed to the utterance's owner
+//   3. attention  (ATT, owner) softmax backward, dq = (sum_j de_j psi~_j)(1 - q^2); dq rows all-gathered (multicast)
+//   4. dh         K-split: acc_d [256 units x utterances] = W_hh slice^T (the resident forward image read MN-major) x dG slice^T
+//                 (+ phi slice^T x dq slice^T, 16 of the 128 query rows per CTA); bf16 partials pushed to the units' owners
+// Exchanges are bulk store -> (multi)cast read-back with a one-CTA mask for the targeted pushes.
+// ------------------------------------------------------------------------------------------------
+constexpr int SB_NSTAGE = 4;
+constexpr int BOFF_W = 0;                             // W_hh slice, forward layout (4 unit blocks of [128 gate rows x 128 B])
+constexpr int BOFF_PHI = BOFF_W + 65536;              // phi rows [16 r, 16 r + 16): 4 unit blocks of [16 rows x 128 B]
+constexpr int BOFF_DG = BOFF_PHI + 8192;              // dG slice operand [NT utterances x 128 gate rows] bf16, 2 k-blocks
+constexpr int BOFF_DQ = BOFF_DG + 8192;               // all-gathered dq tile [NT x 128 m] bf16, 2 k-blocks
+constexpr int BOFF_DHOUT = BOFF_DQ + 8192;            // outgoing dh partials [8 destinations][NT][32 units] bf16
+constexpr int BOFF_DHIN = BOFF_DHOUT + 16384;         // incoming dh partials [2 buffers][8 sources][NT][32 units] bf16
+constexpr int BOFF_DAOUT = BOFF_DHIN + 32768;         // outgoing dalpha partials [8 owners][4][64] fp32
+constexpr int BOFF_DAIN = BOFF_DAOUT + 8192;          // incoming dalpha partials [8 sources][4][64] fp32
+constexpr int BOFF_RING = BOFF_DAIN + 8192;           // P / psi~ ring
+constexpr int BOFF_DQIMG = BOFF_RING + SB_NSTAGE * SP_STAGE;   // outgoing dq rows [4][2 k-blocks][128 B]
+constexpr int BOFF_DES = BOFF_DQIMG + 1024;           // [4][64] fp32 de of the own utterances
+constexpr int BOFF_RED = BOFF_DES + 1024;
+constexpr int BOFF_BARS = BOFF_RED + 64;
+constexpr int SB_SMEM = BOFF_BARS + 32 * 8 + 1024;
+static_assert(BOFF_RING % 1024 == 0 && SB_SMEM <= 232448, "shared-memory map (backward)");
+constexpr int SB_SLOT = 32768;                        // exchange slot: dh partials 16 KB | dalpha partials 8 KB | dq rows 1 KB
+
+struct SpellClBwdP {
+  int B, U, Tp, t0, t1, per;
+  const int* enc_lens;
+  float* act; long long act_ldb, act_ldt;             // in: gate activations, out: gate gradients (in place)
+  const float* c; long long c_ldb, c_ldt;
+  const float* dh_in; long long dh_ldb, dh_ldt;       // gradient arriving on h(t) from outside the chain
+  __nv_bfloat16* dgb; long long dgb_ldb, dgb_ldt;     // out: bf16 copy of the gate gradients [.., 4Sd]
+  const float* alpha; long long al_ldb, al_ldt;
+  const float* q; long long q_ldb, q_ldt;
+  float* de; long long de_ldb, de_ldt;                // out [.., Tp]
+  float* dqpre; long long dq_ldb, dq_ldt;             // out [.., M]
+  uint8_t* ring;
+};
+
+template <int NT, bool ATT>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmPhiS,
+                    const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmPsi, int w_col0, SpellClBwdP p) {
+  constexpr int DHB = NT * 64;              // one (source, destination) block of dh partials: [NT utterances][32 units] bf16
+  constexpr int NJ = NT / 16;               // cells per thread
+  constexpr int KBLK = NT * 128;            // one k-block of the dG / dq operand tiles
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wsm = smem + BOFF_W;
+  uint8_t* Phis = smem + BOFF_PHI;
+  uint8_t* dGsm = smem + BOFF_DG;
+  uint8_t* dQsm = smem + BOFF_DQ;
+  uint8_t* dhout = smem + BOFF_DHOUT;
+  uint8_t* dhin = smem + BOFF_DHIN;
+  float* daout = reinterpret_cast<float*>(smem + BOFF_DAOUT);
+  float* dain = reinterpret_cast<float*>(smem + BOFF_DAIN);
+  uint8_t* Ring = smem + BOFF_RING;
+  uint8_t* dqimg = smem + BOFF_DQIMG;
+  float* des = reinterpret_cast<float*>(smem + BOFF_DES);
+  float* red = reinterpret_cast<float*>(smem + BOFF_RED);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BOFF_BARS);
+  uint64_t* w_full = bars;
+  uint64_t* dh_full = bars + 1;             // [2]
+  uint64_t* da_full = bars + 3;
+  uint64_t* dq_full = bars + 4;
+  uint64_t* d_done = bars + 5;
+  uint64_t* dg_ready = bars + 6;
+  uint64_t* da_ready = bars + 7;
+  uint64_t* dq_ready = bars + 8;
+  uint64_t* dh_ready = bars + 9;
+  uint64_t* r_full = bars + 10;             // [SB_NSTAGE]
+  uint64_t* r_empty = bars + 10 + SB_NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * SB_NSTAGE);
+
+  const int r = blockIdx.x;
+  const int b0 = blockIdx.z * p.per;
+  const int NU = min(p.per, p.B - b0);
+  const int n_own = (ATT && NU > r) ? (NU - r + SP_NC - 1) / SP_NC : 0;
+  const int step_stages = ATT ? NU + n_own : 0;       // ring stages per step: all P tiles, then the own psi~ tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_steps = p.t1 - p.t0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmW);
+    if (ATT) {
+      tma_prefetch_desc(&tmPhiS);
+      tma_prefetch_desc(&tmP);
+      tma_prefetch_desc(&tmPsi);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(dh_full, 1);
+    mbar_init(dh_full + 1, 1);
+    mbar_init(da_full, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(d_done, 1);
+    mbar_init(dg_ready, SP_EPW);
+    mbar_init(da_ready, SP_EPW);
+    mbar_init(dq_ready, 1);
+    mbar_init(dh_ready, SP_EPW);
+    for (int i = 0; i < SB_NSTAGE; ++i) {
+      mbar_init(r_full + i, 1);
+      mbar_init(r_empty + i, SP_EPW);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  // operand tiles start out as zeros: rows of unused utterance slots are never written
+  for (int i = threadIdx.x; i < (8192 + 8192 + 16384) / 16; i += SP_THREADS) reinterpret_cast<uint4*>(dGsm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 8192 / 16; i += SP_THREADS) reinterpret_cast<uint4*>(daout)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, 65536 + (ATT ? 8192 : 0));
+    for (int kb = 0; kb < 4; ++kb) {
+      tma_load_2d(&tmW, w_full, Wsm + kb * 16384, w_col0 + kb * 64, r * 128);
+      if (ATT) tma_load_2d(&tmPhiS, w_full, Phis + kb * 2048, kb * 64, r * 16);
+    }
+    mbar_expect_tx(dh_full, SP_NC * DHB);
+    mbar_expect_tx(dh_full + 1, SP_NC * DHB);
+    if (ATT) {
+      mbar_expect_tx(da_full, SP_NC * n_own * 256);
+      mbar_expect_tx(dq_full, NU * 256);
+    }
+  }
+  cluster_sync_all();
+
+  if (warp == 0) {
+    // ---------------- exchange thread ----------------
+    if (elect_one()) {
+      const uint16_t cmask = (uint16_t)((1u << SP_NC) - 1u);
+      const size_t n_cta = (size_t)gridDim.x * gridDim.z;
+      const size_t cta = (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+      for (int s = 0; s < n_steps; ++s) {
+        uint8_t* slot = p.ring + ((size_t)(s % SP_RING) * n_cta + cta) * SB_SLOT;
+        if (ATT) {
+          mbar_wait_t(da_ready, s & 1);
+          bulk_store_wait(slot + 16384, daout, 8192);
+          for (int o = 0; o < SP_NC; ++o) {            // partial dalpha rows of owner o's utterances -> its row block r
+            const int no = (NU > o) ? (NU - o + SP_NC - 1) / SP_NC : 0;
+            if (no > 0) bulk_load_mc(dain + r * 256, slot + 16384 + o * 1024, no * 256, da_full, (uint16_t)(1u << o));
+          }
+          if (n_own > 0 && s + 1 < n_steps) {      // (the dq of the last step feeds nothing inside the chain)
+            mbar_wait_t(dq_ready, s & 1);
+            bulk_store_wait(slot + 24576, dqimg, n_own * 256);
+            for (int o = 0; o < n_own; ++o)
+              for (int kb = 0; kb < 2; ++kb)
+                bulk_load_mc(dQsm + kb * KBLK + (r + 8 * o) * 128, slot + 24576 + (o * 2 + kb) * 128, 128, dq_full, cmask);
+          }
+        }
+        if (s + 1 < n_steps) {
+          mbar_wait_t(dh_ready, s & 1);
+          bulk_store_wait(slot, dhout, SP_NC * DHB);
+          for (int d = 0; d < SP_NC; ++d)
+            bulk_load_mc(dhin + ((s & 1) * SP_NC + r) * DHB, slot + d * DHB, DHB, dh_full + (s & 1), (uint16_t)(1u << d));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA thread ----------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 1, 0);        // A MN-major (units contiguous), B K-major
+      mbar_wait_t(w_full, 0);
+      for (int s = 0; s + 1 < n_steps; ++s) {                            // the last step has no predecessor to feed
+        mbar_wait_t(dg_ready, s & 1);
+        tc_fence_after();
+        const uint32_t w0 = smem_u32(Wsm), g0 = smem_u32(dGsm);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma_bf16_ss(tmem + h * NT, umma_desc_mn128(w0 + h * 32768, 16384) + (uint64_t)(kk * 128),
+                        umma_desc_k128(g0 + (kk >> 2) * KBLK) + (uint64_t)((kk & 3) * 2), idesc, kk != 0);
+        if (ATT) {
+          mbar_wait_t(dq_full, s & 1);
+          if (s + 2 < n_steps) mbar_expect_tx(dq_full, NU * 256);
+          tc_fence_after();
+          const uint32_t f0 = smem_u32(Phis), q0 = smem_u32(dQsm);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            mma_bf16_ss(tmem + h * NT, umma_desc_mn128(f0 + h * 4096, 2048), umma_desc_k128(q0 + (r >> 2) * KBLK) + (uint64_t)((r & 3) * 2),
+                        idesc, 1u);
+        }
+        mma_commit(d_done);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ---------------- ring producer ----------------
+    if (ATT && elect_one()) {
+      int pos = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        for (int i = 0; i < step_stages; ++i, ++pos) {
+          const int stg = pos % SB_NSTAGE;
+          mbar_wait_t(r_empty + stg, ((pos / SB_NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(r_full + stg, SP_STAGE);
+          uint8_t* dst = Ring + stg * SP_STAGE;
+          if (i < NU) {                     // P of utterance i, this CTA's 128 gate rows: two k-blocks of [64 frames x 64 rows]
+            const int row = (b0 + i) * p.Tp;
+            tma_load_2d(&tmP, r_full + stg, dst, r * 128, row);
+            tma_load_2d(&tmP, r_full + stg, dst + 8192, r * 128 + 64, row);
+          } else {                          // psi~ of own utterance i - NU
+            const int row = (b0 + r + 8 * (i - NU)) * p.Tp;
+            tma_load_2d(&tmPsi, r_full + stg, dst, 0, row);
+            tma_load_2d(&tmPsi, r_full + stg, dst + 8192, 64, row);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---------------- compute warps ----------------
+    const int cw = warp - 4;                       // 0 .. 15
+    const int ct = threadIdx.x - 128;              // 0 .. 511
+    const int unit = 32 * r + lane;                // cells: warp cw owns utterance slots cw (+ 16), lane = unit of the CTA
+    bool cvalid[NJ];
+    float dcreg[NJ];
+    float4 act_n[NJ];
+    float c_n[NJ], cp_n[NJ], dh_n[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      cvalid[j] = cw + 16 * j < NU;
+      dcreg[j] = 0.f;
+    }
+    // everything of a step that does not depend on the chain is fetched one whole step ahead
+    auto fetch = [&](int t_) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (cvalid[j]) {
+          const size_t bq = (size_t)(b0 + cw + 16 * j);
+          act_n[j] = __ldcs(reinterpret_cast<const float4*>(p.act + bq * p.act_ldb + (size_t)t_ * p.act_ldt + (size_t)unit * 4));
+          c_n[j] = __ldg(p.c + bq * p.c_ldb + (size_t)t_ * p.c_ldt + unit);
+          cp_n[j] = t_ > 0 ? __ldg(p.c + bq * p.c_ldb + (size_t)(t_ - 1) * p.c_ldt + unit) : 0.f;
+          dh_n[j] = __ldcs(p.dh_in + bq * p.dh_ldb + (size_t)t_ * p.dh_ldt + unit);
+        }
+      }
+    };
+    fetch(p.t1 - 1);
+    // attention role (warps 4-11): thread = (own utterance ua, frame ja)
+    const int ua = (ct >> 6) & 3, ja = ct & 63;
+    const bool att_warp = ATT && cw < 8;
+    const bool att_on = att_warp && ua < n_own;
+    const int sa_slot = r + 8 * ua;
+    const int ba = b0 + sa_slot;
+    int len_a = 0;
+    if (att_on) len_a = min(p.enc_lens[ba], p.Tp);
+    // dalpha role: thread = (frame 4 cw + (lane >> 3), 16-column part lane & 7 of the CTA's 128 gate rows)
+    const int jf = 4 * cw + (lane >> 3), part = lane & 7;
+    int rpos = 0;                                  // ring position of the compute warps
+
+    for (int s = 0; s < n_steps; ++s) {
+      const int t = p.t1 - 1 - s;
+      float4 a[NJ];
+      float cv[NJ], cpv[NJ], dh[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { a[j] = act_n[j]; cv[j] = c_n[j]; cpv[j] = cp_n[j]; dh[j] = dh_n[j]; }
+      if (s + 1 < n_steps) fetch(t - 1);
+      float al_a = 0.f, q_a0 = 0.f, q_a1 = 0.f;
+      if (att_on) {
+        al_a = ja < p.Tp ? __ldg(p.alpha + (size_t)ba * p.al_ldb + (size_t)t * p.al_ldt + ja) : 0.f;
+        const float2 qq = *reinterpret_cast<const float2*>(p.q + (size_t)ba * p.q_ldb + (size_t)t * p.q_ldt + 2 * ja);
+        q_a0 = qq.x; q_a1 = qq.y;
+      }
+      // ---- 1. dh1(t): the partial sums of the 8 CTAs of the previous step, then the cell backward ----
+      if (s > 0) {
+        mbar_wait_t(dh_full + ((s - 1) & 1), ((s - 1) >> 1) & 1);
+        if (ct == 0 && s + 2 < n_steps) mbar_expect_tx(dh_full + ((s - 1) & 1), SP_NC * DHB);   // re-armed for the pushes of step s + 1
+        const uint8_t* base = dhin + ((s - 1) & 1) * SP_NC * DHB;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int src = 0; src < SP_NC; ++src)
+            acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + src * DHB + (cw + 16 * j) * 64 + lane * 2));
+          dh[j] += acc;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int slot = cw + 16 * j;
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cvalid[j]) {
+          const float tc = tanh_apx(cv[j]);
+          const float dc = dh[j] * a[j].w * (1.f - tc * tc) + dcreg[j];
+          dg.w = dh[j] * tc * a[j].w * (1.f - a[j].w);
+          dg.x = dc * a[j].z * a[j].x * (1.f - a[j].x);
+          dg.z = dc * a[j].x * (1.f - a[j].z * a[j].z);
+          dg.y = dc * cpv[j] * a[j].y * (1.f - a[j].y);
+          dcreg[j] = dc * a[j].y;
+        }
+        const __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&b01);
+        pk.y = *reinterpret_cast<const uint32_t*>(&b23);
+        // operand tile: row = utterance slot, gate column 4 lane + g of the CTA's 128: k-block lane / 16, 16-byte chunk (lane % 16) / 2
+        *reinterpret_cast<uint2*>(dGsm + (lane >> 4) * KBLK + slot * 128 + ((((lane & 15) >> 1) ^ (slot & 7)) << 4) + (lane & 1) * 8) = pk;
+        if (cvalid[j]) {
+          const size_t bq = (size_t)(b0 + slot);
+          __stcs(reinterpret_cast<float4*>(p.act + bq * p.act_ldb + (size_t)t * p.act_ldt + (size_t)unit * 4), dg);
+          *reinterpret_cast<uint2*>(p.dgb + bq * p.dgb_ldb + (size_t)t * p.dgb_ldt + (size_t)unit * 4) = pk;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dg_ready);
+      if (ATT) {
+        // ---- 2. partial dalpha over the CTA's 128 gate rows, all utterances of the cluster ----
+        mbar_wait_t(dg_ready, s & 1);               // every warp's rows of the operand tile are in place
+        for (int u = 0; u < NU; ++u, ++rpos) {
+          const int stg = rpos % SB_NSTAGE;
+          mbar_wait_t(r_full + stg, (rpos / SB_NSTAGE) & 1);
+          // P row jf, columns 16 part .. 16 part + 15: k-block part / 4, chunks 2 (part % 4) and + 1 (order swapped in the upper
+          // k-block so that the 8 lanes of a quarter warp hit 8 different bank groups)
+          const uint8_t* prow = Ring + stg * SP_STAGE + (part >> 2) * 8192 + jf * 128;
+          const uint8_t* grow = dGsm + (part >> 2) * KBLK + u * 128;
+          const int c0 = 2 * (part & 3) + (part >> 2), c1 = c0 ^ 1;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(prow + ((c0 ^ (jf & 7)) << 4));
+          const uint4 w1 = *reinterpret_cast<const uint4*>(prow + ((c1 ^ (jf & 7)) << 4));
+          const uint4 g0 = *reinterpret_cast<const uint4*>(grow + ((c0 ^ (u & 7)) << 4));
+          const uint4 g1 = *reinterpret_cast<const uint4*>(grow + ((c1 ^ (u & 7)) << 4));
+          float d0 = 0.f, d1 = 0.f;
+          d0 = fmaf(bf_lo(w0.x), bf_lo(g0.x), d0); d1 = fmaf(bf_hi(w0.x), bf_hi(g0.x), d1);
+          d0 = fmaf(bf_lo(w0.y), bf_lo(g0.y), d0); d1 = fmaf(bf_hi(w0.y), bf_hi(g0.y), d1);
+          d0 = fmaf(bf_lo(w0.z), bf_lo(g0.z), d0); d1 = fmaf(bf_hi(w0.z), bf_hi(g0.z), d1);
+          d0 = fmaf(bf_lo(w0.w), bf_lo(g0.w), d0); d1 = fmaf(bf_hi(w0.w), bf_hi(g0.w), d1);
+          d0 = fmaf(bf_lo(w1.x), bf_lo(g1.x), d0); d1 = fmaf(bf_hi(w1.x), bf_hi(g1.x), d1);
+          d0 = fmaf(bf_lo(w1.y), bf_lo(g1.y), d0); d1 = fmaf(bf_hi(w1.y), bf_hi(g1.y), d1);
+          d0 = fmaf(bf_lo(w1.z), bf_lo(g1.z), d0); d1 = fmaf(bf_hi(w1.z), bf_hi(g1.z), d1);
+          d0 = fmaf(bf_lo(w1.w), bf_lo(g1.w), d0); d1 = fmaf(bf_hi(w1.w), bf_hi(g1.w), d1);
+          float d = d0 + d1;
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if (part == 0) daout[(u & 7) * 256 + (u >> 3) * 64 + jf] = d;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(r_empty + stg);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(da_ready);
+        // ---- 3. owner: softmax backward and dq of the own utterances ----
+        if (att_warp && n_own > 0) {
+          float de = 0.f;
+          mbar_wait_t(da_full, s & 1);
+          if (ct == 0 && s + 1 < n_steps) mbar_expect_tx(da_full, SP_NC * n_own * 256);
+          float da = 0.f;
+          if (att_on) {
+#pragma unroll
+            for (int src = 0; src < SP_NC; ++src) da += dain[src * 256 + ua * 64 + ja];
+          }
+          const float wd = warp_sum(al_a * da);
+          if (lane == 0) red[ct >> 5] = wd;
+          named_bar(1, 256);
+          if (att_on) {
+            const float dot = red[ua * 2] + red[ua * 2 + 1];
+            de = ja < len_a ? al_a * (da - dot) : 0.f;
+            if (ja < p.Tp) p.de[(size_t)ba * p.de_ldb + (size_t)t * p.de_ldt + ja] = de;
+            des[ua * 64 + ja] = de;
+          }
+          named_bar(1, 256);
+        }
+        // the psi~ stages are walked by every warp in ring order (only the owner warps read them)
+        for (int o = 0; o < n_own; ++o, ++rpos) {
+          const int stg = rpos % SB_NSTAGE;
+          mbar_wait_t(r_full + stg, (rpos / SB_NSTAGE) & 1);
+          if (att_on && o == ua) {
+            // dq_pre[m] for m = 2 ja, 2 ja + 1: column sums of de_j psi~[j, m] over the frames
+            const uint8_t* pt = Ring + stg * SP_STAGE + (ja >> 5) * 8192;      // k-block of m
+            const int mc = (2 * ja) & 63;                                        // column inside the k-block
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < 64; ++j) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(pt + j * 128 + (((mc >> 3) ^ (j & 7)) << 4) + (mc & 7) * 2);
+              const float dj = des[ua * 64 + j];
+              s0 = fmaf(dj, bf_lo(w), s0);
+              s1 = fmaf(dj, bf_hi(w), s1);
+            }
+            const float dq0 = s0 * (1.f - q_a0 * q_a0), dq1 = s1 * (1.f - q_a1 * q_a1);
+            *reinterpret_cast<float2*>(p.dqpre + (size_t)ba * p.dq_ldb + (size_t)t * p.dq_ldt + 2 * ja) = make_float2(dq0, dq1);
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(dq0, dq1);
+            *reinterpret_cast<__nv_bfloat162*>(dqimg + (ua * 2 + (ja >> 5)) * 128 + (((mc >> 3) ^ (sa_slot & 7)) << 4) + (mc & 7) * 2) = pk;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(r_empty + stg);
+        }
+        if (att_warp && n_own > 0) {
+          fence_proxy_async();
+          named_bar(1, 256);
+          if (ct == 0) mbar_arrive(dq_ready);
+        }
+      }
+      // ---- 4. partial dh of all 256 units (this CTA's gate rows / query rows contracted) -> bf16 -> the units' owners ----
+      if (s + 1 < n_steps) {
+        mbar_wait_t(d_done, s & 1);
+        tc_fence_after();
+        const int sp = warp & 3, cgrp = cw >> 2;   // TMEM sub-partition = 32 units = one destination per half; 8 (4) columns
+        constexpr int NCOL = NT / 4;
+        uint32_t v[2][NCOL];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t ta = tmem + ((uint32_t)(sp * 32) << 16) + (uint32_t)(h * NT + cgrp * NCOL);
+          if constexpr (NCOL == 8) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(v[h][0]), "=r"(v[h][1]), "=r"(v[h][2]), "=r"(v[h][3]), "=r"(v[h][4]), "=r"(v[h][5]), "=r"(v[h][6]), "=r"(v[h][7])
+                         : "r"(ta) : "memory");
+          } else {
+            tmem_ld4(ta, v[h]);
+          }
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int c = 0; c < NCOL; ++c)
+            *reinterpret_cast<__nv_bfloat16*>(dhout + (h * 4 + sp) * DHB + (cgrp * NCOL + c) * 64 + lane * 2) =
+                __float2bfloat16_rn(__uint_as_float(v[h][c]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dh_ready);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem);
+  cluster_sync_all();
+}
+
 // xin1 rows for the weight-gradient products: [emb(tok) ; context ; h1(t-1)].  One CTA per utterance: the attention maps of all
 // steps sit in shared memory (transposed, 16 steps per 64-byte line), a thread owns context columns and accumulates 16 steps at a
 // time over the utterance's valid frames.
@@ -537,7 +975,7 @@ uint8_t* sp_ring_for(cudaStream_t st) {
     if (g_sp_rings[i].st == st && g_sp_rings[i].dev == dev) return g_sp_rings[i].buf;
   if (g_sp_nrings == 16) return nullptr;
   uint8_t* b = nullptr;
-  if (cudaMalloc(&b, (size_t)SP_RING * 160 * SP_SLOT) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMalloc(&b, (size_t)SP_RING * 160 * SB_SLOT) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   g_sp_rings[g_sp_nrings++] = {st, dev, b};
   return b;
 }
@@ -546,15 +984,15 @@ long long* g_sp_dbg = nullptr;
 int g_sp_cap = -1;                         // co-resident clusters of the forward kernel (queried once)
 
 template <typename Kern>
-int sp_query(Kern kern) {
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SP_SMEM) != cudaSuccess) {
+int sp_query(Kern kern, int smem_bytes = SP_SMEM) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(SP_NC, 1, 1);
   cfg.blockDim = dim3(SP_THREADS);
-  cfg.dynamicSmemBytes = SP_SMEM;
+  cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = SP_NC;
@@ -573,6 +1011,10 @@ int sp_capacity() {
     g_sp_cap = a < b ? a : b;
     if (c < g_sp_cap) g_sp_cap = c;
     if (d < g_sp_cap) g_sp_cap = d;
+    const int e[4] = {sp_query(spell_cl_bwd_kernel<16, true>, SB_SMEM), sp_query(spell_cl_bwd_kernel<32, true>, SB_SMEM),
+                      sp_query(spell_cl_bwd_kernel<16, false>, SB_SMEM), sp_query(spell_cl_bwd_kernel<32, false>, SB_SMEM)};
+    for (int i = 0; i < 4; ++i)
+      if (e[i] < g_sp_cap) g_sp_cap = e[i];
   }
   return g_sp_cap;
 }
@@ -654,6 +1096,60 @@ int spell_cl_fwd(cudaStream_t st, const SpellClFwdArgs& a) {
   } else {
     if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<16, false>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
     else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<32, false>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
+  }
+  return 0;
+}
+
+int spell_cl_bwd(cudaStream_t st, const SpellClBwdArgs& a) {
+  SSASR_REQUIRE(a.t0 == 0 && a.t1 == a.U && a.U >= 1, "spell_cl_bwd: the backward chain runs over all %d steps", a.U);
+  SSASR_REQUIRE(sp_capacity() > 0, "spell_cl_bwd: the cluster kernel cannot be launched on this device");
+  int clusters, per;
+  sp_split(a.B, &clusters, &per);
+  SSASR_REQUIRE(per <= SP_MAXU, "spell_cl_bwd: %d utterances do not fit %d co-resident clusters", a.B, sp_capacity());
+  const bool att = a.P_bf != nullptr;
+  SpellClBwdP p = {};
+  p.B = a.B; p.U = a.U; p.Tp = a.Tp; p.t0 = a.t0; p.t1 = a.t1; p.per = per; p.enc_lens = a.enc_lens;
+  p.act = a.act; p.act_ldb = a.act_ldb; p.act_ldt = a.act_ldt;
+  p.c = a.c; p.c_ldb = a.c_ldb; p.c_ldt = a.c_ldt;
+  p.dh_in = a.dh_in; p.dh_ldb = a.dh_ldb; p.dh_ldt = a.dh_ldt;
+  p.dgb = (__nv_bfloat16*)a.dgb; p.dgb_ldb = a.dgb_ldb; p.dgb_ldt = a.dgb_ldt;
+  p.alpha = a.alpha; p.al_ldb = a.al_ldb; p.al_ldt = a.al_ldt;
+  p.q = a.q; p.q_ldb = a.q_ldb; p.q_ldt = a.q_ldt;
+  p.de = a.de; p.de_ldb = a.de_ldb; p.de_ldt = a.de_ldt;
+  p.dqpre = a.dqpre; p.dq_ldb = a.dq_ldb; p.dq_ldt = a.dq_ldt;
+  p.ring = sp_ring_for(st);
+  SSASR_REQUIRE(p.ring != nullptr, "spell_cl_bwd: cannot allocate the exchange ring");
+  CUtensorMap tmW, tmPhiS, tmP, tmPsi;
+  int rc = make_tmap_bf16(&tmW, a.wcat_bf, 4 * SP_SD, a.X, a.X, 128);
+  if (rc) return rc;
+  tmPhiS = tmW; tmP = tmW; tmPsi = tmW;
+  if (att) {
+    rc = make_tmap_bf16(&tmPhiS, a.phi_bf, SP_M, SP_SD, SP_SD, 16);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmP, a.P_bf, (long long)a.B * a.Tp, 4 * SP_SD, 4 * SP_SD, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmPsi, a.psi_bf, (long long)a.B * a.Tp, SP_M, SP_M, 64);
+    if (rc) return rc;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(SP_NC, 1, clusters);
+  cfg.blockDim = dim3(SP_THREADS);
+  cfg.dynamicSmemBytes = SB_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SP_NC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  ProfScope ps(F_SPELL_BWD, st);
+  if (att) {
+    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<16, true>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<32, true>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+  } else {
+    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<16, false>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<32, false>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
   }
   return 0;
 }

@@ -1327,7 +1327,32 @@ typedef struct {
   // gradients) is enqueued on this stream, ordered after the loop, and NOT joined into `stream`: the caller joins it before it
   // reads the gradients.  `stream` then carries just what the encoder's backward needs (denc).
   void* wgrad_stream;
+  // cluster-persistent path (csrc/spell_cl.cu), all optional: the forward call's `cl_ws` (P, psi~, phi in bf16), the forward
+  // bf16 weights [4Sd, X1] / [4Sd, X2] and a scratch of ssasr_speller_cl_bwd_ws_bytes() bytes.  When given (and the forward ran
+  // on that path) both cell chains and the attention backward run as ONE launch each over all steps.
+  const void* cl_ws;
+  const void *w1cat_bf, *w2cat_bf;
+  void* cl_ws_bwd;
+  long long cl_ws_bwd_bytes;
 } ssasr_speller_bwd_args;
+
+struct SpellClBwdWs {
+  size_t dgb1, dgb2, dh1, total;
+};
+static SpellClBwdWs spell_cl_bwd_ws_layout(int B, int Sd, int U) {
+  SpellClBwdWs w;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = 0;
+  w.dgb1 = o; o += up((size_t)B * U * 4 * Sd * 2);
+  w.dgb2 = o; o += up((size_t)B * U * 4 * Sd * 2);
+  w.dh1 = o; o += up((size_t)B * U * Sd * 4);
+  w.total = o;
+  return w;
+}
+long long ssasr_speller_cl_bwd_ws_bytes(int B, int Tp, int E, int Sd, int M, int U) {
+  if (!spell_cl_supported(B, Tp, E, Sd, M)) return 0;
+  return (long long)spell_cl_bwd_ws_layout(B, Sd, U).total;
+}
 
 int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -1367,7 +1392,9 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
   cudaStream_t sb = dual ? side->s : st;
   __nv_bfloat16* dgb2 = dual ? dgb + (size_t)B * 4 * Sd : dgb;
   auto dxin2_at = [&](int t) { return dual ? a->dxin2 + (size_t)t * B * X2 : a->dxin2; };
-  const int chain_splits = tc ? step_gemm_splits() : 1;        // see ssasr_speller_fwd_f32
+  const bool cl = tc && a->dual_stream && a->cl_ws && a->cl_ws_bwd && a->w1cat_bf && a->w2cat_bf && spell_cl_supported(B, Tp, E, Sd, M) &&
+                  a->cl_ws_bwd_bytes >= (long long)spell_cl_bwd_ws_layout(B, Sd, U).total;
+  const int chain_splits = (tc && !cl) ? step_gemm_splits() : 1;        // see ssasr_speller_fwd_f32
   if (chain_splits > 1) SSASR_CHECK_CUDA(cudaMemsetAsync(a->dxin1, 0, sizeof(float) * (size_t)B * U * X1, st));
   auto dgrad_gemm = [&](cudaStream_t st, const __nv_bfloat16* dgb, const float* dg, int N, const float* w, const void* wT_bf,
                         float* out, int ldo, int splits = 1) -> int {
@@ -1433,7 +1460,42 @@ int ssasr_speller_bwd_f32(const ssasr_speller_bwd_args* a, void* stream) {
     ProfScope ps(F_ATTN_BWD, st);
     attn_bwd_kernel<<<B, 256, attn_smem, st>>>(g);
   };
-  if (!dual) {
+  if (cl) {
+    // ---- cluster-persistent path: layer-2 chain, its input gradient in one product, layer-1 chain + attention backward ----
+    const SpellClWs wl = spell_cl_ws_layout(B, Tp, Sd, M, C, U);
+    const SpellClBwdWs bl = spell_cl_bwd_ws_layout(B, Sd, U);
+    const uint8_t* fws = (const uint8_t*)a->cl_ws;
+    uint8_t* bws = (uint8_t*)a->cl_ws_bwd;
+    __nv_bfloat16* dgb1 = (__nv_bfloat16*)(bws + bl.dgb1);
+    __nv_bfloat16* dgb2 = (__nv_bfloat16*)(bws + bl.dgb2);
+    float* dh1 = (float*)(bws + bl.dh1);
+    SpellClBwdArgs g = {};
+    g.B = B; g.U = U; g.Tp = Tp; g.t0 = 0; g.t1 = U; g.enc_lens = a->enc_lens;
+    g.wcat_bf = a->w2cat_bf; g.X = X2; g.Kcol = Sd;
+    g.act = a->act2; g.act_ldb = (long long)U * 4 * Sd; g.act_ldt = 4 * Sd;
+    g.c = a->c2; g.c_ldb = (long long)U * Sd; g.c_ldt = Sd;
+    g.dh_in = a->dh2all; g.dh_ldb = (long long)U * Sd; g.dh_ldt = Sd;
+    g.dgb = dgb2; g.dgb_ldb = (long long)U * 4 * Sd; g.dgb_ldt = 4 * Sd;
+    rc = spell_cl_bwd(st, g);
+    if (rc) return rc;
+    // dh1(t) from layer 2, all steps: dG2 W_ih2
+    rc = gemm_bf16_tc(st, B * U, Sd, 4 * Sd, dgb2, 4 * Sd, 0, a->w2catT_bf, 4 * Sd, 0, dh1, Sd, nullptr, 0);
+    if (rc) return rc;
+    g.wcat_bf = a->w1cat_bf; g.X = X1; g.Kcol = K1;
+    g.phi_bf = fws + wl.phi_bf; g.P_bf = fws + wl.p_bf; g.psi_bf = fws + wl.psi_bf;
+    g.act = a->act1; g.c = a->c1;
+    g.dh_in = dh1;
+    g.dgb = dgb1;
+    g.alpha = a->alpha; g.al_ldb = (long long)U * Tp; g.al_ldt = Tp;
+    g.q = a->q; g.q_ldb = (long long)U * M; g.q_ldt = M;
+    g.de = a->de_all; g.de_ldb = (long long)U * Tp; g.de_ldt = Tp;
+    g.dqpre = a->dqpre; g.dq_ldb = (long long)U * M; g.dq_ldt = M;
+    rc = spell_cl_bwd(st, g);
+    if (rc) return rc;
+    // gradient of the step inputs [emb ; ctx] of all steps: dG1 [W_emb | W_ctx] (the recurrent part stayed inside the kernel)
+    rc = gemm_bf16_tc(st, B * U, K1, 4 * Sd, dgb1, 4 * Sd, 0, a->w1catT_bf, 4 * Sd, 0, a->dxin1, X1, nullptr, 0);
+    if (rc) return rc;
+  } else if (!dual) {
     for (int t = U - 1; t >= 0; --t) {
       rc = layer2_bwd(t, st);
       if (rc) return rc;

@@ -17,9 +17,14 @@ _DUAL_STREAM_SPELLER = os.environ.get('SSASR_DUAL_STREAM_SPELLER', '1') != '0'
 _CLUSTER_SPELLER = os.environ.get('SSASR_SPELL_CL', '1') != '0'
 
 
-def set_cluster_speller(on):
-    global _CLUSTER_SPELLER
+_CLUSTER_SPELLER_BWD = os.environ.get('SSASR_SPELL_CL_BWD', '1') != '0'
+
+
+def set_cluster_speller(on, backward=None):
+    """on: forward (and, unless `backward` says otherwise, backward) of the decoder loop in the cluster-persistent kernels"""
+    global _CLUSTER_SPELLER, _CLUSTER_SPELLER_BWD
     _CLUSTER_SPELLER = bool(on)
+    _CLUSTER_SPELLER_BWD = bool(on if backward is None else backward)
 
 
 def set_dual_stream_speller(on):
@@ -363,6 +368,7 @@ class _Spell(torch.autograd.Function):
                               c2, h2all, q, alpha)
         ctx.dims = (B, Tp, E, Sd, M, Cc, U)
         ctx.cl_ws = cl_ws
+        ctx.w_bf = (w1b, w2b) if cl_ws is not None else None
         ctx.mark_non_differentiable(alpha, tok_in)
         return logits, alpha, tok_in
 
@@ -398,6 +404,14 @@ class _Spell(torch.autograd.Function):
         # BEFORE the call: whatever used that memory earlier is ordered before the side stream's first write.
         fresh = all(getattr(w, 'grad', None) is None for w in ctx.param_refs)
         side = side_stream(dev) if (ctx.dual and _OVERLAP['on'] and fresh) else None
+        cl_bws = None
+        clk = {}
+        if ctx.cl_ws is not None and _CLUSTER_SPELLER_BWD:
+            nb = int(lib.ssasr_speller_cl_bwd_ws_bytes(B, Tp, E, Sd, M, U))
+            if nb > 0:
+                cl_bws = torch.empty(nb, dtype=torch.uint8, device=dev)
+                clk = dict(cl_ws=ptr(ctx.cl_ws), w1cat_bf=ptr(ctx.w_bf[0]), w2cat_bf=ptr(ctx.w_bf[1]), cl_ws_bwd=ptr(cl_bws),
+                           cl_ws_bwd_bytes=nb)
         z = lambda *s: torch.zeros(*s, device=dev)
         g1 = [z(4 * Sd, K1), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
         g2 = [z(4 * Sd, Sd), z(4 * Sd, Sd), z(4 * Sd), z(4 * Sd)]
@@ -411,7 +425,7 @@ class _Spell(torch.autograd.Function):
                                 dh2all=ptr(scr[0]), dxin1=ptr(scr[1]), dxin2=ptr(scr[2]), dc1s=ptr(scr[3]),
                                 dc2s=ptr(scr[4]), dh1att=ptr(scr[5]), dpsi=ptr(scr[6]), dqpre=ptr(scr[7]), de_all=ptr(scr[8]),
                                 w1catT_bf=ptr(w1T), w2catT_bf=ptr(w2T), wsA=ptr(wsA), wsB=ptr(wsB), BUp=BUp, BTp=BTp,
-                                dual_stream=int(ctx.dual), wgrad_stream=side.cuda_stream if side else None)
+                                dual_stream=int(ctx.dual), wgrad_stream=side.cuda_stream if side else None, **clk)
         check(lib.ssasr_speller_bwd_f32(C.byref(a), st), 'ssasr_speller_bwd_f32')
         ust = side.cuda_stream if side else st
         check(lib.ssasr_unpack_lstmcell_grads(ptr(d_w1cat), ptr(d_b1), Sd, K1, *[ptr(t) for t in g1], ust), 'unpack1')
@@ -421,7 +435,8 @@ class _Spell(torch.autograd.Function):
             ev.record(side)
             # everything the side stream still reads or writes, EXCEPT the returned gradient buffers (AccumulateGrad only adopts
             # a buffer it holds the sole reference to; otherwise it clones it on the main stream, before it has been written)
-            _OVERLAP['pending'].append((ev, (ctx.saved_tensors, dlogits, scr, wsA, wsB, w1T, w2T, d_w1cat, d_b1, d_w2cat, d_b2)))
+            _OVERLAP['pending'].append((ev, (ctx.saved_tensors, dlogits, scr, wsA, wsB, w1T, w2T, d_w1cat, d_b1, d_w2cat, d_b2, cl_bws,
+                                             ctx.cl_ws, ctx.w_bf)))
             _OVERLAP['deferred_total'] += 1
             _join_after_backward()
         return (denc, None, None, None, None, None, None, d_phi_w, d_psi_w, d_psi_b) + tuple(g1) + tuple(g2) + (d_emb_w, d_wc, d_bc)
