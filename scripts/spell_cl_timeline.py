@@ -8,7 +8,8 @@ from ss_asr_b200.asr import ASR
 dev = 'cuda'
 torch.manual_seed(1)
 m = ASR(50, 256, 256, 128, 80, 0.9).to(dev).train()
-B, Tp, U = 256, 64, 41
+import sys as _s
+B, Tp, U = (int(_s.argv[1]) if len(_s.argv) > 1 else 256), 64, 41
 g = torch.Generator().manual_seed(1)
 enc = (0.3 * torch.randn(B, Tp, 512, generator=g)).to(dev)
 lens = sorted([int(v) for v in torch.randint(48, 65, (B,), generator=g)], reverse=True)
@@ -30,3 +31,18 @@ print('step period (h landed -> h landed): %.0f cycles' % float((d[2:, 0] - d[1:
 for i in range(1, 6):
     print('%-14s +%.0f cycles after h landed' % (names[i], float((d[1:-1, i] - d[1:-1, 0]).double().mean())))
 print('h img -> next h landed: %.0f' % float((d[2:, 0] - d[1:-1, 5]).double().mean()))
+
+# backward kernel (layer-1 chain + attention): stamps of thread 128 of CTA 0
+dbgb = torch.zeros(U, 8, dtype=torch.int64, device=dev)
+e = enc.clone().requires_grad_(True)
+logits, att, toks = m._spell(e, lens, tok.clone(), [0] * U, 'bf16')
+lib.ssasr_spell_cl_set_debug_bwd(dbgb.data_ptr())
+logits.backward(torch.ones_like(logits) * 1e-3)
+torch.cuda.synchronize()
+lib.ssasr_spell_cl_set_debug_bwd(None)
+d = dbgb.cpu()
+nb = ['dh landed', 'dG written', 'dalpha partials done', 'dalpha landed', 'dq written', 'dh accumulator ready', 'dh partials written']
+sl = slice(2, U - 2)
+print('backward step period: %.0f cycles' % float((d[3:U - 1, 0] - d[2:U - 2, 0]).double().mean()))
+for i in range(1, 7):
+    print('%-24s +%.0f cycles after dh landed' % (nb[i], float((d[sl, i] - d[sl, 0]).double().mean())))

@@ -523,7 +523,12 @@ struct SpellClBwdP {
   float* de; long long de_ldb, de_ldt;                // out [.., Tp]
   float* dqpre; long long dq_ldb, dq_ldt;             // out [.., M]
   uint8_t* ring;
+  long long* dbg;                                     // optional [steps][8] clock64 stamps of CTA 0 (thread 128)
 };
+#define SB_STAMP(idx)                                                                                       \
+  do {                                                                                                      \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 128) p.dbg[(size_t)s * 8 + (idx)] = clock64(); \
+  } while (0)
 
 template <int NT, bool ATT>
 __global__ void __launch_bounds__(SP_THREADS, 1)
@@ -755,6 +760,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       // ---- 1. dh1(t): the partial sums of the 8 CTAs of the previous step, then the cell backward ----
       if (s > 0) {
         mbar_wait_t(dh_full + ((s - 1) & 1), ((s - 1) >> 1) & 1);
+        SB_STAMP(0);
         if (ct == 0 && s + 2 < n_steps) mbar_expect_tx(dh_full + ((s - 1) & 1), SP_NC * DHB);   // re-armed for the pushes of step s + 1
         const uint8_t* base = dhin + ((s - 1) & 1) * SP_NC * DHB;
 #pragma unroll
@@ -794,6 +800,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(dg_ready);
+      SB_STAMP(1);
       if (ATT) {
         // ---- 2. partial dalpha over the CTA's 128 gate rows, all utterances of the cluster ----
         mbar_wait_t(dg_ready, s & 1);               // every warp's rows of the operand tile are in place
@@ -829,10 +836,12 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(da_ready);
+        SB_STAMP(2);
         // ---- 3. owner: softmax backward and dq of the own utterances ----
         if (att_warp && n_own > 0) {
           float de = 0.f;
           mbar_wait_t(da_full, s & 1);
+          SB_STAMP(3);
           if (ct == 0 && s + 1 < n_steps) mbar_expect_tx(da_full, SP_NC * n_own * 256);
           float da = 0.f;
           if (att_on) {
@@ -878,11 +887,13 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           fence_proxy_async();
           named_bar(1, 256);
           if (ct == 0) mbar_arrive(dq_ready);
+          SB_STAMP(4);
         }
       }
       // ---- 4. partial dh of all 256 units (this CTA's gate rows / query rows contracted) -> bf16 -> the units' owners ----
       if (s + 1 < n_steps) {
         mbar_wait_t(d_done, s & 1);
+        SB_STAMP(5);
         tc_fence_after();
         const int sp = warp & 3, cgrp = cw >> 2;   // TMEM sub-partition = 32 units = one destination per half; 8 (4) columns
         constexpr int NCOL = NT / 4;
@@ -909,6 +920,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(dh_ready);
+        SB_STAMP(6);
       }
     }
   }
@@ -981,6 +993,7 @@ uint8_t* sp_ring_for(cudaStream_t st) {
 }
 
 long long* g_sp_dbg = nullptr;
+long long* g_sp_dbg_bwd = nullptr;
 int g_sp_cap = -1;                         // co-resident clusters of the forward kernel (queried once)
 
 template <typename Kern>
@@ -1118,6 +1131,7 @@ int spell_cl_bwd(cudaStream_t st, const SpellClBwdArgs& a) {
   p.de = a.de; p.de_ldb = a.de_ldb; p.de_ldt = a.de_ldt;
   p.dqpre = a.dqpre; p.dq_ldb = a.dq_ldb; p.dq_ldt = a.dq_ldt;
   p.ring = sp_ring_for(st);
+  p.dbg = att ? g_sp_dbg_bwd : nullptr;
   SSASR_REQUIRE(p.ring != nullptr, "spell_cl_bwd: cannot allocate the exchange ring");
   CUtensorMap tmW, tmPhiS, tmP, tmPsi;
   int rc = make_tmap_bf16(&tmW, a.wcat_bf, 4 * SP_SD, a.X, a.X, 128);
@@ -1172,4 +1186,5 @@ int spell_fill_xin1(cudaStream_t st, int B, int U, int Tp, int E, int Sd, const 
 extern "C" {
 // debug: device buffer [steps][8] of clock64 stamps written by CTA 0 of the next cluster decoder-loop launches
 void ssasr_spell_cl_set_debug(long long* dev_buf) { ssasr::g_sp_dbg = dev_buf; }
+void ssasr_spell_cl_set_debug_bwd(long long* dev_buf) { ssasr::g_sp_dbg_bwd = dev_buf; }
 }
