@@ -1,0 +1,132 @@
+"""GPU parity tests of the cluster-persistent attend-and-spell kernels (ss_asr_b200/csrc/spell_cl.cu), through the drop-in module
+API: the bf16 training path at the default decoder dimensions (S_d = 256, mlp = 128) against the CPU oracle (oracle/las_oracle.py,
+pinned to the unmodified reference) and against the per-step kernels on the same inputs.
+
+Reference semantics: asr.py:65-110 (loop), :314-326 (Speller), :343-392 (Attention); loss trainer.py:426-434."""
+import random
+
+import pytest
+import torch
+
+from oracle import las_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+DIMS = (50, 64, 256, 128, 40)          # small encoder, DEFAULT decoder / attention sizes (what the cluster kernels cover)
+
+
+def _model(sd, tf=1.0):
+    from ss_asr_b200.asr import ASR
+    m = ASR(*DIMS, tf).to(DEV)
+    m.load_state_dict(sd)
+    m.train_precision = 'bf16'
+    m.train()
+    return m
+
+
+def _families(fn):
+    """-> {family: launches} of one call of fn"""
+    from ss_asr_b200 import _lib
+    lib = _lib.load()
+    lib.ssasr_profile_enable(1)
+    _lib.profile_read()
+    out = fn()
+    fam = _lib.profile_read()
+    lib.ssasr_profile_enable(0)
+    return out, {k: v[1] for k, v in fam.items() if v[1]}
+
+
+# B = 20: two clusters of 10 utterances (16-row tiles, partially filled); B = 150: ten clusters of 15; B = 250: 15 clusters of
+# 17 / 12 utterances (32-row tiles, CTAs owning 3 and 2 attention utterances): the C4 geometry
+@pytest.mark.parametrize('B,T,U', [(20, 256, 9), (150, 64, 5), (250, 96, 4)])
+def test_cluster_speller_matches_oracle(B, T, U):
+    """forward (logits, attention maps, loss) and every gradient against the fp32 CPU oracle at the bf16-path tolerances
+    (logits 1e-2, loss 1e-3 rel, gradients rel-L2 3e-2 and cosine >= 0.999), the cluster kernels verifiably running"""
+    from ss_asr_b200 import functional as Fk
+    from ss_asr_b200.functional import asr_loss
+    sd = O.make_state_dict(*DIMS, seed=1)
+    x, lens, y = O.synth_batch(B, T, DIMS[4], U, seed=21)
+    loss_o, logits_o, att_o, enc_o, grads_o = O.train_step_grads(sd, x, lens, y)
+    Fk.set_cluster_speller(True)
+    m = _model(sd)
+
+    def step():
+        _, logits, att = m(x.to(DEV), logits_o.shape[1], teacher=y.to(DEV), state_len=lens)
+        loss = asr_loss(logits, y.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        return logits, att, loss
+    (logits, att, loss), fam = _families(step)
+    assert fam.get('spell_fwd', 0) >= 2 and fam.get('spell_bwd', 0) == 2, fam      # layer-1 + layer-2 chains, forward and backward
+    assert 'attn_fwd' not in fam and fam.get('attn_bwd', 0) <= 2, fam              # no per-step attention launches (2 = outer accums)
+    assert float((logits.detach().cpu() - logits_o).abs().max()) < 1e-2
+    assert float((att - att_o).abs().max()) < 1e-3
+    assert abs(float(loss) - float(loss_o)) < 1e-3 * float(loss_o)
+    gtot = float(torch.sqrt(sum(v.double().pow(2).sum() for v in grads_o.values())))
+    for k, p in m.named_parameters():
+        a, b = p.grad.cpu().double(), grads_o[k].double()
+        assert float((a - b).norm()) <= 3e-2 * float(b.norm()) + 1e-4 * gtot, k
+        if float(b.norm()) > 1e-3 * gtot:
+            assert float((a * b).sum() / (a.norm() * b.norm())) >= 0.999, k
+
+
+@pytest.mark.parametrize('tf_rate', [1.0, 0.6])
+def test_cluster_speller_matches_per_step_kernels(tf_rate):
+    """Same inputs through the cluster kernels and through the per-step kernels (bf16 path both): results equal up to the
+    bf16 rounding points that differ (P = W_ctx enc and psi~ in bf16, tanh.approx in the cell); with sampled steps (several runs
+    per call, the loop leaves the kernel to select a token) the tokens drawn must agree and the race check repeats the call."""
+    from ss_asr_b200 import functional as Fk
+    from ss_asr_b200.functional import asr_loss
+    sd = O.make_state_dict(*DIMS, seed=2)
+    x, lens, y = O.synth_batch(37, 128, DIMS[4], 14, seed=5)
+
+    def run(cl):
+        Fk.set_cluster_speller(cl)
+        m = _model(sd, tf=tf_rate)
+        m.sample_seed = 9
+        random.seed(4)
+        _, logits, att = m(x.to(DEV), 15, teacher=y.to(DEV), state_len=lens)
+        asr_loss(logits, y.to(DEV)).backward()
+        torch.cuda.synchronize()
+        return logits.detach().clone(), att.clone(), m.last_tokens.clone(), {k: p.grad.clone() for k, p in m.named_parameters()}
+    try:
+        want = run(False)
+        first = None
+        for _ in range(3):
+            got = run(True)
+            if tf_rate < 1.0:       # sampled tokens: identical draws unless a probability boundary falls inside the bf16 difference
+                assert float((got[2] == want[2]).float().mean()) > 0.98
+            same = (got[2] == want[2]).all(dim=1)                   # utterances whose token history is the same on both paths
+            assert float((got[0][same] - want[0][same]).abs().max()) < 1e-2
+            assert float((got[1][same.cpu()] - want[1][same.cpu()]).abs().max()) < 2e-3
+            if tf_rate == 1.0:
+                for k in want[3]:
+                    a, b = got[3][k].double(), want[3][k].double()
+                    assert float((a - b).norm()) <= 2e-2 * float(b.norm()) + 1e-9, k
+            if first is None:
+                first = got
+            else:                   # run-to-run: same kernels, same data -> identical forward results
+                assert torch.equal(got[0], first[0]) and torch.equal(got[1], first[1]) and torch.equal(got[2], first[2])
+    finally:
+        Fk.set_cluster_speller(True)
+
+
+def test_cluster_speller_can_be_switched_off():
+    """SSASR_SPELL_CL=0 / set_cluster_speller(False): the per-step kernels run (the cluster path is an optimisation, never a
+    dependency of the result)."""
+    from ss_asr_b200 import functional as Fk
+    from ss_asr_b200.functional import asr_loss
+    sd = O.make_state_dict(*DIMS, seed=1)
+    x, lens, y = O.synth_batch(6, 64, DIMS[4], 5, seed=3)
+    try:
+        Fk.set_cluster_speller(False)
+        m = _model(sd)
+
+        def step():
+            _, logits, att = m(x.to(DEV), 6, teacher=y.to(DEV), state_len=lens)
+            asr_loss(logits, y.to(DEV)).backward()
+            torch.cuda.synchronize()
+        _, fam = _families(step)
+        assert 'spell_fwd' not in fam and 'spell_bwd' not in fam and fam.get('attn_fwd', 0) == 6, fam
+    finally:
+        Fk.set_cluster_speller(True)
