@@ -238,6 +238,7 @@ int ssasr_rec_cl_capacity(int S, int backward); /* co-resident (direction, tile)
 void ssasr_rec_cl_enable(int on);              /* 0: counter-barrier recurrent kernels everywhere (A/B comparison) */
 void ssasr_spell_cl_set_debug(long long* dev_buf /*[steps][8], cluster decoder-step kernels (spell_cl.cu)*/);
 void ssasr_spell_cl_set_debug_bwd(long long* dev_buf /*[steps][8], backward kernel*/);
+void ssasr_spell_cl_set_debug_mode(int plain_recurrence /*1: stamp the layer-2 (plain recurrence) launches instead*/);
 void ssasr_rec_q_set_rows(int rows);           /* batch rows per tile of the quad-cluster recurrence: 32 / 16; 0 = 8-CTA kernels */
 
 #ifdef __cplusplus

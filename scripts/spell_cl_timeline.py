@@ -46,3 +46,20 @@ sl = slice(2, U - 2)
 print('backward step period: %.0f cycles' % float((d[3:U - 1, 0] - d[2:U - 2, 0]).double().mean()))
 for i in range(1, 7):
     print('%-24s +%.0f cycles after dh landed' % (nb[i], float((d[sl, i] - d[sl, 0]).double().mean())))
+
+# plain-recurrence mode (the layer-2 chain): forward stamps 0 (h landed), 4 (accumulator ready), 5 (h image written); backward
+# stamps 0 (dh landed), 1 (dG written), 5 (dh accumulator ready), 6 (dh partials written)
+lib.ssasr_spell_cl_set_debug_mode(1)
+dbg.zero_(); dbgb.zero_()
+lib.ssasr_spell_cl_set_debug(dbg.data_ptr()); lib.ssasr_spell_cl_set_debug_bwd(dbgb.data_ptr())
+e = enc.clone().requires_grad_(True)
+logits, att, toks = m._spell(e, lens, tok.clone(), [0] * U, 'bf16')
+logits.backward(torch.ones_like(logits) * 1e-3)
+torch.cuda.synchronize()
+lib.ssasr_spell_cl_set_debug(None); lib.ssasr_spell_cl_set_debug_bwd(None); lib.ssasr_spell_cl_set_debug_mode(0)
+d = dbg.cpu(); db = dbgb.cpu()
+print('layer-2 forward step period %.0f cycles: accumulator ready +%.0f, h image +%.0f' % (
+    float((d[3:U - 1, 0] - d[2:U - 2, 0]).double().mean()), float((d[sl, 4] - d[sl, 0]).double().mean()), float((d[sl, 5] - d[sl, 0]).double().mean())))
+print('layer-2 backward step period %.0f cycles: dG written +%.0f, dh accumulator +%.0f, partials written +%.0f' % (
+    float((db[3:U - 1, 0] - db[2:U - 2, 0]).double().mean()), float((db[sl, 1] - db[sl, 0]).double().mean()),
+    float((db[sl, 5] - db[sl, 0]).double().mean()), float((db[sl, 6] - db[sl, 0]).double().mean())))

@@ -107,5 +107,30 @@ __device__ __forceinline__ uint64_t umma_desc_k64(uint32_t smem_addr) {
   return d;
 }
 
+__device__ __forceinline__ void tmem_ld1(uint32_t ta, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(ta) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t ta, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(ta) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+// 4 x 4 transpose inside a lane quad: before, lane g holds columns 0..3 of ITS row; afterwards lane gp holds rows 0..3 of column gp
+__device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, float& a3, int gp) {
+  {
+    const float x = (gp & 1) ? a0 : a1, y = (gp & 1) ? a2 : a3;
+    const float xr = __shfl_xor_sync(0xffffffffu, x, 1), yr = __shfl_xor_sync(0xffffffffu, y, 1);
+    if (gp & 1) { a0 = xr; a2 = yr; } else { a1 = xr; a3 = yr; }
+  }
+  {
+    const float x = (gp & 2) ? a0 : a2, y = (gp & 2) ? a1 : a3;
+    const float xr = __shfl_xor_sync(0xffffffffu, x, 2), yr = __shfl_xor_sync(0xffffffffu, y, 2);
+    if (gp & 2) { a0 = xr; a1 = yr; } else { a2 = xr; a3 = yr; }
+  }
+}
+
+
 }  // namespace clx
 }  // namespace ssasr

@@ -124,6 +124,13 @@ int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
                int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias);
 
 
+// 16-CTA cluster recurrent kernels for S = 512 (rec_wide.cu): the long-utterance configuration
+int rec_wide_supported(int S, int n_batch, int backward);
+int rec_wide_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
+                 int n_seq, int n_batch, long long rs_seq, long long rs_batch);
+int rec_wide_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
+                 int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias);
+
 // cluster-persistent decoder-step kernels (spell_cl.cu): steps [t0, t1) of the attend-and-spell loop (attention + layer-1 cell)
 // in ONE launch.  Strides (`*_ldb` per utterance, `*_ldt` per step) are in elements.
 struct SpellClFwdArgs {

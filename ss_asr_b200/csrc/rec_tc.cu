@@ -717,6 +717,7 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
                int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar) {
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_fwd: unsupported state size %d", S);
   if (rec_cl_supported(S, n_batch, 0)) return rec_cl_fwd(st, xp, whh_bf, hout, cbuf, hb, lens, S, n_seq, n_batch, rs_seq, rs_batch);
+  if (rec_wide_supported(S, n_batch, 0)) return rec_wide_fwd(st, xp, whh_bf, hout, cbuf, hb, lens, S, n_seq, n_batch, rs_seq, rs_batch);
   const int TM = pick_tm(S, n_batch);
   RecTcParams p;
   p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.xb2 = nullptr; p.dhout = nullptr; p.dcstate = nullptr; p.dbias = nullptr;
@@ -792,6 +793,8 @@ int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_bwd: unsupported state size %d", S);
   if (!need_dg32 && rec_cl_supported(S, n_batch, 1))     // the cluster kernel only produces the bf16 dG
     return rec_cl_bwd(st, act, whhT_bf, cbuf, dhout, dgb, lens, S, n_seq, n_batch, rs_seq, rs_batch, dbias);
+  if (!need_dg32 && rec_wide_supported(S, n_batch, 1))
+    return rec_wide_bwd(st, act, whhT_bf, cbuf, dhout, dgb, lens, S, n_seq, n_batch, rs_seq, rs_batch, dbias);
   const int TM = pick_tm(S, n_batch);
   RecTcParams p;
   p.xp = act; p.hout = nullptr; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.xb2 = nullptr; p.dhout = dhout; p.dcstate = dcstate;

@@ -1,0 +1,488 @@
+// Cluster recurrent BLSTM kernels for the WIDE state size (S = 512: the long-utterance configuration, BASELINE configs[4]).
+// The quad-cluster kernels of rec_cl.cu keep a 256-gate-row slice of W_hh resident per CTA, which at S = 512 is 256 KB; here
+// a (direction, 16-utterance tile) belongs to ONE 16-CTA thread-block cluster (non-portable size), CTA r owning hidden units
+// [32 r, 32 r + 32) = 128 gate rows:
+//   forward   gates^T [128 rows x 16 utt] = W_hh slice [128 x 512] (resident, 128 KB) x h(t-1)^T tile (all-gathered: every CTA
+//             multicasts its 1 KB slice); cell math from TMEM, one cell per epilogue thread
+//   backward  K-split, as in spell_cl.cu: every CTA contracts ITS 128 gate rows,
+//             dh^T partial [512 units x 16 utt] = W_hh^T slice [512 x 128] (resident, 128 KB) x dG slice^T,
+//             and pushes the bf16 partial of each 32-unit block to the block's owner (bulk store + read-back with a one-CTA
+//             multicast mask); the owner adds the 16 partials to dh_out(t) and runs the cell backward
+// so neither direction streams weights and the per-step MMA count is 32 (N = 16) instead of 128 on the all-gathered dG tile.
+//
+// Reference semantics: nn.LSTM(bidirectional) over a packed batch (asr.py:410-418): masking and row-stride conventions, bf16
+// operand rounding, fp32 accumulation and tanh.approx cell math exactly as in rec_cl.cu / rec_tc.cu.
+#include <limits.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "cl_common.cuh"
+
+namespace ssasr {
+
+using namespace tc;
+using namespace clx;
+
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+
+namespace {
+
+constexpr int RW_S = 512;
+constexpr int RW_NC = RW_S / 32;          // 16 CTAs per cluster, 32 hidden units each
+constexpr int RW_NT = 16;                 // utterances per tile
+constexpr int RW_EPW = 16;
+constexpr int RW_THREADS = 128 + 32 * RW_EPW;     // warp 0 exchange, 1 MMA / TMEM, 2-3 idle, 4.. compute
+constexpr int RW_HBLK = RW_NT * 64;       // one producer's k-block of the h tile (32 units): [16 rows x 64 B], 64-byte swizzle
+constexpr int RW_DHB = RW_NT * 64;        // one (source, destination) block of dh partials: [16 utterances][32 units] bf16
+constexpr int RW_RING = 4;
+constexpr int RW_SLOT = RW_NC * RW_DHB;   // exchange slot per CTA and ring position (backward: 16 KB; forward uses 1 KB of it)
+
+constexpr int FOFF_W = 0;                                 // W_hh slice [128 gate rows x 512]: 8 k-blocks of [128 x 128 B]
+constexpr int FOFF_H = FOFF_W + 131072;                   // h tile [2 buffers][16 producers][HBLK]
+constexpr int FOFF_HIMG = FOFF_H + 2 * RW_NC * RW_HBLK;
+constexpr int FOFF_BARS = FOFF_HIMG + RW_HBLK;
+constexpr int RWF_SMEM = FOFF_BARS + 16 * 8 + 1024;
+
+constexpr int WOFF_W = 0;                                 // W_hh^T slice [512 units x 128 gates]: [4 unit blocks][2 k-blocks] of [128 x 128 B]
+constexpr int WOFF_DG = WOFF_W + 131072;                  // dG slice operand [16 utterances x 128 gates] bf16, 2 k-blocks
+constexpr int WOFF_DHOUT = WOFF_DG + 4096;                // outgoing dh partials [16 destinations][DHB]
+constexpr int WOFF_DHIN = WOFF_DHOUT + RW_NC * RW_DHB;    // incoming dh partials [2 buffers][16 sources][DHB]
+constexpr int WOFF_BARS = WOFF_DHIN + 2 * RW_NC * RW_DHB;
+constexpr int RWB_SMEM = WOFF_BARS + 16 * 8 + 1024;
+static_assert(RWF_SMEM <= 232448 && RWB_SMEM <= 232448, "shared-memory map");
+
+struct RecWideP {
+  float* xp;                 // fwd: [rows, 8S] pre-activations in / activations out.  bwd: activations in
+  float* hout;               // fwd out [rows, 2S]
+  float* cbuf;               // fwd out / bwd in [rows, 2S]
+  __nv_bfloat16* xb;         // fwd out: bf16 h [rows, 2S].  bwd out: bf16 dG [rows, 8S]
+  const float* dhout;        // bwd in [rows, 2S]
+  float* dbias;              // bwd: [8S] pre-zeroed, atomically accumulated; may be null
+  uint8_t* ring;
+  const int* lens;
+  int n_seq, n_batch;
+  long long rs_seq, rs_batch;
+};
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecWideP p) {
+  constexpr int S = RW_S;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wsm = smem + FOFF_W;
+  uint8_t* Hsm = smem + FOFF_H;
+  uint8_t* himg = smem + FOFF_HIMG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FOFF_BARS);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;            // [2]
+  uint64_t* g_done = bars + 3;
+  uint64_t* stage_ready = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int r = blockIdx.x, dir = blockIdx.y, b0 = blockIdx.z * RW_NT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_steps = p.n_seq;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmW);
+    mbar_init(w_full, 1);
+    mbar_init(a_full, 1);
+    mbar_init(a_full + 1, 1);
+    mbar_init(g_done, 1);
+    mbar_init(stage_ready, RW_EPW);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<32>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, 131072);
+    for (int kb = 0; kb < 8; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * 16384, kb * 64, dir * 4 * S + r * 128);
+    mbar_expect_tx(a_full, RW_NC * RW_HBLK);
+    mbar_expect_tx(a_full + 1, RW_NC * RW_HBLK);
+  }
+  cluster_sync_all();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint16_t cmask = 0xFFFFu;
+      const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      for (int s = 0; s + 1 < n_steps; ++s) {
+        uint8_t* slot = p.ring + ((size_t)(s % RW_RING) * n_cta + cta) * RW_SLOT;
+        mbar_wait_t(stage_ready, s & 1);
+        bulk_store_wait(slot, himg, RW_HBLK);
+        bulk_load_mc(Hsm + ((s & 1) * RW_NC + r) * RW_HBLK, slot, RW_HBLK, a_full + (s & 1), cmask);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, RW_NT);
+      mbar_wait_t(w_full, 0);
+      for (int s = 1; s < n_steps; ++s) {                  // step 0 starts from the zero state: no product
+        const int hb = (s - 1) & 1;
+        mbar_wait_t(a_full + hb, ((s - 1) >> 1) & 1);
+        if (s + 2 < n_steps) mbar_expect_tx(a_full + hb, RW_NC * RW_HBLK);
+        tc_fence_after();
+        const uint32_t h0 = smem_u32(Hsm + hb * RW_NC * RW_HBLK), w0 = smem_u32(Wsm);
+#pragma unroll 4
+        for (int kk = 0; kk < S / 16; ++kk)
+          mma_bf16_ss(tmem, umma_desc_k128(w0 + (kk >> 2) * 16384) + (uint64_t)((kk & 3) * 2),
+                      umma_desc_k64(h0 + (kk >> 1) * RW_HBLK) + (uint64_t)((kk & 1) * 2), idesc, kk != 0);
+        mma_commit(g_done);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int sp = warp & 3, cg = (warp - 4) >> 2;
+    const int uq = lane >> 2, gp = lane & 3;
+    const int unit = 32 * r + 8 * sp + uq;         // hidden unit (inside the direction) of this thread's cell
+    const int slot = 4 * cg + gp;                  // utterance slot of the tile
+    const int n = b0 + slot;
+    const bool inr = n < p.n_batch;
+    const int len = inr ? (p.lens ? p.lens[n] : INT_MAX) : 0;
+    const size_t rowb = (size_t)(inr ? n : 0) * p.rs_batch;
+    const size_t gcol = (size_t)dir * 4 * S + (size_t)unit * 4, hcol = (size_t)dir * S + unit;
+    uint8_t* himg_dst = himg + slot * 64 + ((sp ^ ((slot >> 1) & 3)) << 4) + uq * 2;
+    float creg = 0.f;
+    float4 gn = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int s_) {
+      const int t_ = dir == 0 ? s_ : n_steps - 1 - s_;
+      gn = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t_ < len) gn = __ldcs(reinterpret_cast<const float4*>(p.xp + ((size_t)t_ * p.rs_seq + rowb) * 8 * S + gcol));
+    };
+    fetch(0);
+    for (int s = 0; s < n_steps; ++s) {
+      const int t = dir == 0 ? s : n_steps - 1 - s;
+      const bool valid = t < len;
+      float4 g = gn;
+      if (s + 1 < n_steps) fetch(s + 1);
+      if (s > 0) {
+        uint32_t v[4];
+        mbar_wait_t(g_done, (s - 1) & 1);
+        tc_fence_after();
+        tmem_ld4(tmem + ((uint32_t)(sp * 32) << 16) + (uint32_t)(4 * cg), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        float a0 = __uint_as_float(v[0]), a1 = __uint_as_float(v[1]), a2 = __uint_as_float(v[2]), a3 = __uint_as_float(v[3]);
+        quad_transpose(a0, a1, a2, a3, gp);
+        g.x += a0; g.y += a1; g.z += a2; g.w += a3;
+      }
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      float cv = 0.f, hv = 0.f;
+      if (valid) {
+        a.x = sigmoid_apx(g.x); a.y = sigmoid_apx(g.y); a.z = tanh_apx(g.z); a.w = sigmoid_apx(g.w);
+        cv = fmaf(a.y, creg, a.x * a.z);
+        hv = a.w * tanh_apx(cv);
+      }
+      creg = cv;
+      *reinterpret_cast<__nv_bfloat16*>(himg_dst) = __float2bfloat16_rn(hv);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stage_ready);
+      if (inr) {
+        const size_t row = (size_t)t * p.rs_seq + rowb;
+        __stcs(reinterpret_cast<float4*>(p.xp + row * 8 * S + gcol), a);
+        p.hout[row * 2 * S + hcol] = hv;
+        p.cbuf[row * 2 * S + hcol] = cv;
+        p.xb[row * 2 * S + hcol] = __float2bfloat16_rn(hv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<32>(tmem);
+  cluster_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, RecWideP p) {
+  constexpr int S = RW_S;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* Wsm = smem + WOFF_W;
+  uint8_t* dGsm = smem + WOFF_DG;
+  uint8_t* dhout = smem + WOFF_DHOUT;
+  uint8_t* dhin = smem + WOFF_DHIN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WOFF_BARS);
+  uint64_t* w_full = bars;
+  uint64_t* dh_full = bars + 1;           // [2]
+  uint64_t* d_done = bars + 3;
+  uint64_t* dg_ready = bars + 4;
+  uint64_t* dh_ready = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int r = blockIdx.x, dir = blockIdx.y, b0 = blockIdx.z * RW_NT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_steps = p.n_seq;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmWT);
+    mbar_init(w_full, 1);
+    mbar_init(dh_full, 1);
+    mbar_init(dh_full + 1, 1);
+    mbar_init(d_done, 1);
+    mbar_init(dg_ready, RW_EPW);
+    mbar_init(dh_ready, RW_EPW);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<64>(tmem_slot);
+  for (int i = threadIdx.x; i < 4096 / 16; i += RW_THREADS) reinterpret_cast<uint4*>(dGsm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && elect_one()) {
+    mbar_expect_tx(w_full, 131072);
+    for (int h = 0; h < 4; ++h)
+      for (int kb = 0; kb < 2; ++kb)
+        tma_load_2d(&tmWT, w_full, Wsm + (h * 2 + kb) * 16384, r * 128 + kb * 64, dir * S + h * 128);
+    mbar_expect_tx(dh_full, RW_NC * RW_DHB);
+    mbar_expect_tx(dh_full + 1, RW_NC * RW_DHB);
+  }
+  cluster_sync_all();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
+      const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      for (int s = 0; s + 1 < n_steps; ++s) {
+        uint8_t* slot = p.ring + ((size_t)(s % RW_RING) * n_cta + cta) * RW_SLOT;
+        mbar_wait_t(dh_ready, s & 1);
+        bulk_store_wait(slot, dhout, RW_NC * RW_DHB);
+        for (int d = 0; d < RW_NC; ++d)
+          bulk_load_mc(dhin + ((s & 1) * RW_NC + r) * RW_DHB, slot + d * RW_DHB, RW_DHB, dh_full + (s & 1), (uint16_t)(1u << d));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, RW_NT);
+      mbar_wait_t(w_full, 0);
+      for (int s = 0; s + 1 < n_steps; ++s) {
+        mbar_wait_t(dg_ready, s & 1);
+        tc_fence_after();
+        const uint32_t w0 = smem_u32(Wsm), g0 = smem_u32(dGsm);
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma_bf16_ss(tmem + h * RW_NT, umma_desc_k128(w0 + (h * 2 + (kk >> 2)) * 16384) + (uint64_t)((kk & 3) * 2),
+                        umma_desc_k128(g0 + (kk >> 2) * 2048) + (uint64_t)((kk & 3) * 2), idesc, kk != 0);
+        mma_commit(d_done);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int cw = warp - 4;                       // utterance slot of this warp's cells; lane = unit of the CTA
+    const int unit = 32 * r + lane;
+    const int n = b0 + cw;
+    const bool inr = n < p.n_batch;
+    const int len = inr ? (p.lens ? p.lens[n] : INT_MAX) : 0;
+    const size_t rowb = (size_t)(inr ? n : 0) * p.rs_batch;
+    const size_t gcol = (size_t)dir * 4 * S + (size_t)unit * 4, hcol = (size_t)dir * S + unit;
+    float dcreg = 0.f, bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 a_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    float c_n = 0.f, cp_n = 0.f, dh_n = 0.f;
+    // the backward chain walks the steps in the opposite order of the forward pass of its direction
+    auto fetch = [&](int s_) {
+      const int t_ = dir == 0 ? n_steps - 1 - s_ : s_;
+      const int tp_ = dir == 0 ? t_ - 1 : t_ + 1;
+      a_n = make_float4(0.f, 0.f, 0.f, 0.f);
+      c_n = 0.f; cp_n = 0.f; dh_n = 0.f;
+      if (t_ < len) {
+        const size_t row = (size_t)t_ * p.rs_seq + rowb;
+        a_n = __ldcs(reinterpret_cast<const float4*>(p.xp + row * 8 * S + gcol));
+        dh_n = __ldcs(p.dhout + row * 2 * S + hcol);
+        c_n = __ldg(p.cbuf + row * 2 * S + hcol);
+        if (tp_ >= 0 && tp_ < n_steps && tp_ < len) cp_n = __ldg(p.cbuf + ((size_t)tp_ * p.rs_seq + rowb) * 2 * S + hcol);
+      }
+    };
+    fetch(0);
+    for (int s = 0; s < n_steps; ++s) {
+      const int t = dir == 0 ? n_steps - 1 - s : s;
+      const int tp = dir == 0 ? t - 1 : t + 1;
+      const bool valid = t < len;
+      const bool pv = valid && tp >= 0 && tp < n_steps && tp < len;
+      const float4 a = a_n;
+      const float cv = c_n, cpv = cp_n;
+      float dh = dh_n;
+      if (s + 1 < n_steps) fetch(s + 1);
+      if (s > 0) {
+        mbar_wait_t(dh_full + ((s - 1) & 1), ((s - 1) >> 1) & 1);
+        if (threadIdx.x == 128 && s + 2 < n_steps) mbar_expect_tx(dh_full + ((s - 1) & 1), RW_NC * RW_DHB);
+        const uint8_t* base = dhin + ((s - 1) & 1) * RW_NC * RW_DHB + cw * 64 + lane * 2;
+        float acc = 0.f;
+#pragma unroll
+        for (int src = 0; src < RW_NC; ++src) acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + src * RW_DHB));
+        dh += acc;
+      }
+      float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+      float dco = 0.f;
+      if (valid) {
+        const float tc_ = tanh_apx(cv);
+        const float dc = fmaf(dh * a.w, 1.f - tc_ * tc_, dcreg);
+        dg.w = dh * tc_ * a.w * (1.f - a.w);
+        dg.x = dc * a.z * a.x * (1.f - a.x);
+        dg.z = dc * a.x * (1.f - a.z * a.z);
+        dg.y = pv ? dc * cpv * a.y * (1.f - a.y) : 0.f;
+        dco = dc * a.y;
+      }
+      dcreg = dco;
+      bsum[0] += dg.x; bsum[1] += dg.y; bsum[2] += dg.z; bsum[3] += dg.w;
+      const __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&b01);
+      pk.y = *reinterpret_cast<const uint32_t*>(&b23);
+      *reinterpret_cast<uint2*>(dGsm + (lane >> 4) * 2048 + cw * 128 + ((((lane & 15) >> 1) ^ (cw & 7)) << 4) + (lane & 1) * 8) = pk;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dg_ready);
+      if (inr) *reinterpret_cast<uint2*>(p.xb + ((size_t)t * p.rs_seq + rowb) * 8 * S + gcol) = pk;
+      if (s + 1 < n_steps) {
+        mbar_wait_t(d_done, s & 1);
+        tc_fence_after();
+        const int sp = warp & 3, cgrp = cw >> 2;
+        uint32_t v[4][4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) tmem_ld4(tmem + ((uint32_t)(sp * 32) << 16) + (uint32_t)(h * RW_NT + cgrp * 4), v[h]);
+        tmem_ld_wait();
+        tc_fence_before();
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<__nv_bfloat16*>(dhout + (h * 4 + sp) * RW_DHB + (cgrp * 4 + c) * 64 + lane * 2) =
+                __float2bfloat16_rn(__uint_as_float(v[h][c]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dh_ready);
+      }
+    }
+    if (p.dbias) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) atomicAdd(p.dbias + gcol + g, bsum[g]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<64>(tmem);
+  cluster_sync_all();
+}
+
+struct RwRing { cudaStream_t st; int dev; uint8_t* buf; };
+RwRing g_rw_rings[16];
+int g_rw_nrings = 0;
+uint8_t* rw_ring_for(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < g_rw_nrings; ++i)
+    if (g_rw_rings[i].st == st && g_rw_rings[i].dev == dev) return g_rw_rings[i].buf;
+  if (g_rw_nrings == 16) return nullptr;
+  uint8_t* b = nullptr;
+  if (cudaMalloc(&b, (size_t)RW_RING * 160 * RW_SLOT) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  g_rw_rings[g_rw_nrings++] = {st, dev, b};
+  return b;
+}
+
+template <typename Kern>
+int rw_query(Kern kern, int smem_bytes) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(RW_NC, 2, 1);
+  cfg.blockDim = dim3(RW_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = RW_NC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nc = 0;
+  if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+  return nc;
+}
+int g_rw_cap[2] = {-1, -1};
+int rw_capacity(int backward) {
+  const int w = backward ? 1 : 0;
+  if (g_rw_cap[w] < 0) g_rw_cap[w] = backward ? rw_query(rec_wide_bwd_kernel, RWB_SMEM) : rw_query(rec_wide_fwd_kernel, RWF_SMEM);
+  return g_rw_cap[w];
+}
+
+template <typename Kern>
+int rw_launch(Kern kern, int smem_bytes, dim3 grid, cudaStream_t st, const CUtensorMap& tm, const RecWideP& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(RW_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = RW_NC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, p));
+  return 0;
+}
+
+}  // namespace
+
+// 1 when the 16-CTA cluster kernels can run this layer with every (direction, 16-utterance tile) cluster co-resident
+int rec_wide_supported(int S, int n_batch, int backward) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SSASR_REC_WIDE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!on || S != RW_S || n_batch < 1) return 0;
+  const int tiles = (n_batch + RW_NT - 1) / RW_NT;
+  return 2 * tiles <= rw_capacity(backward) ? 1 : 0;
+}
+
+int rec_wide_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
+                 int n_seq, int n_batch, long long rs_seq, long long rs_batch) {
+  SSASR_REQUIRE(rec_wide_supported(S, n_batch, 0), "rec_wide_fwd: unsupported shape S=%d n_batch=%d", S, n_batch);
+  RecWideP p = {};
+  p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.lens = lens;
+  p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
+  p.ring = rw_ring_for(st);
+  SSASR_REQUIRE(p.ring != nullptr, "rec_wide_fwd: cannot allocate the exchange ring");
+  CUtensorMap tmW;
+  int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 128);
+  if (rc) return rc;
+  ProfScope ps(F_REC_TC_FWD, st);
+  return rw_launch(rec_wide_fwd_kernel, RWF_SMEM, dim3(RW_NC, 2, (n_batch + RW_NT - 1) / RW_NT), st, tmW, p);
+}
+
+int rec_wide_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
+                 int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias) {
+  SSASR_REQUIRE(rec_wide_supported(S, n_batch, 1), "rec_wide_bwd: unsupported shape S=%d n_batch=%d", S, n_batch);
+  RecWideP p = {};
+  p.xp = act; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dbias = dbias; p.lens = lens;
+  p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
+  p.ring = rw_ring_for(st);
+  SSASR_REQUIRE(p.ring != nullptr, "rec_wide_bwd: cannot allocate the exchange ring");
+  CUtensorMap tmWT;
+  int rc = make_tmap_bf16(&tmWT, whhT_bf, 2 * S, 4 * S, 4 * S, 128);
+  if (rc) return rc;
+  ProfScope ps(F_REC_TC_BWD, st);
+  return rw_launch(rec_wide_bwd_kernel, RWB_SMEM, dim3(RW_NC, 2, (n_batch + RW_NT - 1) / RW_NT), st, tmWT, p);
+}
+
+}  // namespace ssasr

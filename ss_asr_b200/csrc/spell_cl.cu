@@ -86,30 +86,6 @@ struct SpellClP {
     if (p.dbg && blockIdx.x == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 8 + (idx)] = clock64(); \
   } while (0)
 
-__device__ __forceinline__ void tmem_ld1(uint32_t ta, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(ta) : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t ta, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(ta) : "memory");
-}
-__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
-// 4 x 4 transpose inside a lane quad: before, lane g holds columns 0..3 of ITS row; afterwards lane gp holds rows 0..3 of column gp
-__device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, float& a3, int gp) {
-  {
-    const float x = (gp & 1) ? a0 : a1, y = (gp & 1) ? a2 : a3;
-    const float xr = __shfl_xor_sync(0xffffffffu, x, 1), yr = __shfl_xor_sync(0xffffffffu, y, 1);
-    if (gp & 1) { a0 = xr; a2 = yr; } else { a1 = xr; a3 = yr; }
-  }
-  {
-    const float x = (gp & 2) ? a0 : a2, y = (gp & 2) ? a1 : a3;
-    const float xr = __shfl_xor_sync(0xffffffffu, x, 2), yr = __shfl_xor_sync(0xffffffffu, y, 2);
-    if (gp & 2) { a0 = xr; a1 = yr; } else { a2 = xr; a3 = yr; }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward.  NT = 16 or 32: rows of the h1 / alpha tiles = N of the cluster-wide products (>= utterances of the cluster).
 // Utterance slot i of the cluster (b = b0 + i): its attention belongs to CTA i % 8 (own index i / 8), its cells to every CTA
@@ -994,6 +970,7 @@ uint8_t* sp_ring_for(cudaStream_t st) {
 
 long long* g_sp_dbg = nullptr;
 long long* g_sp_dbg_bwd = nullptr;
+int g_sp_dbg_mode = 0;
 int g_sp_cap = -1;                         // co-resident clusters of the forward kernel (queried once)
 
 template <typename Kern>
@@ -1075,7 +1052,7 @@ int spell_cl_fwd(cudaStream_t st, const SpellClFwdArgs& a) {
   p.alpha = a.alpha; p.al_ldb = a.al_ldb; p.al_ldt = a.al_ldt;
   p.xpre = a.xpre; p.xpre_ldb = a.xpre_ldb; p.xpre_ldt = a.xpre_ldt;
   p.h2nd = a.h2nd; p.h2nd_ldb = a.h2nd_ldb; p.h2nd_ldt = a.h2nd_ldt; p.h2nd_toff = a.h2nd_toff;
-  p.dbg = att ? g_sp_dbg : nullptr;
+  p.dbg = (att != (g_sp_dbg_mode != 0)) ? g_sp_dbg : nullptr;      // mode 1: stamps of the plain-recurrence launches instead
   p.ring = sp_ring_for(st);
   SSASR_REQUIRE(p.ring != nullptr, "spell_cl_fwd: cannot allocate the exchange ring");
   CUtensorMap tmW, tmPhi, tmP, tmPsi;
@@ -1131,7 +1108,7 @@ int spell_cl_bwd(cudaStream_t st, const SpellClBwdArgs& a) {
   p.de = a.de; p.de_ldb = a.de_ldb; p.de_ldt = a.de_ldt;
   p.dqpre = a.dqpre; p.dq_ldb = a.dq_ldb; p.dq_ldt = a.dq_ldt;
   p.ring = sp_ring_for(st);
-  p.dbg = att ? g_sp_dbg_bwd : nullptr;
+  p.dbg = (att != (g_sp_dbg_mode != 0)) ? g_sp_dbg_bwd : nullptr;
   SSASR_REQUIRE(p.ring != nullptr, "spell_cl_bwd: cannot allocate the exchange ring");
   CUtensorMap tmW, tmPhiS, tmP, tmPsi;
   int rc = make_tmap_bf16(&tmW, a.wcat_bf, 4 * SP_SD, a.X, a.X, 128);
@@ -1187,4 +1164,5 @@ extern "C" {
 // debug: device buffer [steps][8] of clock64 stamps written by CTA 0 of the next cluster decoder-loop launches
 void ssasr_spell_cl_set_debug(long long* dev_buf) { ssasr::g_sp_dbg = dev_buf; }
 void ssasr_spell_cl_set_debug_bwd(long long* dev_buf) { ssasr::g_sp_dbg_bwd = dev_buf; }
+void ssasr_spell_cl_set_debug_mode(int plain_recurrence) { ssasr::g_sp_dbg_mode = plain_recurrence; }
 }
