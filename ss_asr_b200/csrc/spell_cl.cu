@@ -498,7 +498,6 @@ struct SpellClBwdP {
   const float* q; long long q_ldb, q_ldt;
   float* de; long long de_ldb, de_ldt;                // out [.., Tp]
   float* dqpre; long long dq_ldb, dq_ldt;             // out [.., M]
-  const __nv_bfloat16* P;                             // [B*Tp, 4Sd] bf16 (read with plain loads)
   uint8_t* ring;
   long long* dbg;                                     // optional [steps][8] clock64 stamps of CTA 0 (thread 128)
 };
@@ -538,13 +537,15 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   uint64_t* da_ready = bars + 7;
   uint64_t* dq_ready = bars + 8;
   uint64_t* dh_ready = bars + 9;
-  uint64_t* psi_full = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* r_full = bars + 10;             // [SB_NSTAGE]
+  uint64_t* r_empty = bars + 10 + SB_NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * SB_NSTAGE);
 
   const int r = blockIdx.x;
   const int b0 = blockIdx.z * p.per;
   const int NU = min(p.per, p.B - b0);
   const int n_own = (ATT && NU > r) ? (NU - r + SP_NC - 1) / SP_NC : 0;
+  const int step_stages = ATT ? NU + n_own : 0;       // ring stages per step: all P tiles, then the own psi~ tiles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_steps = p.t1 - p.t0;
 
@@ -565,7 +566,10 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     mbar_init(da_ready, SP_EPW);
     mbar_init(dq_ready, 1);
     mbar_init(dh_ready, SP_EPW);
-    mbar_init(psi_full, 1);
+    for (int i = 0; i < SB_NSTAGE; ++i) {
+      mbar_init(r_full + i, 1);
+      mbar_init(r_empty + i, SP_EPW);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<64>(tmem_slot);
@@ -588,15 +592,6 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     if (ATT) {
       mbar_expect_tx(da_full, SP_NC * n_own * 256);
       mbar_expect_tx(dq_full, NU * 256);
-      // psi~ of the own utterances stays resident for the whole kernel (step-invariant): [n_own][2 k-blocks][64 frames x 128 B]
-      if (n_own > 0) {
-        mbar_expect_tx(psi_full, n_own * SP_STAGE);
-        for (int o = 0; o < n_own; ++o) {
-          const int row = (b0 + r + 8 * o) * p.Tp;
-          tma_load_2d(&tmPsi, psi_full, Ring + o * SP_STAGE, 0, row);
-          tma_load_2d(&tmPsi, psi_full, Ring + o * SP_STAGE + 8192, 64, row);
-        }
-      }
     }
   }
   cluster_sync_all();
@@ -662,6 +657,29 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       }
     }
     __syncwarp();
+  } else if (warp == 2) {
+    // ---------------- ring producer ----------------
+    if (ATT && elect_one()) {
+      int pos = 0;
+      for (int s = 0; s < n_steps; ++s) {
+        for (int i = 0; i < step_stages; ++i, ++pos) {
+          const int stg = pos % SB_NSTAGE;
+          mbar_wait_t(r_empty + stg, ((pos / SB_NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(r_full + stg, SP_STAGE);
+          uint8_t* dst = Ring + stg * SP_STAGE;
+          if (i < NU) {                     // P of utterance i, this CTA's 128 gate rows: two k-blocks of [64 frames x 64 rows]
+            const int row = (b0 + i) * p.Tp;
+            tma_load_2d(&tmP, r_full + stg, dst, r * 128, row);
+            tma_load_2d(&tmP, r_full + stg, dst + 8192, r * 128 + 64, row);
+          } else {                          // psi~ of own utterance i - NU
+            const int row = (b0 + r + 8 * (i - NU)) * p.Tp;
+            tma_load_2d(&tmPsi, r_full + stg, dst, 0, row);
+            tma_load_2d(&tmPsi, r_full + stg, dst + 8192, 64, row);
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ---------------- compute warps ----------------
     const int cw = warp - 4;                       // 0 .. 15
@@ -700,6 +718,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     if (att_on) len_a = min(p.enc_lens[ba], p.Tp);
     // dalpha role: thread = (frame 4 cw + (lane >> 3), 16-column part lane & 7 of the CTA's 128 gate rows)
     const int jf = 4 * cw + (lane >> 3), part = lane & 7;
+    int rpos = 0;                                  // ring position of the compute warps
 
     for (int s = 0; s < n_steps; ++s) {
       const int t = p.t1 - 1 - s;
@@ -761,59 +780,34 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       if (ATT) {
         // ---- 2. partial dalpha over the CTA's 128 gate rows, all utterances of the cluster ----
         mbar_wait_t(dg_ready, s & 1);               // every warp's rows of the operand tile are in place
-        // P row jf of utterance u, gate rows 128 r + 16 part .. + 15: 32 bytes per thread straight from L2 (a warp reads four
-        // 256-byte row segments); three utterances in flight while three are being reduced
-        const bool jv = jf < p.Tp;
-        const __nv_bfloat16* pbase = p.P + ((size_t)b0 * p.Tp + jf) * (4 * SP_SD) + 128 * r + 16 * part;
-        const size_t ustride = (size_t)p.Tp * (4 * SP_SD);
-        uint4 wa[3][2], wb[3][2];
-        auto loadp = [&](uint4 (*w)[2], int u0) {
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            w[g][0] = make_uint4(0u, 0u, 0u, 0u);
-            w[g][1] = make_uint4(0u, 0u, 0u, 0u);
-            if (jv && u0 + g < NU) {
-              const uint4* src = reinterpret_cast<const uint4*>(pbase + (size_t)(u0 + g) * ustride);
-              w[g][0] = __ldg(src);
-              w[g][1] = __ldg(src + 1);
-            }
-          }
-        };
-        auto reduce = [&](uint4 (*w)[2], int u0) {
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const int u = u0 + g;
-            if (u < NU) {
-              // dG row u of the operand tile, the same 16 gate rows: k-block part / 4, chunks 2 (part % 4) and + 1
-              const uint8_t* grow = dGsm + (part >> 2) * KBLK + u * 128;
-              // (chunk order swapped in the upper k-block: the 8 lanes of a quarter warp then hit 8 different bank groups)
-              const int up = part >> 2, c0 = 2 * (part & 3) + up;
-              const uint4 g0 = *reinterpret_cast<const uint4*>(grow + ((c0 ^ (u & 7)) << 4));
-              const uint4 g1 = *reinterpret_cast<const uint4*>(grow + (((c0 ^ 1) ^ (u & 7)) << 4));
-              const uint4 w0 = up ? w[g][1] : w[g][0], w1 = up ? w[g][0] : w[g][1];
-              float d0 = 0.f, d1 = 0.f;
-              d0 = fmaf(bf_lo(w0.x), bf_lo(g0.x), d0); d1 = fmaf(bf_hi(w0.x), bf_hi(g0.x), d1);
-              d0 = fmaf(bf_lo(w0.y), bf_lo(g0.y), d0); d1 = fmaf(bf_hi(w0.y), bf_hi(g0.y), d1);
-              d0 = fmaf(bf_lo(w0.z), bf_lo(g0.z), d0); d1 = fmaf(bf_hi(w0.z), bf_hi(g0.z), d1);
-              d0 = fmaf(bf_lo(w0.w), bf_lo(g0.w), d0); d1 = fmaf(bf_hi(w0.w), bf_hi(g0.w), d1);
-              d0 = fmaf(bf_lo(w1.x), bf_lo(g1.x), d0); d1 = fmaf(bf_hi(w1.x), bf_hi(g1.x), d1);
-              d0 = fmaf(bf_lo(w1.y), bf_lo(g1.y), d0); d1 = fmaf(bf_hi(w1.y), bf_hi(g1.y), d1);
-              d0 = fmaf(bf_lo(w1.z), bf_lo(g1.z), d0); d1 = fmaf(bf_hi(w1.z), bf_hi(g1.z), d1);
-              d0 = fmaf(bf_lo(w1.w), bf_lo(g1.w), d0); d1 = fmaf(bf_hi(w1.w), bf_hi(g1.w), d1);
-              float d = d0 + d1;
-              d += __shfl_xor_sync(0xffffffffu, d, 1);
-              d += __shfl_xor_sync(0xffffffffu, d, 2);
-              d += __shfl_xor_sync(0xffffffffu, d, 4);
-              if (part == 0) daout[(u & 7) * 256 + (u >> 3) * 64 + jf] = d;
-            }
-          }
-        };
-        loadp(wa, 0);
-        for (int u0 = 0; u0 < NU; u0 += 6) {
-          loadp(wb, u0 + 3);
-          reduce(wa, u0);
-          loadp(wa, u0 + 6);
-          reduce(wb, u0 + 3);
+        for (int u = 0; u < NU; ++u, ++rpos) {
+          const int stg = rpos % SB_NSTAGE;
+          mbar_wait_t(r_full + stg, (rpos / SB_NSTAGE) & 1);
+          // P row jf, columns 16 part .. 16 part + 15: k-block part / 4, chunks 2 (part % 4) and + 1 (order swapped in the upper
+          // k-block so that the 8 lanes of a quarter warp hit 8 different bank groups)
+          const uint8_t* prow = Ring + stg * SP_STAGE + (part >> 2) * 8192 + jf * 128;
+          const uint8_t* grow = dGsm + (part >> 2) * KBLK + u * 128;
+          const int c0 = 2 * (part & 3) + (part >> 2), c1 = c0 ^ 1;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(prow + ((c0 ^ (jf & 7)) << 4));
+          const uint4 w1 = *reinterpret_cast<const uint4*>(prow + ((c1 ^ (jf & 7)) << 4));
+          const uint4 g0 = *reinterpret_cast<const uint4*>(grow + ((c0 ^ (u & 7)) << 4));
+          const uint4 g1 = *reinterpret_cast<const uint4*>(grow + ((c1 ^ (u & 7)) << 4));
+          float d0 = 0.f, d1 = 0.f;
+          d0 = fmaf(bf_lo(w0.x), bf_lo(g0.x), d0); d1 = fmaf(bf_hi(w0.x), bf_hi(g0.x), d1);
+          d0 = fmaf(bf_lo(w0.y), bf_lo(g0.y), d0); d1 = fmaf(bf_hi(w0.y), bf_hi(g0.y), d1);
+          d0 = fmaf(bf_lo(w0.z), bf_lo(g0.z), d0); d1 = fmaf(bf_hi(w0.z), bf_hi(g0.z), d1);
+          d0 = fmaf(bf_lo(w0.w), bf_lo(g0.w), d0); d1 = fmaf(bf_hi(w0.w), bf_hi(g0.w), d1);
+          d0 = fmaf(bf_lo(w1.x), bf_lo(g1.x), d0); d1 = fmaf(bf_hi(w1.x), bf_hi(g1.x), d1);
+          d0 = fmaf(bf_lo(w1.y), bf_lo(g1.y), d0); d1 = fmaf(bf_hi(w1.y), bf_hi(g1.y), d1);
+          d0 = fmaf(bf_lo(w1.z), bf_lo(g1.z), d0); d1 = fmaf(bf_hi(w1.z), bf_hi(g1.z), d1);
+          d0 = fmaf(bf_lo(w1.w), bf_lo(g1.w), d0); d1 = fmaf(bf_hi(w1.w), bf_hi(g1.w), d1);
+          float d = d0 + d1;
+          d += __shfl_xor_sync(0xffffffffu, d, 1);
+          d += __shfl_xor_sync(0xffffffffu, d, 2);
+          d += __shfl_xor_sync(0xffffffffu, d, 4);
+          if (part == 0) daout[(u & 7) * 256 + (u >> 3) * 64 + jf] = d;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(r_empty + stg);
         }
         fence_proxy_async();
         __syncwarp();
@@ -841,23 +835,29 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           }
           named_bar(1, 256);
         }
-        if (att_on) {
-          // dq_pre[m] for m = 2 ja, 2 ja + 1: column sums of de_j psi~[j, m] over the frames (psi~ tile resident in shared memory)
-          if (s == 0) mbar_wait_t(psi_full, 0);
-          const uint8_t* pt = Ring + ua * SP_STAGE + (ja >> 5) * 8192;         // k-block of m
-          const int mc = (2 * ja) & 63;                                        // column inside the k-block
-          float s0 = 0.f, s1 = 0.f;
+        // the psi~ stages are walked by every warp in ring order (only the owner warps read them)
+        for (int o = 0; o < n_own; ++o, ++rpos) {
+          const int stg = rpos % SB_NSTAGE;
+          mbar_wait_t(r_full + stg, (rpos / SB_NSTAGE) & 1);
+          if (att_on && o == ua) {
+            // dq_pre[m] for m = 2 ja, 2 ja + 1: column sums of de_j psi~[j, m] over the frames
+            const uint8_t* pt = Ring + stg * SP_STAGE + (ja >> 5) * 8192;      // k-block of m
+            const int mc = (2 * ja) & 63;                                        // column inside the k-block
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-          for (int j = 0; j < 64; ++j) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(pt + j * 128 + (((mc >> 3) ^ (j & 7)) << 4) + (mc & 7) * 2);
-            const float dj = des[ua * 64 + j];
-            s0 = fmaf(dj, bf_lo(w), s0);
-            s1 = fmaf(dj, bf_hi(w), s1);
+            for (int j = 0; j < 64; ++j) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(pt + j * 128 + (((mc >> 3) ^ (j & 7)) << 4) + (mc & 7) * 2);
+              const float dj = des[ua * 64 + j];
+              s0 = fmaf(dj, bf_lo(w), s0);
+              s1 = fmaf(dj, bf_hi(w), s1);
+            }
+            const float dq0 = s0 * (1.f - q_a0 * q_a0), dq1 = s1 * (1.f - q_a1 * q_a1);
+            *reinterpret_cast<float2*>(p.dqpre + (size_t)ba * p.dq_ldb + (size_t)t * p.dq_ldt + 2 * ja) = make_float2(dq0, dq1);
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(dq0, dq1);
+            *reinterpret_cast<__nv_bfloat162*>(dqimg + (ua * 2 + (ja >> 5)) * 128 + (((mc >> 3) ^ (sa_slot & 7)) << 4) + (mc & 7) * 2) = pk;
           }
-          const float dq0 = s0 * (1.f - q_a0 * q_a0), dq1 = s1 * (1.f - q_a1 * q_a1);
-          *reinterpret_cast<float2*>(p.dqpre + (size_t)ba * p.dq_ldb + (size_t)t * p.dq_ldt + 2 * ja) = make_float2(dq0, dq1);
-          const __nv_bfloat162 pk = __floats2bfloat162_rn(dq0, dq1);
-          *reinterpret_cast<__nv_bfloat162*>(dqimg + (ua * 2 + (ja >> 5)) * 128 + (((mc >> 3) ^ (sa_slot & 7)) << 4) + (mc & 7) * 2) = pk;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(r_empty + stg);
         }
         if (att_warp && n_own > 0) {
           fence_proxy_async();
@@ -1106,7 +1106,6 @@ int spell_cl_bwd(cudaStream_t st, const SpellClBwdArgs& a) {
   p.alpha = a.alpha; p.al_ldb = a.al_ldb; p.al_ldt = a.al_ldt;
   p.q = a.q; p.q_ldb = a.q_ldb; p.q_ldt = a.q_ldt;
   p.de = a.de; p.de_ldb = a.de_ldb; p.de_ldt = a.de_ldt;
-  p.P = (const __nv_bfloat16*)a.P_bf;
   p.dqpre = a.dqpre; p.dq_ldb = a.dq_ldb; p.dq_ldt = a.dq_ldt;
   p.ring = sp_ring_for(st);
   p.dbg = (att != (g_sp_dbg_mode != 0)) ? g_sp_dbg_bwd : nullptr;
