@@ -236,6 +236,7 @@ void ssasr_rec_tc_set_debug(long long* dev_buf /*[n_seq][12] clock64 stamps of C
 void ssasr_rec_cl_set_debug(long long* dev_buf /*[n_seq][12], cluster recurrent kernels (rec_cl.cu)*/);
 int ssasr_rec_cl_capacity(int S, int backward); /* co-resident (direction, tile) clusters of the cluster recurrence; 0 = unavailable */
 void ssasr_rec_cl_enable(int on);              /* 0: counter-barrier recurrent kernels everywhere (A/B comparison) */
+void ssasr_rec_wide_set_debug(long long* dev_buf /*[n_seq][12], K-split backward kernels (rec_wide.cu)*/);
 void ssasr_spell_cl_set_debug(long long* dev_buf /*[steps][8], cluster decoder-step kernels (spell_cl.cu)*/);
 void ssasr_spell_cl_set_debug_bwd(long long* dev_buf /*[steps][8], backward kernel*/);
 void ssasr_spell_cl_set_debug_mode(int plain_recurrence /*1: stamp the layer-2 (plain recurrence) launches instead*/);

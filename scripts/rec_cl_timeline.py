@@ -32,9 +32,11 @@ for (B, T, K, S) in [(256, 256, 1024, 256)]:
             setdbg(None)
         else:
             setdbg(dbg.data_ptr())
+            lib.ssasr_rec_wide_set_debug(dbg.data_ptr())      # the K-split backward kernel (rec_wide.cu) stamps the same buffer
             out.sum().backward()
             torch.cuda.synchronize()
             setdbg(None)
+            lib.ssasr_rec_wide_set_debug(None)
         d = dbg.cpu()
         print(f'B={B} T={T} K={K} S={S} cluster={cluster} {which}: stamps rel. to stamp[{origin}], steps 100..102')
         for s in range(100, 103):

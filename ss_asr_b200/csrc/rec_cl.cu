@@ -1315,6 +1315,7 @@ int rec_cl_supported(int S, int n_batch, int backward) {
 }
 
 void rec_cl_enable(int on) { g_cl_on = on ? 1 : 0; }
+int rec_cl_is_enabled() { return cl_enabled() ? 1 : 0; }
 
 // co-resident cluster capacity (0 = cluster kernels unavailable for this state size)
 int rec_cl_capacity(int S, int backward) {

@@ -791,6 +791,8 @@ int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
                const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar, float* dbias,
                int need_dg32) {
   SSASR_REQUIRE(rec_tc_supported(S), "rec_tc_bwd: unsupported state size %d", S);
+  if (!need_dg32 && rec_ks_supported(S, n_batch))        // K-split cluster kernel (rec_wide.cu): bf16 dG only
+    return rec_wide_bwd(st, act, whhT_bf, cbuf, dhout, dgb, lens, S, n_seq, n_batch, rs_seq, rs_batch, dbias);
   if (!need_dg32 && rec_cl_supported(S, n_batch, 1))     // the cluster kernel only produces the bf16 dG
     return rec_cl_bwd(st, act, whhT_bf, cbuf, dhout, dgb, lens, S, n_seq, n_batch, rs_seq, rs_batch, dbias);
   if (!need_dg32 && rec_wide_supported(S, n_batch, 1))

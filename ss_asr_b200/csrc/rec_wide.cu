@@ -25,6 +25,7 @@ using namespace tc;
 using namespace clx;
 
 int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+int rec_cl_is_enabled();      // rec_cl.cu: SSASR_REC_CLUSTER / ssasr_rec_cl_enable (A/B switch of all cluster recurrent kernels)
 
 namespace {
 
@@ -34,9 +35,8 @@ constexpr int RW_NT = 16;                 // utterances per tile
 constexpr int RW_EPW = 16;
 constexpr int RW_THREADS = 128 + 32 * RW_EPW;     // warp 0 exchange, 1 MMA / TMEM, 2-3 idle, 4.. compute
 constexpr int RW_HBLK = RW_NT * 64;       // one producer's k-block of the h tile (32 units): [16 rows x 64 B], 64-byte swizzle
-constexpr int RW_DHB = RW_NT * 64;        // one (source, destination) block of dh partials: [16 utterances][32 units] bf16
 constexpr int RW_RING = 4;
-constexpr int RW_SLOT = RW_NC * RW_DHB;   // exchange slot per CTA and ring position (backward: 16 KB; forward uses 1 KB of it)
+constexpr int RW_SLOT = 16384;            // exchange slot per CTA and ring position (backward: up to 16 KB; forward uses 1 KB of it)
 
 constexpr int FOFF_W = 0;                                 // W_hh slice [128 gate rows x 512]: 8 k-blocks of [128 x 128 B]
 constexpr int FOFF_H = FOFF_W + 131072;                   // h tile [2 buffers][16 producers][HBLK]
@@ -44,13 +44,7 @@ constexpr int FOFF_HIMG = FOFF_H + 2 * RW_NC * RW_HBLK;
 constexpr int FOFF_BARS = FOFF_HIMG + RW_HBLK;
 constexpr int RWF_SMEM = FOFF_BARS + 16 * 8 + 1024;
 
-constexpr int WOFF_W = 0;                                 // W_hh^T slice [512 units x 128 gates]: [4 unit blocks][2 k-blocks] of [128 x 128 B]
-constexpr int WOFF_DG = WOFF_W + 131072;                  // dG slice operand [16 utterances x 128 gates] bf16, 2 k-blocks
-constexpr int WOFF_DHOUT = WOFF_DG + 4096;                // outgoing dh partials [16 destinations][DHB]
-constexpr int WOFF_DHIN = WOFF_DHOUT + RW_NC * RW_DHB;    // incoming dh partials [2 buffers][16 sources][DHB]
-constexpr int WOFF_BARS = WOFF_DHIN + 2 * RW_NC * RW_DHB;
-constexpr int RWB_SMEM = WOFF_BARS + 16 * 8 + 1024;
-static_assert(RWF_SMEM <= 232448 && RWB_SMEM <= 232448, "shared-memory map");
+static_assert(RWF_SMEM <= 232448, "shared-memory map");
 
 struct RecWideP {
   float* xp;                 // fwd: [rows, 8S] pre-activations in / activations out.  bwd: activations in
@@ -63,7 +57,12 @@ struct RecWideP {
   const int* lens;
   int n_seq, n_batch;
   long long rs_seq, rs_batch;
+  long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0)
 };
+#define RW_STAMP(idx)                                                                                            \
+  do {                                                                                                           \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 12 + (idx)] = clock64(); \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -202,17 +201,40 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward
+// backward, K-split.  Template: state size S and hidden units per CTA (32: the 16-CTA clusters of S = 512; 64: the quad
+// clusters of S = 256 / 128, same geometry as rec_q_bwd_kernel of rec_cl.cu, which all-gathers the dG tile and issues 4S/16
+// MMAs per step -- here S/128 * UNITS/4 on the CTA's own dG slice).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, RecWideP p) {
-  constexpr int S = RW_S;
+template <int S, int UNITS>
+struct KsGeom {
+  static constexpr int NC = S / UNITS;              // CTAs per cluster
+  static constexpr int G = 4 * UNITS;               // gate rows per CTA
+  static constexpr int KB = G / 64;                 // k-blocks of the dG slice operand
+  static constexpr int NH = S / 128;                // 128-unit blocks of the accumulator
+  static constexpr int CPT = UNITS / 32;            // cells per thread
+  static constexpr int DPH = 128 / UNITS;           // destinations per 128-unit block
+  static constexpr int DHB = RW_NT * UNITS * 2;     // one (source, destination) block: [16 utterances][UNITS] bf16
+  static constexpr int OFF_W = 0;                   // W_hh^T slice: [NH][KB] blocks of [128 units x 128 B]
+  static constexpr int OFF_DG = OFF_W + NH * KB * 16384;
+  static constexpr int OFF_DHOUT = OFF_DG + KB * 2048;
+  static constexpr int OFF_DHIN = OFF_DHOUT + NC * DHB;
+  static constexpr int OFF_BARS = OFF_DHIN + 2 * NC * DHB;
+  static constexpr int SMEM = OFF_BARS + 16 * 8 + 1024;
+  static constexpr int TCOLS = NH * RW_NT < 32 ? 32 : NH * RW_NT;
+  static constexpr int SLOT = NC * DHB;             // exchange slot per CTA and ring position
+};
+
+template <int S, int UNITS>
+__global__ void __launch_bounds__(RW_THREADS, 1) rec_ks_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, RecWideP p) {
+  using GE = KsGeom<S, UNITS>;
+  constexpr int NC = GE::NC, KB = GE::KB, NH = GE::NH, CPT = GE::CPT, DHB = GE::DHB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* Wsm = smem + WOFF_W;
-  uint8_t* dGsm = smem + WOFF_DG;
-  uint8_t* dhout = smem + WOFF_DHOUT;
-  uint8_t* dhin = smem + WOFF_DHIN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WOFF_BARS);
+  uint8_t* Wsm = smem + GE::OFF_W;
+  uint8_t* dGsm = smem + GE::OFF_DG;
+  uint8_t* dhout = smem + GE::OFF_DHOUT;
+  uint8_t* dhin = smem + GE::OFF_DHIN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GE::OFF_BARS);
   uint64_t* w_full = bars;
   uint64_t* dh_full = bars + 1;           // [2]
   uint64_t* d_done = bars + 3;
@@ -234,20 +256,20 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_bwd_kernel(const __gri
     mbar_init(dh_ready, RW_EPW);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<64>(tmem_slot);
-  for (int i = threadIdx.x; i < 4096 / 16; i += RW_THREADS) reinterpret_cast<uint4*>(dGsm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 1) tmem_alloc<GE::TCOLS>(tmem_slot);
+  for (int i = threadIdx.x; i < KB * 2048 / 16; i += RW_THREADS) reinterpret_cast<uint4*>(dGsm)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp == 0 && elect_one()) {
-    mbar_expect_tx(w_full, 131072);
-    for (int h = 0; h < 4; ++h)
-      for (int kb = 0; kb < 2; ++kb)
-        tma_load_2d(&tmWT, w_full, Wsm + (h * 2 + kb) * 16384, r * 128 + kb * 64, dir * S + h * 128);
-    mbar_expect_tx(dh_full, RW_NC * RW_DHB);
-    mbar_expect_tx(dh_full + 1, RW_NC * RW_DHB);
+    mbar_expect_tx(w_full, NH * KB * 16384);
+    for (int h = 0; h < NH; ++h)
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d(&tmWT, w_full, Wsm + (h * KB + kb) * 16384, r * GE::G + kb * 64, dir * S + h * 128);
+    mbar_expect_tx(dh_full, NC * DHB);
+    mbar_expect_tx(dh_full + 1, NC * DHB);
   }
   cluster_sync_all();
 
@@ -256,11 +278,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_bwd_kernel(const __gri
       const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
       const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
       for (int s = 0; s + 1 < n_steps; ++s) {
-        uint8_t* slot = p.ring + ((size_t)(s % RW_RING) * n_cta + cta) * RW_SLOT;
+        uint8_t* slot = p.ring + ((size_t)(s % RW_RING) * n_cta + cta) * GE::SLOT;
         mbar_wait_t(dh_ready, s & 1);
-        bulk_store_wait(slot, dhout, RW_NC * RW_DHB);
-        for (int d = 0; d < RW_NC; ++d)
-          bulk_load_mc(dhin + ((s & 1) * RW_NC + r) * RW_DHB, slot + d * RW_DHB, RW_DHB, dh_full + (s & 1), (uint16_t)(1u << d));
+        RW_STAMP(8);
+        bulk_store_wait(slot, dhout, NC * DHB);
+        RW_STAMP(9);
+        for (int d = 0; d < NC; ++d)
+          bulk_load_mc(dhin + ((s & 1) * NC + r) * DHB, slot + d * DHB, DHB, dh_full + (s & 1), (uint16_t)(1u << d));
+        RW_STAMP(10);
       }
     }
     __syncwarp();
@@ -270,41 +295,49 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_bwd_kernel(const __gri
       mbar_wait_t(w_full, 0);
       for (int s = 0; s + 1 < n_steps; ++s) {
         mbar_wait_t(dg_ready, s & 1);
+        RW_STAMP(2);
         tc_fence_after();
         const uint32_t w0 = smem_u32(Wsm), g0 = smem_u32(dGsm);
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
+        for (int h = 0; h < NH; ++h)
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)
-            mma_bf16_ss(tmem + h * RW_NT, umma_desc_k128(w0 + (h * 2 + (kk >> 2)) * 16384) + (uint64_t)((kk & 3) * 2),
+          for (int kk = 0; kk < 4 * KB; ++kk)
+            mma_bf16_ss(tmem + h * RW_NT, umma_desc_k128(w0 + (h * KB + (kk >> 2)) * 16384) + (uint64_t)((kk & 3) * 2),
                         umma_desc_k128(g0 + (kk >> 2) * 2048) + (uint64_t)((kk & 3) * 2), idesc, kk != 0);
         mma_commit(d_done);
+        RW_STAMP(3);
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int cw = warp - 4;                       // utterance slot of this warp's cells; lane = unit of the CTA
-    const int unit = 32 * r + lane;
+    const int cw = warp - 4;                       // utterance slot of this warp's cells; lane (+ 32) = unit of the CTA
     const int n = b0 + cw;
     const bool inr = n < p.n_batch;
     const int len = inr ? (p.lens ? p.lens[n] : INT_MAX) : 0;
     const size_t rowb = (size_t)(inr ? n : 0) * p.rs_batch;
-    const size_t gcol = (size_t)dir * 4 * S + (size_t)unit * 4, hcol = (size_t)dir * S + unit;
-    float dcreg = 0.f, bsum[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 a_n = make_float4(0.f, 0.f, 0.f, 0.f);
-    float c_n = 0.f, cp_n = 0.f, dh_n = 0.f;
+    const size_t gcol0 = (size_t)dir * 4 * S + (size_t)(UNITS * r) * 4, hcol0 = (size_t)dir * S + UNITS * r;
+    float dcreg[CPT], bsum[CPT][4];
+    float4 a_n[CPT];
+    float c_n[CPT], cp_n[CPT], dh_n[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { dcreg[j] = 0.f; bsum[j][0] = bsum[j][1] = bsum[j][2] = bsum[j][3] = 0.f; }
     // the backward chain walks the steps in the opposite order of the forward pass of its direction
     auto fetch = [&](int s_) {
       const int t_ = dir == 0 ? n_steps - 1 - s_ : s_;
       const int tp_ = dir == 0 ? t_ - 1 : t_ + 1;
-      a_n = make_float4(0.f, 0.f, 0.f, 0.f);
-      c_n = 0.f; cp_n = 0.f; dh_n = 0.f;
-      if (t_ < len) {
-        const size_t row = (size_t)t_ * p.rs_seq + rowb;
-        a_n = __ldcs(reinterpret_cast<const float4*>(p.xp + row * 8 * S + gcol));
-        dh_n = __ldcs(p.dhout + row * 2 * S + hcol);
-        c_n = __ldg(p.cbuf + row * 2 * S + hcol);
-        if (tp_ >= 0 && tp_ < n_steps && tp_ < len) cp_n = __ldg(p.cbuf + ((size_t)tp_ * p.rs_seq + rowb) * 2 * S + hcol);
+      const bool v = t_ < len, pv_ = v && tp_ >= 0 && tp_ < n_steps && tp_ < len;
+      const size_t row = (size_t)t_ * p.rs_seq + rowb, rowp = (size_t)(pv_ ? tp_ : 0) * p.rs_seq + rowb;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int ul = lane + 32 * j;
+        a_n[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        c_n[j] = 0.f; cp_n[j] = 0.f; dh_n[j] = 0.f;
+        if (v) {
+          a_n[j] = __ldcs(reinterpret_cast<const float4*>(p.xp + row * 8 * S + gcol0 + (size_t)ul * 4));
+          dh_n[j] = __ldcs(p.dhout + row * 2 * S + hcol0 + ul);
+          c_n[j] = __ldg(p.cbuf + row * 2 * S + hcol0 + ul);
+          if (pv_) cp_n[j] = __ldg(p.cbuf + rowp * 2 * S + hcol0 + ul);
+        }
       }
     };
     fetch(0);
@@ -313,72 +346,94 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_bwd_kernel(const __gri
       const int tp = dir == 0 ? t - 1 : t + 1;
       const bool valid = t < len;
       const bool pv = valid && tp >= 0 && tp < n_steps && tp < len;
-      const float4 a = a_n;
-      const float cv = c_n, cpv = cp_n;
-      float dh = dh_n;
+      float4 a[CPT];
+      float cv[CPT], cpv[CPT], dh[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { a[j] = a_n[j]; cv[j] = c_n[j]; cpv[j] = cp_n[j]; dh[j] = dh_n[j]; }
       if (s + 1 < n_steps) fetch(s + 1);
       if (s > 0) {
         mbar_wait_t(dh_full + ((s - 1) & 1), ((s - 1) >> 1) & 1);
-        if (threadIdx.x == 128 && s + 2 < n_steps) mbar_expect_tx(dh_full + ((s - 1) & 1), RW_NC * RW_DHB);
-        const uint8_t* base = dhin + ((s - 1) & 1) * RW_NC * RW_DHB + cw * 64 + lane * 2;
-        float acc = 0.f;
+        if (threadIdx.x == 128) RW_STAMP(1);
+        if (threadIdx.x == 128 && s + 2 < n_steps) mbar_expect_tx(dh_full + ((s - 1) & 1), NC * DHB);
+        const uint8_t* base = dhin + ((s - 1) & 1) * NC * DHB + cw * (UNITS * 2) + lane * 2;
 #pragma unroll
-        for (int src = 0; src < RW_NC; ++src) acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + src * RW_DHB));
-        dh += acc;
+        for (int j = 0; j < CPT; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int src = 0; src < NC; ++src) acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + src * DHB + j * 64));
+          dh[j] += acc;
+        }
       }
-      float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-      float dco = 0.f;
-      if (valid) {
-        const float tc_ = tanh_apx(cv);
-        const float dc = fmaf(dh * a.w, 1.f - tc_ * tc_, dcreg);
-        dg.w = dh * tc_ * a.w * (1.f - a.w);
-        dg.x = dc * a.z * a.x * (1.f - a.x);
-        dg.z = dc * a.x * (1.f - a.z * a.z);
-        dg.y = pv ? dc * cpv * a.y * (1.f - a.y) : 0.f;
-        dco = dc * a.y;
+      uint2 pk[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dco = 0.f;
+        if (valid) {
+          const float tc_ = tanh_apx(cv[j]);
+          const float dc = fmaf(dh[j] * a[j].w, 1.f - tc_ * tc_, dcreg[j]);
+          dg.w = dh[j] * tc_ * a[j].w * (1.f - a[j].w);
+          dg.x = dc * a[j].z * a[j].x * (1.f - a[j].x);
+          dg.z = dc * a[j].x * (1.f - a[j].z * a[j].z);
+          dg.y = pv ? dc * cpv[j] * a[j].y * (1.f - a[j].y) : 0.f;
+          dco = dc * a[j].y;
+        }
+        dcreg[j] = dco;
+        bsum[j][0] += dg.x; bsum[j][1] += dg.y; bsum[j][2] += dg.z; bsum[j][3] += dg.w;
+        const __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
+        pk[j].x = *reinterpret_cast<const uint32_t*>(&b01);
+        pk[j].y = *reinterpret_cast<const uint32_t*>(&b23);
+        // operand tile: row = utterance slot, gate column 4 ul + g of the CTA's G: k-block ul / 16, 16-byte chunk (ul % 16) / 2
+        const int ul = lane + 32 * j;
+        *reinterpret_cast<uint2*>(dGsm + (ul >> 4) * 2048 + cw * 128 + ((((ul & 15) >> 1) ^ (cw & 7)) << 4) + (ul & 1) * 8) = pk[j];
       }
-      dcreg = dco;
-      bsum[0] += dg.x; bsum[1] += dg.y; bsum[2] += dg.z; bsum[3] += dg.w;
-      const __nv_bfloat162 b01 = __floats2bfloat162_rn(dg.x, dg.y), b23 = __floats2bfloat162_rn(dg.z, dg.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&b01);
-      pk.y = *reinterpret_cast<const uint32_t*>(&b23);
-      *reinterpret_cast<uint2*>(dGsm + (lane >> 4) * 2048 + cw * 128 + ((((lane & 15) >> 1) ^ (cw & 7)) << 4) + (lane & 1) * 8) = pk;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(dg_ready);
-      if (inr) *reinterpret_cast<uint2*>(p.xb + ((size_t)t * p.rs_seq + rowb) * 8 * S + gcol) = pk;
+      if (threadIdx.x == 128) RW_STAMP(4);
+      if (inr) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          *reinterpret_cast<uint2*>(p.xb + ((size_t)t * p.rs_seq + rowb) * 8 * S + gcol0 + (size_t)(lane + 32 * j) * 4) = pk[j];
+      }
       if (s + 1 < n_steps) {
         mbar_wait_t(d_done, s & 1);
+        if (threadIdx.x == 128) RW_STAMP(5);
         tc_fence_after();
-        const int sp = warp & 3, cgrp = cw >> 2;
-        uint32_t v[4][4];
+        const int sp = warp & 3, cgrp = cw >> 2;   // TMEM sub-partition = 32 units; this warp converts 4 utterance columns
+        uint32_t v[NH][4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) tmem_ld4(tmem + ((uint32_t)(sp * 32) << 16) + (uint32_t)(h * RW_NT + cgrp * 4), v[h]);
+        for (int h = 0; h < NH; ++h) tmem_ld4(tmem + ((uint32_t)(sp * 32) << 16) + (uint32_t)(h * RW_NT + cgrp * 4), v[h]);
         tmem_ld_wait();
         tc_fence_before();
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
+        for (int h = 0; h < NH; ++h) {
+          const int unit = 128 * h + 32 * sp + lane;             // unit inside the direction
+          uint8_t* dst = dhout + (unit / UNITS) * DHB + (unit % UNITS) * 2;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<__nv_bfloat16*>(dhout + (h * 4 + sp) * RW_DHB + (cgrp * 4 + c) * 64 + lane * 2) =
-                __float2bfloat16_rn(__uint_as_float(v[h][c]));
+            *reinterpret_cast<__nv_bfloat16*>(dst + (cgrp * 4 + c) * (UNITS * 2)) = __float2bfloat16_rn(__uint_as_float(v[h][c]));
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(dh_ready);
+        if (threadIdx.x == 128) RW_STAMP(6);
       }
     }
     if (p.dbias) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) atomicAdd(p.dbias + gcol + g, bsum[g]);
+      for (int j = 0; j < CPT; ++j)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) atomicAdd(p.dbias + gcol0 + (size_t)(lane + 32 * j) * 4 + g, bsum[j][g]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<64>(tmem);
+  if (warp == 1) tmem_dealloc<GE::TCOLS>(tmem);
   cluster_sync_all();
 }
 
+long long* g_rw_dbg = nullptr;
 struct RwRing { cudaStream_t st; int dev; uint8_t* buf; };
 RwRing g_rw_rings[16];
 int g_rw_nrings = 0;
@@ -395,19 +450,22 @@ uint8_t* rw_ring_for(cudaStream_t st) {
 }
 
 template <typename Kern>
-int rw_query(Kern kern, int smem_bytes) {
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
-      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+int rw_query(Kern kern, int smem_bytes, int cluster) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (cluster > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(RW_NC, 2, 1);
+  cfg.gridDim = dim3(cluster, 2, 1);
   cfg.blockDim = dim3(RW_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = RW_NC;
+  at[0].val.clusterDim.x = cluster;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
@@ -416,15 +474,22 @@ int rw_query(Kern kern, int smem_bytes) {
   if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
   return nc;
 }
-int g_rw_cap[2] = {-1, -1};
-int rw_capacity(int backward) {
-  const int w = backward ? 1 : 0;
-  if (g_rw_cap[w] < 0) g_rw_cap[w] = backward ? rw_query(rec_wide_bwd_kernel, RWB_SMEM) : rw_query(rec_wide_fwd_kernel, RWF_SMEM);
-  return g_rw_cap[w];
+// co-resident cluster capacity: [0] wide forward, [1] wide backward (S = 512), [2] / [3] K-split backward at S = 256 / 128
+int g_rw_cap[4] = {-1, -1, -1, -1};
+int rw_capacity(int which) {
+  if (g_rw_cap[which] < 0) {
+    switch (which) {
+      case 0: g_rw_cap[0] = rw_query(rec_wide_fwd_kernel, RWF_SMEM, RW_NC); break;
+      case 1: g_rw_cap[1] = rw_query(rec_ks_bwd_kernel<512, 32>, KsGeom<512, 32>::SMEM, 16); break;
+      case 2: g_rw_cap[2] = rw_query(rec_ks_bwd_kernel<256, 64>, KsGeom<256, 64>::SMEM, 4); break;
+      default: g_rw_cap[3] = rw_query(rec_ks_bwd_kernel<128, 64>, KsGeom<128, 64>::SMEM, 2); break;
+    }
+  }
+  return g_rw_cap[which];
 }
 
 template <typename Kern>
-int rw_launch(Kern kern, int smem_bytes, dim3 grid, cudaStream_t st, const CUtensorMap& tm, const RecWideP& p) {
+int rw_launch(Kern kern, int smem_bytes, dim3 grid, int cluster, cudaStream_t st, const CUtensorMap& tm, const RecWideP& p) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(RW_THREADS);
@@ -432,7 +497,7 @@ int rw_launch(Kern kern, int smem_bytes, dim3 grid, cudaStream_t st, const CUten
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = RW_NC;
+  at[0].val.clusterDim.x = cluster;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
@@ -441,18 +506,29 @@ int rw_launch(Kern kern, int smem_bytes, dim3 grid, cudaStream_t st, const CUten
   return 0;
 }
 
+int env_on(const char* name) {
+  const char* e = getenv(name);
+  return (e && e[0] == '0') ? 0 : 1;
+}
+
 }  // namespace
 
 // 1 when the 16-CTA cluster kernels can run this layer with every (direction, 16-utterance tile) cluster co-resident
 int rec_wide_supported(int S, int n_batch, int backward) {
   static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("SSASR_REC_WIDE");
-    on = (e && e[0] == '0') ? 0 : 1;
-  }
-  if (!on || S != RW_S || n_batch < 1) return 0;
+  if (on < 0) on = env_on("SSASR_REC_WIDE");
+  if (!on || !rec_cl_is_enabled() || S != RW_S || n_batch < 1) return 0;
   const int tiles = (n_batch + RW_NT - 1) / RW_NT;
-  return 2 * tiles <= rw_capacity(backward) ? 1 : 0;
+  return 2 * tiles <= rw_capacity(backward ? 1 : 0) ? 1 : 0;
+}
+
+// 1 when the K-split backward kernel (64 units per CTA, 16-row tiles) can run this layer with every cluster co-resident
+int rec_ks_supported(int S, int n_batch) {
+  static int on = -1;
+  if (on < 0) on = env_on("SSASR_REC_KSPLIT");
+  if (!on || !rec_cl_is_enabled() || (S != 256 && S != 128) || n_batch < 1) return 0;
+  const int tiles = (n_batch + RW_NT - 1) / RW_NT;
+  return (2 * tiles <= rw_capacity(S == 256 ? 2 : 3) && 2 * tiles * (S / 64) <= 148) ? 1 : 0;
 }
 
 int rec_wide_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
@@ -467,22 +543,33 @@ int rec_wide_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, fl
   int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 128);
   if (rc) return rc;
   ProfScope ps(F_REC_TC_FWD, st);
-  return rw_launch(rec_wide_fwd_kernel, RWF_SMEM, dim3(RW_NC, 2, (n_batch + RW_NT - 1) / RW_NT), st, tmW, p);
+  return rw_launch(rec_wide_fwd_kernel, RWF_SMEM, dim3(RW_NC, 2, (n_batch + RW_NT - 1) / RW_NT), RW_NC, st, tmW, p);
 }
 
+// K-split backward: S = 512 (16-CTA clusters of 32 units) or S = 256 / 128 (clusters of S / 64 CTAs, 64 units each)
 int rec_wide_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,
                  int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, float* dbias) {
-  SSASR_REQUIRE(rec_wide_supported(S, n_batch, 1), "rec_wide_bwd: unsupported shape S=%d n_batch=%d", S, n_batch);
+  SSASR_REQUIRE(S == 512 ? rec_wide_supported(S, n_batch, 1) : rec_ks_supported(S, n_batch),
+                "rec_wide_bwd: unsupported shape S=%d n_batch=%d", S, n_batch);
   RecWideP p = {};
   p.xp = act; p.cbuf = const_cast<float*>(cbuf); p.xb = (__nv_bfloat16*)dgb; p.dhout = dhout; p.dbias = dbias; p.lens = lens;
   p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
   p.ring = rw_ring_for(st);
+  p.dbg = g_rw_dbg;
   SSASR_REQUIRE(p.ring != nullptr, "rec_wide_bwd: cannot allocate the exchange ring");
   CUtensorMap tmWT;
   int rc = make_tmap_bf16(&tmWT, whhT_bf, 2 * S, 4 * S, 4 * S, 128);
   if (rc) return rc;
+  const int tiles = (n_batch + RW_NT - 1) / RW_NT;
   ProfScope ps(F_REC_TC_BWD, st);
-  return rw_launch(rec_wide_bwd_kernel, RWB_SMEM, dim3(RW_NC, 2, (n_batch + RW_NT - 1) / RW_NT), st, tmWT, p);
+  if (S == 512) return rw_launch(rec_ks_bwd_kernel<512, 32>, KsGeom<512, 32>::SMEM, dim3(16, 2, tiles), 16, st, tmWT, p);
+  if (S == 256) return rw_launch(rec_ks_bwd_kernel<256, 64>, KsGeom<256, 64>::SMEM, dim3(4, 2, tiles), 4, st, tmWT, p);
+  return rw_launch(rec_ks_bwd_kernel<128, 64>, KsGeom<128, 64>::SMEM, dim3(2, 2, tiles), 2, st, tmWT, p);
 }
 
 }  // namespace ssasr
+
+extern "C" {
+// debug: device buffer [n_seq][12] of clock64 stamps written by CTA (0,0,0) of the next K-split backward launches
+void ssasr_rec_wide_set_debug(long long* dev_buf) { ssasr::g_rw_dbg = dev_buf; }
+}

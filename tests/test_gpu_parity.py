@@ -472,7 +472,7 @@ def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
     x0 = torch.randn(B, T, K, generator=g)
     x0 = x0 * (torch.arange(T)[None, :, None] < torch.tensor(lens)[:, None, None])
     res = {}
-    stamps = torch.zeros(T, 12, dtype=torch.int64, device=DEV)
+    stamps = torch.zeros(T + 2, 12, dtype=torch.int64, device=DEV)     # one row per step; odd T runs T + 1 (padded) steps
     try:
         for name, rows, on in (('quad16', 16, 1), ('quad32', 32, 1), ('cl8', 0, 1), ('counter', 0, 0)):
             lib.ssasr_rec_q_set_rows(rows)
