@@ -58,6 +58,58 @@ class FbankPlan:
         return out
 
 
+    def run_host(self, audio_host, out_host, n_parts=8):
+        """Host buffers in, host buffers out (both pinned): the utterances are processed in `n_parts` contiguous groups whose
+        host -> device copy, kernel and device -> host copy run on three streams, so the PCIe transfers in both directions
+        overlap each other and the kernel (what the preprocessing loop of preprocess.py:62-80 needs: waveforms come from and
+        features go back to host memory).  Returns after enqueuing; `out_host` is complete after `self.sync()`."""
+        lib = _lib.load()
+        dev = self.off_d.device
+        assert audio_host.is_pinned() and out_host.is_pinned() and audio_host.numel() == self.n_samples
+        if getattr(self, '_pipe', None) is None:
+            self._pipe = {'s_in': torch.cuda.Stream(dev), 's_out': torch.cuda.Stream(dev),
+                          'audio': torch.empty(self.n_samples, device=dev, dtype=torch.float32),
+                          'fb': torch.empty(self.foff[-1], self.n_mels, device=dev, dtype=torch.float32),
+                          'computed': None, 'copied_out': None}
+        pp = self._pipe
+        cur = torch.cuda.current_stream(dev)
+        out_flat = out_host.view(-1, self.n_mels)
+        off = self.off_d_host if hasattr(self, 'off_d_host') else None
+        if off is None:
+            off = self.off_d_host = [int(v) for v in self.off_d.tolist()]
+        if pp['computed'] is not None:
+            pp['s_in'].wait_event(pp['computed'])          # the previous call's kernels have read the device audio buffer
+        if pp['copied_out'] is not None:
+            cur.wait_event(pp['copied_out'])               # ... and its features have left the device output buffer
+        per = (self.n_utt + n_parts - 1) // n_parts
+        for u0 in range(0, self.n_utt, per):
+            u1 = min(self.n_utt, u0 + per)
+            with torch.cuda.stream(pp['s_in']):
+                pp['audio'][off[u0]:off[u1]].copy_(audio_host[off[u0]:off[u1]], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(pp['s_in'])
+            cur.wait_event(ev_in)
+            for c0 in range(u0, u1, MAX_UTT_PER_CALL):
+                c1 = min(u1, c0 + MAX_UTT_PER_CALL)
+                check(lib.ssasr_fbank(ptr(pp['audio']), self.off_d.data_ptr() + 8 * c0, c1 - c0, self.sample_rate, self.n_mels,
+                                      ptr(pp['fb']), self.foff_d.data_ptr() + 8 * c0, max(self.frames[c0:c1]), cur.cuda_stream),
+                      'ssasr_fbank')
+            ev_k = torch.cuda.Event()
+            ev_k.record(cur)
+            pp['computed'] = ev_k
+            with torch.cuda.stream(pp['s_out']):
+                pp['s_out'].wait_event(ev_k)
+                out_flat[self.foff[u0]:self.foff[u1]].copy_(pp['fb'][self.foff[u0]:self.foff[u1]], non_blocking=True)
+                ev_o = torch.cuda.Event()
+                ev_o.record(pp['s_out'])
+                pp['copied_out'] = ev_o
+        return out_host
+
+    def sync(self):
+        if getattr(self, '_pipe', None) is not None and self._pipe['copied_out'] is not None:
+            self._pipe['copied_out'].synchronize()
+
+
 def log_fbank_device(audio, offsets, sample_rate, n_mels=None, out=None):
     """audio: 1-D float32 CUDA tensor holding all utterances back to back; offsets: int64 CPU tensor/list
     [n_utt+1].  Returns (fbank [total_frames, n_mels] CUDA float32, frame_offsets list)."""

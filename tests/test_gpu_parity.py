@@ -103,6 +103,25 @@ def test_fbank_ragged_batch_and_edges():
         PP.log_fbank_batch([np.zeros(200, np.float32)], 16000, 80)  # numpy reflect pad needs > ws//2 samples
 
 
+def test_fbank_host_pipeline_matches_device_path():
+    """FbankPlan.run_host (pinned host buffers in and out, three streams, groups of utterances) == FbankPlan.run on the same
+    ragged batch, twice in a row (buffer reuse across calls)."""
+    from ss_asr_b200 import preprocess as PP
+    rs = np.random.RandomState(5)
+    lens = [int(v) for v in rs.randint(3000, 40000, size=37)]
+    off = [0]
+    for n in lens:
+        off.append(off[-1] + n)
+    plan = PP.FbankPlan(off, 16000, 80, device=DEV)
+    for rep in range(2):
+        host = torch.from_numpy((0.1 * rs.randn(off[-1])).astype(np.float32)).pin_memory()
+        want = plan.run(host.to(DEV)).cpu()
+        out = torch.empty(want.shape, dtype=torch.float32).pin_memory()
+        plan.run_host(host, out, n_parts=5)
+        plan.sync()
+        assert torch.equal(out, want)
+
+
 def test_fbank_full_size_properties():
     """C2 shape (160 000-sample utterances): linearity in the power domain and agreement with the oracle on
     sampled utterances."""
