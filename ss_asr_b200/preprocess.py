@@ -133,3 +133,19 @@ def log_fbank_batch(ys, sample_rate, n_mels=None, device='cuda'):
 def log_fbank(y, sample_rate):
     """Given a signal and a sample rate, the [num_frames, N_DIMS] float32 log mel filterbank (preprocess.py:187)."""
     return log_fbank_batch([y], sample_rate, N_DIMS)[0]
+
+
+def fbank_to_listener_batch(fb, frame_offsets):
+    """fbank -> Listener hand-off without the `.npy` round trip (preprocess.py:47-60 writes every utterance to disk zero-padded
+    to the data set's longest; ASRDataset reads it back): `fb` [total_frames, n_mels] as returned by `log_fbank_device` /
+    `FbankPlan.run` stays on the device and is re-laid-out as the zero-padded batch `x [B, T_max, n_mels]` the Listener takes,
+    utterances in decreasing length (the pack_padded_sequence contract, asr.py:413).
+    Returns (x, lens, order) with order[i] = index of the i-th batch row in the original utterance order."""
+    n = len(frame_offsets) - 1
+    lens_all = [int(frame_offsets[i + 1]) - int(frame_offsets[i]) for i in range(n)]
+    order = sorted(range(n), key=lambda i: -lens_all[i])
+    lens = [lens_all[i] for i in order]
+    x = fb.new_zeros(n, lens[0], fb.shape[1])
+    for row, i in enumerate(order):                     # B device-to-device copies (data movement only)
+        x[row, :lens[row]].copy_(fb[int(frame_offsets[i]):int(frame_offsets[i + 1])])
+    return x, lens, order

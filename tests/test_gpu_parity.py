@@ -122,6 +122,26 @@ def test_fbank_host_pipeline_matches_device_path():
         assert torch.equal(out, want)
 
 
+def test_fbank_to_listener_handoff():
+    """fbank output -> padded, length-sorted Listener batch on the device == the reference's disk format read back
+    (zero_pad of preprocess.py:253-269 + the prepare_x length count)."""
+    from ss_asr_b200 import preprocess as PP
+    from ss_asr_b200.dataset import prepare_x
+    rs = np.random.RandomState(2)
+    ys = [(0.1 * rs.randn(n)).astype(np.float32) for n in (9000, 20000, 4100, 15000)]
+    off = [0]
+    for y in ys:
+        off.append(off[-1] + len(y))
+    fb, foff = PP.log_fbank_device(torch.from_numpy(np.concatenate(ys)).to(DEV), off, 16000, 40)
+    x, lens, order = PP.fbank_to_listener_batch(fb, foff)
+    assert order == [1, 3, 0, 2] and lens == sorted(lens, reverse=True) and x.shape == (4, lens[0], 40)
+    padded = np.zeros((4, lens[0], 40))                             # what preprocess.py would have written, per utterance
+    for row, i in enumerate(order):
+        padded[row, :lens[row]] = fb[foff[i]:foff[i + 1]].cpu().numpy()
+    x_ref, lens_ref = prepare_x(torch.from_numpy(padded).unsqueeze(0), DEV)
+    assert lens_ref == lens and torch.equal(x_ref, x)
+
+
 def test_fbank_full_size_properties():
     """C2 shape (160 000-sample utterances): linearity in the power domain and agreement with the oracle on
     sampled utterances."""
