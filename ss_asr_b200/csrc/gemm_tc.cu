@@ -177,6 +177,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tmem_dealloc<BN>(tmem_base);
 }
 
+// ---- persistent variant for the large products (input projections, dgrad): one CTA per SM walks 128 x 256 output tiles
+// (N fastest: the CTAs that share a 128-row block of A run at the same time, B = the weights stays in L2), 4 x 48 KB TMA stages,
+// and TWO TMEM accumulators (2 x 256 columns) so that the epilogue of tile i (tcgen05.ld -> transpose -> coalesced stores, as
+// above) runs under the MMAs of tile i + 1 instead of relying on a second co-resident CTA.  Twice the operand reuse per tile
+// of the 128 x 128 kernel (48 KB of operands per 2 x 128 x 256 x 64 MACs).
+constexpr int GP_BN = 256;
+constexpr int GP_STAGES = 4;
+constexpr int GP_A_BYTES = GT_BM * GT_BK * 2;
+constexpr int GP_B_BYTES = GP_BN * GT_BK * 2;
+constexpr int GP_STAGE_BYTES = GP_A_BYTES + GP_B_BYTES;
+constexpr int GP_EPW = 8;                                             // epilogue warps: two per TMEM sub-partition, 128 columns each
+constexpr int GP_THREADS = 128 + 32 * GP_EPW;
+constexpr int GP_STAGING_OFF = GP_STAGES * GP_STAGE_BYTES;          // one 4 KB transpose tile per epilogue warp
+constexpr int GP_BAR_OFF = GP_STAGING_OFF + GP_EPW * 4096;
+constexpr int GP_TOTAL = GP_BAR_OFF + (2 * GP_STAGES + 4) * 8 + 16;
+
+__global__ void __launch_bounds__(GP_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+                       int ldc, const float* __restrict__ bias, int M, int N, int K, int a_koff, int b_koff, int accumulate,
+                       int act_tanh, int n_mt, int n_nt) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GP_BAR_OFF);
+  uint64_t* empty_bar = full_bar + GP_STAGES;
+  uint64_t* tfull = empty_bar + GP_STAGES;       // [2]
+  uint64_t* tempty = tfull + 2;                  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5;
+  const int num_k = (K + GT_BK - 1) / GT_BK;
+  const int total = n_mt * n_nt;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < GP_STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tfull + 1, 1);
+    mbar_init(tempty, GP_EPW);
+    mbar_init(tempty + 1, GP_EPW);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (tile / n_nt) * GT_BM, n0 = (tile % n_nt) * GP_BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % GP_STAGES;
+          mbar_wait(empty_bar + s, ((it / GP_STAGES) & 1) ^ 1);
+          mbar_expect_tx(full_bar + s, GP_STAGE_BYTES);
+          uint8_t* st = smem + s * GP_STAGE_BYTES;
+          tma_load_2d(&tmA, full_bar + s, st, a_koff + kb * GT_BK, m0);
+          tma_load_2d(&tmB, full_bar + s, st + GP_A_BYTES, b_koff + kb * GT_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GT_BM, GP_BN);
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+        const int acc = tl & 1;
+        mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator (two tiles ago)
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * GP_BN);
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % GP_STAGES;
+          mbar_wait(full_bar + s, (it / GP_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * GP_STAGE_BYTES);
+          const uint64_t da = umma_desc_k128(a_addr), db = umma_desc_k128(a_addr + GP_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GT_BK / 16; ++k) mma_bf16_ss(d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          mma_commit(empty_bar + s);
+        }
+        mma_commit(tfull + acc);
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = (warp - 4) & 3, ch = (warp - 4) >> 2;      // TMEM sub-partition, column half of the tile
+    float* stage = reinterpret_cast<float*>(smem + GP_STAGING_OFF) + (warp - 4) * 1024;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+      const int m0 = (tile / n_nt) * GT_BM, n0 = (tile % n_nt) * GP_BN;
+      const int acc = tl & 1;
+      mbar_wait(tfull + acc, (tl >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = ch * (GP_BN / 2); c0 < (ch + 1) * (GP_BN / 2); c0 += 32) {
+        if (n0 + c0 >= N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * GP_BN + c0), v);
+        tmem_ld_wait();
+        epi_chunk<false>(stage, v, C, ldc, m0 + ew * 32, n0 + c0, M, N, bias, accumulate, act_tanh);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(tempty + acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 // ---- fp32-accurate variant ("tf32x3"): C = A·B^T with fp32 operands split as x = hi + lo, hi = the upper 19 bits the
 // tf32 tensor core reads, lo = x - hi (computed once per operand by split_lo_kernel); three MMAs per K step
 // (hi·hi + hi·lo + lo·hi) accumulate in the same TMEM tile.  Dropped terms are O(2^-21) relative: fp32-level accuracy
@@ -609,6 +723,36 @@ static int launch_gemm_tc(cudaStream_t st, int M, int N, int K, const void* A, l
   return 0;
 }
 
+static int gemm_persist_on() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSASR_GEMM_PERSIST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
+static int launch_gemm_tc_persist(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B,
+                                  long long ldb, int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, M, (long long)a_koff + K, lda, GT_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, N, (long long)b_koff + K, ldb, GP_BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_TOTAL + 1024));
+    attr_set = true;
+  }
+  const int n_mt = (M + GT_BM - 1) / GT_BM, n_nt = (N + GP_BN - 1) / GP_BN;
+  const int total = n_mt * n_nt;
+  const int grid = total < sm_count() ? total : sm_count();
+  ProfScope ps(F_GEMM_TC, st);
+  gemm_tc_persist_kernel<<<grid, GP_THREADS, GP_TOTAL + 1024, st>>>(tmA, tmB, C, ldc, bias, M, N, K, a_koff, b_koff, accumulate, act_tanh,
+                                                             n_mt, n_nt);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+
 int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long lda, int a_koff, const void* B, long long ldb,
                  int b_koff, float* C, int ldc, const float* bias, int accumulate, int act_tanh, int splits) {
   if (M <= 0 || N <= 0) return 0;
@@ -620,6 +764,10 @@ int gemm_bf16_tc(cudaStream_t st, int M, int N, int K, const void* A, long long 
   const long long tiles128 = (long long)((M + GT_BM - 1) / GT_BM) * ((N + 127) / 128);
   if (tiles128 < sm_count() / 2 && N >= 64)
     return launch_gemm_tc<32, 4>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh, splits);
+  // large products: persistent 128 x 256 tiles with double-buffered accumulators (at least two tiles per SM, full-width tiles)
+  const long long tiles256 = (long long)((M + GT_BM - 1) / GT_BM) * ((N + GP_BN - 1) / GP_BN);
+  if (gemm_persist_on() && tiles256 >= 2LL * sm_count() && N % 64 == 0 && N >= GP_BN && K >= 2 * GT_BK)
+    return launch_gemm_tc_persist(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh);
   return launch_gemm_tc<128, 3>(st, M, N, K, A, lda, a_koff, B, ldb, b_koff, C, ldc, bias, accumulate, act_tanh, 1);
 }
 

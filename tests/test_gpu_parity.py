@@ -344,7 +344,8 @@ def test_teacher_forcing_draws_follow_python_rng():
 # ------------------------------------------------------------------------------------------------ bf16 / tcgen05 path
 @pytest.mark.parametrize('M,N,K,ak,bk', [(128, 128, 64, 0, 0), (300, 200, 80, 0, 0), (1024, 2048, 1024, 0, 0),
                                          (128, 128, 512, 16, 0), (256, 128, 1000, 0, 8), (2048, 80, 4096, 0, 0), (50, 256, 333, 0, 0),
-                                         (8242, 1576, 328, 0, 0), (16384 + 128, 1024, 520, 8, 16)])   # many tiles per SM, ragged edges
+                                         (8242, 1576, 328, 0, 0), (16384 + 128, 1024, 520, 8, 16),    # many tiles per SM, ragged edges
+                                         (20000, 768, 256, 0, 0), (40000 + 77, 320, 192, 0, 8)])       # persistent 128 x 256 kernel, partial N tile
 def test_gemm_bf16_tcgen05(M, N, K, ak, bk):
     """tcgen05+TMA GEMM against an fp64 product of the same bf16-rounded operands (fp32 accumulation tolerance)."""
     from ss_asr_b200 import _lib
