@@ -39,7 +39,7 @@ constexpr int SP_NC = 8;                  // CTAs per cluster
 constexpr int SP_MAXU = 24;               // utterances per cluster at most (TMEM: one 16-column accumulator per utterance)
 constexpr int SP_SD = 256;                // decoder state size
 constexpr int SP_M = 128;                 // attention MLP size
-constexpr int SP_TP = 64;                 // encoder frames per utterance (padded)
+constexpr int SP_TP = 64;                 // encoder frames per frame block; TPB = 1 or 4 blocks per utterance (T' <= 64 / 256)
 constexpr int SP_EPW = 16;                // epilogue warps
 constexpr int SP_THREADS = 128 + 32 * SP_EPW;     // warp 0 exchange, 1 MMA / TMEM, 2 ring producer, 3 idle, 4.. epilogue
 constexpr int SP_STAGE = 16384;           // ring stage: a phi k-block [128 m x 64 k], the psi~ tile [64 frames x 128 m] of an utterance
@@ -52,7 +52,7 @@ constexpr int SP_MAXOWN = 4;              // attention utterances per CTA at mos
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int OFF_W = 0;                          // W_hh slice: 4 k-blocks [128 rows x 128 B], 128-byte swizzle
 constexpr int OFF_AL = OFF_W + 65536;             // attention weights of the step [32 utterances x 64 frames] bf16, 128-byte swizzle
-constexpr int OFF_H = OFF_AL + 4096;              // h1 tile [2 buffers][8 producers][NT rows x 64 B], 64-byte swizzle
+constexpr int OFF_H = OFF_AL + 8192;              // (4 frame blocks x 16 rows at TPB = 4)  h1 tile [2 buffers][8 producers][NT rows x 64 B], 64-byte swizzle
 constexpr int OFF_RING = OFF_H + 32768;           // P / psi~ ring
 constexpr int OFF_HIMG = OFF_RING + SP_NSTAGE * SP_STAGE;
 constexpr int OFF_AIMG = OFF_HIMG + 2048;
@@ -95,7 +95,8 @@ struct SpellClP {
 // ------------------------------------------------------------------------------------------------
 // ATT = false: the same cluster recurrence WITHOUT the attention part -- gates = W_hh h(t-1) + xpre[b, t] -- used for the
 // layer-2 cell chain of the Speller (its input projection W_ih h1(t) is one batched GEMM per run of steps).
-template <int NT, bool ATT>
+// TPB: 64-frame blocks per utterance (1: T' <= 64; 4: T' <= 256, then with 16-row tiles and at most ONE attention utterance per CTA)
+template <int NT, bool ATT, int TPB>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmPhi,
                     const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmPsi, int w_col0, SpellClP p) {
@@ -127,7 +128,7 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const int b0 = blockIdx.z * p.per;      // first utterance of the cluster
   const int NU = min(p.per, p.B - b0);    // utterances of the cluster (>= 1 by construction of the grid)
   const int n_own = (ATT && NU > r) ? (NU - r + SP_NC - 1) / SP_NC : 0;    // attention utterances of this CTA: slots r, r + 8, ...
-  const int step_stages = 4 + n_own + NU;           // ring stages per step: 4 phi k-blocks, own psi~ tiles, all P tiles
+  const int step_stages = 4 + (n_own + NU) * TPB;   // ring stages per step: 4 phi k-blocks, own psi~ tiles, all P tiles
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_steps = p.t1 - p.t0;
 
@@ -153,7 +154,7 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  for (int i = threadIdx.x; i < 4096 / 16; i += SP_THREADS) reinterpret_cast<uint4*>(Al)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 8192 / 16; i += SP_THREADS) reinterpret_cast<uint4*>(Al)[i] = make_uint4(0u, 0u, 0u, 0u);
   // h1(t0 - 1) of the cluster's utterances -> buffer 1 of the tile (64-byte swizzle), zeros at t0 == 0 and in unused rows
   for (int i = threadIdx.x; i < NT * SP_SD / 2; i += SP_THREADS) {
     const int row = i >> 7, k = (i & 127) * 2;
@@ -177,7 +178,7 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     for (int kb = 0; kb < 4; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * 16384, w_col0 + kb * 64, r * 128);
     mbar_expect_tx(a_full, SP_NC * HBLK);
     mbar_expect_tx(a_full + 1, SP_NC * HBLK);
-    mbar_expect_tx(al_full, NU * 128);
+    mbar_expect_tx(al_full, NU * TPB * 128);
   }
   cluster_sync_all();                      // every CTA's barriers exist (and are armed) before any multicast can signal them
 
@@ -192,9 +193,10 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (ATT && n_own > 0) {
           mbar_wait_t(alpha_ready, s & 1);
           SP_STAMP(2);
-          bulk_store_wait(slot + 2048, aimg, n_own * 128);
-          for (int o = 0; o < n_own; ++o)      // row r + 8 o of the alpha tile
-            bulk_load_mc(Al + (r + 8 * o) * 128, slot + 2048 + o * 128, 128, al_full, cmask);
+          bulk_store_wait(slot + 2048, aimg, n_own * TPB * 128);
+          for (int o = 0; o < n_own; ++o)      // row r + 8 o of the alpha tile, one 128-byte piece per frame block
+            for (int f = 0; f < TPB; ++f)
+              bulk_load_mc(Al + f * (NT * 128) + (r + 8 * o) * 128, slot + 2048 + (o * TPB + f) * 128, 128, al_full, cmask);
         }
         mbar_wait_t(stage_ready, s & 1);
         SP_STAMP(5);
@@ -245,20 +247,21 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         }
         if (ATT) {
           mbar_wait_t(al_full, s & 1);      // the attention rows of every utterance of the cluster have landed
-          if (s + 1 < n_steps) mbar_expect_tx(al_full, NU * 128);
+          if (s + 1 < n_steps) mbar_expect_tx(al_full, NU * TPB * 128);
           SP_STAMP(3);
           tc_fence_after();
         }
         const uint32_t al0 = smem_u32(Al);
-        for (int u = 0; ATT && u < NU; ++u) {
-          const int pos = rp + 4 + n_own + u, stg = pos % SP_NSTAGE;
+        for (int i = 0; ATT && i < NU * TPB; ++i) {
+          const int u = i / TPB, f = i % TPB;
+          const int pos = rp + 4 + n_own * TPB + i, stg = pos % SP_NSTAGE;
           mbar_wait_t(r_full + stg, (pos / SP_NSTAGE) & 1);
           tc_fence_after();
           const uint64_t da = umma_desc_mn128(smem_u32(Ring + stg * SP_STAGE), 8192);
-          const uint64_t db = umma_desc_k128(al0 + (u >> 4) * 2048);
+          const uint64_t db = umma_desc_k128(al0 + f * (NT * 128) + (u >> 4) * 2048);
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4)
-            mma_bf16_ss(acc_u + 16 * u, da + (uint64_t)(k4 * 128), db + (uint64_t)(k4 * 2), idesc_p, k4 != 0);
+            mma_bf16_ss(acc_u + 16 * u, da + (uint64_t)(k4 * 128), db + (uint64_t)(k4 * 2), idesc_p, (f | k4) != 0);
           mma_commit(r_empty + stg);
         }
         mma_commit(g_done);
@@ -277,12 +280,14 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           uint8_t* dst = Ring + stg * SP_STAGE;
           if (i < 4) {                      // phi k-block i: [128 m x 64 k]
             tma_load_2d(&tmPhi, r_full + stg, dst, i * 64, 0);
-          } else if (i < 4 + n_own) {       // psi~ of own utterance i - 4 (slot r + 8 (i - 4)): two k-blocks of [64 frames x 64 m]
-            const int row = (b0 + r + 8 * (i - 4)) * p.Tp;
+          } else if (i < 4 + n_own * TPB) { // psi~ of own utterance o (slot r + 8 o), frame block f: two k-blocks of [64 frames x 64 m]
+            const int o = (i - 4) / TPB, f = (i - 4) % TPB;
+            const int row = (b0 + r + 8 * o) * p.Tp + 64 * f;
             tma_load_2d(&tmPsi, r_full + stg, dst, 0, row);
             tma_load_2d(&tmPsi, r_full + stg, dst + 8192, 64, row);
-          } else {                          // P of utterance u, this CTA's 128 gate rows: two blocks of [64 frames x 64 rows]
-            const int row = (b0 + (i - 4 - n_own)) * p.Tp;
+          } else {                          // P of utterance u, frame block f, this CTA's 128 gate rows: two blocks of [64 frames x 64 rows]
+            const int j = i - 4 - n_own * TPB;
+            const int row = (b0 + j / TPB) * p.Tp + 64 * (j % TPB);
             tma_load_2d(&tmP, r_full + stg, dst, r * 128, row);
             tma_load_2d(&tmP, r_full + stg, dst + 8192, r * 128 + 64, row);
           }
@@ -354,49 +359,65 @@ spell_cl_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             }
         }
         named_bar(1, 256);
-        // ---- energy of frame ja of own utterance ua: psi~ row (two k-block stages of the ring) . q ----
-        float e = -INFINITY;
+        // ---- energies of frames ja + 64 f of own utterance ua: psi~ rows (ring stages, one per frame block) . q ----
+        float e[TPB];
+#pragma unroll
+        for (int f = 0; f < TPB; ++f) e[f] = -INFINITY;
         if (att_on) {
-          const int pos = s * step_stages + 4 + ua, stg = pos % SP_NSTAGE;
-          mbar_wait_t(r_full + stg, (pos / SP_NSTAGE) & 1);
-          float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;      // four independent chains
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint8_t* row = Ring + stg * SP_STAGE + kb * 8192 + ja * 128;
-            const float* qq = qs + ua * SP_M + kb * 64;
+          for (int f = 0; f < TPB; ++f) {
+            const int pos = s * step_stages + 4 + ua * TPB + f, stg = pos % SP_NSTAGE;
+            mbar_wait_t(r_full + stg, (pos / SP_NSTAGE) & 1);
+            float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;      // four independent chains
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 w = *reinterpret_cast<const uint4*>(row + ((c ^ (ja & 7)) << 4));
-              const float4 qa = *reinterpret_cast<const float4*>(qq + c * 8), qb = *reinterpret_cast<const float4*>(qq + c * 8 + 4);
-              e0 = fmaf(bf_lo(w.x), qa.x, e0); e1 = fmaf(bf_hi(w.x), qa.y, e1);
-              e2 = fmaf(bf_lo(w.y), qa.z, e2); e3 = fmaf(bf_hi(w.y), qa.w, e3);
-              e0 = fmaf(bf_lo(w.z), qb.x, e0); e1 = fmaf(bf_hi(w.z), qb.y, e1);
-              e2 = fmaf(bf_lo(w.w), qb.z, e2); e3 = fmaf(bf_hi(w.w), qb.w, e3);
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint8_t* row = Ring + stg * SP_STAGE + kb * 8192 + ja * 128;
+              const float* qq = qs + ua * SP_M + kb * 64;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 w = *reinterpret_cast<const uint4*>(row + ((c ^ (ja & 7)) << 4));
+                const float4 qa = *reinterpret_cast<const float4*>(qq + c * 8), qb = *reinterpret_cast<const float4*>(qq + c * 8 + 4);
+                e0 = fmaf(bf_lo(w.x), qa.x, e0); e1 = fmaf(bf_hi(w.x), qa.y, e1);
+                e2 = fmaf(bf_lo(w.y), qa.z, e2); e3 = fmaf(bf_hi(w.y), qa.w, e3);
+                e0 = fmaf(bf_lo(w.z), qb.x, e0); e1 = fmaf(bf_hi(w.z), qb.y, e1);
+                e2 = fmaf(bf_lo(w.w), qb.z, e2); e3 = fmaf(bf_hi(w.w), qb.w, e3);
+              }
             }
+            e[f] = (ja + 64 * f < len_a) ? (e0 + e1) + (e2 + e3) : -INFINITY;
           }
-          e = (e0 + e1) + (e2 + e3);
-          if (ja >= len_a) e = -INFINITY;
         }
-        // ---- masked softmax over the utterance's 64 frames (two warps) ----
-        const float wm = warp_max(e);
+        // ---- masked softmax over the utterance's frames (two warps) ----
+        float em = e[0];
+#pragma unroll
+        for (int f = 1; f < TPB; ++f) em = fmaxf(em, e[f]);
+        const float wm = warp_max(em);
         if (lane == 0) red[ta >> 5] = wm;
         named_bar(1, 256);
         const float mx = fmaxf(red[ua * 2], red[ua * 2 + 1]);
-        const float ex = (e == -INFINITY) ? 0.f : expf(e - mx);
-        const float wsum = warp_sum(ex);
+        float ex[TPB], es = 0.f;
+#pragma unroll
+        for (int f = 0; f < TPB; ++f) {
+          ex[f] = (e[f] == -INFINITY) ? 0.f : expf(e[f] - mx);
+          es += ex[f];
+        }
+        const float wsum = warp_sum(es);
         if (lane == 0) red[8 + (ta >> 5)] = wsum;
         named_bar(1, 256);
         if (att_on) {
           const float sum = red[8 + ua * 2] + red[8 + ua * 2 + 1];
-          const float al = sum > 0.f ? ex * (1.0f / sum) : 0.f;
-          if (ja < p.Tp) p.alpha[(size_t)ba * p.al_ldb + (size_t)t * p.al_ldt + ja] = al;
-          *reinterpret_cast<__nv_bfloat16*>(aimg + ua * 128 + (((ja >> 3) ^ (sa_slot & 7)) << 4) + (ja & 7) * 2) = __float2bfloat16_rn(al);
+          const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+#pragma unroll
+          for (int f = 0; f < TPB; ++f) {
+            const float al = ex[f] * inv;
+            if (ja + 64 * f < p.Tp) p.alpha[(size_t)ba * p.al_ldb + (size_t)t * p.al_ldt + ja + 64 * f] = al;
+            *reinterpret_cast<__nv_bfloat16*>(aimg + (ua * TPB + f) * 128 + (((ja >> 3) ^ (sa_slot & 7)) << 4) + (ja & 7) * 2) = __float2bfloat16_rn(al);
+          }
         }
         fence_proxy_async();
         named_bar(1, 256);
         if (ta == 0) {
           mbar_arrive(alpha_ready);
-          for (int i = 0; i < n_own; ++i) mbar_arrive(r_empty + (s * step_stages + 4 + i) % SP_NSTAGE);   // psi~ stages are free
+          for (int i = 0; i < n_own * TPB; ++i) mbar_arrive(r_empty + (s * step_stages + 4 + i) % SP_NSTAGE);   // psi~ stages are free
         }
       }
       // ---- layer-1 cells of (unit, slots 4 cg + gp + 16 j): gates = acc_h + context column of the slot's accumulator + G_emb ----
@@ -506,7 +527,7 @@ struct SpellClBwdP {
     if (p.dbg && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 128) p.dbg[(size_t)s * 8 + (idx)] = clock64(); \
   } while (0)
 
-template <int NT, bool ATT>
+template <int NT, bool ATT, int TPB>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmPhiS,
                     const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmPsi, int w_col0, SpellClBwdP p) {
@@ -545,7 +566,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const int b0 = blockIdx.z * p.per;
   const int NU = min(p.per, p.B - b0);
   const int n_own = (ATT && NU > r) ? (NU - r + SP_NC - 1) / SP_NC : 0;
-  const int step_stages = ATT ? NU + n_own : 0;       // ring stages per step: all P tiles, then the own psi~ tiles
+  const int step_stages = ATT ? (NU + n_own) * TPB : 0;   // ring stages per step: all P tiles, then the own psi~ tiles (n_own * TPB <= 4)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_steps = p.t1 - p.t0;
 
@@ -590,7 +611,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     mbar_expect_tx(dh_full, SP_NC * DHB);
     mbar_expect_tx(dh_full + 1, SP_NC * DHB);
     if (ATT) {
-      mbar_expect_tx(da_full, SP_NC * n_own * 256);
+      mbar_expect_tx(da_full, SP_NC * n_own * TPB * 256);
       mbar_expect_tx(dq_full, NU * 256);
     }
   }
@@ -609,7 +630,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           bulk_store_wait(slot + 16384, daout, 8192);
           for (int o = 0; o < SP_NC; ++o) {            // partial dalpha rows of owner o's utterances -> its row block r
             const int no = (NU > o) ? (NU - o + SP_NC - 1) / SP_NC : 0;
-            if (no > 0) bulk_load_mc(dain + r * 256, slot + 16384 + o * 1024, no * 256, da_full, (uint16_t)(1u << o));
+            if (no > 0) bulk_load_mc(dain + r * 256, slot + 16384 + o * 1024, no * TPB * 256, da_full, (uint16_t)(1u << o));
           }
           if (n_own > 0 && s + 1 < n_steps) {      // (the dq of the last step feeds nothing inside the chain)
             mbar_wait_t(dq_ready, s & 1);
@@ -667,12 +688,13 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           mbar_wait_t(r_empty + stg, ((pos / SB_NSTAGE) & 1) ^ 1);
           mbar_expect_tx(r_full + stg, SP_STAGE);
           uint8_t* dst = Ring + stg * SP_STAGE;
-          if (i < NU) {                     // P of utterance i, this CTA's 128 gate rows: two k-blocks of [64 frames x 64 rows]
-            const int row = (b0 + i) * p.Tp;
+          if (i < NU * TPB) {               // P of utterance i / TPB, frame block i % TPB, this CTA's 128 gate rows
+            const int row = (b0 + i / TPB) * p.Tp + 64 * (i % TPB);
             tma_load_2d(&tmP, r_full + stg, dst, r * 128, row);
             tma_load_2d(&tmP, r_full + stg, dst + 8192, r * 128 + 64, row);
-          } else {                          // psi~ of own utterance i - NU
-            const int row = (b0 + r + 8 * (i - NU)) * p.Tp;
+          } else {                          // psi~ of own utterance o, frame block f
+            const int j = i - NU * TPB;
+            const int row = (b0 + r + 8 * (j / TPB)) * p.Tp + 64 * (j % TPB);
             tma_load_2d(&tmPsi, r_full + stg, dst, 0, row);
             tma_load_2d(&tmPsi, r_full + stg, dst + 8192, 64, row);
           }
@@ -727,9 +749,13 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #pragma unroll
       for (int j = 0; j < NJ; ++j) { a[j] = act_n[j]; cv[j] = c_n[j]; cpv[j] = cp_n[j]; dh[j] = dh_n[j]; }
       if (s + 1 < n_steps) fetch(t - 1);
-      float al_a = 0.f, q_a0 = 0.f, q_a1 = 0.f;
+      float al_a[TPB], q_a0 = 0.f, q_a1 = 0.f;
+#pragma unroll
+      for (int f = 0; f < TPB; ++f) al_a[f] = 0.f;
       if (att_on) {
-        al_a = ja < p.Tp ? __ldg(p.alpha + (size_t)ba * p.al_ldb + (size_t)t * p.al_ldt + ja) : 0.f;
+#pragma unroll
+        for (int f = 0; f < TPB; ++f)
+          if (ja + 64 * f < p.Tp) al_a[f] = __ldg(p.alpha + (size_t)ba * p.al_ldb + (size_t)t * p.al_ldt + ja + 64 * f);
         const float2 qq = *reinterpret_cast<const float2*>(p.q + (size_t)ba * p.q_ldb + (size_t)t * p.q_ldt + 2 * ja);
         q_a0 = qq.x; q_a1 = qq.y;
       }
@@ -780,7 +806,8 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       if (ATT) {
         // ---- 2. partial dalpha over the CTA's 128 gate rows, all utterances of the cluster ----
         mbar_wait_t(dg_ready, s & 1);               // every warp's rows of the operand tile are in place
-        for (int u = 0; u < NU; ++u, ++rpos) {
+        for (int i = 0; i < NU * TPB; ++i, ++rpos) {
+          const int u = i / TPB, fb = i % TPB;
           const int stg = rpos % SB_NSTAGE;
           mbar_wait_t(r_full + stg, (rpos / SB_NSTAGE) & 1);
           // P row jf, columns 16 part .. 16 part + 15: k-block part / 4, chunks 2 (part % 4) and + 1 (order swapped in the upper
@@ -805,7 +832,7 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           d += __shfl_xor_sync(0xffffffffu, d, 1);
           d += __shfl_xor_sync(0xffffffffu, d, 2);
           d += __shfl_xor_sync(0xffffffffu, d, 4);
-          if (part == 0) daout[(u & 7) * 256 + (u >> 3) * 64 + jf] = d;
+          if (part == 0) daout[(u & 7) * 256 + ((u >> 3) * TPB + fb) * 64 + jf] = d;
           __syncwarp();
           if (lane == 0) mbar_arrive(r_empty + stg);
         }
@@ -815,49 +842,59 @@ spell_cl_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         SB_STAMP(2);
         // ---- 3. owner: softmax backward and dq of the own utterances ----
         if (att_warp && n_own > 0) {
-          float de = 0.f;
           mbar_wait_t(da_full, s & 1);
           SB_STAMP(3);
-          if (ct == 0 && s + 1 < n_steps) mbar_expect_tx(da_full, SP_NC * n_own * 256);
-          float da = 0.f;
-          if (att_on) {
+          if (ct == 0 && s + 1 < n_steps) mbar_expect_tx(da_full, SP_NC * n_own * TPB * 256);
+          float da[TPB], ad = 0.f;
 #pragma unroll
-            for (int src = 0; src < SP_NC; ++src) da += dain[src * 256 + ua * 64 + ja];
+          for (int f = 0; f < TPB; ++f) {
+            da[f] = 0.f;
+            if (att_on) {
+#pragma unroll
+              for (int src = 0; src < SP_NC; ++src) da[f] += dain[src * 256 + (ua * TPB + f) * 64 + ja];
+            }
+            ad = fmaf(al_a[f], da[f], ad);
           }
-          const float wd = warp_sum(al_a * da);
+          const float wd = warp_sum(ad);
           if (lane == 0) red[ct >> 5] = wd;
           named_bar(1, 256);
           if (att_on) {
             const float dot = red[ua * 2] + red[ua * 2 + 1];
-            de = ja < len_a ? al_a * (da - dot) : 0.f;
-            if (ja < p.Tp) p.de[(size_t)ba * p.de_ldb + (size_t)t * p.de_ldt + ja] = de;
-            des[ua * 64 + ja] = de;
+#pragma unroll
+            for (int f = 0; f < TPB; ++f) {
+              const float de = ja + 64 * f < len_a ? al_a[f] * (da[f] - dot) : 0.f;
+              if (ja + 64 * f < p.Tp) p.de[(size_t)ba * p.de_ldb + (size_t)t * p.de_ldt + ja + 64 * f] = de;
+              des[(ua * TPB + f) * 64 + ja] = de;
+            }
           }
           named_bar(1, 256);
         }
         // the psi~ stages are walked by every warp in ring order (only the owner warps read them)
-        for (int o = 0; o < n_own; ++o, ++rpos) {
+        float s0 = 0.f, s1 = 0.f;
+        const int mc = (2 * ja) & 63;                                          // column of m = 2 ja inside its k-block
+        for (int i = 0; i < n_own * TPB; ++i, ++rpos) {
+          const int o = i / TPB, fb = i % TPB;
           const int stg = rpos % SB_NSTAGE;
           mbar_wait_t(r_full + stg, (rpos / SB_NSTAGE) & 1);
           if (att_on && o == ua) {
-            // dq_pre[m] for m = 2 ja, 2 ja + 1: column sums of de_j psi~[j, m] over the frames
+            // dq_pre[m] for m = 2 ja, 2 ja + 1: column sums of de_j psi~[j, m] over the frames of this block
             const uint8_t* pt = Ring + stg * SP_STAGE + (ja >> 5) * 8192;      // k-block of m
-            const int mc = (2 * ja) & 63;                                        // column inside the k-block
-            float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
             for (int j = 0; j < 64; ++j) {
               const uint32_t w = *reinterpret_cast<const uint32_t*>(pt + j * 128 + (((mc >> 3) ^ (j & 7)) << 4) + (mc & 7) * 2);
-              const float dj = des[ua * 64 + j];
+              const float dj = des[(ua * TPB + fb) * 64 + j];
               s0 = fmaf(dj, bf_lo(w), s0);
               s1 = fmaf(dj, bf_hi(w), s1);
             }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(r_empty + stg);
+          if (att_on && o == ua && fb == TPB - 1) {
             const float dq0 = s0 * (1.f - q_a0 * q_a0), dq1 = s1 * (1.f - q_a1 * q_a1);
             *reinterpret_cast<float2*>(p.dqpre + (size_t)ba * p.dq_ldb + (size_t)t * p.dq_ldt + 2 * ja) = make_float2(dq0, dq1);
             const __nv_bfloat162 pk = __floats2bfloat162_rn(dq0, dq1);
             *reinterpret_cast<__nv_bfloat162*>(dqimg + (ua * 2 + (ja >> 5)) * 128 + (((mc >> 3) ^ (sa_slot & 7)) << 4) + (mc & 7) * 2) = pk;
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(r_empty + stg);
         }
         if (att_warp && n_own > 0) {
           fence_proxy_async();
@@ -996,27 +1033,28 @@ int sp_query(Kern kern, int smem_bytes = SP_SMEM) {
 }
 int sp_capacity() {
   if (g_sp_cap < 0) {
-    const int a = sp_query(spell_cl_fwd_kernel<16, true>), b = sp_query(spell_cl_fwd_kernel<32, true>);
-    const int c = sp_query(spell_cl_fwd_kernel<16, false>), d = sp_query(spell_cl_fwd_kernel<32, false>);
-    g_sp_cap = a < b ? a : b;
-    if (c < g_sp_cap) g_sp_cap = c;
-    if (d < g_sp_cap) g_sp_cap = d;
-    const int e[4] = {sp_query(spell_cl_bwd_kernel<16, true>, SB_SMEM), sp_query(spell_cl_bwd_kernel<32, true>, SB_SMEM),
-                      sp_query(spell_cl_bwd_kernel<16, false>, SB_SMEM), sp_query(spell_cl_bwd_kernel<32, false>, SB_SMEM)};
-    for (int i = 0; i < 4; ++i)
-      if (e[i] < g_sp_cap) g_sp_cap = e[i];
+    const int q[10] = {sp_query(spell_cl_fwd_kernel<16, true, 1>), sp_query(spell_cl_fwd_kernel<32, true, 1>),
+                       sp_query(spell_cl_fwd_kernel<16, false, 1>), sp_query(spell_cl_fwd_kernel<32, false, 1>),
+                       sp_query(spell_cl_fwd_kernel<16, true, 4>),
+                       sp_query(spell_cl_bwd_kernel<16, true, 1>, SB_SMEM), sp_query(spell_cl_bwd_kernel<32, true, 1>, SB_SMEM),
+                       sp_query(spell_cl_bwd_kernel<16, false, 1>, SB_SMEM), sp_query(spell_cl_bwd_kernel<32, false, 1>, SB_SMEM),
+                       sp_query(spell_cl_bwd_kernel<16, true, 4>, SB_SMEM)};
+    g_sp_cap = q[0];
+    for (int i = 1; i < 10; ++i)
+      if (q[i] < g_sp_cap) g_sp_cap = q[i];
   }
   return g_sp_cap;
 }
-// clusters and utterances per cluster for a batch of B
+// clusters and utterances per cluster for a batch of B: as many co-resident clusters as there are (the step time grows with
+// the utterances per cluster: their P tiles stream through every CTA)
 void sp_split(int B, int* clusters, int* per) {
   const int cap = sp_capacity();
-  int nc = (B + 15) / 16;
-  if (nc > cap) nc = cap;
+  int nc = B < cap ? B : cap;
   if (nc < 1) nc = 1;
   *per = (B + nc - 1) / nc;
   *clusters = (B + *per - 1) / *per;
 }
+int sp_tpb(int Tp) { return Tp <= SP_TP ? 1 : 4; }
 
 }  // namespace
 
@@ -1027,11 +1065,11 @@ int spell_cl_supported(int B, int Tp, int E, int Sd, int M) {
     const char* e = getenv("SSASR_SPELL_CL");
     on = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!on || Sd != SP_SD || M != SP_M || Tp < 1 || Tp > SP_TP || E % 8 != 0 || B < 1) return 0;
+  if (!on || Sd != SP_SD || M != SP_M || Tp < 1 || Tp > 4 * SP_TP || E % 8 != 0 || B < 1) return 0;
   if (sp_capacity() < 1) return 0;
   int clusters, per;
   sp_split(B, &clusters, &per);
-  return per <= SP_MAXU ? 1 : 0;
+  return per <= (sp_tpb(Tp) == 1 ? SP_MAXU : 8) ? 1 : 0;       // four frame blocks: at most one attention utterance per CTA
 }
 
 int spell_cl_fwd(cudaStream_t st, const SpellClFwdArgs& a) {
@@ -1080,12 +1118,15 @@ int spell_cl_fwd(cudaStream_t st, const SpellClFwdArgs& a) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   ProfScope ps(F_SPELL_FWD, st);
-  if (att) {
-    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<16, true>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
-    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<32, true>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
+  if (att && sp_tpb(a.Tp) == 4) {
+    SSASR_REQUIRE(per <= 8, "spell_cl_fwd: T' = %d needs at most 8 utterances per cluster (got %d)", a.Tp, per);
+    SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<16, true, 4>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
+  } else if (att) {
+    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<16, true, 1>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
+    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<32, true, 1>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
   } else {
-    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<16, false>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
-    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<32, false>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
+    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<16, false, 1>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
+    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_fwd_kernel<32, false, 1>, tmW, tmPhi, tmP, tmPsi, a.K1, p));
   }
   return 0;
 }
@@ -1135,12 +1176,15 @@ int spell_cl_bwd(cudaStream_t st, const SpellClBwdArgs& a) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   ProfScope ps(F_SPELL_BWD, st);
-  if (att) {
-    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<16, true>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
-    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<32, true>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+  if (att && sp_tpb(a.Tp) == 4) {
+    SSASR_REQUIRE(per <= 8, "spell_cl_bwd: T' = %d needs at most 8 utterances per cluster (got %d)", a.Tp, per);
+    SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<16, true, 4>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+  } else if (att) {
+    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<16, true, 1>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<32, true, 1>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
   } else {
-    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<16, false>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
-    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<32, false>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+    if (per <= 16) SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<16, false, 1>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
+    else SSASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, spell_cl_bwd_kernel<32, false, 1>, tmW, tmPhiS, tmP, tmPsi, a.Kcol, p));
   }
   return 0;
 }

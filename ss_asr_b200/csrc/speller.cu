@@ -1057,6 +1057,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   // bf16 mode: layer-2 chain on a second stream (one layer-2 input block per step in ws_bf)
   // cluster-persistent step kernel for the teacher-forced runs (spell_cl.cu); needs one layer-2 input block per step in ws_bf
   const bool cl = tc && a->dual_stream && a->cl_ws && a->enc_bf && E % 8 == 0 && spell_cl_supported(B, Tp, E, Sd, M) &&
+                  (size_t)Tp * ((U + 15) / 16 * 16) * sizeof(float) <= 96 * 1024 &&      // spell_fill_xin1's attention-map tile
                   a->cl_ws_bytes >= (long long)spell_cl_ws_layout(B, Tp, Sd, M, C, U).total;
   SideStream* side = (!cl && tc && a->dual_stream && U > 1) ? side_stream(2 * U + 2) : nullptr;
   const bool dual = side != nullptr;

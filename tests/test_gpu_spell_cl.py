@@ -38,7 +38,9 @@ def _families(fn):
 
 # B = 20: two clusters of 10 utterances (16-row tiles, partially filled); B = 150: ten clusters of 15; B = 250: 15 clusters of
 # 17 / 12 utterances (32-row tiles, CTAs owning 3 and 2 attention utterances): the C4 geometry
-@pytest.mark.parametrize('B,T,U', [(20, 256, 9), (150, 64, 5), (250, 96, 4)])
+# T' in (64, 256] (four 64-frame blocks per utterance, at most 8 utterances per cluster): B = 6, T = 1040 (T' = 130, one
+# utterance per cluster) and B = 100, T = 560 (T' = 70, 7 utterances per cluster): the long-utterance geometry of C5
+@pytest.mark.parametrize('B,T,U', [(20, 256, 9), (150, 64, 5), (250, 96, 4), (6, 1040, 5), (100, 560, 3)])
 def test_cluster_speller_matches_oracle(B, T, U):
     """forward (logits, attention maps, loss) and every gradient against the fp32 CPU oracle at the bf16-path tolerances
     (logits 1e-2, loss 1e-3 rel, gradients rel-L2 3e-2 and cosine >= 0.999), the cluster kernels verifiably running"""
