@@ -212,7 +212,6 @@ struct KsGeom {
   static constexpr int KB = G / 64;                 // k-blocks of the dG slice operand
   static constexpr int NH = S / 128;                // 128-unit blocks of the accumulator
   static constexpr int CPT = UNITS / 32;            // cells per thread
-  static constexpr int DPH = 128 / UNITS;           // destinations per 128-unit block
   static constexpr int DHB = RW_NT * UNITS * 2;     // one (source, destination) block: [16 utterances][UNITS] bf16
   static constexpr int OFF_W = 0;                   // W_hh^T slice: [NH][KB] blocks of [128 units x 128 B]
   static constexpr int OFF_DG = OFF_W + NH * KB * 16384;
