@@ -4,12 +4,11 @@
 // Reference semantics: log_fbank, /root/reference/src/preprocess.py:187-208, i.e.
 // librosa(0.6.3).feature.melspectrogram(y, sr, n_mels=N_DIMS, n_fft=ws, hop_length=st) -> log(. + eps) -> T.
 //
-// One CTA handles FPB consecutive frames of one utterance: the audio span they share is read once
-// (hop < window, every sample is used by 2.5 frames), frames are built in shared memory, the
-// 25 ms window at 16 kHz (400 samples) is transformed as a 200-point complex FFT (radix 5*5*4*2
-// Stockham, one butterfly per thread) plus the real-input split; other window sizes (the reference's
-// default 22.05 kHz gives 551 = 19*29) take a direct-DFT path in the same kernel.  The mel matrix is
-// applied in its sparse (two triangles per bin) form.
+// One CTA handles groups of 16 consecutive frames of one utterance: the audio span they share is read once
+// (hop < window, every sample is used by 2.5 frames); at 16 kHz (25 ms = 400 samples) two real frames are packed
+// into one 400-point complex FFT (20 x 20, two register-resident 20-point DFTs per thread with one exchange through
+// shared memory) followed by the real-pair split; other window sizes (the reference's default 22.05 kHz gives
+// 551 = 19*29) take a direct-DFT kernel.  The mel matrix is applied in its sparse (two triangles per bin) form.
 #include "common.cuh"
 #include <math.h>
 #include <stdlib.h>
@@ -20,12 +19,17 @@ namespace ssasr {
 
 constexpr int FPB = 16;            // frames per CTA
 constexpr int NT = 256;
+constexpr int TWP = 10;            // twiddles per column of the 20 x 20 register FFT (fbank400q)
 
 struct FbankTables {
   int sr = 0, n_mels = 0, ws = 0, st = 0, nbins = 0;
   float* window = nullptr;     // [ws]
   float2* tw = nullptr;        // fast path: [200] W_200^m then [201] W_400^k ; generic: [ws] W_ws^m
   float2* tw400 = nullptr;     // 16 kHz register-FFT path: [400] W_400^e
+  float* win_half = nullptr;   // fbank400q: [400] 0.5 * window (the 1/2 of the frame separation folded into the input)
+  float2* twc = nullptr;       // fbank400q: [20][TWP] W_400^(c k1), k1 = 1..10; row c = the thread's column
+  int2* mel_meta = nullptr;    // fbank400q: [n_mels] {first bin | padded count << 16, offset into mel_w4}
+  float* mel_w4 = nullptr;     // fbank400q: zero-padded filter weights (see get_tables)
   int* mel_start = nullptr;    // [n_mels]
   int* mel_cnt = nullptr;      // [n_mels]
   int* mel_off = nullptr;      // [n_mels]
@@ -95,6 +99,40 @@ static int get_tables(int sr, int n_mels, FbankTables* out) {
     for (int e = 0; e < 400; ++e) t4[e] = make_float2((float)cos(2.0 * M_PI * e / 400), (float)-sin(2.0 * M_PI * e / 400));
     SSASR_CHECK_CUDA(cudaMalloc(&t.tw400, sizeof(float2) * 400));
     SSASR_CHECK_CUDA(cudaMemcpy(t.tw400, t4.data(), sizeof(float2) * 400, cudaMemcpyHostToDevice));
+    std::vector<float> wh(400);
+    for (int n = 0; n < 400; ++n) wh[n] = 0.5f * win[n];
+    std::vector<float2> tc(20 * TWP);                      // row c: W_400^(c k1) for k1 = 1..9, then k1 = 10
+    for (int c = 0; c < 20; ++c)
+      for (int j = 0; j < TWP; ++j) tc[c * TWP + j] = t4[(c * (j + 1)) % 400];
+    // mel filters for the (mel, frame pair) work items of fbank400q: the two filters of a half-warp (mels 2m, 2m+1) start
+    // on bins of different parity (one leading zero weight where needed: conflict-free 64-bit loads of the interleaved
+    // power spectrum) and every filter is padded with zero weights to a multiple of 4 bins (no remainder loop)
+    std::vector<int> qs(start), qc(cnt);
+    for (int i = 0; i + 1 < n_mels; i += 2)
+      if (((qs[i] ^ qs[i + 1]) & 1) == 0) {
+        const int v = qs[i + 1] > 0 ? i + 1 : (qs[i] > 0 ? i : -1);
+        if (v >= 0) { qs[v] -= 1; qc[v] += 1; }
+      }
+    std::vector<float> qw;
+    std::vector<int2> meta(n_mels);
+    for (int i = 0; i < n_mels; ++i) {
+      const int lead = start[i] - qs[i];
+      const int c4 = (qc[i] + 3) & ~3;
+      meta[i] = make_int2(qs[i] | (c4 << 16), (int)qw.size());
+      for (int b = 0; b < c4; ++b) {
+        const int src = b - lead;
+        qw.push_back(src >= 0 && src < cnt[i] ? wts[off[i] + src] : 0.f);
+      }
+    }
+    if (qw.empty()) qw.push_back(0.f);
+    SSASR_CHECK_CUDA(cudaMalloc(&t.win_half, sizeof(float) * 400));
+    SSASR_CHECK_CUDA(cudaMalloc(&t.twc, sizeof(float2) * tc.size()));
+    SSASR_CHECK_CUDA(cudaMalloc(&t.mel_meta, sizeof(int2) * n_mels));
+    SSASR_CHECK_CUDA(cudaMalloc(&t.mel_w4, sizeof(float) * qw.size()));
+    SSASR_CHECK_CUDA(cudaMemcpy(t.win_half, wh.data(), sizeof(float) * 400, cudaMemcpyHostToDevice));
+    SSASR_CHECK_CUDA(cudaMemcpy(t.twc, tc.data(), sizeof(float2) * tc.size(), cudaMemcpyHostToDevice));
+    SSASR_CHECK_CUDA(cudaMemcpy(t.mel_meta, meta.data(), sizeof(int2) * n_mels, cudaMemcpyHostToDevice));
+    SSASR_CHECK_CUDA(cudaMemcpy(t.mel_w4, qw.data(), sizeof(float) * qw.size(), cudaMemcpyHostToDevice));
   }
   SSASR_CHECK_CUDA(cudaMalloc(&t.window, sizeof(float) * ws));
   SSASR_CHECK_CUDA(cudaMalloc(&t.tw, sizeof(float2) * tw.size()));
@@ -116,54 +154,6 @@ static int get_tables(int sr, int n_mels, FbankTables* out) {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-
-// one Stockham stage of radix R (sub-transform length Ns so far) over `nfr` frames of N=200 complex points
-// (src -> dst); everything but nfr is a compile-time constant, so the index arithmetic is mul/shift only.
-template <int R, int Ns>
-__device__ __forceinline__ void stockham_stage(const float2* __restrict__ src, float2* __restrict__ dst, const float2* __restrict__ tw200,
-                                               int nfr) {
-  constexpr int N = 200;
-  constexpr int NB = N / R;
-  constexpr int TS = N / (Ns * R);      // twiddle index step per unit k: W_{Ns*R}^{k r} = W_200^{k r TS}  (k r TS < N)
-  for (int w = threadIdx.x; w < nfr * NB; w += NT) {
-    const int f = w / NB, j = w - f * NB;
-    const float2* x = src + f * N;
-    float2* y = dst + f * N;
-    const int k = j % Ns;
-    float2 v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      v[r] = x[j + r * NB];
-      if (r > 0 && Ns > 1) v[r] = cmul(v[r], tw200[k * TS * r]);
-    }
-    float2 o[R];
-    if constexpr (R == 2) {
-      o[0] = cadd(v[0], v[1]);
-      o[1] = csub(v[0], v[1]);
-    } else if constexpr (R == 4) {
-      const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]), t3 = csub(v[1], v[3]);
-      o[0] = cadd(t0, t2);
-      o[2] = csub(t0, t2);
-      o[1] = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i*t3
-      o[3] = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i*t3
-    } else {  // R == 5
-      const float c1 = 0.30901699437494745f, c2 = -0.8090169943749475f, s1 = 0.9510565162951535f, s2 = 0.5877852522924731f;
-      const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
-      o[0] = make_float2(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
-      const float2 a1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-      const float2 a2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-      const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-      const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-      o[1] = make_float2(a1.x + b1.y, a1.y - b1.x);   // a1 - i*b1
-      o[4] = make_float2(a1.x - b1.y, a1.y + b1.x);
-      o[2] = make_float2(a2.x + b2.y, a2.y - b2.x);
-      o[3] = make_float2(a2.x - b2.y, a2.y + b2.x);
-    }
-    const int j0 = (j - k) * R + k;
-#pragma unroll
-    for (int r = 0; r < R; ++r) y[j0 + r * Ns] = o[r];
-  }
-}
 
 // ---- register-resident 20-point DFT (4 x 5 Cooley-Tukey, compile-time twiddles) --------------------------------
 __device__ __forceinline__ float2 w20(int e) {     // W_20^e = exp(-2 pi i e / 20); e is a compile-time constant after unrolling
@@ -230,6 +220,7 @@ struct FbankParams {
   int ws, st, nbins, n_mels;
   const float* window; const float2* tw;
   const int *mel_start, *mel_cnt, *mel_off; const float* mel_w;
+  const float* win_half; const float2* twc; const int2* mel_meta; const float* mel_w4;      // fbank400q
 };
 
 // ---- 16 kHz / 25 ms fast path, register FFT: two real frames are packed into one 400-point complex FFT
@@ -315,78 +306,178 @@ __global__ void __launch_bounds__(NTP, 4) fbank400p_kernel(FbankParams p) {
   }
 }
 
-// ---- 16 kHz / 25 ms fast path: 400-sample frames, hop 160 ----------------------------------------------------
-// shared: A [FPB][200] float2 | B [FPB][200] float2 (also: audio span before the FFT, power spectrum after) |
-//         twiddles [401] float2 | window [400] float
-__global__ void __launch_bounds__(NT, 4) fbank400_kernel(FbankParams p) {
-  extern __shared__ __align__(16) float smem[];
-  float2* A = reinterpret_cast<float2*>(smem);
-  float2* Bf = A + FPB * 200;
-  float* span = reinterpret_cast<float*>(Bf);                 // aliases B until the first FFT stage writes it
-  float* P = reinterpret_cast<float*>(Bf);                    // aliases B after the last FFT stage (result is in A)
-  float2* tws = Bf + FPB * 200;
-  float* win = reinterpret_cast<float*>(tws + 401);
-  const int u = blockIdx.y;
-  const long long a0 = p.offsets[u];
-  const int n = (int)(p.offsets[u + 1] - a0);
-  constexpr int ws = 400, st = 160, half = 200;
-  const int nframes = 1 + n / st;
-  const int f0 = blockIdx.x * FPB;
-  if (f0 >= nframes) return;
-  const int nfr = min(FPB, nframes - f0);
-  for (int i = threadIdx.x; i < 401; i += NT) tws[i] = p.tw[i];
-  for (int i = threadIdx.x; i < ws; i += NT) win[i] = p.window[i];
-  const float* au = p.audio + a0;
+// ---- 16 kHz / 25 ms fast path, second generation (round 2).  The first-generation kernel above issued 844 warp
+// instructions per frame for ~ 310 of FFT work (issue-bound at 0.11 of the HBM roofline).  Same 20 x 20 register FFT of
+// frame PAIRS (z = a + i b), everything around it rebuilt:
+//  * the two frames are separated BETWEEN the passes, in registers: after the first 20-point DFT (over n1, thread = column
+//    n2) a real frame's rows obey Ya[20-k1] = conj Ya[k1], so Ya[k1] = Y[k1] + conj Y[20-k1], Yb[k1] ~ Y[k1] - conj Y[20-k1]
+//    (k1 = 1..9; the 1/2 is folded into the window) and rows 0 and 10 are real for both frames, i.e. Y[0] and Y[10] ARE the
+//    packed pairs.  The second pass then runs exactly 20 row DFTs per pair again -- a1..a9, b1..b9, packed row 0, packed
+//    row 10 -- whose 20 outputs are 20 DISTINCT wanted bins (k1 + 20 k2 for k2 < 10, the mirror bin (20-k1) + 20 (19-k2)
+//    otherwise): no mirror exchange through shared memory, no barrier for it, |X|^2 straight from the DFT registers.  Only the
+//    two packed rows need the conj-symmetric split, inside one thread; all 16 of them sit in warp 4, so four warps of five
+//    never execute that path;
+//  * a CTA walks QG groups of 16 frames; the audio span of group g+1 is prefetched with cp.async into the other of two
+//    buffers while group g computes (the exposed load was 25 % of all stall samples), stored with 20 floats of padding per
+//    320 so that the strided window reads of adjacent pairs fall on disjoint banks;
+//  * twiddles: 10 per column (rows a_k and b_k share theirs), five 128-bit loads;
+//  * power spectrum interleaved (a, b) per bin, pair stride = 4 banks (mod 32), living in the dead span buffer (no barrier
+//    between the second-pass reads and the stores); mel projection: work item = (mel, pair), one weight feeds both frames,
+//    the lanes of a half-warp are 8 pairs x 2 adjacent mels whose first bins differ in parity (padded on the host) =
+//    conflict-free 64-bit loads; 4 adjacent mels per warp have near-equal widths (the first kernel's thread per
+//    (frame, mel) made every warp wait for its widest filter); weights padded to 4 bins: one 128-bit load, no remainder loop;
+//    log via lg2.approx (abs. error < 1e-5 over the range of log-mel energies).
+constexpr int QG = 8;              // groups of 16 frames per CTA
+constexpr int QPB = 210;           // power-spectrum row pitch (float2): 420 words = 4 banks mod 32
+constexpr int QSPAN = 2960;        // span with 20 floats of padding after every 320 samples
+constexpr int QBUF = FPAIRS * QPB * 2;           // floats per span / power-spectrum buffer (3360 >= QSPAN)
+constexpr int QSMEM = (2 * QBUF + 400) * 4 + (20 * TWP + FPAIRS * 20 * EXP) * 8;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// span of the 16 frames from f0 on -> buf (padded layout), asynchronously
+__device__ __forceinline__ void q_prefetch(float* buf, const float* au, int n, int nframes, int f0, int tid) {
+  constexpr int ws = 400, st = 160, half = 200, NF = 2 * FPAIRS, SPAN = (NF - 1) * st + ws;
+  const int nfr = min(NF, nframes - f0);
   const int s0 = f0 * st - half;
-  const int need = (nfr - 1) * st + ws;
-  if (s0 >= 0 && s0 + need <= n) {          // interior block: straight coalesced copy
-    for (int i = threadIdx.x; i < need; i += NT) span[i] = __ldcs(au + s0 + i);
-  } else {                                  // utterance edges: numpy 'reflect' padding
-    for (int i = threadIdx.x; i < need; i += NT) {
+  if (nfr == NF && s0 >= 0 && s0 + SPAN <= n && ((reinterpret_cast<uintptr_t>(au + s0) & 15) == 0)) {
+    for (int j = tid; j < SPAN / 4; j += NTP) cp_async16(buf + 4 * j + 20 * (j / 80), au + s0 + 4 * j);
+  } else {                                                        // utterance edges (numpy 'reflect' padding), short last
+    const int need = (nfr - 1) * st + ws;                         // group (zeros: a pair partner reads them), unaligned audio
+    for (int i = tid; i < SPAN; i += NTP) {
       int idx = s0 + i;
       if (idx < 0) idx = -idx;
       if (idx >= n) idx = 2 * (n - 1) - idx;
-      span[i] = au[idx];
+      float* d = buf + i + 20 * (i / 320);
+      if (i < need) cp_async4(d, au + idx); else *d = 0.f;
     }
   }
-  __syncthreads();
-  for (int w = threadIdx.x; w < nfr * 200; w += NT) {          // window and pack z[m] = xw[2m] + i*xw[2m+1]
-    const int f = w / 200, m = w - f * 200;
-    const float2 sv = *reinterpret_cast<const float2*>(span + f * st + 2 * m);
-    const float2 wv = *reinterpret_cast<const float2*>(win + 2 * m);
-    A[w] = make_float2(sv.x * wv.x, sv.y * wv.y);
-  }
-  __syncthreads();
-  stockham_stage<5, 1>(A, Bf, tws, nfr);
-  __syncthreads();
-  stockham_stage<5, 5>(Bf, A, tws, nfr);
-  __syncthreads();
-  stockham_stage<4, 25>(A, Bf, tws, nfr);
-  __syncthreads();
-  stockham_stage<2, 100>(Bf, A, tws, nfr);
-  __syncthreads();
-  // real-input split: X[k] = E[k] + W_400^k * O[k], k = 0..200; power spectrum
-  constexpr int PB = 202;
-  const float2* w400 = tws + 200;
-  for (int w = threadIdx.x; w < nfr * 201; w += NT) {
-    const int f = w / 201, k = w - f * 201;
-    const float2 zk = A[f * 200 + (k == 200 ? 0 : k)];
-    const float2 zn = A[f * 200 + (k == 0 ? 0 : 200 - k)];
-    const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-    const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));   // (zk - conj(zn)) / (2i)
-    const float2 x = cadd(e, cmul(w400[k], o));
-    P[f * PB + k] = x.x * x.x + x.y * x.y;
-  }
-  __syncthreads();
-  float* outp = p.out + (size_t)(p.out_offsets[u] + f0) * p.n_mels;
-  for (int w = threadIdx.x; w < nfr * p.n_mels; w += NT) {
-    const int f = w / p.n_mels, i = w - f * p.n_mels;
-    const int b0 = __ldg(p.mel_start + i), c = __ldg(p.mel_cnt + i);
-    const float* wt = p.mel_w + __ldg(p.mel_off + i);
-    const float* pr = P + f * PB + b0;
-    float s = 0.f;
-    for (int b = 0; b < c; ++b) s = fmaf(__ldg(wt + b), pr[b], s);
-    __stcs(outp + w, logf(s + 2.220446049250313e-16f));
+}
+
+__global__ void __launch_bounds__(NTP, 4) fbank400q_kernel(FbankParams p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int st = 160, NF = 2 * FPAIRS;
+  float* win = smem + 2 * QBUF;                                   // [400]
+  float2* twc = reinterpret_cast<float2*>(win + 400);             // [20][TWP]
+  float2* ex = twc + 20 * TWP;                                    // [FPAIRS][20*EXP]: rows a1..a8, b1..b8, a9, b9, r0, r10
+  const int u = blockIdx.y;
+  const long long a0 = p.offsets[u];
+  const int n = (int)(p.offsets[u + 1] - a0);
+  const int nframes = 1 + n / st;
+  const int tid = threadIdx.x;
+  const int fbase = blockIdx.x * (QG * NF);
+  if (fbase >= nframes) return;
+  const float* au = p.audio + a0;
+  q_prefetch(smem, au, n, nframes, fbase, tid);
+  for (int i = tid; i < 400; i += NTP) win[i] = __ldg(p.win_half + i);
+  for (int i = tid; i < 20 * TWP; i += NTP) twc[i] = __ldg(p.twc + i);
+  for (int i = QSPAN + tid; i < QBUF; i += NTP) { smem[i] = 0.f; smem[QBUF + i] = 0.f; }   // never written by a span: the
+  const int pr = tid / 20, c = tid - pr * 20;       // first pass: pair, column n2         // padded filters read them as P
+  smem[340 * pr + 320 + c] = 0.f;                   // (the padding gaps too)
+  smem[QBUF + 340 * pr + 320 + c] = 0.f;
+  // second pass: pair q, row.  warps 0-3: pairs (w, w+4) x rows 0..15; warp 4: 4 pairs x rows 16..19 per half-warp
+  int q, row;
+  if (tid < 128) { q = (tid >> 5) + 4 * ((tid >> 4) & 1); row = tid & 15; }
+  else { const int l = tid - 128; q = (l & 3) + 4 * (l >> 4); row = 16 + ((l >> 2) & 3); }
+  const bool special = row >= 18, is_r0 = row == 18;
+  const int fr = row < 16 ? row >> 3 : row & 1;     // frame of the pair (normal rows)
+  const int k1 = row < 16 ? (row & 7) + 1 : 9;
+  const int n_items = p.n_mels * FPAIRS;
+  float* const out_u = p.out + (size_t)p.out_offsets[u] * p.n_mels;
+#pragma unroll 1
+  for (int g = 0; g < QG; ++g) {
+    const int f0 = fbase + g * NF;
+    if (f0 >= nframes) break;
+    const int nfr = min(NF, nframes - f0);
+    float* span = smem + (g & 1) * QBUF;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                              // B1: span g landed; everybody is done with group g-1
+    if (g + 1 < QG && f0 + NF < nframes) q_prefetch(smem + ((g + 1) & 1) * QBUF, au, n, nframes, f0 + NF, tid);
+    float2 x[20];
+    {
+      const float* sa = span + 340 * pr + c;
+      const float* wv = win + c;
+#pragma unroll
+      for (int n1 = 0; n1 < 20; ++n1) {
+        const float w = wv[20 * n1];
+        x[n1] = make_float2(sa[20 * n1 + (n1 >= 16 ? 20 : 0)] * w, sa[st + 20 * n1 + (n1 >= 8 ? 20 : 0)] * w);
+      }
+    }
+    dft20(x);                                                     // over n1 (stride 20): Y[k1] for this n2
+    {
+      float2* e = ex + pr * 20 * EXP + c;
+      const float4* tq = reinterpret_cast<const float4*>(twc + c * TWP);
+      e[18 * EXP] = x[0];                                         // packed row 0: Ya[0] + i Yb[0], both real
+      float4 t2;
+#pragma unroll
+      for (int k = 1; k <= 9; ++k) {
+        if (k & 1) t2 = tq[k >> 1];                               // W^(c k), W^(c (k+1))
+        const float2 tw = (k & 1) ? make_float2(t2.x, t2.y) : make_float2(t2.z, t2.w);
+        const float2 y = x[k], m = x[20 - k];
+        const float2 ya = make_float2(y.x + m.x, y.y - m.y);      // Y[k] + conj Y[20-k]
+        const float2 yb = make_float2(y.x - m.x, y.y + m.y);      // Y[k] - conj Y[20-k] = i * (row of frame b)
+        e[(k <= 8 ? k - 1 : 16) * EXP] = cmul(ya, tw);
+        e[(k <= 8 ? k + 7 : 17) * EXP] = cmul(yb, tw);
+      }
+      e[19 * EXP] = cmul(x[10], make_float2(t2.z, t2.w));         // packed row 10, W^(10 c)
+    }
+    __syncthreads();                                              // B2: the span buffer is dead from here on
+    {
+      const float2* e = ex + q * 20 * EXP + row * EXP;
+#pragma unroll
+      for (int n2 = 0; n2 < 20; ++n2) x[n2] = e[n2];
+    }
+    dft20(x);                                                     // over n2: X[k1 + 20 k2] = x[k2]
+    float* Pw = span;                                             // power spectrum [FPAIRS][QPB] x (a, b) in the dead span
+    if (!special) {
+      float* lo = Pw + q * (2 * QPB) + fr + 2 * k1;               // bins k1 + 20 k2, k2 < 10
+      float* hi = Pw + q * (2 * QPB) + fr + 2 * (20 - k1);        // bins (20 - k1) + 20 (19 - k2), k2 >= 10
+#pragma unroll
+      for (int k2 = 0; k2 < 10; ++k2) lo[40 * k2] = x[k2].x * x[k2].x + x[k2].y * x[k2].y;
+#pragma unroll
+      for (int k2 = 10; k2 < 20; ++k2) hi[40 * (19 - k2)] = x[k2].x * x[k2].x + x[k2].y * x[k2].y;
+    } else {
+      // packed rows: C[k2] = Xa[k] + i Xb[k] (k = 20 k2 or 10 + 20 k2), mirror C[(20-k2) % 20] or C[19-k2]
+      float2* po = reinterpret_cast<float2*>(Pw) + q * QPB + (is_r0 ? 0 : 10);
+#pragma unroll
+      for (int k2 = 0; k2 < 10; ++k2) {
+        const float2 zk = x[k2];
+        const float2 z0 = x[(20 - k2) % 20], z1 = x[19 - k2];
+        const float2 zn = is_r0 ? z0 : z1;
+        const float ar = zk.x + zn.x, ai = zk.y - zn.y, br = zk.x - zn.x, bi = zk.y + zn.y;
+        po[20 * k2] = make_float2(ar * ar + ai * ai, br * br + bi * bi);
+      }
+      if (is_r0) po[200] = make_float2(4.f * x[10].x * x[10].x, 4.f * x[10].y * x[10].y);   // bin 200: its own mirror
+    }
+    __syncthreads();                                              // B4
+    float* outp = out_u + (size_t)f0 * p.n_mels;
+    for (int w = tid; w < n_items; w += NTP) {
+      const int pq = w & (FPAIRS - 1), i = w >> 3;
+      if (2 * pq >= nfr) continue;
+      const int2 mm = __ldg(p.mel_meta + i);
+      const int b0 = mm.x & 0xffff, cnt = mm.x >> 16;
+      const float4* wt = reinterpret_cast<const float4*>(p.mel_w4 + mm.y);
+      const float2* pw = reinterpret_cast<const float2*>(Pw) + pq * QPB + b0;
+      float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
+      for (int b = 0; b < cnt; b += 4) {
+        const float4 w4 = __ldg(wt + (b >> 2));
+        const float2 p0 = pw[b], p1 = pw[b + 1], p2 = pw[b + 2], p3 = pw[b + 3];
+        sa0 = fmaf(w4.x, p0.x, sa0); sb0 = fmaf(w4.x, p0.y, sb0);
+        sa1 = fmaf(w4.y, p1.x, sa1); sb1 = fmaf(w4.y, p1.y, sb1);
+        sa0 = fmaf(w4.z, p2.x, sa0); sb0 = fmaf(w4.z, p2.y, sb0);
+        sa1 = fmaf(w4.w, p3.x, sa1); sb1 = fmaf(w4.w, p3.y, sb1);
+      }
+      float* o = outp + (size_t)(2 * pq) * p.n_mels + i;
+      __stcs(o, __logf(sa0 + sa1 + 2.220446049250313e-16f));
+      if (2 * pq + 1 < nfr) __stcs(o + p.n_mels, __logf(sb0 + sb1 + 2.220446049250313e-16f));
+    }
+    // group g+1: its prefetch into THIS buffer is issued after its B1, which no thread passes before everybody has finished
+    // this mel phase; its ex writes come after that B1 too
   }
 }
 
@@ -479,8 +570,14 @@ int ssasr_fbank(const float* audio, const long long* offsets, int n_utt, int sam
   p.window = t.window; p.tw = t.tw; p.mel_start = t.mel_start; p.mel_cnt = t.mel_cnt; p.mel_off = t.mel_off; p.mel_w = t.mel_w;
   dim3 grid((max_frames + FPB - 1) / FPB, n_utt);
   ProfScope ps(F_FBANK, st);
-  static const bool use_stockham = getenv("SSASR_FBANK_STOCKHAM") != nullptr;   // previous smem-FFT kernel, kept for A/B timing
-  if (t.ws == 400 && !use_stockham) {
+  static const bool use_gen1 = getenv("SSASR_FBANK_GEN1") != nullptr;   // first-generation register-FFT kernel, kept for A/B timing
+  if (t.ws == 400 && !use_gen1) {
+    p.win_half = t.win_half; p.twc = t.twc; p.mel_meta = t.mel_meta; p.mel_w4 = t.mel_w4;
+    constexpr int NF = 2 * FPAIRS;
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank400q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QSMEM));
+    dim3 g2((max_frames + QG * NF - 1) / (QG * NF), n_utt);
+    fbank400q_kernel<<<g2, NTP, QSMEM, st>>>(p);
+  } else if (t.ws == 400) {
     p.tw = t.tw400;
     constexpr int NF = 2 * FPAIRS;
     const size_t smem = (size_t)((NF - 1) * 160 + 400 + 400) * sizeof(float) + (size_t)(400 + FPAIRS * 20 * EXP) * sizeof(float2) +
@@ -488,10 +585,6 @@ int ssasr_fbank(const float* audio, const long long* offsets, int n_utt, int sam
     SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank400p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g2((max_frames + NF - 1) / NF, n_utt);
     fbank400p_kernel<<<g2, NTP, smem, st>>>(p);
-  } else if (t.ws == 400) {
-    const size_t smem = (size_t)(2 * FPB * 200 + 401) * sizeof(float2) + 400 * sizeof(float);
-    SSASR_CHECK_CUDA(cudaFuncSetAttribute(fbank400_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fbank400_kernel<<<grid, NT, smem, st>>>(p);
   } else {
     const int span_len = (FPB - 1) * t.st + t.ws;
     const size_t floats = ((span_len + 3) & ~3) + ((FPB * t.ws + 3) & ~3) + ((FPB * (t.nbins + 1) + 3) & ~3) + 2 * (size_t)t.ws;
