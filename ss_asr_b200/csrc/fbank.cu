@@ -340,13 +340,25 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
+// ln(x) for normal positive x (here x >= 2^-52): one MUFU and one multiply, abs. error < 1e-5 over the log-mel range
+__device__ __forceinline__ float ln_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.6931471805599453f;
+}
+
 // span of the 16 frames from f0 on -> buf (padded layout), asynchronously
 __device__ __forceinline__ void q_prefetch(float* buf, const float* au, int n, int nframes, int f0, int tid) {
   constexpr int ws = 400, st = 160, half = 200, NF = 2 * FPAIRS, SPAN = (NF - 1) * st + ws;
   const int nfr = min(NF, nframes - f0);
   const int s0 = f0 * st - half;
   if (nfr == NF && s0 >= 0 && s0 + SPAN <= n && ((reinterpret_cast<uintptr_t>(au + s0) & 15) == 0)) {
-    for (int j = tid; j < SPAN / 4; j += NTP) cp_async16(buf + 4 * j + 20 * (j / 80), au + s0 + 4 * j);
+    // 700 chunks of 16 bytes, chunk j = tid + 160 t at float 4 j + 20 (j / 80) = 4 tid + 20 (tid / 80) + 680 t
+    float* d = buf + 4 * tid + (tid >= 80 ? 20 : 0);
+    const float* sp = au + s0 + 4 * tid;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) cp_async16(d + 680 * t, sp + 640 * t);
+    if (tid < SPAN / 4 - 4 * NTP) cp_async16(d + 680 * 4, sp + 640 * 4);
   } else {                                                        // utterance edges (numpy 'reflect' padding), short last
     const int need = (nfr - 1) * st + ws;                         // group (zeros: a pair partner reads them), unaligned audio
     for (int i = tid; i < SPAN; i += NTP) {
@@ -387,7 +399,6 @@ __global__ void __launch_bounds__(NTP, 4) fbank400q_kernel(FbankParams p) {
   const bool special = row >= 18, is_r0 = row == 18;
   const int fr = row < 16 ? row >> 3 : row & 1;     // frame of the pair (normal rows)
   const int k1 = row < 16 ? (row & 7) + 1 : 9;
-  const int n_items = p.n_mels * FPAIRS;
   float* const out_u = p.out + (size_t)p.out_offsets[u] * p.n_mels;
 #pragma unroll 1
   for (int g = 0; g < QG; ++g) {
@@ -456,25 +467,33 @@ __global__ void __launch_bounds__(NTP, 4) fbank400q_kernel(FbankParams p) {
     }
     __syncthreads();                                              // B4
     float* outp = out_u + (size_t)f0 * p.n_mels;
-    for (int w = tid; w < n_items; w += NTP) {
-      const int pq = w & (FPAIRS - 1), i = w >> 3;
-      if (2 * pq >= nfr) continue;
-      const int2 mm = __ldg(p.mel_meta + i);
-      const int b0 = mm.x & 0xffff, cnt = mm.x >> 16;
-      const float4* wt = reinterpret_cast<const float4*>(p.mel_w4 + mm.y);
-      const float2* pw = reinterpret_cast<const float2*>(Pw) + pq * QPB + b0;
-      float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
-      for (int b = 0; b < cnt; b += 4) {
-        const float4 w4 = __ldg(wt + (b >> 2));
-        const float2 p0 = pw[b], p1 = pw[b + 1], p2 = pw[b + 2], p3 = pw[b + 3];
-        sa0 = fmaf(w4.x, p0.x, sa0); sb0 = fmaf(w4.x, p0.y, sb0);
-        sa1 = fmaf(w4.y, p1.x, sa1); sb1 = fmaf(w4.y, p1.y, sb1);
-        sa0 = fmaf(w4.z, p2.x, sa0); sb0 = fmaf(w4.z, p2.y, sb0);
-        sa1 = fmaf(w4.w, p3.x, sa1); sb1 = fmaf(w4.w, p3.y, sb1);
+    if (2 * (tid & (FPAIRS - 1)) < nfr) {
+      const int pq = tid & (FPAIRS - 1);
+      const float2* prow = reinterpret_cast<const float2*>(Pw) + pq * QPB;
+      float* orow = outp + (2 * pq) * p.n_mels;
+      const bool has_b = 2 * pq + 1 < nfr;
+      int2 mm = __ldg(p.mel_meta + (tid >> 3));
+      for (int i = tid >> 3; i < p.n_mels; i += NTP / FPAIRS) {
+        const int in = i + NTP / FPAIRS;
+        int2 mn = mm;
+        if (in < p.n_mels) mn = __ldg(p.mel_meta + in);            // next item's filter: in flight under this one
+        const float4* wt = reinterpret_cast<const float4*>(p.mel_w4 + mm.y);
+        const float2* pw = prow + (mm.x & 0xffff);
+        const float2* pe = pw + (mm.x >> 16);
+        float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
+#pragma unroll 1
+        for (; pw < pe; pw += 4, ++wt) {
+          const float4 w4 = __ldg(wt);
+          const float2 p0 = pw[0], p1 = pw[1], p2 = pw[2], p3 = pw[3];
+          sa0 = fmaf(w4.x, p0.x, sa0); sb0 = fmaf(w4.x, p0.y, sb0);
+          sa1 = fmaf(w4.y, p1.x, sa1); sb1 = fmaf(w4.y, p1.y, sb1);
+          sa0 = fmaf(w4.z, p2.x, sa0); sb0 = fmaf(w4.z, p2.y, sb0);
+          sa1 = fmaf(w4.w, p3.x, sa1); sb1 = fmaf(w4.w, p3.y, sb1);
+        }
+        __stcs(orow + i, ln_fast(sa0 + sa1 + 2.220446049250313e-16f));
+        if (has_b) __stcs(orow + p.n_mels + i, ln_fast(sb0 + sb1 + 2.220446049250313e-16f));
+        mm = mn;
       }
-      float* o = outp + (size_t)(2 * pq) * p.n_mels + i;
-      __stcs(o, __logf(sa0 + sa1 + 2.220446049250313e-16f));
-      if (2 * pq + 1 < nfr) __stcs(o + p.n_mels, __logf(sb0 + sb1 + 2.220446049250313e-16f));
     }
     // group g+1: its prefetch into THIS buffer is issued after its B1, which no thread passes before everybody has finished
     // this mel phase; its ex writes come after that B1 too
