@@ -952,7 +952,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 
   const int slice = blockIdx.x, dir = blockIdx.y, bt = blockIdx.z;      // cluster = the NC CTAs along x
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tile_bytes = (uint32_t)NC * IMG;
+  const uint32_t tile_bytes = (uint32_t)(NC - 1) * IMG;      // the CTA's own slice of h is written in place by its epilogue
   const int seq_inner = p.rs_seq < p.rs_batch ? 1 : 0;
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmW);
@@ -988,7 +988,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (warp == 0) {
     // ---------------- exchange thread ----------------
     if (elect_one()) {
-      const uint16_t cmask = (uint16_t)((1u << NC) - 1u);
+      const uint16_t cmask = (uint16_t)(((1u << NC) - 1u) & ~(1u << slice));   // the peers
       const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
       const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
       auto load_x = [&](int s_) {
@@ -1007,14 +1007,15 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * IMG;
         mbar_wait_t(stage_ready, s & 1);                           // all 256 epilogue threads have written the image
         CL_STAMP(8);
+        uint8_t* img_s = Hsm + ((s & 1) * NC + slice) * IMG;       // the image = this CTA's k-block of the tile h(s)
         if (s + 1 < p.n_seq) {
-          bulk_store_wait(slot, img, IMG);
+          bulk_store_wait(slot, img_s, IMG);
           CL_STAMP(9);
-          bulk_load_mc(Hsm + ((s & 1) * NC + slice) * IMG, slot, IMG, a_full + (s & 1), cmask);
+          bulk_load_mc(img_s, slot, IMG, a_full + (s & 1), cmask);
           CL_STAMP(6);
         }
         // bf16 copy of h (next layer's input, weight-gradient operand): the image IS the swizzled TMA box
-        tma_store_3d(&tmH, img, dir * S + slice * Q_UNITS, seq_inner ? t : bt * R, seq_inner ? bt * R : t);
+        tma_store_3d(&tmH, img_s, dir * S + slice * Q_UNITS, seq_inner ? t : bt * R, seq_inner ? bt * R : t);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         mbar_arrive(img_free);
@@ -1043,18 +1044,30 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         if (s > 0) {
           const int b = (s - 1) & 1;
-          mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // all NC slices of h(s-1) have landed
-          if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
+          const uint32_t h0 = smem_u32(Hsm + b * NC * IMG), w0 = smem_u32(Wsm);
+          // the CTA's OWN k-block of h(s-1) was written in place by its epilogue: its MMAs run while the peers' slices are
+          // still on their way through the exchange
+          mbar_wait_t(stage_ready, (s - 1) & 1);
           if (!XF && s > 1) mbar_wait_t(tmem_free, (s - 2) & 1);     // epilogue has drained the accumulators
+          tc_fence_after();
+#pragma unroll
+          for (int kq = 0; kq < 4; ++kq) {
+            const uint64_t dh = umma_desc_k128(h0 + slice * IMG) + (uint64_t)(kq * 2);
+            const uint64_t dw = umma_desc_k128(w0 + slice * W_BLK) + (uint64_t)(kq * 2);
+            mma_bf16_ss(tmem, dw, dh, idesc, (XF || kq != 0) ? 1u : 0u);
+            mma_bf16_ss(tmem + R, dw + (uint64_t)((128 * 128) >> 4), dh, idesc, (XF || kq != 0) ? 1u : 0u);
+          }
+          mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // the NC - 1 remote slices of h(s-1) have landed
+          if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
           CL_STAMP(1);
           tc_fence_after();
-          const uint32_t h0 = smem_u32(Hsm + b * NC * IMG), w0 = smem_u32(Wsm);
 #pragma unroll 4
           for (int kk = 0; kk < nk; ++kk) {
+            if ((kk >> 2) == slice) continue;
             const uint64_t dh = umma_desc_k128(h0 + (kk >> 2) * IMG) + (uint64_t)((kk & 3) * 2);
             const uint64_t dw = umma_desc_k128(w0 + (kk >> 2) * W_BLK) + (uint64_t)((kk & 3) * 2);
-            mma_bf16_ss(tmem, dw, dh, idesc, (XF || kk != 0) ? 1u : 0u);
-            mma_bf16_ss(tmem + R, dw + (uint64_t)((128 * 128) >> 4), dh, idesc, (XF || kk != 0) ? 1u : 0u);
+            mma_bf16_ss(tmem, dw, dh, idesc, 1u);
+            mma_bf16_ss(tmem + R, dw + (uint64_t)((128 * 128) >> 4), dh, idesc, 1u);
           }
         }
         mma_commit(mma_done);
@@ -1086,7 +1099,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     float creg[CPT];
 #pragma unroll
     for (int m = 0; m < CPT; ++m) creg[m] = 0.f;
-    uint8_t* img_u = img + (ul & 7) * 2;           // + row*128 + swizzled 16-byte chunk (ul >> 3)
+    uint8_t* img_u0 = Hsm + slice * IMG + (ul & 7) * 2;   // own k-block of tile buffer 0: + row*128 + swizzled 16-byte chunk (ul >> 3)
 
     // pre-activations are fetched ONE WHOLE STEP ahead (registers): a load issued at the top of its own step is not back
     // when the accumulator is (measured: the epilogue then stalls on HBM latency under the kernel's own store bursts)
@@ -1154,7 +1167,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         const int r = cgp * (R / 2) + 4 * m + gp;
-        *reinterpret_cast<__nv_bfloat16*>(img_u + r * 128 + (((ul >> 3) ^ (r & 7)) << 4)) = __float2bfloat16_rn(hv[m]);
+        *reinterpret_cast<__nv_bfloat16*>(img_u0 + (s & 1) * NC * IMG + r * 128 + (((ul >> 3) ^ (r & 7)) << 4)) = __float2bfloat16_rn(hv[m]);
       }
       fence_proxy_async();                         // generic-proxy smem writes -> visible to the bulk (async proxy) copies
       __syncwarp();
