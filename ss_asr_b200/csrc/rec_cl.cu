@@ -74,6 +74,7 @@ struct RecClParams {
   long long rs_seq, rs_batch;
   long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0)
   long long gld, hld;        // quad kernels: row pitch of the gate buffers (n_dir * 4S) and of the h / c / dh buffers (n_dir * S)
+  const __nv_bfloat16* whh;  // rec_q_fwd: packed W_hh [n_dir * 4S, S] bf16 (row-major): the resident slice goes to TENSOR memory
 };
 
 #define CL_STAMP(idx)                                                                                            \
@@ -930,7 +931,8 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   constexpr int WX_BLK = 256 * 32;       // fused projection: 256 gate rows x 16 bf16
   constexpr int X_BLK = R * 32;          // fused projection: R rows x 16 bf16
   constexpr int CPT = R / 8;             // cells (batch rows of ONE unit) per epilogue thread
-  constexpr int TCOLS = 2 * R < 32 ? 32 : 2 * R;
+  constexpr int WCOL = 64;               // TMEM: accumulators in columns [0, 2R), the W_hh slice from column 64:
+  constexpr int TCOLS = 512;             // half 0 (gate rows 0..127) in [64, 64 + S/2), half 1 behind it (S <= 256)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.S, KB = S / 64, NC = S / Q_UNITS;
@@ -982,6 +984,14 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       for (int kx = 0; kx < p.nkx; ++kx) tma_load_3d(&tmWx, w_full, Wx + kx * WX_BLK, kx * 16, dir * 4 * S + slice * 256, 0);
     mbar_expect_tx(a_full, tile_bytes);          // h(0) and h(1); re-armed by the MMA thread after each wait
     mbar_expect_tx(a_full + 1, tile_bytes);
+  }
+  if (warp >= 2) {
+    // resident W_hh slice -> tensor memory (A operand of every step's product): thread = one gate row, the 16 warps split
+    // the two M = 128 halves and the two halves of K
+    const int q_ = warp & 3, half_ = ((warp - 2) >> 2) & 1, kh_ = (warp - 2) >> 3;
+    const __nv_bfloat16* wrow = p.whh + ((size_t)dir * 4 * S + slice * 256 + half_ * 128 + q_ * 32 + lane) * S + kh_ * (S / 2);
+    tmem_store_row(tmem + ((uint32_t)(q_ * 32) << 16) + (uint32_t)(WCOL + half_ * (S / 2) + kh_ * (S / 4)), wrow, S / 4);
+    tc_fence_before();
   }
   cluster_sync_all();                            // every CTA's barriers exist before any multicast can signal them
 
@@ -1044,7 +1054,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         if (s > 0) {
           const int b = (s - 1) & 1;
-          const uint32_t h0 = smem_u32(Hsm + b * NC * IMG), w0 = smem_u32(Wsm);
+          const uint32_t h0 = smem_u32(Hsm + b * NC * IMG);
           // the CTA's OWN k-block of h(s-1) was written in place by its epilogue: its MMAs run while the peers' slices are
           // still on their way through the exchange
           mbar_wait_t(stage_ready, (s - 1) & 1);
@@ -1053,9 +1063,9 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
           for (int kq = 0; kq < 4; ++kq) {
             const uint64_t dh = umma_desc_k128(h0 + slice * IMG) + (uint64_t)(kq * 2);
-            const uint64_t dw = umma_desc_k128(w0 + slice * W_BLK) + (uint64_t)(kq * 2);
-            mma_bf16_ss(tmem, dw, dh, idesc, (XF || kq != 0) ? 1u : 0u);
-            mma_bf16_ss(tmem + R, dw + (uint64_t)((128 * 128) >> 4), dh, idesc, (XF || kq != 0) ? 1u : 0u);
+            const uint32_t aw = tmem + WCOL + (slice * 4 + kq) * 8;
+            mma_bf16_ts(tmem, aw, dh, idesc, (XF || kq != 0) ? 1u : 0u);
+            mma_bf16_ts(tmem + R, aw + S / 2, dh, idesc, (XF || kq != 0) ? 1u : 0u);
           }
           mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // the NC - 1 remote slices of h(s-1) have landed
           if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
@@ -1065,9 +1075,9 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           for (int kk = 0; kk < nk; ++kk) {
             if ((kk >> 2) == slice) continue;
             const uint64_t dh = umma_desc_k128(h0 + (kk >> 2) * IMG) + (uint64_t)((kk & 3) * 2);
-            const uint64_t dw = umma_desc_k128(w0 + (kk >> 2) * W_BLK) + (uint64_t)((kk & 3) * 2);
-            mma_bf16_ss(tmem, dw, dh, idesc, 1u);
-            mma_bf16_ss(tmem + R, dw + (uint64_t)((128 * 128) >> 4), dh, idesc, 1u);
+            const uint32_t aw = tmem + WCOL + kk * 8;
+            mma_bf16_ts(tmem, aw, dh, idesc, 1u);
+            mma_bf16_ts(tmem + R, aw + S / 2, dh, idesc, 1u);
           }
         }
         mma_commit(mma_done);
@@ -1356,6 +1366,7 @@ static int rec_q_fwd_launch(cudaStream_t st, RecClParams& p, const void* whh_bf,
     attr_set = true;
   }
   CUtensorMap tmW, tmX, tmWx, tmH;
+  p.whh = (const __nv_bfloat16*)whh_bf;
   int rc = make_tmap_bf16(&tmW, whh_bf, ndir * 4 * S, S, S, 256);
   if (rc) return rc;
   const bool si = p.rs_seq < p.rs_batch;

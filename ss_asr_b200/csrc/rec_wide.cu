@@ -58,7 +58,9 @@ struct RecWideP {
   int n_seq, n_batch;
   long long rs_seq, rs_batch;
   long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0)
+  const __nv_bfloat16* w;    // fwd: packed W_hh [8S, S]; bwd: W_hh^T [2S, 4S] (bf16, row-major): the resident slice -> TENSOR memory
 };
+constexpr int RW_WCOL = 64;  // TMEM: accumulators in columns [0, 64), the resident weight slice (A operand) from column 64
 #define RW_STAMP(idx)                                                                                            \
   do {                                                                                                           \
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[(size_t)s * 12 + (idx)] = clock64(); \
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
     mbar_init(stage_ready, RW_EPW);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<32>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,6 +106,14 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
     for (int kb = 0; kb < 8; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * 16384, kb * 64, dir * 4 * S + r * 128);
     mbar_expect_tx(a_full, RW_NC * RW_HBLK);
     mbar_expect_tx(a_full + 1, RW_NC * RW_HBLK);
+  }
+  if (warp >= 4) {
+    // resident W_hh slice [128 gate rows x S] -> tensor memory: thread = one gate row, the four warps of a sub-partition
+    // split K into quarters (S / 8 packed words each)
+    const int sp_ = warp & 3, part_ = (warp - 4) >> 2;
+    const __nv_bfloat16* wrow = p.w + ((size_t)dir * 4 * S + r * 128 + sp_ * 32 + lane) * S + part_ * (S / 4);
+    tmem_store_row(tmem + ((uint32_t)(sp_ * 32) << 16) + (uint32_t)(RW_WCOL + part_ * (S / 8)), wrow, S / 8);
+    tc_fence_before();
   }
   cluster_sync_all();
 
@@ -129,11 +139,10 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
         mbar_wait_t(a_full + hb, ((s - 1) >> 1) & 1);
         if (s + 2 < n_steps) mbar_expect_tx(a_full + hb, RW_NC * RW_HBLK);
         tc_fence_after();
-        const uint32_t h0 = smem_u32(Hsm + hb * RW_NC * RW_HBLK), w0 = smem_u32(Wsm);
+        const uint32_t h0 = smem_u32(Hsm + hb * RW_NC * RW_HBLK);
 #pragma unroll 4
         for (int kk = 0; kk < S / 16; ++kk)
-          mma_bf16_ss(tmem, umma_desc_k128(w0 + (kk >> 2) * 16384) + (uint64_t)((kk & 3) * 2),
-                      umma_desc_k64(h0 + (kk >> 1) * RW_HBLK) + (uint64_t)((kk & 1) * 2), idesc, kk != 0);
+          mma_bf16_ts(tmem, tmem + RW_WCOL + kk * 8, umma_desc_k64(h0 + (kk >> 1) * RW_HBLK) + (uint64_t)((kk & 1) * 2), idesc, kk != 0);
         mma_commit(g_done);
       }
     }
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<32>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
   cluster_sync_all();
 }
 
@@ -219,7 +228,7 @@ struct KsGeom {
   static constexpr int OFF_DHIN = OFF_DHOUT + NC * DHB;
   static constexpr int OFF_BARS = OFF_DHIN + 2 * NC * DHB;
   static constexpr int SMEM = OFF_BARS + 16 * 8 + 1024;
-  static constexpr int TCOLS = NH * RW_NT < 32 ? 32 : NH * RW_NT;
+  static constexpr int TCOLS = 512;                 // accumulators [0, NH * 16) + the W_hh^T slice from column RW_WCOL: NH x G/2 columns
   static constexpr int SLOT = NC * DHB;             // exchange slot per CTA and ring position
 };
 
@@ -270,6 +279,15 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_ks_bwd_kernel(const __grid_
     mbar_expect_tx(dh_full, NC * DHB);
     mbar_expect_tx(dh_full + 1, NC * DHB);
   }
+  if (warp >= 4) {
+    // resident W_hh^T slice [S units x G own gate rows] -> tensor memory: thread = one unit row of a 128-unit block, the 16
+    // warps = 4 sub-partitions x NH blocks x 4 / NH parts of K
+    constexpr int PARTS = 4 / NH, PW = GE::G / 2 / PARTS;      // packed words per part
+    const int sp_ = warp & 3, j_ = (warp - 4) >> 2, h_ = j_ / PARTS, part_ = j_ % PARTS;
+    const __nv_bfloat16* wrow = p.w + ((size_t)dir * S + h_ * 128 + sp_ * 32 + lane) * (4 * S) + r * GE::G + part_ * (2 * PW);
+    tmem_store_row(tmem + ((uint32_t)(sp_ * 32) << 16) + (uint32_t)(RW_WCOL + h_ * (GE::G / 2) + part_ * PW), wrow, PW);
+    tc_fence_before();
+  }
   cluster_sync_all();
 
   if (warp == 0) {
@@ -296,12 +314,12 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_ks_bwd_kernel(const __grid_
         mbar_wait_t(dg_ready, s & 1);
         RW_STAMP(2);
         tc_fence_after();
-        const uint32_t w0 = smem_u32(Wsm), g0 = smem_u32(dGsm);
+        const uint32_t g0 = smem_u32(dGsm);
 #pragma unroll
         for (int h = 0; h < NH; ++h)
 #pragma unroll
           for (int kk = 0; kk < 4 * KB; ++kk)
-            mma_bf16_ss(tmem + h * RW_NT, umma_desc_k128(w0 + (h * KB + (kk >> 2)) * 16384) + (uint64_t)((kk & 3) * 2),
+            mma_bf16_ts(tmem + h * RW_NT, tmem + RW_WCOL + h * (GE::G / 2) + kk * 8,
                         umma_desc_k128(g0 + (kk >> 2) * 2048) + (uint64_t)((kk & 3) * 2), idesc, kk != 0);
         mma_commit(d_done);
         RW_STAMP(3);
@@ -350,6 +368,18 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_ks_bwd_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < CPT; ++j) { a[j] = a_n[j]; cv[j] = c_n[j]; cpv[j] = cp_n[j]; dh[j] = dh_n[j]; }
       if (s + 1 < n_steps) fetch(s + 1);
+      // everything of the cell backward that does not need dh(t) is computed BEFORE the wait for the partial sums:
+      //   dc = dh * k_dc + dc_carry,  dG_o = dh * k_o,  dG_i = dc * k_i,  dG_g = dc * k_g,  dG_f = dc * k_f,  carry' = dc * f
+      float k_dc[CPT], k_o[CPT], k_i[CPT], k_g[CPT], k_f[CPT];
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const float tc_ = tanh_apx(cv[j]);
+        k_dc[j] = a[j].w * (1.f - tc_ * tc_);
+        k_o[j] = tc_ * a[j].w * (1.f - a[j].w);
+        k_i[j] = a[j].z * a[j].x * (1.f - a[j].x);
+        k_g[j] = a[j].x * (1.f - a[j].z * a[j].z);
+        k_f[j] = pv ? cpv[j] * a[j].y * (1.f - a[j].y) : 0.f;
+      }
       if (s > 0) {
         mbar_wait_t(dh_full + ((s - 1) & 1), ((s - 1) >> 1) & 1);
         if (threadIdx.x == 128) RW_STAMP(1);
@@ -369,12 +399,11 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_ks_bwd_kernel(const __grid_
         float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
         float dco = 0.f;
         if (valid) {
-          const float tc_ = tanh_apx(cv[j]);
-          const float dc = fmaf(dh[j] * a[j].w, 1.f - tc_ * tc_, dcreg[j]);
-          dg.w = dh[j] * tc_ * a[j].w * (1.f - a[j].w);
-          dg.x = dc * a[j].z * a[j].x * (1.f - a[j].x);
-          dg.z = dc * a[j].x * (1.f - a[j].z * a[j].z);
-          dg.y = pv ? dc * cpv[j] * a[j].y * (1.f - a[j].y) : 0.f;
+          const float dc = fmaf(dh[j], k_dc[j], dcreg[j]);
+          dg.w = dh[j] * k_o[j];
+          dg.x = dc * k_i[j];
+          dg.z = dc * k_g[j];
+          dg.y = dc * k_f[j];
           dco = dc * a[j].y;
         }
         dcreg[j] = dco;
@@ -537,6 +566,7 @@ int rec_wide_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, fl
   p.xp = xp; p.hout = hout; p.cbuf = cbuf; p.xb = (__nv_bfloat16*)hb; p.lens = lens;
   p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
   p.ring = rw_ring_for(st);
+  p.w = (const __nv_bfloat16*)whh_bf;
   SSASR_REQUIRE(p.ring != nullptr, "rec_wide_fwd: cannot allocate the exchange ring");
   CUtensorMap tmW;
   int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 128);
@@ -555,6 +585,7 @@ int rec_wide_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* 
   p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
   p.ring = rw_ring_for(st);
   p.dbg = g_rw_dbg;
+  p.w = (const __nv_bfloat16*)whhT_bf;
   SSASR_REQUIRE(p.ring != nullptr, "rec_wide_bwd: cannot allocate the exchange ring");
   CUtensorMap tmWT;
   int rc = make_tmap_bf16(&tmWT, whhT_bf, 2 * S, 4 * S, 4 * S, 128);

@@ -88,6 +88,18 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[TMEM] * B[smem]: the A operand (M = 128: lane = row, one 32-bit column = two consecutive k, low half first;
+// 8 columns per K = 16 instruction) is read from tensor memory.  With N <= 32 the SS form is bound by the shared-memory read
+// of its 4 KB A tile (44 cycles per M=128 x N=16 instruction measured); from TMEM the same instruction takes 13
+// (scripts/mma_ts_bench.cu).  Resident weights of the recurrent kernels live there.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // same, kind::tf32: A/B are fp32 in shared memory, the tensor core uses their upper 19 bits (K = 8 per instruction)
 __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -125,6 +137,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> TMEM: the warp's own 32 lanes x 32 consecutive columns (thread i writes lane i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one row-major bf16 matrix row (n_words packed pairs, a multiple of 32, 16-byte aligned) -> this thread's TMEM lane, columns
+// taddr.col .. + n_words (the A-operand layout of mma_bf16_ts); whole warp, lane i of the warp = TMEM lane taddr.lane + i
+__device__ __forceinline__ void tmem_store_row(uint32_t taddr, const void* row, int n_words) {
+  const uint4* src = reinterpret_cast<const uint4*>(row);
+  for (int c0 = 0; c0 < n_words; c0 += 32) {
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 q = __ldg(src + (c0 >> 2) + j);
+      v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    }
+    tmem_st32(taddr + c0, v);
+  }
+  tmem_st_wait();
+}
 
 // ---- descriptors ----------------------------------------------------------------------------------
 // K-major operand tile stored as rows of 64 bf16 (128 B) with the 128-byte swizzle, 8-row groups 1024 B apart
