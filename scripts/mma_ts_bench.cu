@@ -14,27 +14,6 @@
 #include "tc_common.cuh"
 using namespace ssasr::tc;
 
-__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
-        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
-        "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 constexpr int M = 128, N = 16, K = 256;
 // shared: A (SW128 K-major, 4 k-blocks of 128 rows x 128 B) | B (4 k-blocks of 16 rows x 128 B)
 constexpr int A_BLK = 128 * 128, B_BLK = N * 128;
@@ -154,6 +133,14 @@ __global__ void __launch_bounds__(192, 1) kern(const __nv_bfloat16* A, const __n
     tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
     tmem_ld_wait();
     for (int j = 0; j < N; ++j) D[(warp * 32 + lane) * N + j] = __uint_as_float(v[j]);
+    // probe of the 16x256b load shape (columns 0..7 of the accumulator): what lands in which thread
+    uint32_t w[8];
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(tmem + ((uint32_t)(warp * 32) << 16)) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(tmem + ((uint32_t)(warp * 32 + 16) << 16)) : "memory");
+    tmem_ld_wait();
+    for (int j = 0; j < 8; ++j) D[M * N + (warp * 32 + lane) * 8 + j] = __uint_as_float(w[j]);
   }
   tc_fence_before();
   __syncthreads();
@@ -162,11 +149,11 @@ __global__ void __launch_bounds__(192, 1) kern(const __nv_bfloat16* A, const __n
 
 int main() {
   std::vector<__nv_bfloat16> hA(M * K), hB(N * K);
-  std::vector<float> fA(M * K), fB(N * K), hD(M * N);
+  std::vector<float> fA(M * K), fB(N * K), hD(M * N + M * 8);
   __nv_bfloat16 *dA, *dB;
   float* dD;
   long long* dC;
-  cudaMalloc(&dA, M * K * 2); cudaMalloc(&dB, N * K * 2); cudaMalloc(&dD, M * N * 4); cudaMalloc(&dC, 64);
+  cudaMalloc(&dA, M * K * 2); cudaMalloc(&dB, N * K * 2); cudaMalloc(&dD, (M * N + M * 8) * 4); cudaMalloc(&dC, 64);
   const int smem = 4 * A_BLK + 4 * B_BLK + 2048;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   // ---- probe: A[m][k] = (m % 8) * 16 + k for k < 16, B = identity on the first 16 k
@@ -200,6 +187,16 @@ int main() {
       if (d > worst) worst = d;
     }
     printf("check %s: %s, max |D - ref| = %g\n", mode == 1 ? "A in TMEM" : "A in smem", cudaGetErrorString(e), worst);
+    if (mode == 1) {
+      // 16x256b: thread t of a warp is expected to hold rows t/4 and t/4 + 8 of the addressed 16-lane block, columns 2 (t % 4), + 1
+      cudaMemcpy(hD.data(), dD, (M * N + M * 8) * 4, cudaMemcpyDeviceToHost);
+      int bad = 0;
+      for (int w = 0; w < 4; ++w) for (int t = 0; t < 32; ++t) for (int blk = 0; blk < 2; ++blk) for (int j = 0; j < 4; ++j) {
+        const int row = w * 32 + blk * 16 + t / 4 + (j >> 1) * 8, col = 2 * (t % 4) + (j & 1);
+        if (hD[M * N + (w * 32 + t) * 8 + blk * 4 + j] != hD[row * N + col]) ++bad;
+      }
+      printf("tcgen05.ld.16x256b.x1 layout (rows t/4, t/4+8; columns 2(t%%4), +1): %d mismatches of 1024\n", bad);
+    }
   }
   kern<<<1, 192, smem>>>(dA, dB, dD, dC, 3);
   e = cudaDeviceSynchronize();

@@ -1039,6 +1039,13 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, R);
       const int nk = S / 16;
+      // every operand of the step's MMAs is a base + a compile-time offset: nothing but the instructions themselves sits
+      // between the arrival of the exchanged tile and the commit (the issue loop with computed descriptors took 28 cycles
+      // per instruction, three times the tensor core's own 8 - 13)
+      const uint64_t dH[2] = {umma_desc_k128(smem_u32(Hsm)), umma_desc_k128(smem_u32(Hsm + NC * IMG))};
+      const uint32_t aw0 = tmem + WCOL, aw1 = tmem + WCOL + S / 2;
+      const uint64_t own_h = (uint64_t)((slice * IMG) >> 4);
+      const uint32_t own_a = (uint32_t)(slice * 32);
       for (int s = XF ? 0 : 1; s < p.n_seq; ++s) {
         if (s == (XF ? 0 : 1)) mbar_wait_t(w_full, 0);
         if (XF) {
@@ -1054,7 +1061,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
         if (s > 0) {
           const int b = (s - 1) & 1;
-          const uint32_t h0 = smem_u32(Hsm + b * NC * IMG);
+          const uint64_t dhb = dH[b];
           // the CTA's OWN k-block of h(s-1) was written in place by its epilogue: its MMAs run while the peers' slices are
           // still on their way through the exchange
           mbar_wait_t(stage_ready, (s - 1) & 1);
@@ -1062,22 +1069,20 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           tc_fence_after();
 #pragma unroll
           for (int kq = 0; kq < 4; ++kq) {
-            const uint64_t dh = umma_desc_k128(h0 + slice * IMG) + (uint64_t)(kq * 2);
-            const uint32_t aw = tmem + WCOL + (slice * 4 + kq) * 8;
-            mma_bf16_ts(tmem, aw, dh, idesc, (XF || kq != 0) ? 1u : 0u);
-            mma_bf16_ts(tmem + R, aw + S / 2, dh, idesc, (XF || kq != 0) ? 1u : 0u);
+            mma_bf16_ts(tmem, aw0 + own_a + kq * 8, dhb + own_h + (uint64_t)(kq * 2), idesc, (XF || kq != 0) ? 1u : 0u);
+            mma_bf16_ts(tmem + R, aw1 + own_a + kq * 8, dhb + own_h + (uint64_t)(kq * 2), idesc, (XF || kq != 0) ? 1u : 0u);
           }
           mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // the NC - 1 remote slices of h(s-1) have landed
           if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
           CL_STAMP(1);
           tc_fence_after();
-#pragma unroll 4
-          for (int kk = 0; kk < nk; ++kk) {
-            if ((kk >> 2) == slice) continue;
-            const uint64_t dh = umma_desc_k128(h0 + (kk >> 2) * IMG) + (uint64_t)((kk & 3) * 2);
-            const uint32_t aw = tmem + WCOL + kk * 8;
-            mma_bf16_ts(tmem, aw, dh, idesc, 1u);
-            mma_bf16_ts(tmem + R, aw + S / 2, dh, idesc, 1u);
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) {
+            if (kk < nk && (kk >> 2) != slice) {
+              const uint64_t dh = dhb + (uint64_t)(((kk >> 2) * IMG) >> 4) + (uint64_t)((kk & 3) * 2);
+              mma_bf16_ts(tmem, aw0 + kk * 8, dh, idesc, 1u);
+              mma_bf16_ts(tmem + R, aw1 + kk * 8, dh, idesc, 1u);
+            }
           }
         }
         mma_commit(mma_done);

@@ -139,10 +139,10 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
         mbar_wait_t(a_full + hb, ((s - 1) >> 1) & 1);
         if (s + 2 < n_steps) mbar_expect_tx(a_full + hb, RW_NC * RW_HBLK);
         tc_fence_after();
-        const uint32_t h0 = smem_u32(Hsm + hb * RW_NC * RW_HBLK);
-#pragma unroll 4
+        const uint64_t dhb = umma_desc_k64(smem_u32(Hsm + hb * RW_NC * RW_HBLK));
+#pragma unroll
         for (int kk = 0; kk < S / 16; ++kk)
-          mma_bf16_ts(tmem, tmem + RW_WCOL + kk * 8, umma_desc_k64(h0 + (kk >> 1) * RW_HBLK) + (uint64_t)((kk & 1) * 2), idesc, kk != 0);
+          mma_bf16_ts(tmem, tmem + RW_WCOL + kk * 8, dhb + (uint64_t)(((kk >> 1) * RW_HBLK) >> 4) + (uint64_t)((kk & 1) * 2), idesc, kk != 0);
         mma_commit(g_done);
       }
     }
