@@ -75,6 +75,8 @@ struct RecClParams {
   long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0)
   long long gld, hld;        // quad kernels: row pitch of the gate buffers (n_dir * 4S) and of the h / c / dh buffers (n_dir * S)
   const __nv_bfloat16* whh;  // rec_q_fwd: packed W_hh [n_dir * 4S, S] bf16 (row-major): the resident slice goes to TENSOR memory
+  const __nv_bfloat16* wih;  // rec_q_fwd, fused input projection: packed W_ih [n_dir * 4S, kp] bf16
+  int kp;
 };
 
 #define CL_STAMP(idx)                                                                                            \
@@ -933,6 +935,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   constexpr int CPT = R / 8;             // cells (batch rows of ONE unit) per epilogue thread
   constexpr int WCOL = 64;               // TMEM: accumulators in columns [0, 2R), the W_hh slice from column 64:
   constexpr int TCOLS = 512;             // half 0 (gate rows 0..127) in [64, 64 + S/2), half 1 behind it (S <= 256)
+  constexpr int WXCOL = WCOL + 256;      // XF: the W_ih slice, FW_MAXKX * 8 columns per half
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.S, KB = S / 64, NC = S / Q_UNITS;
@@ -987,10 +990,28 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   }
   if (warp >= 2) {
     // resident W_hh slice -> tensor memory (A operand of every step's product): thread = one gate row, the 16 warps split
-    // the two M = 128 halves and the two halves of K
+    // the two M = 128 halves and the two halves of K.  Row order inside a 32-lane sub-partition: lane = gate * 8 + unit
+    // (not unit * 4 + gate): a 16-lane x 256-bit accumulator load then hands thread t gates {0,1} / {2,3} of unit t/4 for
+    // batch columns 2 (t % 4), + 1 -- all four gates of its cells without any shuffle.
     const int q_ = warp & 3, half_ = ((warp - 2) >> 2) & 1, kh_ = (warp - 2) >> 3;
-    const __nv_bfloat16* wrow = p.whh + ((size_t)dir * 4 * S + slice * 256 + half_ * 128 + q_ * 32 + lane) * S + kh_ * (S / 2);
-    tmem_store_row(tmem + ((uint32_t)(q_ * 32) << 16) + (uint32_t)(WCOL + half_ * (S / 2) + kh_ * (S / 4)), wrow, S / 4);
+    const size_t grow = (size_t)dir * 4 * S + slice * 256 + half_ * 128 + (q_ * 8 + (lane & 7)) * 4 + (lane >> 3);
+    const uint32_t tl = tmem + ((uint32_t)(q_ * 32) << 16);
+    tmem_store_row(tl + (uint32_t)(WCOL + half_ * (S / 2) + kh_ * (S / 4)), p.whh + grow * S + kh_ * (S / 2), S / 4);
+    if (XF && kh_ == 0) {                        // the W_ih slice of the fused input projection, same row order
+      const uint4* xr = reinterpret_cast<const uint4*>(p.wih + grow * p.kp);
+      const int nq = p.kp / 8;                   // 16-byte groups of the row
+      for (int kx = 0; kx < p.nkx; ++kx) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
+          if (2 * kx + j < nq) w4 = __ldg(xr + 2 * kx + j);
+          v[4 * j] = w4.x; v[4 * j + 1] = w4.y; v[4 * j + 2] = w4.z; v[4 * j + 3] = w4.w;
+        }
+        tmem_st8(tl + (uint32_t)(WXCOL + half_ * (FW_MAXKX * 8) + kx * 8), v);
+      }
+      tmem_st_wait();
+    }
     tc_fence_before();
   }
   cluster_sync_all();                            // every CTA's barriers exist before any multicast can signal them
@@ -1053,10 +1074,13 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           if (s > 0) mbar_wait_t(tmem_free, (s - 1) & 1);          // epilogue has drained the accumulators
           mbar_wait_t(x_full + (s & 1), (s >> 1) & 1);
           tc_fence_after();
-          const uint32_t x0 = smem_u32(Xs + (s & 1) * FW_MAXKX * X_BLK), wx0 = smem_u32(Wx);
-          for (int kx = 0; kx < p.nkx; ++kx) {
-            mma_bf16_ss(tmem, umma_desc_k32(wx0 + kx * WX_BLK), umma_desc_k32(x0 + kx * X_BLK), idesc, kx != 0);
-            mma_bf16_ss(tmem + R, umma_desc_k32(wx0 + kx * WX_BLK + 128 * 32), umma_desc_k32(x0 + kx * X_BLK), idesc, kx != 0);
+          const uint64_t dx0 = umma_desc_k32(smem_u32(Xs + (s & 1) * FW_MAXKX * X_BLK));
+#pragma unroll
+          for (int kx = 0; kx < FW_MAXKX; ++kx) {
+            if (kx < p.nkx) {
+              mma_bf16_ts(tmem, tmem + WXCOL + kx * 8, dx0 + (uint64_t)((kx * X_BLK) >> 4), idesc, kx != 0);
+              mma_bf16_ts(tmem + R, tmem + WXCOL + FW_MAXKX * 8 + kx * 8, dx0 + (uint64_t)((kx * X_BLK) >> 4), idesc, kx != 0);
+            }
           }
         }
         if (s > 0) {
@@ -1104,7 +1128,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     bool inr[CPT];
 #pragma unroll
     for (int m = 0; m < CPT; ++m) {
-      const int n = bt * R + cgp * (R / 2) + 4 * m + gp;
+      const int n = bt * R + cgp * (R / 2) + 8 * (m >> 1) + 2 * gp + (m & 1);
       inr[m] = n < p.n_batch;
       len[m] = inr[m] ? (p.lens ? p.lens[n] : INT_MAX) : 0;
       rowb[m] = (size_t)(inr[m] ? n : 0) * p.rs_batch;
@@ -1137,33 +1161,27 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       if (!XF && s + 1 < p.n_seq) fetch_g(s + 1);
       if (s > 0) mbar_wait_t(img_free, (s - 1) & 1);     // the previous image has been read out: checked off the dependent chain
       if (XF || s > 0) {
-        uint32_t v[R / 2];
+        uint32_t v[4 * CPT];
         mbar_wait_t(mma_done, XF ? (s & 1) : ((s - 1) & 1));
         if (threadIdx.x == 64) CL_STAMP(3);
         tc_fence_after();
         const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * R + cgp * (R / 2));
-        tmem_ld_n<R / 2>(ta, v);
+#pragma unroll
+        for (int rep = 0; rep < CPT / 2; ++rep) {
+          tmem_ld_16x256(ta + 8 * rep, v + 8 * rep);                    // gates i, f of unit uq, batch columns 2 gp, 2 gp + 1
+          tmem_ld_16x256(ta + (16u << 16) + 8 * rep, v + 8 * rep + 4);  // gates g, o
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_free);
-        // 4x4 transposes inside the lane quad: lane gate g holds rows 4m..4m+3 of ITS gate; afterwards lane gp holds the four
-        // gates of row 4m + gp
 #pragma unroll
         for (int m = 0; m < CPT; ++m) {
-          float a0 = __uint_as_float(v[4 * m]), a1 = __uint_as_float(v[4 * m + 1]), a2 = __uint_as_float(v[4 * m + 2]),
-                a3 = __uint_as_float(v[4 * m + 3]);
-          {
-            const float x = (gp & 1) ? a0 : a1, y = (gp & 1) ? a2 : a3;
-            const float xr = __shfl_xor_sync(0xffffffffu, x, 1), yr = __shfl_xor_sync(0xffffffffu, y, 1);
-            if (gp & 1) { a0 = xr; a2 = yr; } else { a1 = xr; a3 = yr; }
+          const int o = 8 * (m >> 1) + (m & 1);
+          if (t < len[m]) {
+            g[m].x += __uint_as_float(v[o]); g[m].y += __uint_as_float(v[o + 2]);
+            g[m].z += __uint_as_float(v[o + 4]); g[m].w += __uint_as_float(v[o + 6]);
           }
-          {
-            const float x = (gp & 2) ? a0 : a2, y = (gp & 2) ? a1 : a3;
-            const float xr = __shfl_xor_sync(0xffffffffu, x, 2), yr = __shfl_xor_sync(0xffffffffu, y, 2);
-            if (gp & 2) { a0 = xr; a1 = yr; } else { a2 = xr; a3 = yr; }
-          }
-          if (t < len[m]) { g[m].x += a0; g[m].y += a1; g[m].z += a2; g[m].w += a3; }
         }
       }
       float hv[CPT], cv[CPT];
@@ -1181,7 +1199,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       }
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
-        const int r = cgp * (R / 2) + 4 * m + gp;
+        const int r = cgp * (R / 2) + 8 * (m >> 1) + 2 * gp + (m & 1);
         *reinterpret_cast<__nv_bfloat16*>(img_u0 + (s & 1) * NC * IMG + r * 128 + (((ul >> 3) ^ (r & 7)) << 4)) = __float2bfloat16_rn(hv[m]);
       }
       fence_proxy_async();                         // generic-proxy smem writes -> visible to the bulk (async proxy) copies
@@ -1372,6 +1390,8 @@ static int rec_q_fwd_launch(cudaStream_t st, RecClParams& p, const void* whh_bf,
   }
   CUtensorMap tmW, tmX, tmWx, tmH;
   p.whh = (const __nv_bfloat16*)whh_bf;
+  p.wih = (const __nv_bfloat16*)wih_bf;
+  p.kp = Kp;
   int rc = make_tmap_bf16(&tmW, whh_bf, ndir * 4 * S, S, S, 256);
   if (rc) return rc;
   const bool si = p.rs_seq < p.rs_batch;

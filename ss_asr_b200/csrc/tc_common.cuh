@@ -149,6 +149,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[30]), "r"(v[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// TMEM -> registers, 16 lanes x 256 bits (8 columns) from lane taddr.lane (a multiple of 16): thread t of the warp gets rows
+// t/4 (v[0], v[1]) and t/4 + 8 (v[2], v[3]) of the block, columns 2 (t % 4) and 2 (t % 4) + 1 (verified: scripts/mma_ts_bench.cu)
+__device__ __forceinline__ void tmem_ld_16x256(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // one row-major bf16 matrix row (n_words packed pairs, a multiple of 32, 16-byte aligned) -> this thread's TMEM lane, columns
 // taddr.col .. + n_words (the A-operand layout of mma_bf16_ts); whole warp, lane i of the warp = TMEM lane taddr.lane + i
