@@ -22,6 +22,7 @@ CPU legs (`cpu_baseline`, `--impl reference`): oracle/cpu_arm.py -- the UNMODIFI
 `config.cpu_sample_batch`.
 """
 import argparse
+import gc
 import json
 import os
 import random
@@ -302,7 +303,12 @@ class Ctx:
         torch.cuda.synchronize()
 
     def timed(self, fn, steps):
-        """CUDA-event time of `steps` calls of fn, bracketed by barrier + synchronize, max over ranks (ms)."""
+        """CUDA-event time of `steps` calls of fn, bracketed by barrier + synchronize, max over ranks (ms).
+        The cyclic garbage collector is run before and held off during the timed region, as a training loop does that must not
+        lose a 25 ms generation-2 pass in the middle of a step (seen as one 32 ms host step in the end-to-end runs, where the
+        host is never more than one step ahead of the device)."""
+        gc.collect()
+        gc.disable()
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -310,6 +316,7 @@ class Ctx:
             fn()
         e1.record()
         self.barrier()
+        gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
         if self.world > 1:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
@@ -639,9 +646,14 @@ def run_train(cx):
             t_prev = t_now
         if st['pending'] is not None:
             consume(st['pending'])
-    e2e_run(max(3, args.warmup))                 # same allocator / pinned-buffer state as the timed run
+    e2e_run(max(6, 2 * args.warmup))             # same allocator / pinned-buffer state as the timed run
+    ms0 = torch.cuda.memory_stats(dev)
     ms_e2e = cx.timed(lambda: e2e_run(args.steps), 1)
+    ms1 = torch.cuda.memory_stats(dev)
     host_ms = sorted(st['host_ms'])
+    e2e_allocs = {'cudaMalloc': ms1.get('num_device_alloc', 0) - ms0.get('num_device_alloc', 0),
+                  'cudaFree': ms1.get('num_device_free', 0) - ms0.get('num_device_free', 0),
+                  'slowest_host_step_index': int(max(range(len(st['host_ms'])), key=lambda i: st['host_ms'][i]))}
     e2e_run(max(3, args.warmup), True)
     ms_e2e_strict = cx.timed(lambda: e2e_run(args.steps, True), 1)
     model.att_async = False
@@ -732,6 +744,7 @@ def run_train(cx):
                     'result_read': 'loss + attention maps of every step copied to pinned host memory and read by the host one step '
                                    'behind its enqueue front (double-buffered); the last step inside the timed region',
                     'host_ms_per_step': {'median': host_ms[len(host_ms) // 2], 'max': host_ms[-1]},
+                    'allocator_calls_in_timed_region': e2e_allocs,
                     'sync_each_step': {'value': world * B * args.steps / (ms_e2e_strict / 1e3), 'ms_per_step': ms_e2e_strict / args.steps}},
             'gpu_launches': launches, 'launches_per_step': launches / args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
             'fp32_exact_ms_per_step': fp32_ms, 'comm': comm, 'extra': extra}

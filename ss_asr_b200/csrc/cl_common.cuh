@@ -69,6 +69,15 @@ __device__ __forceinline__ void bulk_load_mc(void* sdst, const void* gsrc, uint3
       ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+// own shared memory -> the same CTA-relative offset `sdst` in cluster CTA `rank`, completing its bytes on the mbarrier at offset
+// `bar` of that CTA (DSMEM bulk copy: no round trip through L2)
+__device__ __forceinline__ void bulk_copy_dsmem(void* sdst, const void* ssrc, uint32_t bytes, uint64_t* bar, uint32_t rank) {
+  uint32_t rdst, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(sdst)), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(rdst), "r"(smem_u32(ssrc)), "r"(bytes), "r"(rbar) : "memory");
+}
 // swizzled shared-memory tile -> global tensor (rows outside the tensor are clipped); joins the thread's bulk group
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* ssrc, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"

@@ -127,6 +127,7 @@ int rec_cl_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cb
 // 16-CTA cluster recurrent kernels for S = 512 (rec_wide.cu): the long-utterance configuration
 int rec_wide_supported(int S, int n_batch, int backward);
 int rec_ks_supported(int S, int n_batch);     // K-split backward at S = 256 / 128 (rec_wide_bwd runs it)
+int rec_dsmem_enabled();                      // cluster exchange by DSMEM bulk copies (SSASR_REC_DSMEM=0: through the L2 ring)
 int rec_wide_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
                  int n_seq, int n_batch, long long rs_seq, long long rs_batch);
 int rec_wide_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, const int* lens,

@@ -77,6 +77,7 @@ struct RecClParams {
   const __nv_bfloat16* whh;  // rec_q_fwd: packed W_hh [n_dir * 4S, S] bf16 (row-major): the resident slice goes to TENSOR memory
   const __nv_bfloat16* wih;  // rec_q_fwd, fused input projection: packed W_ih [n_dir * 4S, kp] bf16
   int kp;
+  int dsmem;                 // rec_q_fwd: the h image goes to the peers by DSMEM bulk copies instead of through the L2 ring
 };
 
 #define CL_STAMP(idx)                                                                                            \
@@ -1040,9 +1041,16 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         CL_STAMP(8);
         uint8_t* img_s = Hsm + ((s & 1) * NC + slice) * IMG;       // the image = this CTA's k-block of the tile h(s)
         if (s + 1 < p.n_seq) {
-          bulk_store_wait(slot, img_s, IMG);
-          CL_STAMP(9);
-          bulk_load_mc(img_s, slot, IMG, a_full + (s & 1), cmask);
+          if (p.dsmem) {
+            // shared -> shared of every peer.  The image (buffer s & 1) is rewritten at step s + 2, after this CTA has received
+            // the peers' h(s + 1), which they computed after consuming THESE copies
+            for (int d = 0; d < NC; ++d)
+              if (d != slice) bulk_copy_dsmem(img_s, img_s, IMG, a_full + (s & 1), (uint32_t)d);
+          } else {
+            bulk_store_wait(slot, img_s, IMG);
+            CL_STAMP(9);
+            bulk_load_mc(img_s, slot, IMG, a_full + (s & 1), cmask);
+          }
           CL_STAMP(6);
         }
         // bf16 copy of h (next layer's input, weight-gradient operand): the image IS the swizzled TMA box
@@ -1392,6 +1400,7 @@ static int rec_q_fwd_launch(cudaStream_t st, RecClParams& p, const void* whh_bf,
   p.whh = (const __nv_bfloat16*)whh_bf;
   p.wih = (const __nv_bfloat16*)wih_bf;
   p.kp = Kp;
+  p.dsmem = rec_dsmem_enabled();
   int rc = make_tmap_bf16(&tmW, whh_bf, ndir * 4 * S, S, S, 256);
   if (rc) return rc;
   const bool si = p.rs_seq < p.rs_batch;

@@ -59,6 +59,7 @@ struct RecWideP {
   long long rs_seq, rs_batch;
   long long* dbg;            // optional [n_seq][12] clock64 stamps of CTA (0,0,0)
   const __nv_bfloat16* w;    // fwd: packed W_hh [8S, S]; bwd: W_hh^T [2S, 4S] (bf16, row-major): the resident slice -> TENSOR memory
+  int dsmem;                 // bwd: partial sums go to their owners by DSMEM bulk copies instead of through the L2 ring
 };
 constexpr int RW_WCOL = 64;  // TMEM: accumulators in columns [0, 64), the resident weight slice (A operand) from column 64
 #define RW_STAMP(idx)                                                                                            \
@@ -225,7 +226,7 @@ struct KsGeom {
   static constexpr int OFF_W = 0;                   // W_hh^T slice: [NH][KB] blocks of [128 units x 128 B]
   static constexpr int OFF_DG = OFF_W + NH * KB * 16384;
   static constexpr int OFF_DHOUT = OFF_DG + KB * 2048;
-  static constexpr int OFF_DHIN = OFF_DHOUT + NC * DHB;
+  static constexpr int OFF_DHIN = OFF_DHOUT + 2 * NC * DHB;   // outgoing partial sums double-buffered (DSMEM mode)
   static constexpr int OFF_BARS = OFF_DHIN + 2 * NC * DHB;
   static constexpr int SMEM = OFF_BARS + 16 * 8 + 1024;
   static constexpr int TCOLS = 512;                 // accumulators [0, NH * 16) + the W_hh^T slice from column RW_WCOL: NH x G/2 columns
@@ -296,13 +297,23 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_ks_bwd_kernel(const __grid_
       const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
       for (int s = 0; s + 1 < n_steps; ++s) {
         uint8_t* slot = p.ring + ((size_t)(s % RW_RING) * n_cta + cta) * GE::SLOT;
+        const uint8_t* out = dhout + (s & 1) * NC * DHB;
         mbar_wait_t(dh_ready, s & 1);
         RW_STAMP(8);
-        bulk_store_wait(slot, dhout, NC * DHB);
-        RW_STAMP(9);
-        for (int d = 0; d < NC; ++d)
-          bulk_load_mc(dhin + ((s & 1) * NC + r) * DHB, slot + d * DHB, DHB, dh_full + (s & 1), (uint16_t)(1u << d));
-        RW_STAMP(10);
+        if (p.dsmem) {
+          // shared -> shared of the owner CTA, completing its bytes on the owner's barrier.  The outgoing buffer of step s is
+          // rewritten at step s + 2, after this CTA has received the peers' partial sums of step s + 1, which they computed
+          // after consuming THESE copies
+          for (int d = 0; d < NC; ++d)
+            bulk_copy_dsmem(dhin + ((s & 1) * NC + r) * DHB, out + d * DHB, DHB, dh_full + (s & 1), (uint32_t)d);
+          RW_STAMP(10);
+        } else {
+          bulk_store_wait(slot, out, NC * DHB);
+          RW_STAMP(9);
+          for (int d = 0; d < NC; ++d)
+            bulk_load_mc(dhin + ((s & 1) * NC + r) * DHB, slot + d * DHB, DHB, dh_full + (s & 1), (uint16_t)(1u << d));
+          RW_STAMP(10);
+        }
       }
     }
     __syncwarp();
@@ -437,7 +448,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_ks_bwd_kernel(const __grid_
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           const int unit = 128 * h + 32 * sp + lane;             // unit inside the direction
-          uint8_t* dst = dhout + (unit / UNITS) * DHB + (unit % UNITS) * 2;
+          uint8_t* dst = dhout + (s & 1) * NC * DHB + (unit / UNITS) * DHB + (unit % UNITS) * 2;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<__nv_bfloat16*>(dst + (cgrp * 4 + c) * (UNITS * 2)) = __float2bfloat16_rn(__uint_as_float(v[h][c]));
@@ -541,6 +552,17 @@ int env_on(const char* name) {
 
 }  // namespace
 
+// cluster exchange by DSMEM bulk copies (default) or through the L2 ring (SSASR_REC_DSMEM=0): measured 2 818 against 3 251
+// cycles per backward step (S = 256, quad clusters)
+int rec_dsmem_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SSASR_REC_DSMEM");
+    on = e ? atoi(e) : 1;                         // 2: the 16-CTA clusters of S = 512 too (A/B switch)
+  }
+  return on;
+}
+
 // 1 when the 16-CTA cluster kernels can run this layer with every (direction, 16-utterance tile) cluster co-resident
 int rec_wide_supported(int S, int n_batch, int backward) {
   static int on = -1;
@@ -586,6 +608,7 @@ int rec_wide_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* 
   p.ring = rw_ring_for(st);
   p.dbg = g_rw_dbg;
   p.w = (const __nv_bfloat16*)whhT_bf;
+  p.dsmem = rec_dsmem_enabled() >= (S == 512 ? 2 : 1);
   SSASR_REQUIRE(p.ring != nullptr, "rec_wide_bwd: cannot allocate the exchange ring");
   CUtensorMap tmWT;
   int rc = make_tmap_bf16(&tmWT, whhT_bf, 2 * S, 4 * S, 4 * S, 128);
