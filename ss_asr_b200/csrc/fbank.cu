@@ -472,27 +472,39 @@ __global__ void __launch_bounds__(NTP, 4) fbank400q_kernel(FbankParams p) {
       const float2* prow = reinterpret_cast<const float2*>(Pw) + pq * QPB;
       float* orow = outp + (2 * pq) * p.n_mels;
       const bool has_b = 2 * pq + 1 < nfr;
-      int2 mm = __ldg(p.mel_meta + (tid >> 3));
-      for (int i = tid >> 3; i < p.n_mels; i += NTP / FPAIRS) {
-        const int in = i + NTP / FPAIRS;
-        int2 mn = mm;
-        if (in < p.n_mels) mn = __ldg(p.mel_meta + in);            // next item's filter: in flight under this one
-        const float4* wt = reinterpret_cast<const float4*>(p.mel_w4 + mm.y);
-        const float2* pw = prow + (mm.x & 0xffff);
-        const float2* pe = pw + (mm.x >> 16);
-        float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
+      constexpr int IS = NTP / FPAIRS;           // mel stride between a thread's items
+      for (int i0 = tid >> 3; i0 < p.n_mels; i0 += 4 * IS) {
+        // four items at a time: their filter metadata, then their first four weights, are all in flight together (one item
+        // after the other exposed two dependent L1 latencies per item to a warp that has only 19 others to hide behind)
+        int2 mm[4];
+        float4 w0[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mm[j] = i0 + j * IS < p.n_mels ? __ldg(p.mel_meta + i0 + j * IS) : make_int2(0, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          w0[j] = (mm[j].x >> 16) > 0 ? __ldg(reinterpret_cast<const float4*>(p.mel_w4 + mm[j].y)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = i0 + j * IS;
+          if (i >= p.n_mels) break;
+          const float4* wt = reinterpret_cast<const float4*>(p.mel_w4 + mm[j].y) + 1;
+          const float2* pw = prow + (mm[j].x & 0xffff);
+          const float2* pe = pw + (mm[j].x >> 16);
+          float sa0 = 0.f, sb0 = 0.f, sa1 = 0.f, sb1 = 0.f;
+          float4 w4 = w0[j];
 #pragma unroll 1
-        for (; pw < pe; pw += 4, ++wt) {
-          const float4 w4 = __ldg(wt);
-          const float2 p0 = pw[0], p1 = pw[1], p2 = pw[2], p3 = pw[3];
-          sa0 = fmaf(w4.x, p0.x, sa0); sb0 = fmaf(w4.x, p0.y, sb0);
-          sa1 = fmaf(w4.y, p1.x, sa1); sb1 = fmaf(w4.y, p1.y, sb1);
-          sa0 = fmaf(w4.z, p2.x, sa0); sb0 = fmaf(w4.z, p2.y, sb0);
-          sa1 = fmaf(w4.w, p3.x, sa1); sb1 = fmaf(w4.w, p3.y, sb1);
+          for (; pw < pe; pw += 4, ++wt) {
+            const float4 wn = pw + 4 < pe ? __ldg(wt) : w4;          // next four weights: under this iteration's FMAs
+            const float2 p0 = pw[0], p1 = pw[1], p2 = pw[2], p3 = pw[3];
+            sa0 = fmaf(w4.x, p0.x, sa0); sb0 = fmaf(w4.x, p0.y, sb0);
+            sa1 = fmaf(w4.y, p1.x, sa1); sb1 = fmaf(w4.y, p1.y, sb1);
+            sa0 = fmaf(w4.z, p2.x, sa0); sb0 = fmaf(w4.z, p2.y, sb0);
+            sa1 = fmaf(w4.w, p3.x, sa1); sb1 = fmaf(w4.w, p3.y, sb1);
+            w4 = wn;
+          }
+          __stcs(orow + i, ln_fast(sa0 + sa1 + 2.220446049250313e-16f));
+          if (has_b) __stcs(orow + p.n_mels + i, ln_fast(sb0 + sb1 + 2.220446049250313e-16f));
         }
-        __stcs(orow + i, ln_fast(sa0 + sa1 + 2.220446049250313e-16f));
-        if (has_b) __stcs(orow + p.n_mels + i, ln_fast(sb0 + sb1 + 2.220446049250313e-16f));
-        mm = mn;
       }
     }
     // group g+1: its prefetch into THIS buffer is issued after its B1, which no thread passes before everybody has finished
