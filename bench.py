@@ -462,7 +462,7 @@ def measure_fbank(cx, steps=5, small=False, with_cpu=True):
     out = {'workload': workload_config('fbank', cx.world)['workload'], 'utterances': n_utt * cx.world,
            'utt_per_s': n_utt * cx.world / (ms / 1e3), 'audio_s_per_s': n_utt * cx.world * 10.0 / (ms / 1e3), 'ms': ms,
            'gpu_launches': launches,
-           'roofline': {'kernel': 'fbank400p_kernel', 'bound': 'hbm', 'achieved': byts / (ms / 1e3) / 1e9, 'peak': cx.hbm, 'unit': 'GB/s',
+           'roofline': {'kernel': 'fbank400q_kernel', 'bound': 'hbm', 'achieved': byts / (ms / 1e3) / 1e9, 'peak': cx.hbm, 'unit': 'GB/s',
                         'frac': byts / (ms / 1e3) / 1e9 / cx.hbm, 'traffic': ncu_traffic('fbank'), 'peak_source': cx.peak_src,
                         'algorithmic_bytes_per_launch': byts, 'launches_per_step': launches, 'ms_per_step_in_kernel': ms,
                         'share_of_step': 1.0}}

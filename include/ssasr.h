@@ -237,6 +237,7 @@ void ssasr_rec_cl_set_debug(long long* dev_buf /*[n_seq][12], cluster recurrent 
 int ssasr_rec_cl_capacity(int S, int backward); /* co-resident (direction, tile) clusters of the cluster recurrence; 0 = unavailable */
 void ssasr_rec_cl_enable(int on);              /* 0: counter-barrier recurrent kernels everywhere (A/B comparison) */
 void ssasr_rec_wide_set_debug(long long* dev_buf /*[n_seq][12], K-split backward kernels (rec_wide.cu)*/);
+void ssasr_rec_set_dsmem(int mode);            /* cluster exchange of the recurrent kernels: 1 DSMEM bulk copies (default), 0 through the L2 ring, 2 DSMEM for the 16-CTA clusters too (A/B comparison) */
 void ssasr_spell_cl_set_debug(long long* dev_buf /*[steps][8], cluster decoder-step kernels (spell_cl.cu)*/);
 void ssasr_spell_cl_set_debug_bwd(long long* dev_buf /*[steps][8], backward kernel*/);
 void ssasr_spell_cl_set_debug_mode(int plain_recurrence /*1: stamp the layer-2 (plain recurrence) launches instead*/);

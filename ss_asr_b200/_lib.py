@@ -93,6 +93,7 @@ SIGNATURES = {
     'ssasr_rec_cl_enable': (None, [_I]),
     'ssasr_rec_q_set_rows': (None, [_I]),
     'ssasr_rec_wide_set_debug': (None, [_P]),
+    'ssasr_rec_set_dsmem': (None, [_I]),
     'ssasr_spell_cl_set_debug': (None, [_P]),
     'ssasr_spell_cl_set_debug_bwd': (None, [_P]),
     'ssasr_spell_cl_set_debug_mode': (None, [_I]),

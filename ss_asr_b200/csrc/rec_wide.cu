@@ -561,13 +561,13 @@ int env_on(const char* name) {
 
 // cluster exchange by DSMEM bulk copies (default) or through the L2 ring (SSASR_REC_DSMEM=0): measured 2 818 against 3 251
 // cycles per backward step (S = 256, quad clusters)
+static int g_rec_dsmem = -1;
 int rec_dsmem_enabled() {
-  static int on = -1;
-  if (on < 0) {
+  if (g_rec_dsmem < 0) {
     const char* e = getenv("SSASR_REC_DSMEM");
-    on = e ? atoi(e) : 1;                         // 2: the 16-CTA clusters of S = 512 too (A/B switch)
+    g_rec_dsmem = e ? atoi(e) : 1;                // 2: the 16-CTA clusters of S = 512 too (A/B switch)
   }
-  return on;
+  return g_rec_dsmem;
 }
 
 // 1 when the 16-CTA cluster kernels can run this layer with every (direction, 16-utterance tile) cluster co-resident
@@ -632,4 +632,5 @@ int rec_wide_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* 
 extern "C" {
 // debug: device buffer [n_seq][12] of clock64 stamps written by CTA (0,0,0) of the next K-split backward launches
 void ssasr_rec_wide_set_debug(long long* dev_buf) { ssasr::g_rw_dbg = dev_buf; }
+void ssasr_rec_set_dsmem(int mode) { ssasr::g_rec_dsmem = mode < 0 ? 0 : mode; }
 }

@@ -514,9 +514,10 @@ def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
     res = {}
     stamps = torch.zeros(T + 2, 12, dtype=torch.int64, device=DEV)     # one row per step; odd T runs T + 1 (padded) steps
     try:
-        for name, rows, on in (('quad16', 16, 1), ('quad32', 32, 1), ('cl8', 0, 1), ('counter', 0, 0)):
+        for name, rows, on in (('quad16', 16, 1), ('quad16_ring', 16, 1), ('quad32', 32, 1), ('cl8', 0, 1), ('counter', 0, 0)):
             lib.ssasr_rec_q_set_rows(rows)
             lib.ssasr_rec_cl_enable(on)
+            lib.ssasr_rec_set_dsmem(0 if name.endswith('_ring') else 1)      # cluster exchange through the L2 ring / by DSMEM copies
             stamps.zero_()
             lib.ssasr_rec_cl_set_debug(stamps.data_ptr())
             x = x0.clone().to(DEV).requires_grad_(True)
@@ -532,9 +533,10 @@ def test_cluster_recurrence_matches_counter_barrier_kernels(S, B, T, K):
     finally:
         lib.ssasr_rec_q_set_rows(16)
         lib.ssasr_rec_cl_enable(1)
+        lib.ssasr_rec_set_dsmem(1)
         lib.ssasr_rec_cl_set_debug(None)
     b = res['counter']
-    for name in ('quad16', 'quad32', 'cl8'):
+    for name in ('quad16', 'quad16_ring', 'quad32', 'cl8'):
         a = res[name]
         assert float((a[0] - b[0]).abs().max()) < 2e-3, name
         assert float(a[1].norm()) > 0 and float((a[1] - b[1]).norm()) <= 5e-3 * float(b[1].norm()), name
