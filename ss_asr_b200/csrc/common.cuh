@@ -96,6 +96,8 @@ int gemm_bf16_tc_tn(cudaStream_t st, int M, int N, int K, const void* A, long lo
 // fp32-accurate tensor-core GEMM: tf32 x 3 split (gemm_tc.cu)
 int split_bf16(cudaStream_t st, const float* x, void* hi, void* lo, size_t n);
 int split_hi_lo_2d(cudaStream_t st, const float* x, long long ld, int rows, int cols, float* hi, float* lo);
+int split3_bf16(cudaStream_t st, const float* x, long long ld, long long rows, int K, void* out, int second);
+int x3_gemm_bf16();
 int split_hi_lo(cudaStream_t st, const float* x, float* hi, float* lo, size_t n);
 int gemm_tf32x3(cudaStream_t st, int M, int N, int K, const float* A, const float* A_lo, long long lda, const float* B,
                 const float* B_lo, long long ldb, float* C, int ldc, const float* bias, int act_tanh);
@@ -108,6 +110,9 @@ int cvt_bf16_t(cudaStream_t st, const float* src, long long ld_src, void* dst, l
 int rec_tc_supported(int S);
 int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, float* cbuf, void* hb, const int* lens, int S,
                int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
+// exact split-operand forward recurrence on the quad clusters (rec_cl.cu); -1: geometry not covered, use rec_tc_fwd_x3
+int rec_q_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, const int* lens, int S, int n_seq,
+                 int n_batch, long long rs_seq, long long rs_batch);
 int rec_tc_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, float* cbuf, void* hb_hi,
                   void* hb_lo, const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,

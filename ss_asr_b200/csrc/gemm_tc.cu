@@ -595,6 +595,50 @@ int split_bf16(cudaStream_t st, const float* x, void* hi, void* lo, size_t n) {
   return 0;
 }
 
+// Split-operand product as ONE plain bf16 GEMM over a three times longer reduction axis:
+//   A B^T ~= A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T = [A_hi | A_hi | A_lo] [B_hi | B_lo | B_hi]^T
+// (x = hi + lo in bf16, residual 2^-17 relative; the dropped lo*lo term is 2^-18): the persistent tcgen05 kernel runs it at the
+// bf16 rate (2 x the tf32 rate of gemm_tf32x3_kernel) with its double-buffered accumulators.  This kernel writes the
+// concatenated operand: rows of 3K bf16, `second` selects the [hi | lo | hi] order of the B side.  K % 8 == 0.
+__global__ void split3_bf16_kernel(const float* __restrict__ x, long long ld, long long rows, int K, __nv_bfloat16* __restrict__ out,
+                                   int second) {
+  const int kc = K / 8;
+  const long long n = rows * kc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / kc;
+    const int c = (int)(i % kc) * 8;
+    const float4 v0 = *reinterpret_cast<const float4*>(x + r * ld + c), v1 = *reinterpret_cast<const float4*>(x + r * ld + c + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16(v[2 * j]), h1 = __float2bfloat16(v[2 * j + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16(v[2 * j] - __bfloat162float(h0)), l1 = __float2bfloat16(v[2 * j + 1] - __bfloat162float(h1));
+      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const uint4 H = make_uint4(h[0], h[1], h[2], h[3]), L = make_uint4(l[0], l[1], l[2], l[3]);
+    __nv_bfloat16* o = out + r * 3 * K + c;
+    *reinterpret_cast<uint4*>(o) = H;
+    *reinterpret_cast<uint4*>(o + K) = second ? L : H;
+    *reinterpret_cast<uint4*>(o + 2 * K) = second ? H : L;
+  }
+}
+int split3_bf16(cudaStream_t st, const float* x, long long ld, long long rows, int K, void* out, int second) {
+  if (rows <= 0 || K <= 0) return 0;
+  SSASR_REQUIRE(K % 8 == 0 && ld % 4 == 0, "split3_bf16: K %% 8 == 0 and ld %% 4 == 0 required (K=%d ld=%lld)", K, ld);
+  ProfScope ps(F_PACK, st);
+  const long long n = rows * (K / 8);
+  split3_bf16_kernel<<<(unsigned)((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256), 256, 0, st>>>(x, ld, rows, K, (__nv_bfloat16*)out, second);
+  SSASR_LAUNCH_CHECK();
+  return 0;
+}
+// 1: split-operand products run as bf16 GEMMs over [hi | hi | lo] x [hi | lo | hi] (default); 0 (SSASR_X3_GEMM=tf32): tf32 x 3 kernel
+int x3_gemm_bf16() {
+  const char* e = getenv("SSASR_X3_GEMM");
+  return (e && e[0] == 't') ? 0 : 1;
+}
+
 __global__ void split_hi_lo_2d_kernel(const float* __restrict__ x, long long ld, int rows, int cols, float* __restrict__ hi,
                                       float* __restrict__ lo) {
   const long long n = (long long)rows * cols;

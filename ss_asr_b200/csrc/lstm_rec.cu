@@ -564,7 +564,17 @@ int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
   cudaStream_t st = (cudaStream_t)stream;
   SSASR_REQUIRE(S % 16 == 0, "blstm_fwd: S=%d must be a multiple of 16", S);
   int rc;
-  if (tf32_ws && K % 4 == 0) {
+  if (tf32_ws && K % 8 == 0 && x3_gemm_bf16()) {
+    // input projection as ONE bf16 tcgen05 GEMM over the tripled reduction axis [hi | hi | lo] x [hi | lo | hi] (6 bytes per
+    // operand element of the 8 the workspace holds)
+    __nv_bfloat16* xa = (__nv_bfloat16*)tf32_ws;
+    __nv_bfloat16* wb = xa + (size_t)n_rows * 3 * K;
+    rc = split3_bf16(st, x, K, n_rows, K, xa, 0);
+    if (rc) return rc;
+    rc = split3_bf16(st, wih_p, K, 8 * S, K, wb, 1);
+    if (rc) return rc;
+    rc = gemm_bf16_tc(st, n_rows, 8 * S, 3 * K, xa, 3 * K, 0, wb, 3 * K, 0, xp, 8 * S, bias_p, 0, 0, 1);
+  } else if (tf32_ws && K % 4 == 0) {
     // input projection on tensor cores with the tf32 x 3 split (hi/lo pairs of x and W_ih in tf32_ws)
     float* xh = tf32_ws;
     float* xl = xh + (size_t)n_rows * K;
@@ -587,6 +597,9 @@ int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
     __nv_bfloat16* hl = hh + (size_t)n_rows * 2 * S;
     rc = split_bf16(st, whh_p, wh, wl, (size_t)8 * S * S);
     if (rc) return rc;
+    // the quad-cluster kernel where it applies (S = 128 / 256, more than a few dependent steps): hout only
+    rc = rec_q_fwd_x3(st, xp, wh, wl, hout, lens, S, n_seq, n_batch, rs_seq, rs_batch);
+    if (rc >= 0) return rc;
     return rec_tc_fwd_x3(st, xp, wh, wl, hout, cbuf, hh, hl, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar);
   }
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));

@@ -78,6 +78,7 @@ struct RecClParams {
   const __nv_bfloat16* wih;  // rec_q_fwd, fused input projection: packed W_ih [n_dir * 4S, kp] bf16
   int kp;
   int dsmem;                 // rec_q_fwd: the h image goes to the peers by DSMEM bulk copies instead of through the L2 ring
+  const __nv_bfloat16* whh_lo;   // rec_q_fwd<.., X3>: low parts of W_hh (whh holds the high parts)
 };
 
 #define CL_STAMP(idx)                                                                                            \
@@ -925,12 +926,20 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 // buffers) -- no staging tiles.  The bf16 h copy (next layer's input / weight-gradient operand) is TMA-stored from the image.
 // XF: the layer's input projection is fused in exactly as in rec_cl_fwd_kernel<true>.
 // ------------------------------------------------------------------------------------------------
-template <int R, bool XF>
+// X3 (forward-only exact path: greedy decoding / validation): W_hh and h are split into bf16 hi + lo parts and the product is
+// W_hi h_hi + W_hi h_lo + W_lo h_hi (fp32-accurate: what rec_tc_fwd_kernel<.., X3> computes, at the cluster kernel's step
+// latency).  W_hi is the TMEM-resident A operand of the first two terms, W_lo lives in shared memory (SS form) in the SAME
+// permuted row order; a producer's image carries the hi and the lo k-block of its 64 units; precise expf / tanhf; only
+// `hout` is written (no activations / cell states: nothing runs backward through this path).
+template <int R, bool XF, bool X3 = false>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                  const __grid_constant__ CUtensorMap tmWx, const __grid_constant__ CUtensorMap tmH, RecClParams p) {
   constexpr int W_BLK = 256 * 128;       // one k-block of the weight slice: 256 gate rows x 64 bf16
-  constexpr int IMG = R * 128;           // one k-block of the h tile = one producer's image: R rows x 64 units bf16
+  constexpr int IMG = R * 128;           // one k-block of the h tile: R rows x 64 units bf16
+  constexpr int PARTS = X3 ? 2 : 1;      // operand parts of h (hi [, lo])
+  constexpr int IMGX = PARTS * IMG;      // one producer's image: its k-block of every part
+  static_assert(!(X3 && XF), "the exact path takes its pre-activations from the split-operand GEMM");
   constexpr int WX_BLK = 256 * 32;       // fused projection: 256 gate rows x 16 bf16
   constexpr int X_BLK = R * 32;          // fused projection: R rows x 16 bf16
   constexpr int CPT = R / 8;             // cells (batch rows of ONE unit) per epilogue thread
@@ -941,8 +950,8 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int S = p.S, KB = S / 64, NC = S / Q_UNITS;
   uint8_t* Wsm = smem;                                                   // [KB] blocks of W_BLK
-  uint8_t* Hsm = Wsm + KB * W_BLK;                                       // [2][NC] k-blocks of IMG
-  uint8_t* img = Hsm + 2 * NC * IMG;                                     // this CTA's outgoing image
+  uint8_t* Hsm = Wsm + KB * W_BLK;                                       // [2][NC][PARTS] k-blocks of IMG
+  uint8_t* img = Hsm + 2 * NC * IMGX;                                    // (spare: the image is written in place)
   uint8_t* Wx = img + (IMG < 1024 ? 1024 : IMG);                         // XF: [nkx] k-blocks of WX_BLK
   uint8_t* Xs = Wx + (XF ? FW_MAXKX * WX_BLK : 0);                       // XF: [2][nkx] k-blocks of X_BLK
   float* bsm = reinterpret_cast<float*>(Xs + (XF ? 2 * FW_MAXKX * X_BLK : 0));   // XF: [256] gate bias slice
@@ -958,11 +967,13 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 
   const int slice = blockIdx.x, dir = blockIdx.y, bt = blockIdx.z;      // cluster = the NC CTAs along x
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tile_bytes = (uint32_t)(NC - 1) * IMG;      // the CTA's own slice of h is written in place by its epilogue
+  const uint32_t tile_bytes = (uint32_t)(NC - 1) * IMGX;     // the CTA's own slice of h is written in place by its epilogue
   const int seq_inner = p.rs_seq < p.rs_batch ? 1 : 0;
   if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmH);
+    if (!X3) {
+      tma_prefetch_desc(&tmW);
+      tma_prefetch_desc(&tmH);
+    }
     mbar_init(w_full, 1);
     mbar_init(a_full, 1);
     mbar_init(a_full + 1, 1);
@@ -982,8 +993,10 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp == 0 && elect_one()) {
-    mbar_expect_tx(w_full, KB * W_BLK + (XF ? p.nkx * WX_BLK : 0));
-    for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * 4 * S + slice * 256);
+    if (!X3) {
+      mbar_expect_tx(w_full, KB * W_BLK + (XF ? p.nkx * WX_BLK : 0));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * W_BLK, kb * 64, dir * 4 * S + slice * 256);
+    }
     if (XF)
       for (int kx = 0; kx < p.nkx; ++kx) tma_load_3d(&tmWx, w_full, Wx + kx * WX_BLK, kx * 16, dir * 4 * S + slice * 256, 0);
     mbar_expect_tx(a_full, tile_bytes);          // h(0) and h(1); re-armed by the MMA thread after each wait
@@ -998,6 +1011,16 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const size_t grow = (size_t)dir * 4 * S + slice * 256 + half_ * 128 + (q_ * 8 + (lane & 7)) * 4 + (lane >> 3);
     const uint32_t tl = tmem + ((uint32_t)(q_ * 32) << 16);
     tmem_store_row(tl + (uint32_t)(WCOL + half_ * (S / 2) + kh_ * (S / 4)), p.whh + grow * S + kh_ * (S / 2), S / 4);
+    if (X3) {
+      // the low part of the slice -> shared memory, SW128 K-major k-blocks of 256 rows, row i = the TMEM lane order above
+      const uint4* src = reinterpret_cast<const uint4*>(p.whh_lo + grow * S + kh_ * (S / 2));
+      const int i = half_ * 128 + q_ * 32 + lane;
+      for (int j = 0; j < S / 16; ++j) {           // 16-byte chunks of this thread's half row
+        const int kg = kh_ * (S / 2) + j * 8, kb = kg >> 6, c = (kg & 63) >> 3;
+        *reinterpret_cast<uint4*>(Wsm + kb * W_BLK + i * 128 + ((c ^ (i & 7)) << 4)) = __ldg(src + j);
+      }
+      fence_proxy_async();
+    }
     if (XF && kh_ == 0) {                        // the W_ih slice of the fused input projection, same row order
       const uint4* xr = reinterpret_cast<const uint4*>(p.wih + grow * p.kp);
       const int nq = p.kp / 8;                   // 16-byte groups of the row
@@ -1036,27 +1059,29 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       }
       for (int s = 0; s < p.n_seq; ++s) {
         const int t = dir == 0 ? s : p.n_seq - 1 - s;
-        uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * IMG;
+        uint8_t* slot = p.ring + ((size_t)(s % CL_RING) * n_cta + cta) * IMGX;
         mbar_wait_t(stage_ready, s & 1);                           // all 256 epilogue threads have written the image
         CL_STAMP(8);
-        uint8_t* img_s = Hsm + ((s & 1) * NC + slice) * IMG;       // the image = this CTA's k-block of the tile h(s)
+        uint8_t* img_s = Hsm + ((s & 1) * NC + slice) * IMGX;      // the image = this CTA's k-block(s) of the tile h(s)
         if (s + 1 < p.n_seq) {
           if (p.dsmem) {
             // shared -> shared of every peer.  The image (buffer s & 1) is rewritten at step s + 2, after this CTA has received
             // the peers' h(s + 1), which they computed after consuming THESE copies
             for (int d = 0; d < NC; ++d)
-              if (d != slice) bulk_copy_dsmem(img_s, img_s, IMG, a_full + (s & 1), (uint32_t)d);
+              if (d != slice) bulk_copy_dsmem(img_s, img_s, IMGX, a_full + (s & 1), (uint32_t)d);
           } else {
-            bulk_store_wait(slot, img_s, IMG);
+            bulk_store_wait(slot, img_s, IMGX);
             CL_STAMP(9);
-            bulk_load_mc(img_s, slot, IMG, a_full + (s & 1), cmask);
+            bulk_load_mc(img_s, slot, IMGX, a_full + (s & 1), cmask);
           }
           CL_STAMP(6);
         }
         // bf16 copy of h (next layer's input, weight-gradient operand): the image IS the swizzled TMA box
-        tma_store_3d(&tmH, img_s, dir * S + slice * Q_UNITS, seq_inner ? t : bt * R, seq_inner ? bt * R : t);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (!X3) {
+          tma_store_3d(&tmH, img_s, dir * S + slice * Q_UNITS, seq_inner ? t : bt * R, seq_inner ? bt * R : t);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
         mbar_arrive(img_free);
         if (XF && s + 2 < p.n_seq) load_x(s + 2);                  // the MMAs of step s (reading Xs[s & 1]) completed before its epilogue
       }
@@ -1071,12 +1096,13 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       // every operand of the step's MMAs is a base + a compile-time offset: nothing but the instructions themselves sits
       // between the arrival of the exchanged tile and the commit (the issue loop with computed descriptors took 28 cycles
       // per instruction, three times the tensor core's own 8 - 13)
-      const uint64_t dH[2] = {umma_desc_k128(smem_u32(Hsm)), umma_desc_k128(smem_u32(Hsm + NC * IMG))};
+      const uint64_t dH[2] = {umma_desc_k128(smem_u32(Hsm)), umma_desc_k128(smem_u32(Hsm + NC * IMGX))};
+      const uint64_t dWl = umma_desc_k128(smem_u32(Wsm));           // X3: low part of the slice (half 1: + 128 rows = 16 KB)
       const uint32_t aw0 = tmem + WCOL, aw1 = tmem + WCOL + S / 2;
-      const uint64_t own_h = (uint64_t)((slice * IMG) >> 4);
+      const uint64_t own_h = (uint64_t)((slice * IMGX) >> 4);
       const uint32_t own_a = (uint32_t)(slice * 32);
       for (int s = XF ? 0 : 1; s < p.n_seq; ++s) {
-        if (s == (XF ? 0 : 1)) mbar_wait_t(w_full, 0);
+        if (!X3 && s == (XF ? 0 : 1)) mbar_wait_t(w_full, 0);
         if (XF) {
           // input projection of step s: independent of the recurrence, issued (and executing) while h(s-1) is exchanged
           if (s > 0) mbar_wait_t(tmem_free, (s - 1) & 1);          // epilogue has drained the accumulators
@@ -1103,6 +1129,14 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           for (int kq = 0; kq < 4; ++kq) {
             mma_bf16_ts(tmem, aw0 + own_a + kq * 8, dhb + own_h + (uint64_t)(kq * 2), idesc, (XF || kq != 0) ? 1u : 0u);
             mma_bf16_ts(tmem + R, aw1 + own_a + kq * 8, dhb + own_h + (uint64_t)(kq * 2), idesc, (XF || kq != 0) ? 1u : 0u);
+            if (X3) {
+              const uint64_t dlo = dhb + own_h + (uint64_t)(IMG >> 4) + (uint64_t)(kq * 2);
+              const uint64_t dw = dWl + (uint64_t)((slice * W_BLK) >> 4) + (uint64_t)(kq * 2);
+              mma_bf16_ts(tmem, aw0 + own_a + kq * 8, dlo, idesc, 1u);
+              mma_bf16_ts(tmem + R, aw1 + own_a + kq * 8, dlo, idesc, 1u);
+              mma_bf16_ss(tmem, dw, dhb + own_h + (uint64_t)(kq * 2), idesc, 1u);
+              mma_bf16_ss(tmem + R, dw + (uint64_t)(16384 >> 4), dhb + own_h + (uint64_t)(kq * 2), idesc, 1u);
+            }
           }
           mbar_wait_t(a_full + b, ((s - 1) >> 1) & 1);               // the NC - 1 remote slices of h(s-1) have landed
           if (s + 2 < p.n_seq) mbar_expect_tx(a_full + b, tile_bytes);   // this buffer next receives h(s+1)
@@ -1111,9 +1145,16 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < 16; ++kk) {
             if (kk < nk && (kk >> 2) != slice) {
-              const uint64_t dh = dhb + (uint64_t)(((kk >> 2) * IMG) >> 4) + (uint64_t)((kk & 3) * 2);
+              const uint64_t dh = dhb + (uint64_t)(((kk >> 2) * IMGX) >> 4) + (uint64_t)((kk & 3) * 2);
               mma_bf16_ts(tmem, aw0 + kk * 8, dh, idesc, 1u);
               mma_bf16_ts(tmem + R, aw1 + kk * 8, dh, idesc, 1u);
+              if (X3) {
+                const uint64_t dw = dWl + (uint64_t)(((kk >> 2) * W_BLK) >> 4) + (uint64_t)((kk & 3) * 2);
+                mma_bf16_ts(tmem, aw0 + kk * 8, dh + (uint64_t)(IMG >> 4), idesc, 1u);
+                mma_bf16_ts(tmem + R, aw1 + kk * 8, dh + (uint64_t)(IMG >> 4), idesc, 1u);
+                mma_bf16_ss(tmem, dw, dh, idesc, 1u);
+                mma_bf16_ss(tmem + R, dw + (uint64_t)(16384 >> 4), dh, idesc, 1u);
+              }
             }
           }
         }
@@ -1146,7 +1187,7 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     float creg[CPT];
 #pragma unroll
     for (int m = 0; m < CPT; ++m) creg[m] = 0.f;
-    uint8_t* img_u0 = Hsm + slice * IMG + (ul & 7) * 2;   // own k-block of tile buffer 0: + row*128 + swizzled 16-byte chunk (ul >> 3)
+    uint8_t* img_u0 = Hsm + slice * IMGX + (ul & 7) * 2;   // own k-block of tile buffer 0: + row*128 + swizzled 16-byte chunk (ul >> 3)
 
     // pre-activations are fetched ONE WHOLE STEP ahead (registers): a load issued at the top of its own step is not back
     // when the accumulator is (measured: the epilogue then stalls on HBM latency under the kernel's own store bursts)
@@ -1198,9 +1239,15 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         hv[m] = 0.f; cv[m] = 0.f;
         if (t < len[m]) {
-          a.x = sigmoid_apx(g[m].x); a.y = sigmoid_apx(g[m].y); a.z = tanh_apx(g[m].z); a.w = sigmoid_apx(g[m].w);
-          cv[m] = fmaf(a.y, creg[m], a.x * a.z);
-          hv[m] = a.w * tanh_apx(cv[m]);
+          if (X3) {
+            a.x = sigmoidf_acc(g[m].x); a.y = sigmoidf_acc(g[m].y); a.z = tanhf(g[m].z); a.w = sigmoidf_acc(g[m].w);
+            cv[m] = a.y * creg[m] + a.x * a.z;
+            hv[m] = a.w * tanhf(cv[m]);
+          } else {
+            a.x = sigmoid_apx(g[m].x); a.y = sigmoid_apx(g[m].y); a.z = tanh_apx(g[m].z); a.w = sigmoid_apx(g[m].w);
+            cv[m] = fmaf(a.y, creg[m], a.x * a.z);
+            hv[m] = a.w * tanh_apx(cv[m]);
+          }
         }
         creg[m] = cv[m];
         g[m] = a;
@@ -1208,7 +1255,10 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         const int r = cgp * (R / 2) + 8 * (m >> 1) + 2 * gp + (m & 1);
-        *reinterpret_cast<__nv_bfloat16*>(img_u0 + (s & 1) * NC * IMG + r * 128 + (((ul >> 3) ^ (r & 7)) << 4)) = __float2bfloat16_rn(hv[m]);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(hv[m]);
+        uint8_t* dst = img_u0 + (s & 1) * NC * IMGX + r * 128 + (((ul >> 3) ^ (r & 7)) << 4);
+        *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+        if (X3) *reinterpret_cast<__nv_bfloat16*>(dst + IMG) = __float2bfloat16_rn(hv[m] - __bfloat162float(hi));
       }
       fence_proxy_async();                         // generic-proxy smem writes -> visible to the bulk (async proxy) copies
       __syncwarp();
@@ -1219,9 +1269,11 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
       for (int m = 0; m < CPT; ++m) {
         if (inr[m]) {
           const size_t row = (size_t)t * p.rs_seq + rowb[m];
-          __stcs(reinterpret_cast<float4*>(p.xp + row * p.gld + gcol), g[m]);
           p.hout[row * p.hld + hcol] = hv[m];
-          p.cbuf[row * p.hld + hcol] = cv[m];
+          if (!X3) {
+            __stcs(reinterpret_cast<float4*>(p.xp + row * p.gld + gcol), g[m]);
+            p.cbuf[row * p.hld + hcol] = cv[m];
+          }
         }
       }
       if (threadIdx.x == 64) CL_STAMP(7);
@@ -1380,8 +1432,8 @@ int rec_cl_capacity(int S, int backward) {
 
 // x_bf / wih_bf / bias non-null: the input projection is fused in (x_bf [rows, Kp] bf16, wih_bf [8S, Kp] bf16, bias [8S]);
 // xp then is an output only (saved activations).  Otherwise xp holds the pre-activations computed by the batched GEMM.
-static size_t fwdq_smem(int S, int R, bool xf) {
-  return (size_t)(S / 64) * 32768 + (size_t)2 * (S / Q_UNITS) * R * 128 + (R * 128 < 1024 ? 1024 : R * 128) + 10 * 8 + 16 + 1024 +
+static size_t fwdq_smem(int S, int R, bool xf, int parts = 1) {
+  return (size_t)(S / 64) * 32768 + (size_t)2 * (S / Q_UNITS) * R * 128 * parts + (R * 128 < 1024 ? 1024 : R * 128) + 10 * 8 + 16 + 1024 +
          (xf ? (size_t)FW_MAXKX * 256 * 32 + 2 * FW_MAXKX * R * 32 + 1024 : 0);
 }
 
@@ -1459,6 +1511,46 @@ int rec_cl_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
   if (rc) return rc;
   ProfScope ps(F_REC_TC_FWD, st);
   return cluster_launch(rec_cl_fwd_kernel<true>, grid, S / CL_UNITS, fwd_smem(S, true), st, tmW, tmX, tmWx, p);
+}
+
+// Exact (split-operand) forward recurrence on the quad clusters: xp [rows, 8S] fp32 pre-activations (split-operand GEMM),
+// whh_hi / whh_lo [8S, S] bf16 parts of the packed W_hh; writes hout only.  Clusters are independent of one another, so the
+// grid may exceed what is co-resident (it then runs in waves).  Returns -1 where the geometry is not covered.
+template <int R>
+static int rec_q_fwd_x3_launch(cudaStream_t st, RecClParams& p) {
+  const int S = p.S;
+  p.gld = (long long)8 * S;
+  p.hld = (long long)2 * S;
+  const size_t smem = fwdq_smem(S, R, false, 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSASR_CHECK_CUDA(cudaFuncSetAttribute(rec_q_fwd_kernel<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)fwdq_smem(256, R, false, 2)));
+    attr_set = true;
+  }
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));                    // the exact path uses no tensor map (operands by DSMEM / plain loads)
+  dim3 grid(S / Q_UNITS, 2, (p.n_batch + R - 1) / R);
+  const size_t n_cta = (size_t)grid.x * grid.y * grid.z;
+  p.dsmem = (rec_dsmem_enabled() || (size_t)CL_RING * n_cta * 2 * R * 128 > RING_BYTES) ? 1 : 0;
+  ProfScope ps(F_REC_TC_FWD, st);
+  return cluster_launch_t(Q_THREADS, rec_q_fwd_kernel<R, false, true>, grid, S / Q_UNITS, smem, st, tm, tm, tm, tm, p);
+}
+
+int rec_q_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, const int* lens, int S, int n_seq,
+                 int n_batch, long long rs_seq, long long rs_batch) {
+  if (!cl_enabled() || !(S == 128 || S == 256) || n_seq < 4) return -1;
+  const char* e = getenv("SSASR_REC_Q_X3");
+  if (e && e[0] == '0') return -1;
+  RecClParams p = {};
+  p.xp = xp; p.hout = hout; p.lens = lens;
+  p.S = S; p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
+  p.whh = (const __nv_bfloat16*)whh_hi; p.whh_lo = (const __nv_bfloat16*)whh_lo;
+  p.dbg = g_cl_dbg;
+  p.ring = ring_for(st);
+  SSASR_REQUIRE(p.ring != nullptr, "rec_q_fwd_x3: cannot allocate the exchange ring");
+  const int R = (e && atoi(e) == 16) ? 16 : 32;
+  return R == 16 ? rec_q_fwd_x3_launch<16>(st, p) : rec_q_fwd_x3_launch<32>(st, p);
 }
 
 // largest padded input width the fused forward projection accepts

@@ -460,6 +460,46 @@ def test_decode_tf32x3_strings_and_gemm(golden_dir):
         assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
 
 
+@pytest.mark.parametrize('S,B,T', [(128, 37, 72), (256, 70, 136), (256, 3, 40)])
+def test_exact_cluster_recurrence_matches_fp32_path(S, B, T):
+    """Forward-only exact path of the decode Listener: the split-operand quad-cluster recurrence (`rec_q_fwd_kernel<R,false,true>`:
+    W_hi in tensor memory, W_lo in shared memory, hi + lo h images exchanged inside the cluster) against the fp32 SIMT path
+    (itself pinned to the reference goldens) and against the counter-barrier X3 kernels it replaces: ragged lengths, partial
+    batch tiles, both tile heights, batched (seq-first `blstm_4` quirk, asr.py:262) and per-utterance `blstm_4`.
+    Tolerance 5e-6 on |h| <= 1 (measured 4e-7 .. 9e-7, the same as the kernels it replaces)."""
+    dims = (50, S, 32, 16, 24)
+    sd = O.make_state_dict(*dims, seed=2)
+    x, lens, _ = O.synth_batch(B, T, 24, 4, seed=5)
+    m = _model(dims, sd).eval()
+    xd = x.to(DEV)
+
+    def enc(prec, env):
+        if env is None:
+            os.environ.pop('SSASR_REC_Q_X3', None)
+        else:
+            os.environ['SSASR_REC_Q_X3'] = env
+        m.encoder.set_precision(prec)
+        try:
+            with torch.no_grad():
+                e, el = m.encoder(xd, lens)
+            torch.cuda.synchronize()
+        finally:
+            m.encoder.set_precision('fp32')
+            os.environ.pop('SSASR_REC_Q_X3', None)
+        return e
+
+    for indep in (False, True):
+        m.encoder.utterance_independent = indep
+        ref = enc('fp32', None)
+        old = enc('tf32x3', '0')
+        for env in (None, '16'):
+            new = enc('tf32x3', env)
+            assert not bool(torch.isnan(new).any())
+            assert float((new - ref).abs().max()) < 5e-6, (indep, env)
+            assert float((new - old).abs().max()) < 2e-6, (indep, env)
+    m.encoder.utterance_independent = False
+
+
 def test_per_step_module_api_matches_fused_forward():
     """Attention.forward / Speller.forward called one step at a time (text_autoencoder.py:52-94 usage) reproduce the
     oracle's logits and gradients, i.e. the TAE/SAE/ADV trainers' call pattern keeps working on the drop-in modules."""
