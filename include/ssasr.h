@@ -18,7 +18,7 @@ extern "C" {
 const char* ssasr_last_error(void);
 /* Bumped whenever a signature or an argument struct of this header changes; the ctypes binding (ss_asr_b200/_lib.py) refuses
  * to bind a library whose version differs from the one it was written for (a stale .so would silently mis-read structs). */
-#define SSASR_ABI_VERSION 3
+#define SSASR_ABI_VERSION 4
 int ssasr_abi_version(void);
 
 /* ---- log-mel filterbank: preprocess.py:187-208 log_fbank(y, sample_rate) (librosa 0.6.3 melspectrogram) ---- */
@@ -129,7 +129,8 @@ typedef struct {
   float lm_weight;
   const float *lm_emb, *lm_w1i, *lm_w1h, *lm_b1i, *lm_b1h, *lm_w2i, *lm_w2h, *lm_b2i, *lm_b2h, *lm_wo, *lm_bo;
   float *lm_h1, *lm_h2;
-  float* x3_ws; /* NULL, or 2*B*max(X1,X2) + 8*Sd*(X1+X2) floats: forward-only gate GEMMs on tensor cores (tf32 x 3) */
+  float* x3_ws; /* NULL, or 2*B*(X1+X2) + 8*Sd*(X1+X2) floats: forward-only gate GEMMs on tensor cores with split operands
+                   (bf16 [hi|hi|lo] x [hi|lo|hi] rows by default; tf32 x 3 pairs with SSASR_X3_GEMM=tf32) */
   int skip_final_logits; /* 1: do not recompute the [B,U,C] logits after the loop (greedy decoding only needs tok_in) */
   int dual_stream;       /* bf16 mode: ws_bf holds B*X1 + U*B*X2 elements (a layer-2 input block per step) and the layer-2
                             chain (asr.py:322-324) runs on an internal second stream, joined into `stream` before returning */

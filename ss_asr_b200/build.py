@@ -20,7 +20,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 # precise math everywhere (no --use_fast_math): greedy parity depends on it
 CFLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
           '-Xcompiler', '-O2', '-I', INCLUDE]
-ABI_VERSION = 3          # must equal SSASR_ABI_VERSION in include/ssasr.h (checked by _lib.load)
+ABI_VERSION = 4          # must equal SSASR_ABI_VERSION in include/ssasr.h (checked by _lib.load)
 
 
 def sources():

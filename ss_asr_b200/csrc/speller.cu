@@ -37,6 +37,7 @@ struct AttnFwd {
   float* cell_cout; long long cco_ld;        // [B,Sd] c1 of the previous step
   float* cell_hout; long long cho_ld;        // [B,Sd] h1 of the previous step, fp32 (layer-2 input row)
   __nv_bfloat16* cell_hb; long long chb_ld;  // [B,Sd] the same in bf16 (layer-2 GEMM operand), or null
+  int skip_emb;                              // 1: the embedding part of the row is written by emb_rows_kernel (two-stream greedy loop)
 };
 
 // LSTM cell, one unit: gates (i,f,g,o pre-activations) -> activations in place; returns h, writes c
@@ -51,7 +52,17 @@ __device__ __forceinline__ float lstm_cell_unit(float4* gp, float cp, float* c_o
 }
 
 // hi = rn_tf32(v), lo = rn_tf32(v - hi): the operand split of the tf32 x 3 GEMM (gemm_tc.cu), fused into the producers
-__device__ __forceinline__ void put_hi_lo(float* hi, float* lo, size_t i, float v) {
+// lo == nullptr: `hi` is the bf16 operand of the tripled-K bf16 GEMM instead (rows of 3 ld: [hi | hi | lo], split3_bf16)
+__device__ __forceinline__ void put_hi_lo(float* hi, float* lo, size_t b, long long ld, size_t col, float v) {
+  if (lo == nullptr) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(hi) + b * 3 * ld + col;
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    o[0] = h;
+    o[ld] = h;
+    o[2 * ld] = __float2bfloat16(v - __bfloat162float(h));
+    return;
+  }
+  const size_t i = b * ld + col;
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   const float h = __uint_as_float(r);
@@ -130,15 +141,15 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
     }
     hs[k] = h;
     xrow[a.Sd + a.E + k] = h;
-    const float e = a.emb_w ? a.emb_w[(size_t)tk * a.Sd + k] : 0.f;
-    xrow[k] = e;
+    const float e = (a.emb_w && !a.skip_emb) ? a.emb_w[(size_t)tk * a.Sd + k] : 0.f;
+    if (!a.skip_emb) xrow[k] = e;
     if (a.xin1b) {
       a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + a.E + k] = __float2bfloat16(h);
-      a.xin1b[(size_t)b * a.xin1b_ld + k] = __float2bfloat16(e);
+      if (!a.skip_emb) a.xin1b[(size_t)b * a.xin1b_ld + k] = __float2bfloat16(e);
     }
     if (a.x3h) {
-      put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + a.Sd + a.E + k, h);
-      put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + k, e);
+      put_hi_lo(a.x3h, a.x3l, (size_t)b, a.x3_ld, a.Sd + a.E + k, h);
+      if (!a.skip_emb) put_hi_lo(a.x3h, a.x3l, (size_t)b, a.x3_ld, k, e);
     }
   }
   __syncthreads();
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
       const float sv = part[c] + part[a.E + c];
       xrow[a.Sd + c] = sv;
       if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(sv);
-      if (a.x3h) put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + a.Sd + c, sv);
+      if (a.x3h) put_hi_lo(a.x3h, a.x3l, (size_t)b, a.x3_ld, a.Sd + c, sv);
     }
   } else {
     for (int c = tid; c < a.E; c += blockDim.x) {
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
       for (int j = 0; j < len; ++j) sv = fmaf(es[j], encb[(size_t)j * a.E + c], sv);
       xrow[a.Sd + c] = sv;
       if (a.xin1b) a.xin1b[(size_t)b * a.xin1b_ld + a.Sd + c] = __float2bfloat16(sv);
-      if (a.x3h) put_hi_lo(a.x3h, a.x3l, (size_t)b * a.x3_ld + a.Sd + c, sv);
+      if (a.x3h) put_hi_lo(a.x3h, a.x3l, (size_t)b, a.x3_ld, a.Sd + c, sv);
     }
   }
 }
@@ -572,6 +583,19 @@ static int attn_outer_accum(cudaStream_t st, int B, int U, int Tp, int D, const 
   return 0;
 }
 
+// embedding part of the step-input rows (two-stream greedy loop: the token is selected on the layer-2 stream while the
+// attention step that writes the rest of the row already runs): xin1[b, 0:Sd] = emb[tok[b]] (+ the split-operand copy)
+__global__ void emb_rows_kernel(int B, int Sd, const float* __restrict__ emb_w, const int* __restrict__ tok, long long tok_ld,
+                                float* __restrict__ xin1, long long xin1_ld, float* __restrict__ x3h, float* __restrict__ x3l,
+                                long long x3_ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Sd) return;
+  const int b = i / Sd, k = i % Sd;
+  const float e = emb_w[(size_t)tok[(size_t)b * tok_ld] * Sd + k];
+  xin1[(size_t)b * xin1_ld + k] = e;
+  if (x3h) put_hi_lo(x3h, x3l, (size_t)b, x3_ld, k, e);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LSTM cell pointwise (gates interleaved: col = unit*4 + gate)
 // ------------------------------------------------------------------------------------------------
@@ -590,14 +614,14 @@ __global__ void cell_fwd_kernel(int B, int S, float* __restrict__ gates, long lo
   const float h = lstm_cell_unit(gp, cp, cout + (size_t)b * c_ld + u);
   hout[(size_t)b * h_ld + u] = h;
   if (hb_out) hb_out[(size_t)b * hb_ld + u] = __float2bfloat16(h);
-  if (x3h) put_hi_lo(x3h, x3l, (size_t)b * x3_ld + u, h);
+  if (x3h) put_hi_lo(x3h, x3l, (size_t)b, x3_ld, u, h);
   if (h_dst2) h_dst2[(size_t)b * hd2_ld + u] = h;
   if (hb_dst2) hb_dst2[(size_t)b * hbd2_ld + u] = __float2bfloat16(h);
   if (cp_dst) {
     const float v = cp_src ? cp_src[(size_t)b * cps_ld + u] : 0.f;
     cp_dst[(size_t)b * cpd_ld + u] = v;
     if (hb_out) hb_out[(size_t)b * hb_ld + hb_cp_off + u] = __float2bfloat16(v);
-    if (x3h) put_hi_lo(x3h, x3l, (size_t)b * x3_ld + hb_cp_off + u, v);
+    if (x3h) put_hi_lo(x3h, x3l, (size_t)b, x3_ld, hb_cp_off + u, v);
   }
 }
 
@@ -918,12 +942,23 @@ static SideStream* side_stream(int n_events) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32 || n_events > 512) return nullptr;
   SideStream* ss = &pool[dev];
-  if (!ss->s && cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) { ss->s = nullptr; return nullptr; }
+  if (!ss->s) {
+    // highest priority: its short kernels take the SMs that the long kernel of the main stream (attention over all utterances,
+    // several waves of CTAs) frees, instead of queueing behind its undispatched CTAs
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&ss->s, cudaStreamNonBlocking, hi) != cudaSuccess) { ss->s = nullptr; cudaGetLastError(); return nullptr; }
+  }
   while (ss->n_ev < n_events) {
     if (cudaEventCreateWithFlags(&ss->ev[ss->n_ev], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ++ss->n_ev;
   }
   return ss;
+}
+// 0 (SSASR_DECODE_DUAL=0): greedy decoding keeps every launch of a step on one stream
+static int decode_dual_on() {
+  const char* e = getenv("SSASR_DECODE_DUAL");
+  return (e && e[0] == '0') ? 0 : 1;
 }
 static int step_gemm_splits() {
   static int v = -1;
@@ -1044,15 +1079,28 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   __nv_bfloat16* x2b = tc ? x1b + (size_t)B * X1 : nullptr;
   const bool x3 = !tc && a->x3_ws && X1 % 4 == 0 && X2 % 4 == 0;
   float *xh = nullptr, *xl = nullptr, *w1h = nullptr, *w1l = nullptr, *w2h = nullptr, *w2l = nullptr;
+  float* xh2 = nullptr;                              // x3b: operand rows of the layer-2 product (else they share xh / xl)
+  // x3b: the split-operand gate products as bf16 GEMMs over the tripled reduction axis (the producers then write bf16
+  // [hi | hi | lo] rows into the same workspace and `xl` stays null); else the tf32 x 3 kernel on fp32 hi / lo pairs
+  const bool x3b = x3 && X1 % 8 == 0 && X2 % 8 == 0 && x3_gemm_bf16();
   if (x3) {
     const int Xm = X1 > X2 ? X1 : X2;
     xh = a->x3_ws; xl = xh + (size_t)B * Xm;
-    w1h = xl + (size_t)B * Xm; w1l = w1h + (size_t)4 * Sd * X1;
+    w1h = xh + (size_t)2 * B * (X1 + X2); w1l = w1h + (size_t)4 * Sd * X1;
     w2h = w1l + (size_t)4 * Sd * X1; w2l = w2h + (size_t)4 * Sd * X2;
-    rc = split_hi_lo(st, a->w1cat, w1h, w1l, (size_t)4 * Sd * X1);
-    if (rc) return rc;
-    rc = split_hi_lo(st, a->w2cat, w2h, w2l, (size_t)4 * Sd * X2);
-    if (rc) return rc;
+    if (x3b) {
+      xl = nullptr;
+      xh2 = xh + ((size_t)3 * B * X1 + 1) / 2;        // the layer-2 input rows have their own block: [B, 3 X1] bf16, then [B, 3 X2]
+      rc = split3_bf16(st, a->w1cat, X1, 4 * Sd, X1, w1h, 1);
+      if (rc) return rc;
+      rc = split3_bf16(st, a->w2cat, X2, 4 * Sd, X2, w2h, 1);
+      if (rc) return rc;
+    } else {
+      rc = split_hi_lo(st, a->w1cat, w1h, w1l, (size_t)4 * Sd * X1);
+      if (rc) return rc;
+      rc = split_hi_lo(st, a->w2cat, w2h, w2l, (size_t)4 * Sd * X2);
+      if (rc) return rc;
+    }
   }
   // bf16 mode: layer-2 chain on a second stream (one layer-2 input block per step in ws_bf)
   // cluster-persistent step kernel for the teacher-forced runs (spell_cl.cu); needs one layer-2 input block per step in ws_bf
@@ -1072,6 +1120,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     if (tc) return gemm_bf16_tc(st, B, 4 * Sd, K, xb, K, 0, w_bf, K, 0, out, U * 4 * Sd, bias, 0, 0, splits);
     if (x3) {                  // xh / xl were written by the kernel that produced x (attention step / layer-1 cell)
       const bool first = (K == X1);
+      if (x3b) return gemm_bf16_tc(st, B, 4 * Sd, 3 * K, first ? xh : xh2, 3 * K, 0, first ? w1h : w2h, 3 * K, 0, out, U * 4 * Sd, bias, 0, 0, 1);
       return gemm_tf32x3(st, B, 4 * Sd, K, xh, xl, K, first ? w1h : w2h, first ? w1l : w2l, K, out, U * 4 * Sd, bias, 0);
     }
     return gemm_f32(st, B, 4 * Sd, K, x, ldx, 1, w, K, 1, out, U * 4 * Sd, bias, 0, 0);
@@ -1087,8 +1136,9 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   }
   auto mode_of = [&](int t) { return a->step_mode ? a->step_mode[t] : 0; };
   // attention step t (+ the step's input row); fuse_prev: the layer-1 cell of step t-1 runs in its prologue
-  auto attn_step = [&](int t, bool fuse_prev) {
+  auto attn_step = [&](int t, bool fuse_prev, bool skip_emb = false) {
     AttnFwd f{};
+    f.skip_emb = skip_emb ? 1 : 0;
     f.Tp = Tp; f.E = E; f.Sd = Sd; f.M = M;
     f.h1prev = t ? a->xin2 + (size_t)(t - 1) * X2 : nullptr; f.h1_ld = (long long)U * X2;
     f.phi_w = a->phi_w; f.psi = a->psi; f.enc = a->enc; f.enc_lens = a->enc_lens;
@@ -1116,7 +1166,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
                                                  a->c1 + (size_t)t * Sd, (long long)U * Sd, a->xin2 + (size_t)t * X2,
                                                  (long long)U * X2, t ? a->h2all + (size_t)(t - 1) * Sd : nullptr,
                                                  (long long)U * Sd, copy_h2 ? a->xin2 + (size_t)t * X2 + Sd : nullptr,
-                                                 (long long)U * X2, x2b_at(t), X2, Sd, x3 ? xh : nullptr, x3 ? xl : nullptr, X2);
+                                                 (long long)U * X2, x2b_at(t), X2, Sd, x3 ? (x3b ? xh2 : xh) : nullptr, x3 ? xl : nullptr, X2);
   };
   // layer 2 of step t on stream s2 (+ token selection for step t+1, which consumes h2(t))
   auto layer2_cell = [&](int t, cudaStream_t s2) -> int {
@@ -1241,7 +1291,48 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   {
   const int stop_every = (!dual && a->stop_check_every > 0 && a->stop_scratch && a->skip_final_logits && a->step_mode &&
                           a->step_mode[0] != 0 && a->step_mode[0] != 2) ? a->stop_check_every : 0;
-  if (!dual) {
+  // greedy / LM decoding (every token selected on the device): the attention query of step t+1 is the LAYER-1 state of step t
+  // (asr.py:84), so the layer-2 chain of step t -- gate product, cell, character projection + selection, embedding row of the
+  // next step's input -- runs on a second stream UNDER the attention step t+1 (the longest kernel of a step) and joins before
+  // its gate product.  Needs the operand rows of the two gate products in separate blocks (x3b, or the fp32 SIMT path).
+  SideStream* gside = nullptr;
+  if (!dual && U > 1 && 2 * U + 2 <= 512 && (!x3 || x3b) && a->step_mode && decode_dual_on()) {
+    bool all_sel = true;
+    for (int t = 0; t + 1 < U; ++t) all_sel = all_sel && (a->step_mode[t] == 1 || a->step_mode[t] == 3);
+    if (all_sel) gside = side_stream(2 * U + 2);
+  }
+  if (gside) {
+    cudaStream_t s2 = gside->s;
+    int last_b = -1;
+    for (int t = 0; t < U; ++t) {
+      attn_step(t, false, t > 0);
+      if (t > 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, gside->ev[U + t - 1], 0));   // token t, its embedding row, h2(t-1)
+      rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b, 1);
+      if (rc) return rc;
+      cell1(t, true);
+      SSASR_HANDOVER(gside->ev[t], st, s2);
+      rc = layer2(t, s2);
+      if (rc) return rc;
+      if (t + 1 < U) {
+        ProfScope ps(F_POINTWISE, s2);
+        emb_rows_kernel<<<cell_blocks, 256, 0, s2>>>(B, Sd, a->emb_w, a->tok_in + t + 1, U, a->xin1 + (size_t)(t + 1) * X1,
+                                                     (long long)U * X1, x3 ? xh : nullptr, x3 ? xl : nullptr, X1);
+      }
+      SSASR_CHECK_CUDA(cudaEventRecord(gside->ev[U + t], s2));
+      last_b = t;
+      steps_done = t + 1;
+      if (stop_every > 0 && t + 1 < U && (t + 1) % stop_every == 0) {
+        SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, gside->ev[U + t], 0));
+        SSASR_CHECK_CUDA(cudaMemsetAsync(a->stop_scratch, 0, sizeof(int), st));
+        count_unfinished_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, a->tok_in, U, t + 1, a->stop_token, a->stop_scratch);
+        int open_utts = 1;
+        SSASR_CHECK_CUDA(cudaMemcpyAsync(&open_utts, a->stop_scratch, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSASR_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (open_utts == 0) break;
+      }
+    }
+    if (last_b >= 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, gside->ev[U + last_b], 0));
+  } else if (!dual) {
     for (int t = 0; t < U; ++t) {
       attn_step(t, false);
       rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b,

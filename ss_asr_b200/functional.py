@@ -334,7 +334,7 @@ class _Spell(torch.autograd.Function):
         ctx.bf16 = bf16
         x3ws = None
         if precision == 'tf32x3' and not torch.is_grad_enabled() and X1 % 4 == 0 and X2 % 4 == 0:
-            x3ws = torch.empty(2 * B * max(X1, X2) + 8 * Sd * (X1 + X2), device=dev)
+            x3ws = torch.empty(2 * B * (X1 + X2) + 8 * Sd * (X1 + X2), device=dev)
         cl_ws = None
         if bf16 and _DUAL_STREAM_SPELLER and _CLUSTER_SPELLER:
             nb = int(lib.ssasr_speller_cl_ws_bytes(B, Tp, E, Sd, M, Cc, U))

@@ -815,6 +815,36 @@ def test_decode_batch_encoder_chunking_is_invisible():
         assert outs[0] == [list(w) for w in want], prec
 
 
+def test_greedy_loop_two_streams_is_invisible():
+    """Greedy decoding runs the layer-2 chain of step t (gate product, cell, character projection + argmax, embedding row of the
+    next input) on a second stream under the attention step t+1 (asr.py:84: the query is the LAYER-1 state): tokens must be
+    identical to the single-stream loop (SSASR_DECODE_DUAL=0) and to the oracle's bs=1 decode, on both exact paths, with the
+    EOS check at several periods, several times in a row (race check)."""
+    dims = (50, 64, 64, 32, 40)
+    sd = O.make_state_dict(*dims, seed=3)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 20
+    g = torch.Generator().manual_seed(11)
+    Ts = sorted([int(v) for v in torch.randint(17, 90, (37,), generator=g)], reverse=True)
+    xb = torch.zeros(len(Ts), Ts[0], 40)
+    for i, t in enumerate(Ts):
+        xb[i, :t] = torch.randn(t, 40, generator=g)
+    m = _model(dims, sd).eval()
+    want = [list(O.decode_greedy(sd, xb[i:i + 1, :t], [t], max_steps=25)) for i, t in enumerate(Ts[:6])]
+    try:
+        for prec in ('fp32', 'tf32x3'):
+            os.environ['SSASR_DECODE_DUAL'] = '0'
+            single = m.decode_batch(xb.to(DEV), Ts, max_steps=25, precision=prec)
+            os.environ.pop('SSASR_DECODE_DUAL')
+            assert single[:6] == want, prec
+            for check in (16, 1, 0, 7):
+                m.decode_stop_check = check
+                for _ in range(3):
+                    assert m.decode_batch(xb.to(DEV), Ts, max_steps=25, precision=prec) == single, (prec, check)
+    finally:
+        os.environ.pop('SSASR_DECODE_DUAL', None)
+        m.decode_stop_check = 16
+
+
 @pytest.mark.parametrize('tf_rate', [1.0, 0.6])
 def test_dual_stream_speller_is_invisible(tf_rate):
     """bf16 path: the Speller's layer-2 chain on the internal second stream (forward and backward) runs the same kernels on the
