@@ -63,8 +63,9 @@ int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
                         float* cbuf /*[n_rows,2S]*/, unsigned* bar /*2 words scratch*/,
                         float* tf32_ws /*NULL: fp32 SIMT input projection; else 2*(n_rows+8S)*K floats scratch: the
                                          projection runs on tensor cores with the tf32 x 3 split (K % 4 == 0)*/,
-                        void* x3_ws /*NULL: fp32 SIMT recurrence; else (16*S*S + 4*n_rows*S) bf16 scratch and `bar` of 4096
-                                      words: recurrence on tensor cores with the bf16 hi/lo x 3 split (S % 64 == 0, S <= 256)*/,
+                        void* x3_ws /*NULL: fp32 SIMT recurrence; else (16*S*S + 4*n_rows*S) bf16 scratch (S == 512: 16*S*S) and `bar` of
+                                      4096 words: recurrence on tensor cores with the bf16 hi/lo x 3 split (S % 64 == 0, S <= 256,
+                                      or S == 512 on the 16-CTA clusters)*/,
                         void* stream);
 int ssasr_blstm_bwd_f32(const float* x, int n_rows, int K, const float* wih_p, const float* whhT_p, int S, int n_seq,
                         int n_batch, long long rs_seq, long long rs_batch, const int* lens,

@@ -26,7 +26,7 @@ def enc(m, x, lens, prec, env=None):
     return e
 
 
-for S, B, T in ((128, 37, 72), (256, 37, 72), (256, 70, 136), (256, 3, 40)):
+for S, B, T in ((128, 37, 72), (256, 37, 72), (256, 70, 136), (256, 3, 40), (512, 21, 72), (512, 40, 136)):
     dims = (50, S, 32, 16, 24)
     sd = O.make_state_dict(*dims, seed=2)
     x, lens, _ = O.synth_batch(B, T, 24, 4, seed=5)

@@ -113,6 +113,8 @@ int rec_tc_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, floa
 // exact split-operand forward recurrence on the quad clusters (rec_cl.cu); -1: geometry not covered, use rec_tc_fwd_x3
 int rec_q_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, const int* lens, int S, int n_seq,
                  int n_batch, long long rs_seq, long long rs_batch);
+int rec_wide_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, const int* lens, int S, int n_seq,
+                    int n_batch, long long rs_seq, long long rs_batch);     // the same at S = 512 (rec_wide.cu)
 int rec_tc_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, float* cbuf, void* hb_hi,
                   void* hb_lo, const int* lens, int S, int n_seq, int n_batch, long long rs_seq, long long rs_batch, unsigned* bar);
 int rec_tc_bwd(cudaStream_t st, float* act, const void* whhT_bf, const float* cbuf, const float* dhout, void* dgb, float* dcstate,

@@ -602,6 +602,15 @@ int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
     if (rc >= 0) return rc;
     return rec_tc_fwd_x3(st, xp, wh, wl, hout, cbuf, hh, hl, lens, S, n_seq, n_batch, rs_seq, rs_batch, bar);
   }
+  if (x3_ws && S == 512) {
+    // the 16-CTA cluster kernel with split operands (x3_ws: 16 S^2 bf16); the SIMT recurrence below where it does not apply
+    __nv_bfloat16* wh = (__nv_bfloat16*)x3_ws;
+    __nv_bfloat16* wl = wh + (size_t)8 * S * S;
+    rc = split_bf16(st, whh_p, wh, wl, (size_t)8 * S * S);
+    if (rc) return rc;
+    rc = rec_wide_fwd_x3(st, xp, wh, wl, hout, lens, S, n_seq, n_batch, rs_seq, rs_batch);
+    if (rc >= 0) return rc;
+  }
   SSASR_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st));
   RecFwdParams p;
   p.xp = xp; p.whh = whh_p; p.hout = hout; p.cbuf = cbuf; p.lens = lens;

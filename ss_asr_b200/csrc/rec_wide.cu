@@ -43,6 +43,8 @@ constexpr int FOFF_H = FOFF_W + 131072;                   // h tile [2 buffers][
 constexpr int FOFF_HIMG = FOFF_H + 2 * RW_NC * RW_HBLK;
 constexpr int FOFF_BARS = FOFF_HIMG + RW_HBLK;
 constexpr int RWF_SMEM = FOFF_BARS + 16 * 8 + 1024;
+constexpr int RWF_SMEM_X3 = FOFF_H + 2 * (2 * RW_NC * RW_HBLK) + 2 * RW_HBLK + 16 * 8 + 1024;   // hi + lo h images
+static_assert(RWF_SMEM_X3 <= 232448, "shared-memory map (exact path)");
 
 static_assert(RWF_SMEM <= 232448, "shared-memory map");
 
@@ -70,14 +72,20 @@ constexpr int RW_WCOL = 64;  // TMEM: accumulators in columns [0, 64), the resid
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// X3 (forward-only exact path, greedy decoding at S = 512): W_hh and h split into bf16 hi + lo parts, product
+// W_hi h_hi + W_hi h_lo + W_lo h_hi; W_hi is the TMEM-resident A operand, W_lo the shared-memory copy (tmW then maps the LOW
+// parts), a producer's image carries its hi and lo k-block; precise expf / tanhf; only `hout` is written.
+template <bool X3>
 __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecWideP p) {
   constexpr int S = RW_S;
+  constexpr int HB = (X3 ? 2 : 1) * RW_HBLK;       // one producer's image: its k-block of every operand part
+  constexpr int SLOT = X3 ? HB : RW_SLOT;          // exchange slot stride (the exact path packs them: grids beyond 160 CTAs)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* Wsm = smem + FOFF_W;
-  uint8_t* Hsm = smem + FOFF_H;
-  uint8_t* himg = smem + FOFF_HIMG;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FOFF_BARS);
+  uint8_t* Hsm = smem + FOFF_H;                    // [2 buffers][16 producers][parts][HBLK]
+  uint8_t* himg = Hsm + 2 * RW_NC * HB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(himg + HB);
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;            // [2]
   uint64_t* g_done = bars + 3;
@@ -105,8 +113,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
   if (warp == 0 && elect_one()) {
     mbar_expect_tx(w_full, 131072);
     for (int kb = 0; kb < 8; ++kb) tma_load_2d(&tmW, w_full, Wsm + kb * 16384, kb * 64, dir * 4 * S + r * 128);
-    mbar_expect_tx(a_full, RW_NC * RW_HBLK);
-    mbar_expect_tx(a_full + 1, RW_NC * RW_HBLK);
+    mbar_expect_tx(a_full, RW_NC * HB);
+    mbar_expect_tx(a_full + 1, RW_NC * HB);
   }
   if (warp >= 4) {
     // resident W_hh slice [128 gate rows x S] -> tensor memory: thread = one gate row, the four warps of a sub-partition
@@ -124,10 +132,10 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
       const size_t n_cta = (size_t)gridDim.x * gridDim.y * gridDim.z;
       const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
       for (int s = 0; s + 1 < n_steps; ++s) {
-        uint8_t* slot = p.ring + ((size_t)(s % RW_RING) * n_cta + cta) * RW_SLOT;
+        uint8_t* slot = p.ring + ((size_t)(s % RW_RING) * n_cta + cta) * SLOT;
         mbar_wait_t(stage_ready, s & 1);
-        bulk_store_wait(slot, himg, RW_HBLK);
-        bulk_load_mc(Hsm + ((s & 1) * RW_NC + r) * RW_HBLK, slot, RW_HBLK, a_full + (s & 1), cmask);
+        bulk_store_wait(slot, himg, HB);
+        bulk_load_mc(Hsm + ((s & 1) * RW_NC + r) * HB, slot, HB, a_full + (s & 1), cmask);
       }
     }
     __syncwarp();
@@ -138,12 +146,19 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
       for (int s = 1; s < n_steps; ++s) {                  // step 0 starts from the zero state: no product
         const int hb = (s - 1) & 1;
         mbar_wait_t(a_full + hb, ((s - 1) >> 1) & 1);
-        if (s + 2 < n_steps) mbar_expect_tx(a_full + hb, RW_NC * RW_HBLK);
+        if (s + 2 < n_steps) mbar_expect_tx(a_full + hb, RW_NC * HB);
         tc_fence_after();
-        const uint64_t dhb = umma_desc_k64(smem_u32(Hsm + hb * RW_NC * RW_HBLK));
+        const uint64_t dhb = umma_desc_k64(smem_u32(Hsm + hb * RW_NC * HB));
+        const uint64_t dWl = umma_desc_k128(smem_u32(Wsm));
 #pragma unroll
-        for (int kk = 0; kk < S / 16; ++kk)
-          mma_bf16_ts(tmem, tmem + RW_WCOL + kk * 8, dhb + (uint64_t)(((kk >> 1) * RW_HBLK) >> 4) + (uint64_t)((kk & 1) * 2), idesc, kk != 0);
+        for (int kk = 0; kk < S / 16; ++kk) {
+          const uint64_t dh = dhb + (uint64_t)(((kk >> 1) * HB) >> 4) + (uint64_t)((kk & 1) * 2);
+          mma_bf16_ts(tmem, tmem + RW_WCOL + kk * 8, dh, idesc, kk != 0);
+          if (X3) {
+            mma_bf16_ts(tmem, tmem + RW_WCOL + kk * 8, dh + (uint64_t)(RW_HBLK >> 4), idesc, 1u);
+            mma_bf16_ss(tmem, dWl + (uint64_t)(((kk >> 2) * 16384) >> 4) + (uint64_t)((kk & 3) * 2), dh, idesc, 1u);
+          }
+        }
         mma_commit(g_done);
       }
     }
@@ -186,21 +201,31 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       float cv = 0.f, hv = 0.f;
       if (valid) {
-        a.x = sigmoid_apx(g.x); a.y = sigmoid_apx(g.y); a.z = tanh_apx(g.z); a.w = sigmoid_apx(g.w);
-        cv = fmaf(a.y, creg, a.x * a.z);
-        hv = a.w * tanh_apx(cv);
+        if (X3) {
+          a.x = sigmoidf_acc(g.x); a.y = sigmoidf_acc(g.y); a.z = tanhf(g.z); a.w = sigmoidf_acc(g.w);
+          cv = a.y * creg + a.x * a.z;
+          hv = a.w * tanhf(cv);
+        } else {
+          a.x = sigmoid_apx(g.x); a.y = sigmoid_apx(g.y); a.z = tanh_apx(g.z); a.w = sigmoid_apx(g.w);
+          cv = fmaf(a.y, creg, a.x * a.z);
+          hv = a.w * tanh_apx(cv);
+        }
       }
       creg = cv;
-      *reinterpret_cast<__nv_bfloat16*>(himg_dst) = __float2bfloat16_rn(hv);
+      const __nv_bfloat16 hhi = __float2bfloat16_rn(hv);
+      *reinterpret_cast<__nv_bfloat16*>(himg_dst) = hhi;
+      if (X3) *reinterpret_cast<__nv_bfloat16*>(himg_dst + RW_HBLK) = __float2bfloat16_rn(hv - __bfloat162float(hhi));
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(stage_ready);
       if (inr) {
         const size_t row = (size_t)t * p.rs_seq + rowb;
-        __stcs(reinterpret_cast<float4*>(p.xp + row * 8 * S + gcol), a);
         p.hout[row * 2 * S + hcol] = hv;
-        p.cbuf[row * 2 * S + hcol] = cv;
-        p.xb[row * 2 * S + hcol] = __float2bfloat16_rn(hv);
+        if (!X3) {
+          __stcs(reinterpret_cast<float4*>(p.xp + row * 8 * S + gcol), a);
+          p.cbuf[row * 2 * S + hcol] = cv;
+          p.xb[row * 2 * S + hcol] = hhi;
+        }
       }
     }
   }
@@ -525,7 +550,7 @@ int g_rw_cap[4] = {-1, -1, -1, -1};
 int rw_capacity(int which) {
   if (g_rw_cap[which] < 0) {
     switch (which) {
-      case 0: g_rw_cap[0] = rw_query(rec_wide_fwd_kernel, RWF_SMEM, RW_NC); break;
+      case 0: g_rw_cap[0] = rw_query(rec_wide_fwd_kernel<false>, RWF_SMEM, RW_NC); break;
       case 1: g_rw_cap[1] = rw_query(rec_ks_bwd_kernel<512, 32>, KsGeom<512, 32>::SMEM, 16); break;
       case 2: g_rw_cap[2] = rw_query(rec_ks_bwd_kernel<256, 64>, KsGeom<256, 64>::SMEM, 4); break;
       default: g_rw_cap[3] = rw_query(rec_ks_bwd_kernel<128, 64>, KsGeom<128, 64>::SMEM, 2); break;
@@ -601,7 +626,30 @@ int rec_wide_fwd(cudaStream_t st, float* xp, const void* whh_bf, float* hout, fl
   int rc = make_tmap_bf16(&tmW, whh_bf, 8 * S, S, S, 128);
   if (rc) return rc;
   ProfScope ps(F_REC_TC_FWD, st);
-  return rw_launch(rec_wide_fwd_kernel, RWF_SMEM, dim3(RW_NC, 2, (n_batch + RW_NT - 1) / RW_NT), RW_NC, st, tmW, p);
+  return rw_launch(rec_wide_fwd_kernel<false>, RWF_SMEM, dim3(RW_NC, 2, (n_batch + RW_NT - 1) / RW_NT), RW_NC, st, tmW, p);
+}
+
+// Exact (split-operand) forward recurrence at S = 512 on the 16-CTA clusters: xp [rows, 8S] fp32 pre-activations, whh_hi / whh_lo
+// [8S, S] bf16 parts of the packed W_hh; writes hout only.  Clusters are independent, the grid may run in waves.  -1: not covered.
+int rec_wide_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh_lo, float* hout, const int* lens, int S, int n_seq,
+                    int n_batch, long long rs_seq, long long rs_batch) {
+  static int cap = -1;
+  const int on = env_on("SSASR_REC_WIDE") && env_on("SSASR_REC_Q_X3");      // read per call: A/B switch of tests and scripts
+  if (!on || !rec_cl_is_enabled() || S != RW_S || n_batch < 1 || n_seq < 4) return -1;
+  if (cap < 0) cap = rw_query(rec_wide_fwd_kernel<true>, RWF_SMEM_X3, RW_NC);
+  const int tiles = (n_batch + RW_NT - 1) / RW_NT;
+  if (cap < 1 || (size_t)RW_NC * 2 * tiles * (2 * RW_HBLK) > (size_t)160 * RW_SLOT) return -1;   // packed slots of the exchange ring
+  RecWideP p = {};
+  p.xp = xp; p.hout = hout; p.lens = lens;
+  p.n_seq = n_seq; p.n_batch = n_batch; p.rs_seq = rs_seq; p.rs_batch = rs_batch;
+  p.ring = rw_ring_for(st);
+  p.w = (const __nv_bfloat16*)whh_hi;
+  SSASR_REQUIRE(p.ring != nullptr, "rec_wide_fwd_x3: cannot allocate the exchange ring");
+  CUtensorMap tmW;
+  int rc = make_tmap_bf16(&tmW, whh_lo, 8 * S, S, S, 128);
+  if (rc) return rc;
+  ProfScope ps(F_REC_TC_FWD, st);
+  return rw_launch(rec_wide_fwd_kernel<true>, RWF_SMEM_X3, dim3(RW_NC, 2, tiles), RW_NC, st, tmW, p);
 }
 
 // K-split backward: S = 512 (16-CTA clusters of 32 units) or S = 256 / 128 (clusters of S / 64 CTAs, 64 units each)

@@ -186,6 +186,8 @@ class _BLSTM(torch.autograd.Function):
                     tws = torch.empty(2 * (n_rows + 8 * S) * K, device=dev)
                 if S % 64 == 0 and S <= 256:
                     x3 = torch.empty(16 * S * S + 4 * n_rows * S, device=dev, dtype=torch.bfloat16)
+                elif S == 512:
+                    x3 = torch.empty(16 * S * S, device=dev, dtype=torch.bfloat16)      # 16-CTA cluster kernel: W_hh parts only
             check(lib.ssasr_blstm_fwd_f32(ptr(x), n_rows, K, ptr(wih_p), ptr(bias_p), ptr(whh_p), S, n_seq, n_batch, rs_seq,
                                           rs_batch, ptr(lens_dev) if time_major else None, ptr(xp), ptr(hout), ptr(cbuf),
                                           ptr(bar), ptr(tws), ptr(x3), st), 'ssasr_blstm_fwd_f32')

@@ -460,11 +460,12 @@ def test_decode_tf32x3_strings_and_gemm(golden_dir):
         assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
 
 
-@pytest.mark.parametrize('S,B,T', [(128, 37, 72), (256, 70, 136), (256, 3, 40)])
+@pytest.mark.parametrize('S,B,T', [(128, 37, 72), (256, 70, 136), (256, 3, 40), (512, 21, 72)])
 def test_exact_cluster_recurrence_matches_fp32_path(S, B, T):
     """Forward-only exact path of the decode Listener: the split-operand quad-cluster recurrence (`rec_q_fwd_kernel<R,false,true>`:
     W_hi in tensor memory, W_lo in shared memory, hi + lo h images exchanged inside the cluster) against the fp32 SIMT path
-    (itself pinned to the reference goldens) and against the counter-barrier X3 kernels it replaces: ragged lengths, partial
+    (itself pinned to the reference goldens) and against the counter-barrier X3 kernels it replaces (S = 512: the 16-CTA cluster
+    kernel `rec_wide_fwd_kernel<true>`, which replaces the SIMT recurrence there): ragged lengths, partial
     batch tiles, both tile heights, batched (seq-first `blstm_4` quirk, asr.py:262) and per-utterance `blstm_4`.
     Tolerance 5e-6 on |h| <= 1 (measured 4e-7 .. 9e-7, the same as the kernels it replaces)."""
     dims = (50, S, 32, 16, 24)
