@@ -570,6 +570,14 @@ def run_train(cx):
         sampler.start()            # started (and waited for) BEFORE the warm-up: it samples every 200 ms from here on
         sampler.wait_ready()
     warm = max(args.warmup, 3)
+    if world > 1:
+        # NCCL sets up its channels / buffers lazily over the first collectives of every size (measured at 2 GPUs with 3 warm-up steps:
+        # 9.8 ms per step inside the timed region against 7.5 ms for the same step a few iterations later): settle that before the W
+        # warm-up steps of the contract -- untimed, and the same code path as the timed steps
+        for _ in range(8):
+            step()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
     for _ in range(warm):
         step()
     first_sample = sampler.lines() if rank == 0 else 0

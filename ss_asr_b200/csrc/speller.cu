@@ -119,7 +119,7 @@ __device__ __forceinline__ float pick_lane(const float* v, int lane) {
 // Every phase is a batch of INDEPENDENT 128-bit loads issued before the first use (the per-utterance working set - phi 128 KB,
 // psi~ 32 KB, encoder states 128 KB at the default sizes - streams from L2, so the phases are latency-bound unless many loads
 // are in flight), followed by the arithmetic and a shuffle / shared-memory reduction.
-__global__ void __launch_bounds__(256) attn_fwd_kernel(AttnFwd a) {
+__global__ void __launch_bounds__(256, 3) attn_fwd_kernel(AttnFwd a) {
   extern __shared__ float sm[];
   float* hs = sm;                 // [Sd]
   float* qs = hs + a.Sd;          // [M]
