@@ -552,6 +552,24 @@ int ssasr_unpack_lstmcell_grads(const float* dwcat, const float* dbcat, int S, i
   return 0;
 }
 
+// A "sequence" of ONE step from the zero state (what bs=1 decoding makes of encoder.blstm_4, asr.py:262: every frame is its own
+// batch element): no recurrent product at all, h = o * tanh(i * g) per (row, direction, unit) straight from the pre-activations.
+// Forward-only (exact decode path): writes hout only.
+__global__ void blstm_single_step_kernel(const float* __restrict__ xp, float* __restrict__ hout, const int* __restrict__ lens, int S,
+                                         long long n_batch, long long rs_batch) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_batch * 2 * S) return;
+  const long long b = i / (2 * S);
+  const int c = (int)(i % (2 * S));                 // dir * S + unit
+  const long long row = b * rs_batch;
+  float h = 0.f;
+  if (!lens || lens[b] > 0) {
+    const float4 g = __ldcs(reinterpret_cast<const float4*>(xp + row * 8 * S) + c);     // col = dir*4S + unit*4
+    h = sigmoidf_acc(g.w) * tanhf(sigmoidf_acc(g.x) * tanhf(g.z));
+  }
+  hout[row * 2 * S + c] = h;
+}
+
 // One bidirectional LSTM layer, forward (fp32 path).
 //   x    [n_rows, K]   input rows; row index = seq*xs_seq + batch*xs_batch  (same indexing for xp/hout/cbuf)
 //   xp   [n_rows, 8S]  workspace; on return holds the gate activations (saved for backward)
@@ -589,6 +607,13 @@ int ssasr_blstm_fwd_f32(const float* x, int n_rows, int K, const float* wih_p, c
     rc = gemm_f32(st, n_rows, 8 * S, K, x, K, 1, wih_p, K, 1, xp, 8 * S, bias_p, 0, 0);
   }
   if (rc) return rc;
+  if (x3_ws && n_seq == 1) {
+    ProfScope ps(F_POINTWISE, st);
+    const long long n = (long long)n_batch * 2 * S;
+    blstm_single_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xp, hout, lens, S, n_batch, rs_batch);
+    SSASR_LAUNCH_CHECK();
+    return 0;
+  }
   if (x3_ws && S % 64 == 0 && S <= 256) {
     // recurrence on tensor cores with the bf16 hi/lo split of h and W_hh (fp32-accurate: 3 MMAs per K step)
     __nv_bfloat16* wh = (__nv_bfloat16*)x3_ws;

@@ -760,17 +760,13 @@ __global__ void __launch_bounds__(256) logits_pick_kernel(int B, int C, int Sd, 
   }
 }
 
-// greedy decoding: number of utterances whose selected tokens tok[b, 1 .. upto] do not contain `eos` yet
+// greedy decoding: number of utterances whose selected tokens tok[b, 1 .. upto] do not contain `eos` yet (a warp per utterance)
 __global__ void count_unfinished_kernel(int B, const int* __restrict__ tok, long long tok_ld, int upto, int eos, int* __restrict__ out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  bool open = false;
-  if (b < B) {
-    open = true;
-    for (int t = 1; t <= upto; ++t)
-      if (tok[(size_t)b * tok_ld + t] == eos) { open = false; break; }
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, open);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, __popc(m));
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  bool hit = false;
+  for (int t = 1 + lane; t <= upto; t += 32) hit = hit || (tok[(size_t)b * tok_ld + t] == eos);
+  if (__ballot_sync(0xffffffffu, hit) == 0u && lane == 0) atomicAdd(out, 1);
 }
 
 // next-token selection from logits row (C <= 1024): mode 1 = argmax (first max index, torch.argmax),
@@ -1324,7 +1320,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
       if (stop_every > 0 && t + 1 < U && (t + 1) % stop_every == 0) {
         SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, gside->ev[U + t], 0));
         SSASR_CHECK_CUDA(cudaMemsetAsync(a->stop_scratch, 0, sizeof(int), st));
-        count_unfinished_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, a->tok_in, U, t + 1, a->stop_token, a->stop_scratch);
+        count_unfinished_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, a->tok_in, U, t + 1, a->stop_token, a->stop_scratch);
         int open_utts = 1;
         SSASR_CHECK_CUDA(cudaMemcpyAsync(&open_utts, a->stop_scratch, sizeof(int), cudaMemcpyDeviceToHost, st));
         SSASR_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -1345,7 +1341,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
       if (stop_every > 0 && t + 1 < U && (t + 1) % stop_every == 0) {
         // tokens 1 .. t+1 have been selected: has every utterance emitted the stop token?
         SSASR_CHECK_CUDA(cudaMemsetAsync(a->stop_scratch, 0, sizeof(int), st));
-        count_unfinished_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, a->tok_in, U, t + 1, a->stop_token, a->stop_scratch);
+        count_unfinished_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, a->tok_in, U, t + 1, a->stop_token, a->stop_scratch);
         int open_utts = 1;
         SSASR_CHECK_CUDA(cudaMemcpyAsync(&open_utts, a->stop_scratch, sizeof(int), cudaMemcpyDeviceToHost, st));
         SSASR_CHECK_CUDA(cudaStreamSynchronize(st));
