@@ -17,6 +17,15 @@ __device__ __forceinline__ float tanh_apx(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_apx(float x) { return fmaf(tanh_apx(0.5f * x), 0.5f, 0.5f); }
+// exact-path activations of the cluster kernels: ex2.approx / rcp.approx based, ABSOLUTE error <= 1e-7 (sigmoid: s (1 - s) x the
+// 2^-22 + |x| 2^-24 relative error of the exponential; tanh: from exp(-2|x|) <= 1, no cancellation beyond one rounding) -- an order
+// of magnitude below the 2^-17 operand split of the products they follow, at a quarter of the instructions of expf / tanhf (the cell
+// math of 4 cells per thread was the longest phase of the exact recurrent step)
+__device__ __forceinline__ float sigmoid_x(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_x(float x) {
+  const float e = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
 
 // time-bounded mbarrier wait (a protocol bug must trap, not hang the GPU): ~2 s at 2 GHz
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {

@@ -929,7 +929,7 @@ rec_q_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
 // X3 (forward-only exact path: greedy decoding / validation): W_hh and h are split into bf16 hi + lo parts and the product is
 // W_hi h_hi + W_hi h_lo + W_lo h_hi (fp32-accurate: what rec_tc_fwd_kernel<.., X3> computes, at the cluster kernel's step
 // latency).  W_hi is the TMEM-resident A operand of the first two terms, W_lo lives in shared memory (SS form) in the SAME
-// permuted row order; a producer's image carries the hi and the lo k-block of its 64 units; precise expf / tanhf; only
+// permuted row order; a producer's image carries the hi and the lo k-block of its 64 units; ex2 / rcp based activations with 1e-7 absolute error (cl_common.cuh); only
 // `hout` is written (no activations / cell states: nothing runs backward through this path).
 template <int R, bool XF, bool X3 = false>
 __global__ void __launch_bounds__(Q_THREADS, 1)
@@ -1240,9 +1240,9 @@ rec_q_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         hv[m] = 0.f; cv[m] = 0.f;
         if (t < len[m]) {
           if (X3) {
-            a.x = sigmoidf_acc(g[m].x); a.y = sigmoidf_acc(g[m].y); a.z = tanhf(g[m].z); a.w = sigmoidf_acc(g[m].w);
+            a.x = sigmoid_x(g[m].x); a.y = sigmoid_x(g[m].y); a.z = tanh_x(g[m].z); a.w = sigmoid_x(g[m].w);
             cv[m] = a.y * creg[m] + a.x * a.z;
-            hv[m] = a.w * tanhf(cv[m]);
+            hv[m] = a.w * tanh_x(cv[m]);
           } else {
             a.x = sigmoid_apx(g[m].x); a.y = sigmoid_apx(g[m].y); a.z = tanh_apx(g[m].z); a.w = sigmoid_apx(g[m].w);
             cv[m] = fmaf(a.y, creg[m], a.x * a.z);

@@ -74,7 +74,7 @@ constexpr int RW_WCOL = 64;  // TMEM: accumulators in columns [0, 64), the resid
 // ------------------------------------------------------------------------------------------------
 // X3 (forward-only exact path, greedy decoding at S = 512): W_hh and h split into bf16 hi + lo parts, product
 // W_hi h_hi + W_hi h_lo + W_lo h_hi; W_hi is the TMEM-resident A operand, W_lo the shared-memory copy (tmW then maps the LOW
-// parts), a producer's image carries its hi and lo k-block; precise expf / tanhf; only `hout` is written.
+// parts), a producer's image carries its hi and lo k-block; ex2 / rcp based activations with 1e-7 absolute error (cl_common.cuh); only `hout` is written.
 template <bool X3>
 __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __grid_constant__ CUtensorMap tmW, RecWideP p) {
   constexpr int S = RW_S;
@@ -202,9 +202,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) rec_wide_fwd_kernel(const __gri
       float cv = 0.f, hv = 0.f;
       if (valid) {
         if (X3) {
-          a.x = sigmoidf_acc(g.x); a.y = sigmoidf_acc(g.y); a.z = tanhf(g.z); a.w = sigmoidf_acc(g.w);
+          a.x = sigmoid_x(g.x); a.y = sigmoid_x(g.y); a.z = tanh_x(g.z); a.w = sigmoid_x(g.w);
           cv = a.y * creg + a.x * a.z;
-          hv = a.w * tanhf(cv);
+          hv = a.w * tanh_x(cv);
         } else {
           a.x = sigmoid_apx(g.x); a.y = sigmoid_apx(g.y); a.z = tanh_apx(g.z); a.w = sigmoid_apx(g.w);
           cv = fmaf(a.y, creg, a.x * a.z);
