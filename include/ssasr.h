@@ -230,6 +230,8 @@ int ssasr_calc_acc_err(const float* predict /*[B,U,C] device*/, long long p_bstr
 /* ---- launch accounting and per-family CUDA-event timing (used by bench.py; no reference counterpart) ---- */
 int ssasr_num_families(void);
 const char* ssasr_family_name(int i);
+/* strided host -> device copy (cudaMemcpy2DAsync): `height` rows of `width` bytes; asynchronous for pinned host memory */
+int ssasr_memcpy2d_h2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height, void* stream);
 long long ssasr_launch_count(void);
 void ssasr_launch_count_reset(void);
 void ssasr_profile_enable(int enable);

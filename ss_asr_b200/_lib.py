@@ -83,6 +83,7 @@ SIGNATURES = {
     'ssasr_calc_acc_err': (_I, [_P, _LL, _LL, _I, _I, _I, _P, _LL, _I, _I, _I, _I, _P, _P, _P]),
     'ssasr_num_families': (_I, []),
     'ssasr_family_name': (C.c_char_p, [_I]),
+    'ssasr_memcpy2d_h2d': (_I, [_P, _LL, _P, _LL, _LL, _LL, _P]),
     'ssasr_launch_count': (_LL, []),
     'ssasr_launch_count_reset': (None, []),
     'ssasr_profile_enable': (None, [_I]),

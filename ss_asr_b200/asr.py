@@ -10,6 +10,8 @@ nn.Embedding) are used ONLY as parameter holders, which gives identical initiali
 import math
 import random
 
+import numpy as np
+
 import torch
 import torch.nn as nn
 
@@ -292,7 +294,8 @@ class ASR(nn.Module):
     @torch.no_grad()
     def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None, eos_id=1):
         """Greedy decoding of many utterances at once with the per-utterance (bs=1) semantics of ASR.decode:
-        xs [N,T,F] zero-padded, x_lens sorted in decreasing order; optional CharLM rescoring (asr.py:153-159).
+        xs [N,T,F] zero-padded (on the device, or a host tensor -- pinned for asynchronous, pipelined uploads), x_lens sorted in
+        decreasing order; optional CharLM rescoring (asr.py:153-159).
         `eos_id`: the token that ends an utterance (`mapper.char_to_ind(EOS_TKN)`, asr.py:167; 1 with the default Mapper).
         Returns a list of token-id lists."""
         prev = self.encoder.utterance_independent
@@ -304,17 +307,56 @@ class ASR(nn.Module):
         N = xs.shape[0]
         lens = _lens_list(x_lens)
         chunk = int(self.decode_encoder_chunk or 0)
+        fetch = None
+        if not xs.is_cuda:
+            # HOST batch (pinned for an asynchronous copy): every Listener group is uploaded on a copy stream, only as many frames
+            # deep as its longest utterance, the next group's copy running under the current group's encoder pass
+            dev = self.embed.weight.device
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            cs = self._copy_stream
+
+            def fetch(r0, r1, tmax):
+                cs.wait_stream(main)
+                with torch.cuda.stream(cs):
+                    src = xs[r0:r1, :tmax]
+                    if src.is_contiguous() or xs.dtype != torch.float32 or not xs.is_contiguous():
+                        t = src.to(dev, non_blocking=True)
+                    else:
+                        # rows of tmax frames out of the T-frame padded batch: one strided copy (torch would stage a
+                        # contiguous host temporary first)
+                        from . import _lib
+                        t = torch.empty(r1 - r0, tmax, xs.shape[2], device=dev)
+                        _lib.check(_lib.load().ssasr_memcpy2d_h2d(t.data_ptr(), tmax * xs.shape[2] * 4, src.data_ptr(),
+                                                                  xs.shape[1] * xs.shape[2] * 4, tmax * xs.shape[2] * 4, r1 - r0,
+                                                                  cs.cuda_stream), 'ssasr_memcpy2d_h2d')
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                t.record_stream(main)
+                return t, ev
         try:
             if chunk <= 0 or N <= chunk:
+                if fetch is not None:
+                    xs, ev = fetch(0, N, xs.shape[1])
+                    main.wait_event(ev)
                 enc, enc_len = self.encoder(xs, x_lens)
             else:
                 # utterances are independent and sorted by length: the Listener runs over groups of `chunk` utterances, each
                 # only as many frames deep as ITS longest utterance (the recurrent kernels are bound by dependent steps, so
                 # the padded tail of a short group is pure waste)
                 enc, enc_len = None, []
-                for r0 in range(0, N, chunk):
-                    r1 = min(N, r0 + chunk)
-                    e, el = self.encoder(xs[r0:r1, :lens[r0]], lens[r0:r1])
+                bounds = [(r0, min(N, r0 + chunk)) for r0 in range(0, N, chunk)]
+                nxt = fetch(bounds[0][0], bounds[0][1], lens[bounds[0][0]]) if fetch is not None else None
+                for i, (r0, r1) in enumerate(bounds):
+                    if fetch is not None:
+                        xg, ev = nxt
+                        if i + 1 < len(bounds):
+                            nxt = fetch(bounds[i + 1][0], bounds[i + 1][1], lens[bounds[i + 1][0]])
+                        main.wait_event(ev)
+                    else:
+                        xg = xs[r0:r1, :lens[r0]]
+                    e, el = self.encoder(xg, lens[r0:r1])
                     if enc is None:
                         enc = torch.zeros(N, e.shape[1], e.shape[2], dtype=e.dtype, device=e.device)
                     enc[r0:r1, :e.shape[1]] = e
@@ -330,16 +372,12 @@ class ASR(nn.Module):
         _, _, toks = self._spell(enc, enc_len, tok_in, [3 if lm is not None else 1] * (max_steps + 1), precision=prec, lm=lm,
                                  need_logits=False, stop_every=int(self.decode_stop_check or 0), stop_token=eos_id)
         self.last_decode_steps = Fk.LAST_SPELL['steps_run']
-        toks = toks[:, 1:].cpu().tolist()
-        out = []
-        for row in toks:
-            ids = []
-            for v in row[:max_steps]:
-                if v == eos_id:
-                    break
-                ids.append(v)
-            out.append(ids)
-        return out
+        # every utterance's tokens up to (not including) its first EOS: vectorised on the host (the per-token Python loop took
+        # 7 ms per 1000 utterances, a fifth of the whole call)
+        t = toks[:, 1:max_steps + 1].cpu().numpy()
+        is_eos = t == eos_id
+        n = np.where(is_eos.any(1), is_eos.argmax(1), t.shape[1])
+        return [t[i, :n[i]].tolist() for i in range(t.shape[0])]
 
     def decode(self, x, x_len, rnn_lm, mapper, lm_weight):
         """asr.py:112-173 (bs=1).  lm_weight == 0 runs entirely in the fused kernels."""

@@ -42,6 +42,15 @@ int ssasr_abi_version(void) { return SSASR_ABI_VERSION; }
 int ssasr_num_families(void) { return F_COUNT; }
 const char* ssasr_family_name(int i) { return (i >= 0 && i < F_COUNT) ? kFamilyNames[i] : ""; }
 
+// strided host -> device copy on `stream` (rows of `width` bytes out of pitched buffers; asynchronous when the host buffer is
+// pinned): the upload of a Listener group that is shallower than the padded host batch (ASR.decode_batch with a host tensor)
+int ssasr_memcpy2d_h2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height, void* stream) {
+  if (width <= 0 || height <= 0) return 0;
+  SSASR_CHECK_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, cudaMemcpyHostToDevice,
+                                     (cudaStream_t)stream));
+  return 0;
+}
+
 // total kernel launches issued by this library since the last reset
 long long ssasr_launch_count(void) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -814,6 +814,11 @@ def test_decode_batch_encoder_chunking_is_invisible():
             outs.append(m.decode_batch(xb.to(DEV), Ts, max_steps=12, precision=prec))
         assert outs[0] == outs[1] == outs[2] == outs[3], prec
         assert outs[0] == [list(w) for w in want], prec
+        # a HOST batch (pinned or pageable) goes through the pipelined per-group upload (strided copy of the group's frames)
+        for chunk in (0, 4):
+            m.decode_encoder_chunk = chunk
+            assert m.decode_batch(xb.pin_memory(), Ts, max_steps=12, precision=prec) == outs[0], (prec, chunk)
+        assert m.decode_batch(xb.clone(), Ts, max_steps=12, precision=prec) == outs[0], prec
 
 
 def test_greedy_loop_two_streams_is_invisible():
