@@ -428,6 +428,14 @@ def measure_decode(cx, steps=1, small=False, with_lm=True, with_cpu=True):
         model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5)
         ms_lm = cx.timed(lambda: model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5), 1)
         out['utt_per_s_lm05'] = n_total / (ms_lm / 1e3)
+    if with_lm and cx.rank == 0 and cx.world == 1:
+        # beam search (the reference's configured `decode_beam_size: 3`, conf/default.yaml:16, which its own
+        # ASRTester never uses): the first 128 utterances of the set, per-step kernels + csrc/beam.cu
+        nb = min(128, len(mine))
+        model.beam_decode_batch(xb[:nb], mine[:nb], 3, precision=best if best != 'fp32' else None)
+        ms_b = cx.timed(lambda: model.beam_decode_batch(xb[:nb], mine[:nb], 3, precision=best if best != 'fp32' else None), 1)
+        out['beam3'] = {'utterances': nb, 'ms': ms_b, 'utt_per_s': nb / (ms_b / 1e3), 'steps_run': int(model.last_decode_steps),
+                        'note': 'beam size 3, 200-step cap; no reference behaviour exists (trainer.py:590 decodes greedily)'}
     if with_cpu and cx.rank == 0 and cx.world == 1 and not cx.args.no_cpu:
         from oracle import cpu_arm
         xs, lens = c3_set(n_total)

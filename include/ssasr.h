@@ -230,6 +230,13 @@ int ssasr_calc_acc_err(const float* predict /*[B,U,C] device*/, long long p_bstr
 /* ---- launch accounting and per-family CUDA-event timing (used by bench.py; no reference counterpart) ---- */
 int ssasr_num_families(void);
 const char* ssasr_family_name(int i);
+/* ---- beam search bookkeeping (semantics: oracle/las_oracle.py decode_beam, = asr.py:143-172 at W = 1) ----
+   logits / lm_logits(or NULL) [N*W, C] (C <= 64), score_in / fin_in [N, W] -> the W best candidates per utterance:
+   score_out, fin_out, parent (hypothesis index 0..W-1 inside the utterance), token [N, W].  W <= 16. */
+int ssasr_beam_select(const float* logits, const float* lm_logits, float lm_weight, int N, int W, int C, int eos, const float* score_in,
+                      const int* fin_in, float* score_out, int* fin_out, int* parent, int* token, void* stream);
+/* dst row i = src row ((group ? (i / group) * group : 0) + idx[i]); rows of row_bytes (multiple of 4) */
+int ssasr_gather_rows(const void* src, void* dst, const int* idx, long long n_rows, long long row_bytes, int group, void* stream);
 /* strided host -> device copy (cudaMemcpy2DAsync): `height` rows of `width` bytes; asynchronous for pinned host memory */
 int ssasr_memcpy2d_h2d(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height, void* stream);
 long long ssasr_launch_count(void);

@@ -353,5 +353,59 @@ def decode_greedy(sd, x, x_len, lm=None, lm_weight=0.0, max_steps=MAX_DECODE, re
     return (out, margin) if return_margin else out
 
 
+def decode_beam(sd, x, x_len, beam_size, lm=None, lm_weight=0.0, max_steps=MAX_DECODE, return_score=False):
+    """Beam search over the step of ASR.decode (asr.py:143-172) for ONE utterance x [1,T,F].  NOT in the reference: it configures
+    a beam (conf/default.yaml:16-19, trainer.py:552-554) and then decodes greedily (trainer.py:590 TODO), so these semantics are
+    this repo's (stated here, implemented by ss_asr_b200.asr.ASR.beam_decode_batch + csrc/beam.cu) and are anchored on the
+    reference by the identity  decode_beam(beam_size=1) == decode_greedy  (same step, same `final` score, same EOS rule):
+      * score of a hypothesis = sum over its tokens (EOS included) of final = log_softmax(asr) [+ lm_weight * log_softmax(lm)];
+      * each step every live hypothesis is extended by all C tokens, a finished one (EOS emitted) stays ONE candidate with its
+        score; the `beam_size` best candidates survive, ties -> lower parent index, then lower token id;
+      * stops when every survivor is finished or after max_steps tokens; returns the tokens (EOS excluded) of the best survivor
+        (ties -> first)."""
+    assert x.dim() == 3 and x.shape[0] == 1
+    W = int(beam_size)
+    enc, enc_lens = listener(sd, x, x_len)
+    psi, mask = attention_memory(sd, enc, enc_lens)
+    Sd = sd['decoder.layer_1.weight_hh'].shape[1]
+    emb = sd['embed.weight']
+    C = sd['char_trans.weight'].shape[0]
+    z = enc.new_zeros(1, Sd)
+    H = lm['layer_1.weight_hh'].shape[1] if lm is not None else 1
+    g0 = enc.new_zeros(1, H)
+    # hypothesis: (score, finished, tokens, last_idx, speller state, lm state)
+    hyps = [(0.0, False, [], 0, ((z, z), (z, z)), (g0, g0))]
+    for _ in range(max_steps):
+        cands = []              # (score, parent, token, new state, new lm state)
+        for w, (score, fin, toks, last_idx, state, (g1, g2)) in enumerate(hyps):
+            if fin:
+                cands.append((score, w, EOS_ID, state, (g1, g2)))
+                continue
+            _, ctx = attention_step(sd, state[0][0], psi, mask, enc)
+            h2, nstate = speller_step(sd, torch.cat([emb[torch.tensor([last_idx])], ctx], -1), state)
+            final = torch.log_softmax(h2 @ sd['char_trans.weight'].t() + sd['char_trans.bias'], -1)
+            ng = (g1, g2)
+            if lm is not None:
+                lo, n1, n2 = charlm_step(lm, torch.tensor([last_idx]), g1, g2)
+                final = final + lm_weight * torch.log_softmax(lo, -1)
+                ng = (n1, n2)
+            sc = (torch.tensor(score, dtype=final.dtype) + final[0])
+            for c in range(C):
+                cands.append((float(sc[c]), w, c, nstate, ng))
+        cands.sort(key=lambda t: (-t[0], t[1], t[2]))
+        new = []
+        for score, w, c, nstate, ng in cands[:W]:
+            _, fin, toks, _, _, _ = hyps[w]
+            if fin:
+                new.append(hyps[w])
+            else:
+                new.append((score, c == EOS_ID, toks + ([] if c == EOS_ID else [c]), c, nstate, ng))
+        hyps = new
+        if all(h[1] for h in hyps):
+            break
+    best = max(range(len(hyps)), key=lambda i: (hyps[i][0], -i))
+    return (hyps[best][2], hyps[best][0]) if return_score else hyps[best][2]
+
+
 def ids_to_str(ids):
     return ''.join(TOKENS[i] for i in ids)

@@ -84,6 +84,8 @@ SIGNATURES = {
     'ssasr_num_families': (_I, []),
     'ssasr_family_name': (C.c_char_p, [_I]),
     'ssasr_memcpy2d_h2d': (_I, [_P, _LL, _P, _LL, _LL, _LL, _P]),
+    'ssasr_beam_select': (_I, [_P, _P, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'ssasr_gather_rows': (_I, [_P, _P, _P, _LL, _LL, _I, _P]),
     'ssasr_launch_count': (_LL, []),
     'ssasr_launch_count_reset': (None, []),
     'ssasr_profile_enable': (None, [_I]),

