@@ -425,8 +425,9 @@ def measure_decode(cx, steps=1, small=False, with_lm=True, with_cpu=True):
                        'ms_per_step_in_kernel': fam[dom][0], 'share_of_step': fam[dom][0] / ms}
     if with_lm and cx.rank == 0 and cx.world == 1:
         lm = _charlm(cx.dev)
-        model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5)
-        ms_lm = cx.timed(lambda: model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5), 1)
+        pl = best if best != 'fp32' else None
+        model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5, precision=pl)
+        ms_lm = cx.timed(lambda: model.decode_batch(xb, mine, rnn_lm=lm, lm_weight=0.5, precision=pl), 1)
         out['utt_per_s_lm05'] = n_total / (ms_lm / 1e3)
     if with_lm and cx.rank == 0 and cx.world == 1:
         # beam search (the reference's configured `decode_beam_size: 3`, conf/default.yaml:16, which its own

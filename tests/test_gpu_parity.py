@@ -328,9 +328,10 @@ def test_decode_default_margin_strings(golden_dir):
         assert O.ids_to_str(ids[j]) == str(z['margin_lm00'][i]), i
     lm = _CharLM()
     lm.load_state_dict(O.make_charlm_state_dict(50, 128, seed=7))
-    ids = m.decode_batch(xb.to(DEV), [Ts[i] for i in order], rnn_lm=lm, lm_weight=0.5)
-    for j, i in enumerate(order):
-        assert O.ids_to_str(ids[j]) == str(z['margin_lm05'][i]), i
+    for prec in ('fp32', 'tf32x3'):            # the CharLM-rescored loop on both exact paths (two-stream greedy loop, mode 3)
+        ids = m.decode_batch(xb.to(DEV), [Ts[i] for i in order], rnn_lm=lm, lm_weight=0.5, precision=prec)
+        for j, i in enumerate(order):
+            assert O.ids_to_str(ids[j]) == str(z['margin_lm05'][i]), (prec, i)
 
 
 def test_teacher_forcing_draws_follow_python_rng():
