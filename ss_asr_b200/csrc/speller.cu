@@ -808,6 +808,7 @@ struct LmStep {
   float weight;
   const float* logits; long long logits_ld;
   const int* tok_in; int* tok_out; long long tok_ld;
+  float* lm_out;                   // lm_step_kernel: [B,C] language-model logits of the step (lm_mix_pick_kernel reads them)
 };
 
 __device__ __forceinline__ float gru_unit(const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ wi,
@@ -879,6 +880,83 @@ __global__ void lm_pick_kernel(LmStep a) {
   }
 }
 
+// The same step in two kernels for the two-stream greedy loop: the CharLM recurrences of step t depend on token t only (not on
+// the attention / speller state), so they run on a THIRD stream under the attention step and the gate products of step t;
+// what is left on the layer-2 stream after the character projection is the mix + argmax.
+__global__ void lm_step_kernel(LmStep a) {
+  extern __shared__ float sm[];
+  float* x = sm;                 // [H]
+  float* h1 = x + a.H;           // [H]
+  float* h2 = h1 + a.H;          // [H]
+  float* h1n = h2 + a.H;         // [H]
+  float* h2n = h1n + a.H;        // [H]
+  const int b = blockIdx.x, tid = threadIdx.x, H = a.H, C = a.C;
+  const int tok = a.tok_in[(size_t)b * a.tok_ld];
+  for (int j = tid; j < H; j += blockDim.x) {
+    x[j] = a.emb[(size_t)tok * H + j];
+    h1[j] = a.h1[(size_t)b * H + j];
+    h2[j] = a.h2[(size_t)b * H + j];
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += blockDim.x) h1n[j] = gru_unit(x, h1, a.w1i, a.w1h, a.b1i, a.b1h, H, j);
+  __syncthreads();
+  for (int j = tid; j < H; j += blockDim.x) h2n[j] = gru_unit(h1n, h2, a.w2i, a.w2h, a.b2i, a.b2h, H, j);
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = a.bo[c];
+    for (int k = 0; k < H; ++k) s = fmaf(h2n[k], a.wo[(size_t)k * C + c], s);
+    a.lm_out[(size_t)b * C + c] = s;
+  }
+  for (int j = tid; j < H; j += blockDim.x) {
+    a.h1[(size_t)b * H + j] = h1n[j];
+    a.h2[(size_t)b * H + j] = h2n[j];
+  }
+}
+// final = log_softmax(asr) + weight * log_softmax(lm) (asr.py:153-156), argmax with torch's first-maximum rule; a warp per utterance
+__global__ void __launch_bounds__(256) lm_mix_pick_kernel(int B, int C, const float* __restrict__ logits, long long logits_ld,
+                                                          const float* __restrict__ lm, float weight, int* __restrict__ tok_out,
+                                                          long long tok_ld) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* lg = logits + (size_t)b * logits_ld;
+  const float* lr = lm + (size_t)b * C;
+  float ml = -INFINITY, ma = -INFINITY;
+  for (int c = lane; c < C; c += 32) { ml = fmaxf(ml, lr[c]); ma = fmaxf(ma, lg[c]); }
+  ml = warp_max(ml);
+  ma = warp_max(ma);
+  float sl = 0.f, sa = 0.f;
+  for (int c = lane; c < C; c += 32) { sl += expf(lr[c] - ml); sa += expf(lg[c] - ma); }
+  sl = warp_sum(sl);
+  sa = warp_sum(sa);
+  const float lse_l = ml + logf(sl), lse_a = ma + logf(sa);
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float f = (lg[c] - lse_a) + weight * (lr[c] - lse_l);
+    if (f > bv) { bv = f; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) tok_out[(size_t)b * tok_ld] = bi == 0x7fffffff ? 0 : bi;
+}
+// per-device scratch of the language-model logits of one step ([B, C] floats, grown on demand)
+static float* lm_out_buffer(size_t n_floats) {
+  static float* buf[32] = {nullptr};
+  static size_t cap[32] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  if (cap[dev] < n_floats) {
+    if (buf[dev]) { cudaDeviceSynchronize(); cudaFree(buf[dev]); buf[dev] = nullptr; cap[dev] = 0; }
+    if (cudaMalloc(&buf[dev], n_floats * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cap[dev] = n_floats;
+  }
+  return buf[dev];
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused cross-entropy (trainer.py:426-434): loss and dL/dlogits in one pass.  One CTA per utterance.
 // ------------------------------------------------------------------------------------------------
@@ -933,11 +1011,11 @@ struct SideStream {
   cudaEvent_t ev[512];
   int n_ev = 0;
 };
-static SideStream* side_stream(int n_events) {
-  static SideStream pool[32];
+static SideStream* side_stream(int n_events, int which = 0) {
+  static SideStream pool[2][32];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32 || n_events > 512) return nullptr;
-  SideStream* ss = &pool[dev];
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32 || n_events > 512 || which < 0 || which > 1) return nullptr;
+  SideStream* ss = &pool[which][dev];
   if (!ss->s) {
     // highest priority: its short kernels take the SMs that the long kernel of the main stream (attention over all utterances,
     // several waves of CTAs) frees, instead of queueing behind its undispatched CTAs
@@ -954,6 +1032,11 @@ static SideStream* side_stream(int n_events) {
 // 0 (SSASR_DECODE_DUAL=0): greedy decoding keeps every launch of a step on one stream
 static int decode_dual_on() {
   const char* e = getenv("SSASR_DECODE_DUAL");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+// 0 (SSASR_DECODE_LM_SPLIT=0): CharLM recurrences + mix + argmax as one kernel on the layer-2 stream
+static int lm_split_on() {
+  const char* e = getenv("SSASR_DECODE_LM_SPLIT");
   return (e && e[0] == '0') ? 0 : 1;
 }
 static int step_gemm_splits() {
@@ -1180,6 +1263,7 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
     }
     return 0;
   };
+  const float* lm_ext = nullptr;     // two-stream greedy loop with the CharLM: the step's LM logits computed on the third stream
   // selection of the token that follows step t (consumes h2(t)) on stream s2; no-op for teacher-forced steps
   auto select_token = [&](int t, cudaStream_t s2) -> int {
     int r = 0;
@@ -1194,7 +1278,11 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
       r = gemm_f32(s2, B, C, Sd, a->h2all + (size_t)t * Sd, U * Sd, 1, a->wc, Sd, 1, a->logits + (size_t)t * C, U * C, a->bc, 0, 0);
       if (r) return r;
     }
-    if (mode == 3) {
+    if (mode == 3 && lm_ext) {                // the recurrences of this step ran on the third stream: mix + argmax only
+      ProfScope ps(F_POINTWISE, s2);
+      lm_mix_pick_kernel<<<(B + 7) / 8, 256, 0, s2>>>(B, C, a->logits + (size_t)t * C, (long long)U * C, lm_ext, a->lm_weight,
+                                                      a->tok_in + t + 1, U);
+    } else if (mode == 3) {
       SSASR_REQUIRE(a->lm_emb && a->lm_h1 && a->lm_h2 && a->lm_H > 0, "speller: step mode 3 needs the language-model arguments");
       LmStep l;
       l.C = C; l.H = a->lm_H;
@@ -1300,14 +1388,46 @@ int ssasr_speller_fwd_f32(const ssasr_speller_fwd_args* a, void* stream) {
   if (gside) {
     cudaStream_t s2 = gside->s;
     int last_b = -1;
+    // CharLM rescoring: the LM recurrences of step t need token t only -> third stream, under the attention step / gate products
+    SideStream* lside = nullptr;
+    float* lm_buf = nullptr;
+    if (a->step_mode[0] == 3 && a->lm_emb && a->lm_h1 && a->lm_h2 && a->lm_H > 0 && U + 2 <= 512 && lm_split_on()) {
+      lm_buf = lm_out_buffer((size_t)B * C);
+      if (lm_buf) lside = side_stream(U + 2, 1);
+    }
+    if (lside) SSASR_HANDOVER(lside->ev[U], st, lside->s);       // everything enqueued so far (weights, LM state) is visible
     for (int t = 0; t < U; ++t) {
+      if (lside && t + 1 < U && mode_of(t) == 3) {
+        cudaStream_t s3 = lside->s;
+        if (t > 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(s3, gside->ev[U + t - 1], 0));    // token t (and the mix that read lm_buf)
+        LmStep l;
+        l.C = C; l.H = a->lm_H;
+        l.emb = a->lm_emb; l.w1i = a->lm_w1i; l.w1h = a->lm_w1h; l.b1i = a->lm_b1i; l.b1h = a->lm_b1h;
+        l.w2i = a->lm_w2i; l.w2h = a->lm_w2h; l.b2i = a->lm_b2i; l.b2h = a->lm_b2h; l.wo = a->lm_wo; l.bo = a->lm_bo;
+        l.h1 = a->lm_h1; l.h2 = a->lm_h2; l.weight = a->lm_weight;
+        l.logits = nullptr; l.logits_ld = 0;
+        l.tok_in = a->tok_in + t; l.tok_out = nullptr; l.tok_ld = U;
+        l.lm_out = lm_buf;
+        const int nt = ((a->lm_H + 31) / 32) * 32 > 256 ? 256 : ((a->lm_H + 31) / 32) * 32;
+        {
+          ProfScope ps(F_POINTWISE, s3);
+          lm_step_kernel<<<B, nt, (size_t)(5 * a->lm_H) * sizeof(float), s3>>>(l);
+        }
+        SSASR_CHECK_CUDA(cudaEventRecord(lside->ev[t], s3));
+      }
       attn_step(t, false, t > 0);
       if (t > 0) SSASR_CHECK_CUDA(cudaStreamWaitEvent(st, gside->ev[U + t - 1], 0));   // token t, its embedding row, h2(t-1)
       rc = gate_gemm(st, a->xin1 + (size_t)t * X1, U * X1, X1, a->w1cat, a->w1cat_bf, a->b1, a->act1 + (size_t)t * 4 * Sd, x1b, 1);
       if (rc) return rc;
       cell1(t, true);
       SSASR_HANDOVER(gside->ev[t], st, s2);
+      lm_ext = nullptr;
+      if (lside && t + 1 < U && mode_of(t) == 3) {
+        SSASR_CHECK_CUDA(cudaStreamWaitEvent(s2, lside->ev[t], 0));
+        lm_ext = lm_buf;
+      }
       rc = layer2(t, s2);
+      lm_ext = nullptr;
       if (rc) return rc;
       if (t + 1 < U) {
         ProfScope ps(F_POINTWISE, s2);

@@ -915,8 +915,22 @@ def test_greedy_loop_two_streams_is_invisible():
                 m.decode_stop_check = check
                 for _ in range(3):
                     assert m.decode_batch(xb.to(DEV), Ts, max_steps=25, precision=prec) == single, (prec, check)
+        # with the CharLM: its recurrences of step t run on a THIRD stream (they need token t only), the layer-2 stream mixes
+        # and selects; against one stream and against the fused LM kernel on the layer-2 stream
+        lm = _charlm_module(O.make_charlm_state_dict(50, 128, seed=7))
+        m.decode_stop_check = 16
+        for prec in ('fp32', 'tf32x3'):
+            os.environ['SSASR_DECODE_DUAL'] = '0'
+            single = m.decode_batch(xb.to(DEV), Ts, max_steps=25, rnn_lm=lm, lm_weight=0.5, precision=prec)
+            os.environ.pop('SSASR_DECODE_DUAL')
+            os.environ['SSASR_DECODE_LM_SPLIT'] = '0'
+            assert m.decode_batch(xb.to(DEV), Ts, max_steps=25, rnn_lm=lm, lm_weight=0.5, precision=prec) == single, prec
+            os.environ.pop('SSASR_DECODE_LM_SPLIT')
+            for _ in range(3):
+                assert m.decode_batch(xb.to(DEV), Ts, max_steps=25, rnn_lm=lm, lm_weight=0.5, precision=prec) == single, prec
     finally:
         os.environ.pop('SSASR_DECODE_DUAL', None)
+        os.environ.pop('SSASR_DECODE_LM_SPLIT', None)
         m.decode_stop_check = 16
 
 
