@@ -1,3 +1,4 @@
+"""A/B of the greedy loop schedule (SSASR_DECODE_DUAL) on NU utterances of the C3 recipe.  GPU only."""
 import os, sys, torch
 sys.path.insert(0, '/root/repo')
 from ss_asr_b200.asr import ASR
@@ -5,7 +6,8 @@ dev='cuda'
 torch.manual_seed(1)
 m = ASR(50, 256, 256, 128, 80, 0.9).to(dev).eval()
 g = torch.Generator().manual_seed(4321)
-Ts = sorted([int(v) for v in torch.randint(256, 513, (1000,), generator=g)], reverse=True)
+NU = int(os.environ.get('NU', '1000'))
+Ts = sorted([int(v) for v in torch.randint(256, 513, (NU,), generator=g)], reverse=True)
 xb = torch.zeros(len(Ts), Ts[0], 80)
 for i, t in enumerate(Ts):
     xb[i, :t] = torch.randn(t, 80, generator=g)
