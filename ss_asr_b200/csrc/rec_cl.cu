@@ -34,6 +34,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "cl_common.cuh"
@@ -1389,12 +1391,26 @@ struct RingSlot { cudaStream_t st; int dev; uint8_t* buf; };
 static RingSlot g_rings[16];
 static int g_nrings = 0;
 
+static std::mutex g_ring_mu;       // the pool is shared by every host thread that launches a cluster recurrence
 static uint8_t* ring_for(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ring_mu);
   int dev = 0;
   cudaGetDevice(&dev);
   for (int i = 0; i < g_nrings; ++i)
     if (g_rings[i].st == st && g_rings[i].dev == dev) return g_rings[i].buf;
-  if (g_nrings == 16) return nullptr;
+  if (g_nrings == 16) {
+    // pool full (17 distinct streams): hand the oldest entry of this device to the new stream once nothing can still be using it
+    for (int i = 0; i < g_nrings; ++i)
+      if (g_rings[i].dev == dev) {
+        if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        RingSlot r = g_rings[i];
+        for (int j = i; j + 1 < g_nrings; ++j) g_rings[j] = g_rings[j + 1];
+        r.st = st;
+        g_rings[g_nrings - 1] = r;
+        return r.buf;
+      }
+    return nullptr;
+  }
   uint8_t* b = nullptr;
   if (cudaMalloc(&b, RING_BYTES) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   g_rings[g_nrings++] = {st, dev, b};

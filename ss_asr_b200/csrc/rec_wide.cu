@@ -15,6 +15,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "cl_common.cuh"
@@ -508,12 +510,26 @@ long long* g_rw_dbg = nullptr;
 struct RwRing { cudaStream_t st; int dev; uint8_t* buf; };
 RwRing g_rw_rings[16];
 int g_rw_nrings = 0;
+std::mutex g_rw_ring_mu;
 uint8_t* rw_ring_for(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_rw_ring_mu);
   int dev = 0;
   cudaGetDevice(&dev);
   for (int i = 0; i < g_rw_nrings; ++i)
     if (g_rw_rings[i].st == st && g_rw_rings[i].dev == dev) return g_rw_rings[i].buf;
-  if (g_rw_nrings == 16) return nullptr;
+  if (g_rw_nrings == 16) {
+    // pool full: hand the oldest entry of this device to the new stream once nothing can still be using it
+    for (int i = 0; i < g_rw_nrings; ++i)
+      if (g_rw_rings[i].dev == dev) {
+        if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        RwRing r = g_rw_rings[i];
+        for (int j = i; j + 1 < g_rw_nrings; ++j) g_rw_rings[j] = g_rw_rings[j + 1];
+        r.st = st;
+        g_rw_rings[g_rw_nrings - 1] = r;
+        return r.buf;
+      }
+    return nullptr;
+  }
   uint8_t* b = nullptr;
   if (cudaMalloc(&b, (size_t)RW_RING * 160 * RW_SLOT) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   g_rw_rings[g_rw_nrings++] = {st, dev, b};

@@ -7,6 +7,7 @@
 // asr.py:103); attention maps are written straight into the stacked [B,U,T'] layout.
 #include "common.cuh"
 #include <stdlib.h>
+#include <mutex>
 #include <cuda_bf16.h>
 #include <curand_kernel.h>
 
@@ -947,6 +948,8 @@ __global__ void __launch_bounds__(256) lm_mix_pick_kernel(int B, int C, const fl
 static float* lm_out_buffer(size_t n_floats) {
   static float* buf[32] = {nullptr};
   static size_t cap[32] = {0};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
   if (cap[dev] < n_floats) {
@@ -1013,6 +1016,8 @@ struct SideStream {
 };
 static SideStream* side_stream(int n_events, int which = 0) {
   static SideStream pool[2][32];
+  static std::mutex mu;              // creation of the per-device streams / events from several host threads
+  std::lock_guard<std::mutex> lk(mu);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32 || n_events > 512 || which < 0 || which > 1) return nullptr;
   SideStream* ss = &pool[which][dev];

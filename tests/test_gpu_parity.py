@@ -1024,3 +1024,27 @@ def test_decode_batch_stops_when_every_utterance_has_emitted_eos():
             assert m.last_decode_steps % 4 == 0 and max(len(w) for w in want) < m.last_decode_steps <= max(len(w) for w in want) + 5
         if eos_bias == 50.0:
             assert all(len(w) == 0 for w in want) and m.last_decode_steps == 4
+
+
+def test_cluster_recurrence_on_many_streams():
+    """The exchange rings of the cluster recurrent kernels are pooled per (device, stream): more distinct streams than pool
+    entries (16) must keep working (the oldest entry is handed over) and give the same result as the default stream."""
+    dims = (50, 128, 32, 16, 24)
+    sd = O.make_state_dict(*dims, seed=2)
+    x, lens, _ = O.synth_batch(9, 40, 24, 4, seed=5)
+    m = _model(dims, sd).eval()
+    xd = x.to(DEV)
+    m.encoder.set_precision('tf32x3')
+    try:
+        with torch.no_grad():
+            ref, _ = m.encoder(xd, lens)
+            torch.cuda.synchronize()
+            for _ in range(20):
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    e, _ = m.encoder(xd, lens)
+                s.synchronize()
+                assert torch.equal(e, ref)
+    finally:
+        m.encoder.set_precision('fp32')
