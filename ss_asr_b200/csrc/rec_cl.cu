@@ -1565,7 +1565,9 @@ int rec_q_fwd_x3(cudaStream_t st, float* xp, const void* whh_hi, const void* whh
   p.dbg = g_cl_dbg;
   p.ring = ring_for(st);
   SSASR_REQUIRE(p.ring != nullptr, "rec_q_fwd_x3: cannot allocate the exchange ring");
-  const int R = (e && atoi(e) == 16) ? 16 : 32;
+  // 16-row tiles while all their clusters are co-resident (small batches are bound by the step latency: 125 utterances 14.3 -> 13.3 ms
+  // per decode), 32-row tiles beyond (the MMAs sit at the N <= 32 issue floor either way: twice the rows per step)
+  const int R = e ? (atoi(e) == 16 ? 16 : 32) : (2 * ((n_batch + 15) / 16) * (S / Q_UNITS) <= 148 ? 16 : 32);
   return R == 16 ? rec_q_fwd_x3_launch<16>(st, p) : rec_q_fwd_x3_launch<32>(st, p);
 }
 

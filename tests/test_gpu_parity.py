@@ -510,7 +510,7 @@ def test_exact_cluster_recurrence_matches_fp32_path(S, B, T):
         m.encoder.utterance_independent = indep
         ref = enc('fp32', None)
         old = enc('tf32x3', '0')
-        for env in (None, '16'):
+        for env in (None, '16', '32'):
             new = enc('tf32x3', env)
             assert not bool(torch.isnan(new).any())
             assert float((new - ref).abs().max()) < 5e-6, (indep, env)
