@@ -305,6 +305,8 @@ class ASR(nn.Module):
             # HOST batch (pinned for an asynchronous copy): every Listener group is uploaded on a copy stream, only as many frames
             # deep as its longest utterance, the next group's copy running under the current group's encoder pass
             dev = self.embed.weight.device
+            if dev.type != 'cuda':
+                raise RuntimeError('ss_asr_b200: the model must live on a CUDA device (there is no CPU fallback)')
             main = torch.cuda.current_stream(dev)
             if getattr(self, '_copy_stream', None) is None:
                 self._copy_stream = torch.cuda.Stream(dev)
